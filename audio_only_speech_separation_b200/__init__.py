@@ -1,0 +1,10 @@
+"""B200-native (sm_100a) implementation of the look2hear dual-path separation hot path.
+
+``models`` and ``losses`` mirror ``look2hear.models`` / ``look2hear.losses`` of the reference for the path
+(``TasNet`` with ``module="DPRNN"``, ``PITLossWrapper``, ``pairwise_neg_*``) so that the reference's
+``getattr(look2hear.models, name)`` / ``getattr(look2hear.losses, name)`` lookups resolve unchanged.
+All arithmetic runs in the hand-written CUDA library ``libdualpath_b200.so`` (C-ABI: ``include/dualpath_b200.h``).
+"""
+from . import _lib  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,668 @@
+// C-ABI (include/dualpath_b200.h) and the TasNet/DPRNN engine: host-side orchestration of the kernels.
+//
+// Data layout in HBM (all fp32, "channels-last"):
+//   waveform   xp [B, Tp]            zero padded (gc3_network.py:123-129)
+//   frames     E, En, Fb, F2, Z [B*L, 64], Mk [B*L, 128], Mx [B*spk*L, 64], D [B*spk*L, 16]
+//   stream     X_l [B, S, K, 64]     position p = (b*S + s)*K + k ; intra sequences walk k, inter sequences walk s,
+//                                    both read rows of 64 contiguous floats -> none of the reference's
+//                                    permute().contiguous() copies (dprnn.py:67,69,76,78) exist here
+//   per path   G [P,1024] gates, H [P,256], Cst [P,256], Y [P,64]
+// Forward of one path: in-proj GEMM -> persistent BiLSTM -> out-proj GEMM (+GroupNorm statistics in its epilogue)
+// -> fused normalise + residual (+ unfold affine/PReLU).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/dualpath_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace dp;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+int cuda_fail(cudaError_t e, const char* what) { return fail("%s: %s", what, cudaGetErrorString(e)); }
+
+#define CK(call)                                        \
+    do {                                                \
+        cudaError_t _e = (call);                        \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+    } while (0)
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline bool is_split(int precision) { return precision == DP_PREC_FP32; }
+
+// ---- packed LSTM buffer layout (bytes) ----
+constexpr size_t PK_WIH_HI = 0;
+constexpr size_t PK_WIH_LO = PK_WIH_HI + 65536 * 2;
+constexpr size_t PK_BIAS = PK_WIH_LO + 65536 * 2;
+constexpr size_t PK_WF_HI = PK_BIAS + 1024 * 4;
+constexpr size_t PK_WF_LO = PK_WF_HI + 2 * 8192 * 16;
+constexpr size_t PK_WB_HI = PK_WF_LO + 2 * 8192 * 16;
+constexpr size_t PK_WB_LO = PK_WB_HI + 2 * 8192 * 16;
+constexpr size_t PK_BYTES = PK_WB_LO + 2 * 8192 * 16;
+
+struct LstmPackView {
+    const __nv_bfloat16* wih_hi;
+    const __nv_bfloat16* wih_lo;
+    const float* bias;
+    LstmPack rec;
+};
+LstmPackView view_pack(const void* pack) {
+    const char* b = static_cast<const char*>(pack);
+    LstmPackView v;
+    v.wih_hi = reinterpret_cast<const __nv_bfloat16*>(b + PK_WIH_HI);
+    v.wih_lo = reinterpret_cast<const __nv_bfloat16*>(b + PK_WIH_LO);
+    v.bias = reinterpret_cast<const float*>(b + PK_BIAS);
+    v.rec.whh_f_hi = reinterpret_cast<const uint4*>(b + PK_WF_HI);
+    v.rec.whh_f_lo = reinterpret_cast<const uint4*>(b + PK_WF_LO);
+    v.rec.whh_b_hi = reinterpret_cast<const uint4*>(b + PK_WB_HI);
+    v.rec.whh_b_lo = reinterpret_cast<const uint4*>(b + PK_WB_LO);
+    return v;
+}
+LstmPackOut out_pack(void* pack) {
+    char* b = static_cast<char*>(pack);
+    LstmPackOut o;
+    o.wih_hi = reinterpret_cast<__nv_bfloat16*>(b + PK_WIH_HI);
+    o.wih_lo = reinterpret_cast<__nv_bfloat16*>(b + PK_WIH_LO);
+    o.bias = reinterpret_cast<float*>(b + PK_BIAS);
+    o.whh_f_hi = reinterpret_cast<uint4*>(b + PK_WF_HI);
+    o.whh_f_lo = reinterpret_cast<uint4*>(b + PK_WF_LO);
+    o.whh_b_hi = reinterpret_cast<uint4*>(b + PK_WB_HI);
+    o.whh_b_lo = reinterpret_cast<uint4*>(b + PK_WB_LO);
+    return o;
+}
+
+GemmNtArgs nt_args(const float* A, long long lda, const __nv_bfloat16* whi, const __nv_bfloat16* wlo, int ldw, int w_kn, float* C,
+                   int ldc, int M, int N, int K) {
+    GemmNtArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = A; a.lda = lda; a.Whi = whi; a.Wlo = wlo; a.ldw = ldw; a.w_kn = w_kn; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
+    a.bias_scale = 1.f;
+    return a;
+}
+GemmTnArgs tn_args(const float* A, int lda, const float* B, long long ldb, float* C, int ldc, int P, int Mo, int No) {
+    GemmTnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.P = P; a.Mo = Mo; a.No = No; a.scale = 1.f;
+    return a;
+}
+
+struct PitWsView {
+    double* sums;
+    double* second;
+    double* noise;
+    float* coef;
+};
+PitWsView pit_view(void* ws, int B) {
+    PitWsView v;
+    double* d = static_cast<double*>(ws);
+    v.sums = d; v.second = d + 4 * B; v.noise = d + 14 * B;
+    v.coef = reinterpret_cast<float*>(d + 18 * B);
+    return v;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int dp_version(void) { return 100; }
+const char* dp_last_error(void) { return g_err; }
+
+int dp_seg_geometry(int L, int K, int* rest, int* Sout) {
+    if (L <= 0 || K <= 0 || (K & 1)) return fail("dp_seg_geometry: need L > 0 and even K > 0 (got L=%d K=%d)", L, K);
+    int P = K / 2, r = K - (P + L % K) % K;
+    if (rest) *rest = r;
+    if (Sout) *Sout = 2 * ((L + r + P) / K);
+    return 0;
+}
+int dp_wave_geometry(int T, int win, int* rest, int* frames) {
+    if (T <= 0 || win <= 0 || (win & 1)) return fail("dp_wave_geometry: need T > 0 and even win > 0");
+    int st = win / 2, r = win - (st + T % win) % win;
+    if (rest) *rest = r;
+    if (frames) *frames = (T + r + 2 * st - win) / st + 1;
+    return 0;
+}
+
+int dp_segment_f32(const float* x, float* y, int B, int N, int L, int K, void* stream) {
+    if (B < 0 || N < 0) return fail("dp_segment_f32: negative size");
+    if (L <= 0 || K <= 0 || (K & 1)) return fail("dp_segment_f32: need L > 0 and even K > 0 (got L=%d K=%d)", L, K);
+    CK(launch_segment_nchw(x, y, B * N, L, K, S(stream)));
+    return 0;
+}
+int dp_overlap_add_f32(const float* y, float* x, int B, int N, int K, int Sc, int L, void* stream) {
+    int rest, S2;
+    if (dp_seg_geometry(L, K, &rest, &S2)) return 1;
+    if (S2 != Sc) return fail("dp_overlap_add_f32: S=%d does not match L=%d K=%d (expected %d)", Sc, L, K, S2);
+    CK(launch_overlap_add_nchw(y, x, B * N, K, Sc, L, S(stream)));
+    return 0;
+}
+int dp_segment_cl_f32(const float* f, float* x, int B, int L, int K, int C, void* stream) {
+    int rest, S2;
+    if (dp_seg_geometry(L, K, &rest, &S2)) return 1;
+    CK(launch_segment_cl(f, x, B, L, K, S2, C, S(stream)));
+    return 0;
+}
+int dp_overlap_add_cl_f32(const float* x, float* f, int B, int L, int K, int C, void* stream) {
+    int rest, S2;
+    if (dp_seg_geometry(L, K, &rest, &S2)) return 1;
+    CK(launch_overlap_add_cl(x, f, B, L, K, S2, C, S(stream)));
+    return 0;
+}
+
+int dp_linear_f32(const float* A, int64_t lda, const void* w_hi, const void* w_lo, int ldw, int w_kn, const float* bias, float bias_scale,
+                  float* C, int ldc, int M, int N, int K, int relu, int accumulate, double* stats, int rows_per_group, int precision,
+                  void* stream) {
+    GemmNtArgs a = nt_args(A, lda, (const __nv_bfloat16*)w_hi, (const __nv_bfloat16*)w_lo, ldw, w_kn, C, ldc, M, N, K);
+    a.bias = bias; a.bias_scale = bias_scale; a.relu = relu; a.accumulate = accumulate; a.stats = stats;
+    a.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+    CK(launch_gemm_nt(a, is_split(precision), S(stream)));
+    return 0;
+}
+int dp_linear_wgrad_f32(const float* A, int lda, const float* B, int64_t ldb, float* dW, int ldc, int P, int Mo, int No, float scale,
+                        int precision, void* stream) {
+    GemmTnArgs a = tn_args(A, lda, B, ldb, dW, ldc, P, Mo, No);
+    a.scale = scale;
+    CK(launch_gemm_tn(a, is_split(precision), S(stream)));
+    return 0;
+}
+int dp_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* stream) {
+    CK(launch_split_bf16(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n, S(stream)));
+    return 0;
+}
+
+int64_t dp_lstm_pack_bytes(void) { return (int64_t)PK_BYTES; }
+int dp_lstm_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* w_ih_r, const float* w_hh_r,
+                 const float* b_ih_r, const float* b_hh_r, void* pack, void* stream) {
+    const float* wi[2] = {w_ih, w_ih_r};
+    const float* wh[2] = {w_hh, w_hh_r};
+    const float* bi[2] = {b_ih, b_ih_r};
+    const float* bh[2] = {b_hh, b_hh_r};
+    CK(launch_pack_lstm(wi, wh, bi, bh, out_pack(pack), S(stream)));
+    return 0;
+}
+
+int dp_bilstm_forward_f32(const void* pack, const float* x, float* G, float* H, float* Cst, int64_t P, int nseq, int len, int qdiv,
+                          int64_t s_hi, int64_t s_lo, int64_t s_t, int save, int precision, void* stream) {
+    if (P > 0x7fffffffLL / 1024) return fail("dp_bilstm_forward_f32: too many positions");
+    LstmPackView v = view_pack(pack);
+    GemmNtArgs a = nt_args(x, kN, v.wih_hi, v.wih_lo, kN, 0, G, 2 * kG, (int)P, 2 * kG, kN);
+    a.bias = v.bias;
+    CK(launch_gemm_nt(a, is_split(precision), S(stream)));
+    SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
+    CK(launch_lstm_fwd(v.rec, G, H, Cst, m, is_split(precision), save != 0, S(stream)));
+    return 0;
+}
+int dp_lstm_recurrence_f32(const void* pack, float* G, float* H, float* Cst, int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo,
+                           int64_t s_t, int save, int precision, void* stream) {
+    LstmPackView v = view_pack(pack);
+    SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
+    CK(launch_lstm_fwd(v.rec, G, H, Cst, m, is_split(precision), save != 0, S(stream)));
+    return 0;
+}
+int dp_bilstm_backward_f32(const void* pack, float* G, const float* Cst, const float* dH, float* dx, int accumulate_dx, int64_t P,
+                           int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int precision, void* stream) {
+    LstmPackView v = view_pack(pack);
+    SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
+    CK(launch_lstm_bwd(v.rec, G, Cst, dH, m, is_split(precision), S(stream)));
+    if (dx) {
+        GemmNtArgs a = nt_args(G, 2 * kG, v.wih_hi, v.wih_lo, kN, 1, dx, kN, (int)P, kN, 2 * kG);
+        a.accumulate = accumulate_dx;
+        CK(launch_gemm_nt(a, is_split(precision), S(stream)));
+    }
+    return 0;
+}
+
+int dp_groupnorm_finalize(const double* stats, float* mean_rstd, int groups, double count, double eps, void* stream) {
+    CK(launch_gn_finalize(stats, mean_rstd, groups, count, eps, S(stream)));
+    return 0;
+}
+int dp_groupnorm_residual_f32(const float* y, const float* res, float* out, const float* mean_rstd, const float* gamma, const float* beta,
+                              int64_t rows, int rows_per_group, int C, const float* cw, const float* cb, const float* prelu_slope,
+                              void* stream) {
+    CK(launch_gn_apply(y, res, out, mean_rstd, gamma, beta, rows, rows_per_group, C, cw, cb, prelu_slope, S(stream)));
+    return 0;
+}
+
+int64_t dp_pit_loss_workspace_bytes(int B) { return (int64_t)B * (18 * 8 + 6 * 4) + 64; }
+int dp_pit_loss_forward(const float* est, const float* tgt, int B, int T, int sdr_type, int threshold_byloss, void* ws, float* pw,
+                        float* loss, int32_t* perm, void* stream) {
+    if (sdr_type < 0 || sdr_type > 2) return fail("dp_pit_loss_forward: sdr_type must be 0 (snr), 1 (sisdr) or 2 (sdsdr)");
+    PitWsView v = pit_view(ws, B);
+    PitLossWs w{v.sums, v.second, v.noise};
+    CK(launch_pit_loss_fwd(est, tgt, B, T, sdr_type, threshold_byloss, w, pw, loss, perm, v.coef, S(stream)));
+    return 0;
+}
+int dp_pit_loss_backward(const float* est, const float* tgt, int B, int T, const void* ws, float grad_scale, float* d_est, void* stream) {
+    PitWsView v = pit_view(const_cast<void*>(ws), B);
+    CK(launch_pit_loss_bwd(est, tgt, B, T, v.sums, v.coef, grad_scale, d_est, S(stream)));
+    return 0;
+}
+int dp_pit_reorder(const float* est, const int32_t* perm, float* out, int B, int T, void* stream) {
+    CK(launch_reorder_sources(est, perm, out, B, T, S(stream)));
+    return 0;
+}
+
+int dp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, double* norm2, float grad_scale, float max_norm, float lr,
+                      float beta1, float beta2, float eps, int step, float weight_decay, void* stream) {
+    if (step < 1) return fail("dp_adam_clip_step: step counts from 1");
+    CK(cudaMemsetAsync(norm2, 0, sizeof(double), S(stream)));
+    if (max_norm > 0.f) CK(launch_sumsq(g, n, norm2, S(stream)));
+    double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    CK(launch_adam_clip(p, g, m, v, n, norm2, grad_scale, max_norm, lr, beta1, beta2, eps, (float)bc1, (float)bc2, weight_decay, S(stream)));
+    return 0;
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// TasNet / DPRNN engine
+// ================================================================================================
+struct dp_tasnet {
+    dp_tasnet_config cfg;
+    std::vector<int64_t> off;
+    int64_t n_params;
+    int npath;
+    int launches;
+};
+
+namespace {
+
+struct Geo {
+    int B, T, rest_w, Tp, L, rest_s, Sc, K, P;  // P = Sc*K positions per utterance
+    long long PT, BL;
+};
+int make_geo(const dp_tasnet* h, int B, int T, Geo& g) {
+    if (B <= 0 || T <= 0) return fail("need B > 0 and T > 0 (got B=%d T=%d)", B, T);
+    g.B = B; g.T = T; g.K = h->cfg.block_size;
+    if (dp_wave_geometry(T, h->cfg.win, &g.rest_w, &g.L)) return 1;
+    g.Tp = T + g.rest_w + h->cfg.win;
+    if (dp_seg_geometry(g.L, g.K, &g.rest_s, &g.Sc)) return 1;
+    g.P = g.Sc * g.K;
+    g.PT = (long long)B * g.P;
+    g.BL = (long long)B * g.L;
+    if (g.PT * 1024 > 0x7fffffffffLL || g.PT > 0x7fffffffLL / 4) return fail("batch too large for 32-bit position indexing");
+    return 0;
+}
+
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    }
+};
+
+struct Layout {
+    size_t xp, E, En, Fb, F2, Z, Mk, Mx, D;
+    size_t small, small_bytes;  // GroupNorm statistics (zeroed by every forward)
+    size_t redz, redz_bytes;    // GroupNorm-backward reductions (zeroed by every backward)
+    size_t statsE, mrE, redE;
+    std::vector<size_t> X, G, H, Cst, Y, stats, mr, red, dpack;
+    // backward temporaries
+    size_t dXs, dY, dH, dpad, dMx, dMk, dE, dZ, dF2, dtmp;
+    size_t total;
+};
+
+void make_layout(const dp_tasnet* h, const Geo& g, bool train, Layout& l) {
+    Carver c;
+    const int np = h->npath, nspk = h->cfg.num_spk;
+    const size_t f = sizeof(float);
+    l.xp = c.take((size_t)g.B * g.Tp * f);
+    l.E = c.take(g.BL * 64 * f);
+    l.En = c.take(g.BL * 64 * f);
+    l.Fb = c.take(g.BL * 64 * f);
+    l.F2 = c.take(g.BL * 64 * f);
+    l.Z = c.take(g.BL * 64 * f);
+    l.Mk = c.take(g.BL * 64 * nspk * f);
+    l.Mx = c.take(g.BL * 64 * nspk * f);
+    l.D = c.take(g.BL * nspk * h->cfg.win * f);
+    // small region
+    size_t s0 = c.off;
+    l.statsE = c.take(2 * g.B * sizeof(double));
+    l.stats.resize(np); l.mr.resize(np); l.red.resize(np);
+    for (int p = 0; p < np; ++p) l.stats[p] = c.take(2 * g.B * sizeof(double));
+    l.small = s0;
+    l.small_bytes = c.off - s0;
+    l.mrE = c.take(2 * g.B * f);
+    for (int p = 0; p < np; ++p) l.mr[p] = c.take(2 * g.B * f);
+    s0 = c.off;
+    l.redE = c.take(2 * g.B * sizeof(double));
+    for (int p = 0; p < np; ++p) l.red[p] = c.take(2 * g.B * sizeof(double));
+    l.redz = s0;
+    l.redz_bytes = c.off - s0;
+    const int nbuf = train ? np : 1;
+    l.X.resize(np + 1); l.G.resize(np); l.H.resize(np); l.Cst.resize(np); l.Y.resize(np); l.dpack.resize(np);
+    if (train) {
+        for (int p = 0; p <= np; ++p) l.X[p] = c.take(g.PT * 64 * f);
+    } else {
+        size_t x = c.take(g.PT * 64 * f);
+        for (int p = 0; p <= np; ++p) l.X[p] = x;  // residual update happens in place
+    }
+    for (int p = 0; p < nbuf; ++p) {
+        l.G[p] = c.take(g.PT * 1024 * f);
+        l.H[p] = c.take(g.PT * 256 * f);
+        l.Cst[p] = train ? c.take(g.PT * 256 * f) : 0;
+        l.Y[p] = c.take(g.PT * 64 * f);
+    }
+    for (int p = nbuf; p < np; ++p) { l.G[p] = l.G[0]; l.H[p] = l.H[0]; l.Cst[p] = l.Cst[0]; l.Y[p] = l.Y[0]; }
+    if (train) {
+        for (int p = 0; p < np; ++p) l.dpack[p] = c.take((65536 + 131072 + 1024) * f);
+        l.dpad = c.take((size_t)g.B * nspk * g.Tp * f);
+        l.dXs = c.take(g.PT * 64 * f);
+        l.dY = c.take(g.PT * 64 * f);
+        l.dH = c.take(g.PT * 256 * f);
+        l.dMx = c.take(g.BL * 64 * nspk * f);
+        l.dMk = c.take(g.BL * 64 * nspk * f);
+        l.dE = c.take(g.BL * 64 * f);
+        l.dZ = c.take(g.BL * 64 * f);
+        l.dF2 = c.take(g.BL * 64 * f);
+        l.dtmp = c.take(g.BL * 64 * f);
+    }
+    l.total = c.off;
+}
+
+template <typename T>
+T* at(void* base, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(base) + off); }
+
+SeqMap path_map(const Geo& g, int pp) {
+    SeqMap m;
+    if ((pp & 1) == 0) {  // intra-chunk (row): sequence (b,s), time k
+        m.nseq = g.B * g.Sc; m.len = g.K; m.qdiv = 1 << 30; m.s_hi = 0; m.s_lo = g.K; m.s_t = 1;
+    } else {              // inter-chunk (col): sequence (b,k), time s
+        m.nseq = g.B * g.K; m.len = g.Sc; m.qdiv = g.K; m.s_hi = (long long)g.Sc * g.K; m.s_lo = 1; m.s_t = g.K;
+    }
+    return m;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dp_tasnet_create(const dp_tasnet_config* cfg, const int64_t* offsets, int n_offsets, int64_t n_params, dp_tasnet** out) {
+    if (!cfg || !offsets || !out) return fail("dp_tasnet_create: null argument");
+    if (cfg->enc_dim != kN || cfg->bn_dim != kN || cfg->hidden_dim != kH)
+        return fail("dp_tasnet_create: this build is specialised for enc_dim = bn_dim = %d, hidden_dim = %d (got %d/%d/%d)", kN, kH,
+                    cfg->enc_dim, cfg->bn_dim, cfg->hidden_dim);
+    if (cfg->win != 16) return fail("dp_tasnet_create: win must be 16 (got %d)", cfg->win);
+    if (cfg->num_spk < 1 || cfg->num_spk > 4) return fail("dp_tasnet_create: num_spk must be in 1..4");
+    if (cfg->block_size <= 0 || (cfg->block_size & 1)) return fail("dp_tasnet_create: block_size must be even and positive");
+    if (cfg->layer < 1) return fail("dp_tasnet_create: layer must be >= 1");
+    int need = DP_TASNET_HEAD_PARAMS + DP_TASNET_PATH_PARAMS * 2 * cfg->layer;
+    if (n_offsets != need) return fail("dp_tasnet_create: expected %d parameter offsets, got %d", need, n_offsets);
+    for (int i = 0; i < n_offsets; ++i) {
+        bool optional = (i >= 9 && i <= 11) && !cfg->unfold;
+        if (!optional && (offsets[i] < 0 || offsets[i] >= n_params)) return fail("dp_tasnet_create: offset %d out of range", i);
+        if (!optional && (offsets[i] & 3)) return fail("dp_tasnet_create: parameter %d is not 16-byte aligned in the flat buffer", i);
+    }
+    dp_tasnet* h = new (std::nothrow) dp_tasnet();
+    if (!h) return fail("dp_tasnet_create: out of host memory");
+    h->cfg = *cfg;
+    h->off.assign(offsets, offsets + n_offsets);
+    h->n_params = n_params;
+    h->npath = 2 * cfg->layer;
+    h->launches = 0;
+    *out = h;
+    return 0;
+}
+void dp_tasnet_destroy(dp_tasnet* h) { delete h; }
+
+int64_t dp_tasnet_pack_bytes(const dp_tasnet* h) {
+    size_t flat = ((size_t)h->n_params * 2 + 255) & ~(size_t)255;
+    return (int64_t)(2 * flat + (size_t)h->npath * PK_BYTES);
+}
+int64_t dp_tasnet_workspace_bytes(const dp_tasnet* h, int B, int T, int train) {
+    Geo g;
+    if (make_geo(h, B, T, g)) return -1;
+    Layout l;
+    make_layout(h, g, train != 0, l);
+    return (int64_t)l.total;
+}
+int dp_tasnet_last_launches(const dp_tasnet* h) { return h->launches; }
+
+int dp_tasnet_pack(dp_tasnet* h, const float* params, void* pack, void* stream) {
+    size_t flat = ((size_t)h->n_params * 2 + 255) & ~(size_t)255;
+    char* b = static_cast<char*>(pack);
+    CK(launch_split_bf16(params, (__nv_bfloat16*)b, (__nv_bfloat16*)(b + flat), h->n_params, S(stream)));
+    for (int pp = 0; pp < h->npath; ++pp) {
+        const int64_t* o = h->off.data() + DP_TASNET_HEAD_PARAMS + DP_TASNET_PATH_PARAMS * pp;
+        const float* wi[2] = {params + o[0], params + o[4]};
+        const float* wh[2] = {params + o[1], params + o[5]};
+        const float* bi[2] = {params + o[2], params + o[6]};
+        const float* bh[2] = {params + o[3], params + o[7]};
+        CK(launch_pack_lstm(wi, wh, bi, bh, out_pack(b + 2 * flat + (size_t)pp * PK_BYTES), S(stream)));
+    }
+    return 0;
+}
+
+int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const float* mixture, float* est, void* ws, int B, int T,
+                      int train, int precision, void* stream) {
+    Geo g;
+    if (make_geo(h, B, T, g)) return 1;
+    Layout l;
+    make_layout(h, g, train != 0, l);
+    cudaStream_t st = S(stream);
+    const bool sp = is_split(precision);
+    const int nspk = h->cfg.num_spk, win = h->cfg.win, stride = win / 2;
+    const int64_t* o = h->off.data();
+    const size_t flat = ((size_t)h->n_params * 2 + 255) & ~(size_t)255;
+    const __nv_bfloat16* whi = reinterpret_cast<const __nv_bfloat16*>(pack);
+    const __nv_bfloat16* wlo = reinterpret_cast<const __nv_bfloat16*>(static_cast<const char*>(pack) + flat);
+    const char* lpack = static_cast<const char*>(pack) + 2 * flat;
+    int nl = 0;
+
+    CK(cudaMemsetAsync(at<char>(ws, l.small), 0, l.small_bytes, st));
+    // pad + encoder (Conv1d 1->64, k16, s8, no bias) as a GEMM over overlapping frames          gc3_network.py:123-140
+    float* xp = at<float>(ws, l.xp);
+    CK(launch_pad_rows(mixture, xp, B, T, g.Tp, stride, st)); ++nl;
+    {
+        GemmNtArgs a = nt_args(xp, stride, whi + o[0], wlo + o[0], win, 0, at<float>(ws, l.E), 64, (int)g.BL, 64, win);
+        a.a_rpb = g.L; a.a_skip = 1;
+        a.stats = at<double>(ws, l.statsE); a.rows_per_group = g.L;
+        CK(launch_gemm_nt(a, sp, st)); ++nl;
+    }
+    // bottleneck: GroupNorm(1,64,eps=2^-23) + 1x1 conv                                            gc3_network.py:53-56,142
+    CK(launch_gn_finalize(at<double>(ws, l.statsE), at<float>(ws, l.mrE), B, (double)g.L * 64, 1.1920928955078125e-07, st)); ++nl;
+    CK(launch_gn_apply(at<float>(ws, l.E), nullptr, at<float>(ws, l.En), at<float>(ws, l.mrE), params + o[1], params + o[2], g.BL, g.L, 64,
+                       nullptr, nullptr, nullptr, st)); ++nl;
+    {
+        GemmNtArgs a = nt_args(at<float>(ws, l.En), 64, whi + o[3], wlo + o[3], 64, 0, at<float>(ws, l.Fb), 64, (int)g.BL, 64, 64);
+        CK(launch_gemm_nt(a, sp, st)); ++nl;
+    }
+    // segmentation into 50%-overlapping chunks, channels-last                                     gc3_basics.py:79-91
+    CK(launch_segment_cl(at<float>(ws, l.Fb), at<float>(ws, l.X[0]), B, g.L, g.K, g.Sc, 64, st)); ++nl;
+
+    for (int pp = 0; pp < h->npath; ++pp) {                                                     // dprnn.py:62-82
+        const int64_t* po = o + DP_TASNET_HEAD_PARAMS + DP_TASNET_PATH_PARAMS * pp;
+        LstmPackView v = view_pack(lpack + (size_t)pp * PK_BYTES);
+        float* X = at<float>(ws, l.X[pp]);
+        float* G = at<float>(ws, l.G[pp]);
+        float* H = at<float>(ws, l.H[pp]);
+        float* Y = at<float>(ws, l.Y[pp]);
+        {
+            GemmNtArgs a = nt_args(X, 64, v.wih_hi, v.wih_lo, 64, 0, G, 1024, (int)g.PT, 1024, 64);
+            a.bias = v.bias;
+            CK(launch_gemm_nt(a, sp, st)); ++nl;
+        }
+        CK(launch_lstm_fwd(v.rec, G, H, train ? at<float>(ws, l.Cst[pp]) : nullptr, path_map(g, pp), sp, train != 0, st)); ++nl;
+        {
+            GemmNtArgs a = nt_args(H, 256, whi + po[8], wlo + po[8], 256, 0, Y, 64, (int)g.PT, 64, 256);
+            a.bias = params + po[9];
+            a.stats = at<double>(ws, l.stats[pp]); a.rows_per_group = g.P;
+            CK(launch_gemm_nt(a, sp, st)); ++nl;
+        }
+        CK(launch_gn_finalize(at<double>(ws, l.stats[pp]), at<float>(ws, l.mr[pp]), B, (double)g.P * 64, 1e-8, st)); ++nl;
+        const bool cat = h->cfg.unfold && (pp & 1);
+        CK(launch_gn_apply(Y, X, at<float>(ws, l.X[pp + 1]), at<float>(ws, l.mr[pp]), params + po[10], params + po[11], g.PT, g.P, 64,
+                           cat ? params + o[9] : nullptr, cat ? params + o[10] : nullptr, cat ? params + o[11] : nullptr, st)); ++nl;
+    }
+    // overlap-add, then the DPRNN output 1x1 conv (linear => conv(a)+conv(b) = W(a+b) + 2 bias)    dprnn.py:85, gc3_basics.py:94-109
+    CK(launch_overlap_add_cl(at<float>(ws, l.X[h->npath]), at<float>(ws, l.F2), B, g.L, g.K, g.Sc, 64, st)); ++nl;
+    {
+        GemmNtArgs a = nt_args(at<float>(ws, l.F2), 64, whi + o[4], wlo + o[4], 64, 0, at<float>(ws, l.Z), 64, (int)g.BL, 64, 64);
+        a.bias = params + o[5]; a.bias_scale = 2.f;
+        CK(launch_gemm_nt(a, sp, st)); ++nl;
+    }
+    // mask = ReLU(Conv1d 64 -> 64*spk), applied to the raw encoder output                         gc3_network.py:169-174
+    {
+        GemmNtArgs a = nt_args(at<float>(ws, l.Z), 64, whi + o[6], wlo + o[6], 64, 0, at<float>(ws, l.Mk), 64 * nspk, (int)g.BL, 64 * nspk, 64);
+        a.bias = params + o[7]; a.relu = 1;
+        CK(launch_gemm_nt(a, sp, st)); ++nl;
+    }
+    CK(launch_mask_apply(at<float>(ws, l.Mk), at<float>(ws, l.E), at<float>(ws, l.Mx), B, g.L, nspk, 64, st)); ++nl;
+    // decoder ConvTranspose1d(64 -> 1, k16, s8): per-frame 64 -> 16 product, stride-8 overlap-add, trim   gc3_network.py:177-179
+    {
+        GemmNtArgs a = nt_args(at<float>(ws, l.Mx), 64, whi + o[8], wlo + o[8], win, 1, at<float>(ws, l.D), win, (int)(g.BL * nspk), win, 64);
+        CK(launch_gemm_nt(a, sp, st)); ++nl;
+    }
+    CK(launch_dec_ola(at<float>(ws, l.D), est, B * nspk, g.L, win, T, st)); ++nl;
+    h->launches = nl;
+    return 0;
+}
+
+int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, const float* d_est, float* grads, void* ws, int B, int T,
+                       int precision, void* stream) {
+    Geo g;
+    if (make_geo(h, B, T, g)) return 1;
+    Layout l;
+    make_layout(h, g, true, l);
+    cudaStream_t st = S(stream);
+    const bool sp = is_split(precision);
+    const int nspk = h->cfg.num_spk, win = h->cfg.win, stride = win / 2;
+    const int64_t* o = h->off.data();
+    const size_t flat = ((size_t)h->n_params * 2 + 255) & ~(size_t)255;
+    const __nv_bfloat16* whi = reinterpret_cast<const __nv_bfloat16*>(pack);
+    const __nv_bfloat16* wlo = reinterpret_cast<const __nv_bfloat16*>(static_cast<const char*>(pack) + flat);
+    const char* lpack = static_cast<const char*>(pack) + 2 * flat;
+    const int BLi = (int)g.BL, PTi = (int)g.PT;
+    int nl = 0;
+
+    CK(cudaMemsetAsync(at<char>(ws, l.dpack[0]), 0, (size_t)h->npath * (((65536 + 131072 + 1024) * sizeof(float) + 255) & ~(size_t)255), st));
+    // ---- decoder: d_out -> padded rows (overlapping 16-sample frames = dD), dMx = dD Wdec^T, dWdec += Mx^T dD
+    CK(cudaMemsetAsync(at<char>(ws, l.redz), 0, l.redz_bytes, st));
+    float* dpad = at<float>(ws, l.dpad);
+    CK(launch_pad_rows(d_est, dpad, B * nspk, T, g.Tp, stride, st)); ++nl;
+    {
+        GemmNtArgs a = nt_args(dpad, stride, whi + o[8], wlo + o[8], win, 0, at<float>(ws, l.dMx), 64, BLi * nspk, 64, win);
+        a.a_rpb = g.L; a.a_skip = 1;
+        CK(launch_gemm_nt(a, sp, st)); ++nl;
+        GemmTnArgs t = tn_args(at<float>(ws, l.Mx), 64, dpad, stride, grads + o[8], win, BLi * nspk, 64, win);
+        t.b_rpb = g.L; t.b_skip = 1;
+        CK(launch_gemm_tn(t, sp, st)); ++nl;
+    }
+    // ---- mask: dMk = dMx * E * [Mk > 0], dE = sum_c dMx * Mk
+    CK(launch_mask_bwd(at<float>(ws, l.dMx), at<float>(ws, l.Mk), at<float>(ws, l.E), at<float>(ws, l.dMk), at<float>(ws, l.dE), 0, B, g.L, nspk,
+                       64, st)); ++nl;
+    {
+        GemmNtArgs a = nt_args(at<float>(ws, l.dMk), 64 * nspk, whi + o[6], wlo + o[6], 64, 1, at<float>(ws, l.dZ), 64, BLi, 64, 64 * nspk);
+        CK(launch_gemm_nt(a, sp, st)); ++nl;
+        GemmTnArgs t = tn_args(at<float>(ws, l.dMk), 64 * nspk, at<float>(ws, l.Z), 64, grads + o[6], 64, BLi, 64 * nspk, 64);
+        CK(launch_gemm_tn(t, sp, st)); ++nl;
+        CK(launch_colsum(at<float>(ws, l.dMk), 64 * nspk, BLi, 64 * nspk, 1.f, grads + o[7], nullptr, st)); ++nl;
+    }
+    // ---- DPRNN output conv (applied after the overlap-add, bias counted twice)
+    {
+        GemmNtArgs a = nt_args(at<float>(ws, l.dZ), 64, whi + o[4], wlo + o[4], 64, 1, at<float>(ws, l.dF2), 64, BLi, 64, 64);
+        CK(launch_gemm_nt(a, sp, st)); ++nl;
+        GemmTnArgs t = tn_args(at<float>(ws, l.dZ), 64, at<float>(ws, l.F2), 64, grads + o[4], 64, BLi, 64, 64);
+        CK(launch_gemm_tn(t, sp, st)); ++nl;
+        CK(launch_colsum(at<float>(ws, l.dZ), 64, BLi, 64, 2.f, grads + o[5], nullptr, st)); ++nl;
+    }
+    // ---- overlap-add backward = segmentation of the frame gradient
+    float* dXs = at<float>(ws, l.dXs);
+    CK(launch_segment_cl(at<float>(ws, l.dF2), dXs, B, g.L, g.K, g.Sc, 64, st)); ++nl;
+
+    for (int pp = h->npath - 1; pp >= 0; --pp) {
+        const int64_t* po = o + DP_TASNET_HEAD_PARAMS + DP_TASNET_PATH_PARAMS * pp;
+        LstmPackView v = view_pack(lpack + (size_t)pp * PK_BYTES);
+        float* X = at<float>(ws, l.X[pp]);
+        float* G = at<float>(ws, l.G[pp]);
+        float* H = at<float>(ws, l.H[pp]);
+        float* Y = at<float>(ws, l.Y[pp]);
+        float* mr = at<float>(ws, l.mr[pp]);
+        float* dY = at<float>(ws, l.dY);
+        float* dH = at<float>(ws, l.dH);
+        float* dpk = at<float>(ws, l.dpack[pp]);
+        const SeqMap m = path_map(g, pp);
+        if (h->cfg.unfold && (pp & 1)) {
+            CK(launch_concat_bwd(dXs, Y, X, mr, params + po[10], params + po[11], g.PT, g.P, 64, params + o[9], params + o[10], params + o[11],
+                                 grads + o[9], grads + o[10], grads + o[11], st)); ++nl;
+        }
+        // GroupNorm backward (dXs itself is the residual branch of the gradient)
+        CK(launch_gn_bwd_reduce(dXs, Y, mr, params + po[10], g.PT, g.P, 64, at<double>(ws, l.red[pp]), grads + po[10], grads + po[11], st)); ++nl;
+        CK(launch_gn_bwd_apply(dXs, Y, dY, mr, at<double>(ws, l.red[pp]), params + po[10], g.PT, g.P, 64, st)); ++nl;
+        // out-projection Linear(256 -> 64)
+        {
+            GemmNtArgs a = nt_args(dY, 64, whi + po[8], wlo + po[8], 256, 1, dH, 256, PTi, 256, 64);
+            CK(launch_gemm_nt(a, sp, st)); ++nl;
+            GemmTnArgs t = tn_args(dY, 64, H, 256, grads + po[8], 256, PTi, 64, 256);
+            CK(launch_gemm_tn(t, sp, st)); ++nl;
+            CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[9], nullptr, st)); ++nl;
+        }
+        // BPTT: G (activated gates) -> d(pre-activations)
+        CK(launch_lstm_bwd(v.rec, G, at<float>(ws, l.Cst[pp]), dH, m, sp, st)); ++nl;
+        // input projection: dX += dG W_ih ; dW_ih += dG^T X ; dW_hh += dG^T h_prev ; db += colsum(dG)   (packed row order)
+        {
+            GemmNtArgs a = nt_args(G, 1024, v.wih_hi, v.wih_lo, 64, 1, dXs, 64, PTi, 64, 1024);
+            a.accumulate = 1;
+            CK(launch_gemm_nt(a, sp, st)); ++nl;
+            GemmTnArgs t = tn_args(G, 1024, X, 64, dpk, 64, PTi, 1024, 64);
+            CK(launch_gemm_tn(t, sp, st)); ++nl;
+            for (int d = 0; d < 2; ++d) {
+                GemmTnArgs r = tn_args(G + d * 512, 1024, H + d * 128, 256, dpk + 65536 + d * 65536, 128, PTi, 512, 128);
+                r.shift = (d == 0 ? -1 : 1) * (int)m.s_t;
+                r.tdiv = (pp & 1) ? g.K : 1;
+                r.tmod = m.len;
+                CK(launch_gemm_tn(r, sp, st)); ++nl;
+            }
+            CK(launch_colsum(G, 1024, PTi, 1024, 1.f, dpk + 65536 + 131072, nullptr, st)); ++nl;
+        }
+    }
+    // ---- segmentation backward = overlap-add ; bottleneck conv ; bottleneck GroupNorm ; encoder
+    float* dFb = at<float>(ws, l.dF2);
+    CK(launch_overlap_add_cl(dXs, dFb, B, g.L, g.K, g.Sc, 64, st)); ++nl;
+    float* dEn = at<float>(ws, l.dZ);
+    {
+        GemmNtArgs a = nt_args(dFb, 64, whi + o[3], wlo + o[3], 64, 1, dEn, 64, BLi, 64, 64);
+        CK(launch_gemm_nt(a, sp, st)); ++nl;
+        GemmTnArgs t = tn_args(dFb, 64, at<float>(ws, l.En), 64, grads + o[3], 64, BLi, 64, 64);
+        CK(launch_gemm_tn(t, sp, st)); ++nl;
+    }
+    CK(launch_gn_bwd_reduce(dEn, at<float>(ws, l.E), at<float>(ws, l.mrE), params + o[1], g.BL, g.L, 64, at<double>(ws, l.redE), grads + o[1],
+                            grads + o[2], st)); ++nl;
+    CK(launch_gn_bwd_apply(dEn, at<float>(ws, l.E), at<float>(ws, l.dtmp), at<float>(ws, l.mrE), at<double>(ws, l.redE), params + o[1], g.BL,
+                           g.L, 64, st)); ++nl;
+    CK(launch_axpy(at<float>(ws, l.dE), at<float>(ws, l.dtmp), 1.f, g.BL * 64, st)); ++nl;
+    {   // encoder weight gradient: dW_enc += dE^T frames(xp)
+        GemmTnArgs t = tn_args(at<float>(ws, l.dE), 64, at<float>(ws, l.xp), stride, grads + o[0], win, BLi, 64, win);
+        t.b_rpb = g.L; t.b_skip = 1;
+        CK(launch_gemm_tn(t, sp, st)); ++nl;
+    }
+    // packed LSTM gradients -> natural parameter layout
+    for (int pp = 0; pp < h->npath; ++pp) {
+        const int64_t* po = o + DP_TASNET_HEAD_PARAMS + DP_TASNET_PATH_PARAMS * pp;
+        const float* dpk = at<float>(ws, l.dpack[pp]);
+        float* wi[2] = {grads + po[0], grads + po[4]};
+        float* wh[2] = {grads + po[1], grads + po[5]};
+        float* bi[2] = {grads + po[2], grads + po[6]};
+        float* bh[2] = {grads + po[3], grads + po[7]};
+        CK(launch_unpack_lstm_grads(dpk, dpk + 65536, dpk + 65536 + 131072, wi, wh, bi, bh, st)); ++nl;
+    }
+    h->launches = nl;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,344 @@
+// Fused normalisation / residual / mask / decoder-OLA kernels of the dual-path hot path (sm_100a).
+// All activations are channels-last rows of C contiguous floats; every kernel moves 128-bit vectors and touches
+// each byte once (HBM-bound).  GroupNorm(1,C) statistics arrive as fp64 (sum, sumsq) per utterance accumulated in
+// the epilogue of the GEMM that produced the tensor, so no separate statistics pass over the data exists.
+//
+// Reference semantics: nn.GroupNorm(1,C,eps) + residual (dprnn.py:71-73,80-82), unfold concat_block = depthwise
+// 1x1 conv + PReLU (dprnn.py:31-34), mask * encoder output (gc3_network.py:174), ConvTranspose1d overlap-add and
+// trim (gc3_network.py:177-179), zero padding (gc3_network.py:123-129).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dp {
+namespace {
+
+inline int grid_for(long long total, int per_block = 256) {
+    long long blocks = ceil_div_ll(total, per_block);
+    long long cap = 148LL * 16;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, float* __restrict__ mr, int groups, double cnt, double eps) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < groups) {
+        double mean = stats[2 * g] / cnt;
+        double var = stats[2 * g + 1] / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mr[2 * g] = (float)mean;
+        mr[2 * g + 1] = (float)(1.0 / sqrt(var + eps));
+    }
+}
+
+__device__ __forceinline__ float prelu_f(float u, float a) { return u >= 0.f ? u : a * u; }
+
+template <bool RES, bool UNFOLD>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float4* __restrict__ y, const float4* __restrict__ res, float4* __restrict__ out,
+                                                       const float* __restrict__ mr, const float4* __restrict__ gamma,
+                                                       const float4* __restrict__ beta, long long rows, int rpg, int C4,
+                                                       const float4* __restrict__ cw, const float4* __restrict__ cb,
+                                                       const float* __restrict__ slope) {
+    const long long total = rows * C4;
+    const float a = UNFOLD ? slope[0] : 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c4 = (int)(i % C4);
+        int g = (int)((i / C4) / rpg);
+        float mean = mr[2 * g], rstd = mr[2 * g + 1];
+        float4 v = ldg_stream(y + i), ga = gamma[c4], be = beta[c4];
+        float4 o;
+        o.x = fmaf((v.x - mean) * rstd, ga.x, be.x);
+        o.y = fmaf((v.y - mean) * rstd, ga.y, be.y);
+        o.z = fmaf((v.z - mean) * rstd, ga.z, be.z);
+        o.w = fmaf((v.w - mean) * rstd, ga.w, be.w);
+        if (RES) {
+            float4 r = ldg_stream(res + i);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (UNFOLD) {
+            float4 w = cw[c4], b = cb[c4];
+            o.x = prelu_f(fmaf(w.x, o.x, b.x), a);
+            o.y = prelu_f(fmaf(w.y, o.y, b.y), a);
+            o.z = prelu_f(fmaf(w.z, o.z, b.z), a);
+            o.w = prelu_f(fmaf(w.w, o.w, b.w), a);
+        }
+        out[i] = o;
+    }
+}
+
+// grid (pieces, groups); 256 threads = 16 row-lanes x 16 channel-quads (C == 64)
+constexpr int GNB_ROWS = 256;
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const float4* __restrict__ d, const float4* __restrict__ y,
+                                                            const float* __restrict__ mr, const float4* __restrict__ gamma, int rpg,
+                                                            double* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float sh[16][16][8];
+    __shared__ double shd[8][2];
+    const int g = blockIdx.y;
+    const int r0 = blockIdx.x * GNB_ROWS, r1 = min(rpg, r0 + GNB_ROWS);
+    const int c4 = threadIdx.x & 15, rl = threadIdx.x >> 4;
+    const float mean = mr[2 * g], rstd = mr[2 * g + 1];
+    const float4 ga = gamma[c4];
+    float dg[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f};
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = r0 + rl; r < r1; r += 16) {
+        size_t i = ((size_t)g * rpg + r) * 16 + c4;
+        float4 dv = ldg_stream(d + i), yv = ldg_stream(y + i);
+        float xh[4] = {(yv.x - mean) * rstd, (yv.y - mean) * rstd, (yv.z - mean) * rstd, (yv.w - mean) * rstd};
+        float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+        float gg[4] = {ga.x, ga.y, ga.z, ga.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dg[k] = fmaf(dd[k], xh[k], dg[k]);
+            db[k] += dd[k];
+            float gd = gg[k] * dd[k];
+            s1 += gd;
+            s2 = fmaf(gd, xh[k], s2);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sh[rl][c4][k] = dg[k]; sh[rl][c4][4 + k] = db[k]; }
+    double a = warp_sum_d((double)s1), b = warp_sum_d((double)s2);
+    if ((threadIdx.x & 31) == 0) { shd[threadIdx.x >> 5][0] = a; shd[threadIdx.x >> 5][1] = b; }
+    __syncthreads();
+    if (threadIdx.x < 128) {  // 16 quads x 8 values
+        int q = threadIdx.x >> 3, k = threadIdx.x & 7;
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) s += sh[r][q][k];
+        if (k < 4) atomicAdd(dgamma + q * 4 + k, s); else atomicAdd(dbeta + q * 4 + (k - 4), s);
+    }
+    if (threadIdx.x == 0) {
+        double x = 0.0, z = 0.0;
+        for (int w = 0; w < 8; ++w) { x += shd[w][0]; z += shd[w][1]; }
+        atomicAdd(red + 2 * g, x);
+        atomicAdd(red + 2 * g + 1, z);
+    }
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float4* __restrict__ d, const float4* __restrict__ y, float4* __restrict__ dy,
+                                                           const float* __restrict__ mr, const double* __restrict__ red,
+                                                           const float4* __restrict__ gamma, long long rows, int rpg, int C4) {
+    const long long total = rows * C4;
+    const float inv_cnt = 1.0f / ((float)rpg * (float)(C4 * 4));
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c4 = (int)(i % C4);
+        int g = (int)((i / C4) / rpg);
+        float mean = mr[2 * g], rstd = mr[2 * g + 1];
+        float m1 = (float)red[2 * g] * inv_cnt, m2 = (float)red[2 * g + 1] * inv_cnt;
+        float4 dv = ldg_stream(d + i), yv = ldg_stream(y + i), ga = gamma[c4];
+        float4 o;
+        o.x = rstd * (ga.x * dv.x - m1 - (yv.x - mean) * rstd * m2);
+        o.y = rstd * (ga.y * dv.y - m1 - (yv.y - mean) * rstd * m2);
+        o.z = rstd * (ga.z * dv.z - m1 - (yv.z - mean) * rstd * m2);
+        o.w = rstd * (ga.w * dv.w - m1 - (yv.w - mean) * rstd * m2);
+        dy[i] = o;
+    }
+}
+
+// unfold backward: out = prelu(u), u = cw*s + cb, s = res + GN(y).  In place: d <- d_s; accumulates dcw, dcb, dslope.
+__global__ void __launch_bounds__(256) concat_bwd_kernel(float4* __restrict__ d, const float4* __restrict__ y, const float4* __restrict__ res,
+                                                         const float* __restrict__ mr, const float4* __restrict__ gamma,
+                                                         const float4* __restrict__ beta, int rpg, const float4* __restrict__ cw,
+                                                         const float4* __restrict__ cb, const float* __restrict__ slope,
+                                                         float* __restrict__ dcw, float* __restrict__ dcb, float* __restrict__ dslope) {
+    __shared__ float sh[16][16][8];
+    __shared__ float shs[8];
+    const int g = blockIdx.y;
+    const int r0 = blockIdx.x * GNB_ROWS, r1 = min(rpg, r0 + GNB_ROWS);
+    const int c4 = threadIdx.x & 15, rl = threadIdx.x >> 4;
+    const float mean = mr[2 * g], rstd = mr[2 * g + 1], a = slope[0];
+    const float4 ga4 = gamma[c4], be4 = beta[c4], w4 = cw[c4], b4 = cb[c4];
+    const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+    const float w[4] = {w4.x, w4.y, w4.z, w4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    float aw[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+    float as = 0.f;
+    for (int r = r0 + rl; r < r1; r += 16) {
+        size_t i = ((size_t)g * rpg + r) * 16 + c4;
+        float4 dv4 = d[i], yv4 = ldg_stream(y + i), rv4 = ldg_stream(res + i);
+        float dv[4] = {dv4.x, dv4.y, dv4.z, dv4.w}, yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w}, rv[4] = {rv4.x, rv4.y, rv4.z, rv4.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float s = rv[k] + fmaf((yv[k] - mean) * rstd, ga[k], be[k]);
+            float u = fmaf(w[k], s, b[k]);
+            float du = dv[k] * (u >= 0.f ? 1.f : a);
+            as += (u >= 0.f) ? 0.f : dv[k] * u;
+            aw[k] = fmaf(du, s, aw[k]);
+            ab[k] += du;
+            o[k] = du * w[k];
+        }
+        d[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sh[rl][c4][k] = aw[k]; sh[rl][c4][4 + k] = ab[k]; }
+    as = warp_sum(as);
+    if ((threadIdx.x & 31) == 0) shs[threadIdx.x >> 5] = as;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        int q = threadIdx.x >> 3, k = threadIdx.x & 7;
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) s += sh[r][q][k];
+        if (k < 4) atomicAdd(dcw + q * 4 + k, s); else atomicAdd(dcb + q * 4 + (k - 4), s);
+    }
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += shs[i];
+        atomicAdd(dslope, s);
+    }
+}
+
+__global__ void pad_rows_kernel(const float* __restrict__ x, float* __restrict__ xp, int rows, int T, int Tp, int front) {
+    const long long total = (long long)rows * Tp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(i / Tp), j = (int)(i % Tp) - front;
+        xp[i] = (j >= 0 && j < T) ? x[(size_t)r * T + j] : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) mask_apply_kernel(const float4* __restrict__ Mk, const float4* __restrict__ E, float4* __restrict__ Mx, int B,
+                                                         int L, int nspk, int C4) {
+    const long long total = (long long)B * nspk * L * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c4 = (int)(i % C4);
+        long long r = i / C4;
+        int t = (int)(r % L);
+        r /= L;
+        int sp = (int)(r % nspk), b = (int)(r / nspk);
+        size_t bt = (size_t)b * L + t;
+        float4 m = Mk[bt * (nspk * C4) + sp * C4 + c4], e = E[bt * C4 + c4];
+        Mx[i] = make_float4(m.x * e.x, m.y * e.y, m.z * e.z, m.w * e.w);
+    }
+}
+
+__global__ void __launch_bounds__(256) mask_bwd_kernel(const float4* __restrict__ dMx, const float4* __restrict__ Mk, const float4* __restrict__ E,
+                                                       float4* __restrict__ dMk, float4* __restrict__ dE, int acc, int B, int L, int nspk, int C4) {
+    const long long total = (long long)B * L * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c4 = (int)(i % C4);
+        long long bt = i / C4;
+        int t = (int)(bt % L), b = (int)(bt / L);
+        float4 e = E[i];
+        float4 de = acc ? dE[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp = 0; sp < nspk; ++sp) {
+            float4 dm = dMx[(((size_t)b * nspk + sp) * L + t) * C4 + c4];
+            size_t mi = (size_t)bt * (nspk * C4) + sp * C4 + c4;
+            float4 m = Mk[mi];
+            de.x = fmaf(dm.x, m.x, de.x); de.y = fmaf(dm.y, m.y, de.y); de.z = fmaf(dm.z, m.z, de.z); de.w = fmaf(dm.w, m.w, de.w);
+            dMk[mi] = make_float4(m.x > 0.f ? dm.x * e.x : 0.f, m.y > 0.f ? dm.y * e.y : 0.f, m.z > 0.f ? dm.z * e.z : 0.f,
+                                  m.w > 0.f ? dm.w * e.w : 0.f);
+        }
+        dE[i] = de;
+    }
+}
+
+__global__ void dec_ola_kernel(const float* __restrict__ D, float* __restrict__ out, int rows, int L, int win, int T) {
+    const int st = win / 2;
+    const long long total = (long long)rows * T;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(i / T), tau = (int)(i % T);
+        int u = tau + st;  // index in the un-trimmed decoder output
+        int t1 = u / st, j1 = u - t1 * st;
+        float v = 0.f;
+        if (t1 < L) v = D[((size_t)r * L + t1) * win + j1];
+        if (t1 >= 1) v += D[((size_t)r * L + t1 - 1) * win + j1 + st];
+        out[i] = v;
+    }
+}
+
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = fmaf(a, x[i], y[i]);
+}
+
+}  // namespace
+
+cudaError_t launch_gn_finalize(const double* stats, float* mr, int groups, double cnt, double eps, cudaStream_t st) {
+    if (groups <= 0) return cudaSuccess;
+    gn_finalize_kernel<<<ceil_div(groups, 128), 128, 0, st>>>(stats, mr, groups, cnt, eps);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gn_apply(const float* y, const float* res, float* out, const float* mr, const float* gamma, const float* beta,
+                            long long rows, int rows_per_group, int C, const float* cw, const float* cb, const float* slope,
+                            cudaStream_t st) {
+    if (C & 3) return cudaErrorInvalidValue;
+    long long total = rows * (C / 4);
+    if (total <= 0) return cudaSuccess;
+    int grid = grid_for(total);
+#define DP_GN(R, U)                                                                                                              \
+    gn_apply_kernel<R, U><<<grid, 256, 0, st>>>((const float4*)y, (const float4*)res, (float4*)out, mr, (const float4*)gamma,     \
+                                                (const float4*)beta, rows, rows_per_group, C / 4, (const float4*)cw,              \
+                                                (const float4*)cb, slope)
+    if (res) { if (cw) DP_GN(true, true); else DP_GN(true, false); }
+    else     { if (cw) DP_GN(false, true); else DP_GN(false, false); }
+#undef DP_GN
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gn_bwd_reduce(const float* d, const float* y, const float* mr, const float* gamma, long long rows, int rows_per_group,
+                                 int C, double* red, float* dgamma, float* dbeta, cudaStream_t st) {
+    if (C != 64) return cudaErrorInvalidValue;
+    int groups = (int)(rows / rows_per_group);
+    if (groups <= 0) return cudaSuccess;
+    dim3 grid(ceil_div(rows_per_group, GNB_ROWS), groups);
+    gn_bwd_reduce_kernel<<<grid, 256, 0, st>>>((const float4*)d, (const float4*)y, mr, (const float4*)gamma, rows_per_group, red, dgamma, dbeta);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gn_bwd_apply(const float* d, const float* y, float* dy, const float* mr, const double* red, const float* gamma,
+                                long long rows, int rows_per_group, int C, cudaStream_t st) {
+    if (C & 3) return cudaErrorInvalidValue;
+    long long total = rows * (C / 4);
+    if (total <= 0) return cudaSuccess;
+    gn_bwd_apply_kernel<<<grid_for(total), 256, 0, st>>>((const float4*)d, (const float4*)y, (float4*)dy, mr, red, (const float4*)gamma, rows,
+                                                         rows_per_group, C / 4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_concat_bwd(float* d, const float* y, const float* res, const float* mr, const float* gamma, const float* beta,
+                              long long rows, int rows_per_group, int C, const float* cw, const float* cb, const float* slope, float* dcw,
+                              float* dcb, float* dslope, cudaStream_t st) {
+    if (C != 64) return cudaErrorInvalidValue;
+    int groups = (int)(rows / rows_per_group);
+    if (groups <= 0) return cudaSuccess;
+    dim3 grid(ceil_div(rows_per_group, GNB_ROWS), groups);
+    concat_bwd_kernel<<<grid, 256, 0, st>>>((float4*)d, (const float4*)y, (const float4*)res, mr, (const float4*)gamma, (const float4*)beta,
+                                            rows_per_group, (const float4*)cw, (const float4*)cb, slope, dcw, dcb, dslope);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pad_rows(const float* x, float* xp, int rows, int T, int Tp, int front, cudaStream_t st) {
+    long long total = (long long)rows * Tp;
+    if (total <= 0) return cudaSuccess;
+    pad_rows_kernel<<<grid_for(total), 256, 0, st>>>(x, xp, rows, T, Tp, front);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mask_apply(const float* Mk, const float* E, float* Mx, int B, int L, int nspk, int C, cudaStream_t st) {
+    long long total = (long long)B * nspk * L * (C / 4);
+    if (total <= 0) return cudaSuccess;
+    mask_apply_kernel<<<grid_for(total), 256, 0, st>>>((const float4*)Mk, (const float4*)E, (float4*)Mx, B, L, nspk, C / 4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mask_bwd(const float* dMx, const float* Mk, const float* E, float* dMk, float* dE, int accumulate_dE, int B, int L,
+                            int nspk, int C, cudaStream_t st) {
+    long long total = (long long)B * L * (C / 4);
+    if (total <= 0) return cudaSuccess;
+    mask_bwd_kernel<<<grid_for(total), 256, 0, st>>>((const float4*)dMx, (const float4*)Mk, (const float4*)E, (float4*)dMk, (float4*)dE,
+                                                     accumulate_dE, B, L, nspk, C / 4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dec_ola(const float* D, float* out, int rows, int L, int win, int T, cudaStream_t st) {
+    long long total = (long long)rows * T;
+    if (total <= 0) return cudaSuccess;
+    dec_ola_kernel<<<grid_for(total), 256, 0, st>>>(D, out, rows, L, win, T);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_axpy(float* y, const float* x, float a, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    axpy_kernel<<<grid_for(n), 256, 0, st>>>(y, x, a, n);
+    return cudaGetLastError();
+}
+
+}  // namespace dp

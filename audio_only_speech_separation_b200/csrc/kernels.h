@@ -1,0 +1,149 @@
+// Internal launcher declarations (host side) for the dual-path kernels.
+// Everything here takes raw device pointers; the public C-ABI lives in include/dualpath_b200.h.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dp {
+
+// ---------------- GEMMs (gemm.cu) ----------------
+// C[M,N] (=|+=) A[M,K] * W^T (+ bias_scale*bias) ; optional ReLU ; optional per-group sum/sumsq.
+// W is given pre-split into bf16 hi/lo.  w_kn == 0: W stored [N,K] (K contiguous, ldw = row stride)
+//                                        w_kn == 1: W stored [K,N] (N contiguous)
+struct GemmNtArgs {
+    const float* A;
+    long long lda;
+    int a_rpb, a_skip;  // row m lives at A + (m + (m / a_rpb) * a_skip) * lda   (a_rpb == 0: plain)
+    const __nv_bfloat16* Whi;
+    const __nv_bfloat16* Wlo;
+    int ldw;
+    int w_kn;
+    float* C;
+    int ldc;
+    int M, N, K;
+    const float* bias;
+    float bias_scale;
+    int relu;
+    int accumulate;
+    double* stats;  // [groups][2] (sum, sumsq) of the stored values, group = row / rows_per_group
+    int rows_per_group;
+};
+cudaError_t launch_gemm_nt(const GemmNtArgs& a, bool split, cudaStream_t st);
+
+// C[Mo,No] += scale * sum_p A[p,Mo]^T * B[p',No]   (fp32 atomics), p' = p + shift when the time index allows.
+struct GemmTnArgs {
+    const float* A;
+    int lda;
+    const float* B;
+    long long ldb;
+    int b_rpb, b_skip;
+    int shift, tdiv, tmod;  // tmod == 0: no shift
+    float* C;
+    int ldc;
+    int P, Mo, No;
+    float scale;
+};
+cudaError_t launch_gemm_tn(const GemmTnArgs& a, bool split, cudaStream_t st);
+
+// out[n] += scale * sum_p A[p*lda + n]  (and the same into out2 when non-null)
+cudaError_t launch_colsum(const float* A, int lda, int P, int N, float scale, float* out, float* out2, cudaStream_t st);
+
+// ---------------- LSTM (lstm.cu) ----------------
+struct SeqMap {  // position of (sequence q, time t):  (q / qdiv) * s_hi + (q % qdiv) * s_lo + t * s_t
+    int nseq, len;
+    int qdiv;
+    long long s_hi, s_lo, s_t;
+};
+struct LstmPack {  // per ProjRNN, both directions
+    const uint4* whh_f_hi;  // [2][8][4][8][32] fragment-ordered W_hh (forward recurrence A operand)
+    const uint4* whh_f_lo;
+    const uint4* whh_b_hi;  // [2][8][32][32]   fragment-ordered W_hh^T (backward recurrence A operand)
+    const uint4* whh_b_lo;
+};
+// G: [P,1024] gate pre-activations (packed column order dir*512 + unit*4 + gate); overwritten with the
+// activated gates when save != 0.  H: [P,256] = [h_fwd | h_bwd].  Cst: [P,256] cell states (save only).
+cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save,
+                            cudaStream_t st);
+// dH: [P,256] incoming gradient of H.  G holds activated gates on entry and d(pre-activations) on exit.
+cudaError_t launch_lstm_bwd(const LstmPack& w, float* G, const float* Cst, const float* dH, const SeqMap& m, bool split,
+                            cudaStream_t st);
+
+// Build all packed forms of one ProjRNN's LSTM weights from the natural fp32 parameters.
+struct LstmPackOut {
+    __nv_bfloat16* wih_hi;  // [1024,64] packed row order
+    __nv_bfloat16* wih_lo;
+    float* bias;  // [1024] = b_ih + b_hh, packed order
+    uint4* whh_f_hi;
+    uint4* whh_f_lo;
+    uint4* whh_b_hi;
+    uint4* whh_b_lo;
+};
+cudaError_t launch_pack_lstm(const float* const w_ih[2], const float* const w_hh[2], const float* const b_ih[2],
+                             const float* const b_hh[2], const LstmPackOut& o, cudaStream_t st);
+// grads of the packed forms -> natural parameter gradients (+=)
+cudaError_t launch_unpack_lstm_grads(const float* d_wih_pack /*[1024,64]*/, const float* d_whh_pack /*[2][512,128]*/,
+                                     const float* d_bias_pack /*[1024]*/, float* const d_w_ih[2], float* const d_w_hh[2],
+                                     float* const d_b_ih[2], float* const d_b_hh[2], cudaStream_t st);
+// flat fp32 -> bf16 hi/lo (elementwise)
+cudaError_t launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t st);
+
+// ---------------- segmentation / overlap-add (seg_ola.cu) ----------------
+cudaError_t launch_segment_nchw(const float* x, float* y, int rows, int L, int K, cudaStream_t st);
+cudaError_t launch_overlap_add_nchw(const float* y, float* x, int rows, int K, int S, int L, cudaStream_t st);
+// channels-last: F[B,L,C] <-> X[B,S,K,C]   (C % 4 == 0)
+cudaError_t launch_segment_cl(const float* f, float* x, int B, int L, int K, int S, int C, cudaStream_t st);
+cudaError_t launch_overlap_add_cl(const float* x, float* f, int B, int L, int K, int S, int C, cudaStream_t st);
+
+// ---------------- norms / elementwise (elementwise.cu) ----------------
+// (sum, sumsq) fp64 per group -> (mean, rstd) fp32 per group; cnt = elements per group
+cudaError_t launch_gn_finalize(const double* stats, float* mr, int groups, double cnt, double eps, cudaStream_t st);
+// out = res + (y - mean_g) * rstd_g * gamma + beta   (res may be null); group = row / rows_per_group; C channels.
+// unfold (cw != null): out = prelu(cw * out + cb, slope)
+cudaError_t launch_gn_apply(const float* y, const float* res, float* out, const float* mr, const float* gamma, const float* beta,
+                            long long rows, int rows_per_group, int C, const float* cw, const float* cb, const float* slope,
+                            cudaStream_t st);
+// reductions for the GroupNorm backward: red[g] += (sum gamma*d, sum gamma*d*xhat); dgamma += sum d*xhat; dbeta += sum d
+cudaError_t launch_gn_bwd_reduce(const float* d, const float* y, const float* mr, const float* gamma, long long rows, int rows_per_group,
+                                 int C, double* red, float* dgamma, float* dbeta, cudaStream_t st);
+// dy = rstd * (gamma*d - s1/cnt - xhat*s2/cnt)
+cudaError_t launch_gn_bwd_apply(const float* d, const float* y, float* dy, const float* mr, const double* red, const float* gamma,
+                                long long rows, int rows_per_group, int C, cudaStream_t st);
+// unfold backward: d holds the gradient of prelu(cw*s+cb) with s = res + GN(y) (recomputed); on exit d holds d_s;
+// accumulates the concat_block parameter gradients
+cudaError_t launch_concat_bwd(float* d, const float* y, const float* res, const float* mr, const float* gamma, const float* beta,
+                              long long rows, int rows_per_group, int C, const float* cw, const float* cb, const float* slope, float* dcw,
+                              float* dcb, float* dslope, cudaStream_t st);
+cudaError_t launch_pad_rows(const float* x, float* xp, int rows, int T, int Tp, int front, cudaStream_t st);
+// Mx[b,c,t,n] = Mk[b,t,c*C+n] * E[b,t,n]
+cudaError_t launch_mask_apply(const float* Mk, const float* E, float* Mx, int B, int L, int nspk, int C, cudaStream_t st);
+// dMk = dMx * E * (Mk > 0) ; dE (=|+=) sum_c dMx * Mk
+cudaError_t launch_mask_bwd(const float* dMx, const float* Mk, const float* E, float* dMk, float* dE, int accumulate_dE, int B,
+                            int L, int nspk, int C, cudaStream_t st);
+// out[r, tau] = D[r, t1, j1] + D[r, t2, j2]  (stride = win/2 overlap-add of decoder frames + trim)
+cudaError_t launch_dec_ola(const float* D, float* out, int rows, int L, int win, int T, cudaStream_t st);
+cudaError_t launch_axpy(float* y, const float* x, float a, long long n, cudaStream_t st);
+
+// ---------------- loss (loss.cu) ----------------
+struct PitLossWs {  // device scratch, all double unless noted
+    double* sums;    // [B][4]   sum e0,e1,t0,t1
+    double* second;  // [B][10]  dot[2][2], dist2[2][2], tt[2]
+    double* noise;   // [B][4]   sisdr noise energy [est][tgt]
+};
+// sdr_type: 0 snr, 1 sisdr, 2 sdsdr.  Outputs: pw [B,2,2] (est,tgt), loss (1), perm [B] (0: identity, 1: swapped),
+// coef [B][2][3] backward coefficients (per estimate: a on (e - mean e), b on (t_j - mean t_j), j index as float)
+cudaError_t launch_pit_loss_fwd(const float* est, const float* tgt, int B, int T, int sdr_type, int threshold_byloss,
+                                const PitLossWs& ws, float* pw, float* loss, int* perm, float* coef, cudaStream_t st);
+cudaError_t launch_pit_loss_bwd(const float* est, const float* tgt, int B, int T, const double* sums, const float* coef,
+                                float grad_scale, float* d_est, cudaStream_t st);
+cudaError_t launch_reorder_sources(const float* est, const int* perm, float* out, int B, int T, cudaStream_t st);
+
+// ---------------- optimizer (optim.cu) ----------------
+cudaError_t launch_sumsq(const float* g, long long n, double* out /*+=*/, cudaStream_t st);
+// torch clip_grad_norm_ + Adam, fused.  norm2 holds sum of squares of the *unscaled* grads; gscale is applied first
+// (1/world_size after an all-reduce SUM).
+cudaError_t launch_adam_clip(float* p, const float* g, float* m, float* v, long long n, const double* norm2, float gscale,
+                             float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2, float wd,
+                             cudaStream_t st);
+
+}  // namespace dp

@@ -1,0 +1,495 @@
+// Persistent bidirectional LSTM recurrence (forward and BPTT) for the dual-path blocks (sm_100a).
+//
+// Replaces the nn.LSTM time loop of ProjRNN (look2hear/models/utils/gc3_basics.py:16,22; cuDNN RNN in the
+// reference) for I = 64, H = 128, one layer, zero initial state, equal-length sequences.
+//
+// Layout / mapping
+//   * one CTA = one direction x a tile of NS = 8*NT sequences; 8 warps; warp w owns hidden units [16w,16w+16)
+//   * the whole time loop runs inside the kernel; W_hh never leaves the SM: its bf16 "hi" half lives in
+//     REGISTERS as ready-made mma A-fragments (128 regs/thread), its bf16 "lo" half (fp32-parity mode only)
+//     in 128 KB of shared memory in fragment order (one conflict-free LDS.128 per fragment)
+//   * gates^T[512 x NS] = W_hh[512 x 128] * h^T[128 x NS] on the tensor cores (m16n8k16, fp32 accumulate);
+//     the four m-tiles of a warp are the i,f,g,o rows of its 16 units, so every thread ends up with all four
+//     gates of its (unit, sequence) cells in its own accumulators: the cell update needs no shuffles or smem
+//   * h_t is written back to shared memory as bf16 hi/lo (the next step's B operand) and to HBM as fp32
+//   * gate pre-activations G = x W_ih^T + b come from the in-projection GEMM in "packed" column order
+//     (dir*512 + unit*4 + gate) so a thread fetches (i,f,g,o) of one cell with a single 128-bit load; they are
+//     loaded straight into the accumulators, the next step's lines are prefetched into L2
+//   * training: the activated gates overwrite G in place and c_t is saved; the backward kernel walks time in
+//     reverse, rebuilds d(gates) per cell, feeds them (bf16 hi/lo, shared memory) to dh_{t-1} = W_hh^T dgates
+//     (K = 512) with W_hh^T resident the same way, and leaves d(pre-activations) in G for the weight-gradient GEMMs
+//
+// SPLIT = true: bf16x3 (hi*hi + hi*lo + lo*hi), precise activations  -> fp32 parity mode
+// SPLIT = false: single bf16 product, tanh.approx activations           -> bf16 mode
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dp {
+namespace {
+
+constexpr int HST = kH + 8;   // h^T smem row stride (bf16): 272 B
+constexpr int DST = kG + 8;   // dgates smem row stride (bf16): 1040 B
+constexpr int ALO_BYTES = 8 * 4 * 8 * 32 * 16;  // 131072
+
+template <int NT>
+__device__ __forceinline__ void load_b_frags(const __nv_bfloat16* base, int stride, int kcol, int lane, uint32_t (&b)[NT][2]) {
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+        uint32_t r[4];
+        int off = (np * 16 + (lane & 7) + (lane >> 4) * 8) * stride + kcol + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4(r, smem_u32(base + off));
+        b[2 * np][0] = r[0]; b[2 * np][1] = r[1]; b[2 * np + 1][0] = r[2]; b[2 * np + 1][1] = r[3];
+    }
+    if (NT & 1) {
+        uint32_t r[2];
+        int off = ((NT - 1) * 8 + (lane & 7)) * stride + kcol + ((lane >> 3) & 1) * 8;
+        ldmatrix_x2(r, smem_u32(base + off));
+        b[NT - 1][0] = r[0]; b[NT - 1][1] = r[1];
+    }
+}
+
+template <int NT, bool SPLIT, bool SAVE>
+__global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, float* __restrict__ G, float* __restrict__ H,
+                                                          float* __restrict__ Cst, const SeqMap m) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NS = 8 * NT;
+    uint4* alo = reinterpret_cast<uint4*>(smem);
+    __nv_bfloat16* hs_hi = reinterpret_cast<__nv_bfloat16*>(smem + (SPLIT ? ALO_BYTES : 0));
+    __nv_bfloat16* hs_lo = hs_hi + NS * HST;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int dir = blockIdx.y;
+    const int q0 = blockIdx.x * NS;
+
+    uint4 ahi[4][8];
+    {
+        const uint4* src = w.whh_f_hi + ((size_t)dir * 8 + warp) * (4 * 8 * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) ahi[j][ks] = src[(j * 8 + ks) * 32 + lane];
+    }
+    if (SPLIT) {
+        const uint4* src = w.whh_f_lo + (size_t)dir * 8192;
+        for (int i = tid; i < 8192; i += 256) alo[i] = src[i];
+    }
+    for (int i = tid; i < NS * HST; i += 256) {  // h_{-1} = 0 (hi and lo arrays are contiguous)
+        reinterpret_cast<uint32_t*>(hs_hi)[i] = 0u;
+    }
+
+    int pbase[NT][2];
+    bool valid[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int q = q0 + n * 8 + 2 * c + e;
+            valid[n][e] = q < m.nseq;
+            int qq = valid[n][e] ? q : 0;
+            pbase[n][e] = (int)((qq / m.qdiv) * m.s_hi + (qq % m.qdiv) * m.s_lo);
+        }
+    float cst[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cst[n][i] = 0.f;
+    const int ucol = dir * kG + (16 * warp + g) * 4;   // packed gate column of (h = 0); h = 1 adds 32
+    const int hcol = dir * kH + 16 * warp + g;         // H / Cst column of (h = 0); h = 1 adds 8
+    __syncthreads();
+
+    for (int step = 0; step < m.len; ++step) {
+        const int t = dir ? (m.len - 1 - step) : step;
+        const long long toff = (long long)t * m.s_t;
+        float acc[4][NT][4];
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid[n][e]) v = *reinterpret_cast<const float4*>(G + (size_t)(pbase[n][e] + toff) * 1024 + ucol + h * 32);
+                    acc[0][n][h * 2 + e] = v.x; acc[1][n][h * 2 + e] = v.y; acc[2][n][h * 2 + e] = v.z; acc[3][n][h * 2 + e] = v.w;
+                }
+        if (step + 1 < m.len && g == 0) {  // pull the next step's gate lines into L2
+            const long long tn = (long long)(dir ? t - 1 : t + 1) * m.s_t;
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (valid[n][e]) {
+                        const float* pn = G + (size_t)(pbase[n][e] + tn) * 1024 + ucol;
+                        prefetch_l2(pn); prefetch_l2(pn + 32);
+                    }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            uint32_t bh[NT][2], bl[NT][2];
+            load_b_frags<NT>(hs_hi, HST, ks * 16, lane, bh);
+            uint4 al[4];
+            if (SPLIT) {
+                load_b_frags<NT>(hs_lo, HST, ks * 16, lane, bl);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) al[j] = alo[((warp * 4 + j) * 8 + ks) * 32 + lane];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    mma_bf16(acc[j][n], ahi[j][ks], bh[n]);
+                    if (SPLIT) {
+                        mma_bf16(acc[j][n], ahi[j][ks], bl[n]);
+                        mma_bf16(acc[j][n], al[j], bh[n]);
+                    }
+                }
+        }
+        __syncthreads();  // every warp is done reading h_{t-1}
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int idx = h * 2 + e;
+                    float ig = sigmoid_f<SPLIT>(acc[0][n][idx]);
+                    float fg = sigmoid_f<SPLIT>(acc[1][n][idx]);
+                    float gg = tanh_f<SPLIT>(acc[2][n][idx]);
+                    float og = sigmoid_f<SPLIT>(acc[3][n][idx]);
+                    float cc = fmaf(fg, cst[n][idx], ig * gg);
+                    cst[n][idx] = cc;
+                    float hh = og * tanh_f<SPLIT>(cc);
+                    if (valid[n][e]) {
+                        size_t pos = (size_t)(pbase[n][e] + toff);
+                        H[pos * 256 + hcol + h * 8] = hh;
+                        if (SAVE) {
+                            *reinterpret_cast<float4*>(G + pos * 1024 + ucol + h * 32) = make_float4(ig, fg, gg, og);
+                            Cst[pos * 256 + hcol + h * 8] = cc;
+                        }
+                    }
+                    const int so = (n * 8 + 2 * c + e) * HST + 16 * warp + g + 8 * h;
+                    __nv_bfloat16 hb = __float2bfloat16_rn(hh);
+                    hs_hi[so] = hb;
+                    if (SPLIT) hs_lo[so] = __float2bfloat16_rn(hh - __bfloat162float(hb));
+                }
+        __syncthreads();
+    }
+}
+
+template <int NT, bool SPLIT>
+__global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, float* __restrict__ G, const float* __restrict__ Cst,
+                                                          const float* __restrict__ dH, const SeqMap m) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NS = 8 * NT;
+    uint4* alo = reinterpret_cast<uint4*>(smem);
+    __nv_bfloat16* dg_hi = reinterpret_cast<__nv_bfloat16*>(smem + (SPLIT ? ALO_BYTES : 0));
+    __nv_bfloat16* dg_lo = dg_hi + NS * DST;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int dir = blockIdx.y;
+    const int q0 = blockIdx.x * NS;
+
+    uint4 ahi[32];
+    {
+        const uint4* src = w.whh_b_hi + ((size_t)dir * 8 + warp) * (32 * 32);
+#pragma unroll
+        for (int ks = 0; ks < 32; ++ks) ahi[ks] = src[ks * 32 + lane];
+    }
+    if (SPLIT) {
+        const uint4* src = w.whh_b_lo + (size_t)dir * 8192;
+        for (int i = tid; i < 8192; i += 256) alo[i] = src[i];
+    }
+    int pbase[NT][2];
+    bool valid[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int q = q0 + n * 8 + 2 * c + e;
+            valid[n][e] = q < m.nseq;
+            int qq = valid[n][e] ? q : 0;
+            pbase[n][e] = (int)((qq / m.qdiv) * m.s_hi + (qq % m.qdiv) * m.s_lo);
+        }
+    float acc[NT][4], dcc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[n][i] = 0.f; dcc[n][i] = 0.f; }
+    const int ucol = dir * kG + (16 * warp + g) * 4;
+    const int hcol = dir * kH + 16 * warp + g;
+    __syncthreads();
+
+    for (int step = 0; step < m.len; ++step) {
+        const int t = dir ? step : (m.len - 1 - step);       // reverse of the forward visiting order
+        const int tp = dir ? t + 1 : t - 1;                  // the step visited just before t in the forward pass
+        const bool first = (step == m.len - 1);              // t is the forward pass's first step: c_{prev} = 0
+        const long long toff = (long long)t * m.s_t, tpoff = (long long)tp * m.s_t;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int idx = h * 2 + e;
+                    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid[n][e]) {
+                        size_t pos = (size_t)(pbase[n][e] + toff);
+                        float4 gt = *reinterpret_cast<const float4*>(G + pos * 1024 + ucol + h * 32);
+                        float ct = Cst[pos * 256 + hcol + h * 8];
+                        float cp = first ? 0.f : Cst[(size_t)(pbase[n][e] + tpoff) * 256 + hcol + h * 8];
+                        float dh = dH[pos * 256 + hcol + h * 8] + acc[n][idx];
+                        float tc = tanh_f<SPLIT>(ct);
+                        float dc = fmaf(dh * gt.w, 1.f - tc * tc, dcc[n][idx]);
+                        dcc[n][idx] = dc * gt.y;
+                        dg.x = dc * gt.z * gt.x * (1.f - gt.x);
+                        dg.y = dc * cp * gt.y * (1.f - gt.y);
+                        dg.z = dc * gt.x * (1.f - gt.z * gt.z);
+                        dg.w = dh * tc * gt.w * (1.f - gt.w);
+                        *reinterpret_cast<float4*>(G + pos * 1024 + ucol + h * 32) = dg;
+                    }
+                    const int so = (n * 8 + 2 * c + e) * DST + (16 * warp + g + 8 * h) * 4;
+                    uint2 hi, lo;
+                    split_pair(dg.x, dg.y, hi.x, lo.x);
+                    split_pair(dg.z, dg.w, hi.y, lo.y);
+                    *reinterpret_cast<uint2*>(dg_hi + so) = hi;
+                    if (SPLIT) *reinterpret_cast<uint2*>(dg_lo + so) = lo;
+                }
+        if (!first && g == 0) {  // next visited step: t2 = tp
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (valid[n][e]) {
+                        size_t pos = (size_t)(pbase[n][e] + tpoff);
+                        prefetch_l2(G + pos * 1024 + ucol); prefetch_l2(G + pos * 1024 + ucol + 32);
+                        prefetch_l2(dH + pos * 256 + hcol);
+                    }
+        }
+        __syncthreads();
+        if (first) break;  // dh_{-1} is not needed
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 32; ++ks) {
+            uint32_t bh[NT][2], bl[NT][2];
+            load_b_frags<NT>(dg_hi, DST, ks * 16, lane, bh);
+            uint4 al;
+            if (SPLIT) {
+                load_b_frags<NT>(dg_lo, DST, ks * 16, lane, bl);
+                al = alo[(warp * 32 + ks) * 32 + lane];
+            }
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                mma_bf16(acc[n], ahi[ks], bh[n]);
+                if (SPLIT) {
+                    mma_bf16(acc[n], ahi[ks], bl[n]);
+                    mma_bf16(acc[n], al, bh[n]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct PackArgs {
+    const float* w_ih[2];
+    const float* w_hh[2];
+    const float* b_ih[2];
+    const float* b_hh[2];
+    LstmPackOut o;
+};
+
+__device__ __forceinline__ void store_split(uint32_t* hi, uint32_t* lo, size_t i, float v0, float v1) {
+    uint32_t h, l;
+    split_pair(v0, v1, h, l);
+    hi[i] = h; lo[i] = l;
+}
+
+__global__ void pack_lstm_kernel(const PackArgs a) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 65536) {  // W_ih -> [1024,64] packed rows (dir*512 + unit*4 + gate)
+        int row = idx >> 6, k = idx & 63;
+        int d = row >> 9, u = (row & 511) >> 2, j = row & 3;
+        float v = a.w_ih[d][(j * kH + u) * kN + k];
+        float vh = bf16_round(v);
+        a.o.wih_hi[idx] = __float2bfloat16_rn(vh);
+        a.o.wih_lo[idx] = __float2bfloat16_rn(v - vh);
+        return;
+    }
+    idx -= 65536;
+    if (idx < 65536) {  // forward-recurrence A fragments of W_hh: [dir][warp][mtile=gate][ks][lane][reg]
+        int d = idx >> 15, r = idx & 32767;
+        int reg = r & 3, lane = (r >> 2) & 31, ks = (r >> 7) & 7, mt = (r >> 10) & 3, wp = r >> 12;
+        int g = lane >> 2, c = lane & 3;
+        int unit = 16 * wp + g + (reg & 1) * 8;
+        int kk = ks * 16 + 2 * c + (reg >> 1) * 8;
+        const float* src = a.w_hh[d] + (size_t)(mt * kH + unit) * kH + kk;
+        store_split(reinterpret_cast<uint32_t*>(a.o.whh_f_hi), reinterpret_cast<uint32_t*>(a.o.whh_f_lo), idx, src[0], src[1]);
+        return;
+    }
+    idx -= 65536;
+    if (idx < 65536) {  // backward-recurrence A fragments of W_hh^T: [dir][warp][ks][lane][reg]; k' = unit*4 + gate
+        int d = idx >> 15, r = idx & 32767;
+        int reg = r & 3, lane = (r >> 2) & 31, ks = (r >> 7) & 31, wp = r >> 12;
+        int g = lane >> 2, c = lane & 3;
+        int mrow = 16 * wp + g + (reg & 1) * 8;
+        int k0 = ks * 16 + 2 * c + (reg >> 1) * 8;
+        float v[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int kp = k0 + i, u = kp >> 2, j = kp & 3;
+            v[i] = a.w_hh[d][(size_t)(j * kH + u) * kH + mrow];
+        }
+        store_split(reinterpret_cast<uint32_t*>(a.o.whh_b_hi), reinterpret_cast<uint32_t*>(a.o.whh_b_lo), idx, v[0], v[1]);
+        return;
+    }
+    idx -= 65536;
+    if (idx < 1024) {
+        int d = idx >> 9, u = (idx & 511) >> 2, j = idx & 3;
+        a.o.bias[idx] = a.b_ih[d][j * kH + u] + a.b_hh[d][j * kH + u];
+    }
+}
+
+struct UnpackArgs {
+    const float* d_wih;
+    const float* d_whh;
+    const float* d_bias;
+    float* w_ih[2];
+    float* w_hh[2];
+    float* b_ih[2];
+    float* b_hh[2];
+};
+__global__ void unpack_lstm_grads_kernel(const UnpackArgs a) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 65536) {
+        int row = idx >> 6, k = idx & 63;
+        int d = row >> 9, u = (row & 511) >> 2, j = row & 3;
+        a.w_ih[d][(j * kH + u) * kN + k] += a.d_wih[idx];
+        return;
+    }
+    idx -= 65536;
+    if (idx < 131072) {  // [2][512 packed rows][128]
+        int d = idx >> 16, r = idx & 65535;
+        int row = r >> 7, k = r & 127;
+        int u = row >> 2, j = row & 3;
+        a.w_hh[d][(size_t)(j * kH + u) * kH + k] += a.d_whh[idx];
+        return;
+    }
+    idx -= 131072;
+    if (idx < 1024) {
+        int d = idx >> 9, u = (idx & 511) >> 2, j = idx & 3;
+        float v = a.d_bias[idx];
+        a.b_ih[d][j * kH + u] += v;
+        a.b_hh[d][j * kH + u] += v;
+    }
+}
+
+__global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float v = src[i], vh = bf16_round(v);
+        hi[i] = __float2bfloat16_rn(vh);
+        lo[i] = __float2bfloat16_rn(v - vh);
+    }
+}
+
+template <typename K>
+cudaError_t set_smem(K kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+int pick_nt(int nseq) {
+    // smallest tile that still fits the whole pass in one wave of 148 SMs (2 directions per tile)
+    for (int nt = 1; nt <= 3; ++nt)
+        if (2 * ceil_div(nseq, 8 * nt) <= 148) return nt;
+    return 3;
+}
+
+template <int NT>
+cudaError_t fwd_launch(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, cudaStream_t st) {
+    dim3 grid(ceil_div(m.nseq, 8 * NT), 2);
+    int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * HST * 2;
+    cudaError_t e;
+#define DP_FWD(SP, SV)                                                               \
+    do {                                                                             \
+        e = set_smem(lstm_fwd_kernel<NT, SP, SV>, smem);                             \
+        if (e != cudaSuccess) return e;                                              \
+        lstm_fwd_kernel<NT, SP, SV><<<grid, 256, smem, st>>>(w, G, H, Cst, m);       \
+    } while (0)
+    if (split) { if (save) DP_FWD(true, true); else DP_FWD(true, false); }
+    else       { if (save) DP_FWD(false, true); else DP_FWD(false, false); }
+#undef DP_FWD
+    return cudaGetLastError();
+}
+
+template <int NT>
+cudaError_t bwd_launch(const LstmPack& w, float* G, const float* Cst, const float* dH, const SeqMap& m, bool split, cudaStream_t st) {
+    dim3 grid(ceil_div(m.nseq, 8 * NT), 2);
+    int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * DST * 2;
+    cudaError_t e;
+    if (split) {
+        e = set_smem(lstm_bwd_kernel<NT, true>, smem);
+        if (e != cudaSuccess) return e;
+        lstm_bwd_kernel<NT, true><<<grid, 256, smem, st>>>(w, G, Cst, dH, m);
+    } else {
+        e = set_smem(lstm_bwd_kernel<NT, false>, smem);
+        if (e != cudaSuccess) return e;
+        lstm_bwd_kernel<NT, false><<<grid, 256, smem, st>>>(w, G, Cst, dH, m);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save,
+                            cudaStream_t st) {
+    if (m.nseq <= 0 || m.len <= 0) return cudaSuccess;
+    switch (pick_nt(m.nseq)) {
+        case 1: return fwd_launch<1>(w, G, H, Cst, m, split, save, st);
+        case 2: return fwd_launch<2>(w, G, H, Cst, m, split, save, st);
+        default: return fwd_launch<3>(w, G, H, Cst, m, split, save, st);
+    }
+}
+
+cudaError_t launch_lstm_bwd(const LstmPack& w, float* G, const float* Cst, const float* dH, const SeqMap& m, bool split,
+                            cudaStream_t st) {
+    if (m.nseq <= 0 || m.len <= 0) return cudaSuccess;
+    switch (pick_nt(m.nseq)) {
+        case 1: return bwd_launch<1>(w, G, Cst, dH, m, split, st);
+        case 2: return bwd_launch<2>(w, G, Cst, dH, m, split, st);
+        default: return bwd_launch<3>(w, G, Cst, dH, m, split, st);
+    }
+}
+
+cudaError_t launch_pack_lstm(const float* const w_ih[2], const float* const w_hh[2], const float* const b_ih[2],
+                             const float* const b_hh[2], const LstmPackOut& o, cudaStream_t st) {
+    PackArgs a;
+    for (int d = 0; d < 2; ++d) { a.w_ih[d] = w_ih[d]; a.w_hh[d] = w_hh[d]; a.b_ih[d] = b_ih[d]; a.b_hh[d] = b_hh[d]; }
+    a.o = o;
+    int total = 65536 * 3 + 1024;
+    pack_lstm_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_lstm_grads(const float* d_wih_pack, const float* d_whh_pack, const float* d_bias_pack,
+                                     float* const d_w_ih[2], float* const d_w_hh[2], float* const d_b_ih[2],
+                                     float* const d_b_hh[2], cudaStream_t st) {
+    UnpackArgs a;
+    a.d_wih = d_wih_pack; a.d_whh = d_whh_pack; a.d_bias = d_bias_pack;
+    for (int d = 0; d < 2; ++d) { a.w_ih[d] = d_w_ih[d]; a.w_hh[d] = d_w_hh[d]; a.b_ih[d] = d_b_ih[d]; a.b_hh[d] = d_b_hh[d]; }
+    int total = 65536 + 131072 + 1024;
+    unpack_lstm_grads_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    split_bf16_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(src, hi, lo, n);
+    return cudaGetLastError();
+}
+
+}  // namespace dp

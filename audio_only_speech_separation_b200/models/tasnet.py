@@ -1,0 +1,296 @@
+"""Drop-in ``TasNet`` (look2hear/models/gc3_network.py:7-188) whose forward/backward run in the CUDA engine.
+
+The constructor signature, ``forward(mixture) -> est_sources`` contract, ``model_name`` attribute and every
+``state_dict`` key/shape are those of the reference, so ``audio_train.py`` / ``audio_test.py`` style lookups
+(``getattr(models, "TasNet")(sample_rate=..., **audionet_config)``, ``from_pretrain``) keep working and existing
+``best_model.pth`` files load.  The sub-modules below are *parameter containers only* (built in the reference's
+construction order so the default initialisation is reproduced bit for bit under the same seed); none of their
+``forward`` methods is ever called.  All parameters live as views of ONE flat fp32 buffer, which is what the engine,
+the fused Adam step and the single NCCL gradient all-reduce operate on.
+
+Supported on this path: ``module="DPRNN"``, ``group_size=1``, ``enc_dim=bn_dim=64``, ``hidden_dim=128``,
+``win=16`` (every DPRNN config of the reference), ``unfold`` True or False.  Anything else raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .._lib import check, lib, ptr, stream_ptr
+from .base_model import BaseModel
+
+
+class _ProjRNN(nn.Module):
+    """Parameter container with the keys of ``ProjRNN`` (gc3_basics.py:7-17): ``rnn.*``, ``proj.*``."""
+
+    def __init__(self, input_size, hidden_size, bidirectional=True):
+        super().__init__()
+        self.rnn = nn.LSTM(input_size, hidden_size, 1, dropout=0, batch_first=True, bidirectional=bidirectional)
+        self.proj = nn.Linear(hidden_size * (int(bidirectional) + 1), input_size)
+
+
+class _DPRNN(nn.Module):
+    """Parameter container with the keys of ``DPRNN`` (dprnn.py:7-51), ``num_group == 1``."""
+
+    def __init__(self, input_size, hidden_size, output_size, num_layers, unfold):
+        super().__init__()
+        self.row_rnn = nn.ModuleList([])
+        self.col_rnn = nn.ModuleList([])
+        self.row_norm = nn.ModuleList([])
+        self.col_norm = nn.ModuleList([])
+        if unfold:  # one shared instance of everything, reused by all layers (dprnn.py:26-34)
+            row_rnn = _ProjRNN(input_size, hidden_size)
+            col_rnn = _ProjRNN(input_size, hidden_size)
+            row_norm = nn.GroupNorm(1, input_size, eps=1e-8)
+            col_norm = nn.GroupNorm(1, input_size, eps=1e-8)
+            self.concat_block = nn.Sequential(nn.Conv2d(input_size, input_size, 1, 1, groups=input_size), nn.PReLU())
+        for _ in range(num_layers):
+            self.row_rnn.append(row_rnn if unfold else _ProjRNN(input_size, hidden_size))
+            self.col_rnn.append(col_rnn if unfold else _ProjRNN(input_size, hidden_size))
+            self.row_norm.append(row_norm if unfold else nn.GroupNorm(1, input_size, eps=1e-8))
+            self.col_norm.append(col_norm if unfold else nn.GroupNorm(1, input_size, eps=1e-8))
+        self.output = nn.Conv2d(input_size, output_size, 1)
+
+
+class _DPWrapper(nn.Module):
+    """Key prefix of ``DP_Wrapper`` (groupcomm.py:49-98): ``seq_model.*``."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, layer, unfold):
+        super().__init__()
+        self.seq_model = _DPRNN(input_dim, hidden_dim, output_dim, layer, unfold)
+
+
+class _TasNetFunction(torch.autograd.Function):
+    """Autograd node for the whole network: forward and backward are single engine calls."""
+
+    @staticmethod
+    def forward(ctx, model, mixture, *params):
+        train = any(ctx.needs_input_grad[2:])
+        est, ws = model._engine_forward(mixture, train)
+        ctx.model, ctx.ws, ctx.dims = model, ws, mixture.shape
+        return est
+
+    @staticmethod
+    def backward(ctx, d_est):
+        model = ctx.model
+        if ctx.ws is None:
+            raise RuntimeError("TasNet backward: forward ran without gradient tracking")
+        gflat = torch.zeros_like(model._flat)
+        model._engine_backward(d_est.contiguous().float(), gflat, ctx.ws, *ctx.dims)
+        ctx.ws = None
+        grads = [gflat[o : o + p.numel()].view(p.shape) for p, o in zip(model._uniq, model._uniq_off)]
+        return (None, None, *grads)
+
+
+class TasNet(BaseModel):
+    def __init__(
+        self,
+        enc_dim=64,
+        bn_dim=64,
+        hidden_dim=128,
+        win=16,
+        layer=6,
+        num_spk=2,
+        module="DPRNN",
+        context_size=24,
+        group_size=1,
+        block_size=100,
+        sample_rate=16000,
+        unfold=False,
+    ):
+        super().__init__(sample_rate=sample_rate)
+        assert module in ["DPRNN", "DPTNet", "TCN", "SudoRMRF", "GC_TCN", "GC_SudoRMRF"]  # gc3_network.py:25-32
+        if module != "DPRNN":
+            raise NotImplementedError(f"module={module!r}: this build accelerates module='DPRNN' (see DESIGN.md scope table)")
+        if group_size != 1:
+            raise NotImplementedError("group_size > 1 (GroupComm/TAC) is not on the accelerated path (DESIGN.md scope table)")
+        self.num_spk = num_spk
+        self.enc_dim = enc_dim
+        self.bn_dim = bn_dim
+        self.hidden_dim = hidden_dim
+        self.context_size = context_size
+        self.group_size = group_size
+        self.win = win
+        self.stride = self.win // 2
+        self.model_name = module
+        self.unfold = unfold
+        self.layer = layer
+        self.block_size = block_size
+        # 'fp32' (bf16x3 tensor-core products, fp32 parity) or 'bf16'
+        self.precision = os.environ.get("DUALPATH_PRECISION", "fp32")
+
+        # ---- parameters, created in the reference's order (gc3_network.py:48-106) ----
+        self.encoder = nn.Conv1d(1, self.enc_dim, self.win, bias=False, stride=self.stride)
+        torch.nn.init.xavier_uniform_(self.encoder.weight)
+        self.bottleneck = nn.Sequential(
+            nn.GroupNorm(1, self.enc_dim, eps=torch.finfo(torch.float32).eps),
+            nn.Conv1d(self.enc_dim, self.bn_dim, 1, bias=False),
+        )
+        self.seq_model = _DPWrapper(self.bn_dim, self.hidden_dim, self.bn_dim, layer, unfold)
+        self.mask = nn.Sequential(nn.Conv1d(self.bn_dim, self.enc_dim * self.num_spk, 1), nn.ReLU(inplace=True))
+        self.decoder = nn.ConvTranspose1d(self.enc_dim, 1, self.win, bias=False, stride=self.stride)
+        torch.nn.init.xavier_uniform_(self.decoder.weight)
+
+        self._handle = None
+        self._flat = None
+        self._uniq: List[nn.Parameter] = []
+        self._uniq_off: List[int] = []
+        self._pack = None
+        self._pack_sig = None
+        self.last_launches = 0
+
+    # ------------------------------------------------------------------ reference API
+    def pad_input(self, input):
+        """Shape normalisation of gc3_network.py:108-131 (the zero padding itself happens inside the engine)."""
+        was_one_d = False
+        if input.ndim == 1:
+            was_one_d = True
+            input = input.unsqueeze(0)
+        if input.ndim == 3:
+            input = input.squeeze(1)
+        nsample = input.shape[1]
+        rest = self.win - (self.stride + nsample % self.win) % self.win
+        return input, rest, was_one_d
+
+    def forward(self, input):
+        x, _, was_one_d = self.pad_input(input)
+        if x.ndim != 2:
+            raise ValueError(f"expected [T], [B, T] or [B, 1, T], got {tuple(input.shape)}")
+        _lib.require_cuda(x.contiguous(), "TasNet input")
+        xin = x.contiguous().float()
+        self._sync_flat(xin.device)
+        est = _TasNetFunction.apply(self, xin, *self._uniq)
+        if est.dtype != input.dtype and input.dtype.is_floating_point:
+            est = est.to(input.dtype)
+        return est.squeeze(0) if was_one_d else est
+
+    def get_model_args(self):
+        return {"n_src": 2}  # gc3_network.py:186-188
+
+    # ------------------------------------------------------------------ flat parameters / engine
+    def _param_table(self):
+        sm = self.seq_model.seq_model
+        cat = sm.concat_block if self.unfold else None
+        table = [
+            self.encoder.weight,
+            self.bottleneck[0].weight,
+            self.bottleneck[0].bias,
+            self.bottleneck[1].weight,
+            sm.output.weight,
+            sm.output.bias,
+            self.mask[0].weight,
+            self.mask[0].bias,
+            self.decoder.weight,
+            cat[0].weight if cat is not None else None,
+            cat[0].bias if cat is not None else None,
+            cat[1].weight if cat is not None else None,
+        ]
+        for i in range(self.layer):
+            for rnn, norm in ((sm.row_rnn[i], sm.row_norm[i]), (sm.col_rnn[i], sm.col_norm[i])):
+                r = rnn.rnn
+                table += [
+                    r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0,
+                    r.weight_ih_l0_reverse, r.weight_hh_l0_reverse, r.bias_ih_l0_reverse, r.bias_hh_l0_reverse,
+                    rnn.proj.weight, rnn.proj.bias, norm.weight, norm.bias,
+                ]
+        return table
+
+    def _flat_is_valid(self, device) -> bool:
+        if self._flat is None or self._flat.device != device:
+            return False
+        base = self._flat.data_ptr()
+        return all(p.data_ptr() == base + 4 * o and p.dtype == torch.float32 for p, o in zip(self._uniq, self._uniq_off))
+
+    def _sync_flat(self, device):
+        """(Re)build the flat parameter buffer and the engine handle when parameters moved (``.to()``, ``.cuda()``)."""
+        if self._flat_is_valid(device):
+            return
+        table = self._param_table()
+        for p in table:
+            if p is not None and p.device != device:
+                raise RuntimeError(
+                    f"TasNet parameters are on {p.device} but the input is on {device}; move the model with .to(device) "
+                    "(the dual-path kernels are CUDA-only, there is no CPU path)"
+                )
+        uniq, offs, seen, total = [], [], {}, 0
+        for p in table:
+            if p is None or id(p) in seen:
+                continue
+            seen[id(p)] = total
+            uniq.append(p)
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4  # keep every parameter 16-byte aligned
+        flat = torch.zeros(total, device=device, dtype=torch.float32)
+        with torch.no_grad():
+            for p, o in zip(uniq, offs):
+                flat[o : o + p.numel()].copy_(p.data.reshape(-1).to(device=device, dtype=torch.float32))
+                p.data = flat[o : o + p.numel()].view(p.shape)
+        self._flat, self._uniq, self._uniq_off = flat, uniq, offs
+        offsets = [(-1 if p is None else seen[id(p)]) for p in table]
+        if self._handle is not None:
+            lib().dp_tasnet_destroy(self._handle)
+            self._handle = None
+        cfg = _lib.TasnetConfig(self.enc_dim, self.bn_dim, self.hidden_dim, self.win, self.layer, self.num_spk, self.block_size,
+                                int(self.unfold))
+        arr = (C.c_int64 * len(offsets))(*offsets)
+        h = C.c_void_p()
+        check(lib().dp_tasnet_create(C.byref(cfg), arr, len(offsets), total, C.byref(h)), "dp_tasnet_create")
+        self._handle = h
+        self._pack = torch.empty(lib().dp_tasnet_pack_bytes(h), device=device, dtype=torch.uint8)
+        self._pack_sig = None
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                lib().dp_tasnet_destroy(self._handle)
+        except Exception:
+            pass
+
+    def mark_params_dirty(self):
+        """Call after writing the flat buffer directly (the fused optimizer step does)."""
+        self._pack_sig = None
+
+    def _prec(self) -> int:
+        p = str(self.precision).lower()
+        if p in ("fp32", "float32"):
+            return _lib.PREC_FP32
+        if p in ("bf16", "bfloat16"):
+            return _lib.PREC_BF16
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision!r}")
+
+    def _ensure_pack(self):
+        sig = tuple(p._version for p in self._uniq)
+        if sig != self._pack_sig:
+            check(lib().dp_tasnet_pack(self._handle, ptr(self._flat), ptr(self._pack), stream_ptr()), "dp_tasnet_pack")
+            self._pack_sig = sig
+
+    def _engine_forward(self, mixture, train: bool, est=None, ws=None):
+        B, T = mixture.shape
+        self._ensure_pack()
+        nbytes = lib().dp_tasnet_workspace_bytes(self._handle, B, T, int(train))
+        if nbytes < 0:
+            check(1, "dp_tasnet_workspace_bytes")
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, device=mixture.device, dtype=torch.uint8)
+        if est is None:
+            est = torch.empty(B, self.num_spk, T, device=mixture.device, dtype=torch.float32)
+        check(
+            lib().dp_tasnet_forward(self._handle, ptr(self._flat), ptr(self._pack), ptr(mixture), ptr(est), ptr(ws), B, T, int(train),
+                                    self._prec(), stream_ptr()),
+            "dp_tasnet_forward",
+        )
+        self.last_launches = lib().dp_tasnet_last_launches(self._handle)
+        return est, (ws if train else None)
+
+    def _engine_backward(self, d_est, gflat, ws, B, T):
+        check(
+            lib().dp_tasnet_backward(self._handle, ptr(self._flat), ptr(self._pack), ptr(d_est), ptr(gflat), ptr(ws), B, T, self._prec(),
+                                     stream_ptr()),
+            "dp_tasnet_backward",
+        )
+        self.last_launches = lib().dp_tasnet_last_launches(self._handle)

@@ -1,0 +1,209 @@
+"""Python-level operators over the C-ABI (one function per reference call they replace).
+
+Each function validates its arguments the way the reference module would fail (TypeError / ValueError), requires
+CUDA tensors, launches on the current torch stream and returns torch tensors.  None of them has a CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, require_cuda, stream_ptr
+
+__all__ = [
+    "split_feature",
+    "merge_feature",
+    "segment_channels_last",
+    "overlap_add_channels_last",
+    "linear",
+    "linear_wgrad",
+    "split_bf16",
+    "LstmPack",
+    "bilstm_forward",
+    "bilstm_backward",
+    "groupnorm_residual",
+]
+
+
+def _prec(precision) -> int:
+    if precision in (0, 1):
+        return precision
+    p = str(precision).lower()
+    if p in ("fp32", "float32"):
+        return _lib.PREC_FP32
+    if p in ("bf16", "bfloat16"):
+        return _lib.PREC_BF16
+    raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+
+
+def split_feature(x: torch.Tensor, block_size: int):
+    """``split_feature`` of look2hear/models/utils/gc3_basics.py:79-91: ``[B,N,L] -> ([B,N,K,S], rest)``, bit-exact."""
+    if x.ndim != 3:
+        raise ValueError(f"expected [B, N, L], got {tuple(x.shape)}")
+    require_cuda(x, "input")
+    if x.dtype != torch.float32:
+        raise TypeError("split_feature: float32 only")
+    B, N, L = x.shape
+    rest, S = _lib.seg_geometry(L, block_size)
+    y = torch.empty(B, N, block_size, S, device=x.device, dtype=x.dtype)
+    check(lib().dp_segment_f32(ptr(x), ptr(y), B, N, L, block_size, stream_ptr()), "dp_segment_f32")
+    return y, rest
+
+
+def merge_feature(y: torch.Tensor, rest: int) -> torch.Tensor:
+    """``merge_feature`` of gc3_basics.py:94-109: ``[B,N,K,S] -> [B,N,L]``, bit-exact."""
+    if y.ndim != 4:
+        raise ValueError(f"expected [B, N, K, S], got {tuple(y.shape)}")
+    require_cuda(y, "input")
+    if y.dtype != torch.float32:
+        raise TypeError("merge_feature: float32 only")
+    B, N, K, S = y.shape
+    L = (S // 2) * K - K // 2 - rest
+    if L <= 0:
+        raise ValueError(f"rest={rest} is inconsistent with K={K}, S={S}")
+    x = torch.empty(B, N, L, device=y.device, dtype=y.dtype)
+    check(lib().dp_overlap_add_f32(ptr(y), ptr(x), B, N, K, S, L, stream_ptr()), "dp_overlap_add_f32")
+    return x
+
+
+def segment_channels_last(f: torch.Tensor, block_size: int) -> torch.Tensor:
+    """Same map as :func:`split_feature` on ``[B,L,C] -> [B,S,K,C]`` (the engine's internal layout)."""
+    require_cuda(f, "input")
+    B, L, Cc = f.shape
+    _, S = _lib.seg_geometry(L, block_size)
+    x = torch.empty(B, S, block_size, Cc, device=f.device, dtype=torch.float32)
+    check(lib().dp_segment_cl_f32(ptr(f), ptr(x), B, L, block_size, Cc, stream_ptr()), "dp_segment_cl_f32")
+    return x
+
+
+def overlap_add_channels_last(x: torch.Tensor, L: int) -> torch.Tensor:
+    require_cuda(x, "input")
+    B, S, K, Cc = x.shape
+    f = torch.empty(B, L, Cc, device=x.device, dtype=torch.float32)
+    check(lib().dp_overlap_add_cl_f32(ptr(x), ptr(f), B, L, K, Cc, stream_ptr()), "dp_overlap_add_cl_f32")
+    return f
+
+
+def split_bf16(w: torch.Tensor):
+    """fp32 -> (bf16 hi, bf16 lo) with ``w ~= hi + lo``."""
+    require_cuda(w, "w")
+    hi = torch.empty(w.shape, device=w.device, dtype=torch.bfloat16)
+    lo = torch.empty(w.shape, device=w.device, dtype=torch.bfloat16)
+    check(lib().dp_split_bf16(ptr(w), ptr(hi), ptr(lo), w.numel(), stream_ptr()), "dp_split_bf16")
+    return hi, lo
+
+
+def linear(a, weight, bias=None, *, w_kn=False, relu=False, out=None, accumulate=False, stats=None, rows_per_group=0,
+           bias_scale=1.0, precision="fp32", lda=None, rows=None):
+    """``y = a @ W^T + bias`` (``nn.Linear`` / 1x1 conv).  ``weight`` is ``[N,K]`` (or ``[K,N]`` with ``w_kn``)."""
+    require_cuda(a, "a")
+    require_cuda(weight, "weight")
+    hi, lo = split_bf16(weight.float().contiguous())
+    if w_kn:
+        K, N = weight.shape
+    else:
+        N, K = weight.shape
+    M = rows if rows is not None else a.shape[0]
+    lda = lda if lda is not None else a.stride(0)
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    check(
+        lib().dp_linear_f32(ptr(a), lda, ptr(hi), ptr(lo), weight.shape[1], int(w_kn), ptr(bias), float(bias_scale), ptr(out),
+                            out.stride(0), M, N, K, int(relu), int(accumulate), ptr(stats), int(rows_per_group), _prec(precision),
+                            stream_ptr()),
+        "dp_linear_f32",
+    )
+    return out
+
+
+def linear_wgrad(a, b, out, *, scale=1.0, precision="fp32"):
+    """``out[Mo,No] += scale * a[P,Mo]^T @ b[P,No]`` (weight gradient of :func:`linear`)."""
+    for t, n in ((a, "a"), (b, "b"), (out, "out")):
+        require_cuda(t, n)
+    P, Mo = a.shape
+    No = b.shape[1]
+    check(
+        lib().dp_linear_wgrad_f32(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), P, Mo, No, float(scale),
+                                  _prec(precision), stream_ptr()),
+        "dp_linear_wgrad_f32",
+    )
+    return out
+
+
+class LstmPack:
+    """Packed weights of one bidirectional ``nn.LSTM(64, 128)`` (gc3_basics.py:16)."""
+
+    def __init__(self, lstm: torch.nn.LSTM):
+        names = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"]
+        ws = [getattr(lstm, n).detach().float().contiguous() for n in names] + [
+            getattr(lstm, n + "_reverse").detach().float().contiguous() for n in names
+        ]
+        if tuple(ws[0].shape) != (512, 64) or tuple(ws[1].shape) != (512, 128):
+            raise ValueError("the recurrent kernel is specialised for input 64 / hidden 128")
+        for w in ws:
+            require_cuda(w, "lstm weight")
+        self.buf = torch.empty(lib().dp_lstm_pack_bytes(), device=ws[0].device, dtype=torch.uint8)
+        check(lib().dp_lstm_pack(*[ptr(w) for w in ws], ptr(self.buf), stream_ptr()), "dp_lstm_pack")
+        self._keep = ws
+
+
+def _seq_map(layout: str, B: int, S: int, K: int):
+    if layout == "intra":  # sequences (b,s) along k
+        return B * S, K, 1 << 30, 0, K, 1
+    if layout == "inter":  # sequences (b,k) along s
+        return B * K, S, K, S * K, 1, K
+    raise ValueError("layout must be 'intra' or 'inter'")
+
+
+def bilstm_forward(pack: LstmPack, x: torch.Tensor, layout: str, *, save=False, precision="fp32"):
+    """BiLSTM over a channels-last dual-path tensor ``x[B,S,K,64]`` along K (``intra``) or S (``inter``).
+
+    Returns ``(H[B,S,K,256], G, Cst)``; ``G``/``Cst`` hold what :func:`bilstm_backward` needs when ``save``.
+    """
+    require_cuda(x, "x")
+    B, S, K, N = x.shape
+    P = B * S * K
+    G = torch.empty(P, 1024, device=x.device, dtype=torch.float32)
+    H = torch.empty(B, S, K, 256, device=x.device, dtype=torch.float32)
+    Cst = torch.empty(P, 256, device=x.device, dtype=torch.float32) if save else None
+    nseq, ln, qdiv, s_hi, s_lo, s_t = _seq_map(layout, B, S, K)
+    check(
+        lib().dp_bilstm_forward_f32(ptr(pack.buf), ptr(x), ptr(G), ptr(H), ptr(Cst), P, nseq, ln, qdiv, s_hi, s_lo, s_t, int(save),
+                                    _prec(precision), stream_ptr()),
+        "dp_bilstm_forward_f32",
+    )
+    return H, G, Cst
+
+
+def bilstm_backward(pack: LstmPack, G, Cst, dH, shape, layout: str, *, precision="fp32"):
+    """BPTT: ``dH[B,S,K,256]`` -> ``dx[B,S,K,64]``; ``G`` is overwritten with d(pre-activations) (packed column order)."""
+    B, S, K = shape
+    P = B * S * K
+    require_cuda(dH, "dH")
+    dx = torch.empty(B, S, K, 64, device=dH.device, dtype=torch.float32)
+    nseq, ln, qdiv, s_hi, s_lo, s_t = _seq_map(layout, B, S, K)
+    check(
+        lib().dp_bilstm_backward_f32(ptr(pack.buf), ptr(G), ptr(Cst), ptr(dH), ptr(dx), 0, P, nseq, ln, qdiv, s_hi, s_lo, s_t,
+                                     _prec(precision), stream_ptr()),
+        "dp_bilstm_backward_f32",
+    )
+    return dx
+
+
+def groupnorm_residual(y, res, gamma, beta, stats, rows_per_group, eps, *, concat=None):
+    """``res + GroupNorm(1,C)(y)`` on channels-last rows, statistics given as fp64 (sum, sumsq) per group."""
+    require_cuda(y, "y")
+    rows = y.numel() // y.shape[-1]
+    Cc = y.shape[-1]
+    groups = rows // rows_per_group
+    mr = torch.empty(groups, 2, device=y.device, dtype=torch.float32)
+    check(lib().dp_groupnorm_finalize(ptr(stats), ptr(mr), groups, float(rows_per_group * Cc), float(eps), stream_ptr()),
+          "dp_groupnorm_finalize")
+    out = torch.empty_like(y)
+    cw, cb, slope = concat if concat is not None else (None, None, None)
+    check(
+        lib().dp_groupnorm_residual_f32(ptr(y), ptr(res), ptr(out), ptr(mr), ptr(gamma), ptr(beta), rows, rows_per_group, Cc, ptr(cw),
+                                        ptr(cb), ptr(slope), stream_ptr()),
+        "dp_groupnorm_residual_f32",
+    )
+    return out

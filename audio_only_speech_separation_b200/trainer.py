@@ -1,0 +1,87 @@
+"""Fused training step with the semantics of the reference's Lightning step.
+
+Reference: ``AudioLightningModule.training_step`` (look2hear/system/audio_litmodule.py:73-88: forward, PIT loss),
+Lightning's ``backward`` + ``DDPStrategy`` gradient all-reduce (audio_train.py:120-132), ``gradient_clip_val=5.0``
+(audio_train.py:128) and ``torch.optim.Adam(lr=1e-3, weight_decay=0)`` (audio_train.py:48, optimizers.py:58-75).
+
+Everything between the host->device copy of the batch and the loss scalar is engine calls on one stream:
+forward, fused PIT loss (+ its analytic backward), engine backward into ONE flat gradient buffer, one NCCL all-reduce of
+that buffer when a process group is given (one process per GPU, batch sharded by utterance), and a fused
+clip + Adam over the flat parameter buffer.  Like the reference's DDP, the loss mean (and ``threshold_byloss``
+filtering) is per rank and the gradients are averaged over ranks.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from .losses.matrix import PairwiseNegSDR, pit_sdr_forward
+from .losses.pit_wrapper import PITLossWrapper
+
+
+class DualPathTrainer:
+    def __init__(self, model, loss: PITLossWrapper, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=5.0,
+                 process_group=None, distributed=False):
+        if not isinstance(loss, PITLossWrapper) or not isinstance(loss.loss_func, PairwiseNegSDR) or loss.pit_from != "pw_mtx":
+            raise NotImplementedError("DualPathTrainer needs PITLossWrapper(PairwiseNegSDR(...), pit_from='pw_mtx')")
+        self.model, self.loss = model, loss
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.group, self.distributed = process_group, distributed
+        self.step_count = 0
+        self._state_for = None
+        self._ws = None
+        self.launches_per_step = 0
+
+    def _ensure_state(self, device):
+        m = self.model
+        m._sync_flat(device)
+        if self._state_for is not m._flat:
+            n = m._flat.numel()
+            self.exp_avg = torch.zeros(n, device=device)
+            self.exp_avg_sq = torch.zeros(n, device=device)
+            self.gflat = torch.zeros(n, device=device)
+            self.norm2 = torch.zeros(1, device=device, dtype=torch.float64)
+            self._state_for = m._flat
+
+    def world_size(self) -> int:
+        if not self.distributed:
+            return 1
+        import torch.distributed as dist
+
+        return dist.get_world_size(self.group)
+
+    def step(self, mixtures: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        """One optimisation step on a device-resident batch; returns the (device, 0-d) loss of this rank."""
+        m = self.model
+        self._ensure_state(mixtures.device)
+        B, T = mixtures.shape
+        est, self._ws = m._engine_forward(mixtures, True, ws=self._ws)
+        launches = m.last_launches
+        loss, _pw, _perm, lws = pit_sdr_forward(est, targets, self.loss.loss_func.sdr_type, self.loss.threshold_byloss)
+        d_est = torch.empty_like(est)
+        check(lib().dp_pit_loss_backward(ptr(est), ptr(targets), B, T, ptr(lws), 1.0, ptr(d_est), stream_ptr()), "dp_pit_loss_backward")
+        launches += 4 + (1 if self.loss.loss_func.sdr_type == "sisdr" else 0)
+        self.gflat.zero_()
+        m._engine_backward(d_est, self.gflat, self._ws, B, T)
+        launches += m.last_launches
+        gscale = 1.0
+        if self.distributed:
+            import torch.distributed as dist
+
+            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.group)
+            gscale = 1.0 / dist.get_world_size(self.group)
+        self.step_count += 1
+        check(
+            lib().dp_adam_clip_step(ptr(m._flat), ptr(self.gflat), ptr(self.exp_avg), ptr(self.exp_avg_sq), m._flat.numel(),
+                                    ptr(self.norm2), gscale, float(self.max_norm), float(self.lr), float(self.betas[0]),
+                                    float(self.betas[1]), float(self.eps), self.step_count, float(self.weight_decay), stream_ptr()),
+            "dp_adam_clip_step",
+        )
+        m.mark_params_dirty()
+        launches += 2 + 1 + 2 * m.layer  # sumsq + adam, and the re-pack of the weights the next forward triggers
+        self.launches_per_step = launches
+        return loss.reshape(())
+
+    def grad_norm(self) -> torch.Tensor:
+        """Total gradient norm of the last step (after the all-reduce average), as clip_grad_norm_ would report it."""
+        return torch.sqrt(self.norm2) / self.world_size()

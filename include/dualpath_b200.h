@@ -1,0 +1,134 @@
+/* dualpath_b200 -- C-ABI of the B200-native look2hear dual-path separation hot path.
+ *
+ * The reference (spkgyk/audio-only-speech-separation) is pure Python/PyTorch and has no FFI of its own; the seam a
+ * maintainer binds against is "the call each torch.nn module on the path makes".  Every entry point below names
+ * the reference code it replaces (paths relative to the reference repo).  All pointers are DEVICE pointers
+ * (fp32 unless said otherwise), `stream` is a cudaStream_t passed as void*, every call is asynchronous on that
+ * stream, allocates nothing, and returns 0 on success or a non-zero code with a message in dp_last_error().
+ * There is no CPU implementation behind these symbols: without a CUDA device they fail.
+ *
+ * precision: DP_PREC_FP32 -> bf16x3 split products on the tensor cores + precise gate activations
+ *                            (model output within rel-L2 1e-4 of the fp32 reference; measured ~1.5e-5)
+ *            DP_PREC_BF16 -> single bf16 products + tanh.approx activations (within 0.05 dB SI-SNR)
+ */
+#ifndef DUALPATH_B200_H
+#define DUALPATH_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DP_PREC_FP32 0
+#define DP_PREC_BF16 1
+
+int dp_version(void);
+const char* dp_last_error(void);
+
+/* ---- geometry (integer index maps) --------------------------------------------------------------------- */
+/* gc3_basics.py:63-76 pad_segment: rest and chunk count S for L frames and chunk size K (K even). */
+int dp_seg_geometry(int L, int K, int* rest, int* S);
+/* gc3_network.py:108-131 pad_input: samples appended (rest) and number of encoder frames for T samples. */
+int dp_wave_geometry(int T, int win, int* rest, int* frames);
+
+/* ---- (a) segmentation / overlap-add ---------------------------------------------------------------------- */
+/* split_feature, gc3_basics.py:79-91 (== sepformer.py:788-814): x[B,N,L] -> y[B,N,K,S], bit-exact. */
+int dp_segment_f32(const float* x, float* y, int B, int N, int L, int K, void* stream);
+/* merge_feature, gc3_basics.py:94-109 (== sepformer.py:816-846): y[B,N,K,S] -> x[B,N,L], bit-exact. */
+int dp_overlap_add_f32(const float* y, float* x, int B, int N, int K, int S, int L, void* stream);
+/* the same maps on channels-last tensors f[B,L,C] <-> x[B,S,K,C] (layout used inside the engine), C % 4 == 0 */
+int dp_segment_cl_f32(const float* f, float* x, int B, int L, int K, int C, void* stream);
+int dp_overlap_add_cl_f32(const float* x, float* f, int B, int L, int K, int C, void* stream);
+
+/* ---- (b) dense contractions: nn.Linear / 1x1 nn.Conv1d / nn.Conv2d / LSTM input projection -------------- */
+/* C[M,N] (=|+=) A[M,K] W^T (+ bias_scale*bias) (ReLU).  gc3_basics.py:22-23, gc3_network.py:55,99, dprnn.py:85.
+ * W is given as bf16 hi / lo halves (w_lo unused for DP_PREC_BF16); w_kn = 0: W is [N,K], 1: W is [K,N].
+ * stats (optional, fp64 [groups][2]) accumulates (sum, sumsq) of the stored C per group of rows_per_group rows:
+ * the GroupNorm(1,C) statistics of dprnn.py:71,80 come out of the producing GEMM. */
+int dp_linear_f32(const float* A, int64_t lda, const void* w_hi, const void* w_lo, int ldw, int w_kn, const float* bias,
+                  float bias_scale, float* C, int ldc, int M, int N, int K, int relu, int accumulate, double* stats,
+                  int rows_per_group, int precision, void* stream);
+/* dW[Mo,No] += scale * A[P,Mo]^T B[P,No]  (weight gradients; fp32 atomics). */
+int dp_linear_wgrad_f32(const float* A, int lda, const float* B, int64_t ldb, float* dW, int ldc, int P, int Mo, int No,
+                        float scale, int precision, void* stream);
+/* elementwise fp32 -> bf16 hi / lo */
+int dp_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* stream);
+
+/* ---- (c) persistent BiLSTM recurrence: nn.LSTM(64,128,1,bidirectional) of ProjRNN, gc3_basics.py:16,22 -- */
+int64_t dp_lstm_pack_bytes(void);
+/* natural nn.LSTM parameters (weight_ih_l0[512,64], weight_hh_l0[512,128], bias_*[512], and *_reverse) ->
+ * packed forms consumed by the kernels (see csrc/lstm.cu). */
+int dp_lstm_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* w_ih_r,
+                 const float* w_hh_r, const float* b_ih_r, const float* b_hh_r, void* pack, void* stream);
+/* x[P,64] rows at position p; sequence q, time t lives at row (q/qdiv)*s_hi + (q%qdiv)*s_lo + t*s_t.
+ * Computes gates = x W_ih^T + b (into G[P,1024], scratch) and the recurrence; H[P,256] = [h_fwd | h_bwd].
+ * save != 0 keeps activated gates in G and cell states in Cst[P,256] for dp_bilstm_backward_f32. */
+int dp_bilstm_forward_f32(const void* pack, const float* x, float* G, float* H, float* Cst, int64_t P, int nseq, int len,
+                          int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int save, int precision, void* stream);
+/* the recurrence alone on precomputed gate pre-activations G (what dp_bilstm_forward_f32 runs after its GEMM) */
+int dp_lstm_recurrence_f32(const void* pack, float* G, float* H, float* Cst, int nseq, int len, int qdiv, int64_t s_hi,
+                           int64_t s_lo, int64_t s_t, int save, int precision, void* stream);
+/* dH[P,256] -> G becomes d(pre-activations) [P,1024]; dx[P,64] (=|+=) dG W_ih. Weight grads via dp_linear_wgrad_f32. */
+int dp_bilstm_backward_f32(const void* pack, float* G, const float* Cst, const float* dH, float* dx, int accumulate_dx,
+                           int64_t P, int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int precision,
+                           void* stream);
+
+/* ---- (d) fused GroupNorm(1,C) + residual (+ unfold depthwise affine + PReLU), dprnn.py:71-73,80-82,31-34 - */
+int dp_groupnorm_finalize(const double* stats, float* mean_rstd, int groups, double count, double eps, void* stream);
+int dp_groupnorm_residual_f32(const float* y, const float* res, float* out, const float* mean_rstd, const float* gamma,
+                              const float* beta, int64_t rows, int rows_per_group, int C, const float* cw, const float* cb,
+                              const float* prelu_slope, void* stream);
+
+/* ---- (e) fused pairwise SNR / SI-SDR + PIT, losses/matrix.py:13-57, losses/pit_wrapper.py:30-131 ---------- */
+int64_t dp_pit_loss_workspace_bytes(int B);
+/* sdr_type 0 snr, 1 sisdr, 2 sdsdr; n_src = 2.  Outputs: pw[B,2,2] (est,tgt), loss[1], perm[B] (0 identity, 1
+ * swapped).  ws keeps what the backward needs. */
+int dp_pit_loss_forward(const float* est, const float* tgt, int B, int T, int sdr_type, int threshold_byloss, void* ws,
+                        float* pw, float* loss, int32_t* perm, void* stream);
+int dp_pit_loss_backward(const float* est, const float* tgt, int B, int T, const void* ws, float grad_scale, float* d_est,
+                         void* stream);
+/* pit_wrapper.py:90-94 reordered_sources */
+int dp_pit_reorder(const float* est, const int32_t* perm, float* out, int B, int T, void* stream);
+
+/* ---- optimizer step: clip_grad_norm_(max_norm) + Adam, audio_train.py:48,128 ------------------------------ */
+/* norm2: device fp64 scalar (scratch).  grad_scale is applied to g first (1/world_size after all-reduce SUM). */
+int dp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, double* norm2, float grad_scale,
+                      float max_norm, float lr, float beta1, float beta2, float eps, int step, float weight_decay,
+                      void* stream);
+
+/* ---- whole-model engine: TasNet(module="DPRNN").forward, gc3_network.py:133-184 --------------------------- */
+typedef struct dp_tasnet dp_tasnet;
+typedef struct {
+    int enc_dim, bn_dim, hidden_dim, win, layer, num_spk, block_size, unfold;
+} dp_tasnet_config;
+
+/* Parameter table: element offsets into one flat fp32 parameter buffer, in this order:
+ *   0 encoder.weight  1 bottleneck.0.weight  2 bottleneck.0.bias  3 bottleneck.1.weight
+ *   4 seq.output.weight  5 seq.output.bias  6 mask.0.weight  7 mask.0.bias  8 decoder.weight
+ *   9 concat_block.0.weight  10 concat_block.0.bias  11 concat_block.1.weight   (-1 unless unfold)
+ *   then for path pp = 2*layer + (0 row | 1 col), 12 entries at 12 + 12*pp:
+ *   weight_ih, weight_hh, bias_ih, bias_hh, weight_ih_reverse, weight_hh_reverse, bias_ih_reverse,
+ *   bias_hh_reverse, proj.weight, proj.bias, norm.weight, norm.bias
+ * Shared (unfold) parameters simply repeat the same offsets. */
+#define DP_TASNET_HEAD_PARAMS 12
+#define DP_TASNET_PATH_PARAMS 12
+int dp_tasnet_create(const dp_tasnet_config* cfg, const int64_t* offsets, int n_offsets, int64_t n_params, dp_tasnet** out);
+void dp_tasnet_destroy(dp_tasnet* h);
+int64_t dp_tasnet_pack_bytes(const dp_tasnet* h);
+int64_t dp_tasnet_workspace_bytes(const dp_tasnet* h, int B, int T, int train);
+/* rebuild the packed / split weights after the parameters changed */
+int dp_tasnet_pack(dp_tasnet* h, const float* params, void* pack, void* stream);
+/* mixture[B,T] -> est[B,num_spk,T].  train != 0 keeps activations in the workspace for dp_tasnet_backward. */
+int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const float* mixture, float* est, void* workspace,
+                      int B, int T, int train, int precision, void* stream);
+/* d_est[B,num_spk,T] -> grads (flat, same layout as params, ACCUMULATED into). Needs the workspace of the forward. */
+int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, const float* d_est, float* grads, void* workspace,
+                       int B, int T, int precision, void* stream);
+/* number of kernels the last forward / backward call of this handle launched */
+int dp_tasnet_last_launches(const dp_tasnet* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,197 @@
+"""GPU parity tests of the whole path: drop-in TasNet forward/backward and the fused training step."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_npz, record, rel_l2
+from oracle import dualpath_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4      # rel-L2, BASELINE.json north_star
+BF16_TOL_DB = 0.05   # |delta PIT SI-SNR| in dB, BASELINE.json north_star
+
+
+def _model(manifest, case, precision="fp32"):
+    from audio_only_speech_separation_b200.models import TasNet
+
+    c = manifest["cases"][case]
+    torch.manual_seed(c["seed"])
+    m = TasNet(sample_rate=c["sample_rate"], **c["audionet_config"])
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda().eval()
+    m.precision = precision
+    return m, sd, c
+
+
+@pytest.mark.parametrize("case", ["dprnn_wsj0_b2_t8001", "dprnn_wsj0_b1_t32000", "dprnn_wsj0_1d_t4000", "dprnn_wsj0_3d_t1234",
+                                  "dprnn_unfold_b2_t8000"])
+def test_forward_matches_reference_golden(manifest, case):
+    m, _, _ = _model(manifest, case)
+    z = load_npz(f"model_{case}.npz")
+    with torch.no_grad():
+        y = m(torch.from_numpy(z["x"]).cuda())
+    ref = torch.from_numpy(z["y"])
+    assert tuple(y.shape) == tuple(ref.shape)
+    err = rel_l2(y, ref)
+    record("model_fwd_fp32", case=case, rel_l2=err, launches=m.last_launches)
+    assert err < FP32_TOL
+
+
+def test_forward_bf16_within_si_snr_budget(manifest):
+    """bf16 mode on structured input (mixture = s1 + s2): PIT SI-SNR within 0.05 dB of the fp32 reference output."""
+    m, sd, c = _model(manifest, "dprnn_wsj0_b2_t8001", precision="bf16")
+    g = torch.Generator().manual_seed(21)
+    src = torch.randn(2, 2, 16000, generator=g) * 0.1
+    mix = src.sum(1)
+    with torch.no_grad():
+        ref = O.tasnet_forward(sd, mix)
+        y = m(mix.cuda()).cpu()
+    si_ref = -O.pit_loss(ref, src, "sisdr", False).item()
+    si_new = -O.pit_loss(y, src, "sisdr", False).item()
+    proxy = -O.pairwise_neg_sdr(y, ref, "sisdr").diagonal(dim1=1, dim2=2).mean().item()  # SI-SDR(new || ref)
+    record("model_fwd_bf16", si_ref=si_ref, si_new=si_new, si_sdr_vs_ref=proxy, rel_l2=rel_l2(y, ref))
+    assert abs(si_new - si_ref) <= BF16_TOL_DB
+    assert proxy > 30.0
+
+
+def test_forward_odd_lengths_and_batch_independence(manifest):
+    m, sd, _ = _model(manifest, "dprnn_wsj0_b2_t8001")
+    g = torch.Generator().manual_seed(4)
+    for T in (1, 17, 801, 3999):
+        x = torch.randn(3, T, generator=g) * 0.1
+        with torch.no_grad():
+            y = m(x.cuda()).cpu()
+            ref = O.tasnet_forward(sd, x)
+        assert tuple(y.shape) == (3, 2, T)
+        assert rel_l2(y, ref) < FP32_TOL, T
+    x = torch.randn(4, 4000, generator=g) * 0.1
+    with torch.no_grad():
+        full = m(x.cuda())
+        single = torch.cat([m(x[i : i + 1].cuda()) for i in range(4)])
+    assert rel_l2(full, single) < 1e-5  # utterances are independent: the property data-parallel sharding relies on
+
+
+def test_state_dict_round_trip_keeps_engine_in_sync(manifest):
+    m, sd, c = _model(manifest, "dprnn_wsj0_b2_t8001")
+    x = torch.randn(1, 2000).cuda() * 0.1
+    with torch.no_grad():
+        y0 = m(x)
+        torch.manual_seed(123)
+        from audio_only_speech_separation_b200.models import TasNet
+
+        other = TasNet(sample_rate=c["sample_rate"], **c["audionet_config"])
+        m.load_state_dict(other.state_dict())
+        y1 = m(x)
+        ref = O.tasnet_forward({k: v.detach() for k, v in other.state_dict().items()}, x.cpu())
+    assert rel_l2(y1, ref) < FP32_TOL and rel_l2(y1, y0) > 1e-2
+
+
+@pytest.mark.parametrize("case", ["dprnn_wsj0_b2_t8001", "dprnn_unfold_b2_t8000"])
+def test_gradients_match_oracle_autograd(manifest, case):
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+
+    m, sd, c = _model(manifest, case)
+    m.train()
+    z = load_npz("grads_dprnn_wsj0.npz")
+    x, tgt = torch.from_numpy(z["x"]), torch.from_numpy(z["tgt"])
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ac = c["audionet_config"]
+    ref_loss = O.pit_loss(O.tasnet_forward(leaf, x, unfold=ac["unfold"]), tgt, "snr", False)
+    ref_loss.backward()
+    loss = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)(m(x.cuda()), tgt.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-4 * max(1.0, abs(ref_loss.item()))
+    named = dict(m.named_parameters())
+    worst, worst_key, tot_num, tot_den = 0.0, None, 0.0, 0.0
+    for k, p in named.items():
+        assert p.grad is not None, k
+        gr = leaf[k].grad
+        e = rel_l2(p.grad, gr)
+        tot_num += float((p.grad.cpu().double() - gr.double()).pow(2).sum())
+        tot_den += float(gr.double().pow(2).sum())
+        if e > worst:
+            worst, worst_key = e, k
+    total = (tot_num / tot_den) ** 0.5
+    record("model_grads", case=case, worst_rel_l2=worst, worst_key=worst_key, total_rel_l2=total, loss=loss.item())
+    assert total < 1e-4
+    assert worst < 2e-3, worst_key
+    if case == "dprnn_wsj0_b2_t8001":  # the same gradients straight from the reference (golden)
+        for key in z.files:
+            if key.startswith("grad::"):
+                assert rel_l2(named[key[6:]].grad, torch.from_numpy(z[key])) < 2e-3, key
+
+
+def test_fused_training_steps_track_reference_semantics(manifest):
+    """3 steps of the fused trainer (fwd + PIT-SNR + bwd + clip 5.0 + Adam 1e-3) vs the oracle's restatement."""
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+    from audio_only_speech_separation_b200.trainer import DualPathTrainer
+
+    m, sd, c = _model(manifest, "dprnn_wsj0_b2_t8001")
+    m.train()
+    tr = DualPathTrainer(m, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False), lr=1e-3, max_norm=5.0)
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 4000, generator=g) * 0.1
+    tgt = torch.randn(2, 2, 4000, generator=g) * 0.1
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    keys = [k for k, _ in m.named_parameters()]
+    ea = [torch.zeros_like(params[k]) for k in keys]
+    es = [torch.zeros_like(params[k]) for k in keys]
+    for step in range(1, 4):
+        loss = tr.step(x.cuda(), tgt.cuda())
+        ref = O.pit_loss(O.tasnet_forward(params, x), tgt, "snr", False)
+        for p in params.values():
+            p.grad = None
+        ref.backward()
+        with torch.no_grad():
+            total = O.adam_clip_step([params[k] for k in keys], [params[k].grad for k in keys], ea, es, step)
+        record("train_step", step=step, loss=loss.item(), ref_loss=ref.item(), gnorm=float(tr.grad_norm()), ref_gnorm=total)
+        assert abs(loss.item() - ref.item()) < 2e-3 * max(1.0, abs(ref.item()))
+        assert abs(float(tr.grad_norm()) - total) < 2e-3 * total
+    new_sd = m.state_dict()
+    worst = max(rel_l2(new_sd[k], params[k].detach()) for k in keys)
+    record("train_params_after_3_steps", worst_rel_l2=worst)
+    assert worst < 5e-3
+
+
+def test_torch_optimizer_drop_in(manifest):
+    """The reference's own recipe (torch Adam + clip_grad_norm_ on model.parameters()) works on the drop-in model."""
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+
+    m, sd, _ = _model(manifest, "dprnn_wsj0_b2_t8001")
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    lossf = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)
+    g = torch.Generator().manual_seed(8)
+    x = (torch.randn(2, 2000, generator=g) * 0.1).cuda()
+    tgt = (torch.randn(2, 2, 2000, generator=g) * 0.1).cuda()
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = lossf(m(x), tgt)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+        opt.step()
+        losses.append(loss.item())
+    assert losses[2] < losses[0]
+    assert m._flat_is_valid(x.device)  # parameters are still views of the flat buffer after optimizer steps
+
+
+def test_full_size_training_batch_properties(manifest):
+    """BASELINE training shape (B=16, T=32000): finite outputs, per-utterance independence at full size."""
+    m, _, _ = _model(manifest, "dprnn_wsj0_b2_t8001")
+    g = torch.Generator().manual_seed(1234)
+    x = (torch.randn(16, 32000, generator=g) * 0.1).cuda()
+    with torch.no_grad():
+        y = m(x)
+        y3 = m(x[3:4])
+    assert tuple(y.shape) == (16, 2, 32000) and bool(torch.isfinite(y).all())
+    assert rel_l2(y[3:4], y3) < 1e-5
+    z = load_npz("model_dprnn_wsj0_b1_t32000.npz")
+    x2 = x.clone()
+    x2[5] = torch.from_numpy(z["x"][0]).cuda()
+    with torch.no_grad():
+        y2 = m(x2)
+    assert rel_l2(y2[5], torch.from_numpy(z["y"][0])) < FP32_TOL  # golden utterance embedded in a full batch

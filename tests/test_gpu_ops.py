@@ -1,0 +1,289 @@
+"""GPU parity tests of the individual kernels, through the C-ABI, against the CPU oracle and the golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_npz, record, rel_l2
+from oracle import dualpath_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4  # rel-L2 gate of BASELINE.json north_star for fp32 mode
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from audio_only_speech_separation_b200 import ops as _ops
+
+    return _ops
+
+
+# ------------------------------------------------------------------------------- (a) segmentation / overlap-add
+def test_segment_overlap_add_golden_bit_exact(ops):
+    z = load_npz("seg_ola.npz")
+    for i in range(int(z["n"])):
+        L, K, rest, S = [int(v) for v in z[f"meta{i}"]]
+        x, blk, y, mrg = (torch.from_numpy(z[f"{k}{i}"]).cuda() for k in ("x", "blk", "y", "mrg"))
+        out, r = ops.split_feature(x, K)
+        assert r == rest and tuple(out.shape) == tuple(blk.shape)
+        assert torch.equal(out, blk), (L, K)
+        assert torch.equal(ops.merge_feature(y, rest), mrg), (L, K)
+
+
+@pytest.mark.parametrize("B,N,L,K", [(3, 5, 4002, 100), (2, 4, 15999, 250), (1, 3, 31999, 250), (2, 64, 1999, 100), (1, 1, 1, 2),
+                                     (2, 2, 63, 64), (1, 2, 4000, 100), (1, 2, 5000, 2000)])
+def test_segment_overlap_add_vs_oracle(ops, B, N, L, K):
+    g = torch.Generator().manual_seed(L + K)
+    x = torch.randn(B, N, L, generator=g)
+    ref, rest = O.split_feature(x, K)
+    out, r = ops.split_feature(x.cuda(), K)
+    assert r == rest and torch.equal(out.cpu(), ref)
+    y = torch.randn(ref.shape, generator=g)
+    assert torch.equal(ops.merge_feature(y.cuda(), rest).cpu(), O.merge_feature(y, rest))
+    # channels-last variants used inside the engine
+    f = x.permute(0, 2, 1).contiguous().cuda()
+    xcl = ops.segment_channels_last(torch.cat([f] * 4, dim=2), K)  # C multiple of 4
+    assert torch.equal(xcl[..., :N].permute(0, 3, 2, 1).cpu(), ref)
+    ycl = torch.cat([y.permute(0, 3, 2, 1)] * 4, dim=3).contiguous().cuda()
+    fcl = ops.overlap_add_channels_last(ycl, L)
+    assert torch.equal(fcl[..., :N].permute(0, 2, 1).cpu(), O.merge_feature(y, rest))
+
+
+def test_segment_full_size_round_trip(ops):
+    """BASELINE size (B=16 utterances of 4 s): merge(split(x)) == 2x exactly, and padding positions are zero."""
+    x = torch.randn(16, 64, 4002, device="cuda")
+    blk, rest = ops.split_feature(x, 100)
+    assert tuple(blk.shape) == (16, 64, 100, 82) and rest == 48
+    assert torch.equal(ops.merge_feature(blk, rest), 2 * x)
+    assert float(blk[:, :, :50, 0].abs().max()) == 0.0  # leading half chunk is padding
+    assert float(blk.double().sum()) == pytest.approx(2 * float(x.double().sum()), rel=1e-9)
+
+
+def test_segment_rejects_bad_arguments(ops):
+    from audio_only_speech_separation_b200._lib import DualPathError
+
+    with pytest.raises(DualPathError):
+        ops.split_feature(torch.randn(1, 2, 100, device="cuda"), 25)
+    with pytest.raises(ValueError):
+        ops.split_feature(torch.randn(2, 100, device="cuda"), 100)
+
+
+# ------------------------------------------------------------------------------- (b) GEMMs
+@pytest.mark.parametrize("M,N,K,w_kn,relu", [(1000, 64, 64, False, False), (777, 1024, 64, False, False), (513, 64, 256, False, True),
+                                            (300, 16, 64, True, False), (4002, 128, 64, False, True), (260, 256, 64, True, False),
+                                            (129, 64, 1024, True, False)])
+def test_linear_fp32_parity(ops, M, N, K, w_kn, relu):
+    g = torch.Generator().manual_seed(M)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K**0.5
+    b = torch.randn(N, generator=g)
+    ref = a.double() @ w.double().t() + b.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    wd = (w.t().contiguous() if w_kn else w).cuda()
+    out = ops.linear(a.cuda(), wd, b.cuda(), w_kn=w_kn, relu=relu)
+    err = rel_l2(out, ref)
+    record("linear_fp32", M=M, N=N, K=K, w_kn=w_kn, rel_l2=err)
+    assert err < 2e-5
+    out16 = ops.linear(a.cuda(), wd, b.cuda(), w_kn=w_kn, relu=relu, precision="bf16")
+    assert rel_l2(out16, ref) < 2e-2
+
+
+def test_linear_accumulate_stats_and_frames(ops):
+    g = torch.Generator().manual_seed(3)
+    # overlapping frames (encoder Conv1d as a GEMM): rows at stride 8, K = 16
+    x = torch.randn(8 * 501, generator=g)
+    w = torch.randn(64, 16, generator=g)
+    frames = x.unfold(0, 16, 8)
+    out = ops.linear(x.cuda(), w.cuda(), None, lda=8, rows=frames.shape[0])
+    assert rel_l2(out, frames.double() @ w.double().t()) < 2e-5
+    # accumulate + per-group statistics
+    a = torch.randn(600, 64, generator=g)
+    w2 = torch.randn(64, 64, generator=g)
+    base = torch.randn(600, 64, generator=g)
+    stats = torch.zeros(3, 2, dtype=torch.float64, device="cuda")
+    out = ops.linear(a.cuda(), w2.cuda(), None, out=base.clone().cuda(), accumulate=True, stats=stats, rows_per_group=200)
+    ref = base.double() + a.double() @ w2.double().t()
+    assert rel_l2(out, ref) < 2e-5
+    rs = torch.stack([ref.reshape(3, -1).sum(1), (ref.reshape(3, -1) ** 2).sum(1)], dim=1)
+    assert torch.allclose(stats.cpu(), rs, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("P,Mo,No", [(5000, 64, 256), (3000, 1024, 64), (1111, 512, 128), (4002, 64, 16)])
+def test_linear_wgrad(ops, P, Mo, No):
+    g = torch.Generator().manual_seed(P)
+    a = torch.randn(P, Mo, generator=g)
+    b = torch.randn(P, No, generator=g)
+    out = torch.zeros(Mo, No, device="cuda")
+    ops.linear_wgrad(a.cuda(), b.cuda(), out)
+    err = rel_l2(out, a.double().t() @ b.double())
+    record("linear_wgrad", P=P, Mo=Mo, No=No, rel_l2=err)
+    assert err < 2e-5
+
+
+# ------------------------------------------------------------------------------- (c) persistent BiLSTM
+def _lstm_and_pack(ops, seed=0):
+    torch.manual_seed(seed)
+    lstm = torch.nn.LSTM(64, 128, 1, batch_first=True, bidirectional=True)
+    sd = {"rnn." + k: v.detach() for k, v in lstm.state_dict().items()}
+    return lstm, sd, ops.LstmPack(lstm.cuda())
+
+
+def _oracle_bilstm(x, sd, layout, impl="aten"):
+    B, S, K, N = x.shape
+    if layout == "intra":
+        return O.bilstm(x.reshape(B * S, K, N), sd, "rnn.", impl).reshape(B, S, K, 256)
+    xi = x.permute(0, 2, 1, 3).reshape(B * K, S, N)
+    return O.bilstm(xi, sd, "rnn.", impl).reshape(B, K, S, 256).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("layout", ["intra", "inter"])
+@pytest.mark.parametrize("B,S,K", [(2, 6, 10), (1, 82, 100), (16, 82, 20), (3, 14, 100)])
+def test_bilstm_forward_parity(ops, layout, B, S, K):
+    lstm, sd, pack = _lstm_and_pack(ops)
+    g = torch.Generator().manual_seed(B * 1000 + S)
+    x = torch.randn(B, S, K, 64, generator=g)
+    with torch.no_grad():
+        ref = _oracle_bilstm(x, sd, layout)
+    H, _, _ = ops.bilstm_forward(pack, x.cuda(), layout)
+    err = rel_l2(H, ref)
+    record("bilstm_fwd_fp32", layout=layout, B=B, S=S, K=K, rel_l2=err)
+    assert err < 2e-5
+    H16, _, _ = ops.bilstm_forward(pack, x.cuda(), layout, precision="bf16")
+    err16 = rel_l2(H16, ref)
+    record("bilstm_fwd_bf16", layout=layout, B=B, S=S, K=K, rel_l2=err16)
+    assert err16 < 3e-2
+
+
+@pytest.mark.parametrize("layout", ["intra", "inter"])
+@pytest.mark.parametrize("B,S,K", [(2, 6, 10), (16, 82, 12)])
+def test_bilstm_backward_parity(ops, layout, B, S, K):
+    lstm, sd, pack = _lstm_and_pack(ops, seed=1)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, S, K, 64, generator=g)
+    dH = torch.randn(B, S, K, 256, generator=g)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    ref = _oracle_bilstm(xr, leaf, layout, impl="loop")
+    ref.backward(dH)
+    H, G, Cst = ops.bilstm_forward(pack, x.cuda(), layout, save=True)
+    assert rel_l2(H, ref.detach()) < 2e-5
+    dx = ops.bilstm_backward(pack, G, Cst, dH.cuda(), (B, S, K), layout)
+    err = rel_l2(dx, xr.grad)
+    record("bilstm_bwd_dx", layout=layout, B=B, S=S, K=K, rel_l2=err)
+    assert err < 5e-5
+    # weight gradient of the input projection from the d(pre-activation) buffer (packed row order u*4 + gate)
+    dW = torch.zeros(1024, 64, device="cuda")
+    ops.linear_wgrad(G, x.reshape(-1, 64).cuda(), dW)
+    perm = torch.tensor([(r % 4) * 128 + r // 4 for r in range(512)])
+    for d, name in enumerate(["rnn.weight_ih_l0", "rnn.weight_ih_l0_reverse"]):
+        got = torch.empty(512, 64)
+        got[perm] = dW[d * 512 : (d + 1) * 512].cpu()
+        e = rel_l2(got, leaf[name].grad)
+        record("bilstm_bwd_dwih", layout=layout, dir=d, rel_l2=e)
+        assert e < 5e-5
+    db = G.double().sum(0).cpu()
+    for d, name in enumerate(["rnn.bias_ih_l0", "rnn.bias_ih_l0_reverse"]):
+        got = torch.empty(512, dtype=torch.float64)
+        got[perm] = db[d * 512 : (d + 1) * 512]
+        assert rel_l2(got, leaf[name].grad) < 5e-5
+
+
+# ------------------------------------------------------------------------------- (d) GroupNorm + residual
+@pytest.mark.parametrize("unfold", [False, True])
+def test_groupnorm_residual(ops, unfold):
+    g = torch.Generator().manual_seed(11)
+    B, P, C = 3, 700, 64
+    y = torch.randn(B * P, C, generator=g) * 2 + 0.3
+    res = torch.randn(B * P, C, generator=g)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    stats = torch.stack([y.double().reshape(B, -1).sum(1), (y.double().reshape(B, -1) ** 2).sum(1)], dim=1).cuda()
+    ref = res + O.group_norm1(y.reshape(B, P, C).permute(0, 2, 1), gamma, beta, 1e-8).permute(0, 2, 1).reshape(B * P, C)
+    concat = None
+    if unfold:
+        cw, cb, sl = torch.randn(C, generator=g), torch.randn(C, generator=g), torch.tensor([0.25])
+        ref = O.prelu(ref * cw + cb, sl)
+        concat = (cw.cuda(), cb.cuda(), sl.cuda())
+    out = ops.groupnorm_residual(y.cuda(), res.cuda(), gamma.cuda(), beta.cuda(), stats, P, 1e-8, concat=concat)
+    assert rel_l2(out, ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------- (e) fused PIT loss
+def _losses():
+    from audio_only_speech_separation_b200 import losses
+
+    return losses
+
+
+def test_pit_loss_golden():
+    L = _losses()
+    z = load_npz("loss.npz")
+    e, t = torch.from_numpy(z["ests"]).cuda(), torch.from_numpy(z["targets"]).cuda()
+    fns = {"snr": L.pairwise_neg_snr, "sisdr": L.pairwise_neg_sisdr, "sdsdr": L.pairwise_neg_sdsdr}
+    for s, fn in fns.items():
+        pw = fn(e, t).cpu()
+        ref = torch.from_numpy(z[f"pw_{s}"])
+        assert torch.allclose(pw, ref, rtol=1e-4, atol=2e-3), (s, (pw - ref).abs().max())
+        for thr in (0, 1):
+            loss, reordered = L.PITLossWrapper(fn, pit_from="pw_mtx", threshold_byloss=bool(thr))(e, t, return_ests=True)
+            assert abs(loss.item() - float(z[f"loss_{s}_{thr}"])) < 1e-3 * max(1.0, abs(float(z[f"loss_{s}_{thr}"])))
+            perm = torch.from_numpy(z[f"perm_{s}"])
+            expect = torch.stack([ee[p] for ee, p in zip(e.cpu(), perm)])
+            assert torch.equal(reordered.cpu(), expect)
+
+
+@pytest.mark.parametrize("sdr", ["snr", "sisdr", "sdsdr"])
+@pytest.mark.parametrize("thr", [False, True])
+def test_pit_loss_gradient(sdr, thr):
+    L = _losses()
+    g = torch.Generator().manual_seed(5)
+    B, T = 5, 3001
+    t = torch.randn(B, 2, T, generator=g)
+    e = torch.randn(B, 2, T, generator=g) * 0.5 + 0.1
+    e[1] = t[1].flip(0) + 0.05 * torch.randn(2, T, generator=g)
+    e[2] = t[2] + 1e-3 * torch.randn(2, T, generator=g)
+    er = e.clone().requires_grad_(True)
+    ref = O.pit_loss(er, t, sdr, thr)
+    ref.backward()
+    ec = e.clone().cuda().requires_grad_(True)
+    fn = {"snr": L.pairwise_neg_snr, "sisdr": L.pairwise_neg_sisdr, "sdsdr": L.pairwise_neg_sdsdr}[sdr]
+    loss = L.PITLossWrapper(fn, pit_from="pw_mtx", threshold_byloss=thr)(ec, t.cuda())
+    (loss * 3.0).backward()
+    assert abs(loss.item() - ref.item()) < 1e-4 * max(1.0, abs(ref.item()))
+    err = rel_l2(ec.grad / 3.0, er.grad)
+    record("pit_loss_grad", sdr=sdr, thr=thr, rel_l2=err)
+    assert err < 1e-4
+
+
+def test_pit_loss_full_size_properties():
+    """B=16 x 4 s: permutation/scale invariances that do not need the oracle."""
+    L = _losses()
+    g = torch.Generator().manual_seed(9)
+    t = torch.randn(16, 2, 32000, generator=g).cuda()
+    e = (t + 0.3 * torch.randn(16, 2, 32000, generator=g).cuda())
+    w = L.PITLossWrapper(L.pairwise_neg_sisdr, pit_from="pw_mtx", threshold_byloss=False)
+    a = w(e, t).item()
+    assert abs(w(e.flip(1).contiguous(), t).item() - a) < 1e-4  # permutation invariant
+    assert abs(w(e * 3.7, t).item() - a) < 1e-3                  # SI-SDR is scale invariant
+    assert abs(w(e + 0.5, t).item() - a) < 1e-3                  # zero-mean
+    snr = 10 * np.log10(1 / 0.09)
+    assert abs(-a - snr) < 0.2
+
+
+# ------------------------------------------------------------------------------- optimizer
+def test_adam_clip_matches_oracle():
+    from audio_only_speech_separation_b200._lib import check, lib, ptr, stream_ptr
+
+    g = torch.Generator().manual_seed(2)
+    n = 100_003
+    p0 = torch.randn(n, generator=g)
+    p_ref, m_ref, v_ref = [p0.clone()], [torch.zeros(n)], [torch.zeros(n)]
+    p, m, v = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    norm2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g) * (0.001 if step == 2 else 0.1)  # step 2 is below the clip threshold
+        total = O.adam_clip_step(p_ref, [grad.clone()], m_ref, v_ref, step)
+        check(lib().dp_adam_clip_step(ptr(p), ptr(grad.cuda()), ptr(m), ptr(v), n, ptr(norm2), 1.0, 5.0, 1e-3, 0.9, 0.999, 1e-8, step, 0.0,
+                                      stream_ptr()))
+        assert abs(float(norm2.sqrt()) - total) < 1e-4 * total
+        assert torch.allclose(p.cpu(), p_ref[0], rtol=1e-5, atol=1e-6)
