@@ -406,7 +406,7 @@ int dp_tasnet_create(const dp_tasnet_config* cfg, const int64_t* offsets, int n_
     for (int i = 0; i < n_offsets; ++i) {
         bool optional = (i >= 9 && i <= 11) && !cfg->unfold;
         if (!optional && (offsets[i] < 0 || offsets[i] >= n_params)) return fail("dp_tasnet_create: offset %d out of range", i);
-        if (!optional && (offsets[i] & 3)) return fail("dp_tasnet_create: parameter %d is not 16-byte aligned in the flat buffer", i);
+        if (!optional && (offsets[i] & 7)) return fail("dp_tasnet_create: parameter %d must start at a multiple of 8 elements in the flat buffer", i);
     }
     dp_tasnet* h = new (std::nothrow) dp_tasnet();
     if (!h) return fail("dp_tasnet_create: out of host memory");

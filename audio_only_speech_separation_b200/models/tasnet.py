@@ -224,7 +224,7 @@ class TasNet(BaseModel):
             seen[id(p)] = total
             uniq.append(p)
             offs.append(total)
-            total += (p.numel() + 3) // 4 * 4  # keep every parameter 16-byte aligned
+            total += (p.numel() + 7) // 8 * 8  # 32-byte aligned: the bf16 copies are read as 16-byte vectors
         flat = torch.zeros(total, device=device, dtype=torch.float32)
         with torch.no_grad():
             for p, o in zip(uniq, offs):

