@@ -212,11 +212,11 @@ int dp_lstm_recurrence_f32(const void* pack, float* G, float* H, float* Cst, int
     CK(launch_lstm_fwd(v.rec, G, H, Cst, m, is_split(precision), save != 0, S(stream)));
     return 0;
 }
-int dp_bilstm_backward_f32(const void* pack, float* G, const float* Cst, const float* dH, float* dx, int accumulate_dx, int64_t P,
-                           int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int precision, void* stream) {
+int dp_bilstm_backward_f32(const void* pack, float* G, const float* Cst, const float* dH, float* dx, int accumulate_dx, float* dbias,
+                           int64_t P, int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int precision, void* stream) {
     LstmPackView v = view_pack(pack);
     SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
-    CK(launch_lstm_bwd(v.rec, G, Cst, dH, m, is_split(precision), S(stream)));
+    CK(launch_lstm_bwd(v.rec, G, Cst, dH, dbias, m, is_split(precision), S(stream)));
     if (dx) {
         GemmNtArgs a = nt_args(G, 2 * kG, v.wih_hi, v.wih_lo, kN, 1, dx, kN, (int)P, kN, 2 * kG);
         a.accumulate = accumulate_dx;
@@ -293,7 +293,7 @@ int make_geo(const dp_tasnet* h, int B, int T, Geo& g) {
     g.P = g.Sc * g.K;
     g.PT = (long long)B * g.P;
     g.BL = (long long)B * g.L;
-    if (g.PT * 1024 > 0x7fffffffffLL || g.PT > 0x7fffffffLL / 4) return fail("batch too large for 32-bit position indexing");
+    if (g.PT * 256 >= 0xffffffffLL) return fail("batch too large for 32-bit position indexing");
     return 0;
 }
 
@@ -613,7 +613,7 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
             CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[9], nullptr, st)); ++nl;
         }
         // BPTT: G (activated gates) -> d(pre-activations)
-        CK(launch_lstm_bwd(v.rec, G, at<float>(ws, l.Cst[pp]), dH, m, sp, st)); ++nl;
+        CK(launch_lstm_bwd(v.rec, G, at<float>(ws, l.Cst[pp]), dH, dpk + 65536 + 131072, m, sp, st)); ++nl;
         // input projection: dX += dG W_ih ; dW_ih += dG^T X ; dW_hh += dG^T h_prev ; db += colsum(dG)   (packed row order)
         {
             GemmNtArgs a = nt_args(G, 1024, v.wih_hi, v.wih_lo, 64, 1, dXs, 64, PTi, 64, 1024);
@@ -628,7 +628,6 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
                 r.tmod = m.len;
                 CK(launch_gemm_tn(r, sp, st)); ++nl;
             }
-            CK(launch_colsum(G, 1024, PTi, 1024, 1.f, dpk + 65536 + 131072, nullptr, st)); ++nl;
         }
     }
     // ---- segmentation backward = overlap-add ; bottleneck conv ; bottleneck GroupNorm ; encoder

@@ -120,16 +120,21 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(const GemmNtArgs p) {
                     bl[2 * np][0] = r[0]; bl[2 * np][1] = r[1]; bl[2 * np + 1][0] = r[2]; bl[2 * np + 1][1] = r[3];
                 }
             }
+            // one sweep per split product so that consecutive HMMAs hit different accumulators
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    mma_bf16(acc[mt][nt], ahi[mt], bh[nt]);
-                    if (SPLIT) {
-                        mma_bf16(acc[mt][nt], ahi[mt], bl[nt]);
-                        mma_bf16(acc[mt][nt], alo[mt], bh[nt]);
-                    }
-                }
+                for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[mt][nt], ahi[mt], bh[nt]);
+            if (SPLIT) {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[mt][nt], ahi[mt], bl[nt]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[mt][nt], alo[mt], bh[nt]);
+            }
         }
         __syncthreads();
     }
@@ -280,13 +285,17 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const GemmTnArgs p) {
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    mma_bf16(acc[mt][nt], ahi[mt], bh[nt]);
-                    if (SPLIT) {
-                        mma_bf16(acc[mt][nt], ahi[mt], bl[nt]);
-                        mma_bf16(acc[mt][nt], alo[mt], bh[nt]);
-                    }
-                }
+                for (int nt = 0; nt < 2; ++nt) mma_bf16(acc[mt][nt], ahi[mt], bh[nt]);
+            if (SPLIT) {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) mma_bf16(acc[mt][nt], ahi[mt], bl[nt]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) mma_bf16(acc[mt][nt], alo[mt], bh[nt]);
+            }
         }
         __syncthreads();
     }
@@ -302,16 +311,35 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const GemmTnArgs p) {
             }
 }
 
-constexpr int CS_ROWS = 512;
+constexpr int CS_ROWS = 256;
+// out[n] += scale * sum_p A[p, n]: 256 threads = (256 / C4) row lanes x C4 float4 columns; coalesced 128-bit loads,
+// shared-memory reduction over the row lanes, one atomic per column per CTA.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int lda, int P, int N, float scale,
                                                      float* out, float* out2) {
+    __shared__ float4 sh[256];
+    const int C4 = N >> 2, lanes = 256 / C4;
+    const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4;
     const int pbeg = blockIdx.x * CS_ROWS, pend = min(P, pbeg + CS_ROWS);
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        float s = 0.f;
-        for (int r = pbeg; r < pend; ++r) s += A[(size_t)r * lda + n];
-        s *= scale;
-        atomicAdd(out + n, s);
-        if (out2) atomicAdd(out2 + n, s);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < lanes)
+        for (int r = pbeg + rl; r < pend; r += lanes) {
+            float4 v = ldg_stream(reinterpret_cast<const float4*>(A + (size_t)r * lda) + c4);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < C4) {
+        float4 t = sh[threadIdx.x];
+        for (int l = 1; l < lanes; ++l) {
+            float4 v = sh[l * C4 + threadIdx.x];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        float* o = out + threadIdx.x * 4;
+        atomicAdd(o, t.x * scale); atomicAdd(o + 1, t.y * scale); atomicAdd(o + 2, t.z * scale); atomicAdd(o + 3, t.w * scale);
+        if (out2) {
+            o = out2 + threadIdx.x * 4;
+            atomicAdd(o, t.x * scale); atomicAdd(o + 1, t.y * scale); atomicAdd(o + 2, t.z * scale); atomicAdd(o + 3, t.w * scale);
+        }
     }
 }
 
@@ -339,6 +367,7 @@ cudaError_t launch_gemm_tn(const GemmTnArgs& a, bool split, cudaStream_t st) {
 
 cudaError_t launch_colsum(const float* A, int lda, int P, int N, float scale, float* out, float* out2, cudaStream_t st) {
     if (P <= 0) return cudaSuccess;
+    if ((N & 3) || N > 1024 || 256 % (N / 4) || (lda & 3)) return cudaErrorInvalidValue;
     colsum_kernel<<<ceil_div(P, CS_ROWS), 256, 0, st>>>(A, lda, P, N, scale, out, out2);
     return cudaGetLastError();
 }

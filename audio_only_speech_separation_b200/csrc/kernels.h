@@ -66,7 +66,8 @@ struct LstmPack {  // per ProjRNN, both directions
 cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save,
                             cudaStream_t st);
 // dH: [P,256] incoming gradient of H.  G holds activated gates on entry and d(pre-activations) on exit.
-cudaError_t launch_lstm_bwd(const LstmPack& w, float* G, const float* Cst, const float* dH, const SeqMap& m, bool split,
+// dbias (optional, [1024] packed order) accumulates sum_p dG[p,:] (the bias gradient) inside the same kernel.
+cudaError_t launch_lstm_bwd(const LstmPack& w, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,
                             cudaStream_t st);
 
 // Build all packed forms of one ProjRNN's LSTM weights from the natural fp32 parameters.

@@ -48,6 +48,23 @@ __device__ __forceinline__ void load_b_frags(const __nv_bfloat16* base, int stri
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+constexpr int GST = kG + 4;  // staged gate-tile row stride (floats): 2064 B keeps the float4 reads conflict-free
+
+// Position bases of the tile's sequences -> shared memory (invalid sequences alias the tile's first one: their
+// loads are harmless and their stores are suppressed).
+__device__ __forceinline__ void fill_seq_bases(int* sbase, int NS, int q0, const SeqMap& m) {
+    for (int i = threadIdx.x; i < NS; i += blockDim.x) {
+        int q = q0 + i;
+        if (q >= m.nseq) q = q0;
+        sbase[i] = (int)((q / m.qdiv) * m.s_hi + (q % m.qdiv) * m.s_lo);
+    }
+}
+
 template <int NT, bool SPLIT, bool SAVE>
 __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, float* __restrict__ G, float* __restrict__ H,
                                                           float* __restrict__ Cst, const SeqMap m) {
@@ -56,6 +73,8 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
     uint4* alo = reinterpret_cast<uint4*>(smem);
     __nv_bfloat16* hs_hi = reinterpret_cast<__nv_bfloat16*>(smem + (SPLIT ? ALO_BYTES : 0));
     __nv_bfloat16* hs_lo = hs_hi + NS * HST;
+    float* gs = reinterpret_cast<float*>(hs_lo + NS * HST);  // [NS][GST] gate pre-activations of the current step
+    int* sbase = reinterpret_cast<int*>(gs + NS * GST);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, c = lane & 3;
@@ -74,33 +93,45 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
         const uint4* src = w.whh_f_lo + (size_t)dir * 8192;
         for (int i = tid; i < 8192; i += 256) alo[i] = src[i];
     }
-    for (int i = tid; i < NS * HST; i += 256) {  // h_{-1} = 0 (hi and lo arrays are contiguous)
-        reinterpret_cast<uint32_t*>(hs_hi)[i] = 0u;
-    }
+    for (int i = tid; i < NS * HST; i += 256) reinterpret_cast<uint32_t*>(hs_hi)[i] = 0u;  // h_{-1} = 0 (hi and lo)
+    fill_seq_bases(sbase, NS, q0, m);
+    __syncthreads();
 
-    int pbase[NT][2];
+    // stage one step's gate tile: NS rows of 2 KB, 16-byte chunks, fully coalesced, L1-bypassing
+    auto stage_gates = [&](int t) {
+        const unsigned toff = (unsigned)t * (unsigned)m.s_t;
+#pragma unroll
+        for (int i = 0; i < NS / 2; ++i) {
+            int ch = tid + 256 * i, sq = ch >> 7, col = ch & 127;
+            const float* src = G + ((size_t)(sbase[sq] + toff) * 1024 + dir * kG + col * 4);
+            cp_async16(gs + sq * GST + col * 4, src);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    stage_gates(dir ? m.len - 1 : 0);
+
+    unsigned hoff[NT][2];   // element offset of (sequence, unit g) in H / Cst at t = 0
     bool valid[NT][2];
 #pragma unroll
     for (int n = 0; n < NT; ++n)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            int q = q0 + n * 8 + 2 * c + e;
-            valid[n][e] = q < m.nseq;
-            int qq = valid[n][e] ? q : 0;
-            pbase[n][e] = (int)((qq / m.qdiv) * m.s_hi + (qq % m.qdiv) * m.s_lo);
+            int sl = n * 8 + 2 * c + e;
+            valid[n][e] = (q0 + sl) < m.nseq;
+            hoff[n][e] = (unsigned)sbase[sl] * 256u + (unsigned)(dir * kH + 16 * warp + g);
         }
     float cst[NT][4];
 #pragma unroll
     for (int n = 0; n < NT; ++n)
 #pragma unroll
         for (int i = 0; i < 4; ++i) cst[n][i] = 0.f;
-    const int ucol = dir * kG + (16 * warp + g) * 4;   // packed gate column of (h = 0); h = 1 adds 32
-    const int hcol = dir * kH + 16 * warp + g;         // H / Cst column of (h = 0); h = 1 adds 8
-    __syncthreads();
+    const int ucol = (16 * warp + g) * 4;  // packed gate column of (h = 0) inside the direction; h = 1 adds 32
 
     for (int step = 0; step < m.len; ++step) {
         const int t = dir ? (m.len - 1 - step) : step;
-        const long long toff = (long long)t * m.s_t;
+        const unsigned toff = (unsigned)t * (unsigned)m.s_t;
+        cp_async_wait_all();
+        __syncthreads();  // gate tile of step t landed; h_{t-1} (written by all warps) visible
         float acc[4][NT][4];
 #pragma unroll
         for (int n = 0; n < NT; ++n)
@@ -108,21 +139,9 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid[n][e]) v = *reinterpret_cast<const float4*>(G + (size_t)(pbase[n][e] + toff) * 1024 + ucol + h * 32);
+                    float4 v = *reinterpret_cast<const float4*>(gs + (n * 8 + 2 * c + e) * GST + ucol + h * 32);
                     acc[0][n][h * 2 + e] = v.x; acc[1][n][h * 2 + e] = v.y; acc[2][n][h * 2 + e] = v.z; acc[3][n][h * 2 + e] = v.w;
                 }
-        if (step + 1 < m.len && g == 0) {  // pull the next step's gate lines into L2
-            const long long tn = (long long)(dir ? t - 1 : t + 1) * m.s_t;
-#pragma unroll
-            for (int n = 0; n < NT; ++n)
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    if (valid[n][e]) {
-                        const float* pn = G + (size_t)(pbase[n][e] + tn) * 1024 + ucol;
-                        prefetch_l2(pn); prefetch_l2(pn + 32);
-                    }
-        }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
             uint32_t bh[NT][2], bl[NT][2];
@@ -133,18 +152,25 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
 #pragma unroll
                 for (int j = 0; j < 4; ++j) al[j] = alo[((warp * 4 + j) * 8 + ks) * 32 + lane];
             }
+            // the three split products go to the same accumulator: issue them in separate sweeps over the 4*NT
+            // accumulators so that consecutive HMMAs are independent
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                    mma_bf16(acc[j][n], ahi[j][ks], bh[n]);
-                    if (SPLIT) {
-                        mma_bf16(acc[j][n], ahi[j][ks], bl[n]);
-                        mma_bf16(acc[j][n], al[j], bh[n]);
-                    }
-                }
+                for (int n = 0; n < NT; ++n) mma_bf16(acc[j][n], ahi[j][ks], bh[n]);
+            if (SPLIT) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) mma_bf16(acc[j][n], ahi[j][ks], bl[n]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) mma_bf16(acc[j][n], al[j], bh[n]);
+            }
         }
-        __syncthreads();  // every warp is done reading h_{t-1}
+        __syncthreads();  // every warp is done reading h_{t-1} and the gate tile
+        if (step + 1 < m.len) stage_gates(dir ? t - 1 : t + 1);  // lands while the cell update below runs
 #pragma unroll
         for (int n = 0; n < NT; ++n)
 #pragma unroll
@@ -160,11 +186,12 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
                     cst[n][idx] = cc;
                     float hh = og * tanh_f<SPLIT>(cc);
                     if (valid[n][e]) {
-                        size_t pos = (size_t)(pbase[n][e] + toff);
-                        H[pos * 256 + hcol + h * 8] = hh;
+                        const unsigned ho = hoff[n][e] + toff * 256u + h * 8;
+                        H[ho] = hh;
                         if (SAVE) {
-                            *reinterpret_cast<float4*>(G + pos * 1024 + ucol + h * 32) = make_float4(ig, fg, gg, og);
-                            Cst[pos * 256 + hcol + h * 8] = cc;
+                            Cst[ho] = cc;
+                            // packed gate column = 4 x hidden column, so the gate offset is exactly 4 * ho
+                            *reinterpret_cast<float4*>(G + (size_t)ho * 4) = make_float4(ig, fg, gg, og);
                         }
                     }
                     const int so = (n * 8 + 2 * c + e) * HST + 16 * warp + g + 8 * h;
@@ -172,125 +199,6 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
                     hs_hi[so] = hb;
                     if (SPLIT) hs_lo[so] = __float2bfloat16_rn(hh - __bfloat162float(hb));
                 }
-        __syncthreads();
-    }
-}
-
-template <int NT, bool SPLIT>
-__global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, float* __restrict__ G, const float* __restrict__ Cst,
-                                                          const float* __restrict__ dH, const SeqMap m) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int NS = 8 * NT;
-    uint4* alo = reinterpret_cast<uint4*>(smem);
-    __nv_bfloat16* dg_hi = reinterpret_cast<__nv_bfloat16*>(smem + (SPLIT ? ALO_BYTES : 0));
-    __nv_bfloat16* dg_lo = dg_hi + NS * DST;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, c = lane & 3;
-    const int dir = blockIdx.y;
-    const int q0 = blockIdx.x * NS;
-
-    uint4 ahi[32];
-    {
-        const uint4* src = w.whh_b_hi + ((size_t)dir * 8 + warp) * (32 * 32);
-#pragma unroll
-        for (int ks = 0; ks < 32; ++ks) ahi[ks] = src[ks * 32 + lane];
-    }
-    if (SPLIT) {
-        const uint4* src = w.whh_b_lo + (size_t)dir * 8192;
-        for (int i = tid; i < 8192; i += 256) alo[i] = src[i];
-    }
-    int pbase[NT][2];
-    bool valid[NT][2];
-#pragma unroll
-    for (int n = 0; n < NT; ++n)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            int q = q0 + n * 8 + 2 * c + e;
-            valid[n][e] = q < m.nseq;
-            int qq = valid[n][e] ? q : 0;
-            pbase[n][e] = (int)((qq / m.qdiv) * m.s_hi + (qq % m.qdiv) * m.s_lo);
-        }
-    float acc[NT][4], dcc[NT][4];
-#pragma unroll
-    for (int n = 0; n < NT; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[n][i] = 0.f; dcc[n][i] = 0.f; }
-    const int ucol = dir * kG + (16 * warp + g) * 4;
-    const int hcol = dir * kH + 16 * warp + g;
-    __syncthreads();
-
-    for (int step = 0; step < m.len; ++step) {
-        const int t = dir ? step : (m.len - 1 - step);       // reverse of the forward visiting order
-        const int tp = dir ? t + 1 : t - 1;                  // the step visited just before t in the forward pass
-        const bool first = (step == m.len - 1);              // t is the forward pass's first step: c_{prev} = 0
-        const long long toff = (long long)t * m.s_t, tpoff = (long long)tp * m.s_t;
-#pragma unroll
-        for (int n = 0; n < NT; ++n)
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int idx = h * 2 + e;
-                    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid[n][e]) {
-                        size_t pos = (size_t)(pbase[n][e] + toff);
-                        float4 gt = *reinterpret_cast<const float4*>(G + pos * 1024 + ucol + h * 32);
-                        float ct = Cst[pos * 256 + hcol + h * 8];
-                        float cp = first ? 0.f : Cst[(size_t)(pbase[n][e] + tpoff) * 256 + hcol + h * 8];
-                        float dh = dH[pos * 256 + hcol + h * 8] + acc[n][idx];
-                        float tc = tanh_f<SPLIT>(ct);
-                        float dc = fmaf(dh * gt.w, 1.f - tc * tc, dcc[n][idx]);
-                        dcc[n][idx] = dc * gt.y;
-                        dg.x = dc * gt.z * gt.x * (1.f - gt.x);
-                        dg.y = dc * cp * gt.y * (1.f - gt.y);
-                        dg.z = dc * gt.x * (1.f - gt.z * gt.z);
-                        dg.w = dh * tc * gt.w * (1.f - gt.w);
-                        *reinterpret_cast<float4*>(G + pos * 1024 + ucol + h * 32) = dg;
-                    }
-                    const int so = (n * 8 + 2 * c + e) * DST + (16 * warp + g + 8 * h) * 4;
-                    uint2 hi, lo;
-                    split_pair(dg.x, dg.y, hi.x, lo.x);
-                    split_pair(dg.z, dg.w, hi.y, lo.y);
-                    *reinterpret_cast<uint2*>(dg_hi + so) = hi;
-                    if (SPLIT) *reinterpret_cast<uint2*>(dg_lo + so) = lo;
-                }
-        if (!first && g == 0) {  // next visited step: t2 = tp
-#pragma unroll
-            for (int n = 0; n < NT; ++n)
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    if (valid[n][e]) {
-                        size_t pos = (size_t)(pbase[n][e] + tpoff);
-                        prefetch_l2(G + pos * 1024 + ucol); prefetch_l2(G + pos * 1024 + ucol + 32);
-                        prefetch_l2(dH + pos * 256 + hcol);
-                    }
-        }
-        __syncthreads();
-        if (first) break;  // dh_{-1} is not needed
-#pragma unroll
-        for (int n = 0; n < NT; ++n)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 32; ++ks) {
-            uint32_t bh[NT][2], bl[NT][2];
-            load_b_frags<NT>(dg_hi, DST, ks * 16, lane, bh);
-            uint4 al;
-            if (SPLIT) {
-                load_b_frags<NT>(dg_lo, DST, ks * 16, lane, bl);
-                al = alo[(warp * 32 + ks) * 32 + lane];
-            }
-#pragma unroll
-            for (int n = 0; n < NT; ++n) {
-                mma_bf16(acc[n], ahi[ks], bh[n]);
-                if (SPLIT) {
-                    mma_bf16(acc[n], ahi[ks], bl[n]);
-                    mma_bf16(acc[n], al, bh[n]);
-                }
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -402,17 +310,10 @@ cudaError_t set_smem(K kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-int pick_nt(int nseq) {
-    // smallest tile that still fits the whole pass in one wave of 148 SMs (2 directions per tile)
-    for (int nt = 1; nt <= 3; ++nt)
-        if (2 * ceil_div(nseq, 8 * nt) <= 148) return nt;
-    return 3;
-}
-
 template <int NT>
 cudaError_t fwd_launch(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, cudaStream_t st) {
     dim3 grid(ceil_div(m.nseq, 8 * NT), 2);
-    int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * HST * 2;
+    int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * HST * 2 + 8 * NT * GST * 4 + 8 * NT * 4;
     cudaError_t e;
 #define DP_FWD(SP, SV)                                                               \
     do {                                                                             \
@@ -426,42 +327,22 @@ cudaError_t fwd_launch(const LstmPack& w, float* G, float* H, float* Cst, const 
     return cudaGetLastError();
 }
 
-template <int NT>
-cudaError_t bwd_launch(const LstmPack& w, float* G, const float* Cst, const float* dH, const SeqMap& m, bool split, cudaStream_t st) {
-    dim3 grid(ceil_div(m.nseq, 8 * NT), 2);
-    int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * DST * 2;
-    cudaError_t e;
-    if (split) {
-        e = set_smem(lstm_bwd_kernel<NT, true>, smem);
-        if (e != cudaSuccess) return e;
-        lstm_bwd_kernel<NT, true><<<grid, 256, smem, st>>>(w, G, Cst, dH, m);
-    } else {
-        e = set_smem(lstm_bwd_kernel<NT, false>, smem);
-        if (e != cudaSuccess) return e;
-        lstm_bwd_kernel<NT, false><<<grid, 256, smem, st>>>(w, G, Cst, dH, m);
-    }
-    return cudaGetLastError();
-}
-
 }  // namespace
+
+int lstm_pick_nt(int nseq) {
+    // smallest tile that still fits the whole pass in one wave of 148 SMs (2 directions per tile)
+    for (int nt = 1; nt <= 3; ++nt)
+        if (2 * ceil_div(nseq, 8 * nt) <= 148) return nt;
+    return 3;
+}
 
 cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save,
                             cudaStream_t st) {
     if (m.nseq <= 0 || m.len <= 0) return cudaSuccess;
-    switch (pick_nt(m.nseq)) {
+    switch (lstm_pick_nt(m.nseq)) {
         case 1: return fwd_launch<1>(w, G, H, Cst, m, split, save, st);
         case 2: return fwd_launch<2>(w, G, H, Cst, m, split, save, st);
         default: return fwd_launch<3>(w, G, H, Cst, m, split, save, st);
-    }
-}
-
-cudaError_t launch_lstm_bwd(const LstmPack& w, float* G, const float* Cst, const float* dH, const SeqMap& m, bool split,
-                            cudaStream_t st) {
-    if (m.nseq <= 0 || m.len <= 0) return cudaSuccess;
-    switch (pick_nt(m.nseq)) {
-        case 1: return bwd_launch<1>(w, G, Cst, dH, m, split, st);
-        case 2: return bwd_launch<2>(w, G, Cst, dH, m, split, st);
-        default: return bwd_launch<3>(w, G, Cst, dH, m, split, st);
     }
 }
 

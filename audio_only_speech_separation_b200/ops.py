@@ -176,18 +176,19 @@ def bilstm_forward(pack: LstmPack, x: torch.Tensor, layout: str, *, save=False, 
 
 
 def bilstm_backward(pack: LstmPack, G, Cst, dH, shape, layout: str, *, precision="fp32"):
-    """BPTT: ``dH[B,S,K,256]`` -> ``dx[B,S,K,64]``; ``G`` is overwritten with d(pre-activations) (packed column order)."""
+    """BPTT: ``dH[B,S,K,256]`` -> ``(dx[B,S,K,64], dbias[1024] packed)``; ``G`` becomes d(pre-activations) (packed columns)."""
     B, S, K = shape
     P = B * S * K
     require_cuda(dH, "dH")
     dx = torch.empty(B, S, K, 64, device=dH.device, dtype=torch.float32)
+    dbias = torch.zeros(1024, device=dH.device, dtype=torch.float32)
     nseq, ln, qdiv, s_hi, s_lo, s_t = _seq_map(layout, B, S, K)
     check(
-        lib().dp_bilstm_backward_f32(ptr(pack.buf), ptr(G), ptr(Cst), ptr(dH), ptr(dx), 0, P, nseq, ln, qdiv, s_hi, s_lo, s_t,
-                                     _prec(precision), stream_ptr()),
+        lib().dp_bilstm_backward_f32(ptr(pack.buf), ptr(G), ptr(Cst), ptr(dH), ptr(dx), 0, ptr(dbias), P, nseq, ln, qdiv, s_hi, s_lo,
+                                     s_t, _prec(precision), stream_ptr()),
         "dp_bilstm_backward_f32",
     )
-    return dx
+    return dx, dbias
 
 
 def groupnorm_residual(y, res, gamma, beta, stats, rows_per_group, eps, *, concat=None):

@@ -69,10 +69,11 @@ int dp_bilstm_forward_f32(const void* pack, const float* x, float* G, float* H, 
 /* the recurrence alone on precomputed gate pre-activations G (what dp_bilstm_forward_f32 runs after its GEMM) */
 int dp_lstm_recurrence_f32(const void* pack, float* G, float* H, float* Cst, int nseq, int len, int qdiv, int64_t s_hi,
                            int64_t s_lo, int64_t s_t, int save, int precision, void* stream);
-/* dH[P,256] -> G becomes d(pre-activations) [P,1024]; dx[P,64] (=|+=) dG W_ih. Weight grads via dp_linear_wgrad_f32. */
+/* dH[P,256] -> G becomes d(pre-activations) [P,1024] (packed column order); dx[P,64] (=|+=) dG W_ih; dbias (optional,
+ * [1024] packed order) += column sums of dG (= d b_ih = d b_hh). Weight grads via dp_linear_wgrad_f32 on G. */
 int dp_bilstm_backward_f32(const void* pack, float* G, const float* Cst, const float* dH, float* dx, int accumulate_dx,
-                           int64_t P, int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int precision,
-                           void* stream);
+                           float* dbias, int64_t P, int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t,
+                           int precision, void* stream);
 
 /* ---- (d) fused GroupNorm(1,C) + residual (+ unfold depthwise affine + PReLU), dprnn.py:71-73,80-82,31-34 - */
 int dp_groupnorm_finalize(const double* stats, float* mean_rstd, int groups, double count, double eps, void* stream);

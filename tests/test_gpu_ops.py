@@ -168,7 +168,7 @@ def test_bilstm_backward_parity(ops, layout, B, S, K):
     ref.backward(dH)
     H, G, Cst = ops.bilstm_forward(pack, x.cuda(), layout, save=True)
     assert rel_l2(H, ref.detach()) < 2e-5
-    dx = ops.bilstm_backward(pack, G, Cst, dH.cuda(), (B, S, K), layout)
+    dx, dbias = ops.bilstm_backward(pack, G, Cst, dH.cuda(), (B, S, K), layout)
     err = rel_l2(dx, xr.grad)
     record("bilstm_bwd_dx", layout=layout, B=B, S=S, K=K, rel_l2=err)
     assert err < 5e-5
@@ -182,7 +182,8 @@ def test_bilstm_backward_parity(ops, layout, B, S, K):
         e = rel_l2(got, leaf[name].grad)
         record("bilstm_bwd_dwih", layout=layout, dir=d, rel_l2=e)
         assert e < 5e-5
-    db = G.double().sum(0).cpu()
+    assert rel_l2(dbias, G.double().sum(0)) < 1e-5  # bias gradient fused into the BPTT kernel
+    db = dbias.double().cpu()
     for d, name in enumerate(["rnn.bias_ih_l0", "rnn.bias_ih_l0_reverse"]):
         got = torch.empty(512, dtype=torch.float64)
         got[perm] = db[d * 512 : (d + 1) * 512]
