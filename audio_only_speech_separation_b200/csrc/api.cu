@@ -51,12 +51,20 @@ constexpr size_t PK_WF_HI = PK_BIAS + 1024 * 4;
 constexpr size_t PK_WF_LO = PK_WF_HI + 2 * 8192 * 16;
 constexpr size_t PK_WB_HI = PK_WF_LO + 2 * 8192 * 16;
 constexpr size_t PK_WB_LO = PK_WB_HI + 2 * 8192 * 16;
-constexpr size_t PK_BYTES = PK_WB_LO + 2 * 8192 * 16;
+constexpr size_t PK_WIHT_HI = PK_WB_LO + 2 * 8192 * 16;
+constexpr size_t PK_WIHT_LO = PK_WIHT_HI + 65536 * 2;
+constexpr size_t PK_PROJT_HI = PK_WIHT_LO + 65536 * 2;
+constexpr size_t PK_PROJT_LO = PK_PROJT_HI + 16384 * 2;
+constexpr size_t PK_BYTES = PK_PROJT_LO + 16384 * 2;
 
 struct LstmPackView {
     const __nv_bfloat16* wih_hi;
     const __nv_bfloat16* wih_lo;
     const float* bias;
+    const __nv_bfloat16* wiht_hi;
+    const __nv_bfloat16* wiht_lo;
+    const __nv_bfloat16* projt_hi;
+    const __nv_bfloat16* projt_lo;
     LstmPack rec;
 };
 LstmPackView view_pack(const void* pack) {
@@ -69,6 +77,10 @@ LstmPackView view_pack(const void* pack) {
     v.rec.whh_f_lo = reinterpret_cast<const uint4*>(b + PK_WF_LO);
     v.rec.whh_b_hi = reinterpret_cast<const uint4*>(b + PK_WB_HI);
     v.rec.whh_b_lo = reinterpret_cast<const uint4*>(b + PK_WB_LO);
+    v.wiht_hi = reinterpret_cast<const __nv_bfloat16*>(b + PK_WIHT_HI);
+    v.wiht_lo = reinterpret_cast<const __nv_bfloat16*>(b + PK_WIHT_LO);
+    v.projt_hi = reinterpret_cast<const __nv_bfloat16*>(b + PK_PROJT_HI);
+    v.projt_lo = reinterpret_cast<const __nv_bfloat16*>(b + PK_PROJT_LO);
     return v;
 }
 LstmPackOut out_pack(void* pack) {
@@ -81,6 +93,10 @@ LstmPackOut out_pack(void* pack) {
     o.whh_f_lo = reinterpret_cast<uint4*>(b + PK_WF_LO);
     o.whh_b_hi = reinterpret_cast<uint4*>(b + PK_WB_HI);
     o.whh_b_lo = reinterpret_cast<uint4*>(b + PK_WB_LO);
+    o.wiht_hi = reinterpret_cast<__nv_bfloat16*>(b + PK_WIHT_HI);
+    o.wiht_lo = reinterpret_cast<__nv_bfloat16*>(b + PK_WIHT_LO);
+    o.projt_hi = reinterpret_cast<__nv_bfloat16*>(b + PK_PROJT_HI);
+    o.projt_lo = reinterpret_cast<__nv_bfloat16*>(b + PK_PROJT_LO);
     return o;
 }
 
@@ -97,6 +113,17 @@ GemmTnArgs tn_args(const float* A, int lda, const float* B, long long ldb, float
     memset(&a, 0, sizeof(a));
     a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.P = P; a.Mo = Mo; a.No = No; a.scale = 1.f;
     return a;
+}
+
+int g_backend = 0;  // 0: legacy mma.sync GEMMs everywhere, 1: tcgen05/TMEM GEMMs where the shape is supported
+
+cudaError_t gemm_nt(const GemmNtArgs& a, bool split, cudaStream_t st) {
+    if (g_backend == 1 && !a.w_kn && gemm_nt_tc5_supported(a)) return launch_gemm_nt_tc5(a, split, st);
+    return launch_gemm_nt(a, split, st);
+}
+cudaError_t gemm_tn(const GemmTnArgs& a, bool split, cudaStream_t st) {
+    if (g_backend == 1 && !a.b_rpb && gemm_tn_tc5_supported(a)) return launch_gemm_tn_tc5(a, split, 0, st);
+    return launch_gemm_tn(a, split, st);
 }
 
 struct PitWsView {
@@ -118,7 +145,12 @@ PitWsView pit_view(void* ws, int B) {
 // ================================================================================================
 extern "C" {
 
-int dp_version(void) { return 100; }
+int dp_version(void) { return 101; }
+int dp_set_gemm_backend(int backend) {
+    if (backend != 0 && backend != 1) return fail("dp_set_gemm_backend: 0 (mma.sync) or 1 (tcgen05)");
+    g_backend = backend;
+    return 0;
+}
 const char* dp_last_error(void) { return g_err; }
 
 int dp_seg_geometry(int L, int K, int* rest, int* Sout) {
@@ -168,14 +200,14 @@ int dp_linear_f32(const float* A, int64_t lda, const void* w_hi, const void* w_l
     GemmNtArgs a = nt_args(A, lda, (const __nv_bfloat16*)w_hi, (const __nv_bfloat16*)w_lo, ldw, w_kn, C, ldc, M, N, K);
     a.bias = bias; a.bias_scale = bias_scale; a.relu = relu; a.accumulate = accumulate; a.stats = stats;
     a.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
-    CK(launch_gemm_nt(a, is_split(precision), S(stream)));
+    CK(gemm_nt(a, is_split(precision), S(stream)));
     return 0;
 }
 int dp_linear_wgrad_f32(const float* A, int lda, const float* B, int64_t ldb, float* dW, int ldc, int P, int Mo, int No, float scale,
                         int precision, void* stream) {
     GemmTnArgs a = tn_args(A, lda, B, ldb, dW, ldc, P, Mo, No);
     a.scale = scale;
-    CK(launch_gemm_tn(a, is_split(precision), S(stream)));
+    CK(gemm_tn(a, is_split(precision), S(stream)));
     return 0;
 }
 int dp_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* stream) {
@@ -190,7 +222,7 @@ int dp_lstm_pack(const float* w_ih, const float* w_hh, const float* b_ih, const 
     const float* wh[2] = {w_hh, w_hh_r};
     const float* bi[2] = {b_ih, b_ih_r};
     const float* bh[2] = {b_hh, b_hh_r};
-    CK(launch_pack_lstm(wi, wh, bi, bh, out_pack(pack), S(stream)));
+    CK(launch_pack_lstm(wi, wh, bi, bh, nullptr, out_pack(pack), S(stream)));
     return 0;
 }
 
@@ -200,7 +232,7 @@ int dp_bilstm_forward_f32(const void* pack, const float* x, float* G, float* H, 
     LstmPackView v = view_pack(pack);
     GemmNtArgs a = nt_args(x, kN, v.wih_hi, v.wih_lo, kN, 0, G, 2 * kG, (int)P, 2 * kG, kN);
     a.bias = v.bias;
-    CK(launch_gemm_nt(a, is_split(precision), S(stream)));
+    CK(gemm_nt(a, is_split(precision), S(stream)));
     SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
     CK(launch_lstm_fwd(v.rec, G, H, Cst, m, is_split(precision), save != 0, S(stream)));
     return 0;
@@ -218,9 +250,9 @@ int dp_bilstm_backward_f32(const void* pack, float* G, const float* Cst, const f
     SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
     CK(launch_lstm_bwd(v.rec, G, Cst, dH, dbias, m, is_split(precision), S(stream)));
     if (dx) {
-        GemmNtArgs a = nt_args(G, 2 * kG, v.wih_hi, v.wih_lo, kN, 1, dx, kN, (int)P, kN, 2 * kG);
+        GemmNtArgs a = nt_args(G, 2 * kG, v.wiht_hi, v.wiht_lo, 2 * kG, 0, dx, kN, (int)P, kN, 2 * kG);
         a.accumulate = accumulate_dx;
-        CK(launch_gemm_nt(a, is_split(precision), S(stream)));
+        CK(gemm_nt(a, is_split(precision), S(stream)));
     }
     return 0;
 }
@@ -443,7 +475,7 @@ int dp_tasnet_pack(dp_tasnet* h, const float* params, void* pack, void* stream) 
         const float* wh[2] = {params + o[1], params + o[5]};
         const float* bi[2] = {params + o[2], params + o[6]};
         const float* bh[2] = {params + o[3], params + o[7]};
-        CK(launch_pack_lstm(wi, wh, bi, bh, out_pack(b + 2 * flat + (size_t)pp * PK_BYTES), S(stream)));
+        CK(launch_pack_lstm(wi, wh, bi, bh, params + o[8], out_pack(b + 2 * flat + (size_t)pp * PK_BYTES), S(stream)));
     }
     return 0;
 }
@@ -495,7 +527,7 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
         {
             GemmNtArgs a = nt_args(X, 64, v.wih_hi, v.wih_lo, 64, 0, G, 1024, (int)g.PT, 1024, 64);
             a.bias = v.bias;
-            CK(launch_gemm_nt(a, sp, st)); ++nl;
+            CK(gemm_nt(a, sp, st)); ++nl;
         }
         CK(launch_lstm_fwd(v.rec, G, H, train ? at<float>(ws, l.Cst[pp]) : nullptr, path_map(g, pp), sp, train != 0, st)); ++nl;
         {
@@ -606,27 +638,32 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
         CK(launch_gn_bwd_apply(dXs, Y, dY, mr, at<double>(ws, l.red[pp]), params + po[10], g.PT, g.P, 64, st)); ++nl;
         // out-projection Linear(256 -> 64)
         {
-            GemmNtArgs a = nt_args(dY, 64, whi + po[8], wlo + po[8], 256, 1, dH, 256, PTi, 256, 64);
-            CK(launch_gemm_nt(a, sp, st)); ++nl;
-            GemmTnArgs t = tn_args(dY, 64, H, 256, grads + po[8], 256, PTi, 64, 256);
-            CK(launch_gemm_tn(t, sp, st)); ++nl;
+            GemmNtArgs a = nt_args(dY, 64, v.projt_hi, v.projt_lo, 64, 0, dH, 256, PTi, 256, 64);
+            CK(gemm_nt(a, sp, st)); ++nl;
+            GemmTnArgs t = tn_args(H, 256, dY, 64, grads + po[8], 256, PTi, 256, 64);  // dWp^T = H^T dY, stored transposed
+            if (g_backend == 1 && gemm_tn_tc5_supported(t)) {
+                CK(launch_gemm_tn_tc5(t, sp, 1, st)); ++nl;
+            } else {
+                GemmTnArgs t2 = tn_args(dY, 64, H, 256, grads + po[8], 256, PTi, 64, 256);
+                CK(launch_gemm_tn(t2, sp, st)); ++nl;
+            }
             CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[9], nullptr, st)); ++nl;
         }
         // BPTT: G (activated gates) -> d(pre-activations)
         CK(launch_lstm_bwd(v.rec, G, at<float>(ws, l.Cst[pp]), dH, dpk + 65536 + 131072, m, sp, st)); ++nl;
         // input projection: dX += dG W_ih ; dW_ih += dG^T X ; dW_hh += dG^T h_prev ; db += colsum(dG)   (packed row order)
         {
-            GemmNtArgs a = nt_args(G, 1024, v.wih_hi, v.wih_lo, 64, 1, dXs, 64, PTi, 64, 1024);
+            GemmNtArgs a = nt_args(G, 1024, v.wiht_hi, v.wiht_lo, 1024, 0, dXs, 64, PTi, 64, 1024);
             a.accumulate = 1;
-            CK(launch_gemm_nt(a, sp, st)); ++nl;
+            CK(gemm_nt(a, sp, st)); ++nl;
             GemmTnArgs t = tn_args(G, 1024, X, 64, dpk, 64, PTi, 1024, 64);
-            CK(launch_gemm_tn(t, sp, st)); ++nl;
+            CK(gemm_tn(t, sp, st)); ++nl;
             for (int d = 0; d < 2; ++d) {
                 GemmTnArgs r = tn_args(G + d * 512, 1024, H + d * 128, 256, dpk + 65536 + d * 65536, 128, PTi, 512, 128);
                 r.shift = (d == 0 ? -1 : 1) * (int)m.s_t;
                 r.tdiv = (pp & 1) ? g.K : 1;
                 r.tmod = m.len;
-                CK(launch_gemm_tn(r, sp, st)); ++nl;
+                CK(gemm_tn(r, sp, st)); ++nl;
             }
         }
     }

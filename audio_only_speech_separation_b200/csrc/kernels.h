@@ -30,6 +30,9 @@ struct GemmNtArgs {
     int rows_per_group;
 };
 cudaError_t launch_gemm_nt(const GemmNtArgs& a, bool split, cudaStream_t st);
+// tcgen05 / TMEM version (gemm_tc5.cu); supported(): K % 64 == 0, N in {64, 128, k*256}, w_kn == 0 preferred, no stats
+bool gemm_nt_tc5_supported(const GemmNtArgs& a);
+cudaError_t launch_gemm_nt_tc5(const GemmNtArgs& a, bool split, cudaStream_t st);
 
 // C[Mo,No] += scale * sum_p A[p,Mo]^T * B[p',No]   (fp32 atomics), p' = p + shift when the time index allows.
 struct GemmTnArgs {
@@ -45,6 +48,9 @@ struct GemmTnArgs {
     float scale;
 };
 cudaError_t launch_gemm_tn(const GemmTnArgs& a, bool split, cudaStream_t st);
+// tcgen05 / TMEM version: whole [Mo,No] output resident in TMEM per CTA; transpose_out writes C[col][row]
+bool gemm_tn_tc5_supported(const GemmTnArgs& a);
+cudaError_t launch_gemm_tn_tc5(const GemmTnArgs& a, bool split, int transpose_out, cudaStream_t st);
 
 // out[n] += scale * sum_p A[p*lda + n]  (and the same into out2 when non-null)
 cudaError_t launch_colsum(const float* A, int lda, int P, int N, float scale, float* out, float* out2, cudaStream_t st);
@@ -79,9 +85,13 @@ struct LstmPackOut {
     uint4* whh_f_lo;
     uint4* whh_b_hi;
     uint4* whh_b_lo;
+    __nv_bfloat16* wiht_hi;   // [64,1024] = packed W_ih transposed (weights of the input-gradient GEMM, K contiguous)
+    __nv_bfloat16* wiht_lo;
+    __nv_bfloat16* projt_hi;  // [256,64] = proj.weight transposed (optional, needs proj_w)
+    __nv_bfloat16* projt_lo;
 };
 cudaError_t launch_pack_lstm(const float* const w_ih[2], const float* const w_hh[2], const float* const b_ih[2],
-                             const float* const b_hh[2], const LstmPackOut& o, cudaStream_t st);
+                             const float* const b_hh[2], const float* proj_w, const LstmPackOut& o, cudaStream_t st);
 // grads of the packed forms -> natural parameter gradients (+=)
 cudaError_t launch_unpack_lstm_grads(const float* d_wih_pack /*[1024,64]*/, const float* d_whh_pack /*[2][512,128]*/,
                                      const float* d_bias_pack /*[1024]*/, float* const d_w_ih[2], float* const d_w_hh[2],

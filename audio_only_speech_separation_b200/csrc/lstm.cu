@@ -208,6 +208,7 @@ struct PackArgs {
     const float* w_hh[2];
     const float* b_ih[2];
     const float* b_hh[2];
+    const float* proj_w;
     LstmPackOut o;
 };
 
@@ -259,6 +260,25 @@ __global__ void pack_lstm_kernel(const PackArgs a) {
     if (idx < 1024) {
         int d = idx >> 9, u = (idx & 511) >> 2, j = idx & 3;
         a.o.bias[idx] = a.b_ih[d][j * kH + u] + a.b_hh[d][j * kH + u];
+        return;
+    }
+    idx -= 1024;
+    if (idx < 65536) {  // packed W_ih transposed: [64 (k)][1024 (packed row)]
+        int k = idx >> 10, row = idx & 1023;
+        int d = row >> 9, u = (row & 511) >> 2, j = row & 3;
+        float v = a.w_ih[d][(j * kH + u) * kN + k];
+        float vh = bf16_round(v);
+        a.o.wiht_hi[idx] = __float2bfloat16_rn(vh);
+        a.o.wiht_lo[idx] = __float2bfloat16_rn(v - vh);
+        return;
+    }
+    idx -= 65536;
+    if (idx < 16384 && a.proj_w != nullptr) {  // proj.weight [64,256] -> [256,64]
+        int c = idx >> 6, r = idx & 63;
+        float v = a.proj_w[r * 256 + c];
+        float vh = bf16_round(v);
+        a.o.projt_hi[idx] = __float2bfloat16_rn(vh);
+        a.o.projt_lo[idx] = __float2bfloat16_rn(v - vh);
     }
 }
 
@@ -347,11 +367,12 @@ cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, c
 }
 
 cudaError_t launch_pack_lstm(const float* const w_ih[2], const float* const w_hh[2], const float* const b_ih[2],
-                             const float* const b_hh[2], const LstmPackOut& o, cudaStream_t st) {
+                             const float* const b_hh[2], const float* proj_w, const LstmPackOut& o, cudaStream_t st) {
     PackArgs a;
+    a.proj_w = proj_w;
     for (int d = 0; d < 2; ++d) { a.w_ih[d] = w_ih[d]; a.w_hh[d] = w_hh[d]; a.b_ih[d] = b_ih[d]; a.b_hh[d] = b_hh[d]; }
     a.o = o;
-    int total = 65536 * 3 + 1024;
+    int total = 65536 * 3 + 1024 + 65536 + 16384;
     pack_lstm_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a);
     return cudaGetLastError();
 }

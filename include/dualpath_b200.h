@@ -25,6 +25,9 @@ extern "C" {
 
 int dp_version(void);
 const char* dp_last_error(void);
+/* GEMM backend of dp_linear*_f32 and of the engine: 1 = tcgen05/TMEM kernels where the shape is supported,
+ * 0 = warp-level mma.sync kernels everywhere.  Both are covered by the parity tests; see DESIGN.md for the default. */
+int dp_set_gemm_backend(int backend);
 
 /* ---- geometry (integer index maps) --------------------------------------------------------------------- */
 /* gc3_basics.py:63-76 pad_segment: rest and chunk count S for L frames and chunk size K (K even). */

@@ -109,15 +109,42 @@ def test_linear_accumulate_stats_and_frames(ops):
     assert torch.allclose(stats.cpu(), rs, rtol=1e-4, atol=1e-3)
 
 
-@pytest.mark.parametrize("P,Mo,No", [(5000, 64, 256), (3000, 1024, 64), (1111, 512, 128), (4002, 64, 16)])
-def test_linear_wgrad(ops, P, Mo, No):
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "mma_sync"])
+def backend(request):
+    from audio_only_speech_separation_b200._lib import check, lib
+
+    check(lib().dp_set_gemm_backend(request.param))
+    yield request.param
+    check(lib().dp_set_gemm_backend(0))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 256, 64), (8200, 1024, 64), (3333, 64, 1024), (700, 128, 256)])
+def test_linear_backends_agree(ops, backend, M, N, K):
+    """Same GEMM through the tcgen05/TMEM kernel and the mma.sync kernel, both against fp64."""
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K**0.5
+    b = torch.randn(N, generator=g)
+    base = torch.randn(M, N, generator=g)
+    ref = a.double() @ w.double().t() + b.double()
+    out = ops.linear(a.cuda(), w.cuda(), b.cuda())
+    err = rel_l2(out, ref)
+    record("linear_backend", backend=backend, M=M, N=N, K=K, rel_l2=err)
+    assert err < 2e-5
+    out2 = ops.linear(a.cuda(), w.cuda(), None, out=base.clone().cuda(), accumulate=True)
+    assert rel_l2(out2, base.double() + a.double() @ w.double().t()) < 2e-5
+    assert rel_l2(ops.linear(a.cuda(), w.cuda(), b.cuda(), precision="bf16"), ref) < 2e-2
+
+
+@pytest.mark.parametrize("P,Mo,No", [(5000, 64, 256), (3000, 1024, 64), (1111, 512, 128), (4002, 64, 16), (2500, 256, 64), (40, 512, 128)])
+def test_linear_wgrad(ops, backend, P, Mo, No):
     g = torch.Generator().manual_seed(P)
     a = torch.randn(P, Mo, generator=g)
     b = torch.randn(P, No, generator=g)
     out = torch.zeros(Mo, No, device="cuda")
     ops.linear_wgrad(a.cuda(), b.cuda(), out)
     err = rel_l2(out, a.double().t() @ b.double())
-    record("linear_wgrad", P=P, Mo=Mo, No=No, rel_l2=err)
+    record("linear_wgrad", backend=backend, P=P, Mo=Mo, No=No, rel_l2=err)
     assert err < 2e-5
 
 
