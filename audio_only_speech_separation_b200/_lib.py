@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libdualpath_b200.so")
 
 PREC_FP32 = 0
 PREC_BF16 = 1
+MODULE_DPRNN = 0
+MODULE_DPTNET = 1
 
 _p = C.c_void_p
 _i = C.c_int
@@ -24,7 +26,7 @@ _d = C.c_double
 
 
 class TasnetConfig(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("enc_dim", "bn_dim", "hidden_dim", "win", "layer", "num_spk", "block_size", "unfold")]
+    _fields_ = [(n, C.c_int) for n in ("enc_dim", "bn_dim", "hidden_dim", "win", "layer", "num_spk", "block_size", "unfold", "module")]
 
 
 # name -> (restype, argtypes); every symbol declared in include/dualpath_b200.h
@@ -48,6 +50,10 @@ PROTOTYPES = {
     "dp_bilstm_backward_f32": (_i, [_p, _p, _p, _p, _p, _i, _p, _i64, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "dp_groupnorm_finalize": (_i, [_p, _p, _i, _d, _d, _p]),
     "dp_groupnorm_residual_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),
+    "dp_attention_forward_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _p]),
+    "dp_attention_backward_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _p]),
+    "dp_add_layernorm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _p]),
+    "dp_layernorm_backward_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _f, _p, _p, _p]),
     "dp_pit_loss_workspace_bytes": (_i64, [_i]),
     "dp_pit_loss_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "dp_pit_loss_backward": (_i, [_p, _p, _i, _i, _p, _f, _p, _p]),

@@ -18,13 +18,12 @@
 #include "../../include/dualpath_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "engine_common.h"
 
 using namespace dp;
 
-namespace {
-
+namespace dp {
 thread_local char g_err[512] = "";
-
 int fail(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -33,15 +32,9 @@ int fail(const char* fmt, ...) {
     return 1;
 }
 int cuda_fail(cudaError_t e, const char* what) { return fail("%s: %s", what, cudaGetErrorString(e)); }
+}  // namespace dp
 
-#define CK(call)                                        \
-    do {                                                \
-        cudaError_t _e = (call);                        \
-        if (_e != cudaSuccess) return cuda_fail(_e, #call); \
-    } while (0)
-
-inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
-inline bool is_split(int precision) { return precision == DP_PREC_FP32; }
+namespace {
 
 // ---- packed LSTM buffer layout (bytes) ----
 constexpr size_t PK_WIH_HI = 0;
@@ -100,23 +93,11 @@ LstmPackOut out_pack(void* pack) {
     return o;
 }
 
-GemmNtArgs nt_args(const float* A, long long lda, const __nv_bfloat16* whi, const __nv_bfloat16* wlo, int ldw, int w_kn, float* C,
-                   int ldc, int M, int N, int K) {
-    GemmNtArgs a;
-    memset(&a, 0, sizeof(a));
-    a.A = A; a.lda = lda; a.Whi = whi; a.Wlo = wlo; a.ldw = ldw; a.w_kn = w_kn; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
-    a.bias_scale = 1.f;
-    return a;
-}
-GemmTnArgs tn_args(const float* A, int lda, const float* B, long long ldb, float* C, int ldc, int P, int Mo, int No) {
-    GemmTnArgs a;
-    memset(&a, 0, sizeof(a));
-    a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.P = P; a.Mo = Mo; a.No = No; a.scale = 1.f;
-    return a;
-}
-
 int g_backend = 0;  // 0: legacy mma.sync GEMMs everywhere, 1: tcgen05/TMEM GEMMs where the shape is supported
 
+}  // namespace
+
+namespace dp {
 cudaError_t gemm_nt(const GemmNtArgs& a, bool split, cudaStream_t st) {
     if (g_backend == 1 && !a.w_kn && gemm_nt_tc5_supported(a)) return launch_gemm_nt_tc5(a, split, st);
     return launch_gemm_nt(a, split, st);
@@ -125,6 +106,9 @@ cudaError_t gemm_tn(const GemmTnArgs& a, bool split, cudaStream_t st) {
     if (g_backend == 1 && !a.b_rpb && gemm_tn_tc5_supported(a)) return launch_gemm_tn_tc5(a, split, 0, st);
     return launch_gemm_tn(a, split, st);
 }
+}  // namespace dp
+
+namespace {
 
 struct PitWsView {
     double* sums;
@@ -268,6 +252,33 @@ int dp_groupnorm_residual_f32(const float* y, const float* res, float* out, cons
     return 0;
 }
 
+int dp_attention_forward_f32(const float* qkv, float* o, float* lse, int E, int heads, int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo,
+                             int64_t s_t, void* stream) {
+    if (heads <= 0 || E % heads || (E / heads != 16 && E / heads != 32)) return fail("dp_attention_forward_f32: head width E/heads must be 16 or 32");
+    SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
+    CK(launch_attn_fwd(qkv, o, lse, E, heads, m, S(stream)));
+    return 0;
+}
+int dp_attention_backward_f32(const float* qkv, const float* o, const float* lse, const float* d_o, float* d_qkv, int E, int heads, int nseq,
+                              int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, void* stream) {
+    if (heads <= 0 || E % heads || (E / heads != 16 && E / heads != 32)) return fail("dp_attention_backward_f32: head width E/heads must be 16 or 32");
+    SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
+    CK(launch_attn_bwd(qkv, o, lse, d_o, d_qkv, E, heads, m, S(stream)));
+    return 0;
+}
+int dp_add_layernorm_f32(const float* a, const float* b, float* z_out, float* out, const float* res, const float* gamma, const float* beta,
+                         int64_t rows, int E, float eps, void* stream) {
+    if (E != 64 && E != 128 && E != 256) return fail("dp_add_layernorm_f32: E must be 64, 128 or 256 (got %d)", E);
+    CK(launch_add_ln(a, b, z_out, out, res, gamma, beta, rows, E, eps, nullptr, nullptr, nullptr, S(stream)));
+    return 0;
+}
+int dp_layernorm_backward_f32(const float* dy, const float* z, float* dz, float* acc, const float* gamma, int64_t rows, int E, float eps,
+                              float* dgamma, float* dbeta, void* stream) {
+    if (E != 64 && E != 128 && E != 256) return fail("dp_layernorm_backward_f32: E must be 64, 128 or 256 (got %d)", E);
+    CK(launch_ln_bwd(dy, z, dz, acc, gamma, rows, E, eps, dgamma, dbeta, S(stream)));
+    return 0;
+}
+
 int64_t dp_pit_loss_workspace_bytes(int B) { return (int64_t)B * (18 * 8 + 6 * 4) + 64; }
 int dp_pit_loss_forward(const float* est, const float* tgt, int B, int T, int sdr_type, int threshold_byloss, void* ws, float* pw,
                         float* loss, int32_t* perm, void* stream) {
@@ -307,6 +318,7 @@ struct dp_tasnet {
     std::vector<int64_t> off;
     int64_t n_params;
     int npath;
+    int ppath;  // parameter-table entries per path: 12 (DPRNN) or 18 (DPTNet)
     int launches;
 };
 
@@ -329,23 +341,15 @@ int make_geo(const dp_tasnet* h, int B, int T, Geo& g) {
     return 0;
 }
 
-struct Carver {
-    size_t off = 0;
-    size_t take(size_t bytes) {
-        size_t o = off;
-        off += (bytes + 255) & ~(size_t)255;
-        return o;
-    }
-};
-
 struct Layout {
     size_t xp, E, En, Fb, F2, Z, Mk, Mx, D;
     size_t small, small_bytes;  // GroupNorm statistics (zeroed by every forward)
     size_t redz, redz_bytes;    // GroupNorm-backward reductions (zeroed by every backward)
     size_t statsE, mrE, redE;
     std::vector<size_t> X, G, H, Cst, Y, stats, mr, red, dpack;
+    std::vector<size_t> QKV, Oa, LSE, Z1, S1, Z2;  // DPTNet only
     // backward temporaries
-    size_t dXs, dY, dH, dpad, dMx, dMk, dE, dZ, dF2, dtmp;
+    size_t dXs, dY, dH, dpad, dMx, dMk, dE, dZ, dF2, dtmp, dQKV, dOa;
     size_t total;
 };
 
@@ -391,6 +395,26 @@ void make_layout(const dp_tasnet* h, const Geo& g, bool train, Layout& l) {
         l.Y[p] = c.take(g.PT * 64 * f);
     }
     for (int p = nbuf; p < np; ++p) { l.G[p] = l.G[0]; l.H[p] = l.H[0]; l.Cst[p] = l.Cst[0]; l.Y[p] = l.Y[0]; }
+    const bool xf = h->cfg.module == DP_MODULE_DPTNET;
+    l.QKV.assign(np, 0); l.Oa.assign(np, 0); l.LSE.assign(np, 0); l.Z1.assign(np, 0); l.S1.assign(np, 0); l.Z2.assign(np, 0);
+    l.dQKV = l.dOa = 0;
+    if (xf) {
+        for (int p = 0; p < nbuf; ++p) {
+            l.QKV[p] = c.take(g.PT * 192 * f);
+            l.Oa[p] = c.take(g.PT * 64 * f);
+            l.S1[p] = c.take(g.PT * 64 * f);
+            if (train) {
+                l.LSE[p] = c.take(g.PT * 4 * f);
+                l.Z1[p] = c.take(g.PT * 64 * f);
+                l.Z2[p] = c.take(g.PT * 64 * f);
+            }
+        }
+        for (int p = nbuf; p < np; ++p) { l.QKV[p] = l.QKV[0]; l.Oa[p] = l.Oa[0]; l.S1[p] = l.S1[0]; }
+        if (train) {
+            l.dQKV = c.take(g.PT * 192 * f);
+            l.dOa = c.take(g.PT * 64 * f);
+        }
+    }
     if (train) {
         for (int p = 0; p < np; ++p) l.dpack[p] = c.take((65536 + 131072 + 1024) * f);
         l.dpad = c.take((size_t)g.B * nspk * g.Tp * f);
@@ -406,9 +430,6 @@ void make_layout(const dp_tasnet* h, const Geo& g, bool train, Layout& l) {
     }
     l.total = c.off;
 }
-
-template <typename T>
-T* at(void* base, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(base) + off); }
 
 SeqMap path_map(const Geo& g, int pp) {
     SeqMap m;
@@ -433,7 +454,9 @@ int dp_tasnet_create(const dp_tasnet_config* cfg, const int64_t* offsets, int n_
     if (cfg->num_spk < 1 || cfg->num_spk > 4) return fail("dp_tasnet_create: num_spk must be in 1..4");
     if (cfg->block_size <= 0 || (cfg->block_size & 1)) return fail("dp_tasnet_create: block_size must be even and positive");
     if (cfg->layer < 1) return fail("dp_tasnet_create: layer must be >= 1");
-    int need = DP_TASNET_HEAD_PARAMS + DP_TASNET_PATH_PARAMS * 2 * cfg->layer;
+    if (cfg->module != DP_MODULE_DPRNN && cfg->module != DP_MODULE_DPTNET) return fail("dp_tasnet_create: module must be DP_MODULE_DPRNN or DP_MODULE_DPTNET");
+    const int ppath = cfg->module == DP_MODULE_DPTNET ? DP_TASNET_PATH_PARAMS_DPTNET : DP_TASNET_PATH_PARAMS;
+    int need = DP_TASNET_HEAD_PARAMS + ppath * 2 * cfg->layer;
     if (n_offsets != need) return fail("dp_tasnet_create: expected %d parameter offsets, got %d", need, n_offsets);
     for (int i = 0; i < n_offsets; ++i) {
         bool optional = (i >= 9 && i <= 11) && !cfg->unfold;
@@ -446,6 +469,7 @@ int dp_tasnet_create(const dp_tasnet_config* cfg, const int64_t* offsets, int n_
     h->off.assign(offsets, offsets + n_offsets);
     h->n_params = n_params;
     h->npath = 2 * cfg->layer;
+    h->ppath = ppath;
     h->launches = 0;
     *out = h;
     return 0;
@@ -470,7 +494,7 @@ int dp_tasnet_pack(dp_tasnet* h, const float* params, void* pack, void* stream) 
     char* b = static_cast<char*>(pack);
     CK(launch_split_bf16(params, (__nv_bfloat16*)b, (__nv_bfloat16*)(b + flat), h->n_params, S(stream)));
     for (int pp = 0; pp < h->npath; ++pp) {
-        const int64_t* o = h->off.data() + DP_TASNET_HEAD_PARAMS + DP_TASNET_PATH_PARAMS * pp;
+        const int64_t* o = h->off.data() + DP_TASNET_HEAD_PARAMS + h->ppath * pp;
         const float* wi[2] = {params + o[0], params + o[4]};
         const float* wh[2] = {params + o[1], params + o[5]};
         const float* bi[2] = {params + o[2], params + o[6]};
@@ -518,12 +542,50 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
     CK(launch_segment_cl(at<float>(ws, l.Fb), at<float>(ws, l.X[0]), B, g.L, g.K, g.Sc, 64, st)); ++nl;
 
     for (int pp = 0; pp < h->npath; ++pp) {                                                     // dprnn.py:62-82
-        const int64_t* po = o + DP_TASNET_HEAD_PARAMS + DP_TASNET_PATH_PARAMS * pp;
+        const int64_t* po = o + DP_TASNET_HEAD_PARAMS + h->ppath * pp;
         LstmPackView v = view_pack(lpack + (size_t)pp * PK_BYTES);
         float* X = at<float>(ws, l.X[pp]);
         float* G = at<float>(ws, l.G[pp]);
         float* H = at<float>(ws, l.H[pp]);
         float* Y = at<float>(ws, l.Y[pp]);
+        if (h->cfg.module == DP_MODULE_DPTNET) {                                                // dptnet.py:66-82,147-157
+            const SeqMap m = path_map(g, pp);
+            float* QKV = at<float>(ws, l.QKV[pp]);
+            float* Oa = at<float>(ws, l.Oa[pp]);
+            float* S1 = at<float>(ws, l.S1[pp]);
+            {   // in_proj: [q|k|v] = x W_in^T + b_in
+                GemmNtArgs a = nt_args(X, 64, whi + po[12], wlo + po[12], 64, 0, QKV, 192, (int)g.PT, 192, 64);
+                a.bias = params + po[13];
+                CK(launch_gemm_nt(a, sp, st)); ++nl;
+            }
+            CK(launch_attn_fwd(QKV, Oa, train ? at<float>(ws, l.LSE[pp]) : nullptr, 64, 4, m, st)); ++nl;
+            {   // out_proj
+                GemmNtArgs a = nt_args(Oa, 64, whi + po[14], wlo + po[14], 64, 0, Y, 64, (int)g.PT, 64, 64);
+                a.bias = params + po[15];
+                CK(launch_gemm_nt(a, sp, st)); ++nl;
+            }
+            // src = norm1(src + attn)
+            CK(launch_add_ln(Y, X, train ? at<float>(ws, l.Z1[pp]) : nullptr, S1, nullptr, params + po[16], params + po[17], g.PT, 64, 1e-5f,
+                             nullptr, nullptr, nullptr, st)); ++nl;
+            {   // the "feed-forward" is a BiLSTM over the sequence axis + ReLU + Linear(256 -> 64)
+                GemmNtArgs a = nt_args(S1, 64, v.wih_hi, v.wih_lo, 64, 0, G, 1024, (int)g.PT, 1024, 64);
+                a.bias = v.bias;
+                CK(gemm_nt(a, sp, st)); ++nl;
+            }
+            CK(launch_lstm_fwd(v.rec, G, H, train ? at<float>(ws, l.Cst[pp]) : nullptr, m, sp, train != 0, st)); ++nl;
+            {
+                GemmNtArgs a = nt_args(H, 256, whi + po[8], wlo + po[8], 256, 0, Y, 64, (int)g.PT, 64, 256);
+                a.bias = params + po[9];
+                a.relu_a = 1;
+                CK(launch_gemm_nt(a, sp, st)); ++nl;
+            }
+            // out = x + norm2(src + ff)  (+ concat_block after the inter-chunk path when unfold)
+            const bool cat = h->cfg.unfold && (pp & 1);
+            CK(launch_add_ln(Y, S1, train ? at<float>(ws, l.Z2[pp]) : nullptr, at<float>(ws, l.X[pp + 1]), X, params + po[10], params + po[11],
+                             g.PT, 64, 1e-5f, cat ? params + o[9] : nullptr, cat ? params + o[10] : nullptr, cat ? params + o[11] : nullptr,
+                             st)); ++nl;
+            continue;
+        }
         {
             GemmNtArgs a = nt_args(X, 64, v.wih_hi, v.wih_lo, 64, 0, G, 1024, (int)g.PT, 1024, 64);
             a.bias = v.bias;
@@ -581,6 +643,8 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
     const char* lpack = static_cast<const char*>(pack) + 2 * flat;
     const int BLi = (int)g.BL, PTi = (int)g.PT;
     int nl = 0;
+    if (h->cfg.module == DP_MODULE_DPTNET && h->cfg.unfold)
+        return fail("dp_tasnet_backward: module=DPTNet with unfold=True has no backward yet (forward only)");
 
     CK(cudaMemsetAsync(at<char>(ws, l.dpack[0]), 0, (size_t)h->npath * (((65536 + 131072 + 1024) * sizeof(float) + 255) & ~(size_t)255), st));
     // ---- decoder: d_out -> padded rows (overlapping 16-sample frames = dD), dMx = dD Wdec^T, dWdec += Mx^T dD
@@ -618,7 +682,7 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
     CK(launch_segment_cl(at<float>(ws, l.dF2), dXs, B, g.L, g.K, g.Sc, 64, st)); ++nl;
 
     for (int pp = h->npath - 1; pp >= 0; --pp) {
-        const int64_t* po = o + DP_TASNET_HEAD_PARAMS + DP_TASNET_PATH_PARAMS * pp;
+        const int64_t* po = o + DP_TASNET_HEAD_PARAMS + h->ppath * pp;
         LstmPackView v = view_pack(lpack + (size_t)pp * PK_BYTES);
         float* X = at<float>(ws, l.X[pp]);
         float* G = at<float>(ws, l.G[pp]);
@@ -629,6 +693,58 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
         float* dH = at<float>(ws, l.dH);
         float* dpk = at<float>(ws, l.dpack[pp]);
         const SeqMap m = path_map(g, pp);
+        if (h->cfg.module == DP_MODULE_DPTNET) {
+            float* QKV = at<float>(ws, l.QKV[pp]);
+            float* Oa = at<float>(ws, l.Oa[pp]);
+            float* S1 = at<float>(ws, l.S1[pp]);
+            float* dQKV = at<float>(ws, l.dQKV);
+            float* dOa = at<float>(ws, l.dOa);
+            // norm2 backward: dXs is d(x + norm2(z2)); dY <- d z2 (= d ff = the residual part of d src)
+            CK(launch_ln_bwd(dXs, at<float>(ws, l.Z2[pp]), dY, nullptr, params + po[10], g.PT, 64, 1e-5f, grads + po[10], grads + po[11], st)); ++nl;
+            {   // linear2 + ReLU
+                GemmNtArgs a = nt_args(dY, 64, v.projt_hi, v.projt_lo, 64, 0, dH, 256, PTi, 256, 64);
+                a.mask = H; a.ldmask = 256;
+                CK(launch_gemm_nt(a, sp, st)); ++nl;
+                GemmTnArgs t = tn_args(dY, 64, H, 256, grads + po[8], 256, PTi, 64, 256);
+                t.relu_b = 1;
+                CK(launch_gemm_tn(t, sp, st)); ++nl;
+                CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[9], nullptr, st)); ++nl;
+            }
+            CK(launch_lstm_bwd(v.rec, G, at<float>(ws, l.Cst[pp]), dH, dpk + 65536 + 131072, m, sp, st)); ++nl;
+            {   // d src (after norm1) = d z2 + dG W_ih ; LSTM weight gradients
+                GemmNtArgs a = nt_args(G, 1024, v.wiht_hi, v.wiht_lo, 1024, 0, dY, 64, PTi, 64, 1024);
+                a.accumulate = 1;
+                CK(gemm_nt(a, sp, st)); ++nl;
+                GemmTnArgs t = tn_args(G, 1024, S1, 64, dpk, 64, PTi, 1024, 64);
+                CK(gemm_tn(t, sp, st)); ++nl;
+                for (int d = 0; d < 2; ++d) {
+                    GemmTnArgs r = tn_args(G + d * 512, 1024, H + d * 128, 256, dpk + 65536 + d * 65536, 128, PTi, 512, 128);
+                    r.shift = (d == 0 ? -1 : 1) * (int)m.s_t;
+                    r.tdiv = (pp & 1) ? g.K : 1;
+                    r.tmod = m.len;
+                    CK(gemm_tn(r, sp, st)); ++nl;
+                }
+            }
+            // norm1 backward: dY <- d z1 (in place), and the residual branch dXs += d z1
+            CK(launch_ln_bwd(dY, at<float>(ws, l.Z1[pp]), dY, dXs, params + po[16], g.PT, 64, 1e-5f, grads + po[16], grads + po[17], st)); ++nl;
+            {   // out_proj
+                GemmNtArgs a = nt_args(dY, 64, whi + po[14], wlo + po[14], 64, 1, dOa, 64, PTi, 64, 64);
+                CK(launch_gemm_nt(a, sp, st)); ++nl;
+                GemmTnArgs t = tn_args(dY, 64, Oa, 64, grads + po[14], 64, PTi, 64, 64);
+                CK(launch_gemm_tn(t, sp, st)); ++nl;
+                CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[15], nullptr, st)); ++nl;
+            }
+            CK(launch_attn_bwd(QKV, Oa, at<float>(ws, l.LSE[pp]), dOa, dQKV, 64, 4, m, st)); ++nl;
+            {   // in_proj
+                GemmNtArgs a = nt_args(dQKV, 192, whi + po[12], wlo + po[12], 64, 1, dXs, 64, PTi, 64, 192);
+                a.accumulate = 1;
+                CK(launch_gemm_nt(a, sp, st)); ++nl;
+                GemmTnArgs t = tn_args(dQKV, 192, X, 64, grads + po[12], 64, PTi, 192, 64);
+                CK(launch_gemm_tn(t, sp, st)); ++nl;
+                CK(launch_colsum_any(dQKV, 192, PTi, 192, 1.f, grads + po[13], st)); ++nl;
+            }
+            continue;
+        }
         if (h->cfg.unfold && (pp & 1)) {
             CK(launch_concat_bwd(dXs, Y, X, mr, params + po[10], params + po[11], g.PT, g.P, 64, params + o[9], params + o[10], params + o[11],
                                  grads + o[9], grads + o[10], grads + o[11], st)); ++nl;
@@ -689,7 +805,7 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
     }
     // packed LSTM gradients -> natural parameter layout
     for (int pp = 0; pp < h->npath; ++pp) {
-        const int64_t* po = o + DP_TASNET_HEAD_PARAMS + DP_TASNET_PATH_PARAMS * pp;
+        const int64_t* po = o + DP_TASNET_HEAD_PARAMS + h->ppath * pp;
         const float* dpk = at<float>(ws, l.dpack[pp]);
         float* wi[2] = {grads + po[0], grads + po[4]};
         float* wh[2] = {grads + po[1], grads + po[5]};

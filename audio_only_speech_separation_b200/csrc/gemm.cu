@@ -74,6 +74,10 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(const GemmNtArgs p) {
         for (int i = 0; i < 4; ++i) {
             int r = (tid >> 3) + 32 * i, kc = (tid & 7) * 4;
             uint2 hi, lo;
+            if (p.relu_a) {
+                areg[i].x = fmaxf(areg[i].x, 0.f); areg[i].y = fmaxf(areg[i].y, 0.f);
+                areg[i].z = fmaxf(areg[i].z, 0.f); areg[i].w = fmaxf(areg[i].w, 0.f);
+            }
             split_pair(areg[i].x, areg[i].y, hi.x, lo.x);
             split_pair(areg[i].z, areg[i].w, hi.y, lo.y);
             *reinterpret_cast<uint2*>(&As[0][r * AST + kc]) = hi;
@@ -170,6 +174,11 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(const GemmNtArgs p) {
                             x0 += o.x; x1 += o.y;
                         }
                         if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                        if (p.mask) {
+                            const float2 mk = *reinterpret_cast<const float2*>(p.mask + (size_t)row * p.ldmask + col);
+                            x0 = mk.x > 0.f ? x0 : 0.f;
+                            x1 = mk.y > 0.f ? x1 : 0.f;
+                        }
                         *dst = make_float2(x0, x1);
                         r1 += x0 + x1;
                         r2 = fmaf(x0, x0, fmaf(x1, x1, r2));
@@ -237,6 +246,10 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const GemmTnArgs p) {
                     }
                     if (p.b_rpb) q += (long long)(pr / p.b_rpb) * p.b_skip;
                     if (ok) br[i] = *reinterpret_cast<const float4*>(p.B + q * p.ldb + no0 + c);
+                    if (p.relu_b) {
+                        br[i].x = fmaxf(br[i].x, 0.f); br[i].y = fmaxf(br[i].y, 0.f);
+                        br[i].z = fmaxf(br[i].z, 0.f); br[i].w = fmaxf(br[i].w, 0.f);
+                    }
                 }
             }
         }

@@ -434,7 +434,7 @@ cudaError_t launch_tn(const GemmTnArgs& a, bool split, int transpose_out, cudaSt
 }  // namespace
 
 bool gemm_nt_tc5_supported(const GemmNtArgs& a) {
-    if (a.stats != nullptr || a.M <= 0) return false;
+    if (a.stats != nullptr || a.M <= 0 || a.relu_a || a.mask) return false;
     if (a.K % TK || (a.lda & 3) || (a.ldc & 3) || (a.ldw & 7)) return false;
     if (!(a.N == 64 || a.N == 128 || a.N % 256 == 0)) return false;
     return true;
@@ -453,7 +453,7 @@ namespace dp {
 
 // Supported weight-gradient shapes: (Mo, No) in {(1024,64), (512,128), (256,64)}; other shapes use the legacy kernel.
 bool gemm_tn_tc5_supported(const GemmTnArgs& a) {
-    if ((a.lda & 3) || (a.ldb & 3) || a.P <= 0) return false;
+    if ((a.lda & 3) || (a.ldb & 3) || a.P <= 0 || a.relu_b) return false;
     return (a.Mo == 1024 && a.No == 64) || (a.Mo == 512 && a.No == 128) || (a.Mo == 256 && a.No == 64);
 }
 

@@ -28,6 +28,9 @@ struct GemmNtArgs {
     int accumulate;
     double* stats;  // [groups][2] (sum, sumsq) of the stored values, group = row / rows_per_group
     int rows_per_group;
+    int relu_a;         // A is replaced by max(A, 0) on load (the ReLU between dptnet.py:79's LSTM and linear2)
+    const float* mask;  // optional [M, ldmask]: C is zeroed where mask <= 0 (ReLU backward fused into the producing GEMM)
+    int ldmask;
 };
 cudaError_t launch_gemm_nt(const GemmNtArgs& a, bool split, cudaStream_t st);
 // tcgen05 / TMEM version (gemm_tc5.cu); supported(): K % 64 == 0, N in {64, 128, k*256}, w_kn == 0 preferred, no stats
@@ -46,6 +49,7 @@ struct GemmTnArgs {
     int ldc;
     int P, Mo, No;
     float scale;
+    int relu_b;  // B is replaced by max(B, 0) on load
 };
 cudaError_t launch_gemm_tn(const GemmTnArgs& a, bool split, cudaStream_t st);
 // tcgen05 / TMEM version: whole [Mo,No] output resident in TMEM per CTA; transpose_out writes C[col][row]
@@ -134,6 +138,21 @@ cudaError_t launch_mask_bwd(const float* dMx, const float* Mk, const float* E, f
 // out[r, tau] = D[r, t1, j1] + D[r, t2, j2]  (stride = win/2 overlap-add of decoder frames + trim)
 cudaError_t launch_dec_ola(const float* D, float* out, int rows, int L, int win, int T, cudaStream_t st);
 cudaError_t launch_axpy(float* y, const float* x, float a, long long n, cudaStream_t st);
+
+// ---------------- transformer blocks (transformer.cu) ----------------
+// Self-attention of nn.MultiheadAttention on channels-last rows: QKV [P,3E] = [q|k|v] -> O [P,E]; sequences via SeqMap.
+// LSE (optional, [P,heads], log2 domain) is what the backward needs.  Head width E/heads must be 16 or 32.
+cudaError_t launch_attn_fwd(const float* QKV, float* O, float* LSE, int E, int heads, const SeqMap& m, cudaStream_t st);
+cudaError_t launch_attn_bwd(const float* QKV, const float* O, const float* LSE, const float* dO, float* dQKV, int E, int heads,
+                            const SeqMap& m, cudaStream_t st);
+// z = a (+ b) [-> zout]; out = (res ? res : 0) + LayerNorm_E(z) * gamma + beta; then optional unfold affine + PReLU.
+cudaError_t launch_add_ln(const float* a, const float* b, float* zout, float* out, const float* res, const float* gamma, const float* beta,
+                          long long rows, int E, float eps, const float* cw, const float* cb, const float* slope, cudaStream_t st);
+// LayerNorm backward from the saved pre-norm rows z: dz (may alias dy), acc (optional) += dz, dgamma/dbeta accumulated.
+cudaError_t launch_ln_bwd(const float* dy, const float* z, float* dz, float* acc, const float* gamma, long long rows, int E, float eps,
+                          float* dgamma, float* dbeta, cudaStream_t st);
+// out[n] += scale * sum_p A[p*lda + n], any N % 4 == 0
+cudaError_t launch_colsum_any(const float* A, long long lda, int P, int N, float scale, float* out, cudaStream_t st);
 
 // ---------------- loss (loss.cu) ----------------
 struct PitLossWs {  // device scratch, all double unless noted

@@ -8,8 +8,9 @@ construction order so the default initialisation is reproduced bit for bit under
 ``forward`` methods is ever called.  All parameters live as views of ONE flat fp32 buffer, which is what the engine,
 the fused Adam step and the single NCCL gradient all-reduce operate on.
 
-Supported on this path: ``module="DPRNN"``, ``group_size=1``, ``enc_dim=bn_dim=64``, ``hidden_dim=128``,
-``win=16`` (every DPRNN config of the reference), ``unfold`` True or False.  Anything else raises.
+Supported on this path: ``module="DPRNN"`` and ``module="DPTNet"``, ``group_size=1``, ``enc_dim=bn_dim=64``,
+``hidden_dim=128``, ``win=16`` (every DPRNN / DPTNet config of the reference), ``unfold`` True or False (DPTNet with
+``unfold`` is forward-only for now).  Anything else raises.
 """
 from __future__ import annotations
 
@@ -57,12 +58,51 @@ class _DPRNN(nn.Module):
         self.output = nn.Conv2d(input_size, output_size, 1)
 
 
+class _TransformerEncoderLayer(nn.Module):
+    """Parameter container with the keys of DPTNet's ``TransformerEncoderLayer`` (dptnet.py:45-56): attention, a BiLSTM
+    as the "feed-forward", Linear(4*d -> d), two LayerNorms.  Built in the reference's order (same default init)."""
+
+    def __init__(self, d_model, nhead):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=0)
+        self.linear1 = nn.LSTM(d_model, d_model * 2, 1, bidirectional=True)
+        self.linear2 = nn.Linear(d_model * 2 * 2, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+
+class _SingleTransformer(nn.Module):
+    """Key prefix ``transformer.*`` of ``SingleTransformer`` (dptnet.py:85-89)."""
+
+    def __init__(self, input_size):
+        super().__init__()
+        self.transformer = _TransformerEncoderLayer(input_size, 4)
+
+
+class _DPTNet(nn.Module):
+    """Parameter container with the keys of ``DPTNet`` (dptnet.py:99-131), ``num_group == 1``."""
+
+    def __init__(self, input_size, hidden_size, output_size, num_layers, unfold):
+        super().__init__()
+        self.row_xfmr = nn.ModuleList([])
+        self.col_xfmr = nn.ModuleList([])
+        if unfold:
+            row_xfmr = _SingleTransformer(input_size)
+            col_xfmr = _SingleTransformer(input_size)
+            self.concat_block = nn.Sequential(nn.Conv2d(input_size, input_size, 1, 1, groups=input_size), nn.PReLU())
+        for _ in range(num_layers):
+            self.row_xfmr.append(row_xfmr if unfold else _SingleTransformer(input_size))
+            self.col_xfmr.append(col_xfmr if unfold else _SingleTransformer(input_size))
+        self.output = nn.Conv2d(input_size, output_size, 1)
+
+
 class _DPWrapper(nn.Module):
     """Key prefix of ``DP_Wrapper`` (groupcomm.py:49-98): ``seq_model.*``."""
 
-    def __init__(self, input_dim, hidden_dim, output_dim, layer, unfold):
+    def __init__(self, input_dim, hidden_dim, output_dim, layer, unfold, module="DPRNN"):
         super().__init__()
-        self.seq_model = _DPRNN(input_dim, hidden_dim, output_dim, layer, unfold)
+        cls = _DPRNN if module == "DPRNN" else _DPTNet
+        self.seq_model = cls(input_dim, hidden_dim, output_dim, layer, unfold)
 
 
 class _TasNetFunction(torch.autograd.Function):
@@ -105,8 +145,9 @@ class TasNet(BaseModel):
     ):
         super().__init__(sample_rate=sample_rate)
         assert module in ["DPRNN", "DPTNet", "TCN", "SudoRMRF", "GC_TCN", "GC_SudoRMRF"]  # gc3_network.py:25-32
-        if module != "DPRNN":
-            raise NotImplementedError(f"module={module!r}: this build accelerates module='DPRNN' (see DESIGN.md scope table)")
+        if module not in ("DPRNN", "DPTNet"):
+            raise NotImplementedError(f"module={module!r}: this build accelerates the dual-path modules 'DPRNN' and 'DPTNet' "
+                                      "(see DESIGN.md scope table)")
         if group_size != 1:
             raise NotImplementedError("group_size > 1 (GroupComm/TAC) is not on the accelerated path (DESIGN.md scope table)")
         self.num_spk = num_spk
@@ -131,7 +172,7 @@ class TasNet(BaseModel):
             nn.GroupNorm(1, self.enc_dim, eps=torch.finfo(torch.float32).eps),
             nn.Conv1d(self.enc_dim, self.bn_dim, 1, bias=False),
         )
-        self.seq_model = _DPWrapper(self.bn_dim, self.hidden_dim, self.bn_dim, layer, unfold)
+        self.seq_model = _DPWrapper(self.bn_dim, self.hidden_dim, self.bn_dim, layer, unfold, module)
         self.mask = nn.Sequential(nn.Conv1d(self.bn_dim, self.enc_dim * self.num_spk, 1), nn.ReLU(inplace=True))
         self.decoder = nn.ConvTranspose1d(self.enc_dim, 1, self.win, bias=False, stride=self.stride)
         torch.nn.init.xavier_uniform_(self.decoder.weight)
@@ -191,6 +232,17 @@ class TasNet(BaseModel):
             cat[1].weight if cat is not None else None,
         ]
         for i in range(self.layer):
+            if self.model_name == "DPTNet":  # order of DP_TASNET_PATH_PARAMS_DPTNET in include/dualpath_b200.h
+                for x in (sm.row_xfmr[i].transformer, sm.col_xfmr[i].transformer):
+                    r = x.linear1
+                    table += [
+                        r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0,
+                        r.weight_ih_l0_reverse, r.weight_hh_l0_reverse, r.bias_ih_l0_reverse, r.bias_hh_l0_reverse,
+                        x.linear2.weight, x.linear2.bias, x.norm2.weight, x.norm2.bias,
+                        x.self_attn.in_proj_weight, x.self_attn.in_proj_bias, x.self_attn.out_proj.weight, x.self_attn.out_proj.bias,
+                        x.norm1.weight, x.norm1.bias,
+                    ]
+                continue
             for rnn, norm in ((sm.row_rnn[i], sm.row_norm[i]), (sm.col_rnn[i], sm.col_norm[i])):
                 r = rnn.rnn
                 table += [
@@ -236,7 +288,7 @@ class TasNet(BaseModel):
             lib().dp_tasnet_destroy(self._handle)
             self._handle = None
         cfg = _lib.TasnetConfig(self.enc_dim, self.bn_dim, self.hidden_dim, self.win, self.layer, self.num_spk, self.block_size,
-                                int(self.unfold))
+                                int(self.unfold), _lib.MODULE_DPTNET if self.model_name == "DPTNet" else _lib.MODULE_DPRNN)
         arr = (C.c_int64 * len(offsets))(*offsets)
         h = C.c_void_p()
         check(lib().dp_tasnet_create(C.byref(cfg), arr, len(offsets), total, C.byref(h)), "dp_tasnet_create")

@@ -22,6 +22,10 @@ __all__ = [
     "bilstm_forward",
     "bilstm_backward",
     "groupnorm_residual",
+    "attention",
+    "attention_backward",
+    "add_layernorm",
+    "layernorm_backward",
 ]
 
 
@@ -208,3 +212,51 @@ def groupnorm_residual(y, res, gamma, beta, stats, rows_per_group, eps, *, conca
         "dp_groupnorm_residual_f32",
     )
     return out
+
+
+def attention(qkv: torch.Tensor, heads: int, layout: str, *, save=False):
+    """Self-attention core of ``nn.MultiheadAttention`` on a channels-last dual-path tensor ``qkv[B,S,K,3E]`` (the
+    in_proj output ``[q|k|v]``), along K (``intra``) or S (``inter``).  Returns ``(o[B,S,K,E], lse or None)``."""
+    require_cuda(qkv, "qkv")
+    B, S, K, E3 = qkv.shape
+    E = E3 // 3
+    o = torch.empty(B, S, K, E, device=qkv.device, dtype=torch.float32)
+    lse = torch.empty(B * S * K, heads, device=qkv.device, dtype=torch.float32) if save else None
+    nseq, ln, qdiv, s_hi, s_lo, s_t = _seq_map(layout, B, S, K)
+    check(lib().dp_attention_forward_f32(ptr(qkv), ptr(o), ptr(lse), E, heads, nseq, ln, qdiv, s_hi, s_lo, s_t, stream_ptr()),
+          "dp_attention_forward_f32")
+    return o, lse
+
+
+def attention_backward(qkv, o, lse, d_o, heads: int, layout: str):
+    require_cuda(d_o, "d_o")
+    B, S, K, E3 = qkv.shape
+    d_qkv = torch.empty_like(qkv)
+    nseq, ln, qdiv, s_hi, s_lo, s_t = _seq_map(layout, B, S, K)
+    check(lib().dp_attention_backward_f32(ptr(qkv), ptr(o), ptr(lse), ptr(d_o), ptr(d_qkv), E3 // 3, heads, nseq, ln, qdiv, s_hi, s_lo, s_t,
+                                          stream_ptr()), "dp_attention_backward_f32")
+    return d_qkv
+
+
+def add_layernorm(a, b, gamma, beta, eps, *, res=None, save_z=False):
+    """``res + LayerNorm(a + b)`` on rows of ``E`` channels (``nn.LayerNorm`` after a residual add)."""
+    require_cuda(a, "a")
+    E = a.shape[-1]
+    rows = a.numel() // E
+    out = torch.empty_like(a)
+    z = torch.empty_like(a) if save_z else None
+    check(lib().dp_add_layernorm_f32(ptr(a), ptr(b), ptr(z), ptr(out), ptr(res), ptr(gamma), ptr(beta), rows, E, float(eps), stream_ptr()),
+          "dp_add_layernorm_f32")
+    return out, z
+
+
+def layernorm_backward(dy, z, gamma, eps):
+    require_cuda(dy, "dy")
+    E = dy.shape[-1]
+    rows = dy.numel() // E
+    dz = torch.empty_like(dy)
+    dgamma = torch.zeros(E, device=dy.device, dtype=torch.float32)
+    dbeta = torch.zeros(E, device=dy.device, dtype=torch.float32)
+    check(lib().dp_layernorm_backward_f32(ptr(dy), ptr(z), ptr(dz), None, ptr(gamma), rows, E, float(eps), ptr(dgamma), ptr(dbeta),
+                                          stream_ptr()), "dp_layernorm_backward_f32")
+    return dz, dgamma, dbeta

@@ -84,6 +84,23 @@ int dp_groupnorm_residual_f32(const float* y, const float* res, float* out, cons
                               const float* beta, int64_t rows, int rows_per_group, int C, const float* cw, const float* cb,
                               const float* prelu_slope, void* stream);
 
+/* ---- (b') transformer blocks: nn.MultiheadAttention core + nn.LayerNorm, dptnet.py:48-82, sepformer.py:124-215,316-370 - */
+/* Self-attention core on channels-last rows.  qkv[P,3E] = [q | k | v] (the in_proj output), head h uses columns
+ * [h*d,(h+1)*d) of each third, d = E/heads in {16, 32}; softmax(q k^T / sqrt(d)) v -> o[P,E].  Sequence q, time t lives
+ * at row (q/qdiv)*s_hi + (q%qdiv)*s_lo + t*s_t (same map as the LSTM entry points), so neither the reference's
+ * permute().contiguous() copies nor its [B*S*h, L, L] probability tensor exist.  lse (optional, [P,heads]) is saved
+ * for dp_attention_backward_f32. */
+int dp_attention_forward_f32(const float* qkv, float* o, float* lse, int E, int heads, int nseq, int len, int qdiv, int64_t s_hi,
+                             int64_t s_lo, int64_t s_t, void* stream);
+int dp_attention_backward_f32(const float* qkv, const float* o, const float* lse, const float* d_o, float* d_qkv, int E, int heads,
+                              int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, void* stream);
+/* z = a (+ b) (stored to z_out when non-null); out = (res ? res : 0) + LayerNorm_E(z) * gamma + beta.  E in {64,128,256}. */
+int dp_add_layernorm_f32(const float* a, const float* b, float* z_out, float* out, const float* res, const float* gamma,
+                         const float* beta, int64_t rows, int E, float eps, void* stream);
+/* LayerNorm backward from the saved pre-norm rows z: dz (may alias dy); acc (optional) += dz; dgamma/dbeta accumulated. */
+int dp_layernorm_backward_f32(const float* dy, const float* z, float* dz, float* acc, const float* gamma, int64_t rows, int E,
+                              float eps, float* dgamma, float* dbeta, void* stream);
+
 /* ---- (e) fused pairwise SNR / SI-SDR + PIT, losses/matrix.py:13-57, losses/pit_wrapper.py:30-131 ---------- */
 int64_t dp_pit_loss_workspace_bytes(int B);
 /* sdr_type 0 snr, 1 sisdr, 2 sdsdr; n_src = 2.  Outputs: pw[B,2,2] (est,tgt), loss[1], perm[B] (0 identity, 1
@@ -103,8 +120,11 @@ int dp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, d
 
 /* ---- whole-model engine: TasNet(module="DPRNN").forward, gc3_network.py:133-184 --------------------------- */
 typedef struct dp_tasnet dp_tasnet;
+#define DP_MODULE_DPRNN 0  /* look2hear/models/utils/dprnn.py */
+#define DP_MODULE_DPTNET 1 /* look2hear/models/utils/dptnet.py */
 typedef struct {
     int enc_dim, bn_dim, hidden_dim, win, layer, num_spk, block_size, unfold;
+    int module; /* DP_MODULE_* : TasNet(module=...) of gc3_network.py:8-22 */
 } dp_tasnet_config;
 
 /* Parameter table: element offsets into one flat fp32 parameter buffer, in this order:
@@ -114,9 +134,14 @@ typedef struct {
  *   then for path pp = 2*layer + (0 row | 1 col), 12 entries at 12 + 12*pp:
  *   weight_ih, weight_hh, bias_ih, bias_hh, weight_ih_reverse, weight_hh_reverse, bias_ih_reverse,
  *   bias_hh_reverse, proj.weight, proj.bias, norm.weight, norm.bias
- * Shared (unfold) parameters simply repeat the same offsets. */
+ * Shared (unfold) parameters simply repeat the same offsets.
+ * DP_MODULE_DPTNET (dptnet.py:45-56): 18 entries per path at 12 + 18*pp, the transformer layer of row_xfmr/col_xfmr:
+ *   linear1.{weight_ih, weight_hh, bias_ih, bias_hh, and _reverse} (the BiLSTM "feed-forward"), linear2.weight,
+ *   linear2.bias, norm2.weight, norm2.bias, self_attn.in_proj_weight, self_attn.in_proj_bias,
+ *   self_attn.out_proj.weight, self_attn.out_proj.bias, norm1.weight, norm1.bias */
 #define DP_TASNET_HEAD_PARAMS 12
 #define DP_TASNET_PATH_PARAMS 12
+#define DP_TASNET_PATH_PARAMS_DPTNET 18
 int dp_tasnet_create(const dp_tasnet_config* cfg, const int64_t* offsets, int n_offsets, int64_t n_params, dp_tasnet** out);
 void dp_tasnet_destroy(dp_tasnet* h);
 int64_t dp_tasnet_pack_bytes(const dp_tasnet* h);

@@ -93,12 +93,12 @@ def split_feature(x: Tensor, K: int) -> Tuple[Tensor, int]:
     P = K // 2
     rest = seg_rest(L, K)
     S = num_chunks(L, K)
-    k = torch.arange(K).view(K, 1)
-    s = torch.arange(S).view(1, S)
+    k = torch.arange(K, device=x.device).view(K, 1)
+    s = torch.arange(S, device=x.device).view(1, S)
     src = (s - 1) * P + k  # [K,S]
     valid = (src >= 0) & (src < L)
     gathered = x[:, :, src.clamp(0, max(L - 1, 0)).reshape(-1)].reshape(B, N, K, S)
-    out = torch.where(valid.view(1, 1, K, S), gathered, torch.zeros((), dtype=x.dtype))
+    out = torch.where(valid.view(1, 1, K, S), gathered, torch.zeros((), dtype=x.dtype, device=x.device))
     return out.contiguous(), rest
 
 
@@ -111,7 +111,7 @@ def merge_feature(y: Tensor, rest: int) -> Tensor:
     B, N, K, S = y.shape
     P = K // 2
     L = (S // 2) * K - P - rest
-    t = torch.arange(L)
+    t = torch.arange(L, device=y.device)
     k1, s1 = (t + P) % K, 2 * ((t + P) // K)
     k2, s2 = t % K, 2 * (t // K) + 1
     flat = y.reshape(B, N, K * S)
@@ -182,7 +182,9 @@ def bilstm(x: Tensor, sd: StateDict, prefix: str, impl: str = "aten", mm: MatMul
         H = fw[1].shape[1]
         nb = x.shape[0] if batch_first else x.shape[1]
         zeros = x.new_zeros(2, nb, H)
-        out, _, _ = torch.lstm(x, (zeros, zeros), fw + bw, True, 1, 0.0, False, True, batch_first)
+        # the "train" flag only selects cuDNN's training kernels (needed for backward on CUDA); dropout is 0 on this path
+        train = torch.is_grad_enabled() and any(t.requires_grad for t in fw + bw + [x])
+        out, _, _ = torch.lstm(x, (zeros, zeros), fw + bw, True, 1, 0.0, train, True, batch_first)
         return out
     xb = x if batch_first else x.transpose(0, 1)
     out = torch.cat([lstm_direction(xb, *fw, reverse=False, mm=mm), lstm_direction(xb, *bw, reverse=True, mm=mm)], dim=2)

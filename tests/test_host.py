@@ -92,7 +92,7 @@ def test_unsupported_configs_fail_loudly():
     from audio_only_speech_separation_b200.models import TasNet
 
     with pytest.raises(NotImplementedError):
-        TasNet(module="DPTNet")
+        TasNet(module="TCN")
     with pytest.raises(NotImplementedError):
         TasNet(group_size=16)
     with pytest.raises(AssertionError):
