@@ -248,7 +248,103 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = fmaf(a, x[i], y[i]);
 }
 
+__global__ void __launch_bounds__(256) add_pe_kernel(const float4* __restrict__ x, const float4* __restrict__ pe, float4* __restrict__ out,
+                                                     long long rows, int E4, int K, int S, int inter) {
+    const long long total = rows * E4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % E4);
+        const long long p = i / E4;
+        const int t = inter ? (int)((p / K) % S) : (int)(p % K);
+        float4 v = ldg_stream(x + i), w = pe[(size_t)t * E4 + c4];
+        out[i] = make_float4(v.x + w.x, v.y + w.y, v.z + w.z, v.w + w.w);
+    }
+}
+
+// grid (pieces, groups): fp32 partial sums per thread over <= 64 rows, fp64 across threads/CTAs
+constexpr int GS_ROWS = 1024;
+__global__ void __launch_bounds__(256) group_stats_kernel(const float4* __restrict__ y, int rpg, int C4, double* __restrict__ stats) {
+    __shared__ double sh[8][2];
+    const int g = blockIdx.y;
+    const long long r0 = (long long)blockIdx.x * GS_ROWS, r1 = min((long long)rpg, r0 + GS_ROWS);
+    const long long beg = ((long long)g * rpg + r0) * C4, end = ((long long)g * rpg + r1) * C4;
+    double s1 = 0.0, s2 = 0.0;
+    for (long long i0 = beg + threadIdx.x; i0 < end; i0 += 256 * 16) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const long long i = i0 + (long long)u * 256;
+            if (i < end) {
+                float4 v = ldg_stream(y + i);
+                a += (v.x + v.y) + (v.z + v.w);
+                b = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, b))));
+            }
+        }
+        s1 += a; s2 += b;
+    }
+    s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5][0] = s1; sh[threadIdx.x >> 5][1] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += sh[w][0]; b += sh[w][1]; }
+        atomicAdd(stats + 2 * g, a);
+        atomicAdd(stats + 2 * g + 1, b);
+    }
+}
+
+__global__ void __launch_bounds__(256) prelu_kernel(const float4* __restrict__ x, float4* __restrict__ out, long long n4, const float* __restrict__ slope) {
+    const float a = slope[0];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = ldg_stream(x + i);
+        out[i] = make_float4(prelu_f(v.x, a), prelu_f(v.y, a), prelu_f(v.z, a), prelu_f(v.w, a));
+    }
+}
+
+__global__ void dec_ola_general_kernel(const float* __restrict__ D, float* __restrict__ out, int B, int nspk, int L, int win, int T, int spk_major) {
+    const int st = win / 2;
+    const long long total = (long long)B * nspk * T;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / T), tau = (int)(i % T);  // r = b*nspk + c : row of D
+        const int t1 = tau / st, j1 = tau - t1 * st;
+        float v = 0.f;
+        if (t1 < L) v = D[((size_t)r * L + t1) * win + j1];
+        if (t1 >= 1 && t1 - 1 < L) v += D[((size_t)r * L + t1 - 1) * win + j1 + st];
+        const int b = r / nspk, c = r % nspk;
+        const int ro = spk_major ? c * B + b : r;
+        out[(size_t)ro * T + tau] = v;
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_add_pe(const float* x, const float* pe, float* out, long long rows, int E, int K, int S, int inter, cudaStream_t st) {
+    if (rows <= 0) return cudaSuccess;
+    if (E & 3) return cudaErrorInvalidValue;
+    add_pe_kernel<<<grid_for(rows * (E / 4)), 256, 0, st>>>((const float4*)x, (const float4*)pe, (float4*)out, rows, E / 4, K, S, inter);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_group_stats(const float* y, long long rows, int rows_per_group, int C, double* stats, cudaStream_t st) {
+    if (rows <= 0) return cudaSuccess;
+    if ((C & 3) || rows % rows_per_group) return cudaErrorInvalidValue;
+    dim3 grid(ceil_div(rows_per_group, GS_ROWS), (unsigned)(rows / rows_per_group));
+    group_stats_kernel<<<grid, 256, 0, st>>>((const float4*)y, rows_per_group, C / 4, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prelu(const float* x, float* out, long long n, const float* slope, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (n & 3) return cudaErrorInvalidValue;
+    prelu_kernel<<<grid_for(n / 4), 256, 0, st>>>((const float4*)x, (float4*)out, n / 4, slope);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dec_ola_general(const float* D, float* out, int B, int nspk, int L, int win, int T, int spk_major, cudaStream_t st) {
+    long long total = (long long)B * nspk * T;
+    if (total <= 0) return cudaSuccess;
+    dec_ola_general_kernel<<<grid_for(total), 256, 0, st>>>(D, out, B, nspk, L, win, T, spk_major);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_gn_finalize(const double* stats, float* mr, int groups, double cnt, double eps, cudaStream_t st) {
     if (groups <= 0) return cudaSuccess;

@@ -173,7 +173,13 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(const GemmNtArgs p) {
                             float2 o = *dst;
                             x0 += o.x; x1 += o.y;
                         }
-                        if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                        if (p.relu == 1) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                        else if (p.relu == 2) { x0 = tanhf(x0); x1 = tanhf(x1); }
+                        else if (p.relu == 3) { x0 = 1.0f / (1.0f + expf(-x0)); x1 = 1.0f / (1.0f + expf(-x1)); }
+                        if (p.mul_c) {
+                            float2 o = *dst;
+                            x0 *= o.x; x1 *= o.y;
+                        }
                         if (p.mask) {
                             const float2 mk = *reinterpret_cast<const float2*>(p.mask + (size_t)row * p.ldmask + col);
                             x0 = mk.x > 0.f ? x0 : 0.f;

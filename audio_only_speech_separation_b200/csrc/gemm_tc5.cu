@@ -434,7 +434,7 @@ cudaError_t launch_tn(const GemmTnArgs& a, bool split, int transpose_out, cudaSt
 }  // namespace
 
 bool gemm_nt_tc5_supported(const GemmNtArgs& a) {
-    if (a.stats != nullptr || a.M <= 0 || a.relu_a || a.mask) return false;
+    if (a.stats != nullptr || a.M <= 0 || a.relu_a || a.mask || a.relu > 1 || a.mul_c) return false;
     if (a.K % TK || (a.lda & 3) || (a.ldc & 3) || (a.ldw & 7)) return false;
     if (!(a.N == 64 || a.N == 128 || a.N % 256 == 0)) return false;
     return true;

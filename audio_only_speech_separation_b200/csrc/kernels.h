@@ -24,8 +24,9 @@ struct GemmNtArgs {
     int M, N, K;
     const float* bias;
     float bias_scale;
-    int relu;
-    int accumulate;
+    int relu;        // output activation: 0 none, 1 ReLU, 2 tanh, 3 sigmoid
+    int accumulate;  // C += ...
+    int mul_c;       // after the activation: C = act(...) * C_old  (gated tanh * sigmoid pair, sepformer.py:747)
     double* stats;  // [groups][2] (sum, sumsq) of the stored values, group = row / rows_per_group
     int rows_per_group;
     int relu_a;         // A is replaced by max(A, 0) on load (the ReLU between dptnet.py:79's LSTM and linear2)
@@ -138,6 +139,13 @@ cudaError_t launch_mask_bwd(const float* dMx, const float* Mk, const float* E, f
 // out[r, tau] = D[r, t1, j1] + D[r, t2, j2]  (stride = win/2 overlap-add of decoder frames + trim)
 cudaError_t launch_dec_ola(const float* D, float* out, int rows, int L, int win, int T, cudaStream_t st);
 cudaError_t launch_axpy(float* y, const float* x, float a, long long n, cudaStream_t st);
+// SepFormer helpers (sepformer.py): out[p,:] = x[p,:] + pe[t(p),:] with t = k (intra) or s (inter) of position p = (b*S+s)*K+k
+cudaError_t launch_add_pe(const float* x, const float* pe, float* out, long long rows, int E, int K, int S, int inter, cudaStream_t st);
+// stats[g] += (sum, sumsq) over the rows of group g = row / rows_per_group (gLN statistics, normalizations.py:17-47)
+cudaError_t launch_group_stats(const float* y, long long rows, int rows_per_group, int C, double* stats, cudaStream_t st);
+cudaError_t launch_prelu(const float* x, float* out, long long n, const float* slope, cudaStream_t st);
+// decoder overlap-add without front padding; row (b,c) of D goes to output row c*B+b (spk_major) or b*nspk+c; zero beyond the frames
+cudaError_t launch_dec_ola_general(const float* D, float* out, int B, int nspk, int L, int win, int T, int spk_major, cudaStream_t st);
 
 // ---------------- transformer blocks (transformer.cu) ----------------
 // Self-attention of nn.MultiheadAttention on channels-last rows: QKV [P,3E] = [q|k|v] -> O [P,E]; sequences via SeqMap.

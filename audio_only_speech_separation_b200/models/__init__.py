@@ -1,8 +1,9 @@
 """Model registry with the lookup contract of look2hear/models/__init__.py:29-56."""
 from .base_model import BaseModel
+from .sepformer import Sepformer
 from .tasnet import TasNet
 
-__all__ = ["TasNet", "BaseModel"]
+__all__ = ["TasNet", "Sepformer", "BaseModel"]
 
 
 def register_model(custom_model):

@@ -157,6 +157,41 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
 /* number of kernels the last forward / backward call of this handle launched */
 int dp_tasnet_last_launches(const dp_tasnet* h);
 
+/* ---- whole-model engine: Sepformer.forward, look2hear/models/sepformer.py:986-1016 (inference) ---------------- */
+typedef struct dp_sepformer dp_sepformer;
+typedef struct {
+    int enc_dim;     /* encoder_out_nchannels (64, 128 or 256)          sepformer.py:906 */
+    int win;         /* encoder_kernel_size (stride = win / 2)           :904 */
+    int chunk;       /* masknet_chunksize K                              :907 */
+    int num_blocks;  /* masknet_numlayers                                :908 */
+    int num_spk;     /* masknet_numspks                                  :910 */
+    int intra_layers, inter_layers, intra_heads, inter_heads, intra_dffn, inter_dffn;
+    int intra_pe, inter_pe;                    /* *_use_positional */
+    int intra_norm_before, inter_norm_before;  /* pre-norm (True in configs/sepformer_base.yml) or post-norm layers */
+} dp_sepformer_config;
+
+/* Parameter table: element offsets into one flat fp32 buffer (parameters AND the pos_enc.pe buffers), in this order:
+ *   0 encoder.conv1d.weight  1 masknet.norm.weight  2 masknet.norm.bias  3 masknet.conv1d.weight  4 masknet.prelu.weight
+ *   5 masknet.conv2d.weight  6 masknet.conv2d.bias  7 masknet.output.0.weight  8 masknet.output.0.bias
+ *   9 masknet.output_gate.0.weight  10 masknet.output_gate.0.bias  11 masknet.end_conv1x1.weight  12 decoder.weight
+ * then for every block j and path (intra_mdl, inter_mdl) a run of 1 + 12*layers + 4 entries:
+ *   pos_enc.pe (-1 when positional encoding is off), then per layer: self_att.att.in_proj_weight, in_proj_bias,
+ *   out_proj.weight, out_proj.bias, pos_ffn.ffn.0.weight, ffn.0.bias, ffn.3.weight, ffn.3.bias, norm1.weight, norm1.bias,
+ *   norm2.weight, norm2.bias; then mdl.norm.weight, mdl.norm.bias, {intra,inter}_norm.gamma, {intra,inter}_norm.beta */
+#define DP_SEPFORMER_HEAD_PARAMS 13
+#define DP_SEPFORMER_LAYER_PARAMS 12
+#define DP_SEPFORMER_PE_LEN 2500 /* PositionalEncoding max_len, sepformer.py:61 */
+int dp_sepformer_create(const dp_sepformer_config* cfg, const int64_t* offsets, int n_offsets, int64_t n_params, dp_sepformer** out);
+void dp_sepformer_destroy(dp_sepformer* h);
+int64_t dp_sepformer_pack_bytes(const dp_sepformer* h);
+int64_t dp_sepformer_workspace_bytes(const dp_sepformer* h, int B, int T);
+/* bf16 hi/lo split of the flat buffer; call again whenever the parameters changed */
+int dp_sepformer_pack(dp_sepformer* h, const float* params, void* pack, void* stream);
+/* mixture[B,T] -> est[B,num_spk,T] (rows laid out exactly like the reference's reshape, sepformer.py:1004) */
+int dp_sepformer_forward(dp_sepformer* h, const float* params, const void* pack, const float* mixture, float* est, void* workspace,
+                         int B, int T, int precision, void* stream);
+int dp_sepformer_last_launches(const dp_sepformer* h);
+
 #ifdef __cplusplus
 }
 #endif

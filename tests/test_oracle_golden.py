@@ -111,3 +111,48 @@ def test_adam_clip_oracle_matches_torch():
         O.adam_clip_step(mine, [g * step for g in gs], m, v, step)
     for a, b in zip(mine, ref):
         assert torch.allclose(a, b.detach(), rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ SepFormer
+SEPFORMER_CASES = ["sepformer_small_b2_t3000", "sepformer_small_b1_t1001_1d", "sepformer_smallpost_b1_t2001", "sepformer_base_b1_t16000"]
+
+
+@pytest.mark.parametrize("case", SEPFORMER_CASES)
+def test_sepformer_oracle_vs_golden(manifest, case):
+    """oracle/sepformer_oracle.py against outputs of the real look2hear Sepformer; the drop-in model's default
+    initialisation must reproduce the reference's weights (checksums pinned in the manifest)."""
+    from audio_only_speech_separation_b200.models import Sepformer
+    from oracle import sepformer_oracle as SO
+
+    c = manifest["cases"][case]
+    torch.manual_seed(c["seed"])
+    m = Sepformer(sample_rate=c["sample_rate"], **c["audionet_config"])
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    ref = manifest["state_dicts"][c["config"]]
+    assert set(sd) == set(ref)
+    for k, (s, a, *shape) in ref.items():
+        assert list(sd[k].shape) == shape, k
+        assert abs(float(sd[k].double().sum()) - s) < 1e-9 and abs(float(sd[k].double().abs().sum()) - a) < 1e-9, k
+    assert sum(p.numel() for p in m.parameters()) == manifest["n_params"][c["config"]]
+    z = load_npz(f"model_{case}.npz")
+    with torch.no_grad():
+        y = SO.sepformer_forward(sd, torch.from_numpy(z["x"]), **c["audionet_config"])
+    assert tuple(y.shape) == z["y"].shape
+    assert rel_l2(y, torch.from_numpy(z["y"])) < 5e-6
+
+
+def test_sepformer_batch_scramble_quirk(manifest):
+    """sepformer.py:1004: decoder rows are ordered (spk, b) but reshaped as (b, spk) -- kept for parity (SURVEY A.4 #7)."""
+    from audio_only_speech_separation_b200.models import Sepformer
+    from oracle import sepformer_oracle as SO
+
+    c = manifest["cases"]["sepformer_small_b2_t3000"]
+    torch.manual_seed(0)
+    sd = {k: v.detach() for k, v in Sepformer(sample_rate=8000, **c["audionet_config"]).state_dict().items()}
+    x = torch.from_numpy(load_npz("model_sepformer_small_b2_t3000.npz")["x"])
+    with torch.no_grad():
+        both = SO.sepformer_forward(sd, x, **c["audionet_config"])
+        one = [SO.sepformer_forward(sd, x[i : i + 1], **c["audionet_config"])[0] for i in range(2)]  # [spk, T] each
+    # row r = spk*B + b of the decoder lands at est[r // spks, r % spks]
+    assert rel_l2(both[0, 0], one[0][0]) < 1e-5 and rel_l2(both[0, 1], one[1][0]) < 1e-5
+    assert rel_l2(both[1, 0], one[0][1]) < 1e-5 and rel_l2(both[1, 1], one[1][1]) < 1e-5
