@@ -47,6 +47,9 @@ PROTOTYPES = {
     "dp_segment_cl_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "dp_overlap_add_cl_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "dp_linear_f32": (_i, [_p, _i64, _p, _p, _i, _i, _p, _f, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "dp_linear_planes_f32": (_i, [_p, _p, _i64, _p, _p, _i, _p, _f, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "dp_linear_wgrad_planes_f32": (_i, [_p, _p, _i64, _i, _p, _p, _i64, _i, _p, _p, _i64, _i, _p, _i, _i, _p, _i, _i, _i, _f, _i, _p]),
+    "dp_split_rows_f32": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _p]),
     "dp_linear_wgrad_f32": (_i, [_p, _i, _p, _i64, _p, _i, _i, _i, _i, _f, _i, _p]),
     "dp_split_bf16": (_i, [_p, _p, _p, _i64, _p]),
     "dp_lstm_pack_bytes": (_i64, []),

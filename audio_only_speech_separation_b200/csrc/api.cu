@@ -93,11 +93,13 @@ LstmPackOut out_pack(void* pack) {
     return o;
 }
 
-int g_backend = 0;  // 0: legacy mma.sync GEMMs everywhere, 1: tcgen05/TMEM GEMMs where the shape is supported
+int g_backend = 2;  // 0: mma.sync GEMMs everywhere; 1: first-generation tcgen05 kernels (threads convert fp32 operands);
+                    // 2 (default): TMA-fed tcgen05 kernels on pre-split bf16 operand planes (gemm_tma.cu) in the engines
 
 }  // namespace
 
 namespace dp {
+int gemm_backend() { return g_backend; }
 cudaError_t gemm_nt(const GemmNtArgs& a, bool split, cudaStream_t st) {
     if (g_backend == 1 && !a.w_kn && gemm_nt_tc5_supported(a)) return launch_gemm_nt_tc5(a, split, st);
     return launch_gemm_nt(a, split, st);
@@ -131,7 +133,7 @@ extern "C" {
 
 int dp_version(void) { return 101; }
 int dp_set_gemm_backend(int backend) {
-    if (backend != 0 && backend != 1) return fail("dp_set_gemm_backend: 0 (mma.sync) or 1 (tcgen05)");
+    if (backend < 0 || backend > 2) return fail("dp_set_gemm_backend: 0 (mma.sync), 1 (tcgen05, converting threads) or 2 (TMA-fed tcgen05 on planes)");
     g_backend = backend;
     return 0;
 }
@@ -185,6 +187,36 @@ int dp_linear_f32(const float* A, int64_t lda, const void* w_hi, const void* w_l
     a.bias = bias; a.bias_scale = bias_scale; a.relu = relu; a.accumulate = accumulate; a.stats = stats;
     a.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
     CK(gemm_nt(a, is_split(precision), S(stream)));
+    return 0;
+}
+int dp_linear_planes_f32(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo, int ldw, const float* bias,
+                         float bias_scale, float* C, int ldc, void* c_hi, void* c_lo, int ldch, int M, int N, int K, int act, int accumulate,
+                         int precision, void* stream) {
+    TmaGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A_hi = (const __nv_bfloat16*)a_hi; a.A_lo = (const __nv_bfloat16*)a_lo; a.lda = lda;
+    a.W_hi = (const __nv_bfloat16*)w_hi; a.W_lo = (const __nv_bfloat16*)w_lo; a.ldw = ldw;
+    a.M = M; a.N = N; a.K = K; a.C = C; a.ldc = ldc; a.C_hi = (__nv_bfloat16*)c_hi; a.C_lo = (__nv_bfloat16*)c_lo; a.ldch = ldch;
+    a.bias = bias; a.bias_scale = bias_scale; a.act = act; a.accumulate = accumulate;
+    if (!gemm_tma_nt_supported(a)) return fail("dp_linear_planes_f32: unsupported shape (need K %% 64 == 0, N %% 64 == 0, aligned strides)");
+    CK(launch_gemm_tma_nt(a, is_split(precision), S(stream)));
+    return 0;
+}
+int dp_linear_wgrad_planes_f32(const void* a_hi, const void* a_lo, int64_t lda, int Mo, const void* b0_hi, const void* b0_lo, int64_t ldb0, int nb0,
+                               const void* b1_hi, const void* b1_lo, int64_t ldb1, int nb1, float* C0, int ldc0, int tr0, float* C1, int ldc1,
+                               int tr1, int P, float scale, int precision, void* stream) {
+    TmaWgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A_hi = (const __nv_bfloat16*)a_hi; a.A_lo = (const __nv_bfloat16*)a_lo; a.lda = lda; a.Mo = Mo;
+    a.B0_hi = (const __nv_bfloat16*)b0_hi; a.B0_lo = (const __nv_bfloat16*)b0_lo; a.ldb0 = ldb0; a.nb0 = nb0;
+    a.B1_hi = (const __nv_bfloat16*)b1_hi; a.B1_lo = (const __nv_bfloat16*)b1_lo; a.ldb1 = ldb1; a.nb1 = nb1;
+    a.C0 = C0; a.ldc0 = ldc0; a.transpose0 = tr0; a.C1 = C1; a.ldc1 = ldc1; a.transpose1 = tr1; a.P = P; a.scale = scale;
+    if (!gemm_tma_tn_supported(a)) return fail("dp_linear_wgrad_planes_f32: unsupported shape (Mo %% 128, nb %% 64, nb0 + nb1 <= 256, aligned strides)");
+    CK(launch_gemm_tma_tn(a, is_split(precision), S(stream)));
+    return 0;
+}
+int dp_split_rows_f32(const float* src, int64_t ld, void* hi, void* lo, int64_t rows, int C, int relu, void* stream) {
+    CK(launch_split_rows(src, ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, C, relu, S(stream)));
     return 0;
 }
 int dp_linear_wgrad_f32(const float* A, int lda, const float* B, int64_t ldb, float* dW, int ldc, int P, int Mo, int No, float scale,
@@ -348,6 +380,8 @@ struct Layout {
     size_t statsE, mrE, redE;
     std::vector<size_t> X, G, H, Cst, Y, stats, mr, red, dpack;
     std::vector<size_t> QKV, Oa, LSE, Z1, S1, Z2;  // DPTNet only
+    std::vector<size_t> Xhl, Hhl, Hphl;            // bf16 hi/lo operand planes (TMA backend): [hi | lo]
+    size_t dGhl, dYhl;
     // backward temporaries
     size_t dXs, dY, dH, dpad, dMx, dMk, dE, dZ, dF2, dtmp, dQKV, dOa;
     size_t total;
@@ -395,6 +429,26 @@ void make_layout(const dp_tasnet* h, const Geo& g, bool train, Layout& l) {
         l.Y[p] = c.take(g.PT * 64 * f);
     }
     for (int p = nbuf; p < np; ++p) { l.G[p] = l.G[0]; l.H[p] = l.H[0]; l.Cst[p] = l.Cst[0]; l.Y[p] = l.Y[0]; }
+    // operand planes of the TMA-fed GEMMs (hi plane followed by lo plane)
+    l.Xhl.assign(np + 1, 0); l.Hhl.assign(np, 0); l.Hphl.assign(np, 0);
+    l.dGhl = l.dYhl = 0;
+    if (h->cfg.module == DP_MODULE_DPRNN) {
+        if (train) {
+            for (int p = 0; p <= np; ++p) l.Xhl[p] = c.take(g.PT * 64 * 2 * 2);
+        } else {
+            size_t x = c.take(g.PT * 64 * 2 * 2);
+            for (int p = 0; p <= np; ++p) l.Xhl[p] = x;
+        }
+        for (int p = 0; p < nbuf; ++p) {
+            l.Hhl[p] = c.take(g.PT * 256 * 2 * 2);
+            l.Hphl[p] = train ? c.take(g.PT * 256 * 2 * 2) : 0;
+        }
+        for (int p = nbuf; p < np; ++p) { l.Hhl[p] = l.Hhl[0]; l.Hphl[p] = l.Hphl[0]; }
+        if (train) {
+            l.dGhl = c.take(g.PT * 1024 * 2 * 2);
+            l.dYhl = c.take(g.PT * 64 * 2 * 2);
+        }
+    }
     const bool xf = h->cfg.module == DP_MODULE_DPTNET;
     l.QKV.assign(np, 0); l.Oa.assign(np, 0); l.LSE.assign(np, 0); l.Z1.assign(np, 0); l.S1.assign(np, 0); l.Z2.assign(np, 0);
     l.dQKV = l.dOa = 0;
@@ -429,6 +483,15 @@ void make_layout(const dp_tasnet* h, const Geo& g, bool train, Layout& l) {
         l.dtmp = c.take(g.BL * 64 * f);
     }
     l.total = c.off;
+}
+
+TmaGemmArgs tma_args(const __nv_bfloat16* ahl, long long plane, long long lda, const __nv_bfloat16* whi, const __nv_bfloat16* wlo, int ldw,
+                     float* C, int ldc, int M, int N, int K) {
+    TmaGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A_hi = ahl; a.A_lo = ahl + plane; a.lda = lda; a.W_hi = whi; a.W_lo = wlo; a.ldw = ldw;
+    a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K; a.bias_scale = 1.f;
+    return a;
 }
 
 SeqMap path_map(const Geo& g, int pp) {
@@ -540,6 +603,12 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
     }
     // segmentation into 50%-overlapping chunks, channels-last                                     gc3_basics.py:79-91
     CK(launch_segment_cl(at<float>(ws, l.Fb), at<float>(ws, l.X[0]), B, g.L, g.K, g.Sc, 64, st)); ++nl;
+    const bool tma = g_backend == 2 && h->cfg.module == DP_MODULE_DPRNN;
+    const long long plX = g.PT * 64, plH = g.PT * 256;  // elements per plane
+    if (tma) {
+        __nv_bfloat16* x0 = at<__nv_bfloat16>(ws, l.Xhl[0]);
+        CK(launch_split_rows(at<float>(ws, l.X[0]), 64, x0, sp ? x0 + plX : nullptr, g.PT, 64, 0, st)); ++nl;
+    }
 
     for (int pp = 0; pp < h->npath; ++pp) {                                                     // dprnn.py:62-82
         const int64_t* po = o + DP_TASNET_HEAD_PARAMS + h->ppath * pp;
@@ -584,6 +653,36 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
             CK(launch_add_ln(Y, S1, train ? at<float>(ws, l.Z2[pp]) : nullptr, at<float>(ws, l.X[pp + 1]), X, params + po[10], params + po[11],
                              g.PT, 64, 1e-5f, cat ? params + o[9] : nullptr, cat ? params + o[10] : nullptr, cat ? params + o[11] : nullptr,
                              st)); ++nl;
+            continue;
+        }
+        if (tma) {
+            // every GEMM operand is a pair of bf16 planes written by its producer; TMA -> tcgen05 (gemm_tma.cu)
+            __nv_bfloat16* Xhl = at<__nv_bfloat16>(ws, l.Xhl[pp]);
+            __nv_bfloat16* Hhl = at<__nv_bfloat16>(ws, l.Hhl[pp]);
+            {
+                TmaGemmArgs a = tma_args(Xhl, plX, 64, v.wih_hi, v.wih_lo, 64, G, 1024, (int)g.PT, 1024, 64);
+                a.bias = v.bias;
+                CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+            }
+            LstmPlanes pl;
+            pl.h_hi = Hhl; pl.h_lo = sp ? Hhl + plH : nullptr;
+            pl.hp_hi = train ? at<__nv_bfloat16>(ws, l.Hphl[pp]) : nullptr;
+            pl.hp_lo = (train && sp) ? pl.hp_hi + plH : nullptr;
+            CK(launch_lstm_fwd(v.rec, G, nullptr, train ? at<float>(ws, l.Cst[pp]) : nullptr, path_map(g, pp), sp, train != 0, st, &pl)); ++nl;
+            {
+                TmaGemmArgs a = tma_args(Hhl, plH, 256, whi + po[8], wlo + po[8], 256, Y, 64, (int)g.PT, 64, 256);
+                a.bias = params + po[9];
+                a.stats = at<double>(ws, l.stats[pp]); a.rows_per_group = g.P;
+                CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+            }
+            CK(launch_gn_finalize(at<double>(ws, l.stats[pp]), at<float>(ws, l.mr[pp]), B, (double)g.P * 64, 1e-8, st)); ++nl;
+            const bool cat = h->cfg.unfold && (pp & 1);
+            CK(launch_gn_apply(Y, X, at<float>(ws, l.X[pp + 1]), at<float>(ws, l.mr[pp]), params + po[10], params + po[11], g.PT, g.P, 64,
+                               cat ? params + o[9] : nullptr, cat ? params + o[10] : nullptr, cat ? params + o[11] : nullptr, st)); ++nl;
+            if (pp + 1 < h->npath) {
+                __nv_bfloat16* xn = at<__nv_bfloat16>(ws, l.Xhl[pp + 1]);
+                CK(launch_split_rows(at<float>(ws, l.X[pp + 1]), 64, xn, sp ? xn + plX : nullptr, g.PT, 64, 0, st)); ++nl;
+            }
             continue;
         }
         {
@@ -752,6 +851,45 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
         // GroupNorm backward (dXs itself is the residual branch of the gradient)
         CK(launch_gn_bwd_reduce(dXs, Y, mr, params + po[10], g.PT, g.P, 64, at<double>(ws, l.red[pp]), grads + po[10], grads + po[11], st)); ++nl;
         CK(launch_gn_bwd_apply(dXs, Y, dY, mr, at<double>(ws, l.red[pp]), params + po[10], g.PT, g.P, 64, st)); ++nl;
+        if (g_backend == 2) {
+            const long long plX = g.PT * 64, plH = g.PT * 256, plG = g.PT * 1024;
+            __nv_bfloat16* dYhl = at<__nv_bfloat16>(ws, l.dYhl);
+            __nv_bfloat16* dGhl = at<__nv_bfloat16>(ws, l.dGhl);
+            const __nv_bfloat16* Xhl = at<__nv_bfloat16>(ws, l.Xhl[pp]);
+            const __nv_bfloat16* Hhl = at<__nv_bfloat16>(ws, l.Hhl[pp]);
+            const __nv_bfloat16* Hphl = at<__nv_bfloat16>(ws, l.Hphl[pp]);
+            CK(launch_split_rows(dY, 64, dYhl, sp ? dYhl + plX : nullptr, g.PT, 64, 0, st)); ++nl;
+            {   // out-projection Linear(256 -> 64): dH = dY Wp ; dWp = dY^T H (computed as H^T dY, stored transposed) ; dbp
+                TmaGemmArgs a = tma_args(dYhl, plX, 64, v.projt_hi, v.projt_lo, 64, dH, 256, PTi, 256, 64);
+                CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                TmaWgradArgs t;
+                memset(&t, 0, sizeof(t));
+                t.A_hi = Hhl; t.A_lo = Hhl + plH; t.lda = 256; t.Mo = 256;
+                t.B0_hi = dYhl; t.B0_lo = dYhl + plX; t.ldb0 = 64; t.nb0 = 64;
+                t.C0 = grads + po[8]; t.ldc0 = 256; t.transpose0 = 1; t.P = PTi; t.scale = 1.f;
+                CK(launch_gemm_tma_tn(t, sp, st)); ++nl;
+                CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[9], nullptr, st)); ++nl;
+            }
+            // BPTT: activated gates (G) + dH -> d(pre-activations) written as operand planes
+            CK(launch_lstm_bwd(v.rec, G, at<float>(ws, l.Cst[pp]), dH, dpk + 65536 + 131072, m, sp, st, dGhl, sp ? dGhl + plG : nullptr)); ++nl;
+            {   // dX += dG W_ih (K = 1024)
+                TmaGemmArgs a = tma_args(dGhl, plG, 1024, v.wiht_hi, v.wiht_lo, 1024, dXs, 64, PTi, 64, 1024);
+                a.accumulate = 1;
+                CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+            }
+            for (int d = 0; d < 2; ++d) {  // dW_ih = dG^T x and dW_hh = dG^T h_prev from ONE pass over this direction's dG
+                TmaWgradArgs t;
+                memset(&t, 0, sizeof(t));
+                t.A_hi = dGhl + d * 512; t.A_lo = dGhl + plG + d * 512; t.lda = 1024; t.Mo = 512;
+                t.B0_hi = Xhl; t.B0_lo = Xhl + plX; t.ldb0 = 64; t.nb0 = 64;
+                t.B1_hi = Hphl + d * 128; t.B1_lo = Hphl + plH + d * 128; t.ldb1 = 256; t.nb1 = 128;
+                t.C0 = dpk + d * 512 * 64; t.ldc0 = 64;
+                t.C1 = dpk + 65536 + d * 65536; t.ldc1 = 128;
+                t.P = PTi; t.scale = 1.f;
+                CK(launch_gemm_tma_tn(t, sp, st)); ++nl;
+            }
+            continue;
+        }
         // out-projection Linear(256 -> 64)
         {
             GemmNtArgs a = nt_args(dY, 64, v.projt_hi, v.projt_lo, 64, 0, dH, 256, PTi, 256, 64);

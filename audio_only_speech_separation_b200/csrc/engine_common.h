@@ -49,6 +49,16 @@ struct Carver {
 template <typename T>
 T* at(void* base, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(base) + off); }
 
+// backend selected with dp_set_gemm_backend: 0 mma.sync, 1 tcgen05 (converting threads), 2 TMA-fed tcgen05 on operand planes
+int gemm_backend();
+inline TmaGemmArgs tma_nt_args(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, long long lda, const __nv_bfloat16* whi,
+                               const __nv_bfloat16* wlo, int ldw, float* C, int ldc, int M, int N, int K) {
+    TmaGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A_hi = a_hi; a.A_lo = a_lo; a.lda = lda; a.W_hi = whi; a.W_lo = wlo; a.ldw = ldw;
+    a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K; a.bias_scale = 1.f;
+    return a;
+}
 // GEMM dispatch honouring dp_set_gemm_backend (defined in api.cu)
 cudaError_t gemm_nt(const GemmNtArgs& a, bool split, cudaStream_t st);
 cudaError_t gemm_tn(const GemmTnArgs& a, bool split, cudaStream_t st);

@@ -1,0 +1,590 @@
+// TMA-fed tcgen05 / TMEM GEMMs on pre-split bf16 operands (sm_100a).
+//
+// The fp32-parity arithmetic of this code base is "bf16x3": x ~= hi + lo (two bf16), products hi*hi + hi*lo + lo*hi with
+// fp32 accumulation.  Converting fp32 operands inside every GEMM costs instruction issue and keeps the loads on the LSU
+// path, so here the PRODUCER of an activation writes it once as two bf16 planes (hi, lo: the same 4 bytes per element as
+// fp32) and every consumer GEMM streams those planes straight into shared memory with TMA (cp.async.bulk.tensor,
+// 128-byte swizzle) and feeds them to tcgen05.mma without touching a register:
+//
+//   warp 0   TMA producer   : waits "slot empty", arms the slot's mbarrier with the byte count, issues the tile loads
+//   warp 1   MMA issuer     : waits "slot full", one elected thread issues tcgen05.mma (M = 128, N = BN, K = 16) for the
+//                             split products, tcgen05.commit -> "slot empty"; after the last k-block -> "accumulator full"
+//   warps 2-5 epilogue      : wait "accumulator full", tcgen05.ld the fp32 tile out of TMEM (thread = row), bias /
+//                             activation / residual, store fp32 and/or hi-lo planes for the next GEMM, -> "accumulator empty"
+//   accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1; CTAs are persistent.
+//
+//   gemm_tma_nt : C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ C)         both operands K-major (K contiguous)
+//   gemm_tma_tn : dW[Mo,No] += sum_p A[p,Mo]^T B[p,No]               both operands MN-major (positions strided): the
+//                 weight gradients; the position range is split over CTAs, fp32 atomics combine the partial sums.
+//
+// Shared-memory operand tiles use the canonical UMMA SWIZZLE_128B layouts (cute/atom/mma_traits_sm100.hpp):
+//   K-major : rows of 64 bf16 (128 B), 8-row atoms of 1024 B, SBO = 1024 B, k-step of 16 elements = +32 B on the start address
+//   MN-major: K-rows of 64 MN-elements (128 B), 8-K-row atoms of 1024 B (SBO = 1024 B), next 64 MN-elements at LBO,
+//             k-step of 16 = +2048 B on the start address
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dp {
+namespace {
+
+constexpr uint32_t SPIN_LIMIT = 1u << 28;
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && ++spins > SPIN_LIMIT) __trap();  // bounded: a protocol bug traps instead of hanging the GPU
+    }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
+}
+// SWIZZLE_128B shared-memory matrix descriptor (sm_100 descriptor version 1)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D = F32, A = B = BF16, dense; a_mn / b_mn select MN-major operands
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+constexpr int BM = 128, BK = 64;
+constexpr int A_TILE = BM * BK * 2;  // 16 KB
+
+template <int BN, bool SPLIT>
+struct NtCfg {
+    static constexpr int W_TILE = BN * BK * 2;
+    static constexpr int STAGE = (A_TILE + W_TILE) * (SPLIT ? 2 : 1);
+    static constexpr int STAGES = (200 * 1024) / STAGE > 6 ? 6 : (200 * 1024) / STAGE;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+};
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(192, 1)
+gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const TmaGemmArgs p) {
+    using Cfg = NtCfg<BN, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* tfull = empty + Cfg::STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        prefetch_tmap(&tmAh); prefetch_tmap(&tmWh);
+        if (SPLIT) { prefetch_tmap(&tmAl); prefetch_tmap(&tmWl); }
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int n_tiles = p.N / BN, m_tiles = ceil_div(p.M, BM), tiles = m_tiles * n_tiles, nkb = p.K / BK;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(empty + stage, phase ^ 1);
+                    uint8_t* st = smem + stage * Cfg::STAGE;
+                    mbar_expect_tx(full + stage, Cfg::STAGE);
+                    tma_load_2d(st, &tmAh, full + stage, kb * BK, m0);
+                    if (SPLIT) tma_load_2d(st + A_TILE, &tmAl, full + stage, kb * BK, m0);
+                    uint8_t* sw = st + A_TILE * (SPLIT ? 2 : 1);
+                    tma_load_2d(sw, &tmWh, full + stage, kb * BK, n0);
+                    if (SPLIT) tma_load_2d(sw + Cfg::W_TILE, &tmWl, full + stage, kb * BK, n0);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t IDESC = idesc_bf16(BM, BN, 0, 0);
+        uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            mbar_wait(tempty + as, aphase ^ 1);  // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t d = tmem + as * BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full + stage, phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE);
+                    const uint32_t a_lo = a_hi + A_TILE;
+                    const uint32_t w_hi = a_hi + A_TILE * (SPLIT ? 2 : 1);
+                    const uint32_t w_lo = w_hi + Cfg::W_TILE;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ah = desc_sw128(a_hi + k * 32, 16, 1024), wh = desc_sw128(w_hi + k * 32, 16, 1024);
+                        umma(d, ah, wh, IDESC, (kb | k) != 0);
+                        if (SPLIT) {
+                            const uint64_t al = desc_sw128(a_lo + k * 32, 16, 1024), wl = desc_sw128(w_lo + k * 32, 16, 1024);
+                            umma(d, ah, wl, IDESC, 1);
+                            umma(d, al, wh, IDESC, 1);
+                        }
+                    }
+                    umma_commit(empty + stage);                    // smem slot reusable once these MMAs retire
+                    if (kb == nkb - 1) umma_commit(tfull + as);    // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        uint32_t as = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            mbar_wait(tfull + as, aphase);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool ok = row < p.M;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * BN + c0, v);
+                if (ok) {
+                    const int col = n0 + c0;
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(p.bias + col + j);
+                            v[j] = fmaf(p.bias_scale, b.x, v[j]); v[j + 1] = fmaf(p.bias_scale, b.y, v[j + 1]);
+                            v[j + 2] = fmaf(p.bias_scale, b.z, v[j + 2]); v[j + 3] = fmaf(p.bias_scale, b.w, v[j + 3]);
+                        }
+                    }
+                    float* dst = p.C ? p.C + (size_t)row * p.ldc + col : nullptr;
+                    if (p.accumulate) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 o = *reinterpret_cast<const float4*>(dst + j);
+                            v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+                        }
+                    }
+                    if (p.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (p.act == 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+                    } else if (p.act == 3) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
+                    }
+                    if (p.mul_c) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 o = *reinterpret_cast<const float4*>(dst + j);
+                            v[j] *= o.x; v[j + 1] *= o.y; v[j + 2] *= o.z; v[j + 3] *= o.w;
+                        }
+                    }
+                    if (p.mask) {
+                        const float* mk = p.mask + (size_t)row * p.ldmask + col;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 o = *reinterpret_cast<const float4*>(mk + j);
+                            v[j] = o.x > 0.f ? v[j] : 0.f; v[j + 1] = o.y > 0.f ? v[j + 1] : 0.f;
+                            v[j + 2] = o.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = o.w > 0.f ? v[j + 3] : 0.f;
+                        }
+                    }
+                    if (dst) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                    if (p.C_hi) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+                        uint4* dh = reinterpret_cast<uint4*>(p.C_hi + (size_t)row * p.ldch + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        if (p.C_lo) {
+                            uint4* dl = reinterpret_cast<uint4*>(p.C_lo + (size_t)row * p.ldch + col);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                    if (p.stats) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + as);  // this warp's quarter of the accumulator is drained
+            if (p.stats) {
+                const int g_lo = (m0 + q * 32) / p.rows_per_group;
+                const int g_hi = (min(m0 + q * 32 + 31, p.M - 1)) / p.rows_per_group;
+                if (g_lo == g_hi) {
+                    double a = warp_sum_d((double)s1), b = warp_sum_d((double)s2);
+                    if (lane == 0 && m0 + q * 32 < p.M) { atomicAdd(p.stats + 2 * g_lo, a); atomicAdd(p.stats + 2 * g_lo + 1, b); }
+                } else if (ok) {
+                    const int g = row / p.rows_per_group;
+                    atomicAdd(p.stats + 2 * g, (double)s1);
+                    atomicAdd(p.stats + 2 * g + 1, (double)s2);
+                }
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [rows, inner] with row stride ld (elements); box = [box_rows, 64 inner elements], 128-byte swizzle
+bool make_map(CUtensorMap* map, const void* base, long long rows, long long inner, long long ld, int box_rows) {
+    auto fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BN, bool SPLIT>
+cudaError_t launch_nt(const TmaGemmArgs& a, cudaStream_t st) {
+    using Cfg = NtCfg<BN, SPLIT>;
+    CUtensorMap mAh, mAl, mWh, mWl;
+    if (!make_map(&mAh, a.A_hi, a.M, a.K, a.lda, BM) || !make_map(&mWh, a.W_hi, a.N, a.K, a.ldw, BN)) return cudaErrorInvalidValue;
+    if (SPLIT) {
+        if (!make_map(&mAl, a.A_lo, a.M, a.K, a.lda, BM) || !make_map(&mWl, a.W_lo, a.N, a.K, a.ldw, BN)) return cudaErrorInvalidValue;
+    } else {
+        mAl = mAh; mWl = mWh;
+    }
+    cudaError_t e = cudaFuncSetAttribute(gemm_tma_nt_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    const int tiles = ceil_div(a.M, BM) * (a.N / BN);
+    const int grid = tiles < 148 ? tiles : 148;
+    gemm_tma_nt_kernel<BN, SPLIT><<<grid, 192, Cfg::SMEM, st>>>(mAh, mAl, mWh, mWl, a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool gemm_tma_nt_supported(const TmaGemmArgs& a) {
+    if (a.M <= 0 || a.K <= 0 || a.K % BK || a.N % 64) return false;
+    if ((a.lda & 7) || (a.ldw & 7)) return false;
+    if (a.C && (a.ldc & 3)) return false;
+    if (a.C_hi && (a.ldch & 7)) return false;
+    if ((a.accumulate || a.mul_c) && !a.C) return false;
+    if (!a.C && !a.C_hi) return false;
+    return encode_fn() != nullptr;
+}
+
+cudaError_t launch_gemm_tma_nt(const TmaGemmArgs& a, bool split, cudaStream_t st) {
+    if (!gemm_tma_nt_supported(a)) return cudaErrorInvalidValue;
+    if (split && (!a.A_lo || !a.W_lo)) return cudaErrorInvalidValue;
+#define DP_NT(BNV) (split ? launch_nt<BNV, true>(a, st) : launch_nt<BNV, false>(a, st))
+    if (a.N % 256 == 0) return DP_NT(256);
+    if (a.N % 128 == 0) return DP_NT(128);
+    return DP_NT(64);
+#undef DP_NT
+}
+
+// (weight-gradient kernel)
+namespace {
+// ================================================================================================
+// Weight gradients: C_s[Mo, nb_s] += scale * sum_p A[p, Mo]^T B_s[p, nb_s] for up to two B segments that share the A
+// operand (e.g. dW_ih = dG^T X and dW_hh = dG^T h_prev in ONE pass over dG).  A and B are [P, cols] planes, i.e. MN-major
+// operands (the contraction index p is the slow one).  One CTA = one 128-row slice of A^T x all N = nb0 + nb1 columns x a
+// contiguous range of positions; accumulators stay in TMEM for the CTA's whole range, fp32 atomics combine the ranges.
+constexpr int KP = 32;                      // positions per pipeline stage (2 MMAs of K = 16)
+constexpr int BOX = KP * 128;               // one TMA box: KP rows of 64 bf16 = 4 KB (4 swizzle atoms of 8 rows)
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(192, 1)
+gemm_tma_tn_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmB0h, const __grid_constant__ CUtensorMap tmB0l,
+                   const __grid_constant__ CUtensorMap tmB1h, const __grid_constant__ CUtensorMap tmB1l, const TmaWgradArgs p,
+                   int rows_per_cta, int stages, uint32_t tmem_cols) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int N = p.nb0 + p.nb1, nbox_b = N / 64;
+    const int a_bytes = 2 * BOX, b_bytes = nbox_b * BOX;
+    const int stage_bytes = (a_bytes + b_bytes) * (SPLIT ? 2 : 1);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+    uint64_t* empty = full + stages;
+    uint64_t* done = empty + stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int m0 = blockIdx.y * 128;
+    const int pbeg = blockIdx.x * rows_per_cta, pend = min(p.P, pbeg + rows_per_cta);
+    const int nst = pbeg < pend ? ceil_div(pend - pbeg, KP) : 0;  // rows beyond pend inside the last stage belong to the next CTA:
+                                                                  // rows_per_cta is a multiple of KP, so only the tensor end is ragged
+                                                                  // and TMA zero-fills it
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int it = 0; it < nst; ++it) {
+                const int p0 = pbeg + it * KP;
+                mbar_wait(empty + stage, phase ^ 1);
+                uint8_t* st = smem + stage * stage_bytes;
+                mbar_expect_tx(full + stage, stage_bytes);
+                for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
+                    uint8_t* sa = st + pl * a_bytes;
+                    const CUtensorMap* ma = pl ? &tmAl : &tmAh;
+                    tma_load_2d(sa, ma, full + stage, m0, p0);
+                    tma_load_2d(sa + BOX, ma, full + stage, m0 + 64, p0);
+                    uint8_t* sb = st + (SPLIT ? 2 : 1) * a_bytes + pl * b_bytes;
+                    const CUtensorMap* mb0 = pl ? &tmB0l : &tmB0h;
+                    const CUtensorMap* mb1 = pl ? &tmB1l : &tmB1h;
+                    int bx = 0;
+                    for (int c = 0; c < p.nb0; c += 64, ++bx) tma_load_2d(sb + bx * BOX, mb0, full + stage, c, p0);
+                    for (int c = 0; c < p.nb1; c += 64, ++bx) tma_load_2d(sb + bx * BOX, mb1, full + stage, c, p0);
+                }
+                if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = idesc_bf16(128, N, 1, 1);
+        uint32_t stage = 0, phase = 0;
+        for (int it = 0; it < nst; ++it) {
+            mbar_wait(full + stage, phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_hi = smem_u32(smem + stage * stage_bytes);
+                const uint32_t a_lo = a_hi + a_bytes;
+                const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * a_bytes;
+                const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int k = 0; k < KP / 16; ++k) {
+                    // MN-major: LBO = next 64 MN elements (one box), SBO = next 8 K-rows (1024 B); 16 K-rows per MMA = 2048 B
+                    const uint64_t ah = desc_sw128(a_hi + k * 2048, BOX, 1024), bh = desc_sw128(b_hi + k * 2048, BOX, 1024);
+                    umma(tmem, ah, bh, idesc, (it | k) != 0);
+                    if (SPLIT) {
+                        const uint64_t al = desc_sw128(a_lo + k * 2048, BOX, 1024), bl = desc_sw128(b_lo + k * 2048, BOX, 1024);
+                        umma(tmem, ah, bl, idesc, 1);
+                        umma(tmem, al, bh, idesc, 1);
+                    }
+                }
+                umma_commit(empty + stage);
+                if (it == nst - 1) umma_commit(done);
+            }
+            __syncwarp();
+            if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (nst > 0) {
+        const int q = warp & 3;
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int row = m0 + q * 32 + lane;  // row of dW = column of A
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+            if (row < p.Mo) {
+                const bool seg1 = c0 >= p.nb0;
+                float* C = seg1 ? p.C1 : p.C0;
+                const int ldc = seg1 ? p.ldc1 : p.ldc0, cb = seg1 ? c0 - p.nb0 : c0;
+                const int tr = seg1 ? p.transpose1 : p.transpose0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float* dst = tr ? C + (size_t)(cb + j) * ldc + row : C + (size_t)row * ldc + cb + j;
+                    atomicAdd(dst, v[j] * p.scale);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, tmem_cols);
+}
+
+// planes [P, cols] -> box of KP positions x 64 columns
+bool make_map_mn(CUtensorMap* map, const void* base, long long P, long long cols, long long ld) {
+    auto fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)P};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)KP};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool gemm_tma_tn_supported(const TmaWgradArgs& a) {
+    if (a.P <= 0 || a.Mo <= 0 || a.Mo % 128) return false;
+    const int N = a.nb0 + a.nb1;
+    if (a.nb0 <= 0 || a.nb0 % 64 || a.nb1 % 64 || N > 256 || N % 16) return false;
+    if ((a.lda & 7) || (a.ldb0 & 7) || (a.nb1 && (a.ldb1 & 7))) return false;
+    return encode_fn() != nullptr;
+}
+
+cudaError_t launch_gemm_tma_tn(const TmaWgradArgs& a, bool split, cudaStream_t st) {
+    if (!gemm_tma_tn_supported(a)) return cudaErrorInvalidValue;
+    if (split && (!a.A_lo || !a.B0_lo || (a.nb1 && !a.B1_lo))) return cudaErrorInvalidValue;
+    const int N = a.nb0 + a.nb1;
+    CUtensorMap mAh, mAl, mB0h, mB0l, mB1h, mB1l;
+    if (!make_map_mn(&mAh, a.A_hi, a.P, a.Mo, a.lda) || !make_map_mn(&mB0h, a.B0_hi, a.P, a.nb0, a.ldb0)) return cudaErrorInvalidValue;
+    mAl = mAh; mB0l = mB0h;
+    if (split && (!make_map_mn(&mAl, a.A_lo, a.P, a.Mo, a.lda) || !make_map_mn(&mB0l, a.B0_lo, a.P, a.nb0, a.ldb0))) return cudaErrorInvalidValue;
+    mB1h = mB0h; mB1l = mB0l;
+    if (a.nb1) {
+        if (!make_map_mn(&mB1h, a.B1_hi, a.P, a.nb1, a.ldb1)) return cudaErrorInvalidValue;
+        mB1l = mB1h;
+        if (split && !make_map_mn(&mB1l, a.B1_lo, a.P, a.nb1, a.ldb1)) return cudaErrorInvalidValue;
+    }
+    const int stage_bytes = (2 * BOX + (N / 64) * BOX) * (split ? 2 : 1);
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    const int smem = stages * stage_bytes + 1024 + 256;
+    const int mtiles = a.Mo / 128;
+    int ksplit = 148 / mtiles;
+    if (ksplit < 1) ksplit = 1;
+    int rows = ceil_div(ceil_div(a.P, ksplit), KP) * KP;
+    if (rows < 4 * KP) rows = 4 * KP;
+    dim3 grid(ceil_div(a.P, rows), mtiles);
+    const uint32_t tcols = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
+    cudaError_t e;
+    if (split) {
+        e = cudaFuncSetAttribute(gemm_tma_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        gemm_tma_tn_kernel<true><<<grid, 192, smem, st>>>(mAh, mAl, mB0h, mB0l, mB1h, mB1l, a, rows, stages, tcols);
+    } else {
+        e = cudaFuncSetAttribute(gemm_tma_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        gemm_tma_tn_kernel<false><<<grid, 192, smem, st>>>(mAh, mAl, mB0h, mB0l, mB1h, mB1l, a, rows, stages, tcols);
+    }
+    return cudaGetLastError();
+}
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ fp32 -> planes
+__global__ void __launch_bounds__(256) split_rows_kernel(const float4* __restrict__ src, long long ld4, uint2* __restrict__ hi, uint2* __restrict__ lo,
+                                                         long long rows, int C4, int relu) {
+    const long long total = rows * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / C4;
+        const int c = (int)(i % C4);
+        float4 v = ldg_stream(src + r * ld4 + c);
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        uint2 h, l;
+        split_pair(v.x, v.y, h.x, l.x);
+        split_pair(v.z, v.w, h.y, l.y);
+        hi[i] = h;
+        if (lo) lo[i] = l;
+    }
+}
+}  // namespace
+
+cudaError_t launch_split_rows(const float* src, long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo, long long rows, int C, int relu,
+                              cudaStream_t st) {
+    if (rows <= 0) return cudaSuccess;
+    if ((C & 3) || (ld & 3)) return cudaErrorInvalidValue;
+    long long total = rows * (C / 4);
+    long long blocks = ceil_div_ll(total, 256);
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), ld / 4, reinterpret_cast<uint2*>(hi),
+                                                         reinterpret_cast<uint2*>(lo), rows, C / 4, relu);
+    return cudaGetLastError();
+}
+
+}  // namespace dp

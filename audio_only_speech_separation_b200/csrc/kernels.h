@@ -38,6 +38,64 @@ cudaError_t launch_gemm_nt(const GemmNtArgs& a, bool split, cudaStream_t st);
 bool gemm_nt_tc5_supported(const GemmNtArgs& a);
 cudaError_t launch_gemm_nt_tc5(const GemmNtArgs& a, bool split, cudaStream_t st);
 
+// ---- TMA-fed tcgen05 GEMMs on pre-split bf16 planes (gemm_tma.cu) ----
+// C[M,N] = act(A[M,K] W[N,K]^T + bias_scale*bias) (+ C); A and W are bf16 hi (and lo) planes, K contiguous.
+// Outputs: fp32 C and/or hi/lo planes (the operand format of the next GEMM).  K % 64 == 0, N % 64 == 0.
+struct TmaGemmArgs {
+    const __nv_bfloat16* A_hi;
+    const __nv_bfloat16* A_lo;  // unused in bf16 mode
+    long long lda;              // elements
+    const __nv_bfloat16* W_hi;
+    const __nv_bfloat16* W_lo;
+    int ldw;
+    int M, N, K;
+    float* C;                   // optional
+    int ldc;
+    __nv_bfloat16* C_hi;        // optional
+    __nv_bfloat16* C_lo;        // optional (with C_hi)
+    int ldch;
+    const float* bias;
+    float bias_scale;
+    int act;         // 0 none, 1 ReLU, 2 tanh, 3 sigmoid
+    int accumulate;  // C += (needs C)
+    int mul_c;       // C = act(..) * C_old
+    double* stats;   // [groups][2] (sum, sumsq) of the stored values
+    int rows_per_group;
+    const float* mask;  // optional [M, ldmask]: zero where mask <= 0
+    int ldmask;
+};
+bool gemm_tma_nt_supported(const TmaGemmArgs& a);
+cudaError_t launch_gemm_tma_nt(const TmaGemmArgs& a, bool split, cudaStream_t st);
+// Weight gradients on planes: C0[Mo,nb0] += scale * A^T B0 and (optionally, same pass over A) C1[Mo,nb1] += scale * A^T B1.
+// A [P, >= Mo] and B [P, >= nb] are planes with the position as the slow index; Mo % 128 == 0, nb % 64 == 0, nb0 + nb1 <= 256.
+struct TmaWgradArgs {
+    const __nv_bfloat16* A_hi;
+    const __nv_bfloat16* A_lo;
+    long long lda;
+    int Mo;
+    const __nv_bfloat16* B0_hi;
+    const __nv_bfloat16* B0_lo;
+    long long ldb0;
+    int nb0;
+    const __nv_bfloat16* B1_hi;
+    const __nv_bfloat16* B1_lo;
+    long long ldb1;
+    int nb1;
+    float* C0;
+    int ldc0;
+    int transpose0;  // store C0[col][row]
+    float* C1;
+    int ldc1;
+    int transpose1;
+    int P;
+    float scale;
+};
+bool gemm_tma_tn_supported(const TmaWgradArgs& a);
+cudaError_t launch_gemm_tma_tn(const TmaWgradArgs& a, bool split, cudaStream_t st);
+// fp32 rows [rows, C] (row stride ld) -> bf16 hi / lo planes [rows, C] (lo optional); relu applies max(x, 0) first
+cudaError_t launch_split_rows(const float* src, long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo, long long rows, int C, int relu,
+                              cudaStream_t st);
+
 // C[Mo,No] += scale * sum_p A[p,Mo]^T * B[p',No]   (fp32 atomics), p' = p + shift when the time index allows.
 struct GemmTnArgs {
     const float* A;
@@ -74,12 +132,24 @@ struct LstmPack {  // per ProjRNN, both directions
 };
 // G: [P,1024] gate pre-activations (packed column order dir*512 + unit*4 + gate); overwritten with the
 // activated gates when save != 0.  H: [P,256] = [h_fwd | h_bwd].  Cst: [P,256] cell states (save only).
+// Optional bf16 hi/lo operand planes written by the forward kernel (all [P,256] = [fwd | bwd] like H; lo unused in bf16 mode):
+// h_* : h_t at its own position (operand of the out-projection and of its weight gradient)
+// hp_*: h of the previously visited step at each position, zeros at a sequence's first step (operand of dW_hh = dG^T h_prev,
+//       so that gradient needs neither a shifted read nor boundary masking)
+struct LstmPlanes {
+    __nv_bfloat16* h_hi;
+    __nv_bfloat16* h_lo;
+    __nv_bfloat16* hp_hi;
+    __nv_bfloat16* hp_lo;
+};
+// H may be null when only the planes are wanted.
 cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save,
-                            cudaStream_t st);
+                            cudaStream_t st, const LstmPlanes* planes = nullptr);
 // dH: [P,256] incoming gradient of H.  G holds activated gates on entry and d(pre-activations) on exit.
 // dbias (optional, [1024] packed order) accumulates sum_p dG[p,:] (the bias gradient) inside the same kernel.
+// dG_hi / dG_lo (optional, [P,1024] planes): d(pre-activations) go there instead of overwriting G.
 cudaError_t launch_lstm_bwd(const LstmPack& w, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,
-                            cudaStream_t st);
+                            cudaStream_t st, __nv_bfloat16* dG_hi = nullptr, __nv_bfloat16* dG_lo = nullptr);
 
 // Build all packed forms of one ProjRNN's LSTM weights from the natural fp32 parameters.
 struct LstmPackOut {
@@ -150,12 +220,15 @@ cudaError_t launch_dec_ola_general(const float* D, float* out, int B, int nspk, 
 // ---------------- transformer blocks (transformer.cu) ----------------
 // Self-attention of nn.MultiheadAttention on channels-last rows: QKV [P,3E] = [q|k|v] -> O [P,E]; sequences via SeqMap.
 // LSE (optional, [P,heads], log2 domain) is what the backward needs.  Head width E/heads must be 16 or 32.
-cudaError_t launch_attn_fwd(const float* QKV, float* O, float* LSE, int E, int heads, const SeqMap& m, cudaStream_t st);
+// O may be null when only the bf16 hi/lo planes (O_hi, O_lo: operands of the out-projection GEMM) are wanted.
+cudaError_t launch_attn_fwd(const float* QKV, float* O, float* LSE, int E, int heads, const SeqMap& m, cudaStream_t st,
+                            __nv_bfloat16* O_hi = nullptr, __nv_bfloat16* O_lo = nullptr);
 cudaError_t launch_attn_bwd(const float* QKV, const float* O, const float* LSE, const float* dO, float* dQKV, int E, int heads,
                             const SeqMap& m, cudaStream_t st);
 // z = a (+ b) [-> zout]; out = (res ? res : 0) + LayerNorm_E(z) * gamma + beta; then optional unfold affine + PReLU.
 cudaError_t launch_add_ln(const float* a, const float* b, float* zout, float* out, const float* res, const float* gamma, const float* beta,
-                          long long rows, int E, float eps, const float* cw, const float* cb, const float* slope, cudaStream_t st);
+                          long long rows, int E, float eps, const float* cw, const float* cb, const float* slope, cudaStream_t st,
+                          __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);  // out may be null with planes
 // LayerNorm backward from the saved pre-norm rows z: dz (may alias dy), acc (optional) += dz, dgamma/dbeta accumulated.
 cudaError_t launch_ln_bwd(const float* dy, const float* z, float* dz, float* acc, const float* gamma, long long rows, int E, float eps,
                           float* dgamma, float* dbeta, cudaStream_t st);

@@ -21,6 +21,8 @@
 //
 // SPLIT = true: bf16x3 (hi*hi + hi*lo + lo*hi), precise activations  -> fp32 parity mode
 // SPLIT = false: single bf16 product, tanh.approx activations           -> bf16 mode
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -67,7 +69,7 @@ __device__ __forceinline__ void fill_seq_bases(int* sbase, int NS, int q0, const
 
 template <int NT, bool SPLIT, bool SAVE>
 __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, float* __restrict__ G, float* __restrict__ H,
-                                                          float* __restrict__ Cst, const SeqMap m) {
+                                                          float* __restrict__ Cst, const SeqMap m, const LstmPlanes pl) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NS = 8 * NT;
     uint4* alo = reinterpret_cast<uint4*>(smem);
@@ -132,6 +134,29 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
         const unsigned toff = (unsigned)t * (unsigned)m.s_t;
         cp_async_wait_all();
         __syncthreads();  // gate tile of step t landed; h_{t-1} (written by all warps) visible
+        if (pl.h_hi != nullptr || pl.hp_hi != nullptr) {
+            // h_{t-1} sits in shared memory as bf16 hi/lo rows: copy it out as the operand planes of the GEMMs that consume it
+            // (H at the previous position; "h_prev" at this position, zeros at the first step) with coalesced 128-bit stores
+            const unsigned tprev = (unsigned)(dir ? t + 1 : t - 1) * (unsigned)m.s_t;
+            for (int ch = tid; ch < NS * 16; ch += 256) {
+                const int sq = ch >> 4, c16 = ch & 15;
+                if (q0 + sq >= m.nseq) continue;
+                const uint4 vh = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
+                uint4 vl = make_uint4(0, 0, 0, 0);
+                if (SPLIT) vl = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
+                const size_t col = (size_t)dir * kH + c16 * 8;
+                if (pl.hp_hi != nullptr) {
+                    const size_t o = (size_t)((unsigned)sbase[sq] + toff) * 256 + col;
+                    *reinterpret_cast<uint4*>(pl.hp_hi + o) = vh;
+                    if (SPLIT && pl.hp_lo != nullptr) *reinterpret_cast<uint4*>(pl.hp_lo + o) = vl;
+                }
+                if (pl.h_hi != nullptr && step > 0) {
+                    const size_t o = (size_t)((unsigned)sbase[sq] + tprev) * 256 + col;
+                    *reinterpret_cast<uint4*>(pl.h_hi + o) = vh;
+                    if (SPLIT && pl.h_lo != nullptr) *reinterpret_cast<uint4*>(pl.h_lo + o) = vl;
+                }
+            }
+        }
         float acc[4][NT][4];
 #pragma unroll
         for (int n = 0; n < NT; ++n)
@@ -187,7 +212,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
                     float hh = og * tanh_f<SPLIT>(cc);
                     if (valid[n][e]) {
                         const unsigned ho = hoff[n][e] + toff * 256u + h * 8;
-                        H[ho] = hh;
+                        if (H != nullptr) H[ho] = hh;
                         if (SAVE) {
                             Cst[ho] = cc;
                             // packed gate column = 4 x hidden column, so the gate offset is exactly 4 * ho
@@ -199,6 +224,17 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
                     hs_hi[so] = hb;
                     if (SPLIT) hs_lo[so] = __float2bfloat16_rn(hh - __bfloat162float(hb));
                 }
+    }
+    if (pl.h_hi != nullptr) {  // the last step's h
+        __syncthreads();
+        const unsigned tlast = (unsigned)(dir ? 0 : m.len - 1) * (unsigned)m.s_t;
+        for (int ch = tid; ch < NS * 16; ch += 256) {
+            const int sq = ch >> 4, c16 = ch & 15;
+            if (q0 + sq >= m.nseq) continue;
+            const size_t o = (size_t)((unsigned)sbase[sq] + tlast) * 256 + (size_t)dir * kH + c16 * 8;
+            *reinterpret_cast<uint4*>(pl.h_hi + o) = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
+            if (SPLIT && pl.h_lo != nullptr) *reinterpret_cast<uint4*>(pl.h_lo + o) = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
+        }
     }
 }
 
@@ -331,7 +367,8 @@ cudaError_t set_smem(K kernel, int bytes) {
 }
 
 template <int NT>
-cudaError_t fwd_launch(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, cudaStream_t st) {
+cudaError_t fwd_launch(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, const LstmPlanes& pl,
+                       cudaStream_t st) {
     dim3 grid(ceil_div(m.nseq, 8 * NT), 2);
     int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * HST * 2 + 8 * NT * GST * 4 + 8 * NT * 4;
     cudaError_t e;
@@ -339,7 +376,7 @@ cudaError_t fwd_launch(const LstmPack& w, float* G, float* H, float* Cst, const 
     do {                                                                             \
         e = set_smem(lstm_fwd_kernel<NT, SP, SV>, smem);                             \
         if (e != cudaSuccess) return e;                                              \
-        lstm_fwd_kernel<NT, SP, SV><<<grid, 256, smem, st>>>(w, G, H, Cst, m);       \
+        lstm_fwd_kernel<NT, SP, SV><<<grid, 256, smem, st>>>(w, G, H, Cst, m, pl);   \
     } while (0)
     if (split) { if (save) DP_FWD(true, true); else DP_FWD(true, false); }
     else       { if (save) DP_FWD(false, true); else DP_FWD(false, false); }
@@ -357,12 +394,15 @@ int lstm_pick_nt(int nseq) {
 }
 
 cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save,
-                            cudaStream_t st) {
+                            cudaStream_t st, const LstmPlanes* planes) {
     if (m.nseq <= 0 || m.len <= 0) return cudaSuccess;
+    LstmPlanes pl;
+    memset(&pl, 0, sizeof(pl));
+    if (planes) pl = *planes;
     switch (lstm_pick_nt(m.nseq)) {
-        case 1: return fwd_launch<1>(w, G, H, Cst, m, split, save, st);
-        case 2: return fwd_launch<2>(w, G, H, Cst, m, split, save, st);
-        default: return fwd_launch<3>(w, G, H, Cst, m, split, save, st);
+        case 1: return fwd_launch<1>(w, G, H, Cst, m, split, save, pl, st);
+        case 2: return fwd_launch<2>(w, G, H, Cst, m, split, save, pl, st);
+        default: return fwd_launch<3>(w, G, H, Cst, m, split, save, pl, st);
     }
 }
 

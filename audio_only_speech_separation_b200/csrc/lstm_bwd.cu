@@ -47,7 +47,8 @@ __device__ __forceinline__ float4 ld_f4_ordered(const float* p) {  // volatile a
 
 template <int NT, bool SPLIT>
 __global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, float* __restrict__ G, const float* __restrict__ Cst,
-                                                          const float* __restrict__ dH, float* __restrict__ dbias, const SeqMap m) {
+                                                          const float* __restrict__ dH, float* __restrict__ dbias, const SeqMap m,
+                                                          __nv_bfloat16* __restrict__ dG_hi, __nv_bfloat16* __restrict__ dG_lo) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NS = 8 * NT;
     uint4* alo = reinterpret_cast<uint4*>(smem);
@@ -179,14 +180,19 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, floa
                 dg.y = dc * cp * a.y * (1.f - a.y);
                 dg.z = dc * a.x * (1.f - a.z * a.z);
                 dg.w = dh * tc * a.w * (1.f - a.w);
-                if (valid[n][e]) {
-                    const unsigned ho = (unsigned)sbase[sl] * 256u + hcol + toff + h * 8;
-                    *reinterpret_cast<float4*>(G + (size_t)ho * 4) = dg;
-                    bsum[h][0] += dg.x; bsum[h][1] += dg.y; bsum[h][2] += dg.z; bsum[h][3] += dg.w;
-                }
                 uint2 hi, lo;
                 split_pair(dg.x, dg.y, hi.x, lo.x);
                 split_pair(dg.z, dg.w, hi.y, lo.y);
+                if (valid[n][e]) {
+                    const unsigned ho = (unsigned)sbase[sl] * 256u + hcol + toff + h * 8;
+                    if (dG_hi != nullptr) {  // operand planes for the TMA-fed GEMMs that consume dG (same 4 bytes per element)
+                        *reinterpret_cast<uint2*>(dG_hi + (size_t)ho * 4) = hi;
+                        if (SPLIT && dG_lo != nullptr) *reinterpret_cast<uint2*>(dG_lo + (size_t)ho * 4) = lo;
+                    } else {
+                        *reinterpret_cast<float4*>(G + (size_t)ho * 4) = dg;
+                    }
+                    bsum[h][0] += dg.x; bsum[h][1] += dg.y; bsum[h][2] += dg.z; bsum[h][3] += dg.w;
+                }
                 *reinterpret_cast<uint2*>(dg_hi + sl * DST + un * 4) = hi;
                 if (SPLIT) *reinterpret_cast<uint2*>(dg_lo + sl * DST + un * 4) = lo;
             }
@@ -210,18 +216,18 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, floa
 
 template <int NT>
 cudaError_t bwd_launch(const LstmPack& w, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,
-                       cudaStream_t st) {
+                       __nv_bfloat16* dG_hi, __nv_bfloat16* dG_lo, cudaStream_t st) {
     dim3 grid(ceil_div(m.nseq, 8 * NT), 2);
     int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * DST * 2 + 3 * 8 * NT * SST * 4 + 4 * NT * 256 * 4 + 8 * NT * 4;
     cudaError_t e;
     if (split) {
         e = cudaFuncSetAttribute(lstm_bwd_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        lstm_bwd_kernel<NT, true><<<grid, 256, smem, st>>>(w, G, Cst, dH, dbias, m);
+        lstm_bwd_kernel<NT, true><<<grid, 256, smem, st>>>(w, G, Cst, dH, dbias, m, dG_hi, dG_lo);
     } else {
         e = cudaFuncSetAttribute(lstm_bwd_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        lstm_bwd_kernel<NT, false><<<grid, 256, smem, st>>>(w, G, Cst, dH, dbias, m);
+        lstm_bwd_kernel<NT, false><<<grid, 256, smem, st>>>(w, G, Cst, dH, dbias, m, dG_hi, dG_lo);
     }
     return cudaGetLastError();
 }
@@ -231,12 +237,12 @@ cudaError_t bwd_launch(const LstmPack& w, float* G, const float* Cst, const floa
 int lstm_pick_nt(int nseq);
 
 cudaError_t launch_lstm_bwd(const LstmPack& w, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,
-                            cudaStream_t st) {
+                            cudaStream_t st, __nv_bfloat16* dG_hi, __nv_bfloat16* dG_lo) {
     if (m.nseq <= 0 || m.len <= 0) return cudaSuccess;
     switch (lstm_pick_nt(m.nseq)) {
-        case 1: return bwd_launch<1>(w, G, Cst, dH, dbias, m, split, st);
-        case 2: return bwd_launch<2>(w, G, Cst, dH, dbias, m, split, st);
-        default: return bwd_launch<3>(w, G, Cst, dH, dbias, m, split, st);
+        case 1: return bwd_launch<1>(w, G, Cst, dH, dbias, m, split, dG_hi, dG_lo, st);
+        case 2: return bwd_launch<2>(w, G, Cst, dH, dbias, m, split, dG_hi, dG_lo, st);
+        default: return bwd_launch<3>(w, G, Cst, dH, dbias, m, split, dG_hi, dG_lo, st);
     }
 }
 

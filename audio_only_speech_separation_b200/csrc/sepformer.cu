@@ -54,6 +54,7 @@ int sep_geo(const dp_sepformer* h, int B, int T, SGeo& g) {
 
 struct SLayout {
     size_t xp, E, En, Fb, X, R, U, QKV, O, Hf, F2, Zs, Gt, Mk, Mx, D, stats, mr, total;
+    size_t Uhl, Ohl, Hfhl;  // bf16 hi/lo operand planes of the TMA-fed GEMMs ([hi | lo])
 };
 void sep_layout(const dp_sepformer* h, const SGeo& g, SLayout& l) {
     Carver c;
@@ -78,6 +79,9 @@ void sep_layout(const dp_sepformer* h, const SGeo& g, SLayout& l) {
     l.D = c.take(g.BL * spk * h->cfg.win * f);
     l.stats = c.take(2 * g.B * sizeof(double));
     l.mr = c.take(2 * g.B * f);
+    l.Uhl = c.take(g.PT * N * 2 * 2);
+    l.Ohl = c.take(g.PT * N * 2 * 2);
+    l.Hfhl = c.take(g.PT * dmax * 2 * 2);
     l.total = c.off;
 }
 
@@ -204,7 +208,48 @@ int dp_sepformer_forward(dp_sepformer* h, const float* params, const void* pack,
             } else {
                 CK(cudaMemcpyAsync(R, X, g.PT * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
             }
-            for (int ly = 0; ly < layers; ++ly) {                                                                // :320-370
+            const bool tma = gemm_backend() == 2 && dffn % 64 == 0;
+            __nv_bfloat16* Uh = at<__nv_bfloat16>(ws, l.Uhl);
+            __nv_bfloat16* Ul = sp ? Uh + g.PT * N : nullptr;
+            __nv_bfloat16* Oh = at<__nv_bfloat16>(ws, l.Ohl);
+            __nv_bfloat16* Ol = sp ? Oh + g.PT * N : nullptr;
+            __nv_bfloat16* Hh = at<__nv_bfloat16>(ws, l.Hfhl);
+            __nv_bfloat16* Hl = sp ? Hh + g.PT * dffn : nullptr;
+            if (tma && !pre) { CK(launch_split_rows(R, N, Uh, Ul, g.PT, N, 0, st)); ++nl; }  // post-norm: the first GEMM reads the stream itself
+            for (int ly = 0; tma && ly < layers; ++ly) {
+                // TMA-fed tcgen05 GEMMs: every operand is a pair of bf16 planes written by its producer (gemm_tma.cu)
+                const int64_t* lo = po + 1 + PER_LAYER * ly;
+                if (pre) { CK(launch_add_ln(R, nullptr, nullptr, nullptr, nullptr, params + lo[8], params + lo[9], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st, Uh, Ul)); ++nl; }
+                {
+                    TmaGemmArgs a = tma_nt_args(Uh, Ul, N, whi + lo[0], wlo + lo[0], N, QKV, 3 * N, PTi, 3 * N, N);
+                    a.bias = params + lo[1];
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                CK(launch_attn_fwd(QKV, nullptr, nullptr, N, heads, m, st, Oh, Ol)); ++nl;
+                {
+                    TmaGemmArgs a = tma_nt_args(Oh, Ol, N, whi + lo[2], wlo + lo[2], N, pre ? R : U, N, PTi, N, N);
+                    a.bias = params + lo[3];
+                    a.accumulate = pre ? 1 : 0;
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                if (pre) { CK(launch_add_ln(R, nullptr, nullptr, nullptr, nullptr, params + lo[10], params + lo[11], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st, Uh, Ul)); ++nl; }
+                else     { CK(launch_add_ln(U, R, nullptr, R, nullptr, params + lo[8], params + lo[9], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st, Uh, Ul)); ++nl; }
+                {   // FFN hidden goes straight to operand planes: the [P, d_ffn] fp32 tensor never exists
+                    TmaGemmArgs a = tma_nt_args(Uh, Ul, N, whi + lo[4], wlo + lo[4], N, nullptr, 0, PTi, dffn, N);
+                    a.C_hi = Hh; a.C_lo = Hl; a.ldch = dffn;
+                    a.bias = params + lo[5];
+                    a.act = 1;
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                {
+                    TmaGemmArgs a = tma_nt_args(Hh, Hl, dffn, whi + lo[6], wlo + lo[6], dffn, pre ? R : U, N, PTi, N, dffn);
+                    a.bias = params + lo[7];
+                    a.accumulate = pre ? 1 : 0;
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                if (!pre) { CK(launch_add_ln(U, R, nullptr, R, nullptr, params + lo[10], params + lo[11], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st, Uh, Ul)); ++nl; }
+            }
+            for (int ly = 0; !tma && ly < layers; ++ly) {                                                        // :320-370
                 const int64_t* lo = po + 1 + PER_LAYER * ly;
                 const float* src = R;
                 if (pre) {

@@ -28,7 +28,8 @@ __device__ __forceinline__ long long seq_base(const SeqMap& m, int q) {
 // grid (nseq, heads); QKV [P, 3E] = [q | k | v], head h uses columns [h*D, (h+1)*D) of each third.
 template <int D>
 __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ QKV, float* __restrict__ O, float* __restrict__ LSE,
-                                                       int E, int heads, SeqMap m, float scale_log2) {
+                                                       int E, int heads, SeqMap m, float scale_log2, __nv_bfloat16* __restrict__ O_hi,
+                                                       __nv_bfloat16* __restrict__ O_lo) {
     extern __shared__ __align__(16) float sm_att[];
     constexpr int DS = D + 4;  // padded row stride
     const int L = m.len;
@@ -99,9 +100,26 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
             mx = cm;
         }
         const float inv = 1.0f / l;
-        float4* dst = reinterpret_cast<float4*>(O + p * E + h * D);
 #pragma unroll
-        for (int c = 0; c < D / 4; ++c) dst[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+        for (int d = 0; d < D; ++d) acc[d] *= inv;
+        if (O != nullptr) {
+            float4* dst = reinterpret_cast<float4*>(O + p * E + h * D);
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c) dst[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        }
+        if (O_hi != nullptr) {  // operand planes for the out-projection GEMM
+            uint32_t hi[D / 2], lo[D / 2];
+#pragma unroll
+            for (int d = 0; d < D / 2; ++d) split_pair(acc[2 * d], acc[2 * d + 1], hi[d], lo[d]);
+            uint4* dh = reinterpret_cast<uint4*>(O_hi + p * E + h * D);
+#pragma unroll
+            for (int c = 0; c < D / 8; ++c) dh[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            if (O_lo != nullptr) {
+                uint4* dl = reinterpret_cast<uint4*>(O_lo + p * E + h * D);
+#pragma unroll
+                for (int c = 0; c < D / 8; ++c) dl[c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+            }
+        }
         if (LSE) LSE[p * heads + h] = mx + log2f(l);  // log2 domain
     }
 }
@@ -234,7 +252,8 @@ template <int E>
 __global__ void __launch_bounds__(256) add_ln_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ zout,
                                                      float4* __restrict__ out, const float4* __restrict__ res, const float4* __restrict__ gamma,
                                                      const float4* __restrict__ beta, long long rows, float eps, const float4* __restrict__ cw,
-                                                     const float4* __restrict__ cb, const float* __restrict__ slope) {
+                                                     const float4* __restrict__ cb, const float* __restrict__ slope, uint2* __restrict__ out_hi,
+                                                     uint2* __restrict__ out_lo) {
     using G = LnGeom<E>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % G::LPR, rw = lane / G::LPR;
@@ -286,7 +305,14 @@ __global__ void __launch_bounds__(256) add_ln_kernel(const float4* __restrict__ 
                 o.x = o.x >= 0.f ? o.x : sl * o.x; o.y = o.y >= 0.f ? o.y : sl * o.y;
                 o.z = o.z >= 0.f ? o.z : sl * o.z; o.w = o.w >= 0.f ? o.w : sl * o.w;
             }
-            out[i] = o;
+            if (out != nullptr) out[i] = o;
+            if (out_hi != nullptr) {  // operand planes for the GEMM that consumes the normalised rows
+                uint2 hh, ll;
+                split_pair(o.x, o.y, hh.x, ll.x);
+                split_pair(o.z, o.w, hh.y, ll.y);
+                out_hi[i] = hh;
+                if (out_lo != nullptr) out_lo[i] = ll;
+            }
         }
     }
 }
@@ -421,7 +447,8 @@ inline int ln_grid(long long rows, int rpw) {
 
 }  // namespace
 
-cudaError_t launch_attn_fwd(const float* QKV, float* O, float* LSE, int E, int heads, const SeqMap& m, cudaStream_t st) {
+cudaError_t launch_attn_fwd(const float* QKV, float* O, float* LSE, int E, int heads, const SeqMap& m, cudaStream_t st,
+                            __nv_bfloat16* O_hi, __nv_bfloat16* O_lo) {
     if (m.nseq <= 0 || m.len <= 0) return cudaSuccess;
     const int D = E / heads;
     if (E % heads || (D != 16 && D != 32)) return cudaErrorInvalidValue;
@@ -434,11 +461,11 @@ cudaError_t launch_attn_fwd(const float* QKV, float* O, float* LSE, int E, int h
     if (D == 16) {
         e = cudaFuncSetAttribute(attn_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attn_fwd_kernel<16><<<grid, threads, smem, st>>>(QKV, O, LSE, E, heads, m, scale_log2);
+        attn_fwd_kernel<16><<<grid, threads, smem, st>>>(QKV, O, LSE, E, heads, m, scale_log2, O_hi, O_lo);
     } else {
         e = cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attn_fwd_kernel<32><<<grid, threads, smem, st>>>(QKV, O, LSE, E, heads, m, scale_log2);
+        attn_fwd_kernel<32><<<grid, threads, smem, st>>>(QKV, O, LSE, E, heads, m, scale_log2, O_hi, O_lo);
     }
     return cudaGetLastError();
 }
@@ -467,13 +494,15 @@ cudaError_t launch_attn_bwd(const float* QKV, const float* O, const float* LSE, 
 }
 
 cudaError_t launch_add_ln(const float* a, const float* b, float* zout, float* out, const float* res, const float* gamma, const float* beta,
-                          long long rows, int E, float eps, const float* cw, const float* cb, const float* slope, cudaStream_t st) {
+                          long long rows, int E, float eps, const float* cw, const float* cb, const float* slope, cudaStream_t st,
+                          __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
     if (rows <= 0) return cudaSuccess;
 #define DP_LN(EE)                                                                                                                   \
     add_ln_kernel<EE><<<ln_grid(rows, LnGeom<EE>::RPW), 256, 0, st>>>(                                                              \
         reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), reinterpret_cast<float4*>(zout),                    \
         reinterpret_cast<float4*>(out), reinterpret_cast<const float4*>(res), reinterpret_cast<const float4*>(gamma),               \
-        reinterpret_cast<const float4*>(beta), rows, eps, reinterpret_cast<const float4*>(cw), reinterpret_cast<const float4*>(cb), slope)
+        reinterpret_cast<const float4*>(beta), rows, eps, reinterpret_cast<const float4*>(cw), reinterpret_cast<const float4*>(cb), slope, \
+        reinterpret_cast<uint2*>(out_hi), reinterpret_cast<uint2*>(out_lo))
     if (E == 64) DP_LN(64);
     else if (E == 128) DP_LN(128);
     else if (E == 256) DP_LN(256);

@@ -26,6 +26,9 @@ __all__ = [
     "attention_backward",
     "add_layernorm",
     "layernorm_backward",
+    "split_rows",
+    "linear_planes",
+    "linear_wgrad_planes",
 ]
 
 
@@ -260,3 +263,44 @@ def layernorm_backward(dy, z, gamma, eps):
     check(lib().dp_layernorm_backward_f32(ptr(dy), ptr(z), ptr(dz), None, ptr(gamma), rows, E, float(eps), ptr(dgamma), ptr(dbeta),
                                           stream_ptr()), "dp_layernorm_backward_f32")
     return dz, dgamma, dbeta
+
+
+def split_rows(x: torch.Tensor, *, relu=False, lo=True):
+    """fp32 rows ``[rows, C]`` -> bf16 (hi, lo) planes, the operand format of the TMA-fed tcgen05 GEMMs."""
+    require_cuda(x, "x")
+    rows, Cc = x.shape
+    hi = torch.empty(rows, Cc, device=x.device, dtype=torch.bfloat16)
+    lo_t = torch.empty(rows, Cc, device=x.device, dtype=torch.bfloat16) if lo else None
+    check(lib().dp_split_rows_f32(ptr(x), x.stride(0), ptr(hi), ptr(lo_t), rows, Cc, int(relu), stream_ptr()), "dp_split_rows_f32")
+    return hi, lo_t
+
+
+def linear_planes(a_hi, a_lo, w_hi, w_lo, bias=None, *, act=0, out=None, accumulate=False, planes_out=False, bias_scale=1.0,
+                  precision="fp32"):
+    """``act(a @ W^T + bias)`` on pre-split operands (TMA-fed tcgen05 kernel).  Returns ``(C fp32, (C_hi, C_lo) or None)``."""
+    M, K = a_hi.shape
+    N = w_hi.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a_hi.device, dtype=torch.float32)
+    ch = cl = None
+    if planes_out:
+        ch = torch.empty(M, N, device=a_hi.device, dtype=torch.bfloat16)
+        cl = torch.empty(M, N, device=a_hi.device, dtype=torch.bfloat16)
+    check(lib().dp_linear_planes_f32(ptr(a_hi), ptr(a_lo), a_hi.stride(0), ptr(w_hi), ptr(w_lo), w_hi.stride(0), ptr(bias), float(bias_scale),
+                                     ptr(out), out.stride(0), ptr(ch), ptr(cl), N, M, N, K, int(act), int(accumulate), _prec(precision),
+                                     stream_ptr()), "dp_linear_planes_f32")
+    return out, ((ch, cl) if planes_out else None)
+
+
+def linear_wgrad_planes(a, b0, out0, b1=None, out1=None, *, tr0=False, tr1=False, scale=1.0, precision="fp32"):
+    """``out0[Mo,nb0] += a^T b0`` and (same pass over ``a``) ``out1[Mo,nb1] += a^T b1``; ``a``/``b*`` are (hi, lo) plane pairs
+    of ``[P, cols]`` tensors (column slices allowed)."""
+    P, Mo = a[0].shape
+    z = (None, None)
+    b1 = b1 if b1 is not None else z
+    check(lib().dp_linear_wgrad_planes_f32(ptr(a[0]), ptr(a[1]), a[0].stride(0), Mo, ptr(b0[0]), ptr(b0[1]), b0[0].stride(0), b0[0].shape[1],
+                                           ptr(b1[0]), ptr(b1[1]), b1[0].stride(0) if b1[0] is not None else 0,
+                                           b1[0].shape[1] if b1[0] is not None else 0, ptr(out0), out0.stride(0), int(tr0), ptr(out1),
+                                           out1.stride(0) if out1 is not None else 0, int(tr1), P, float(scale), _prec(precision),
+                                           stream_ptr()), "dp_linear_wgrad_planes_f32")
+    return out0, out1

@@ -52,6 +52,19 @@ int dp_overlap_add_cl_f32(const float* x, float* f, int B, int L, int K, int C, 
 int dp_linear_f32(const float* A, int64_t lda, const void* w_hi, const void* w_lo, int ldw, int w_kn, const float* bias,
                   float bias_scale, float* C, int ldc, int M, int N, int K, int relu, int accumulate, double* stats,
                   int rows_per_group, int precision, void* stream);
+/* The same contraction on operands already stored as bf16 hi/lo planes (what the engine's producers write): TMA-fed
+ * tcgen05/TMEM kernel, fp32 and/or plane output.  act: 0 none, 1 ReLU, 2 tanh, 3 sigmoid.  K % 64 == 0, N % 64 == 0. */
+int dp_linear_planes_f32(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo, int ldw, const float* bias,
+                         float bias_scale, float* C, int ldc, void* c_hi, void* c_lo, int ldch, int M, int N, int K, int act,
+                         int accumulate, int precision, void* stream);
+/* Weight gradients on planes, one pass over A for up to two outputs: C0[Mo,nb0] += scale * A^T B0, C1[Mo,nb1] += scale * A^T B1
+ * (A [P,>=Mo], B [P,>=nb]: the position is the slow index; Mo % 128 == 0, nb % 64 == 0, nb0 + nb1 <= 256; tr != 0 stores C[col][row]).
+ * This is how dW_ih = dG^T x and dW_hh = dG^T h_prev of nn.LSTM come out of a single read of dG. */
+int dp_linear_wgrad_planes_f32(const void* a_hi, const void* a_lo, int64_t lda, int Mo, const void* b0_hi, const void* b0_lo, int64_t ldb0,
+                               int nb0, const void* b1_hi, const void* b1_lo, int64_t ldb1, int nb1, float* C0, int ldc0, int tr0, float* C1,
+                               int ldc1, int tr1, int P, float scale, int precision, void* stream);
+/* fp32 rows -> bf16 hi/lo planes (lo may be NULL); relu != 0 applies max(x, 0) first */
+int dp_split_rows_f32(const float* src, int64_t ld, void* hi, void* lo, int64_t rows, int C, int relu, void* stream);
 /* dW[Mo,No] += scale * A[P,Mo]^T B[P,No]  (weight gradients; fp32 atomics). */
 int dp_linear_wgrad_f32(const float* A, int lda, const float* B, int64_t ldb, float* dW, int ldc, int P, int Mo, int No,
                         float scale, int precision, void* stream);

@@ -214,3 +214,29 @@ def test_full_size_training_batch_properties(manifest):
     with torch.no_grad():
         y2 = m(x2)
     assert rel_l2(y2[5], torch.from_numpy(z["y"][0])) < FP32_TOL  # golden utterance embedded in a full batch
+
+
+def test_tma_and_mma_sync_engines_agree(manifest):
+    """The default engine (TMA-fed tcgen05 GEMMs on operand planes) against the mma.sync engine: outputs and all gradients."""
+    from audio_only_speech_separation_b200._lib import check, lib
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+
+    z = load_npz("grads_dprnn_wsj0.npz")
+    x, tgt = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["tgt"]).cuda()
+    res = {}
+    try:
+        for backend in (2, 0):
+            check(lib().dp_set_gemm_backend(backend))
+            for precision in ("fp32", "bf16"):
+                m, _, _ = _model(manifest, "dprnn_wsj0_b2_t8001", precision=precision)
+                m.train()
+                y = m(x)
+                PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)(y, tgt).backward()
+                res[backend, precision] = (y.detach().clone(), torch.cat([p.grad.reshape(-1) for p in m.parameters()]))
+    finally:
+        check(lib().dp_set_gemm_backend(2))
+    e_y, e_g = rel_l2(res[2, "fp32"][0], res[0, "fp32"][0]), rel_l2(res[2, "fp32"][1], res[0, "fp32"][1])
+    b_y, b_g = rel_l2(res[2, "bf16"][0], res[0, "bf16"][0]), rel_l2(res[2, "bf16"][1], res[0, "bf16"][1])
+    record("engines_agree", fp32_out=e_y, fp32_grads=e_g, bf16_out=b_y, bf16_grads=b_g)
+    assert e_y < 5e-5 and e_g < 1e-4
+    assert b_y < 3e-2 and b_g < 1e-1

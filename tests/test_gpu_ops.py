@@ -115,7 +115,7 @@ def backend(request):
 
     check(lib().dp_set_gemm_backend(request.param))
     yield request.param
-    check(lib().dp_set_gemm_backend(0))
+    check(lib().dp_set_gemm_backend(2))  # the library default
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 256, 64), (8200, 1024, 64), (3333, 64, 1024), (700, 128, 256)])
