@@ -677,12 +677,10 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
             }
             CK(launch_gn_finalize(at<double>(ws, l.stats[pp]), at<float>(ws, l.mr[pp]), B, (double)g.P * 64, 1e-8, st)); ++nl;
             const bool cat = h->cfg.unfold && (pp & 1);
+            __nv_bfloat16* xn = pp + 1 < h->npath ? at<__nv_bfloat16>(ws, l.Xhl[pp + 1]) : nullptr;
             CK(launch_gn_apply(Y, X, at<float>(ws, l.X[pp + 1]), at<float>(ws, l.mr[pp]), params + po[10], params + po[11], g.PT, g.P, 64,
-                               cat ? params + o[9] : nullptr, cat ? params + o[10] : nullptr, cat ? params + o[11] : nullptr, st)); ++nl;
-            if (pp + 1 < h->npath) {
-                __nv_bfloat16* xn = at<__nv_bfloat16>(ws, l.Xhl[pp + 1]);
-                CK(launch_split_rows(at<float>(ws, l.X[pp + 1]), 64, xn, sp ? xn + plX : nullptr, g.PT, 64, 0, st)); ++nl;
-            }
+                               cat ? params + o[9] : nullptr, cat ? params + o[10] : nullptr, cat ? params + o[11] : nullptr, st, xn,
+                               (xn && sp) ? xn + plX : nullptr)); ++nl;
             continue;
         }
         {

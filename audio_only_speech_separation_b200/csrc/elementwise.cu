@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float4* __restrict_
                                                        const float* __restrict__ mr, const float4* __restrict__ gamma,
                                                        const float4* __restrict__ beta, long long rows, int rpg, int C4,
                                                        const float4* __restrict__ cw, const float4* __restrict__ cb,
-                                                       const float* __restrict__ slope) {
+                                                       const float* __restrict__ slope, uint2* __restrict__ out_hi, uint2* __restrict__ out_lo) {
     const long long total = rows * C4;
     const float a = UNFOLD ? slope[0] : 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -61,6 +61,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float4* __restrict_
             o.w = prelu_f(fmaf(w.w, o.w, b.w), a);
         }
         out[i] = o;
+        if (out_hi != nullptr) {  // the same rows as bf16 hi/lo operand planes for the next in-projection GEMM
+            uint2 hh, ll;
+            split_pair(o.x, o.y, hh.x, ll.x);
+            split_pair(o.z, o.w, hh.y, ll.y);
+            out_hi[i] = hh;
+            if (out_lo != nullptr) out_lo[i] = ll;
+        }
     }
 }
 
@@ -354,7 +361,7 @@ cudaError_t launch_gn_finalize(const double* stats, float* mr, int groups, doubl
 
 cudaError_t launch_gn_apply(const float* y, const float* res, float* out, const float* mr, const float* gamma, const float* beta,
                             long long rows, int rows_per_group, int C, const float* cw, const float* cb, const float* slope,
-                            cudaStream_t st) {
+                            cudaStream_t st, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
     if (C & 3) return cudaErrorInvalidValue;
     long long total = rows * (C / 4);
     if (total <= 0) return cudaSuccess;
@@ -362,7 +369,7 @@ cudaError_t launch_gn_apply(const float* y, const float* res, float* out, const 
 #define DP_GN(R, U)                                                                                                              \
     gn_apply_kernel<R, U><<<grid, 256, 0, st>>>((const float4*)y, (const float4*)res, (float4*)out, mr, (const float4*)gamma,     \
                                                 (const float4*)beta, rows, rows_per_group, C / 4, (const float4*)cw,              \
-                                                (const float4*)cb, slope)
+                                                (const float4*)cb, slope, (uint2*)out_hi, (uint2*)out_lo)
     if (res) { if (cw) DP_GN(true, true); else DP_GN(true, false); }
     else     { if (cw) DP_GN(false, true); else DP_GN(false, false); }
 #undef DP_GN

@@ -186,9 +186,10 @@ cudaError_t launch_overlap_add_cl(const float* x, float* f, int B, int L, int K,
 cudaError_t launch_gn_finalize(const double* stats, float* mr, int groups, double cnt, double eps, cudaStream_t st);
 // out = res + (y - mean_g) * rstd_g * gamma + beta   (res may be null); group = row / rows_per_group; C channels.
 // unfold (cw != null): out = prelu(cw * out + cb, slope)
+// out_hi / out_lo (optional): the result also as bf16 hi/lo operand planes for the GEMM that consumes it
 cudaError_t launch_gn_apply(const float* y, const float* res, float* out, const float* mr, const float* gamma, const float* beta,
                             long long rows, int rows_per_group, int C, const float* cw, const float* cb, const float* slope,
-                            cudaStream_t st);
+                            cudaStream_t st, __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);
 // reductions for the GroupNorm backward: red[g] += (sum gamma*d, sum gamma*d*xhat); dgamma += sum d*xhat; dbeta += sum d
 cudaError_t launch_gn_bwd_reduce(const float* d, const float* y, const float* mr, const float* gamma, long long rows, int rows_per_group,
                                  int C, double* red, float* dgamma, float* dbeta, cudaStream_t st);
