@@ -96,6 +96,13 @@ LstmPackOut out_pack(void* pack) {
 int g_backend = 2;  // 0: mma.sync GEMMs everywhere; 1: first-generation tcgen05 kernels (threads convert fp32 operands);
                     // 2 (default): TMA-fed tcgen05 kernels on pre-split bf16 operand planes (gemm_tma.cu) in the engines
 
+// backend 2 only: fused in-projection + recurrence tcgen05 kernel (lstm_tc5.cu) instead of GEMM + mma.sync recurrence.
+// 1 = automatic: the fused kernel streams every weight tile through the tensor core once per step (measured ~80 cycles per
+// TMEM-operand MMA, ~38 per shared-memory-operand MMA, independent of N), which wins in bf16 mode (48 MMAs per step) but not
+// with the three split products of the fp32-parity mode, where the register-stationary mma.sync recurrence is faster.
+// 2 = always, 0 = never.
+int g_fused_lstm = 1;
+
 }  // namespace
 
 namespace dp {
@@ -135,6 +142,11 @@ int dp_version(void) { return 101; }
 int dp_set_gemm_backend(int backend) {
     if (backend < 0 || backend > 2) return fail("dp_set_gemm_backend: 0 (mma.sync), 1 (tcgen05, converting threads) or 2 (TMA-fed tcgen05 on planes)");
     g_backend = backend;
+    return 0;
+}
+int dp_set_fused_lstm(int mode) {
+    if (mode < 0 || mode > 2) return fail("dp_set_fused_lstm: 0 (never), 1 (automatic) or 2 (always)");
+    g_fused_lstm = mode;
     return 0;
 }
 const char* dp_last_error(void) { return g_err; }
@@ -539,9 +551,10 @@ int dp_tasnet_create(const dp_tasnet_config* cfg, const int64_t* offsets, int n_
 }
 void dp_tasnet_destroy(dp_tasnet* h) { delete h; }
 
+inline size_t tc5_pack_stride() { return (lstm_tc5_pack_bytes() + 255) & ~(size_t)255; }
 int64_t dp_tasnet_pack_bytes(const dp_tasnet* h) {
     size_t flat = ((size_t)h->n_params * 2 + 255) & ~(size_t)255;
-    return (int64_t)(2 * flat + (size_t)h->npath * PK_BYTES);
+    return (int64_t)(2 * flat + (size_t)h->npath * PK_BYTES + (size_t)h->npath * tc5_pack_stride());
 }
 int64_t dp_tasnet_workspace_bytes(const dp_tasnet* h, int B, int T, int train) {
     Geo g;
@@ -563,6 +576,7 @@ int dp_tasnet_pack(dp_tasnet* h, const float* params, void* pack, void* stream) 
         const float* bi[2] = {params + o[2], params + o[6]};
         const float* bh[2] = {params + o[3], params + o[7]};
         CK(launch_pack_lstm(wi, wh, bi, bh, params + o[8], out_pack(b + 2 * flat + (size_t)pp * PK_BYTES), S(stream)));
+        CK(launch_pack_lstm_tc5(wi, wh, b + 2 * flat + (size_t)h->npath * PK_BYTES + (size_t)pp * tc5_pack_stride(), S(stream)));
     }
     return 0;
 }
@@ -659,16 +673,23 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
             // every GEMM operand is a pair of bf16 planes written by its producer; TMA -> tcgen05 (gemm_tma.cu)
             __nv_bfloat16* Xhl = at<__nv_bfloat16>(ws, l.Xhl[pp]);
             __nv_bfloat16* Hhl = at<__nv_bfloat16>(ws, l.Hhl[pp]);
-            {
-                TmaGemmArgs a = tma_args(Xhl, plX, 64, v.wih_hi, v.wih_lo, 64, G, 1024, (int)g.PT, 1024, 64);
-                a.bias = v.bias;
-                CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
-            }
             LstmPlanes pl;
             pl.h_hi = Hhl; pl.h_lo = sp ? Hhl + plH : nullptr;
             pl.hp_hi = train ? at<__nv_bfloat16>(ws, l.Hphl[pp]) : nullptr;
             pl.hp_lo = (train && sp) ? pl.hp_hi + plH : nullptr;
-            CK(launch_lstm_fwd(v.rec, G, nullptr, train ? at<float>(ws, l.Cst[pp]) : nullptr, path_map(g, pp), sp, train != 0, st, &pl)); ++nl;
+            if (g_fused_lstm == 2 || (g_fused_lstm == 1 && !sp)) {
+                // input projection + recurrence in one tcgen05 kernel: the [P,1024] gate pre-activations never exist in HBM
+                LstmFusedGeom gm;
+                gm.inter = pp & 1; gm.len = (pp & 1) ? g.Sc : g.K; gm.nseq = (pp & 1) ? B * g.K : B * g.Sc; gm.K = g.K; gm.S = g.Sc; gm.B = B;
+                const char* t5 = static_cast<const char*>(pack) + 2 * flat + (size_t)h->npath * PK_BYTES + (size_t)pp * tc5_pack_stride();
+                CK(launch_lstm_fused_fwd(t5, v.bias, Xhl, sp ? Xhl + plX : nullptr, train ? G : nullptr, train ? at<float>(ws, l.Cst[pp]) : nullptr,
+                                         pl, gm, sp, train != 0, st)); ++nl;
+            } else {
+                TmaGemmArgs a = tma_args(Xhl, plX, 64, v.wih_hi, v.wih_lo, 64, G, 1024, (int)g.PT, 1024, 64);
+                a.bias = v.bias;
+                CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                CK(launch_lstm_fwd(v.rec, G, nullptr, train ? at<float>(ws, l.Cst[pp]) : nullptr, path_map(g, pp), sp, train != 0, st, &pl)); ++nl;
+            }
             {
                 TmaGemmArgs a = tma_args(Hhl, plH, 256, whi + po[8], wlo + po[8], 256, Y, 64, (int)g.PT, 64, 256);
                 a.bias = params + po[9];

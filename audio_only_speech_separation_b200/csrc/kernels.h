@@ -147,6 +147,20 @@ cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, c
                             cudaStream_t st, const LstmPlanes* planes = nullptr);
 // dH: [P,256] incoming gradient of H.  G holds activated gates on entry and d(pre-activations) on exit.
 // dbias (optional, [1024] packed order) accumulates sum_p dG[p,:] (the bias gradient) inside the same kernel.
+// ---- fused input projection + recurrence on tcgen05 (lstm_tc5.cu) ----
+struct LstmFusedGeom {
+    int inter;  // 0: sequences (b,s) of the stream [B,S,K,64] walk k ; 1: sequences (b,k) walk s
+    int len;    // time steps (K intra, S inter)
+    int nseq;   // number of sequences (B*S intra, B*K inter)
+    int K, S, B;
+};
+size_t lstm_tc5_pack_bytes();
+// weight images for the fused kernel: bf16 hi rows (tensor-memory A operand) and swizzled lo images (shared-memory A operand)
+cudaError_t launch_pack_lstm_tc5(const float* const w_ih[2], const float* const w_hh[2], void* pack, cudaStream_t st);
+// x planes [P,64] -> H planes (+ h_prev planes, activated gates G [P,1024] and c_t Cst [P,256] when save); bias = packed b_ih + b_hh
+cudaError_t launch_lstm_fused_fwd(const void* pack, const float* bias, const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, float* G, float* Cst,
+                                  const LstmPlanes& pl, const LstmFusedGeom& gm, bool split, bool save, cudaStream_t st);
+
 // dG_hi / dG_lo (optional, [P,1024] planes): d(pre-activations) go there instead of overwriting G.
 cudaError_t launch_lstm_bwd(const LstmPack& w, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,
                             cudaStream_t st, __nv_bfloat16* dG_hi = nullptr, __nv_bfloat16* dG_lo = nullptr);

@@ -25,9 +25,14 @@ extern "C" {
 
 int dp_version(void);
 const char* dp_last_error(void);
-/* GEMM backend of dp_linear*_f32 and of the engine: 1 = tcgen05/TMEM kernels where the shape is supported,
- * 0 = warp-level mma.sync kernels everywhere.  Both are covered by the parity tests; see DESIGN.md for the default. */
+/* GEMM backend of the engines: 2 (default) = TMA-fed tcgen05/TMEM kernels on bf16 hi/lo operand planes written by the
+ * producers; 1 = first-generation tcgen05 kernels (threads convert fp32 operands); 0 = warp-level mma.sync kernels
+ * everywhere.  All are covered by the parity tests. */
 int dp_set_gemm_backend(int backend);
+/* backend 2 only: the LSTM input projection and recurrence as ONE tcgen05 kernel (weights resident in tensor memory / shared
+ * memory, gate pre-activations never in HBM).  mode 1 (default) = automatic (used in bf16 mode, where it is faster than the TMA
+ * GEMM + register-stationary mma.sync recurrence), 2 = always, 0 = never. */
+int dp_set_fused_lstm(int mode);
 
 /* ---- geometry (integer index maps) --------------------------------------------------------------------- */
 /* gc3_basics.py:63-76 pad_segment: rest and chunk count S for L frames and chunk size K (K even). */
