@@ -27,6 +27,8 @@ import torch  # noqa: E402
 
 SR, SECONDS, BATCH = 8000, 4.0, 16
 CFG = dict(enc_dim=64, bn_dim=64, hidden_dim=128, win=16, layer=6, num_spk=2, module="DPRNN", group_size=1, block_size=100, unfold=False)
+# dram__bytes_read.sum + dram__bytes_write.sum of one lstm_fwd_kernel launch (ncu --set full capture under profiles/), by batch
+TRAFFIC_BYTES_PER_LAUNCH = {16: 537967872 + 884442368}  # profiles/r1_lstm_fwd_v7_full.summary.txt (engine launch, inter-chunk pass)
 METRIC = "train samples/sec (DPRNN wsj0, batch 16/GPU, 4 s @ 8 kHz, fwd + PIT-SNR loss + bwd + clip + Adam)"
 
 
@@ -38,33 +40,61 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock / throttle reasons sampled every 20 ms through NVML while the timed region runs (nvidia-smi fallback)."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.max_sm, self.reasons, self.stop_flag = index, [], 0, set(), False
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        self.max_sm = max(self.max_sm, int(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        for name, bit in (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        c = [v.strip() for v in out.split(",")]
+        if c and c[0].isdigit():
+            self.sm.append(int(c[0]))
+            self.max_sm = max(self.max_sm, int(c[1]) if c[1].isdigit() else 0)
+            for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                if len(c) > 2 + i and c[2 + i].lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02 if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag = True
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm or None, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def synthetic(batch, seed):
@@ -131,7 +161,8 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ our arm
 def time_recurrence(model, B, precision):
-    """Average duration of the dominant kernel (intra-chunk forward recurrence at the bench shape), CUDA events."""
+    """Average duration of the dominant kernel family's forward member (persistent BiLSTM recurrence, intra-chunk pass at the
+    bench shape, training mode: activated gates and cell states saved), timed alone with CUDA events."""
     from audio_only_speech_separation_b200 import _lib, ops
 
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -141,21 +172,22 @@ def time_recurrence(model, B, precision):
     G0 = torch.randn(P, 1024, device=dev) * 0.5
     G = torch.empty_like(G0)
     H = torch.empty(P, 256, device=dev)
+    Cst = torch.empty(P, 256, device=dev)
     prec = _lib.PREC_FP32 if precision == "fp32" else _lib.PREC_BF16
     times = []
     for it in range(6):
-        G.copy_(G0)  # also evicts nothing we care about: G (537 MB at B=16) is larger than L2
+        G.copy_(G0)  # G (537 MB at B=16) is larger than L2, so every timed launch starts cold
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(_lib.lib().dp_lstm_recurrence_f32(_lib.ptr(pack.buf), _lib.ptr(G), _lib.ptr(H), 0, B * S, K, 1 << 30, 0, K, 1, 0, prec,
-                                                      _lib.stream_ptr()))
+        _lib.check(_lib.lib().dp_lstm_recurrence_f32(_lib.ptr(pack.buf), _lib.ptr(G), _lib.ptr(H), _lib.ptr(Cst), B * S, K, 1 << 30, 0, K, 1, 1,
+                                                      prec, _lib.stream_ptr()))
         e1.record()
         torch.cuda.synchronize()
         if it >= 2:
             times.append(e0.elapsed_time(e1) * 1e-3)
     sec = sum(times) / len(times)
-    flops = 2.0 * 512 * 128 * (B * S) * K * 2  # h_{t-1} W_hh^T, both directions (algorithmic: one product per MAC)
-    hbm = P * (1024 + 256) * 4.0               # read G, write H
+    flops = 2.0 * 512 * 128 * (B * S) * K * 2   # h_{t-1} W_hh^T, both directions (algorithmic: one product per MAC)
+    hbm = P * (1024 + 1024 + 256 + 256) * 4.0   # read G, write activated gates, c_t and H = 84 MB per utterance
     return sec, flops, hbm
 
 
@@ -249,11 +281,14 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * sec_e2e / args.steps, "loss": last.get("loss")},
             "gpu_launches": trainer.launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "lstm_fwd_kernel (persistent BiLSTM recurrence, intra-chunk pass)", "bound": "tensor",
-                         "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"], "traffic": None,
-                         "peak_source": f"{pk_kind} burst bf16 (kernel timed alone)", "ms_per_launch": 1e3 * k_sec,
-                         "hbm_gbs": k_hbm / k_sec / 1e9, "hbm_frac": k_hbm / k_sec / 1e9 / pk["hbm_gbs"],
-                         "note": "recurrence is latency/issue bound (SURVEY 8d); both fractions reported"},
+            "roofline": {"kernel": "lstm_fwd_kernel (persistent BiLSTM recurrence, intra-chunk pass, training mode; the recurrence "
+                                   "kernels fwd+bwd are ~58% of the step)", "bound": "hbm",
+                         "achieved": k_hbm / k_sec / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": k_hbm / k_sec / 1e9 / pk["hbm_gbs"],
+                         "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.batch),
+                         "peak_source": f"{pk_kind} HBM copy bandwidth (kernel timed alone)", "ms_per_launch": 1e3 * k_sec,
+                         "algorithmic_bytes_per_launch": k_hbm, "tensor_tflops": tf, "tensor_frac": tf / pk["bf16_tflops"],
+                         "note": "84 MB per utterance (SURVEY 8d: read G, write gates + c_t + H); the kernel is bound by the per-step "
+                                 "dependent chain (tensor-core issue + MUFU), not by HBM: both fractions reported"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -265,7 +300,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("DUALPATH_PRECISION", "fp32"), choices=["fp32", "bf16"])
