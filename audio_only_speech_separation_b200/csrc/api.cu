@@ -97,9 +97,9 @@ int g_backend = 2;  // 0: mma.sync GEMMs everywhere; 1: first-generation tcgen05
                     // 2 (default): TMA-fed tcgen05 kernels on pre-split bf16 operand planes (gemm_tma.cu) in the engines
 
 // backend 2 only: fused in-projection + recurrence tcgen05 kernel (lstm_tc5.cu) instead of GEMM + mma.sync recurrence.
-// 1 = automatic: the fused kernel streams every weight tile through the tensor core once per step (measured ~80 cycles per
-// TMEM-operand MMA, ~38 per shared-memory-operand MMA, independent of N), which wins in bf16 mode (48 MMAs per step) but not
-// with the three split products of the fp32-parity mode, where the register-stationary mma.sync recurrence is faster.
+// 1 = automatic: the fused kernel issues 48 small tcgen05.mma per split product and step (measured ~110 cycles each for
+// N <= 32), which wins in bf16 mode but not with the three split products of the fp32-parity mode, where the
+// register-stationary mma.sync recurrence is faster.
 // 2 = always, 0 = never.
 int g_fused_lstm = 1;
 

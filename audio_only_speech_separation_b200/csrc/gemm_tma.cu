@@ -102,7 +102,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(full + stage, phase);
                 tc_fence_after();
-                if (lane == 0) {
+                {   // whole warp, uniform operands; one elected lane issues (see umma_w)
                     const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE);
                     const uint32_t a_lo = a_hi + A_TILE;
                     const uint32_t w_hi = a_hi + A_TILE * (SPLIT ? 2 : 1);
@@ -110,15 +110,15 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t ah = desc_sw128(a_hi + k * 32, 16, 1024), wh = desc_sw128(w_hi + k * 32, 16, 1024);
-                        umma(d, ah, wh, IDESC, (kb | k) != 0);
+                        umma_w(d, ah, wh, IDESC, (kb | k) != 0);
                         if (SPLIT) {
                             const uint64_t al = desc_sw128(a_lo + k * 32, 16, 1024), wl = desc_sw128(w_lo + k * 32, 16, 1024);
-                            umma(d, ah, wl, IDESC, 1);
-                            umma(d, al, wh, IDESC, 1);
+                            umma_w(d, ah, wl, IDESC, 1);
+                            umma_w(d, al, wh, IDESC, 1);
                         }
                     }
-                    umma_commit(empty + stage);                    // smem slot reusable once these MMAs retire
-                    if (kb == nkb - 1) umma_commit(tfull + as);    // accumulator complete
+                    umma_commit_w(empty + stage);                    // smem slot reusable once these MMAs retire
+                    if (kb == nkb - 1) umma_commit_w(tfull + as);    // accumulator complete
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -369,7 +369,7 @@ gemm_tma_tn_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         for (int it = 0; it < nst; ++it) {
             mbar_wait(full + stage, phase);
             tc_fence_after();
-            if (lane == 0) {
+            {   // whole warp, uniform operands; one elected lane issues
                 const uint32_t a_hi = smem_u32(smem + stage * stage_bytes);
                 const uint32_t a_lo = a_hi + a_bytes;
                 const uint32_t b_hi = a_hi + (SPLIT ? 2 : 1) * a_bytes;
@@ -378,15 +378,15 @@ gemm_tma_tn_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 for (int k = 0; k < KP / 16; ++k) {
                     // MN-major: LBO = next 64 MN elements (one box), SBO = next 8 K-rows (1024 B); 16 K-rows per MMA = 2048 B
                     const uint64_t ah = desc_sw128(a_hi + k * 2048, BOX, 1024), bh = desc_sw128(b_hi + k * 2048, BOX, 1024);
-                    umma(tmem, ah, bh, idesc, (it | k) != 0);
+                    umma_w(tmem, ah, bh, idesc, (it | k) != 0);
                     if (SPLIT) {
                         const uint64_t al = desc_sw128(a_lo + k * 2048, BOX, 1024), bl = desc_sw128(b_lo + k * 2048, BOX, 1024);
-                        umma(tmem, ah, bl, idesc, 1);
-                        umma(tmem, al, bh, idesc, 1);
+                        umma_w(tmem, ah, bl, idesc, 1);
+                        umma_w(tmem, al, bh, idesc, 1);
                     }
                 }
-                umma_commit(empty + stage);
-                if (it == nst - 1) umma_commit(done);
+                umma_commit_w(empty + stage);
+                if (it == nst - 1) umma_commit_w(done);
             }
             __syncwarp();
             if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }

@@ -5,17 +5,19 @@
 // chain of tcgen05.mma instructions (M = 128 gate rows, N = 16 sequences, K = 16), so the [P, 1024] gate pre-activation
 // tensor (16x the activation, SURVEY 7 hard part 2) is never written to or read from HBM.
 //
-// One CTA = one direction x two groups of 16 sequences; the whole time loop runs inside the kernel.
-//   * weights never leave the SM: the bf16 "hi" halves of W_hh and W_ih live in TENSOR MEMORY as the A operand
-//     (256 + 128 columns), their "lo" halves (fp32-parity mode) in 192 KB of shared memory in the UMMA 128-byte-swizzle
-//     K-major layout; the four M tiles are the i, f, g, o rows of the 128 hidden units, so TMEM lane r holds all four
-//     gates of unit r and the cell update needs no exchange
+// One CTA = one direction x 32 sequences; the whole time loop runs inside the kernel.
+//   * weights never leave the SM: the bf16 "hi" halves of W_hh and W_ih (read by two of the three split products) sit in
+//     192 KB of shared memory in the UMMA 128-byte-swizzle K-major layout, their "lo" halves (fp32-parity mode) in TENSOR
+//     MEMORY as the A operand (256 + 128 columns, written once with tcgen05.st).  The four M tiles are the i, f, g, o rows
+//     of the 128 hidden units, so TMEM lane r holds all four gates of unit r and the cell update needs no exchange
+//   * measured on B200 (tests/tools/time_lstm.py): a tcgen05.mma with M = 128, K = 16 and N <= 32 occupies the tensor pipe
+//     for ~110 cycles whatever the operand source (shared or tensor memory), the accumulator or the issuing warp, i.e. ~7x its
+//     arithmetic floor; a step needs (512/128) x (192/16) = 48 of them per split product.  That makes the kernel a win in bf16
+//     mode (48 MMAs per step) and a small loss against the register-stationary mma.sync recurrence in fp32-parity mode (144)
 //   * x_t tiles arrive by TMA straight from the producer's bf16 hi/lo planes (4-D tensor map: the strided positions of
 //     the 16 sequences at time t are one box), double buffered, one step ahead
-//   * warp roles: TMA producer | one MMA issuer per group | 4 epilogue warps per group (tcgen05.ld gates -> activations -> c, h; h goes
-//     back to shared memory as the next step's B operand) | 1 copy-out warp per group (h tiles -> H / h_prev planes with
-//     128-bit stores).  The two groups ping-pong: while one group's gates are in the MUFU-bound cell update, the tensor
-//     core runs the other group's step.
+//   * warp roles: TMA producer | 4 MMA issuers (one per gate tile) | 4 cell-update warps (tcgen05.ld gates -> activations -> c, h; h goes back to
+//     shared memory as the next step's B operand) | 2 copy-out warps (h tile -> H / h_prev planes with 128-bit stores).
 //   * training additionally stores the activated gates [P,1024] and c_t for the BPTT kernel.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -31,15 +33,15 @@ namespace {
 
 constexpr int GN = 16;                 // sequences per group (UMMA N)
 constexpr int TILE = GN * 128;         // one [16 rows x 64 bf16] operand tile: 2 KB
-constexpr int HH_LO_BYTES = 4 * 2 * 128 * 128;  // 128 KB
-constexpr int IH_LO_BYTES = 4 * 128 * 128;      // 64 KB
+constexpr int HH_SM_BYTES = 4 * 2 * 128 * 128;  // 128 KB swizzled shared-memory image of W_hh (hi half)
+constexpr int IH_SM_BYTES = 4 * 128 * 128;      // 64 KB  swizzled shared-memory image of W_ih (hi half)
 constexpr uint32_t COL_IH = 256, COL_D = 384;
 
 struct FusedArgs {
-    const uint32_t* hh_hi;  // [dir][4][128][64] u32 (pairs of bf16 along k)
-    const uint4* hh_lo;     // [dir][HH_LO_BYTES / 16] swizzled image
-    const uint32_t* ih_hi;  // [dir][4][128][32] u32
-    const uint4* ih_lo;     // [dir][IH_LO_BYTES / 16]
+    const uint32_t* hh_tm;  // lo half, tensor-memory rows: [dir][4][128][64] u32 (pairs of bf16 along k)
+    const uint4* hh_sm;     // hi half, [dir][HH_SM_BYTES / 16] swizzled shared-memory image
+    const uint32_t* ih_tm;  // [dir][4][128][32] u32
+    const uint4* ih_sm;     // [dir][IH_SM_BYTES / 16]
     const float* bias;      // [1024] packed (dir*512 + unit*4 + gate)
     float* G;               // [P,1024] activated gates (SAVE)
     float* Cst;             // [P,256]
@@ -55,70 +57,71 @@ struct FusedArgs {
 };
 
 template <bool SPLIT, bool SAVE>
-__global__ void __launch_bounds__(416, 1)
+__global__ void __launch_bounds__(352, 1)
 lstm_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl, const FusedArgs p) {
     constexpr int PL = SPLIT ? 2 : 1;
-    constexpr int OFF_IH = SPLIT ? HH_LO_BYTES : 0;
-    constexpr int OFF_HS = SPLIT ? HH_LO_BYTES + IH_LO_BYTES : 0;
-    constexpr int HS_G = PL * 2 * TILE;             // per group: planes x k-blocks
-    constexpr int OFF_XS = OFF_HS + 2 * HS_G;
-    constexpr int XS_GB = PL * TILE;                // per (group, buffer)
-    constexpr int OFF_BAR = OFF_XS + 4 * XS_GB;
+    constexpr int NS = 2 * GN;                      // 32 sequences per CTA = UMMA N (two 16-row TMA boxes)
+    constexpr int T32 = NS * 128;                   // one [32 rows x 64 bf16] operand tile: 4 KB
+    constexpr int OFF_IH = HH_SM_BYTES;
+    constexpr int OFF_HS = HH_SM_BYTES + IH_SM_BYTES;
+    constexpr int HS_BYTES = PL * 2 * T32;          // planes x k-blocks
+    constexpr int OFF_XS = OFF_HS + HS_BYTES;
+    constexpr int XS_B = PL * T32;                  // per buffer
+    constexpr int OFF_BAR = OFF_XS + 2 * XS_B;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);  // [g][b]
-    uint64_t* x_empty = x_full + 4;
-    uint64_t* d_full = x_empty + 4;   // [g]
-    uint64_t* h_ready = d_full + 2;   // [g]
-    uint64_t* h_copied = h_ready + 2; // [g]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_copied + 2);
-    int* sbase = reinterpret_cast<int*>(tmem_slot + 2);  // [2][GN] position of (sequence, t = 0), -1 = not a sequence
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);  // [b]
+    uint64_t* x_empty = x_full + 2;
+    uint64_t* d_full = x_empty + 2;
+    uint64_t* h_ready = d_full + 1;
+    uint64_t* h_copied = h_ready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_copied + 1);
+    int* sbase = reinterpret_cast<int*>(tmem_slot + 2);  // [NS] position of (sequence, t = 0), -1 = not a sequence
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
     const int len = p.len;
-    const int tpb = (p.nseq + GN - 1) / GN;  // inter: tiles per utterance
+    const int tpb = (p.nseq + GN - 1) / GN;  // inter: 16-row boxes per utterance
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(d_full + g, 1); mbar_init(h_ready + g, 128); mbar_init(h_copied + g, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 4); }
+        mbar_init(d_full, 4); mbar_init(h_ready, 128); mbar_init(h_copied, 2);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         prefetch_tmap(&tmXh);
         if (SPLIT) prefetch_tmap(&tmXl);
     }
-    if (tid < 2 * GN) {
-        const int g = tid / GN, n = tid % GN;
-        const int tile = blockIdx.x * 2 + g;
+    if (tid < NS) {
+        const int box = blockIdx.x * 2 + tid / GN, n = tid % GN;
         int v = -1;
         if (!p.inter) {
-            const int q = tile * GN + n;
+            const int q = box * GN + n;
             if (q < p.nseq) v = q * len;
         } else {
-            const int b = tile / tpb, k = (tile % tpb) * GN + n;
+            const int b = box / tpb, k = (box % tpb) * GN + n;
             if (b < p.B && k < p.nseq) v = b * p.S * p.nseq + k;
         }
         sbase[tid] = v;
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
-    if (SPLIT) {  // lo halves of the weights: ready-made swizzled images, plain 128-bit copies
-        const uint4* s0 = p.hh_lo + (size_t)dir * (HH_LO_BYTES / 16);
+    {   // hi halves of the weights -> shared memory: ready-made 128-byte-swizzled K-major images, plain 128-bit copies
+        const uint4* s0 = p.hh_sm + (size_t)dir * (HH_SM_BYTES / 16);
         uint4* d0 = reinterpret_cast<uint4*>(smem);
-        for (int i = tid; i < HH_LO_BYTES / 16; i += 416) d0[i] = s0[i];
-        const uint4* s1 = p.ih_lo + (size_t)dir * (IH_LO_BYTES / 16);
+        for (int i = tid; i < HH_SM_BYTES / 16; i += 352) d0[i] = s0[i];
+        const uint4* s1 = p.ih_sm + (size_t)dir * (IH_SM_BYTES / 16);
         uint4* d1 = reinterpret_cast<uint4*>(smem + OFF_IH);
-        for (int i = tid; i < IH_LO_BYTES / 16; i += 416) d1[i] = s1[i];
+        for (int i = tid; i < IH_SM_BYTES / 16; i += 352) d1[i] = s1[i];
         proxy_fence_async();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (warp >= 2 && warp < 6) {  // hi halves -> tensor memory (lane = gate row of unit r, one column = two k values)
+    if (SPLIT && warp >= 5 && warp < 9) {  // lo halves -> tensor memory (lane = gate row of unit r, one column = two k values)
         const int q = warp & 3, r = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
-            const uint32_t* src = p.hh_hi + ((size_t)(dir * 4 + j) * 128 + r) * 64;
+            const uint32_t* src = p.hh_tm + ((size_t)(dir * 4 + j) * 128 + r) * 64;
 #pragma unroll 1
             for (int c = 0; c < 64; c += 32) {
                 uint32_t v[32];
@@ -129,7 +132,7 @@ lstm_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_con
                 }
                 tmem_st32(lane_addr + j * 64 + c, v);
             }
-            const uint32_t* si = p.ih_hi + ((size_t)(dir * 4 + j) * 128 + r) * 32;
+            const uint32_t* si = p.ih_tm + ((size_t)(dir * 4 + j) * 128 + r) * 32;
             uint32_t v[32];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -145,103 +148,95 @@ lstm_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_con
     tc_fence_after();
 
     if (warp == 0) {
-        // ===================== TMA producer: x_t tiles of both groups, one step ahead =====================
+        // ===================== TMA producer: x_t tiles (two 16-sequence boxes per plane), one step ahead =====================
         if (lane == 0) {
             for (int step = 0; step < len; ++step) {
                 const int t = dir ? len - 1 - step : step;
                 const int b = step & 1;
-                for (int g = 0; g < 2; ++g) {
-                    const int tile = blockIdx.x * 2 + g;
-                    mbar_wait(x_empty + g * 2 + b, ((step >> 1) & 1) ^ 1);
-                    uint8_t* dst = smem + OFF_XS + (g * 2 + b) * XS_GB;
-                    mbar_expect_tx(x_full + g * 2 + b, XS_GB);
+                mbar_wait(x_empty + b, ((step >> 1) & 1) ^ 1);
+                uint8_t* dst = smem + OFF_XS + b * XS_B;
+                mbar_expect_tx(x_full + b, XS_B);
+                for (int half = 0; half < 2; ++half) {
+                    const int box = blockIdx.x * 2 + half;
                     int c1, c2, c3;
-                    if (!p.inter) { c1 = t; c2 = tile * GN; c3 = 0; }
-                    else { c1 = (tile % tpb) * GN; c2 = t; c3 = tile / tpb; }
-                    tma_load_4d(dst, &tmXh, x_full + g * 2 + b, 0, c1, c2, c3);
-                    if (SPLIT) tma_load_4d(dst + TILE, &tmXl, x_full + g * 2 + b, 0, c1, c2, c3);
+                    if (!p.inter) { c1 = t; c2 = box * GN; c3 = 0; }
+                    else { c1 = (box % tpb) * GN; c2 = t; c3 = box / tpb; }
+                    tma_load_4d(dst + half * TILE, &tmXh, x_full + b, 0, c1, c2, c3);
+                    if (SPLIT) tma_load_4d(dst + T32 + half * TILE, &tmXl, x_full + b, 0, c1, c2, c3);
                 }
             }
         }
-    } else if (warp == 1 || warp == 12) {
-        // ===================== MMA issuers: one warp per group so the two groups' instruction streams overlap =====================
-        // All shared-memory descriptors are loop invariant: they are built once and stepped by adding (bytes >> 4) to the
-        // start-address field, so issuing one MMA costs a handful of scalar instructions (the MMAs are tiny: N = 16).
-        constexpr uint32_t IDESC = idesc_bf16(128, GN, 0, 0);
-        const int g = warp == 1 ? 0 : 1;
-        const uint64_t d_hh = desc_sw128(smem_u32(smem), 16, 1024);              // W_hh lo, tile (j, kb) at +(j*2+kb)*16 KB
-        const uint64_t d_ih = desc_sw128(smem_u32(smem + OFF_IH), 16, 1024);     // W_ih lo, tile j at +j*16 KB
-        const uint64_t d_hs = desc_sw128(smem_u32(smem + OFF_HS + g * HS_G), 16, 1024);
-        const uint64_t d_xs0 = desc_sw128(smem_u32(smem + OFF_XS + (g * 2) * XS_GB), 16, 1024);
+    } else if (warp < 5) {
+        // ===================== MMA issuers: one warp per gate tile =====================
+        // The four independent gate tiles (i, f, g, o rows = four accumulators) are issued by four warps with warp-uniform
+        // control flow (one elected lane issues; see umma_w).  hi weights are the shared-memory A operand (two of the three split
+        // products), lo weights the tensor-memory A operand.
+        constexpr uint32_t IDESC = idesc_bf16(128, NS, 0, 0);
+        const int j = warp - 1;
+        const uint64_t d_hh = desc_sw128(smem_u32(smem) + j * 32768, 16, 1024);            // W_hh hi, tile (j, kb) at +(j*2+kb)*16 KB
+        const uint64_t d_ih = desc_sw128(smem_u32(smem + OFF_IH) + j * 16384, 16, 1024);   // W_ih hi, tile j at +j*16 KB
+        const uint64_t d_hs = desc_sw128(smem_u32(smem + OFF_HS), 16, 1024);
+        const uint64_t d_xs0 = desc_sw128(smem_u32(smem + OFF_XS), 16, 1024);
+        const uint32_t d = tmem + COL_D + j * NS;
+        const uint32_t a_ih = tmem + COL_IH + j * 32, a_hh = tmem + j * 64;
         for (int step = 0; step < len; ++step) {
             const int b = step & 1;
-            if (step > 0) mbar_wait(h_ready + g, (step - 1) & 1);   // h_{t-1} of this group is in shared memory
-            mbar_wait(x_full + g * 2 + b, (step >> 1) & 1);
+            if (step > 0) mbar_wait(h_ready, (step - 1) & 1);   // h_{t-1} is in shared memory
+            mbar_wait(x_full + b, (step >> 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
-                const uint64_t d_xs = d_xs0 + (uint64_t)(b * (XS_GB >> 4));
-                const uint32_t d0 = tmem + COL_D + g * 64;
-                // Consecutive MMAs on one accumulator serialise on the tensor pipe's latency (~100 cycles for these tiny
-                // N = 16 tiles), so the four gate tiles (independent accumulators) are interleaved innermost.
+            const uint64_t d_xs = d_xs0 + (uint64_t)(b * (XS_B >> 4));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // x_t W_ih^T, K = 64
-                    const uint64_t bxh = d_xs + (uint64_t)(k * 2);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) umma_ts(d0 + j * GN, tmem + COL_IH + j * 32 + k * 8, bxh, IDESC, k != 0);
-                    if (SPLIT) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) umma_ts(d0 + j * GN, tmem + COL_IH + j * 32 + k * 8, bxh + (uint64_t)(TILE >> 4), IDESC, 1);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) umma(d0 + j * GN, d_ih + (uint64_t)(j * 1024 + k * 2), bxh, IDESC, 1);
-                    }
+            for (int k = 0; k < 4; ++k) {  // x_t W_ih^T, K = 64
+                const uint64_t bxh = d_xs + (uint64_t)(k * 2);
+                umma_w(d, d_ih + (uint64_t)(k * 2), bxh, IDESC, k != 0);
+                if (SPLIT) {
+                    umma_w(d, d_ih + (uint64_t)(k * 2), bxh + (uint64_t)(T32 >> 4), IDESC, 1);
+                    umma_ts_w(d, a_ih + k * 8, bxh, IDESC, 1);
                 }
-                if (step > 0) {
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {  // h_{t-1} W_hh^T, K = 128 (two 64-wide k blocks)
-                        const int kb = kk >> 2, k = kk & 3;
-                        const uint64_t bhh = d_hs + (uint64_t)(kb * (TILE >> 4) + k * 2);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) umma_ts(d0 + j * GN, tmem + j * 64 + kk * 8, bhh, IDESC, 1);
-                        if (SPLIT) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) umma_ts(d0 + j * GN, tmem + j * 64 + kk * 8, bhh + (uint64_t)((2 * TILE) >> 4), IDESC, 1);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) umma(d0 + j * GN, d_hh + (uint64_t)((j * 2 + kb) * 1024 + k * 2), bhh, IDESC, 1);
-                        }
-                    }
-                }
-                umma_commit(x_empty + g * 2 + b);
-                umma_commit(d_full + g);
             }
+            if (step > 0) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {  // h_{t-1} W_hh^T, K = 128 (two 64-wide k blocks)
+                    const int kb = kk >> 2, k = kk & 3;
+                    const uint64_t bhh = d_hs + (uint64_t)(kb * (T32 >> 4) + k * 2);
+                    umma_w(d, d_hh + (uint64_t)(kb * 1024 + k * 2), bhh, IDESC, 1);
+                    if (SPLIT) {
+                        umma_w(d, d_hh + (uint64_t)(kb * 1024 + k * 2), bhh + (uint64_t)((2 * T32) >> 4), IDESC, 1);
+                        umma_ts_w(d, a_hh + kk * 8, bhh, IDESC, 1);
+                    }
+                }
+            }
+            umma_commit_w(x_empty + b);
+            umma_commit_w(d_full);
             __syncwarp();
         }
-    } else if (warp < 10) {
-        // ===================== cell update: 4 warps per group, thread = hidden unit =====================
-        const int g = (warp - 2) >> 2, q = warp & 3, r = q * 32 + lane;
+    } else if (warp < 9) {
+        // ===================== cell update: thread = hidden unit, 32 sequences =====================
+        const int q = warp & 3, r = q * 32 + lane;
         const float4 bias = *reinterpret_cast<const float4*>(p.bias + dir * kG + r * 4);
-        const uint32_t d_addr = tmem + ((uint32_t)(q * 32) << 16) + COL_D + g * 64;
-        uint8_t* hs = smem + OFF_HS + g * HS_G;
+        const uint32_t d_addr = tmem + ((uint32_t)(q * 32) << 16) + COL_D;
+        uint8_t* hs = smem + OFF_HS;
         const int kb = r >> 6, cch = (r & 63) >> 3, e2 = (r & 7) * 2;
-        float cst[GN];
+        float cst[NS];
 #pragma unroll
-        for (int n = 0; n < GN; ++n) cst[n] = 0.f;
+        for (int n = 0; n < NS; ++n) cst[n] = 0.f;
         for (int step = 0; step < len; ++step) {
             const int t = dir ? len - 1 - step : step;
             const long long toff = (long long)t * p.s_t;
-            mbar_wait(d_full + g, step & 1);
+            mbar_wait(d_full, step & 1);
             tc_fence_after();
-            if (step > 0) mbar_wait(h_copied + g, (step - 1) & 1);  // the copy-out warp is done with the previous h tile
+            if (step > 0) mbar_wait(h_copied, (step - 1) & 1);  // the copy-out warps are done with the previous h tile
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int part = 0; part < NS / 8; ++part) {
                 float gi[8], gf[8], gg[8], go[8];
-                tmem_ld8_nowait(d_addr + 0 * GN + half * 8, gi);
-                tmem_ld8_nowait(d_addr + 1 * GN + half * 8, gf);
-                tmem_ld8_nowait(d_addr + 2 * GN + half * 8, gg);
-                tmem_ld8_nowait(d_addr + 3 * GN + half * 8, go);
+                tmem_ld8_nowait(d_addr + 0 * NS + part * 8, gi);
+                tmem_ld8_nowait(d_addr + 1 * NS + part * 8, gf);
+                tmem_ld8_nowait(d_addr + 2 * NS + part * 8, gg);
+                tmem_ld8_nowait(d_addr + 3 * NS + part * 8, go);
                 tmem_ld_wait();
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
-                    const int sl = half * 8 + n;
+                    const int sl = part * 8 + n;
                     const float ig = sigmoid_f<SPLIT>(gi[n] + bias.x);
                     const float fg = sigmoid_f<SPLIT>(gf[n] + bias.y);
                     const float g2 = tanh_f<SPLIT>(gg[n] + bias.z);
@@ -250,7 +245,7 @@ lstm_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_con
                     cst[sl] = cc;
                     const float hh = og * tanh_f<SPLIT>(cc);
                     if (SAVE) {
-                        const int sb = sbase[g * GN + sl];
+                        const int sb = sbase[sl];
                         if (sb >= 0) {
                             const size_t pos = (size_t)(sb + toff);
                             *reinterpret_cast<float4*>(p.G + pos * 1024 + dir * kG + r * 4) = make_float4(ig, fg, g2, og);
@@ -258,23 +253,23 @@ lstm_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_con
                         }
                     }
                     const __nv_bfloat16 hb = __float2bfloat16_rn(hh);
-                    const uint32_t off = kb * TILE + sl * 128 + ((cch ^ (sl & 7)) << 4) + e2;
+                    const uint32_t off = kb * T32 + sl * 128 + ((cch ^ (sl & 7)) << 4) + e2;
                     *reinterpret_cast<__nv_bfloat16*>(hs + off) = hb;
-                    if (SPLIT) *reinterpret_cast<__nv_bfloat16*>(hs + 2 * TILE + off) = __float2bfloat16_rn(hh - __bfloat162float(hb));
+                    if (SPLIT) *reinterpret_cast<__nv_bfloat16*>(hs + 2 * T32 + off) = __float2bfloat16_rn(hh - __bfloat162float(hb));
                 }
             }
             proxy_fence_async();  // h tile (generic-proxy stores) -> visible to the tensor core's async proxy
             tc_fence_before();
-            mbar_arrive(h_ready + g);
+            mbar_arrive(h_ready);
         }
-    } else if (warp < 12) {
-        // ===================== copy-out: h tiles -> H (own position) and h_prev (next visited position) planes =====================
-        const int g = warp - 10;
-        const uint8_t* hs = smem + OFF_HS + g * HS_G;
+    } else {
+        // ===================== copy-out (2 warps, 16 sequences each): h tile -> H (own position) and h_prev (next position) planes =====================
+        const int g = warp - 9;
+        const uint8_t* hs = smem + OFF_HS;
         if (SAVE && p.hp_hi != nullptr) {  // h_prev of the first visited step is zero
             const long long t0 = (long long)(dir ? len - 1 : 0) * p.s_t;
             for (int ch = lane; ch < GN * 16; ch += 32) {
-                const int n = ch >> 4, u = ch & 15, sb = sbase[g * GN + n];
+                const int n = g * GN + (ch >> 4), u = ch & 15, sb = sbase[n];
                 if (sb < 0) continue;
                 const size_t o = (size_t)(sb + t0) * 256 + dir * kH + u * 8;
                 *reinterpret_cast<uint4*>(p.hp_hi + o) = make_uint4(0, 0, 0, 0);
@@ -286,14 +281,14 @@ lstm_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_con
             const long long toff = (long long)t * p.s_t;
             const long long tnext = (long long)(dir ? t - 1 : t + 1) * p.s_t;
             const bool has_next = step + 1 < len;
-            mbar_wait(h_ready + g, step & 1);
+            mbar_wait(h_ready, step & 1);
             for (int ch = lane; ch < GN * 16; ch += 32) {
-                const int n = ch >> 4, u = ch & 15, sb = sbase[g * GN + n];
+                const int n = g * GN + (ch >> 4), u = ch & 15, sb = sbase[n];
                 if (sb < 0) continue;
-                const uint32_t off = (u >> 3) * TILE + n * 128 + (((u & 7) ^ (n & 7)) << 4);
+                const uint32_t off = (u >> 3) * T32 + n * 128 + (((u & 7) ^ (n & 7)) << 4);
                 const uint4 vh = *reinterpret_cast<const uint4*>(hs + off);
                 uint4 vl = make_uint4(0, 0, 0, 0);
-                if (SPLIT) vl = *reinterpret_cast<const uint4*>(hs + 2 * TILE + off);
+                if (SPLIT) vl = *reinterpret_cast<const uint4*>(hs + 2 * T32 + off);
                 const size_t col = (size_t)dir * kH + u * 8;
                 if (p.h_hi != nullptr) {
                     const size_t o = (size_t)(sb + toff) * 256 + col;
@@ -307,7 +302,7 @@ lstm_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_con
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(h_copied + g);
+            if (lane == 0) mbar_arrive(h_copied);
         }
     }
     tc_fence_before();
@@ -319,10 +314,10 @@ lstm_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_con
 struct Tc5PackArgs {
     const float* w_ih[2];
     const float* w_hh[2];
-    uint16_t* hh_hi;  // [dir][4][128][128]
-    uint8_t* hh_lo;   // [dir][HH_LO_BYTES]
-    uint16_t* ih_hi;  // [dir][4][128][64]
-    uint8_t* ih_lo;   // [dir][IH_LO_BYTES]
+    uint16_t* hh_tm;  // lo half rows [dir][4][128][128]
+    uint8_t* hh_sm;   // hi half image [dir][HH_SM_BYTES]
+    uint16_t* ih_tm;  // [dir][4][128][64]
+    uint8_t* ih_sm;   // [dir][IH_SM_BYTES]
 };
 __device__ __forceinline__ uint16_t bf16_bits(float v) {
     __nv_bfloat16 b = __float2bfloat16_rn(v);
@@ -334,10 +329,10 @@ __global__ void pack_tc5_kernel(const Tc5PackArgs a) {
         const int k = idx & 127, r = (idx >> 7) & 127, j = (idx >> 14) & 3, d = idx >> 16;
         const float v = a.w_hh[d][(size_t)(j * kH + r) * kH + k];
         const float vh = bf16_round(v);
-        a.hh_hi[idx] = bf16_bits(vh);
+        a.hh_tm[idx] = bf16_bits(v - vh);
         const int kb = k >> 6, c = (k & 63) >> 3, e = k & 7;
-        const size_t off = (size_t)d * HH_LO_BYTES + ((size_t)((j * 2 + kb) * 128 + r)) * 128 + ((c ^ (r & 7)) << 4) + e * 2;
-        *reinterpret_cast<uint16_t*>(a.hh_lo + off) = bf16_bits(v - vh);
+        const size_t off = (size_t)d * HH_SM_BYTES + ((size_t)((j * 2 + kb) * 128 + r)) * 128 + ((c ^ (r & 7)) << 4) + e * 2;
+        *reinterpret_cast<uint16_t*>(a.hh_sm + off) = bf16_bits(vh);
         return;
     }
     idx -= 2 * 4 * 128 * 128;
@@ -345,10 +340,10 @@ __global__ void pack_tc5_kernel(const Tc5PackArgs a) {
         const int k = idx & 63, r = (idx >> 6) & 127, j = (idx >> 13) & 3, d = idx >> 15;
         const float v = a.w_ih[d][(size_t)(j * kH + r) * kN + k];
         const float vh = bf16_round(v);
-        a.ih_hi[idx] = bf16_bits(vh);
+        a.ih_tm[idx] = bf16_bits(v - vh);
         const int c = k >> 3, e = k & 7;
-        const size_t off = (size_t)d * IH_LO_BYTES + ((size_t)(j * 128 + r)) * 128 + ((c ^ (r & 7)) << 4) + e * 2;
-        *reinterpret_cast<uint16_t*>(a.ih_lo + off) = bf16_bits(v - vh);
+        const size_t off = (size_t)d * IH_SM_BYTES + ((size_t)(j * 128 + r)) * 128 + ((c ^ (r & 7)) << 4) + e * 2;
+        *reinterpret_cast<uint16_t*>(a.ih_sm + off) = bf16_bits(vh);
     }
 }
 
@@ -384,16 +379,16 @@ bool make_x_map(CUtensorMap* map, const void* base, const LstmFusedGeom& gm) {
 
 }  // namespace
 
-size_t lstm_tc5_pack_bytes() { return (size_t)2 * 4 * 128 * 128 * 2 + 2 * HH_LO_BYTES + (size_t)2 * 4 * 128 * 64 * 2 + 2 * IH_LO_BYTES; }
+size_t lstm_tc5_pack_bytes() { return (size_t)2 * 4 * 128 * 128 * 2 + 2 * HH_SM_BYTES + (size_t)2 * 4 * 128 * 64 * 2 + 2 * IH_SM_BYTES; }
 
 cudaError_t launch_pack_lstm_tc5(const float* const w_ih[2], const float* const w_hh[2], void* pack, cudaStream_t st) {
     Tc5PackArgs a;
     uint8_t* b = static_cast<uint8_t*>(pack);
     for (int d = 0; d < 2; ++d) { a.w_ih[d] = w_ih[d]; a.w_hh[d] = w_hh[d]; }
-    a.hh_hi = reinterpret_cast<uint16_t*>(b);
-    a.hh_lo = b + (size_t)2 * 4 * 128 * 128 * 2;
-    a.ih_hi = reinterpret_cast<uint16_t*>(a.hh_lo + 2 * HH_LO_BYTES);
-    a.ih_lo = reinterpret_cast<uint8_t*>(a.ih_hi) + (size_t)2 * 4 * 128 * 64 * 2;
+    a.hh_tm = reinterpret_cast<uint16_t*>(b);
+    a.hh_sm = b + (size_t)2 * 4 * 128 * 128 * 2;
+    a.ih_tm = reinterpret_cast<uint16_t*>(a.hh_sm + 2 * HH_SM_BYTES);
+    a.ih_sm = reinterpret_cast<uint8_t*>(a.ih_tm) + (size_t)2 * 4 * 128 * 64 * 2;
     const int total = 2 * 4 * 128 * 128 + 2 * 4 * 128 * 64;
     pack_tc5_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a);
     return cudaGetLastError();
@@ -410,10 +405,10 @@ cudaError_t launch_lstm_fused_fwd(const void* pack, const float* bias, const __n
     const uint8_t* b = static_cast<const uint8_t*>(pack);
     FusedArgs a;
     memset(&a, 0, sizeof(a));
-    a.hh_hi = reinterpret_cast<const uint32_t*>(b);
-    a.hh_lo = reinterpret_cast<const uint4*>(b + (size_t)2 * 4 * 128 * 128 * 2);
-    a.ih_hi = reinterpret_cast<const uint32_t*>(b + (size_t)2 * 4 * 128 * 128 * 2 + 2 * HH_LO_BYTES);
-    a.ih_lo = reinterpret_cast<const uint4*>(b + (size_t)2 * 4 * 128 * 128 * 2 + 2 * HH_LO_BYTES + (size_t)2 * 4 * 128 * 64 * 2);
+    a.hh_tm = reinterpret_cast<const uint32_t*>(b);
+    a.hh_sm = reinterpret_cast<const uint4*>(b + (size_t)2 * 4 * 128 * 128 * 2);
+    a.ih_tm = reinterpret_cast<const uint32_t*>(b + (size_t)2 * 4 * 128 * 128 * 2 + 2 * HH_SM_BYTES);
+    a.ih_sm = reinterpret_cast<const uint4*>(b + (size_t)2 * 4 * 128 * 128 * 2 + 2 * HH_SM_BYTES + (size_t)2 * 4 * 128 * 64 * 2);
     a.bias = bias; a.G = G; a.Cst = Cst;
     a.h_hi = pl.h_hi; a.h_lo = pl.h_lo; a.hp_hi = pl.hp_hi; a.hp_lo = pl.hp_lo;
     a.inter = gm.inter; a.len = gm.len;
@@ -423,13 +418,13 @@ cudaError_t launch_lstm_fused_fwd(const void* pack, const float* bias, const __n
     const int tiles = gm.inter ? gm.B * ceil_div(gm.K, GN) : ceil_div(gm.nseq, GN);
     dim3 grid(ceil_div(tiles, 2), 2);
     const int pl_n = split ? 2 : 1;
-    const int smem = (split ? HH_LO_BYTES + IH_LO_BYTES : 0) + 2 * pl_n * 2 * TILE + 4 * pl_n * TILE + 512 + 1024;
+    const int smem = HH_SM_BYTES + IH_SM_BYTES + pl_n * 2 * (2 * TILE) + 2 * pl_n * (2 * TILE) + 512 + 1024;
     cudaError_t e;
 #define DP_FUSED(SP, SV)                                                                                     \
     do {                                                                                                     \
         e = cudaFuncSetAttribute(lstm_fused_fwd_kernel<SP, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
         if (e != cudaSuccess) return e;                                                                      \
-        lstm_fused_fwd_kernel<SP, SV><<<grid, 416, smem, st>>>(mh, ml, a);                                   \
+        lstm_fused_fwd_kernel<SP, SV><<<grid, 352, smem, st>>>(mh, ml, a);                                   \
     } while (0)
     if (split) { if (save) DP_FUSED(true, true); else DP_FUSED(true, false); }
     else       { if (save) DP_FUSED(false, true); else DP_FUSED(false, false); }

@@ -88,6 +88,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 
+// Warp-collective variants: EVERY lane of a converged warp calls them with warp-uniform operands and one elected lane issues
+// the instruction.  Keeping the control flow uniform (no `if (lane == 0)` around the issue loop) lets the compiler hold the
+// descriptors in uniform registers; under a divergent branch it wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall loop,
+// which costs ~100 cycles per instruction and dominates when the MMAs are small.
+__device__ __forceinline__ void umma_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p, q;\n elect.sync _|q, 0xffffffff;\n setp.ne.b32 p, %4, 0;\n"
+        " @q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p, q;\n elect.sync _|q, 0xffffffff;\n setp.ne.b32 p, %4, 0;\n"
+        " @q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+    asm volatile(
+        "{\n .reg .pred q;\n elect.sync _|q, 0xffffffff;\n"
+        " @q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar))
+        : "memory");
+}
 // A operand read from tensor memory (lane = M row, one 32-bit column = two consecutive bf16 K elements)
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
