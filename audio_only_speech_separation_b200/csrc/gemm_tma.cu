@@ -38,19 +38,22 @@ template <int BN, bool SPLIT>
 struct NtCfg {
     static constexpr int W_TILE = BN * BK * 2;
     static constexpr int STAGE = (A_TILE + W_TILE) * (SPLIT ? 2 : 1);
-    static constexpr int STAGES = (200 * 1024) / STAGE > 6 ? 6 : (200 * 1024) / STAGE;
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int STAGES = (196 * 1024) / STAGE > 6 ? 6 : (196 * 1024) / STAGE;
+    static constexpr int OUT_STAGE = 2 * 128 * 128;  // two [128 rows x 32 fp32] swizzled staging tiles for the TMA stores (one per warp set)
+    static constexpr int SMEM = STAGES * STAGE + OUT_STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 };
 
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(320, 1)
 gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const TmaGemmArgs p) {
+                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                   const __grid_constant__ CUtensorMap tmC, const TmaGemmArgs p, const int tma_store) {
     using Cfg = NtCfg<BN, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
+    uint8_t* out_stage = smem + Cfg::STAGES * Cfg::STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(out_stage + Cfg::OUT_STAGE);
     uint64_t* empty = full + Cfg::STAGES;
     uint64_t* tfull = empty + Cfg::STAGES;
     uint64_t* tempty = tfull + 2;
@@ -186,7 +189,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                             v[j + 2] = o.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = o.w > 0.f ? v[j + 3] : 0.f;
                         }
                     }
-                    if (dst) {
+                    if (dst && !tma_store) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
@@ -208,6 +211,26 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                         for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
                     }
                 }
+                if (tma_store) {
+                    // fp32 output through shared memory and a TMA store: full 128-byte rows leave the SM as bulk writes instead
+                    // of 16-byte pieces of 32 different lines per store instruction.  One staging tile per warp set (4 warps).
+                    uint8_t* stg = out_stage + half * (128 * 128);
+                    const int bar_id = 1 + half;
+                    if ((warp & 3) == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous store drained
+                    asm volatile("bar.sync %0, 128;\n" ::"r"(bar_id) : "memory");
+                    const int rl = q * 32 + lane;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stg + rl * 128 + ((j ^ (rl & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    proxy_fence_async();
+                    asm volatile("bar.sync %0, 128;\n" ::"r"(bar_id) : "memory");
+                    if ((warp & 3) == 2 && lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(&tmC),
+                                     "r"(smem_u32(stg)), "r"(n0 + c0), "r"(m0)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -226,6 +249,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (tma_store && (warp & 3) == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -257,21 +281,37 @@ bool make_map(CUtensorMap* map, const void* base, long long rows, long long inne
     return r == CUDA_SUCCESS;
 }
 
+// fp32 output [M, N] (row stride ldc): box = 128 rows x 32 columns (128 bytes), 128-byte swizzle
+bool make_map_c(CUtensorMap* map, const void* base, long long M, long long N, long long ldc) {
+    auto fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t gstr[1] = {(cuuint64_t)ldc * 4};
+    cuuint32_t box[2] = {32u, 128u};
+    cuuint32_t estr[2] = {1u, 1u};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN, bool SPLIT>
 cudaError_t launch_nt(const TmaGemmArgs& a, cudaStream_t st) {
     using Cfg = NtCfg<BN, SPLIT>;
-    CUtensorMap mAh, mAl, mWh, mWl;
+    CUtensorMap mAh, mAl, mWh, mWl, mC;
     if (!make_map(&mAh, a.A_hi, a.M, a.K, a.lda, BM) || !make_map(&mWh, a.W_hi, a.N, a.K, a.ldw, BN)) return cudaErrorInvalidValue;
     if (SPLIT) {
         if (!make_map(&mAl, a.A_lo, a.M, a.K, a.lda, BM) || !make_map(&mWl, a.W_lo, a.N, a.K, a.ldw, BN)) return cudaErrorInvalidValue;
     } else {
         mAl = mAh; mWl = mWh;
     }
+    // plain fp32 outputs leave through TMA stores; read-modify-write epilogues keep the direct path
+    int tma_store = a.C != nullptr && !a.accumulate && !a.mul_c && !a.mask && (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0;
+    mC = mAh;
+    if (tma_store && !make_map_c(&mC, a.C, a.M, a.N, a.ldc)) tma_store = 0;
     cudaError_t e = cudaFuncSetAttribute(gemm_tma_nt_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return e;
     const int tiles = ceil_div(a.M, BM) * (a.N / BN);
     const int grid = tiles < 148 ? tiles : 148;
-    gemm_tma_nt_kernel<BN, SPLIT><<<grid, 320, Cfg::SMEM, st>>>(mAh, mAl, mWh, mWl, a);
+    gemm_tma_nt_kernel<BN, SPLIT><<<grid, 320, Cfg::SMEM, st>>>(mAh, mAl, mWh, mWl, mC, a, tma_store);
     return cudaGetLastError();
 }
 
