@@ -310,6 +310,15 @@ int dp_attention_backward_f32(const float* qkv, const float* o, const float* lse
     CK(launch_attn_bwd(qkv, o, lse, d_o, d_qkv, E, heads, m, S(stream)));
     return 0;
 }
+int dp_attention_forward_planes_f32(const void* qkv_hi, const void* qkv_lo, float* o, void* o_hi, void* o_lo, float* lse, int E, int heads,
+                                    int inter, int B, int Sc, int K, int precision, void* stream) {
+    LstmFusedGeom gm;
+    gm.inter = inter; gm.len = inter ? Sc : K; gm.nseq = inter ? B * K : B * Sc; gm.K = K; gm.S = Sc; gm.B = B;
+    if (!attn_tc5_supported(E, heads, gm)) return fail("dp_attention_forward_planes_f32: need head width 16 or 32 and sequence length <= 256");
+    CK(launch_attn_fwd_tc5((const __nv_bfloat16*)qkv_hi, (const __nv_bfloat16*)qkv_lo, o, (__nv_bfloat16*)o_hi, (__nv_bfloat16*)o_lo, lse, E, heads,
+                           gm, is_split(precision), S(stream)));
+    return 0;
+}
 int dp_add_layernorm_f32(const float* a, const float* b, float* z_out, float* out, const float* res, const float* gamma, const float* beta,
                          int64_t rows, int E, float eps, void* stream) {
     if (E != 64 && E != 128 && E != 256) return fail("dp_add_layernorm_f32: E must be 64, 128 or 256 (got %d)", E);
@@ -394,6 +403,7 @@ struct Layout {
     std::vector<size_t> QKV, Oa, LSE, Z1, S1, Z2;  // DPTNet only
     std::vector<size_t> Xhl, Hhl, Hphl;            // bf16 hi/lo operand planes (TMA backend): [hi | lo]
     size_t dGhl, dYhl;
+    size_t tXhl, tQKVhl, tOhl, tS1hl, tHrhl;       // DPTNet forward operand planes (shared by all paths, nothing is saved)
     // backward temporaries
     size_t dXs, dY, dH, dpad, dMx, dMk, dE, dZ, dF2, dtmp, dQKV, dOa;
     size_t total;
@@ -464,7 +474,13 @@ void make_layout(const dp_tasnet* h, const Geo& g, bool train, Layout& l) {
     const bool xf = h->cfg.module == DP_MODULE_DPTNET;
     l.QKV.assign(np, 0); l.Oa.assign(np, 0); l.LSE.assign(np, 0); l.Z1.assign(np, 0); l.S1.assign(np, 0); l.Z2.assign(np, 0);
     l.dQKV = l.dOa = 0;
+    l.tXhl = l.tQKVhl = l.tOhl = l.tS1hl = l.tHrhl = 0;
     if (xf) {
+        l.tXhl = c.take(g.PT * 64 * 2 * 2);
+        l.tQKVhl = c.take(g.PT * 192 * 2 * 2);
+        l.tOhl = c.take(g.PT * 64 * 2 * 2);
+        l.tS1hl = c.take(g.PT * 64 * 2 * 2);
+        l.tHrhl = c.take(g.PT * 256 * 2 * 2);
         for (int p = 0; p < nbuf; ++p) {
             l.QKV[p] = c.take(g.PT * 192 * f);
             l.Oa[p] = c.take(g.PT * 64 * f);
@@ -623,6 +639,11 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
         __nv_bfloat16* x0 = at<__nv_bfloat16>(ws, l.Xhl[0]);
         CK(launch_split_rows(at<float>(ws, l.X[0]), 64, x0, sp ? x0 + plX : nullptr, g.PT, 64, 0, st)); ++nl;
     }
+    const bool xtma = g_backend == 2 && h->cfg.module == DP_MODULE_DPTNET;
+    if (xtma) {
+        __nv_bfloat16* x0 = at<__nv_bfloat16>(ws, l.tXhl);
+        CK(launch_split_rows(at<float>(ws, l.X[0]), 64, x0, sp ? x0 + plX : nullptr, g.PT, 64, 0, st)); ++nl;
+    }
 
     for (int pp = 0; pp < h->npath; ++pp) {                                                     // dprnn.py:62-82
         const int64_t* po = o + DP_TASNET_HEAD_PARAMS + h->ppath * pp;
@@ -636,6 +657,56 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
             float* QKV = at<float>(ws, l.QKV[pp]);
             float* Oa = at<float>(ws, l.Oa[pp]);
             float* S1 = at<float>(ws, l.S1[pp]);
+            if (xtma) {
+                // TMA-fed tcgen05 GEMMs on operand planes + tcgen05 attention; fp32 copies only where the backward reads them
+                __nv_bfloat16* Xh = at<__nv_bfloat16>(ws, l.tXhl);
+                __nv_bfloat16* Qh = at<__nv_bfloat16>(ws, l.tQKVhl);
+                __nv_bfloat16* Oh = at<__nv_bfloat16>(ws, l.tOhl);
+                __nv_bfloat16* S1h = at<__nv_bfloat16>(ws, l.tS1hl);
+                __nv_bfloat16* Hrh = at<__nv_bfloat16>(ws, l.tHrhl);
+                const long long plQ = g.PT * 192;
+                LstmFusedGeom gm;
+                gm.inter = pp & 1; gm.len = m.len; gm.nseq = m.nseq; gm.K = g.K; gm.S = g.Sc; gm.B = B;
+                const bool tc_attn = attn_tc5_supported(64, 4, gm);
+                {   // in_proj: [q|k|v] = x W_in^T + b_in
+                    TmaGemmArgs a = tma_args(Xh, plX, 64, whi + po[12], wlo + po[12], 64, (train || !tc_attn) ? QKV : nullptr, 192, (int)g.PT, 192, 64);
+                    if (tc_attn) { a.C_hi = Qh; a.C_lo = sp ? Qh + plQ : nullptr; a.ldch = 192; }
+                    a.bias = params + po[13];
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                if (tc_attn) {
+                    CK(launch_attn_fwd_tc5(Qh, sp ? Qh + plQ : nullptr, train ? Oa : nullptr, Oh, sp ? Oh + plX : nullptr,
+                                           train ? at<float>(ws, l.LSE[pp]) : nullptr, 64, 4, gm, sp, st)); ++nl;
+                } else {
+                    CK(launch_attn_fwd(QKV, train ? Oa : nullptr, train ? at<float>(ws, l.LSE[pp]) : nullptr, 64, 4, m, st, Oh, sp ? Oh + plX : nullptr)); ++nl;
+                }
+                {   // out_proj
+                    TmaGemmArgs a = tma_args(Oh, plX, 64, whi + po[14], wlo + po[14], 64, Y, 64, (int)g.PT, 64, 64);
+                    a.bias = params + po[15];
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                // src = norm1(src + attn)
+                CK(launch_add_ln(Y, X, train ? at<float>(ws, l.Z1[pp]) : nullptr, S1, nullptr, params + po[16], params + po[17], g.PT, 64, 1e-5f,
+                                 nullptr, nullptr, nullptr, st, S1h, sp ? S1h + plX : nullptr)); ++nl;
+                {   // BiLSTM "feed-forward": in-projection, recurrence, ReLU, Linear(256 -> 64)
+                    TmaGemmArgs a = tma_args(S1h, plX, 64, v.wih_hi, v.wih_lo, 64, G, 1024, (int)g.PT, 1024, 64);
+                    a.bias = v.bias;
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                CK(launch_lstm_fwd(v.rec, G, H, train ? at<float>(ws, l.Cst[pp]) : nullptr, m, sp, train != 0, st)); ++nl;
+                CK(launch_split_rows(H, 256, Hrh, sp ? Hrh + plH : nullptr, g.PT, 256, 1, st)); ++nl;   // relu(H) as operand planes
+                {
+                    TmaGemmArgs a = tma_args(Hrh, plH, 256, whi + po[8], wlo + po[8], 256, Y, 64, (int)g.PT, 64, 256);
+                    a.bias = params + po[9];
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                // out = x + norm2(src + ff)  (+ concat_block after the inter-chunk path when unfold); planes of the result feed the next in_proj
+                const bool cat = h->cfg.unfold && (pp & 1);
+                CK(launch_add_ln(Y, S1, train ? at<float>(ws, l.Z2[pp]) : nullptr, at<float>(ws, l.X[pp + 1]), X, params + po[10], params + po[11],
+                                 g.PT, 64, 1e-5f, cat ? params + o[9] : nullptr, cat ? params + o[10] : nullptr, cat ? params + o[11] : nullptr,
+                                 st, Xh, sp ? Xh + plX : nullptr)); ++nl;
+                continue;
+            }
             {   // in_proj: [q|k|v] = x W_in^T + b_in
                 GemmNtArgs a = nt_args(X, 64, whi + po[12], wlo + po[12], 64, 0, QKV, 192, (int)g.PT, 192, 64);
                 a.bias = params + po[13];

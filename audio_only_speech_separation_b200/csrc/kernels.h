@@ -118,6 +118,14 @@ cudaError_t launch_gemm_tn_tc5(const GemmTnArgs& a, bool split, int transpose_ou
 // out[n] += scale * sum_p A[p*lda + n]  (and the same into out2 when non-null)
 cudaError_t launch_colsum(const float* A, int lda, int P, int N, float scale, float* out, float* out2, cudaStream_t st);
 
+// geometry of the sequences of one dual-path pass over the stream [B,S,K,C] (shared by the TMA-fed sequence kernels)
+struct LstmFusedGeom {
+    int inter;  // 0: sequences (b,s) of the stream [B,S,K,64] walk k ; 1: sequences (b,k) walk s
+    int len;    // time steps (K intra, S inter)
+    int nseq;   // number of sequences (B*S intra, B*K inter)
+    int K, S, B;
+};
+
 // ---------------- LSTM (lstm.cu) ----------------
 struct SeqMap {  // position of (sequence q, time t):  (q / qdiv) * s_hi + (q % qdiv) * s_lo + t * s_t
     int nseq, len;
@@ -148,12 +156,6 @@ cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, c
 // dH: [P,256] incoming gradient of H.  G holds activated gates on entry and d(pre-activations) on exit.
 // dbias (optional, [1024] packed order) accumulates sum_p dG[p,:] (the bias gradient) inside the same kernel.
 // ---- fused input projection + recurrence on tcgen05 (lstm_tc5.cu) ----
-struct LstmFusedGeom {
-    int inter;  // 0: sequences (b,s) of the stream [B,S,K,64] walk k ; 1: sequences (b,k) walk s
-    int len;    // time steps (K intra, S inter)
-    int nseq;   // number of sequences (B*S intra, B*K inter)
-    int K, S, B;
-};
 size_t lstm_tc5_pack_bytes();
 // weight images for the fused kernel: bf16 hi rows (tensor-memory A operand) and swizzled lo images (shared-memory A operand)
 cudaError_t launch_pack_lstm_tc5(const float* const w_ih[2], const float* const w_hh[2], void* pack, cudaStream_t st);
@@ -240,6 +242,11 @@ cudaError_t launch_attn_fwd(const float* QKV, float* O, float* LSE, int E, int h
                             __nv_bfloat16* O_hi = nullptr, __nv_bfloat16* O_lo = nullptr);
 cudaError_t launch_attn_bwd(const float* QKV, const float* O, const float* LSE, const float* dO, float* dQKV, int E, int heads,
                             const SeqMap& m, cudaStream_t st);
+// The same attention on tcgen05 (attention_tc5.cu): QKV given as bf16 hi/lo planes [P,3E] (what the QKV GEMM writes), TMA-fed;
+// S and P live in tensor memory.  Sequences up to 256 long; geometry as for the fused LSTM kernel (gm.nseq sequences).
+bool attn_tc5_supported(int E, int heads, const LstmFusedGeom& gm);
+cudaError_t launch_attn_fwd_tc5(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, float* O, __nv_bfloat16* O_hi, __nv_bfloat16* O_lo,
+                                float* LSE, int E, int heads, const LstmFusedGeom& gm, bool split, cudaStream_t st);
 // z = a (+ b) [-> zout]; out = (res ? res : 0) + LayerNorm_E(z) * gamma + beta; then optional unfold affine + PReLU.
 cudaError_t launch_add_ln(const float* a, const float* b, float* zout, float* out, const float* res, const float* gamma, const float* beta,
                           long long rows, int E, float eps, const float* cw, const float* cb, const float* slope, cudaStream_t st,

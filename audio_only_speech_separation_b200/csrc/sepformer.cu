@@ -209,6 +209,9 @@ int dp_sepformer_forward(dp_sepformer* h, const float* params, const void* pack,
                 CK(cudaMemcpyAsync(R, X, g.PT * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
             }
             const bool tma = gemm_backend() == 2 && dffn % 64 == 0;
+            LstmFusedGeom gm;
+            gm.inter = path; gm.len = m.len; gm.nseq = m.nseq; gm.K = g.K; gm.S = g.Sc; gm.B = B;
+            const bool tc_attn = tma && attn_tc5_supported(N, heads, gm);
             __nv_bfloat16* Uh = at<__nv_bfloat16>(ws, l.Uhl);
             __nv_bfloat16* Ul = sp ? Uh + g.PT * N : nullptr;
             __nv_bfloat16* Oh = at<__nv_bfloat16>(ws, l.Ohl);
@@ -220,12 +223,21 @@ int dp_sepformer_forward(dp_sepformer* h, const float* params, const void* pack,
                 // TMA-fed tcgen05 GEMMs: every operand is a pair of bf16 planes written by its producer (gemm_tma.cu)
                 const int64_t* lo = po + 1 + PER_LAYER * ly;
                 if (pre) { CK(launch_add_ln(R, nullptr, nullptr, nullptr, nullptr, params + lo[8], params + lo[9], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st, Uh, Ul)); ++nl; }
-                {
+                if (tc_attn) {
+                    // QKV leaves the GEMM as operand planes only; attention runs on tcgen05 with S and P in tensor memory
+                    __nv_bfloat16* Qh = reinterpret_cast<__nv_bfloat16*>(QKV);
+                    __nv_bfloat16* Ql = sp ? Qh + g.PT * 3 * N : nullptr;
+                    TmaGemmArgs a = tma_nt_args(Uh, Ul, N, whi + lo[0], wlo + lo[0], N, nullptr, 0, PTi, 3 * N, N);
+                    a.C_hi = Qh; a.C_lo = Ql; a.ldch = 3 * N;
+                    a.bias = params + lo[1];
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                    CK(launch_attn_fwd_tc5(Qh, Ql, nullptr, Oh, Ol, nullptr, N, heads, gm, sp, st)); ++nl;
+                } else {
                     TmaGemmArgs a = tma_nt_args(Uh, Ul, N, whi + lo[0], wlo + lo[0], N, QKV, 3 * N, PTi, 3 * N, N);
                     a.bias = params + lo[1];
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                    CK(launch_attn_fwd(QKV, nullptr, nullptr, N, heads, m, st, Oh, Ol)); ++nl;
                 }
-                CK(launch_attn_fwd(QKV, nullptr, nullptr, N, heads, m, st, Oh, Ol)); ++nl;
                 {
                     TmaGemmArgs a = tma_nt_args(Oh, Ol, N, whi + lo[2], wlo + lo[2], N, pre ? R : U, N, PTi, N, N);
                     a.bias = params + lo[3];

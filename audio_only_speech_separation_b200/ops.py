@@ -29,6 +29,7 @@ __all__ = [
     "split_rows",
     "linear_planes",
     "linear_wgrad_planes",
+    "attention_planes",
 ]
 
 
@@ -304,3 +305,19 @@ def linear_wgrad_planes(a, b0, out0, b1=None, out1=None, *, tr0=False, tr1=False
                                            out1.stride(0) if out1 is not None else 0, int(tr1), P, float(scale), _prec(precision),
                                            stream_ptr()), "dp_linear_wgrad_planes_f32")
     return out0, out1
+
+
+def attention_planes(qkv: torch.Tensor, heads: int, layout: str, *, precision="fp32", save=False):
+    """Self-attention core on the tcgen05 kernel: ``qkv[B,S,K,3E]`` is split into bf16 hi/lo planes (what the QKV GEMM writes in
+    the engines) and streamed by TMA.  Returns ``(o fp32 [B,S,K,E], (o_hi, o_lo), lse or None)``."""
+    require_cuda(qkv, "qkv")
+    B, S, K, E3 = qkv.shape
+    E = E3 // 3
+    hi, lo = split_rows(qkv.reshape(-1, E3).contiguous())
+    o = torch.empty(B, S, K, E, device=qkv.device, dtype=torch.float32)
+    oh = torch.empty(B * S * K, E, device=qkv.device, dtype=torch.bfloat16)
+    ol = torch.empty(B * S * K, E, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(B * S * K, heads, device=qkv.device, dtype=torch.float32) if save else None
+    check(lib().dp_attention_forward_planes_f32(ptr(hi), ptr(lo), ptr(o), ptr(oh), ptr(ol), ptr(lse), E, heads, int(layout == "inter"), B, S, K,
+                                                _prec(precision), stream_ptr()), "dp_attention_forward_planes_f32")
+    return o, (oh, ol), lse

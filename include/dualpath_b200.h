@@ -112,6 +112,11 @@ int dp_attention_forward_f32(const float* qkv, float* o, float* lse, int E, int 
                              int64_t s_lo, int64_t s_t, void* stream);
 int dp_attention_backward_f32(const float* qkv, const float* o, const float* lse, const float* d_o, float* d_qkv, int E, int heads,
                               int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, void* stream);
+/* The same attention on the 5th-generation tensor cores: qkv given as bf16 hi/lo planes [P,3E] on a dual-path stream [B,S,K,.]
+ * (inter = 0: sequences (b,s) along k; 1: sequences (b,k) along s), TMA-fed, scores and probabilities in tensor memory.
+ * Outputs: o fp32 and/or o_hi/o_lo planes, lse (all optional).  Sequence length <= 256. */
+int dp_attention_forward_planes_f32(const void* qkv_hi, const void* qkv_lo, float* o, void* o_hi, void* o_lo, float* lse, int E, int heads,
+                                    int inter, int B, int S, int K, int precision, void* stream);
 /* z = a (+ b) (stored to z_out when non-null); out = (res ? res : 0) + LayerNorm_E(z) * gamma + beta.  E in {64,128,256}. */
 int dp_add_layernorm_f32(const float* a, const float* b, float* z_out, float* out, const float* res, const float* gamma,
                          const float* beta, int64_t rows, int E, float eps, void* stream);

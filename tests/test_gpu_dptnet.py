@@ -190,3 +190,34 @@ def test_add_layernorm_forward_backward_vs_torch(E, rows):
     dz, dg, db = ops.layernorm_backward(dy.cuda(), z, gamma.cuda(), 1e-5)
     assert rel_l2(dz, zr.grad) < 1e-5
     assert rel_l2(dg, gr.grad) < 1e-5 and rel_l2(db, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("E,heads,B,S,K", [(64, 4, 2, 6, 100), (64, 4, 1, 82, 10), (256, 8, 1, 5, 250), (256, 8, 1, 130, 3), (256, 8, 1, 258, 2),
+                                           (256, 8, 2, 4, 128), (64, 4, 1, 3, 17)])
+@pytest.mark.parametrize("layout", ["intra", "inter"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_tcgen05_attention_vs_torch(E, heads, B, S, K, layout, precision):
+    """attention_tc5.cu (TMA-fed, S and P in tensor memory) against fp64 torch and against the CUDA-core kernel."""
+    from audio_only_speech_separation_b200 import ops
+
+    L = K if layout == "intra" else S
+    if L > 256:
+        pytest.skip("tcgen05 attention covers sequences up to 256")
+    g = torch.Generator().manual_seed(E + S + K)
+    qkv = torch.randn(B, S, K, 3 * E, generator=g)
+    x = qkv.double()
+    if layout == "intra":
+        ref = _torch_mha_core(x.reshape(B * S, K, 3 * E), heads).reshape(B, S, K, E)
+    else:
+        ref = _torch_mha_core(x.permute(0, 2, 1, 3).reshape(B * K, S, 3 * E), heads).reshape(B, K, S, E).permute(0, 2, 1, 3)
+    o, (oh, ol), lse = ops.attention_planes(qkv.cuda(), heads, layout, precision=precision, save=True)
+    o2, lse2 = ops.attention(qkv.cuda(), heads, layout, save=True)
+    err = rel_l2(o, ref)
+    record("attention_tc5", E=E, heads=heads, S=S, K=K, layout=layout, precision=precision, rel_l2=err)
+    if precision == "fp32":
+        assert err < 2e-5
+        assert rel_l2(oh.float() + ol.float(), o.reshape(-1, E)) < 1e-5
+        assert rel_l2(lse, lse2) < 1e-5
+    else:
+        assert err < 2e-2
+        assert rel_l2(oh.float(), o.reshape(-1, E)) < 1e-2
