@@ -85,6 +85,9 @@ PROTOTYPES = {
     "dp_sepformer_pack": (_i, [_p, _p, _p, _p]),
     "dp_sepformer_forward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "dp_sepformer_last_launches": (_i, [_p]),
+    "dp_sepformer_train_workspace_bytes": (_i64, [_p, _i, _i]),
+    "dp_sepformer_forward_train": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "dp_sepformer_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
 }
 
 _lib = None

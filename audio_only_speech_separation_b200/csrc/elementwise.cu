@@ -322,7 +322,161 @@ __global__ void dec_ola_general_kernel(const float* __restrict__ D, float* __res
     }
 }
 
+// ---- SepFormer training helpers -----------------------------------------------------------------------------
+// GroupNorm / gLN backward reductions for any C % 4 == 0 with 256 % (C/4) == 0: grid (pieces, groups)
+__global__ void __launch_bounds__(256) gn_bwd_reduce_any_kernel(const float4* __restrict__ d, const float4* __restrict__ y, const float* __restrict__ mr,
+                                                                const float4* __restrict__ gamma, int rpg, int C4, double* __restrict__ red,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float sh[256][8];
+    __shared__ double shd[8][2];
+    const int g = blockIdx.y;
+    const int r0 = blockIdx.x * GNB_ROWS, r1 = min(rpg, r0 + GNB_ROWS);
+    const int RL = 256 / C4;
+    const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4;
+    const float mean = mr[2 * g], rstd = mr[2 * g + 1];
+    const float4 ga = gamma[c4];
+    float dg[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f};
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = r0 + rl; r < r1; r += RL) {
+        size_t i = ((size_t)g * rpg + r) * C4 + c4;
+        float4 dv = ldg_stream(d + i), yv = ldg_stream(y + i);
+        float xh[4] = {(yv.x - mean) * rstd, (yv.y - mean) * rstd, (yv.z - mean) * rstd, (yv.w - mean) * rstd};
+        float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+        float gg[4] = {ga.x, ga.y, ga.z, ga.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dg[k] = fmaf(dd[k], xh[k], dg[k]);
+            db[k] += dd[k];
+            float gd = gg[k] * dd[k];
+            s1 += gd;
+            s2 = fmaf(gd, xh[k], s2);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sh[threadIdx.x][k] = dg[k]; sh[threadIdx.x][4 + k] = db[k]; }
+    double a = warp_sum_d((double)s1), b = warp_sum_d((double)s2);
+    if ((threadIdx.x & 31) == 0) { shd[threadIdx.x >> 5][0] = a; shd[threadIdx.x >> 5][1] = b; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < C4 * 8; e += 256) {
+        const int q = e >> 3, k = e & 7;
+        float s = 0.f;
+        for (int r = 0; r < RL; ++r) s += sh[r * C4 + q][k];
+        if (k < 4) atomicAdd(dgamma + q * 4 + k, s); else atomicAdd(dbeta + q * 4 + (k - 4), s);
+    }
+    if (threadIdx.x == 0) {
+        double x = 0.0, z = 0.0;
+        for (int w = 0; w < 8; ++w) { x += shd[w][0]; z += shd[w][1]; }
+        atomicAdd(red + 2 * g, x);
+        atomicAdd(red + 2 * g + 1, z);
+    }
+}
+
+// dD[(r, l), j] = d_est[ro, l*st + j] (0 beyond T): backward of dec_ola_general (every output sample feeds <= 2 frames)
+__global__ void dec_ola_general_bwd_kernel(const float* __restrict__ d_est, float* __restrict__ dD, int B, int nspk, int L, int win, int T,
+                                           int spk_major) {
+    const int st = win / 2;
+    const long long total = (long long)B * nspk * L * win;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % win);
+        const long long rl = i / win;
+        const int l = (int)(rl % L), r = (int)(rl / L);
+        const int b = r / nspk, c = r % nspk;
+        const int ro = spk_major ? c * B + b : r;
+        const int tau = l * st + j;
+        dD[i] = tau < T ? d_est[(size_t)ro * T + tau] : 0.f;
+    }
+}
+
+// g = t1 * t2 (gated output, sepformer.py:747)
+__global__ void __launch_bounds__(256) mul_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 x = ldg_stream(a + i), y = ldg_stream(b + i);
+        out[i] = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
+    }
+}
+// backward of g = tanh(a) * sigmoid(b) given t1 = tanh(a), t2 = sigmoid(b): da = dg t2 (1 - t1^2), db = dg t1 t2 (1 - t2)
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const float4* __restrict__ dg, const float4* __restrict__ t1, const float4* __restrict__ t2,
+                                                       float4* __restrict__ da, float4* __restrict__ db, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 g = ldg_stream(dg + i), x = ldg_stream(t1 + i), y = ldg_stream(t2 + i);
+        da[i] = make_float4(g.x * y.x * (1.f - x.x * x.x), g.y * y.y * (1.f - x.y * x.y), g.z * y.z * (1.f - x.z * x.z), g.w * y.w * (1.f - x.w * x.w));
+        db[i] = make_float4(g.x * x.x * y.x * (1.f - y.x), g.y * x.y * y.y * (1.f - y.y), g.z * x.z * y.z * (1.f - y.z), g.w * x.w * y.w * (1.f - y.w));
+    }
+}
+// dx = du * (x > 0 ? 1 : a) (dx may alias du); dslope += sum du * x [x <= 0]   (nn.PReLU with one slope)
+__global__ void __launch_bounds__(256) prelu_bwd_kernel(const float4* __restrict__ du, const float4* __restrict__ x, float4* __restrict__ dx, long long n4,
+                                                        const float* __restrict__ slope, float* __restrict__ dslope) {
+    __shared__ float sh[8];
+    const float a = slope[0];
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 d = du[i], v = ldg_stream(x + i);
+        float4 o;
+        o.x = v.x > 0.f ? d.x : a * d.x; o.y = v.y > 0.f ? d.y : a * d.y; o.z = v.z > 0.f ? d.z : a * d.z; o.w = v.w > 0.f ? d.w : a * d.w;
+        acc += (v.x > 0.f ? 0.f : d.x * v.x) + (v.y > 0.f ? 0.f : d.y * v.y) + (v.z > 0.f ? 0.f : d.z * v.z) + (v.w > 0.f ? 0.f : d.w * v.w);
+        dx[i] = o;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += sh[w];
+        atomicAdd(dslope, s);
+    }
+}
+// out = (a + b) * (m > 0): gradient entering a ReLU whose output m was saved (b optional)
+__global__ void __launch_bounds__(256) relu_bwd_add_kernel(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ m,
+                                                           float4* __restrict__ out, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 x = a[i], k = ldg_stream(m + i);
+        if (b) { float4 y = b[i]; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+        out[i] = make_float4(k.x > 0.f ? x.x : 0.f, k.y > 0.f ? x.y : 0.f, k.z > 0.f ? x.z : 0.f, k.w > 0.f ? x.w : 0.f);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_gn_bwd_reduce_any(const float* d, const float* y, const float* mr, const float* gamma, long long rows, int rows_per_group,
+                                     int C, double* red, float* dgamma, float* dbeta, cudaStream_t st) {
+    if ((C & 3) || 256 % (C / 4)) return cudaErrorInvalidValue;
+    int groups = (int)(rows / rows_per_group);
+    if (groups <= 0) return cudaSuccess;
+    dim3 grid(ceil_div(rows_per_group, GNB_ROWS), groups);
+    gn_bwd_reduce_any_kernel<<<grid, 256, 0, st>>>((const float4*)d, (const float4*)y, mr, (const float4*)gamma, rows_per_group, C / 4, red, dgamma,
+                                                   dbeta);
+    return cudaGetLastError();
+}
+cudaError_t launch_dec_ola_general_bwd(const float* d_est, float* dD, int B, int nspk, int L, int win, int T, int spk_major, cudaStream_t st) {
+    long long total = (long long)B * nspk * L * win;
+    if (total <= 0) return cudaSuccess;
+    dec_ola_general_bwd_kernel<<<grid_for(total), 256, 0, st>>>(d_est, dD, B, nspk, L, win, T, spk_major);
+    return cudaGetLastError();
+}
+cudaError_t launch_mul(const float* a, const float* b, float* out, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (n & 3) return cudaErrorInvalidValue;
+    mul_kernel<<<grid_for(n / 4), 256, 0, st>>>((const float4*)a, (const float4*)b, (float4*)out, n / 4);
+    return cudaGetLastError();
+}
+cudaError_t launch_gate_bwd(const float* dg, const float* t1, const float* t2, float* da, float* db, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (n & 3) return cudaErrorInvalidValue;
+    gate_bwd_kernel<<<grid_for(n / 4), 256, 0, st>>>((const float4*)dg, (const float4*)t1, (const float4*)t2, (float4*)da, (float4*)db, n / 4);
+    return cudaGetLastError();
+}
+cudaError_t launch_prelu_bwd(const float* du, const float* x, float* dx, long long n, const float* slope, float* dslope, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (n & 3) return cudaErrorInvalidValue;
+    prelu_bwd_kernel<<<grid_for(n / 4), 256, 0, st>>>((const float4*)du, (const float4*)x, (float4*)dx, n / 4, slope, dslope);
+    return cudaGetLastError();
+}
+cudaError_t launch_relu_bwd_add(const float* a, const float* b, const float* m, float* out, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (n & 3) return cudaErrorInvalidValue;
+    relu_bwd_add_kernel<<<grid_for(n / 4), 256, 0, st>>>((const float4*)a, (const float4*)b, (const float4*)m, (float4*)out, n / 4);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_add_pe(const float* x, const float* pe, float* out, long long rows, int E, int K, int S, int inter, cudaStream_t st) {
     if (rows <= 0) return cudaSuccess;

@@ -157,9 +157,10 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                     }
                     float* dst = p.C ? p.C + (size_t)row * p.ldc + col : nullptr;
                     if (p.accumulate) {
+                        const float* rsrc = p.Cin ? p.Cin + (size_t)row * p.ldc + col : dst;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 o = *reinterpret_cast<const float4*>(dst + j);
+                            const float4 o = *reinterpret_cast<const float4*>(rsrc + j);
                             v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
                         }
                     }

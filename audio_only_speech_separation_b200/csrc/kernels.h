@@ -58,6 +58,7 @@ struct TmaGemmArgs {
     float bias_scale;
     int act;         // 0 none, 1 ReLU, 2 tanh, 3 sigmoid
     int accumulate;  // C += (needs C)
+    const float* Cin;  // with accumulate: read the residual from here instead of C (C = Cin + ...), row stride ldc
     int mul_c;       // C = act(..) * C_old
     double* stats;   // [groups][2] (sum, sumsq) of the stored values
     int rows_per_group;
@@ -256,6 +257,15 @@ cudaError_t launch_ln_bwd(const float* dy, const float* z, float* dz, float* acc
                           float* dgamma, float* dbeta, cudaStream_t st);
 // out[n] += scale * sum_p A[p*lda + n], any N % 4 == 0
 cudaError_t launch_colsum_any(const float* A, long long lda, int P, int N, float scale, float* out, cudaStream_t st);
+
+// SepFormer training helpers (elementwise.cu)
+cudaError_t launch_gn_bwd_reduce_any(const float* d, const float* y, const float* mr, const float* gamma, long long rows, int rows_per_group,
+                                     int C, double* red, float* dgamma, float* dbeta, cudaStream_t st);
+cudaError_t launch_dec_ola_general_bwd(const float* d_est, float* dD, int B, int nspk, int L, int win, int T, int spk_major, cudaStream_t st);
+cudaError_t launch_mul(const float* a, const float* b, float* out, long long n, cudaStream_t st);
+cudaError_t launch_gate_bwd(const float* dg, const float* t1, const float* t2, float* da, float* db, long long n, cudaStream_t st);
+cudaError_t launch_prelu_bwd(const float* du, const float* x, float* dx, long long n, const float* slope, float* dslope, cudaStream_t st);
+cudaError_t launch_relu_bwd_add(const float* a, const float* b, const float* m, float* out, long long n, cudaStream_t st);
 
 // ---------------- loss (loss.cu) ----------------
 struct PitLossWs {  // device scratch, all double unless noted

@@ -8,8 +8,11 @@ same recursive reset, so the default initialisation is reproduced bit for bit un
 ``forward`` methods is ever called.  All parameters and the positional-encoding tables live as views of ONE flat fp32
 buffer that the engine reads through an offset table (include/dualpath_b200.h).
 
-This round's engine covers inference (``model.eval()`` / ``torch.no_grad()``), fp32-parity and bf16 modes.  Training
-(dropout 0.1 inside every layer, SURVEY A.4 #15, plus the backward pass) raises ``NotImplementedError``.
+The engine covers inference (``model.eval()`` / ``torch.no_grad()``, TMA-fed tcgen05 GEMMs and attention, fp32-parity and bf16
+modes) and training for pre-norm layers: forward + backward are two engine calls behind one autograd node, gradients are
+checked against autograd through the reference algorithm.  The reference trains with dropout 0.1 in four places per layer
+(SURVEY A.4 #15); those sites are not implemented yet, so a training forward requires the explicit opt-in
+``model.dropout = 0.0`` (the default 0.1, like the reference, raises ``NotImplementedError``).
 Reference quirk kept on purpose: for batch > 1 the output rows are the reference's ``reshape`` of (spk, batch)-ordered
 decoder rows (sepformer.py:1004), identity only for batch 1 (the YAML's ``batch_size: 1``).
 """
@@ -127,6 +130,32 @@ def _reset_layer_recursively(layer):
             _reset_layer_recursively(child)
 
 
+class _SepformerFunction(torch.autograd.Function):
+    """Autograd node for the whole network: forward and backward are single engine calls."""
+
+    @staticmethod
+    def forward(ctx, model, mixture, *params):
+        est, ws = model._engine_forward_train(mixture)
+        ctx.model, ctx.ws, ctx.dims = model, ws, mixture.shape
+        return est
+
+    @staticmethod
+    def backward(ctx, d_est):
+        model = ctx.model
+        if ctx.ws is None:
+            raise RuntimeError("Sepformer backward: the saved workspace was already consumed")
+        gflat = torch.zeros_like(model._flat)
+        B, T = ctx.dims
+        check(lib().dp_sepformer_backward(model._handle, ptr(model._flat), ptr(model._pack), ptr(d_est.contiguous().float()), ptr(gflat),
+                                          ptr(ctx.ws), B, T, model._prec(), stream_ptr()), "dp_sepformer_backward")
+        ctx.ws = None
+        grads = []
+        for e, o in zip(model._views, model._view_off):
+            t = model._tensor_of(e)
+            grads.append(None if isinstance(e, tuple) else gflat[o : o + t.numel()].view(t.shape))
+        return (None, None, *[g for g in grads if g is not None])
+
+
 class Sepformer(BaseModel):
     def __init__(
         self,
@@ -178,6 +207,7 @@ class Sepformer(BaseModel):
             _reset_layer_recursively(module)
         # 'fp32' (bf16x3 tensor-core products, fp32 parity) or 'bf16'
         self.precision = os.environ.get("DUALPATH_PRECISION", "fp32")
+        self.dropout = 0.1  # TransformerBlock default (sepformer.py:507); see the module docstring
         self._handle = None
         self._flat = None
         self._views: List[torch.Tensor] = []
@@ -198,13 +228,18 @@ class Sepformer(BaseModel):
             x = x.squeeze(1)
         if x.ndim != 2:
             raise ValueError(f"expected [T], [B, T] or [B, 1, T], got {tuple(mix.shape)}")
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError(
-                "Sepformer training (dropout 0.1 in every layer + backward) is not built yet; use model.eval() / torch.no_grad()")
         _lib.require_cuda(x.contiguous(), "Sepformer input")
         xin = x.contiguous().float()
         self._sync_flat(xin.device)
-        est = self._engine_forward(xin)
+        params = [e for e in self._views if not isinstance(e, tuple)]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            if self.training and self.dropout != 0.0:
+                raise NotImplementedError(
+                    "Sepformer training: the reference's dropout (0.1 in every layer) is not implemented; set model.dropout = 0.0 to "
+                    "train without it, or use model.eval() / torch.no_grad() for inference")
+            est = _SepformerFunction.apply(self, xin, *params)
+        else:
+            est = self._engine_forward(xin)
         if est.dtype != mix.dtype and mix.dtype.is_floating_point:
             est = est.to(mix.dtype)
         return est.squeeze(0) if was_one_d else est
@@ -302,6 +337,19 @@ class Sepformer(BaseModel):
         if sig != self._pack_sig:
             check(lib().dp_sepformer_pack(self._handle, ptr(self._flat), ptr(self._pack), stream_ptr()), "dp_sepformer_pack")
             self._pack_sig = sig
+
+    def _engine_forward_train(self, mixture):
+        B, T = mixture.shape
+        self._ensure_pack()
+        nbytes = lib().dp_sepformer_train_workspace_bytes(self._handle, B, T)
+        if nbytes < 0:
+            check(1, "dp_sepformer_train_workspace_bytes")
+        ws = torch.empty(nbytes, device=mixture.device, dtype=torch.uint8)
+        est = torch.empty(B, self.num_spks, T, device=mixture.device, dtype=torch.float32)
+        check(lib().dp_sepformer_forward_train(self._handle, ptr(self._flat), ptr(self._pack), ptr(mixture), ptr(est), ptr(ws), B, T,
+                                               self._prec(), stream_ptr()), "dp_sepformer_forward_train")
+        self.last_launches = lib().dp_sepformer_last_launches(self._handle)
+        return est, ws
 
     def _engine_forward(self, mixture, est=None):
         B, T = mixture.shape

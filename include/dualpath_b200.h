@@ -214,6 +214,14 @@ int dp_sepformer_pack(dp_sepformer* h, const float* params, void* pack, void* st
 int dp_sepformer_forward(dp_sepformer* h, const float* params, const void* pack, const float* mixture, float* est, void* workspace,
                          int B, int T, int precision, void* stream);
 int dp_sepformer_last_launches(const dp_sepformer* h);
+/* Training (pre-norm layers; the reference's dropout sites are NOT applied: the caller opts in, see models/sepformer.py):
+ * a forward that keeps in its workspace what the backward needs, and the backward into a flat gradient buffer laid out like
+ * params (ACCUMULATED into).  Same pack as the inference engine. */
+int64_t dp_sepformer_train_workspace_bytes(const dp_sepformer* h, int B, int T);
+int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void* pack, const float* mixture, float* est, void* workspace,
+                               int B, int T, int precision, void* stream);
+int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack, const float* d_est, float* grads, void* workspace,
+                          int B, int T, int precision, void* stream);
 
 #ifdef __cplusplus
 }

@@ -78,3 +78,39 @@ for name, cfgname, cfg, B, T, kind in CASES:
 
 json.dump(manifest, open(os.path.join(HERE, "manifest.json"), "w"), indent=1, sort_keys=True)
 print("manifest updated")
+
+# ---------------------------------------------------------------- gradients (training semantics with dropout disabled)
+from look2hear.losses import PITLossWrapper, pairwise_neg_snr  # noqa: E402
+from oracle import dualpath_oracle as O  # noqa: E402
+
+torch.manual_seed(0)
+m = Sepformer(sample_rate=8000, **small).train()
+for mod in m.modules():  # the reference hard-codes dropout 0.1 (sepformer.py:507); parity is only defined without it
+    if isinstance(mod, torch.nn.Dropout):
+        mod.p = 0.0
+    if isinstance(mod, torch.nn.MultiheadAttention):
+        mod.dropout = 0.0
+sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+g = torch.Generator().manual_seed(99)
+x = torch.randn(1, 2500, generator=g) * 0.1
+tgt = torch.randn(1, 2, 2500, generator=g) * 0.1
+loss = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)(m(x), tgt)
+m.zero_grad()
+loss.backward()
+ref_grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+lo = O.pit_loss(SO.sepformer_forward(leaf, x, **small), tgt, "snr", False)
+lo.backward()
+worst = max(rel(leaf[k].grad, ref_grads[k]) for k in ref_grads)
+assert abs(lo.item() - loss.item()) < 1e-5 and worst < 1e-3, (lo.item(), loss.item(), worst)
+keep = ["encoder.conv1d.weight", "decoder.weight", "masknet.prelu.weight", "masknet.conv2d.bias", "masknet.norm.weight",
+        "masknet.dual_mdl.0.intra_mdl.mdl.layers.0.self_att.att.in_proj_weight", "masknet.dual_mdl.1.inter_mdl.mdl.layers.1.pos_ffn.ffn.3.weight",
+        "masknet.dual_mdl.0.inter_norm.gamma", "masknet.dual_mdl.1.intra_mdl.mdl.norm.bias", "masknet.output_gate.0.weight"]
+gnpz = {"x": x.numpy(), "tgt": tgt.numpy(), "loss": np.array(loss.item())}
+for k in keep:
+    gnpz["grad::" + k] = ref_grads[k].numpy()
+np.savez_compressed(os.path.join(HERE, "grads_sepformer_small.npz"), **gnpz)
+manifest["grad_norms_sepformer_small"] = {k: float(v.double().norm()) for k, v in ref_grads.items()}
+manifest["grad_oracle_worst_rel_sepformer"] = worst
+json.dump(manifest, open(os.path.join(HERE, "manifest.json"), "w"), indent=1, sort_keys=True)
+print("sepformer grads ok, worst oracle-vs-reference rel", worst)

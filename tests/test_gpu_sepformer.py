@@ -79,8 +79,80 @@ def test_forward_bf16_within_si_snr_budget(manifest):
     assert proxy > 30.0
 
 
-def test_training_mode_is_refused_loudly(manifest):
-    m, _, _ = _model(manifest, "sepformer_small_b2_t3000")
+
+
+def test_training_needs_dropout_opt_in_and_gradients_match_oracle(manifest):
+    """Forward + backward engine calls behind one autograd node (dropout sites off): loss and every parameter gradient
+    against autograd through the oracle; a few of them also against the real reference's gradients (golden)."""
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+
+    m, sd, cfg = _model(manifest, "sepformer_small_b2_t3000")
+    z = load_npz("grads_sepformer_small.npz")
+    x, tgt = torch.from_numpy(z["x"]), torch.from_numpy(z["tgt"])
     m.train()
     with pytest.raises(NotImplementedError):
-        m(torch.randn(1, 2000).cuda())
+        m(x.cuda())                       # the reference's dropout 0.1 is not implemented: explicit opt-in required
+    m.dropout = 0.0
+    leaf = {k: v.clone().requires_grad_(not k.endswith("pos_enc.pe")) for k, v in sd.items()}
+    ref_loss = O.pit_loss(SO.sepformer_forward(leaf, x, **cfg), tgt, "snr", False)
+    ref_loss.backward()
+    loss = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)(m(x.cuda()), tgt.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-4 * max(1.0, abs(ref_loss.item()))
+    worst, worst_key, num, den, errs = 0.0, None, 0.0, 0.0, []
+    named = dict(m.named_parameters())
+    for k, p in named.items():
+        assert p.grad is not None, k
+        gr = leaf[k].grad
+        e = rel_l2(p.grad, gr)
+        errs.append(e)
+        num += float((p.grad.cpu().double() - gr.double()).pow(2).sum())
+        den += float(gr.double().pow(2).sum())
+        if e > worst:
+            worst, worst_key = e, k
+    total = (num / den) ** 0.5
+    errs.sort()
+    median = errs[len(errs) // 2]
+    record("sepformer_grads", worst_rel_l2=worst, worst_key=worst_key, total_rel_l2=total, median_rel_l2=median, loss=loss.item())
+    # ReLU-flip conditioning (DESIGN.md section 4): on this input 7 of the 716 800 FFN pre-activations of the reference lie within
+    # 1e-5 of zero (4 of them in block 0 / intra / layer 1); our forward agrees with the reference to ~1e-5, so exactly those
+    # units can take the other side of the ReLU and move the gradients of their layer (and of everything upstream) by ~1e-2,
+    # while all other layers agree to ~3e-5.  Hence a strict bound on the typical key and loose bounds on the total / worst.
+    assert median < 1e-4
+    assert total < 5e-3
+    assert worst < 5e-2, worst_key
+    for key in z.files:
+        if key.startswith("grad::"):
+            assert rel_l2(named[key[6:]].grad, torch.from_numpy(z[key])) < 5e-2, key
+
+
+def test_training_batch2_and_optimizer_step(manifest):
+    m, sd, cfg = _model(manifest, "sepformer_small_b2_t3000")
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+
+    m.train()
+    m.dropout = 0.0
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    lossf = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)
+    g = torch.Generator().manual_seed(8)
+    x = (torch.randn(2, 2000, generator=g) * 0.1).cuda()
+    tgt = (torch.randn(2, 2, 2000, generator=g) * 0.1).cuda()
+    # gradient of a B = 2 batch against the oracle (covers the (spk, batch) row scramble in the backward)
+    leaf = {k: v.clone().requires_grad_(not k.endswith("pos_enc.pe")) for k, v in sd.items()}
+    O.pit_loss(SO.sepformer_forward(leaf, x.cpu(), **cfg), tgt.cpu(), "snr", False).backward()
+    loss = lossf(m(x), tgt)
+    loss.backward()
+    errs = sorted(rel_l2(p.grad, leaf[k].grad) for k, p in m.named_parameters())
+    num = sum(float((p.grad.cpu().double() - leaf[k].grad.double()).pow(2).sum()) for k, p in m.named_parameters())
+    den = sum(float(leaf[k].grad.double().pow(2).sum()) for k, _ in m.named_parameters())
+    assert errs[len(errs) // 2] < 1e-4 and (num / den) ** 0.5 < 5e-3  # same ReLU-flip conditioning as above
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        loss = lossf(m(x), tgt)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    assert m._flat_is_valid(x.device)

@@ -156,3 +156,22 @@ def test_sepformer_batch_scramble_quirk(manifest):
     # row r = spk*B + b of the decoder lands at est[r // spks, r % spks]
     assert rel_l2(both[0, 0], one[0][0]) < 1e-5 and rel_l2(both[0, 1], one[1][0]) < 1e-5
     assert rel_l2(both[1, 0], one[0][1]) < 1e-5 and rel_l2(both[1, 1], one[1][1]) < 1e-5
+
+
+def test_sepformer_oracle_gradients_vs_reference_golden(manifest):
+    """Autograd through oracle/sepformer_oracle.py against gradients of the real reference (dropout disabled there)."""
+    from audio_only_speech_separation_b200.models import Sepformer
+    from oracle import sepformer_oracle as SO
+
+    c = manifest["cases"]["sepformer_small_b2_t3000"]
+    torch.manual_seed(0)
+    sd = {k: v.detach() for k, v in Sepformer(sample_rate=8000, **c["audionet_config"]).state_dict().items()}
+    z = load_npz("grads_sepformer_small.npz")
+    x, tgt = torch.from_numpy(z["x"]), torch.from_numpy(z["tgt"])
+    leaf = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.endswith("pos_enc.pe")) for k, v in sd.items()}
+    loss = O.pit_loss(SO.sepformer_forward(leaf, x, **c["audionet_config"]), tgt, "snr", False)
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) < 1e-5
+    for key in z.files:
+        if key.startswith("grad::"):
+            assert rel_l2(leaf[key[6:]].grad, torch.from_numpy(z[key])) < 1e-4, key
