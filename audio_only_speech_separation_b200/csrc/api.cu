@@ -404,6 +404,7 @@ struct Layout {
     std::vector<size_t> Xhl, Hhl, Hphl;            // bf16 hi/lo operand planes (TMA backend): [hi | lo]
     size_t dGhl, dYhl;
     size_t tXhl, tQKVhl, tOhl, tS1hl, tHrhl;       // DPTNet forward operand planes (shared by all paths, nothing is saved)
+    std::vector<size_t> Spre;                      // DPTNet + unfold, training: x + norm2(..) before the concat_block
     // backward temporaries
     size_t dXs, dY, dH, dpad, dMx, dMk, dE, dZ, dF2, dtmp, dQKV, dOa;
     size_t total;
@@ -475,6 +476,9 @@ void make_layout(const dp_tasnet* h, const Geo& g, bool train, Layout& l) {
     l.QKV.assign(np, 0); l.Oa.assign(np, 0); l.LSE.assign(np, 0); l.Z1.assign(np, 0); l.S1.assign(np, 0); l.Z2.assign(np, 0);
     l.dQKV = l.dOa = 0;
     l.tXhl = l.tQKVhl = l.tOhl = l.tS1hl = l.tHrhl = 0;
+    l.Spre.assign(np, 0);
+    if (xf && train && h->cfg.unfold)
+        for (int p = 1; p < np; p += 2) l.Spre[p] = c.take(g.PT * 64 * f);
     if (xf) {
         l.tXhl = c.take(g.PT * 64 * 2 * 2);
         l.tQKVhl = c.take(g.PT * 192 * 2 * 2);
@@ -702,6 +706,14 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
                 }
                 // out = x + norm2(src + ff)  (+ concat_block after the inter-chunk path when unfold); planes of the result feed the next in_proj
                 const bool cat = h->cfg.unfold && (pp & 1);
+                if (cat && train) {  // keep the sum before the concat_block for its backward
+                    float* Spre = at<float>(ws, l.Spre[pp]);
+                    CK(launch_add_ln(Y, S1, at<float>(ws, l.Z2[pp]), Spre, X, params + po[10], params + po[11], g.PT, 64, 1e-5f, nullptr, nullptr,
+                                     nullptr, st)); ++nl;
+                    CK(launch_affine_prelu(Spre, at<float>(ws, l.X[pp + 1]), g.PT, 64, params + o[9], params + o[10], params + o[11], Xh,
+                                           sp ? Xh + plX : nullptr, st)); ++nl;
+                    continue;
+                }
                 CK(launch_add_ln(Y, S1, train ? at<float>(ws, l.Z2[pp]) : nullptr, at<float>(ws, l.X[pp + 1]), X, params + po[10], params + po[11],
                                  g.PT, 64, 1e-5f, cat ? params + o[9] : nullptr, cat ? params + o[10] : nullptr, cat ? params + o[11] : nullptr,
                                  st, Xh, sp ? Xh + plX : nullptr)); ++nl;
@@ -735,6 +747,14 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
             }
             // out = x + norm2(src + ff)  (+ concat_block after the inter-chunk path when unfold)
             const bool cat = h->cfg.unfold && (pp & 1);
+            if (cat && train) {
+                float* Spre = at<float>(ws, l.Spre[pp]);
+                CK(launch_add_ln(Y, S1, at<float>(ws, l.Z2[pp]), Spre, X, params + po[10], params + po[11], g.PT, 64, 1e-5f, nullptr, nullptr, nullptr,
+                                 st)); ++nl;
+                CK(launch_affine_prelu(Spre, at<float>(ws, l.X[pp + 1]), g.PT, 64, params + o[9], params + o[10], params + o[11], nullptr, nullptr,
+                                       st)); ++nl;
+                continue;
+            }
             CK(launch_add_ln(Y, S1, train ? at<float>(ws, l.Z2[pp]) : nullptr, at<float>(ws, l.X[pp + 1]), X, params + po[10], params + po[11],
                              g.PT, 64, 1e-5f, cat ? params + o[9] : nullptr, cat ? params + o[10] : nullptr, cat ? params + o[11] : nullptr,
                              st)); ++nl;
@@ -832,8 +852,6 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
     const char* lpack = static_cast<const char*>(pack) + 2 * flat;
     const int BLi = (int)g.BL, PTi = (int)g.PT;
     int nl = 0;
-    if (h->cfg.module == DP_MODULE_DPTNET && h->cfg.unfold)
-        return fail("dp_tasnet_backward: module=DPTNet with unfold=True has no backward yet (forward only)");
 
     CK(cudaMemsetAsync(at<char>(ws, l.dpack[0]), 0, (size_t)h->npath * (((65536 + 131072 + 1024) * sizeof(float) + 255) & ~(size_t)255), st));
     // ---- decoder: d_out -> padded rows (overlapping 16-sample frames = dD), dMx = dD Wdec^T, dWdec += Mx^T dD
@@ -888,6 +906,10 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
             float* S1 = at<float>(ws, l.S1[pp]);
             float* dQKV = at<float>(ws, l.dQKV);
             float* dOa = at<float>(ws, l.dOa);
+            if (h->cfg.unfold && (pp & 1)) {  // concat_block (depthwise 1x1 + PReLU) on the stored sum: dXs <- d(sum), parameter gradients
+                CK(launch_concat_bwd(dXs, at<float>(ws, l.Spre[pp]), nullptr, nullptr, nullptr, nullptr, g.PT, g.P, 64, params + o[9], params + o[10],
+                                     params + o[11], grads + o[9], grads + o[10], grads + o[11], st)); ++nl;
+            }
             // norm2 backward: dXs is d(x + norm2(z2)); dY <- d z2 (= d ff = the residual part of d src)
             CK(launch_ln_bwd(dXs, at<float>(ws, l.Z2[pp]), dY, nullptr, params + po[10], g.PT, 64, 1e-5f, grads + po[10], grads + po[11], st)); ++nl;
             {   // linear2 + ReLU

@@ -151,15 +151,17 @@ __global__ void __launch_bounds__(256) concat_bwd_kernel(float4* __restrict__ d,
     const int g = blockIdx.y;
     const int r0 = blockIdx.x * GNB_ROWS, r1 = min(rpg, r0 + GNB_ROWS);
     const int c4 = threadIdx.x & 15, rl = threadIdx.x >> 4;
-    const float mean = mr[2 * g], rstd = mr[2 * g + 1], a = slope[0];
-    const float4 ga4 = gamma[c4], be4 = beta[c4], w4 = cw[c4], b4 = cb[c4];
+    const bool direct = (mr == nullptr);  // y already holds s (pre-activation input of the affine + PReLU), no norm / residual to redo
+    const float mean = direct ? 0.f : mr[2 * g], rstd = direct ? 1.f : mr[2 * g + 1], a = slope[0];
+    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 ga4 = direct ? one4 : gamma[c4], be4 = direct ? zero4 : beta[c4], w4 = cw[c4], b4 = cb[c4];
     const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
     const float w[4] = {w4.x, w4.y, w4.z, w4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
     float aw[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
     float as = 0.f;
     for (int r = r0 + rl; r < r1; r += 16) {
         size_t i = ((size_t)g * rpg + r) * 16 + c4;
-        float4 dv4 = d[i], yv4 = ldg_stream(y + i), rv4 = ldg_stream(res + i);
+        float4 dv4 = d[i], yv4 = ldg_stream(y + i), rv4 = direct ? zero4 : ldg_stream(res + i);
         float dv[4] = {dv4.x, dv4.y, dv4.z, dv4.w}, yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w}, rv[4] = {rv4.x, rv4.y, rv4.z, rv4.w};
         float o[4];
 #pragma unroll
@@ -322,6 +324,29 @@ __global__ void dec_ola_general_kernel(const float* __restrict__ D, float* __res
     }
 }
 
+// out = prelu(cw * s + cb) per channel (the unfold concat_block on an already formed sum), optional operand planes
+__global__ void __launch_bounds__(256) affine_prelu_kernel(const float4* __restrict__ s, float4* __restrict__ out, long long rows, int C4,
+                                                           const float4* __restrict__ cw, const float4* __restrict__ cb,
+                                                           const float* __restrict__ slope, uint2* __restrict__ out_hi, uint2* __restrict__ out_lo) {
+    const long long total = rows * C4;
+    const float a = slope[0];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        const float4 v = ldg_stream(s + i), w = cw[c4], b = cb[c4];
+        float4 o;
+        o.x = prelu_f(fmaf(w.x, v.x, b.x), a); o.y = prelu_f(fmaf(w.y, v.y, b.y), a);
+        o.z = prelu_f(fmaf(w.z, v.z, b.z), a); o.w = prelu_f(fmaf(w.w, v.w, b.w), a);
+        out[i] = o;
+        if (out_hi != nullptr) {
+            uint2 hh, ll;
+            split_pair(o.x, o.y, hh.x, ll.x);
+            split_pair(o.z, o.w, hh.y, ll.y);
+            out_hi[i] = hh;
+            if (out_lo != nullptr) out_lo[i] = ll;
+        }
+    }
+}
+
 // ---- SepFormer training helpers -----------------------------------------------------------------------------
 // GroupNorm / gLN backward reductions for any C % 4 == 0 with 256 % (C/4) == 0: grid (pieces, groups)
 __global__ void __launch_bounds__(256) gn_bwd_reduce_any_kernel(const float4* __restrict__ d, const float4* __restrict__ y, const float* __restrict__ mr,
@@ -437,6 +462,14 @@ __global__ void __launch_bounds__(256) relu_bwd_add_kernel(const float4* __restr
 
 }  // namespace
 
+cudaError_t launch_affine_prelu(const float* s, float* out, long long rows, int C, const float* cw, const float* cb, const float* slope,
+                                __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
+    if (rows <= 0) return cudaSuccess;
+    if (C & 3) return cudaErrorInvalidValue;
+    affine_prelu_kernel<<<grid_for(rows * (C / 4)), 256, 0, st>>>((const float4*)s, (float4*)out, rows, C / 4, (const float4*)cw, (const float4*)cb,
+                                                                 slope, (uint2*)out_hi, (uint2*)out_lo);
+    return cudaGetLastError();
+}
 cudaError_t launch_gn_bwd_reduce_any(const float* d, const float* y, const float* mr, const float* gamma, long long rows, int rows_per_group,
                                      int C, double* red, float* dgamma, float* dbeta, cudaStream_t st) {
     if ((C & 3) || 256 % (C / 4)) return cudaErrorInvalidValue;

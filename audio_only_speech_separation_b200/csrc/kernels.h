@@ -258,6 +258,10 @@ cudaError_t launch_ln_bwd(const float* dy, const float* z, float* dz, float* acc
 // out[n] += scale * sum_p A[p*lda + n], any N % 4 == 0
 cudaError_t launch_colsum_any(const float* A, long long lda, int P, int N, float scale, float* out, cudaStream_t st);
 
+// out = prelu(cw * s + cb) (unfold concat_block applied to a stored sum; launch_concat_bwd with mr == nullptr is its backward,
+// y = s, res / gamma / beta unused)
+cudaError_t launch_affine_prelu(const float* s, float* out, long long rows, int C, const float* cw, const float* cb, const float* slope,
+                                __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st);
 // SepFormer training helpers (elementwise.cu)
 cudaError_t launch_gn_bwd_reduce_any(const float* d, const float* y, const float* mr, const float* gamma, long long rows, int rows_per_group,
                                      int C, double* red, float* dgamma, float* dbeta, cudaStream_t st);

@@ -9,8 +9,8 @@ construction order so the default initialisation is reproduced bit for bit under
 the fused Adam step and the single NCCL gradient all-reduce operate on.
 
 Supported on this path: ``module="DPRNN"`` and ``module="DPTNet"``, ``group_size=1``, ``enc_dim=bn_dim=64``,
-``hidden_dim=128``, ``win=16`` (every DPRNN / DPTNet config of the reference), ``unfold`` True or False (DPTNet with
-``unfold`` is forward-only for now).  Anything else raises.
+``hidden_dim=128``, ``win=16`` (every DPRNN / DPTNet config of the reference), ``unfold`` True or False.  Anything else
+raises.
 """
 from __future__ import annotations
 

@@ -121,6 +121,39 @@ def test_gradients_match_oracle_autograd(manifest):
     assert worst < 2e-2, worst_key
 
 
+def test_unfold_gradients_match_oracle_autograd(manifest):
+    """DPTNet with unfold=True (shared transformer layers + concat_block): backward through the stored pre-concat sum."""
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+
+    m, sd, cfg = _model(manifest, unfold=True, layer=2)
+    m.train()
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(2, 3000, generator=g) * 0.1
+    tgt = torch.randn(2, 2, 3000, generator=g) * 0.1
+    by_storage, leaf = {}, {}
+    for k, v in m.state_dict().items():   # aliased entries share one leaf so the oracle sums their gradients
+        if v.data_ptr() not in by_storage:
+            by_storage[v.data_ptr()] = sd[k].clone().requires_grad_(True)
+        leaf[k] = by_storage[v.data_ptr()]
+    ref_loss = O.pit_loss(O.tasnet_forward(leaf, x, module="DPTNet", unfold=True, layer=2), tgt, "snr", False)
+    ref_loss.backward()
+    loss = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)(m(x.cuda()), tgt.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-4 * max(1.0, abs(ref_loss.item()))
+    errs, num, den = [], 0.0, 0.0
+    for k, p in m.named_parameters():
+        gr = leaf[k].grad
+        errs.append(rel_l2(p.grad, gr))
+        num += float((p.grad.cpu().double() - gr.double()).pow(2).sum())
+        den += float(gr.double().pow(2).sum())
+    errs.sort()
+    total = (num / den) ** 0.5
+    record("dptnet_unfold_grads", total_rel_l2=total, median_rel_l2=errs[len(errs) // 2], worst=errs[-1])
+    assert errs[len(errs) // 2] < 5e-4 and total < 5e-3   # ReLU / LayerNorm conditioning as in the test above
+    for k in ("seq_model.seq_model.concat_block.0.weight", "seq_model.seq_model.concat_block.0.bias", "seq_model.seq_model.concat_block.1.weight"):
+        assert rel_l2(dict(m.named_parameters())[k].grad, leaf[k].grad) < 5e-3, k
+
+
 def test_fused_training_step(manifest):
     from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
     from audio_only_speech_separation_b200.trainer import DualPathTrainer
