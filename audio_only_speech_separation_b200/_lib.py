@@ -41,6 +41,7 @@ PROTOTYPES = {
     "dp_last_error": (C.c_char_p, []),
     "dp_set_gemm_backend": (_i, [_i]),
     "dp_set_fused_lstm": (_i, [_i]),
+    "dp_set_lstm_pipeline": (_i, [_i]),
     "dp_seg_geometry": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "dp_wave_geometry": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "dp_segment_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),

@@ -149,6 +149,10 @@ int dp_set_fused_lstm(int mode) {
     g_fused_lstm = mode;
     return 0;
 }
+int dp_set_lstm_pipeline(int mode) {
+    if (lstm_set_pipeline(mode) != 0) return fail("dp_set_lstm_pipeline: 0 (plain 8-warp kernels), 1 (automatic), 2 (pipelined sequence groups) or 3 (16-warp kernel)");
+    return 0;
+}
 const char* dp_last_error(void) { return g_err; }
 
 int dp_seg_geometry(int L, int K, int* rest, int* Sout) {

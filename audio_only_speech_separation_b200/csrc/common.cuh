@@ -44,6 +44,13 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint4& a, const ui
         : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b[0]), "r"(b[1]));
 }
 
+// non-volatile form: ptxas may schedule it among independent instructions (used where MMAs are interleaved with other work)
+__device__ __forceinline__ void mma_bf16_sched(float (&d)[4], const uint4& a, const uint32_t (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b[0]), "r"(b[1]));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
@@ -95,6 +102,48 @@ __device__ __forceinline__ float tanh_f(float x) {
         asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
         return t;
     }
+}
+
+// Branch-free recurrent-cell versions: bare MUFU ops (ex2.approx / rcp.approx, ~2 ulp each, same units __expf / __fdividef use)
+// without the range fix-ups of __fdividef -- 1 + 2^y never needs them: y -> +inf gives rcp(inf) = 0, y -> -inf gives rcp(1) = 1.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <bool PRECISE>
+__device__ __forceinline__ float sigmoid_cell(float x) {
+    if (PRECISE) {
+        return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+    } else {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+        return fmaf(0.5f, t, 0.5f);
+    }
+}
+template <bool PRECISE>
+__device__ __forceinline__ float tanh_cell(float x) {
+    if (PRECISE) {
+        return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f);
+    } else {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+        return t;
+    }
+}
+// predicated global stores: keep the recurrent cell update one basic block (an `if` around the stores makes ptxas branch per cell)
+__device__ __forceinline__ void stg_pred(float* p, float v, bool pred) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p st.global.f32 [%0], %1;\n}\n" ::"l"(p), "f"(v), "r"((unsigned)pred) : "memory");
+}
+__device__ __forceinline__ void stg_pred(float4* p, float x, float y, float z, float w, bool pred) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %5, 0;\n @p st.global.v4.f32 [%0], {%1,%2,%3,%4};\n}\n" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w),
+                 "r"((unsigned)pred)
+                 : "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -151,6 +151,9 @@ struct LstmPlanes {
     __nv_bfloat16* hp_hi;
     __nv_bfloat16* hp_lo;
 };
+// forward recurrence kernel choice: 0 plain 8-warp kernels, 1 automatic, 2 software-pipelined sequence groups, 3 16-warp kernel
+int lstm_set_pipeline(int mode);
+int lstm_get_pipeline();
 // H may be null when only the planes are wanted.
 cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save,
                             cudaStream_t st, const LstmPlanes* planes = nullptr);

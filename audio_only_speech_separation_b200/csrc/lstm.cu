@@ -67,6 +67,49 @@ __device__ __forceinline__ void fill_seq_bases(int* sbase, int NS, int q0, const
     }
 }
 
+template <int NT>
+struct PipeGroup {          // per-thread view of one sequence group
+    float cst[NT][4];
+    unsigned hoff[NT][2];   // element offset of (sequence, unit g) in H / Cst at t = 0
+    bool valid[NT][2];
+};
+
+// One cell update.  FAST = true: bare MUFU activations and predicated stores, one basic block (pipelined kernels);
+// FAST = false: the original formulation of the plain kernels (branch around the stores).
+template <int NT, bool SPLIT, bool SAVE, bool FAST>
+__device__ __forceinline__ void pipe_cell(int q, float (&acc)[4][NT][4], PipeGroup<NT>& gr, __nv_bfloat16* h_hi, __nv_bfloat16* h_lo,
+                                          unsigned toff256, bool store, float* __restrict__ G, float* __restrict__ H,
+                                          float* __restrict__ Cst, int warp, int g, int c) {
+    const int n = q >> 2, idx = q & 3, h = idx >> 1, e = idx & 1;
+    const float ig = FAST ? sigmoid_cell<SPLIT>(acc[0][n][idx]) : sigmoid_f<SPLIT>(acc[0][n][idx]);
+    const float fg = FAST ? sigmoid_cell<SPLIT>(acc[1][n][idx]) : sigmoid_f<SPLIT>(acc[1][n][idx]);
+    const float gg = FAST ? tanh_cell<SPLIT>(acc[2][n][idx]) : tanh_f<SPLIT>(acc[2][n][idx]);
+    const float og = FAST ? sigmoid_cell<SPLIT>(acc[3][n][idx]) : sigmoid_f<SPLIT>(acc[3][n][idx]);
+    const float cc = fmaf(fg, gr.cst[n][idx], ig * gg);
+    gr.cst[n][idx] = cc;
+    const float hh = og * (FAST ? tanh_cell<SPLIT>(cc) : tanh_f<SPLIT>(cc));
+    const bool st = gr.valid[n][e] && store;
+    const unsigned ho = gr.hoff[n][e] + toff256 + h * 8;
+    if (FAST) {
+        stg_pred(H + ho, hh, st && H != nullptr);
+        if (SAVE) {
+            stg_pred(Cst + ho, cc, st);
+            // packed gate column = 4 x hidden column, so the gate offset is exactly 4 * ho
+            stg_pred(reinterpret_cast<float4*>(G + (size_t)ho * 4), ig, fg, gg, og, st);
+        }
+    } else if (st) {
+        if (H != nullptr) H[ho] = hh;
+        if (SAVE) {
+            Cst[ho] = cc;
+            *reinterpret_cast<float4*>(G + (size_t)ho * 4) = make_float4(ig, fg, gg, og);
+        }
+    }
+    const int so = (n * 8 + 2 * c + e) * HST + 16 * warp + g + 8 * h;
+    const __nv_bfloat16 hb = __float2bfloat16_rn(hh);
+    h_hi[so] = hb;
+    if (SPLIT) h_lo[so] = __float2bfloat16_rn(hh - __bfloat162float(hb));
+}
+
 template <int NT, bool SPLIT, bool SAVE>
 __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, float* __restrict__ G, float* __restrict__ H,
                                                           float* __restrict__ Cst, const SeqMap m, const LstmPlanes pl) {
@@ -238,6 +281,374 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
     }
 }
 
+// ---- software-pipelined forward recurrence ---------------------------------------------------------------------
+// The plain kernel above alternates two phases per step in which every warp does the same thing: tensor-core products
+// (tensor pipe busy, MUFU idle) and the cell update (MUFU / stores busy, tensor pipe idle) -- ncu: tensor pipe 45 % active.
+// Here a CTA's sequences form two independent groups A (NTA n-tiles) and B (NTB n-tiles) that run half a step apart:
+//   block 1 of step t:  W_hh h_A(t-1) on the tensor cores  ||  cell update of group B for step t-1
+//   block 2 of step t:  W_hh h_B(t-1) on the tensor cores  ||  cell update of group A for step t
+// Both halves of a block sit in ONE basic block of straight-line code (cells spread through the k loop), so the HMMA
+// stream of one group and the MUFU / store stream of the other issue from the same warp back to back.  Two CTA barriers
+// per step as before; gate tiles are staged per group one block ahead.
+template <int NT>
+__device__ __forceinline__ void pipe_acc_init(float (&acc)[4][NT][4], const float* gs, int c, int ucol) {
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float4 v = *reinterpret_cast<const float4*>(gs + (n * 8 + 2 * c + e) * GST + ucol + h * 32);
+                acc[0][n][h * 2 + e] = v.x; acc[1][n][h * 2 + e] = v.y; acc[2][n][h * 2 + e] = v.z; acc[3][n][h * 2 + e] = v.w;
+            }
+}
+
+// products of group X (accumulators pre-loaded with the gate pre-activations) interleaved with the cell update of group Y
+template <int NTX, int NTY, bool SPLIT, bool SAVE>
+__device__ __forceinline__ void pipe_block(float (&accX)[4][NTX][4], const uint4 (&ahi)[4][8], const uint4* alo, const __nv_bfloat16* hX_hi,
+                                           const __nv_bfloat16* hX_lo, float (&accY)[4][NTY][4], PipeGroup<NTY>& gy, __nv_bfloat16* hY_hi,
+                                           __nv_bfloat16* hY_lo, unsigned toffY256, bool storeY, float* __restrict__ G,
+                                           float* __restrict__ H, float* __restrict__ Cst, int warp, int lane) {
+    const int g = lane >> 2, c = lane & 3;
+    constexpr int CY = 4 * NTY;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        uint32_t bh[NTX][2], bl[NTX][2];
+        load_b_frags<NTX>(hX_hi, HST, ks * 16, lane, bh);
+        uint4 al[4];
+        if (SPLIT) {
+            load_b_frags<NTX>(hX_lo, HST, ks * 16, lane, bl);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) al[j] = alo[((warp * 4 + j) * 8 + ks) * 32 + lane];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int n = 0; n < NTX; ++n) mma_bf16_sched(accX[j][n], ahi[j][ks], bh[n]);
+        if (SPLIT) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int n = 0; n < NTX; ++n) mma_bf16_sched(accX[j][n], ahi[j][ks], bl[n]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int n = 0; n < NTX; ++n) mma_bf16_sched(accX[j][n], al[j], bh[n]);
+        }
+#pragma unroll
+        for (int q = 0; q < CY; ++q)
+            if ((q * 8) / CY == ks) pipe_cell<NTY, SPLIT, SAVE, true>(q, accY, gy, hY_hi, hY_lo, toffY256, storeY, G, H, Cst, warp, g, c);
+    }
+}
+
+template <int NTA, int NTB, bool SPLIT, bool SAVE>
+__global__ void __launch_bounds__(256, 1) lstm_fwd_pipe_kernel(const LstmPack w, float* __restrict__ G, float* __restrict__ H,
+                                                               float* __restrict__ Cst, const SeqMap m, const LstmPlanes pl) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NS = 8 * (NTA + NTB), RA = 8 * NTA;
+    uint4* alo = reinterpret_cast<uint4*>(smem);
+    __nv_bfloat16* hs_hi = reinterpret_cast<__nv_bfloat16*>(smem + (SPLIT ? ALO_BYTES : 0));
+    __nv_bfloat16* hs_lo = hs_hi + NS * HST;
+    float* gs = reinterpret_cast<float*>(hs_lo + NS * HST);  // [NS][GST]: rows [0, RA) group A, [RA, NS) group B
+    int* sbase = reinterpret_cast<int*>(gs + NS * GST);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int dir = blockIdx.y;
+    const int q0 = blockIdx.x * NS;
+
+    uint4 ahi[4][8];
+    {
+        const uint4* src = w.whh_f_hi + ((size_t)dir * 8 + warp) * (4 * 8 * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) ahi[j][ks] = src[(j * 8 + ks) * 32 + lane];
+    }
+    if (SPLIT) {
+        const uint4* src = w.whh_f_lo + (size_t)dir * 8192;
+        for (int i = tid; i < 8192; i += 256) alo[i] = src[i];
+    }
+    for (int i = tid; i < NS * HST; i += 256) reinterpret_cast<uint32_t*>(hs_hi)[i] = 0u;  // h_{-1} = 0 (hi and lo)
+    fill_seq_bases(sbase, NS, q0, m);
+    __syncthreads();
+
+    // stage one step's gate rows [r0, r0 + nr): 2 KB per row in 16-byte chunks, L1-bypassing
+    auto stage_gates = [&](int r0, int nr, int t) {
+        const unsigned toff = (unsigned)t * (unsigned)m.s_t;
+        for (int ch = tid; ch < nr * 128; ch += 256) {
+            const int sq = r0 + (ch >> 7), col = ch & 127;
+            const float* src = G + ((size_t)(sbase[sq] + toff) * 1024 + dir * kG + col * 4);
+            cp_async16(gs + sq * GST + col * 4, src);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    // rows [r0, r0 + nr) of the h tile hold h of the previous step: emit them as operand planes ("h_prev" at time t, H at tprev)
+    auto copy_planes = [&](int r0, int nr, int t, int tprev, bool has_prev) {
+        if (pl.h_hi == nullptr && pl.hp_hi == nullptr) return;
+        const unsigned toff = (unsigned)t * (unsigned)m.s_t, tpo = (unsigned)tprev * (unsigned)m.s_t;
+        for (int ch = tid; ch < nr * 16; ch += 256) {
+            const int sq = r0 + (ch >> 4), c16 = ch & 15;
+            if (q0 + sq >= m.nseq) continue;
+            const uint4 vh = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
+            uint4 vl = make_uint4(0, 0, 0, 0);
+            if (SPLIT) vl = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
+            const size_t col = (size_t)dir * kH + c16 * 8;
+            if (pl.hp_hi != nullptr) {
+                const size_t o = (size_t)((unsigned)sbase[sq] + toff) * 256 + col;
+                *reinterpret_cast<uint4*>(pl.hp_hi + o) = vh;
+                if (SPLIT && pl.hp_lo != nullptr) *reinterpret_cast<uint4*>(pl.hp_lo + o) = vl;
+            }
+            if (pl.h_hi != nullptr && has_prev) {
+                const size_t o = (size_t)((unsigned)sbase[sq] + tpo) * 256 + col;
+                *reinterpret_cast<uint4*>(pl.h_hi + o) = vh;
+                if (SPLIT && pl.h_lo != nullptr) *reinterpret_cast<uint4*>(pl.h_lo + o) = vl;
+            }
+        }
+    };
+
+    PipeGroup<NTA> ga;
+    PipeGroup<NTB> gb;
+    float accA[4][NTA][4], accB[4][NTB][4];
+#pragma unroll
+    for (int n = 0; n < NTA; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            ga.cst[n][e] = 0.f;
+            if (e < 2) {
+                const int sl = n * 8 + 2 * c + e;
+                ga.valid[n][e] = (q0 + sl) < m.nseq;
+                ga.hoff[n][e] = (unsigned)sbase[sl] * 256u + (unsigned)(dir * kH + 16 * warp + g);
+            }
+        }
+#pragma unroll
+    for (int n = 0; n < NTB; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            gb.cst[n][e] = 0.f;
+            // zero pre-activations give h = c = 0: group B's "step -1" cell update in the first block reproduces the initial state
+#pragma unroll
+            for (int j = 0; j < 4; ++j) accB[j][n][e] = 0.f;
+            if (e < 2) {
+                const int sl = RA + n * 8 + 2 * c + e;
+                gb.valid[n][e] = (q0 + sl) < m.nseq;
+                gb.hoff[n][e] = (unsigned)sbase[sl] * 256u + (unsigned)(dir * kH + 16 * warp + g);
+            }
+        }
+    const int ucol = (16 * warp + g) * 4;  // packed gate column of (h = 0) inside the direction; h = 1 adds 32
+    const unsigned st256 = (unsigned)m.s_t * 256u;
+
+    stage_gates(0, RA, dir ? m.len - 1 : 0);
+    for (int step = 0; step < m.len; ++step) {
+        const int t = dir ? (m.len - 1 - step) : step;
+        const int tprev = dir ? t + 1 : t - 1;
+        cp_async_wait_all();
+        __syncthreads();  // A's gate tile of step t landed; h_A(t-1) complete; everyone is done with B's tile and h_B of the last block
+        stage_gates(RA, NS - RA, t);
+        copy_planes(0, RA, t, tprev, step > 0);
+        pipe_acc_init<NTA>(accA, gs, c, ucol);
+        pipe_block<NTA, NTB, SPLIT, SAVE>(accA, ahi, alo, hs_hi, hs_lo, accB, gb, hs_hi + RA * HST, hs_lo + RA * HST,
+                                          (unsigned)tprev * st256, step > 0, G, H, Cst, warp, lane);
+        cp_async_wait_all();
+        __syncthreads();  // B's gate tile of step t landed; h_B(t-1) complete; everyone is done with A's tile and h_A(t-1)
+        if (step + 1 < m.len) stage_gates(0, RA, dir ? t - 1 : t + 1);
+        copy_planes(RA, NS - RA, t, tprev, step > 0);
+        pipe_acc_init<NTB>(accB, gs + RA * GST, c, ucol);
+        pipe_block<NTB, NTA, SPLIT, SAVE>(accB, ahi, alo, hs_hi + RA * HST, hs_lo + RA * HST, accA, ga, hs_hi, hs_lo, (unsigned)t * st256,
+                                          true, G, H, Cst, warp, lane);
+    }
+    {   // group B's last cell update
+        const unsigned tl = (unsigned)(dir ? 0 : m.len - 1) * st256;
+#pragma unroll
+        for (int q = 0; q < 4 * NTB; ++q)
+            pipe_cell<NTB, SPLIT, SAVE, true>(q, accB, gb, hs_hi + RA * HST, hs_lo + RA * HST, tl, true, G, H, Cst, warp, g, c);
+    }
+    if (pl.h_hi != nullptr) {  // the last step's h
+        __syncthreads();
+        const unsigned tlast = (unsigned)(dir ? 0 : m.len - 1) * (unsigned)m.s_t;
+        for (int ch = tid; ch < NS * 16; ch += 256) {
+            const int sq = ch >> 4, c16 = ch & 15;
+            if (q0 + sq >= m.nseq) continue;
+            const size_t o = (size_t)((unsigned)sbase[sq] + tlast) * 256 + (size_t)dir * kH + c16 * 8;
+            *reinterpret_cast<uint4*>(pl.h_hi + o) = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
+            if (SPLIT && pl.h_lo != nullptr) *reinterpret_cast<uint4*>(pl.h_lo + o) = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
+        }
+    }
+}
+
+// ---- 16-warp forward recurrence -----------------------------------------------------------------------------------
+// Same algorithm and shared-memory layout as lstm_fwd_kernel, but 512 threads: warp w owns the 8 hidden units [8w, 8w+8) as two
+// m-tiles (rows = [i | f] and [g | o] of its units), so W_hh hi costs 64 registers per thread instead of 128 and the kernel runs
+// at <= 128 registers with FOUR warps per scheduler instead of two.  The 8-warp kernels are latency-bound (ncu: 0.26 IPC per
+// scheduler, tensor pipe 45 % busy, no dominant stall reason); twice the warps per scheduler hide the MUFU / LDS / store-operand
+// latencies of the cell update behind the other warps' work.  The fragments are re-gathered from the 8-warp pack at start-up.
+template <int NT, bool SPLIT, bool SAVE>
+__global__ void __launch_bounds__(512, 1) lstm_fwd16_kernel(const LstmPack w, float* __restrict__ G, float* __restrict__ H,
+                                                            float* __restrict__ Cst, const SeqMap m, const LstmPlanes pl) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NS = 8 * NT;
+    uint4* alo = reinterpret_cast<uint4*>(smem);
+    __nv_bfloat16* hs_hi = reinterpret_cast<__nv_bfloat16*>(smem + (SPLIT ? ALO_BYTES : 0));
+    __nv_bfloat16* hs_lo = hs_hi + NS * HST;
+    float* gs = reinterpret_cast<float*>(hs_lo + NS * HST);
+    int* sbase = reinterpret_cast<int*>(gs + NS * GST);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int dir = blockIdx.y;
+    const int q0 = blockIdx.x * NS;
+
+    // 8-warp pack: [dir][wp][gate][ks][lane][reg], unit = 16 wp + g + 8 (reg & 1), k half = reg >> 1.  This warp's units are
+    // 16 (warp >> 1) + 8 (warp & 1) + g: component (warp & 1) (+ 2 for the upper k half) of the words of gates 2 mt and 2 mt + 1.
+    uint4 ahi[2][8];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(w.whh_f_hi) + ((size_t)dir * 8 + (warp >> 1)) * (4 * 8 * 32 * 4);
+        const int comp = warp & 1;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const int b0 = (((2 * mt) * 8 + ks) * 32 + lane) * 4, b1 = (((2 * mt + 1) * 8 + ks) * 32 + lane) * 4;
+                ahi[mt][ks] = make_uint4(src[b0 + comp], src[b1 + comp], src[b0 + comp + 2], src[b1 + comp + 2]);
+            }
+    }
+    if (SPLIT) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(w.whh_f_lo) + (size_t)dir * 8192 * 4;
+        for (int i = tid; i < 8192; i += 512) {  // alo[((w16 * 2 + mt) * 8 + ks) * 32 + lane]
+            const int ln = i & 31, ks = (i >> 5) & 7, mt = (i >> 8) & 1, w16 = i >> 9, comp = w16 & 1;
+            const int wb = (w16 >> 1) * (4 * 8 * 32 * 4);
+            const int b0 = wb + (((2 * mt) * 8 + ks) * 32 + ln) * 4, b1 = wb + (((2 * mt + 1) * 8 + ks) * 32 + ln) * 4;
+            alo[i] = make_uint4(src[b0 + comp], src[b1 + comp], src[b0 + comp + 2], src[b1 + comp + 2]);
+        }
+    }
+    for (int i = tid; i < NS * HST; i += 512) reinterpret_cast<uint32_t*>(hs_hi)[i] = 0u;  // h_{-1} = 0 (hi and lo)
+    fill_seq_bases(sbase, NS, q0, m);
+    __syncthreads();
+
+    auto stage_gates = [&](int t) {
+        const unsigned toff = (unsigned)t * (unsigned)m.s_t;
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+            int ch = tid + 512 * i, sq = ch >> 7, col = ch & 127;
+            const float* src = G + ((size_t)(sbase[sq] + toff) * 1024 + dir * kG + col * 4);
+            cp_async16(gs + sq * GST + col * 4, src);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    stage_gates(dir ? m.len - 1 : 0);
+
+    unsigned hoff[NT][2];
+    bool valid[NT][2];
+    float cst[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int sl = n * 8 + 2 * c + e;
+            valid[n][e] = (q0 + sl) < m.nseq;
+            hoff[n][e] = (unsigned)sbase[sl] * 256u + (unsigned)(dir * kH + 8 * warp + g);
+            cst[n][e] = 0.f;
+        }
+    const int ucol = (8 * warp + g) * 4;  // packed gate column of this thread's unit inside the direction
+
+    for (int step = 0; step < m.len; ++step) {
+        const int t = dir ? (m.len - 1 - step) : step;
+        const unsigned toff = (unsigned)t * (unsigned)m.s_t;
+        cp_async_wait_all();
+        __syncthreads();  // gate tile of step t landed; h_{t-1} (written by all warps) visible
+        if (pl.h_hi != nullptr || pl.hp_hi != nullptr) {
+            const unsigned tprev = (unsigned)(dir ? t + 1 : t - 1) * (unsigned)m.s_t;
+            for (int ch = tid; ch < NS * 16; ch += 512) {
+                const int sq = ch >> 4, c16 = ch & 15;
+                if (q0 + sq >= m.nseq) continue;
+                const uint4 vh = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
+                uint4 vl = make_uint4(0, 0, 0, 0);
+                if (SPLIT) vl = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
+                const size_t col = (size_t)dir * kH + c16 * 8;
+                if (pl.hp_hi != nullptr) {
+                    const size_t o = (size_t)((unsigned)sbase[sq] + toff) * 256 + col;
+                    *reinterpret_cast<uint4*>(pl.hp_hi + o) = vh;
+                    if (SPLIT && pl.hp_lo != nullptr) *reinterpret_cast<uint4*>(pl.hp_lo + o) = vl;
+                }
+                if (pl.h_hi != nullptr && step > 0) {
+                    const size_t o = (size_t)((unsigned)sbase[sq] + tprev) * 256 + col;
+                    *reinterpret_cast<uint4*>(pl.h_hi + o) = vh;
+                    if (SPLIT && pl.h_lo != nullptr) *reinterpret_cast<uint4*>(pl.h_lo + o) = vl;
+                }
+            }
+        }
+        float acc[2][NT][4];  // [0]: rows g = i, g + 8 = f;  [1]: g-gate, o
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float4 v = *reinterpret_cast<const float4*>(gs + (n * 8 + 2 * c + e) * GST + ucol);
+                acc[0][n][e] = v.x; acc[0][n][2 + e] = v.y; acc[1][n][e] = v.z; acc[1][n][2 + e] = v.w;
+            }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            uint32_t bh[NT][2];
+            load_b_frags<NT>(hs_hi, HST, ks * 16, lane, bh);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) mma_bf16(acc[mt][n], ahi[mt][ks], bh[n]);
+            if (SPLIT) {
+                {
+                    uint4 al[2];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) al[mt] = alo[((warp * 2 + mt) * 8 + ks) * 32 + lane];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int n = 0; n < NT; ++n) mma_bf16(acc[mt][n], al[mt], bh[n]);
+                }
+                uint32_t bl[NT][2];
+                load_b_frags<NT>(hs_lo, HST, ks * 16, lane, bl);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) mma_bf16(acc[mt][n], ahi[mt][ks], bl[n]);
+            }
+        }
+        __syncthreads();  // every warp is done reading h_{t-1} and the gate tile
+        if (step + 1 < m.len) stage_gates(dir ? t - 1 : t + 1);
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float ig = sigmoid_cell<SPLIT>(acc[0][n][e]);
+                const float fg = sigmoid_cell<SPLIT>(acc[0][n][2 + e]);
+                const float gg = tanh_cell<SPLIT>(acc[1][n][e]);
+                const float og = sigmoid_cell<SPLIT>(acc[1][n][2 + e]);
+                const float cc = fmaf(fg, cst[n][e], ig * gg);
+                cst[n][e] = cc;
+                const float hh = og * tanh_cell<SPLIT>(cc);
+                const unsigned ho = hoff[n][e] + toff * 256u;
+                stg_pred(H + ho, hh, valid[n][e] && H != nullptr);
+                if (SAVE) {
+                    stg_pred(Cst + ho, cc, valid[n][e]);
+                    stg_pred(reinterpret_cast<float4*>(G + (size_t)ho * 4), ig, fg, gg, og, valid[n][e]);
+                }
+                const int so = (n * 8 + 2 * c + e) * HST + 8 * warp + g;
+                const __nv_bfloat16 hb = __float2bfloat16_rn(hh);
+                hs_hi[so] = hb;
+                if (SPLIT) hs_lo[so] = __float2bfloat16_rn(hh - __bfloat162float(hb));
+            }
+    }
+    if (pl.h_hi != nullptr) {  // the last step's h
+        __syncthreads();
+        const unsigned tlast = (unsigned)(dir ? 0 : m.len - 1) * (unsigned)m.s_t;
+        for (int ch = tid; ch < NS * 16; ch += 512) {
+            const int sq = ch >> 4, c16 = ch & 15;
+            if (q0 + sq >= m.nseq) continue;
+            const size_t o = (size_t)((unsigned)sbase[sq] + tlast) * 256 + (size_t)dir * kH + c16 * 8;
+            *reinterpret_cast<uint4*>(pl.h_hi + o) = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
+            if (SPLIT && pl.h_lo != nullptr) *reinterpret_cast<uint4*>(pl.h_lo + o) = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 struct PackArgs {
     const float* w_ih[2];
@@ -384,7 +795,53 @@ cudaError_t fwd_launch(const LstmPack& w, float* G, float* H, float* Cst, const 
     return cudaGetLastError();
 }
 
+template <int NTA, int NTB>
+cudaError_t fwd_pipe_launch(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, const LstmPlanes& pl,
+                            cudaStream_t st) {
+    constexpr int NS = 8 * (NTA + NTB);
+    dim3 grid(ceil_div(m.nseq, NS), 2);
+    int smem = (split ? ALO_BYTES : 0) + 2 * NS * HST * 2 + NS * GST * 4 + NS * 4;
+    cudaError_t e;
+#define DP_FWDP(SP, SV)                                                                          \
+    do {                                                                                         \
+        e = set_smem(lstm_fwd_pipe_kernel<NTA, NTB, SP, SV>, smem);                              \
+        if (e != cudaSuccess) return e;                                                          \
+        lstm_fwd_pipe_kernel<NTA, NTB, SP, SV><<<grid, 256, smem, st>>>(w, G, H, Cst, m, pl);    \
+    } while (0)
+    if (split) { if (save) DP_FWDP(true, true); else DP_FWDP(true, false); }
+    else       { if (save) DP_FWDP(false, true); else DP_FWDP(false, false); }
+#undef DP_FWDP
+    return cudaGetLastError();
+}
+
+template <int NT>
+cudaError_t fwd16_launch(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, const LstmPlanes& pl,
+                         cudaStream_t st) {
+    dim3 grid(ceil_div(m.nseq, 8 * NT), 2);
+    int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * HST * 2 + 8 * NT * GST * 4 + 8 * NT * 4;
+    cudaError_t e;
+#define DP_FWD16(SP, SV)                                                               \
+    do {                                                                               \
+        e = set_smem(lstm_fwd16_kernel<NT, SP, SV>, smem);                             \
+        if (e != cudaSuccess) return e;                                                \
+        lstm_fwd16_kernel<NT, SP, SV><<<grid, 512, smem, st>>>(w, G, H, Cst, m, pl);   \
+    } while (0)
+    if (split) { if (save) DP_FWD16(true, true); else DP_FWD16(true, false); }
+    else       { if (save) DP_FWD16(false, true); else DP_FWD16(false, false); }
+#undef DP_FWD16
+    return cudaGetLastError();
+}
+
+int g_lstm_pipeline = 1;  // 0 plain kernels, 1 automatic, 2 pipelined (groups of 16 + 8 sequences), 3 16-warp kernel
+
 }  // namespace
+
+int lstm_set_pipeline(int mode) {
+    if (mode < 0 || mode > 3) return -1;
+    g_lstm_pipeline = mode;
+    return 0;
+}
+int lstm_get_pipeline() { return g_lstm_pipeline; }
 
 int lstm_pick_nt(int nseq) {
     // smallest tile that still fits the whole pass in one wave of 148 SMs (2 directions per tile)
@@ -399,7 +856,21 @@ cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, c
     LstmPlanes pl;
     memset(&pl, 0, sizeof(pl));
     if (planes) pl = *planes;
-    switch (lstm_pick_nt(m.nseq)) {
+    const int nt = lstm_pick_nt(m.nseq);
+    int pipe = g_lstm_pipeline;
+    // automatic (measured on B200, tests/tools/time_recurrence.py): one-wave tiles of 8 / 16 sequences run best on the 16-warp kernel
+    // (B = 1: 237 -> 220 us intra, 193 -> 182 us inter); full 24-sequence tiles in fp32-parity mode on the pipelined kernel
+    // (B = 16: 552 -> 513 us intra, 457 -> 424 us inter); in bf16 mode the three kernels are within 2 %
+    if (pipe == 1) pipe = nt < 3 ? 3 : (split ? 2 : 0);
+    if (pipe == 2) return fwd_pipe_launch<2, 1>(w, G, H, Cst, m, split, save, pl, st);
+    if (pipe == 3) {
+        switch (nt) {
+            case 1: return fwd16_launch<1>(w, G, H, Cst, m, split, save, pl, st);
+            case 2: return fwd16_launch<2>(w, G, H, Cst, m, split, save, pl, st);
+            default: return fwd16_launch<3>(w, G, H, Cst, m, split, save, pl, st);
+        }
+    }
+    switch (nt) {
         case 1: return fwd_launch<1>(w, G, H, Cst, m, split, save, pl, st);
         case 2: return fwd_launch<2>(w, G, H, Cst, m, split, save, pl, st);
         default: return fwd_launch<3>(w, G, H, Cst, m, split, save, pl, st);

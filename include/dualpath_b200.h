@@ -33,6 +33,11 @@ int dp_set_gemm_backend(int backend);
  * memory, gate pre-activations never in HBM).  mode 1 (default) = automatic (used in bf16 mode, where it is faster than the TMA
  * GEMM + register-stationary mma.sync recurrence), 2 = always, 0 = never. */
 int dp_set_fused_lstm(int mode);
+/* Forward recurrence kernel of the register-stationary path: 0 = plain 8-warp kernels; 2 = software-pipelined (two sequence
+ * groups per CTA half a step apart: one group's tensor-core products are interleaved with the other group's cell update);
+ * 3 = 16-warp kernel (8 hidden units per warp, 128 registers, four warps per scheduler); 1 (default) = automatic by pass size and
+ * precision.  All variants perform the same arithmetic in the same order per cell. */
+int dp_set_lstm_pipeline(int mode);
 
 /* ---- geometry (integer index maps) --------------------------------------------------------------------- */
 /* gc3_basics.py:63-76 pad_segment: rest and chunk count S for L frames and chunk size K (K even). */

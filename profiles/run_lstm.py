@@ -11,6 +11,8 @@ B, S, K = int(os.environ.get("B", 16)), 82, 100
 layout = os.environ.get("LAYOUT", "intra")
 prec = os.environ.get("PREC", "fp32")
 torch.manual_seed(0)
+from audio_only_speech_separation_b200 import _lib
+_lib.check(_lib.lib().dp_set_lstm_pipeline(int(os.environ.get("PIPE", 1))))
 lstm = torch.nn.LSTM(64, 128, 1, batch_first=True, bidirectional=True).cuda()
 pack = ops.LstmPack(lstm)
 x = torch.randn(B, S, K, 64, device="cuda")

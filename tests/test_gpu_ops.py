@@ -183,6 +183,38 @@ def test_bilstm_forward_parity(ops, layout, B, S, K):
 
 
 @pytest.mark.parametrize("layout", ["intra", "inter"])
+@pytest.mark.parametrize("mode", [0, 2, 3])
+@pytest.mark.parametrize("B,S,K", [(1, 5, 7), (3, 21, 9), (16, 82, 6)])   # ragged tiles (5, 63, 27 sequences) and full-size sequence counts
+def test_bilstm_forward_kernel_variants(ops, layout, mode, B, S, K):
+    """dp_set_lstm_pipeline: plain 8-warp, software-pipelined (16 + 8 sequence groups) and 16-warp forward kernels against the
+    oracle, with and without saving the activated gates / cell states (the backward then consumes what each variant saved)."""
+    from audio_only_speech_separation_b200 import _lib
+
+    lstm, sd, pack = _lstm_and_pack(ops, seed=3)
+    g = torch.Generator().manual_seed(B * 100 + S + K)
+    x = torch.randn(B, S, K, 64, generator=g)
+    dH = torch.randn(B, S, K, 256, generator=g)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    ref = _oracle_bilstm(xr, leaf, layout, impl="aten")
+    ref.backward(dH)
+    _lib.check(_lib.lib().dp_set_lstm_pipeline(mode))
+    try:
+        for prec, tol in (("fp32", 2e-5), ("bf16", 3e-2)):
+            H, _, _ = ops.bilstm_forward(pack, x.cuda(), layout, precision=prec)
+            Hs, G, Cst = ops.bilstm_forward(pack, x.cuda(), layout, save=True, precision=prec)
+            assert torch.equal(H, Hs)
+            err = rel_l2(H, ref.detach())
+            record("bilstm_fwd_variant", mode=mode, prec=prec, layout=layout, B=B, S=S, K=K, rel_l2=err)
+            assert err < tol
+            if prec == "fp32":
+                dx, _ = ops.bilstm_backward(pack, G, Cst, dH.cuda(), (B, S, K), layout)
+                assert rel_l2(dx, xr.grad) < 5e-5
+    finally:
+        _lib.check(_lib.lib().dp_set_lstm_pipeline(1))
+
+
+@pytest.mark.parametrize("layout", ["intra", "inter"])
 @pytest.mark.parametrize("B,S,K", [(2, 6, 10), (16, 82, 12)])
 def test_bilstm_backward_parity(ops, layout, B, S, K):
     lstm, sd, pack = _lstm_and_pack(ops, seed=1)
