@@ -59,10 +59,10 @@ constexpr int GST = kG + 4;  // staged gate-tile row stride (floats): 2064 B kee
 
 // Position bases of the tile's sequences -> shared memory (invalid sequences alias the tile's first one: their
 // loads are harmless and their stores are suppressed).
-__device__ __forceinline__ void fill_seq_bases(int* sbase, int NS, int q0, const SeqMap& m) {
+__device__ __forceinline__ void fill_seq_bases(int* sbase, int NS, int q0, int nv, const SeqMap& m) {
     for (int i = threadIdx.x; i < NS; i += blockDim.x) {
         int q = q0 + i;
-        if (q >= m.nseq) q = q0;
+        if (i >= nv) q = q0;
         sbase[i] = (int)((q / m.qdiv) * m.s_hi + (q % m.qdiv) * m.s_lo);
     }
 }
@@ -112,7 +112,7 @@ __device__ __forceinline__ void pipe_cell(int q, float (&acc)[4][NT][4], PipeGro
 
 template <int NT, bool SPLIT, bool SAVE>
 __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, float* __restrict__ G, float* __restrict__ H,
-                                                          float* __restrict__ Cst, const SeqMap m, const LstmPlanes pl) {
+                                                          float* __restrict__ Cst, const SeqMap m, const LstmPlanes pl, const int spc) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NS = 8 * NT;
     uint4* alo = reinterpret_cast<uint4*>(smem);
@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, c = lane & 3;
     const int dir = blockIdx.y;
-    const int q0 = blockIdx.x * NS;
+    const int q0 = blockIdx.x * spc;           // this CTA's sequences: slots [0, nv) of its NS-slot tile
+    const int nv = min(spc, m.nseq - q0);
 
     uint4 ahi[4][8];
     {
@@ -139,7 +140,8 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
         for (int i = tid; i < 8192; i += 256) alo[i] = src[i];
     }
     for (int i = tid; i < NS * HST; i += 256) reinterpret_cast<uint32_t*>(hs_hi)[i] = 0u;  // h_{-1} = 0 (hi and lo)
-    fill_seq_bases(sbase, NS, q0, m);
+    for (int i = tid; i < NS * GST; i += 256) gs[i] = 0.f;                                   // unused slots are never staged
+    fill_seq_bases(sbase, NS, q0, nv, m);
     __syncthreads();
 
     // stage one step's gate tile: NS rows of 2 KB, 16-byte chunks, fully coalesced, L1-bypassing
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
         for (int i = 0; i < NS / 2; ++i) {
             int ch = tid + 256 * i, sq = ch >> 7, col = ch & 127;
             const float* src = G + ((size_t)(sbase[sq] + toff) * 1024 + dir * kG + col * 4);
-            cp_async16(gs + sq * GST + col * 4, src);
+            if (sq < nv) cp_async16(gs + sq * GST + col * 4, src);
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             int sl = n * 8 + 2 * c + e;
-            valid[n][e] = (q0 + sl) < m.nseq;
+            valid[n][e] = sl < nv;
             hoff[n][e] = (unsigned)sbase[sl] * 256u + (unsigned)(dir * kH + 16 * warp + g);
         }
     float cst[NT][4];
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
             const unsigned tprev = (unsigned)(dir ? t + 1 : t - 1) * (unsigned)m.s_t;
             for (int ch = tid; ch < NS * 16; ch += 256) {
                 const int sq = ch >> 4, c16 = ch & 15;
-                if (q0 + sq >= m.nseq) continue;
+                if (sq >= nv) continue;
                 const uint4 vh = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
                 uint4 vl = make_uint4(0, 0, 0, 0);
                 if (SPLIT) vl = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const LstmPack w, floa
         const unsigned tlast = (unsigned)(dir ? 0 : m.len - 1) * (unsigned)m.s_t;
         for (int ch = tid; ch < NS * 16; ch += 256) {
             const int sq = ch >> 4, c16 = ch & 15;
-            if (q0 + sq >= m.nseq) continue;
+            if (sq >= nv) continue;
             const size_t o = (size_t)((unsigned)sbase[sq] + tlast) * 256 + (size_t)dir * kH + c16 * 8;
             *reinterpret_cast<uint4*>(pl.h_hi + o) = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
             if (SPLIT && pl.h_lo != nullptr) *reinterpret_cast<uint4*>(pl.h_lo + o) = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
@@ -343,7 +345,7 @@ __device__ __forceinline__ void pipe_block(float (&accX)[4][NTX][4], const uint4
 
 template <int NTA, int NTB, bool SPLIT, bool SAVE>
 __global__ void __launch_bounds__(256, 1) lstm_fwd_pipe_kernel(const LstmPack w, float* __restrict__ G, float* __restrict__ H,
-                                                               float* __restrict__ Cst, const SeqMap m, const LstmPlanes pl) {
+                                                               float* __restrict__ Cst, const SeqMap m, const LstmPlanes pl, const int spc) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NS = 8 * (NTA + NTB), RA = 8 * NTA;
     uint4* alo = reinterpret_cast<uint4*>(smem);
@@ -355,7 +357,8 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_pipe_kernel(const LstmPack w,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, c = lane & 3;
     const int dir = blockIdx.y;
-    const int q0 = blockIdx.x * NS;
+    const int q0 = blockIdx.x * spc;           // this CTA's sequences: slots [0, nv) of its NS-slot tile
+    const int nv = min(spc, m.nseq - q0);
 
     uint4 ahi[4][8];
     {
@@ -370,7 +373,8 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_pipe_kernel(const LstmPack w,
         for (int i = tid; i < 8192; i += 256) alo[i] = src[i];
     }
     for (int i = tid; i < NS * HST; i += 256) reinterpret_cast<uint32_t*>(hs_hi)[i] = 0u;  // h_{-1} = 0 (hi and lo)
-    fill_seq_bases(sbase, NS, q0, m);
+    for (int i = tid; i < NS * GST; i += 256) gs[i] = 0.f;                                   // unused slots are never staged
+    fill_seq_bases(sbase, NS, q0, nv, m);
     __syncthreads();
 
     // stage one step's gate rows [r0, r0 + nr): 2 KB per row in 16-byte chunks, L1-bypassing
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_pipe_kernel(const LstmPack w,
         for (int ch = tid; ch < nr * 128; ch += 256) {
             const int sq = r0 + (ch >> 7), col = ch & 127;
             const float* src = G + ((size_t)(sbase[sq] + toff) * 1024 + dir * kG + col * 4);
-            cp_async16(gs + sq * GST + col * 4, src);
+            if (sq < nv) cp_async16(gs + sq * GST + col * 4, src);
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_pipe_kernel(const LstmPack w,
         const unsigned toff = (unsigned)t * (unsigned)m.s_t, tpo = (unsigned)tprev * (unsigned)m.s_t;
         for (int ch = tid; ch < nr * 16; ch += 256) {
             const int sq = r0 + (ch >> 4), c16 = ch & 15;
-            if (q0 + sq >= m.nseq) continue;
+            if (sq >= nv) continue;
             const uint4 vh = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
             uint4 vl = make_uint4(0, 0, 0, 0);
             if (SPLIT) vl = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_pipe_kernel(const LstmPack w,
             ga.cst[n][e] = 0.f;
             if (e < 2) {
                 const int sl = n * 8 + 2 * c + e;
-                ga.valid[n][e] = (q0 + sl) < m.nseq;
+                ga.valid[n][e] = sl < nv;
                 ga.hoff[n][e] = (unsigned)sbase[sl] * 256u + (unsigned)(dir * kH + 16 * warp + g);
             }
         }
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_pipe_kernel(const LstmPack w,
             for (int j = 0; j < 4; ++j) accB[j][n][e] = 0.f;
             if (e < 2) {
                 const int sl = RA + n * 8 + 2 * c + e;
-                gb.valid[n][e] = (q0 + sl) < m.nseq;
+                gb.valid[n][e] = sl < nv;
                 gb.hoff[n][e] = (unsigned)sbase[sl] * 256u + (unsigned)(dir * kH + 16 * warp + g);
             }
         }
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_pipe_kernel(const LstmPack w,
         const unsigned tlast = (unsigned)(dir ? 0 : m.len - 1) * (unsigned)m.s_t;
         for (int ch = tid; ch < NS * 16; ch += 256) {
             const int sq = ch >> 4, c16 = ch & 15;
-            if (q0 + sq >= m.nseq) continue;
+            if (sq >= nv) continue;
             const size_t o = (size_t)((unsigned)sbase[sq] + tlast) * 256 + (size_t)dir * kH + c16 * 8;
             *reinterpret_cast<uint4*>(pl.h_hi + o) = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
             if (SPLIT && pl.h_lo != nullptr) *reinterpret_cast<uint4*>(pl.h_lo + o) = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
@@ -484,7 +488,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_pipe_kernel(const LstmPack w,
 // latencies of the cell update behind the other warps' work.  The fragments are re-gathered from the 8-warp pack at start-up.
 template <int NT, bool SPLIT, bool SAVE>
 __global__ void __launch_bounds__(512, 1) lstm_fwd16_kernel(const LstmPack w, float* __restrict__ G, float* __restrict__ H,
-                                                            float* __restrict__ Cst, const SeqMap m, const LstmPlanes pl) {
+                                                            float* __restrict__ Cst, const SeqMap m, const LstmPlanes pl, const int spc) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NS = 8 * NT;
     uint4* alo = reinterpret_cast<uint4*>(smem);
@@ -496,7 +500,8 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd16_kernel(const LstmPack w, fl
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, c = lane & 3;
     const int dir = blockIdx.y;
-    const int q0 = blockIdx.x * NS;
+    const int q0 = blockIdx.x * spc;           // this CTA's sequences: slots [0, nv) of its NS-slot tile
+    const int nv = min(spc, m.nseq - q0);
 
     // 8-warp pack: [dir][wp][gate][ks][lane][reg], unit = 16 wp + g + 8 (reg & 1), k half = reg >> 1.  This warp's units are
     // 16 (warp >> 1) + 8 (warp & 1) + g: component (warp & 1) (+ 2 for the upper k half) of the words of gates 2 mt and 2 mt + 1.
@@ -522,7 +527,8 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd16_kernel(const LstmPack w, fl
         }
     }
     for (int i = tid; i < NS * HST; i += 512) reinterpret_cast<uint32_t*>(hs_hi)[i] = 0u;  // h_{-1} = 0 (hi and lo)
-    fill_seq_bases(sbase, NS, q0, m);
+    for (int i = tid; i < NS * GST; i += 512) gs[i] = 0.f;                                   // unused slots are never staged
+    fill_seq_bases(sbase, NS, q0, nv, m);
     __syncthreads();
 
     auto stage_gates = [&](int t) {
@@ -531,7 +537,7 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd16_kernel(const LstmPack w, fl
         for (int i = 0; i < NS / 4; ++i) {
             int ch = tid + 512 * i, sq = ch >> 7, col = ch & 127;
             const float* src = G + ((size_t)(sbase[sq] + toff) * 1024 + dir * kG + col * 4);
-            cp_async16(gs + sq * GST + col * 4, src);
+            if (sq < nv) cp_async16(gs + sq * GST + col * 4, src);
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
@@ -545,7 +551,7 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd16_kernel(const LstmPack w, fl
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int sl = n * 8 + 2 * c + e;
-            valid[n][e] = (q0 + sl) < m.nseq;
+            valid[n][e] = sl < nv;
             hoff[n][e] = (unsigned)sbase[sl] * 256u + (unsigned)(dir * kH + 8 * warp + g);
             cst[n][e] = 0.f;
         }
@@ -560,7 +566,7 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd16_kernel(const LstmPack w, fl
             const unsigned tprev = (unsigned)(dir ? t + 1 : t - 1) * (unsigned)m.s_t;
             for (int ch = tid; ch < NS * 16; ch += 512) {
                 const int sq = ch >> 4, c16 = ch & 15;
-                if (q0 + sq >= m.nseq) continue;
+                if (sq >= nv) continue;
                 const uint4 vh = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
                 uint4 vl = make_uint4(0, 0, 0, 0);
                 if (SPLIT) vl = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
@@ -641,7 +647,7 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd16_kernel(const LstmPack w, fl
         const unsigned tlast = (unsigned)(dir ? 0 : m.len - 1) * (unsigned)m.s_t;
         for (int ch = tid; ch < NS * 16; ch += 512) {
             const int sq = ch >> 4, c16 = ch & 15;
-            if (q0 + sq >= m.nseq) continue;
+            if (sq >= nv) continue;
             const size_t o = (size_t)((unsigned)sbase[sq] + tlast) * 256 + (size_t)dir * kH + c16 * 8;
             *reinterpret_cast<uint4*>(pl.h_hi + o) = *reinterpret_cast<const uint4*>(hs_hi + sq * HST + c16 * 8);
             if (SPLIT && pl.h_lo != nullptr) *reinterpret_cast<uint4*>(pl.h_lo + o) = *reinterpret_cast<const uint4*>(hs_lo + sq * HST + c16 * 8);
@@ -772,6 +778,19 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* 
     }
 }
 
+}  // namespace
+
+// Sequences per CTA for a tile of `slots` sequence slots: when the whole pass fits one wave (2 directions x <= 74 CTAs) the
+// sequences are spread evenly over all 74 CTAs per direction instead of filling tiles -- the tensor-core work per CTA depends
+// only on the slot count, the cell-update / staging / store work on the sequences actually present.
+int lstm_seqs_per_cta(int nseq, int slots) {
+    if (ceil_div(nseq, slots) > 74) return slots;
+    const int spc = ceil_div(nseq, 74);
+    return spc < 1 ? 1 : (spc > slots ? slots : spc);
+}
+
+namespace {
+
 template <typename K>
 cudaError_t set_smem(K kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -780,14 +799,15 @@ cudaError_t set_smem(K kernel, int bytes) {
 template <int NT>
 cudaError_t fwd_launch(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, const LstmPlanes& pl,
                        cudaStream_t st) {
-    dim3 grid(ceil_div(m.nseq, 8 * NT), 2);
+    const int spc = lstm_seqs_per_cta(m.nseq, 8 * NT);
+    dim3 grid(ceil_div(m.nseq, spc), 2);
     int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * HST * 2 + 8 * NT * GST * 4 + 8 * NT * 4;
     cudaError_t e;
 #define DP_FWD(SP, SV)                                                               \
     do {                                                                             \
         e = set_smem(lstm_fwd_kernel<NT, SP, SV>, smem);                             \
         if (e != cudaSuccess) return e;                                              \
-        lstm_fwd_kernel<NT, SP, SV><<<grid, 256, smem, st>>>(w, G, H, Cst, m, pl);   \
+        lstm_fwd_kernel<NT, SP, SV><<<grid, 256, smem, st>>>(w, G, H, Cst, m, pl, spc);   \
     } while (0)
     if (split) { if (save) DP_FWD(true, true); else DP_FWD(true, false); }
     else       { if (save) DP_FWD(false, true); else DP_FWD(false, false); }
@@ -799,14 +819,15 @@ template <int NTA, int NTB>
 cudaError_t fwd_pipe_launch(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, const LstmPlanes& pl,
                             cudaStream_t st) {
     constexpr int NS = 8 * (NTA + NTB);
-    dim3 grid(ceil_div(m.nseq, NS), 2);
+    const int spc = lstm_seqs_per_cta(m.nseq, NS);
+    dim3 grid(ceil_div(m.nseq, spc), 2);
     int smem = (split ? ALO_BYTES : 0) + 2 * NS * HST * 2 + NS * GST * 4 + NS * 4;
     cudaError_t e;
 #define DP_FWDP(SP, SV)                                                                          \
     do {                                                                                         \
         e = set_smem(lstm_fwd_pipe_kernel<NTA, NTB, SP, SV>, smem);                              \
         if (e != cudaSuccess) return e;                                                          \
-        lstm_fwd_pipe_kernel<NTA, NTB, SP, SV><<<grid, 256, smem, st>>>(w, G, H, Cst, m, pl);    \
+        lstm_fwd_pipe_kernel<NTA, NTB, SP, SV><<<grid, 256, smem, st>>>(w, G, H, Cst, m, pl, spc);    \
     } while (0)
     if (split) { if (save) DP_FWDP(true, true); else DP_FWDP(true, false); }
     else       { if (save) DP_FWDP(false, true); else DP_FWDP(false, false); }
@@ -817,14 +838,15 @@ cudaError_t fwd_pipe_launch(const LstmPack& w, float* G, float* H, float* Cst, c
 template <int NT>
 cudaError_t fwd16_launch(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, const LstmPlanes& pl,
                          cudaStream_t st) {
-    dim3 grid(ceil_div(m.nseq, 8 * NT), 2);
+    const int spc = lstm_seqs_per_cta(m.nseq, 8 * NT);
+    dim3 grid(ceil_div(m.nseq, spc), 2);
     int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * HST * 2 + 8 * NT * GST * 4 + 8 * NT * 4;
     cudaError_t e;
 #define DP_FWD16(SP, SV)                                                               \
     do {                                                                               \
         e = set_smem(lstm_fwd16_kernel<NT, SP, SV>, smem);                             \
         if (e != cudaSuccess) return e;                                                \
-        lstm_fwd16_kernel<NT, SP, SV><<<grid, 512, smem, st>>>(w, G, H, Cst, m, pl);   \
+        lstm_fwd16_kernel<NT, SP, SV><<<grid, 512, smem, st>>>(w, G, H, Cst, m, pl, spc);   \
     } while (0)
     if (split) { if (save) DP_FWD16(true, true); else DP_FWD16(true, false); }
     else       { if (save) DP_FWD16(false, true); else DP_FWD16(false, false); }
@@ -858,10 +880,11 @@ cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, c
     if (planes) pl = *planes;
     const int nt = lstm_pick_nt(m.nseq);
     int pipe = g_lstm_pipeline;
-    // automatic (measured on B200, tests/tools/time_recurrence.py): one-wave tiles of 8 / 16 sequences run best on the 16-warp kernel
-    // (B = 1: 237 -> 220 us intra, 193 -> 182 us inter); full 24-sequence tiles in fp32-parity mode on the pipelined kernel
-    // (B = 16: 552 -> 513 us intra, 457 -> 424 us inter); in bf16 mode the three kernels are within 2 %
-    if (pipe == 1) pipe = nt < 3 ? 3 : (split ? 2 : 0);
+    // automatic (measured on B200 with tests/tools/time_recurrence.py, training mode, intra / inter pass):
+    //   B = 16 fp32: plain 552 / 459 us, pipelined 502 / 420, 16-warp 543 / 464      -> pipelined
+    //   B = 16 bf16: pipelined 329 / 309, 16-warp 320 / 296                          -> 16-warp
+    //   B = 1  fp32: plain 213 / 172, 16-warp 198 / 165; bf16: 113 / 95 vs 107 / 88  -> 16-warp
+    if (pipe == 1) pipe = (nt == 3 && split) ? 2 : 3;
     if (pipe == 2) return fwd_pipe_launch<2, 1>(w, G, H, Cst, m, split, save, pl, st);
     if (pipe == 3) {
         switch (nt) {

@@ -13,6 +13,7 @@
 #include "kernels.h"
 
 namespace dp {
+int lstm_seqs_per_cta(int nseq, int slots);
 namespace {
 
 constexpr int DST = kG + 8;    // dgates smem row stride (bf16): 1040 B
@@ -48,7 +49,7 @@ __device__ __forceinline__ float4 ld_f4_ordered(const float* p) {  // volatile a
 template <int NT, bool SPLIT>
 __global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, float* __restrict__ G, const float* __restrict__ Cst,
                                                           const float* __restrict__ dH, float* __restrict__ dbias, const SeqMap m,
-                                                          __nv_bfloat16* __restrict__ dG_hi, __nv_bfloat16* __restrict__ dG_lo) {
+                                                          __nv_bfloat16* __restrict__ dG_hi, __nv_bfloat16* __restrict__ dG_lo, const int spc) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NS = 8 * NT;
     uint4* alo = reinterpret_cast<uint4*>(smem);
@@ -62,7 +63,8 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, floa
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, c = lane & 3;
     const int dir = blockIdx.y;
-    const int q0 = blockIdx.x * NS;
+    const int q0 = blockIdx.x * spc;           // this CTA's sequences: slots [0, nv) of its NS-slot tile (lstm_seqs_per_cta)
+    const int nv = min(spc, m.nseq - q0);
 
     uint4 ahi[32];
     {
@@ -76,9 +78,10 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, floa
     }
     for (int i = tid; i < NS; i += 256) {  // invalid sequences alias the tile's first one (loads harmless, stores masked)
         int q = q0 + i;
-        if (q >= m.nseq) q = q0;
+        if (i >= nv) q = q0;
         sbase[i] = (int)((q / m.qdiv) * m.s_hi + (q % m.qdiv) * m.s_lo);
     }
+    for (int i = tid; i < 3 * NS * SST; i += 256) st_c[i] = 0.f;  // c ping-pong tiles and the dH tile (contiguous)
     __syncthreads();
 
     // stage the c_{t-1} (= Cst at tp, into c buffer `cb`) and dH_t tiles of one step: NS rows x 512 B each
@@ -89,6 +92,7 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, floa
             const int which = ch >= NS * 32;
             const int rem = which ? ch - NS * 32 : ch;
             const int sq = rem >> 5, col = rem & 31;
+            if (sq >= nv) continue;  // unused slots keep their zero-initialised tiles
             if (which) {
                 cp_async16(st_dh + sq * SST + col * 4, dH + ((size_t)(sbase[sq] + (unsigned)t * (unsigned)m.s_t) * 256 + dir * kH + col * 4));
             } else if (!first) {
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, floa
 #pragma unroll
     for (int n = 0; n < NT; ++n)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) valid[n][e] = (q0 + n * 8 + 2 * c + e) < m.nseq;
+        for (int e = 0; e < 2; ++e) valid[n][e] = (n * 8 + 2 * c + e) < nv;
     const unsigned hcol = (unsigned)(dir * kH + 16 * warp + g);  // H / Cst / dH column of (h = 0); the packed gate
     const int ucol = (16 * warp + g) * 4;                        // column is exactly 4x the H column: G offset = 4 * H offset
     float acc[NT][4];
@@ -217,17 +221,18 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, floa
 template <int NT>
 cudaError_t bwd_launch(const LstmPack& w, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,
                        __nv_bfloat16* dG_hi, __nv_bfloat16* dG_lo, cudaStream_t st) {
-    dim3 grid(ceil_div(m.nseq, 8 * NT), 2);
+    const int spc = lstm_seqs_per_cta(m.nseq, 8 * NT);
+    dim3 grid(ceil_div(m.nseq, spc), 2);
     int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * DST * 2 + 3 * 8 * NT * SST * 4 + 4 * NT * 256 * 4 + 8 * NT * 4;
     cudaError_t e;
     if (split) {
         e = cudaFuncSetAttribute(lstm_bwd_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        lstm_bwd_kernel<NT, true><<<grid, 256, smem, st>>>(w, G, Cst, dH, dbias, m, dG_hi, dG_lo);
+        lstm_bwd_kernel<NT, true><<<grid, 256, smem, st>>>(w, G, Cst, dH, dbias, m, dG_hi, dG_lo, spc);
     } else {
         e = cudaFuncSetAttribute(lstm_bwd_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        lstm_bwd_kernel<NT, false><<<grid, 256, smem, st>>>(w, G, Cst, dH, dbias, m, dG_hi, dG_lo);
+        lstm_bwd_kernel<NT, false><<<grid, 256, smem, st>>>(w, G, Cst, dH, dbias, m, dG_hi, dG_lo, spc);
     }
     return cudaGetLastError();
 }
@@ -235,6 +240,7 @@ cudaError_t bwd_launch(const LstmPack& w, float* G, const float* Cst, const floa
 }  // namespace
 
 int lstm_pick_nt(int nseq);
+int lstm_seqs_per_cta(int nseq, int slots);
 
 cudaError_t launch_lstm_bwd(const LstmPack& w, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,
                             cudaStream_t st, __nv_bfloat16* dG_hi, __nv_bfloat16* dG_lo) {
