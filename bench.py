@@ -8,7 +8,8 @@ clip_grad_norm_(5.0) + Adam(1e-3) on synthetic data, random-init weights of the 
 * ``value``  : training samples/s over all ranks, inputs already resident in HBM, CUDA-event timed, max over ranks.
 * ``e2e``    : same metric through the public trainer call with HOST (pinned) inputs: per step H2D copy of the
                mixtures and targets and a D2H read of the loss scalar inside the timed region.
-* ``roofline``: the dominant kernel (persistent LSTM recurrence), timed alone with CUDA events in this process.
+* ``roofline``: the dominant kernel (persistent LSTM BPTT recurrence; the forward member reported beside it), timed alone
+               with CUDA events in this process.
 * ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference (torch CPU, all host threads) on a bounded
   sample of the same workload.  The reference itself is pure Python and cannot travel to the GPU box.
 """
@@ -28,7 +29,8 @@ import torch  # noqa: E402
 SR, SECONDS, BATCH = 8000, 4.0, 16
 CFG = dict(enc_dim=64, bn_dim=64, hidden_dim=128, win=16, layer=6, num_spk=2, module="DPRNN", group_size=1, block_size=100, unfold=False)
 # dram__bytes_read.sum + dram__bytes_write.sum of one lstm_fwd_kernel launch (ncu --set full capture under profiles/), by batch
-TRAFFIC_BYTES_PER_LAUNCH = {16: 537967872 + 884442368}  # profiles/r1_lstm_fwd_v7_full.summary.txt (engine launch, inter-chunk pass)
+TRAFFIC_BYTES_PER_LAUNCH = {16: 806841600 + 488006912}      # lstm_bwd_kernel, filled from profiles/r1_lstm_bwd_v9_full.summary.txt
+TRAFFIC_FWD_BYTES_PER_LAUNCH = {16: 537961984 + 751281920}  # lstm_fwd_pipe_kernel, profiles/r1_lstm_fwd_v9_full.summary.txt
 METRIC = "train samples/sec (DPRNN wsj0, batch 16/GPU, 4 s @ 8 kHz, fwd + PIT-SNR loss + bwd + clip + Adam)"
 
 
@@ -161,8 +163,10 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ our arm
 def time_recurrence(model, B, precision):
-    """Average duration of the dominant kernel family's forward member (persistent BiLSTM recurrence, intra-chunk pass at the
-    bench shape, training mode: activated gates and cell states saved), timed alone with CUDA events."""
+    """Average duration of the dominant kernel family (persistent BiLSTM recurrence, intra-chunk pass at the bench shape,
+    training mode), each member timed alone with CUDA events on the launching stream: the forward kernel (reads the gate
+    pre-activations, writes activated gates, cell states and H) and the BPTT kernel (reads gates, cell states and dH, writes
+    d(pre-activations)).  Both move 84 MB per utterance; buffers (537 MB of gates at B = 16) exceed the L2."""
     from audio_only_speech_separation_b200 import _lib, ops
 
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -173,22 +177,28 @@ def time_recurrence(model, B, precision):
     G = torch.empty_like(G0)
     H = torch.empty(P, 256, device=dev)
     Cst = torch.empty(P, 256, device=dev)
+    dH = torch.randn(P, 256, device=dev) * 0.1
+    dbias = torch.zeros(1024, device=dev)
     prec = _lib.PREC_FP32 if precision == "fp32" else _lib.PREC_BF16
-    times = []
+    L = _lib.lib()
+    tf, tb = [], []
     for it in range(6):
-        G.copy_(G0)  # G (537 MB at B=16) is larger than L2, so every timed launch starts cold
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        G.copy_(G0)  # every timed launch starts from a cold L2
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        _lib.check(_lib.lib().dp_lstm_recurrence_f32(_lib.ptr(pack.buf), _lib.ptr(G), _lib.ptr(H), _lib.ptr(Cst), B * S, K, 1 << 30, 0, K, 1, 1,
-                                                      prec, _lib.stream_ptr()))
+        _lib.check(L.dp_lstm_recurrence_f32(_lib.ptr(pack.buf), _lib.ptr(G), _lib.ptr(H), _lib.ptr(Cst), B * S, K, 1 << 30, 0, K, 1, 1, prec,
+                                            _lib.stream_ptr()))
         e1.record()
+        _lib.check(L.dp_bilstm_backward_f32(_lib.ptr(pack.buf), _lib.ptr(G), _lib.ptr(Cst), _lib.ptr(dH), None, 0, _lib.ptr(dbias), P, B * S, K,
+                                            1 << 30, 0, K, 1, prec, _lib.stream_ptr()))
+        e2.record()
         torch.cuda.synchronize()
         if it >= 2:
-            times.append(e0.elapsed_time(e1) * 1e-3)
-    sec = sum(times) / len(times)
-    flops = 2.0 * 512 * 128 * (B * S) * K * 2   # h_{t-1} W_hh^T, both directions (algorithmic: one product per MAC)
-    hbm = P * (1024 + 1024 + 256 + 256) * 4.0   # read G, write activated gates, c_t and H = 84 MB per utterance
-    return sec, flops, hbm
+            tf.append(e0.elapsed_time(e1) * 1e-3)
+            tb.append(e1.elapsed_time(e2) * 1e-3)
+    flops = 2.0 * 512 * 128 * (B * S) * K * 2   # one recurrent product per step, both directions (algorithmic: one product per MAC)
+    hbm = P * (1024 + 1024 + 256 + 256) * 4.0   # 84 MB per utterance for either kernel
+    return sum(tf) / len(tf), sum(tb) / len(tb), flops, hbm
 
 
 def run_ours(args):
@@ -256,7 +266,7 @@ def run_ours(args):
 
     if rank == 0:
         pk, pk_kind = peaks()
-        k_sec, k_flops, k_hbm = time_recurrence(model, args.batch, args.precision)
+        f_sec, k_sec, k_flops, k_hbm = time_recurrence(model, args.batch, args.precision)
         tf = k_flops / k_sec / 1e12
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -281,14 +291,18 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * sec_e2e / args.steps, "loss": last.get("loss")},
             "gpu_launches": trainer.launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "lstm_fwd_kernel (persistent BiLSTM recurrence, intra-chunk pass, training mode; the recurrence "
-                                   "kernels fwd+bwd are ~58% of the step)", "bound": "hbm",
+            "roofline": {"kernel": "lstm_bwd_kernel (persistent BiLSTM BPTT recurrence, intra-chunk pass; largest single share of the step: "
+                                   "the recurrence kernels fwd + bwd are ~57% of it)", "bound": "hbm",
                          "achieved": k_hbm / k_sec / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": k_hbm / k_sec / 1e9 / pk["hbm_gbs"],
                          "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.batch),
                          "peak_source": f"{pk_kind} HBM copy bandwidth (kernel timed alone)", "ms_per_launch": 1e3 * k_sec,
                          "algorithmic_bytes_per_launch": k_hbm, "tensor_tflops": tf, "tensor_frac": tf / pk["bf16_tflops"],
-                         "note": "84 MB per utterance (SURVEY 8d: read G, write gates + c_t + H); the kernel is bound by the per-step "
-                                 "dependent chain (tensor-core issue + MUFU), not by HBM: both fractions reported"},
+                         "forward_kernel": {"kernel": "lstm_fwd_pipe_kernel (same pass, forward, training mode)", "ms_per_launch": 1e3 * f_sec,
+                                            "achieved": k_hbm / f_sec / 1e9, "frac": k_hbm / f_sec / 1e9 / pk["hbm_gbs"],
+                                            "traffic": TRAFFIC_FWD_BYTES_PER_LAUNCH.get(args.batch)},
+                         "note": "84 MB per utterance (SURVEY 8d: bwd reads activated gates, c_t and dH and writes d(pre-activations); fwd "
+                                 "reads G and writes gates + c_t + H); the kernels are bound by the per-step dependent chain (tensor-core "
+                                 "issue, shared-memory operand traffic, MUFU), not by HBM: both fractions reported"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
