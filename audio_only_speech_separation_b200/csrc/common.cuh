@@ -146,6 +146,11 @@ __device__ __forceinline__ void stg_pred(float4* p, float x, float y, float z, f
                  : "memory");
 }
 
+__device__ __forceinline__ void stg_pred(uint2* p, const uint2& v, bool pred) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %3, 0;\n @p st.global.v2.u32 [%0], {%1,%2};\n}\n" ::"l"(p), "r"(v.x), "r"(v.y), "r"((unsigned)pred)
+                 : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

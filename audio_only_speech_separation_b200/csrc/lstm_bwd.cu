@@ -218,6 +218,218 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const LstmPack w, floa
         }
 }
 
+template <int NT, bool SPLIT>
+__global__ void __launch_bounds__(256, 1) lstm_bwd_ks_kernel(const LstmPack w, float* __restrict__ G, const float* __restrict__ Cst,
+                                                          const float* __restrict__ dH, float* __restrict__ dbias, const SeqMap m,
+                                                          __nv_bfloat16* __restrict__ dG_hi, __nv_bfloat16* __restrict__ dG_lo, const int spc) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NS = 8 * NT;
+    uint4* alo = reinterpret_cast<uint4*>(smem);
+    __nv_bfloat16* dg_hi = reinterpret_cast<__nv_bfloat16*>(smem + (SPLIT ? ALO_BYTES : 0));
+    __nv_bfloat16* dg_lo = dg_hi + NS * DST;
+    float* st_c = reinterpret_cast<float*>(dg_lo + NS * DST);   // [2][NS][SST] ping-pong: c_t of this step / c_{t-1}
+    float* st_dh = st_c + 2 * NS * SST;                         // [NS][SST] dH_t
+    float* dcs = st_dh + NS * SST;                              // [4*NT][256] per-thread dc carry slots
+    int* sbase = reinterpret_cast<int*>(dcs + 4 * NT * 256);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int dir = blockIdx.y;
+    const int q0 = blockIdx.x * spc;           // this CTA's sequences: slots [0, nv) of its NS-slot tile (lstm_seqs_per_cta)
+    const int nv = min(spc, m.nseq - q0);
+
+    // warp (mg, kh): hidden units [32 mg, 32 mg + 32) (m-tiles j = 0, 1 = fragments of the 8-warp pack's warps 2 mg + j), gate columns
+    // [256 kh, 256 kh + 256) of the contraction; after the products the two warps of a pair swap one partial tile through shared
+    // memory and warp kh finishes m-tile j = kh.  Every warp therefore reads only HALF of the dgates tile (the B operand).
+    const int mg = warp >> 1, kh = warp & 1;
+    uint4 ahi[2][16];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const uint4* src = w.whh_b_hi + ((size_t)dir * 8 + 2 * mg + j) * (32 * 32) + (size_t)kh * 16 * 32;
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) ahi[j][ks] = src[ks * 32 + lane];
+    }
+    if (SPLIT) {
+        const uint4* src = w.whh_b_lo + (size_t)dir * 8192;
+        for (int i = tid; i < 8192; i += 256) alo[i] = src[i];
+    }
+    for (int i = tid; i < NS; i += 256) {  // invalid sequences alias the tile's first one (loads harmless, stores masked)
+        int q = q0 + i;
+        if (i >= nv) q = q0;
+        sbase[i] = (int)((q / m.qdiv) * m.s_hi + (q % m.qdiv) * m.s_lo);
+    }
+    for (int i = tid; i < 3 * NS * SST; i += 256) st_c[i] = 0.f;  // c ping-pong tiles and the dH tile (contiguous)
+    __syncthreads();
+
+    // stage the c_{t-1} (= Cst at tp, into c buffer `cb`) and dH_t tiles of one step: NS rows x 512 B each
+    auto stage = [&](int t, int tp, bool first, int cb) {
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+            const int ch = tid + 256 * i;
+            const int which = ch >= NS * 32;
+            const int rem = which ? ch - NS * 32 : ch;
+            const int sq = rem >> 5, col = rem & 31;
+            if (sq >= nv) continue;  // unused slots keep their zero-initialised tiles
+            if (which) {
+                cp_async16(st_dh + sq * SST + col * 4, dH + ((size_t)(sbase[sq] + (unsigned)t * (unsigned)m.s_t) * 256 + dir * kH + col * 4));
+            } else if (!first) {
+                cp_async16(st_c + (cb * NS + sq) * SST + col * 4, Cst + ((size_t)(sbase[sq] + (unsigned)tp * (unsigned)m.s_t) * 256 + dir * kH + col * 4));
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    bool valid[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) valid[n][e] = (n * 8 + 2 * c + e) < nv;
+    const int wu = 2 * mg + kh;                                  // the 16-unit block this warp finishes
+    const unsigned hcol = (unsigned)(dir * kH + 16 * wu + g);    // H / Cst / dH column of (h = 0); the packed gate
+    const int ucol = (16 * wu + g) * 4;                          // column is exactly 4x the H column: G offset = 4 * H offset
+    float acc[NT][4];
+    float bsum[2][4];
+    {
+        const int t0 = dir ? 0 : m.len - 1;
+        stage(t0, t0, false, 0);                               // c_t of the first visited step -> buffer 0 (dH staged too)
+        stage(t0, dir ? t0 + 1 : t0 - 1, m.len == 1, 1);       // its c_{t-1} -> buffer 1 (dH re-staged, harmless)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { acc[n][i] = 0.f; dcs[(n * 4 + i) * 256 + tid] = 0.f; }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bsum[h][i] = 0.f;
+    }
+
+    for (int step = 0; step < m.len; ++step) {
+        const int t = dir ? step : (m.len - 1 - step);       // reverse of the forward visiting order
+        const int tp = dir ? t + 1 : t - 1;                  // the step visited just before t in the forward pass
+        const bool first = (step == m.len - 1);              // t is the forward pass's first step: c_{prev} = 0
+        const unsigned toff = (unsigned)t * (unsigned)m.s_t * 256u;
+        // 1. request this step's activated gates; they are consumed after the MMA phase below
+        float4 gt[NT][4];
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned ho = (unsigned)sbase[n * 8 + 2 * c + (i & 1)] * 256u + hcol + toff + (i >> 1) * 8;
+                gt[n][i] = ld_f4_ordered(G + (size_t)ho * 4);
+            }
+        // 2. dh_rec = W_hh^T dgates of the previous step
+        float part[2][NT][4];  // partial products over this warp's half of the contraction, m-tiles j = 0, 1
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) part[j][n][i] = 0.f;
+        if (step > 0) {
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) {
+                const int ksg = kh * 16 + ks;
+                uint32_t bh[NT][2], bl[NT][2];
+                load_b_frags<NT>(dg_hi, DST, ksg * 16, lane, bh);
+                uint4 al[2];
+                if (SPLIT) {
+                    load_b_frags<NT>(dg_lo, DST, ksg * 16, lane, bl);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) al[j] = alo[((2 * mg + j) * 32 + ksg) * 32 + lane];
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) mma_bf16(part[j][n], ahi[j][ks], bh[n]);
+                if (SPLIT) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int n = 0; n < NT; ++n) mma_bf16(part[j][n], ahi[j][ks], bl[n]);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int n = 0; n < NT; ++n) mma_bf16(part[j][n], al[j], bh[n]);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        __syncthreads();  // staged tiles landed; every warp is done reading the previous dgates tile
+        // swap partials inside the warp pair through the (now dead) dgates-lo tile: the word of cell (sequence, unit) is written by the
+        // partner's lane that holds the same accumulator element, read by this lane, and later overwritten by this lane's own dgates
+        {
+            float* xw = reinterpret_cast<float*>(dg_lo);
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int sl = n * 8 + 2 * c + (i & 1), un = 16 * (2 * mg + (1 - kh)) + g + 8 * (i >> 1);
+                    xw[sl * (DST / 2) + un * 2] = kh ? part[0][n][i] : part[1][n][i];
+                }
+        }
+        __syncthreads();
+        {
+            const float* xr = reinterpret_cast<const float*>(dg_lo);
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int sl = n * 8 + 2 * c + (i & 1), un = 16 * wu + g + 8 * (i >> 1);
+                    acc[n][i] = (kh ? part[1][n][i] : part[0][n][i]) + xr[sl * (DST / 2) + un * 2];
+                }
+        }
+        // 3. cell backward
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int h = i >> 1, e = i & 1;
+                const int sl = n * 8 + 2 * c + e, un = 16 * wu + g + 8 * h;
+                const float4 a = gt[n][i];
+                const float cp = first ? 0.f : st_c[(((step + 1) & 1) * NS + sl) * SST + un];
+                const float dh = st_dh[sl * SST + un] + acc[n][i];
+                const float tc = tanh_cell<SPLIT>(st_c[((step & 1) * NS + sl) * SST + un]);
+                const float dc = fmaf(dh * a.w, 1.f - tc * tc, dcs[(n * 4 + i) * 256 + tid]);
+                dcs[(n * 4 + i) * 256 + tid] = dc * a.y;
+                float4 dg;
+                dg.x = dc * a.z * a.x * (1.f - a.x);
+                dg.y = dc * cp * a.y * (1.f - a.y);
+                dg.z = dc * a.x * (1.f - a.z * a.z);
+                dg.w = dh * tc * a.w * (1.f - a.w);
+                uint2 hi, lo;
+                split_pair(dg.x, dg.y, hi.x, lo.x);
+                split_pair(dg.z, dg.w, hi.y, lo.y);
+                {   // predicated stores: the whole cell phase stays one basic block
+                    const bool v = valid[n][e];
+                    const unsigned ho = (unsigned)sbase[sl] * 256u + hcol + toff + h * 8;
+                    const bool planes = dG_hi != nullptr;
+                    stg_pred(reinterpret_cast<uint2*>(dG_hi + (size_t)ho * 4), hi, v && planes);
+                    if (SPLIT) stg_pred(reinterpret_cast<uint2*>(dG_lo + (size_t)ho * 4), lo, v && planes && dG_lo != nullptr);
+                    stg_pred(reinterpret_cast<float4*>(G + (size_t)ho * 4), dg.x, dg.y, dg.z, dg.w, v && !planes);
+                    bsum[h][0] += v ? dg.x : 0.f; bsum[h][1] += v ? dg.y : 0.f;   // selects: unused slots may hold NaN
+                    bsum[h][2] += v ? dg.z : 0.f; bsum[h][3] += v ? dg.w : 0.f;
+                }
+                *reinterpret_cast<uint2*>(dg_hi + sl * DST + un * 4) = hi;
+                if (SPLIT) *reinterpret_cast<uint2*>(dg_lo + sl * DST + un * 4) = lo;
+            }
+        __syncthreads();  // dgates tile complete; staged tiles free
+        if (!first) {
+            const int tn = tp, tnp = dir ? tn + 1 : tn - 1;
+            stage(tn, tnp, step + 1 == m.len - 1, step & 1);  // overwrites this step's (now dead) c_t tile
+        }
+    }
+    // d(b_ih + b_hh) in packed order: reduce over the 4 lanes that share a unit (different sequences), one atomic each
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float v = bsum[h][i];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (c == 0 && dbias != nullptr) atomicAdd(dbias + dir * kG + ucol + h * 32 + i, v);
+        }
+}
+
 template <int NT>
 cudaError_t bwd_launch(const LstmPack& w, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,
                        __nv_bfloat16* dG_hi, __nv_bfloat16* dG_lo, cudaStream_t st) {
@@ -225,15 +437,15 @@ cudaError_t bwd_launch(const LstmPack& w, float* G, const float* Cst, const floa
     dim3 grid(ceil_div(m.nseq, spc), 2);
     int smem = (split ? ALO_BYTES : 0) + 2 * 8 * NT * DST * 2 + 3 * 8 * NT * SST * 4 + 4 * NT * 256 * 4 + 8 * NT * 4;
     cudaError_t e;
-    if (split) {
-        e = cudaFuncSetAttribute(lstm_bwd_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        lstm_bwd_kernel<NT, true><<<grid, 256, smem, st>>>(w, G, Cst, dH, dbias, m, dG_hi, dG_lo, spc);
-    } else {
-        e = cudaFuncSetAttribute(lstm_bwd_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        lstm_bwd_kernel<NT, false><<<grid, 256, smem, st>>>(w, G, Cst, dH, dbias, m, dG_hi, dG_lo, spc);
-    }
+#define DP_BWD(KERNEL, SP)                                                                                    \
+    do {                                                                                                      \
+        e = cudaFuncSetAttribute(KERNEL<NT, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
+        if (e != cudaSuccess) return e;                                                                       \
+        KERNEL<NT, SP><<<grid, 256, smem, st>>>(w, G, Cst, dH, dbias, m, dG_hi, dG_lo, spc);                  \
+    } while (0)
+    if (lstm_get_pipeline() == 0) { if (split) DP_BWD(lstm_bwd_kernel, true); else DP_BWD(lstm_bwd_kernel, false); }
+    else                          { if (split) DP_BWD(lstm_bwd_ks_kernel, true); else DP_BWD(lstm_bwd_ks_kernel, false); }
+#undef DP_BWD
     return cudaGetLastError();
 }
 
