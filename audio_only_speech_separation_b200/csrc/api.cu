@@ -409,6 +409,7 @@ struct Layout {
     size_t dGhl, dYhl;
     size_t tXhl, tQKVhl, tOhl, tS1hl, tHrhl;       // DPTNet forward operand planes (shared by all paths, nothing is saved)
     std::vector<size_t> Spre;                      // DPTNet + unfold, training: x + norm2(..) before the concat_block
+    std::vector<size_t> S1hl;                      // DPTNet training: planes of the LSTM input (norm1 output) per path
     // backward temporaries
     size_t dXs, dY, dH, dpad, dMx, dMk, dE, dZ, dF2, dtmp, dQKV, dOa;
     size_t total;
@@ -483,6 +484,15 @@ void make_layout(const dp_tasnet* h, const Geo& g, bool train, Layout& l) {
     l.Spre.assign(np, 0);
     if (xf && train && h->cfg.unfold)
         for (int p = 1; p < np; p += 2) l.Spre[p] = c.take(g.PT * 64 * f);
+    l.S1hl.assign(np, 0);
+    if (xf && train) {  // what the TMA-fed weight-gradient GEMMs of the BiLSTM read: x planes, h_prev planes, dG / dY planes
+        for (int p = 0; p < np; ++p) {
+            l.S1hl[p] = c.take(g.PT * 64 * 2 * 2);
+            l.Hphl[p] = c.take(g.PT * 256 * 2 * 2);
+        }
+        l.dGhl = c.take(g.PT * 1024 * 2 * 2);
+        l.dYhl = c.take(g.PT * 64 * 2 * 2);
+    }
     if (xf) {
         l.tXhl = c.take(g.PT * 64 * 2 * 2);
         l.tQKVhl = c.take(g.PT * 192 * 2 * 2);
@@ -670,7 +680,7 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
                 __nv_bfloat16* Xh = at<__nv_bfloat16>(ws, l.tXhl);
                 __nv_bfloat16* Qh = at<__nv_bfloat16>(ws, l.tQKVhl);
                 __nv_bfloat16* Oh = at<__nv_bfloat16>(ws, l.tOhl);
-                __nv_bfloat16* S1h = at<__nv_bfloat16>(ws, l.tS1hl);
+                __nv_bfloat16* S1h = at<__nv_bfloat16>(ws, train ? l.S1hl[pp] : l.tS1hl);
                 __nv_bfloat16* Hrh = at<__nv_bfloat16>(ws, l.tHrhl);
                 const long long plQ = g.PT * 192;
                 LstmFusedGeom gm;
@@ -701,7 +711,15 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
                     a.bias = v.bias;
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
-                CK(launch_lstm_fwd(v.rec, G, H, train ? at<float>(ws, l.Cst[pp]) : nullptr, m, sp, train != 0, st)); ++nl;
+                if (train) {  // h_prev planes for the dW_hh gradient GEMM
+                    LstmPlanes hp;
+                    memset(&hp, 0, sizeof(hp));
+                    hp.hp_hi = at<__nv_bfloat16>(ws, l.Hphl[pp]);
+                    hp.hp_lo = sp ? hp.hp_hi + plH : nullptr;
+                    CK(launch_lstm_fwd(v.rec, G, H, at<float>(ws, l.Cst[pp]), m, sp, true, st, &hp)); ++nl;
+                } else {
+                    CK(launch_lstm_fwd(v.rec, G, H, nullptr, m, sp, false, st)); ++nl;
+                }
                 CK(launch_split_rows(H, 256, Hrh, sp ? Hrh + plH : nullptr, g.PT, 256, 1, st)); ++nl;   // relu(H) as operand planes
                 {
                     TmaGemmArgs a = tma_args(Hrh, plH, 256, whi + po[8], wlo + po[8], 256, Y, 64, (int)g.PT, 64, 256);
@@ -916,28 +934,69 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
             }
             // norm2 backward: dXs is d(x + norm2(z2)); dY <- d z2 (= d ff = the residual part of d src)
             CK(launch_ln_bwd(dXs, at<float>(ws, l.Z2[pp]), dY, nullptr, params + po[10], g.PT, 64, 1e-5f, grads + po[10], grads + po[11], st)); ++nl;
-            {   // linear2 + ReLU
-                GemmNtArgs a = nt_args(dY, 64, v.projt_hi, v.projt_lo, 64, 0, dH, 256, PTi, 256, 64);
-                a.mask = H; a.ldmask = 256;
-                CK(launch_gemm_nt(a, sp, st)); ++nl;
-                GemmTnArgs t = tn_args(dY, 64, H, 256, grads + po[8], 256, PTi, 64, 256);
-                t.relu_b = 1;
-                CK(launch_gemm_tn(t, sp, st)); ++nl;
-                CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[9], nullptr, st)); ++nl;
-            }
-            CK(launch_lstm_bwd(v.rec, G, at<float>(ws, l.Cst[pp]), dH, dpk + 65536 + 131072, m, sp, st)); ++nl;
-            {   // d src (after norm1) = d z2 + dG W_ih ; LSTM weight gradients
-                GemmNtArgs a = nt_args(G, 1024, v.wiht_hi, v.wiht_lo, 1024, 0, dY, 64, PTi, 64, 1024);
-                a.accumulate = 1;
-                CK(gemm_nt(a, sp, st)); ++nl;
-                GemmTnArgs t = tn_args(G, 1024, S1, 64, dpk, 64, PTi, 1024, 64);
-                CK(gemm_tn(t, sp, st)); ++nl;
-                for (int d = 0; d < 2; ++d) {
-                    GemmTnArgs r = tn_args(G + d * 512, 1024, H + d * 128, 256, dpk + 65536 + d * 65536, 128, PTi, 512, 128);
-                    r.shift = (d == 0 ? -1 : 1) * (int)m.s_t;
-                    r.tdiv = (pp & 1) ? g.K : 1;
-                    r.tmod = m.len;
-                    CK(gemm_tn(r, sp, st)); ++nl;
+            if (g_backend == 2) {
+                // TMA-fed tcgen05 GEMMs on operand planes for the BiLSTM "feed-forward" (the same kernels as the DPRNN path)
+                const long long plX = g.PT * 64, plH = g.PT * 256, plG = g.PT * 1024;
+                __nv_bfloat16* dYhl = at<__nv_bfloat16>(ws, l.dYhl);
+                __nv_bfloat16* dGhl = at<__nv_bfloat16>(ws, l.dGhl);
+                __nv_bfloat16* Hrh = at<__nv_bfloat16>(ws, l.tHrhl);
+                const __nv_bfloat16* S1hl = at<__nv_bfloat16>(ws, l.S1hl[pp]);
+                const __nv_bfloat16* Hphl = at<__nv_bfloat16>(ws, l.Hphl[pp]);
+                CK(launch_split_rows(dY, 64, dYhl, sp ? dYhl + plX : nullptr, g.PT, 64, 0, st)); ++nl;
+                CK(launch_split_rows(H, 256, Hrh, sp ? Hrh + plH : nullptr, g.PT, 256, 1, st)); ++nl;   // relu(H), recomputed
+                {   // linear2 + ReLU: dH = (dY Wp) where H > 0 ; dWp = dY^T relu(H) (as relu(H)^T dY, stored transposed) ; dbp
+                    TmaGemmArgs a = tma_args(dYhl, plX, 64, v.projt_hi, v.projt_lo, 64, dH, 256, PTi, 256, 64);
+                    a.mask = H; a.ldmask = 256;
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                    TmaWgradArgs t;
+                    memset(&t, 0, sizeof(t));
+                    t.A_hi = Hrh; t.A_lo = Hrh + plH; t.lda = 256; t.Mo = 256;
+                    t.B0_hi = dYhl; t.B0_lo = dYhl + plX; t.ldb0 = 64; t.nb0 = 64;
+                    t.C0 = grads + po[8]; t.ldc0 = 256; t.transpose0 = 1; t.P = PTi; t.scale = 1.f;
+                    CK(launch_gemm_tma_tn(t, sp, st)); ++nl;
+                    CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[9], nullptr, st)); ++nl;
+                }
+                CK(launch_lstm_bwd(v.rec, G, at<float>(ws, l.Cst[pp]), dH, dpk + 65536 + 131072, m, sp, st, dGhl, sp ? dGhl + plG : nullptr)); ++nl;
+                {   // d src (after norm1) = d z2 + dG W_ih (K = 1024)
+                    TmaGemmArgs a = tma_args(dGhl, plG, 1024, v.wiht_hi, v.wiht_lo, 1024, dY, 64, PTi, 64, 1024);
+                    a.accumulate = 1;
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                for (int d = 0; d < 2; ++d) {  // dW_ih = dG^T src and dW_hh = dG^T h_prev from ONE pass over this direction's dG
+                    TmaWgradArgs t;
+                    memset(&t, 0, sizeof(t));
+                    t.A_hi = dGhl + d * 512; t.A_lo = dGhl + plG + d * 512; t.lda = 1024; t.Mo = 512;
+                    t.B0_hi = S1hl; t.B0_lo = S1hl + plX; t.ldb0 = 64; t.nb0 = 64;
+                    t.B1_hi = Hphl + d * 128; t.B1_lo = Hphl + plH + d * 128; t.ldb1 = 256; t.nb1 = 128;
+                    t.C0 = dpk + d * 512 * 64; t.ldc0 = 64;
+                    t.C1 = dpk + 65536 + d * 65536; t.ldc1 = 128;
+                    t.P = PTi; t.scale = 1.f;
+                    CK(launch_gemm_tma_tn(t, sp, st)); ++nl;
+                }
+            } else {
+                {   // linear2 + ReLU
+                    GemmNtArgs a = nt_args(dY, 64, v.projt_hi, v.projt_lo, 64, 0, dH, 256, PTi, 256, 64);
+                    a.mask = H; a.ldmask = 256;
+                    CK(launch_gemm_nt(a, sp, st)); ++nl;
+                    GemmTnArgs t = tn_args(dY, 64, H, 256, grads + po[8], 256, PTi, 64, 256);
+                    t.relu_b = 1;
+                    CK(launch_gemm_tn(t, sp, st)); ++nl;
+                    CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[9], nullptr, st)); ++nl;
+                }
+                CK(launch_lstm_bwd(v.rec, G, at<float>(ws, l.Cst[pp]), dH, dpk + 65536 + 131072, m, sp, st)); ++nl;
+                {   // d src (after norm1) = d z2 + dG W_ih ; LSTM weight gradients
+                    GemmNtArgs a = nt_args(G, 1024, v.wiht_hi, v.wiht_lo, 1024, 0, dY, 64, PTi, 64, 1024);
+                    a.accumulate = 1;
+                    CK(gemm_nt(a, sp, st)); ++nl;
+                    GemmTnArgs t = tn_args(G, 1024, S1, 64, dpk, 64, PTi, 1024, 64);
+                    CK(gemm_tn(t, sp, st)); ++nl;
+                    for (int d = 0; d < 2; ++d) {
+                        GemmTnArgs r = tn_args(G + d * 512, 1024, H + d * 128, 256, dpk + 65536 + d * 65536, 128, PTi, 512, 128);
+                        r.shift = (d == 0 ? -1 : 1) * (int)m.s_t;
+                        r.tdiv = (pp & 1) ? g.K : 1;
+                        r.tmod = m.len;
+                        CK(gemm_tn(r, sp, st)); ++nl;
+                    }
                 }
             }
             // norm1 backward: dY <- d z1 (in place), and the residual branch dXs += d z1
