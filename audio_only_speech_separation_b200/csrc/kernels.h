@@ -192,6 +192,8 @@ cudaError_t launch_unpack_lstm_grads(const float* d_wih_pack /*[1024,64]*/, cons
                                      const float* d_bias_pack /*[1024]*/, float* const d_w_ih[2], float* const d_w_hh[2],
                                      float* const d_b_ih[2], float* const d_b_hh[2], cudaStream_t st);
 // flat fp32 -> bf16 hi/lo (elementwise)
+// fp32 [R, C] -> bf16 hi / lo planes of the transpose [C, R]
+cudaError_t launch_transpose_split(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, int R, int C, cudaStream_t st);
 cudaError_t launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t st);
 
 // ---------------- segmentation / overlap-add (seg_ola.cu) ----------------

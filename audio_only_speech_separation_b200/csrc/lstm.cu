@@ -791,6 +791,25 @@ int lstm_seqs_per_cta(int nseq, int slots) {
 
 namespace {
 
+// fp32 [R, C] row-major -> bf16 hi / lo planes of the TRANSPOSE [C, R] (weights for the input-gradient GEMMs, K-major)
+__global__ void transpose_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int R, int C) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < R && c < C) ? src[(size_t)r * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < C && r < R) {
+            const float v = tile[threadIdx.x][i], vh = bf16_round(v);
+            hi[(size_t)c * R + r] = __float2bfloat16_rn(vh);
+            lo[(size_t)c * R + r] = __float2bfloat16_rn(v - vh);
+        }
+    }
+}
+
 template <typename K>
 cudaError_t set_smem(K kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -919,6 +938,12 @@ cudaError_t launch_unpack_lstm_grads(const float* d_wih_pack, const float* d_whh
     for (int d = 0; d < 2; ++d) { a.w_ih[d] = d_w_ih[d]; a.w_hh[d] = d_w_hh[d]; a.b_ih[d] = d_b_ih[d]; a.b_hh[d] = d_b_hh[d]; }
     int total = 65536 + 131072 + 1024;
     unpack_lstm_grads_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transpose_split(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, int R, int C, cudaStream_t st) {
+    if (R <= 0 || C <= 0) return cudaSuccess;
+    transpose_split_kernel<<<dim3(ceil_div(C, 32), ceil_div(R, 32)), dim3(32, 8), 0, st>>>(src, hi, lo, R, C);
     return cudaGetLastError();
 }
 

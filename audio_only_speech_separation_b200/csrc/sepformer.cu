@@ -92,7 +92,7 @@ int dp_sepformer_last_launches(const dp_sepformer* h) { return h->launches; }
 
 int64_t dp_sepformer_pack_bytes(const dp_sepformer* h) {
     size_t flat = ((size_t)h->n_params * 2 + 255) & ~(size_t)255;
-    return (int64_t)(2 * flat);
+    return (int64_t)(4 * flat);   // [hi | lo | hi of the transposed layer weights | lo of those], each at the parameter's own offset
 }
 int64_t dp_sepformer_workspace_bytes(const dp_sepformer* h, int B, int T) {
     SGeo g;
@@ -105,6 +105,26 @@ int dp_sepformer_pack(dp_sepformer* h, const float* params, void* pack, void* st
     size_t flat = ((size_t)h->n_params * 2 + 255) & ~(size_t)255;
     char* b = static_cast<char*>(pack);
     CK(launch_split_bf16(params, (__nv_bfloat16*)b, (__nv_bfloat16*)(b + flat), h->n_params, S(stream)));
+    // transposed copies of every layer's four weights: the K-major W operand of the input-gradient GEMMs (training, TMA backend)
+    __nv_bfloat16* thi = (__nv_bfloat16*)(b + 2 * flat);
+    __nv_bfloat16* tlo = (__nv_bfloat16*)(b + 3 * flat);
+    const dp_sepformer_config& c = h->cfg;
+    const int N = c.enc_dim;
+    int idx = HEAD;
+    for (int pi = 0; pi < 2 * c.num_blocks; ++pi) {
+        const int path = pi & 1;
+        const int layers = path ? c.inter_layers : c.intra_layers;
+        const int dffn = path ? c.inter_dffn : c.intra_dffn;
+        const int64_t* po = h->off.data() + idx;
+        idx += path_entries(layers);
+        for (int ly = 0; ly < layers; ++ly) {
+            const int64_t* lo = po + 1 + PER_LAYER * ly;
+            CK(launch_transpose_split(params + lo[0], thi + lo[0], tlo + lo[0], 3 * N, N, S(stream)));   // in_proj  [3N, N]
+            CK(launch_transpose_split(params + lo[2], thi + lo[2], tlo + lo[2], N, N, S(stream)));       // out_proj [N, N]
+            CK(launch_transpose_split(params + lo[4], thi + lo[4], tlo + lo[4], dffn, N, S(stream)));    // FFN 1    [dffn, N]
+            CK(launch_transpose_split(params + lo[6], thi + lo[6], tlo + lo[6], N, dffn, S(stream)));    // FFN 2    [N, dffn]
+        }
+    }
     return 0;
 }
 

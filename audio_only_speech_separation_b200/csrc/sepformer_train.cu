@@ -3,6 +3,7 @@
 // (sepformer.py:124-128,261,318-319) are not applied, see models/sepformer.py).  Same data layout and kernels as the inference
 // engine (sepformer.cu); the contractions run on the mma.sync GEMMs on fp32 operands (bf16x3 in fp32-parity mode), attention
 // forward/backward on the exact streaming-softmax kernels, so every tensor the backward reads is saved in fp32.
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -17,7 +18,7 @@ using namespace dp;
 
 namespace {
 
-struct TLayer { size_t Rin, U1, QKV, LSE, Oa, Rmid, U2, Hf; };
+struct TLayer { size_t Rin, U1, QKV, LSE, Oa, Rmid, U2, Hf, U1hl, Oahl, U2hl, Hfhl; };
 struct TPath { size_t Rfin, Uf, mr; int first_layer, layers; };
 struct TLayout {
     size_t xp, E, En, Fb, statsE, mrE, stats;
@@ -27,6 +28,7 @@ struct TLayout {
     size_t Upre, F2, Zs, T1, T2, Gt, Mk, Mx, D;
     // backward scratch
     size_t dX, dR, dU, dHf, dOa, dQKV, dD, dMx, dMk, dE, dGt, dA, dB, dZs, dF2, dEn, red;
+    size_t QKVhl, dRhl, dHfhl, dQKVhl;   // operand planes (hi | lo) shared by all layers (TMA backend)
     size_t total;
 };
 
@@ -64,6 +66,11 @@ void train_layout(const dp_sepformer* h, const SGeo& g, TLayout& l) {
             t.Rmid = c.take(g.PT * N * f);
             t.U2 = c.take(g.PT * N * f);
             t.Hf = c.take(g.PT * dffn * f);
+            // operand planes (hi | lo) of what the backward's weight-gradient GEMMs read (TMA backend)
+            t.U1hl = c.take(g.PT * N * 4);
+            t.Oahl = c.take(g.PT * N * 4);
+            t.U2hl = c.take(g.PT * N * 4);
+            t.Hfhl = c.take(g.PT * dffn * 4);
             l.layer.push_back(t);
         }
         l.path[p].Rfin = c.take(g.PT * N * f);
@@ -96,6 +103,10 @@ void train_layout(const dp_sepformer* h, const SGeo& g, TLayout& l) {
     l.dF2 = c.take(g.BL * N * f);
     l.dEn = c.take(g.BL * N * f);
     l.red = c.take(2 * g.B * sizeof(double));
+    l.QKVhl = c.take(g.PT * 3 * N * 4);
+    l.dRhl = c.take(g.PT * N * 4);
+    l.dHfhl = c.take(g.PT * dmax * 4);
+    l.dQKVhl = c.take(g.PT * 3 * N * 4);
     l.total = c.off;
 }
 
@@ -105,6 +116,10 @@ SeqMap seq_map(const SGeo& g, int B, int path) {
     else       { m.nseq = B * g.K; m.len = g.Sc; m.qdiv = g.K; m.s_hi = (long long)g.Sc * g.K; m.s_lo = 1; m.s_t = g.K; }
     return m;
 }
+
+// TMA-fed tcgen05 GEMMs for a path's layers (forward and backward must agree: they exchange operand planes): the weight-gradient
+// kernel wants its output rows in blocks of 128 and at most 256 output columns
+bool train_tma(int N, int dffn) { return gemm_backend() == 2 && N % 128 == 0 && N <= 256 && dffn % 128 == 0; }
 
 int check_trainable(const dp_sepformer* h) {
     if (!h->cfg.intra_norm_before || !h->cfg.inter_norm_before)
@@ -176,6 +191,10 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
         idx += path_entries(layers);
         const SeqMap m = seq_map(g, B, path);
         const TPath& tp = l.path[pi];
+        const bool tma = train_tma(N, dffn);
+        LstmFusedGeom gm;
+        gm.inter = path; gm.len = m.len; gm.nseq = m.nseq; gm.K = g.K; gm.S = g.Sc; gm.B = B;
+        const bool tc_attn = tma && attn_tc5_supported(N, heads, gm);
         float* Xin = at<float>(ws, l.X[pi]);
         float* R0 = at<float>(ws, l.layer[tp.first_layer].Rin);
         if (use_pe) {
@@ -196,6 +215,48 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
             float* U2 = at<float>(ws, t.U2);
             float* Hf = at<float>(ws, t.Hf);
             float* Rout = (ly + 1 < layers) ? at<float>(ws, l.layer[tp.first_layer + ly + 1].Rin) : at<float>(ws, tp.Rfin);
+            if (tma) {
+                // TMA-fed tcgen05 GEMMs on operand planes (the inference engine's layer), keeping in fp32 only what the backward reads in
+                // fp32 (Rin, QKV, O, LSE, Rmid, the FFN hidden as the ReLU mask) and as planes what its weight-gradient GEMMs read
+                const long long pN = g.PT * N, pD = g.PT * dffn, pQ = g.PT * 3 * N;
+                __nv_bfloat16* U1h = at<__nv_bfloat16>(ws, t.U1hl);
+                __nv_bfloat16* Oh = at<__nv_bfloat16>(ws, t.Oahl);
+                __nv_bfloat16* U2h = at<__nv_bfloat16>(ws, t.U2hl);
+                __nv_bfloat16* Hh = at<__nv_bfloat16>(ws, t.Hfhl);
+                __nv_bfloat16* Qh = at<__nv_bfloat16>(ws, l.QKVhl);
+                CK(launch_add_ln(Rin, nullptr, nullptr, nullptr, nullptr, params + lo[8], params + lo[9], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st,
+                                 U1h, sp ? U1h + pN : nullptr)); ++nl;
+                {
+                    TmaGemmArgs a = tma_nt_args(U1h, sp ? U1h + pN : nullptr, N, whi + lo[0], wlo + lo[0], N, QKV, 3 * N, PTi, 3 * N, N);
+                    if (tc_attn) { a.C_hi = Qh; a.C_lo = sp ? Qh + pQ : nullptr; a.ldch = 3 * N; }
+                    a.bias = params + lo[1];
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                if (tc_attn) {
+                    CK(launch_attn_fwd_tc5(Qh, sp ? Qh + pQ : nullptr, Oa, Oh, sp ? Oh + pN : nullptr, at<float>(ws, t.LSE), N, heads, gm, sp, st)); ++nl;
+                } else {
+                    CK(launch_attn_fwd(QKV, Oa, at<float>(ws, t.LSE), N, heads, m, st, Oh, sp ? Oh + pN : nullptr)); ++nl;
+                }
+                {   // Rmid = Rin + O W_o^T + b_o
+                    TmaGemmArgs a = tma_nt_args(Oh, sp ? Oh + pN : nullptr, N, whi + lo[2], wlo + lo[2], N, Rmid, N, PTi, N, N);
+                    a.bias = params + lo[3]; a.accumulate = 1; a.Cin = Rin;
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                CK(launch_add_ln(Rmid, nullptr, nullptr, nullptr, nullptr, params + lo[10], params + lo[11], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st,
+                                 U2h, sp ? U2h + pN : nullptr)); ++nl;
+                {
+                    TmaGemmArgs a = tma_nt_args(U2h, sp ? U2h + pN : nullptr, N, whi + lo[4], wlo + lo[4], N, Hf, dffn, PTi, dffn, N);
+                    a.C_hi = Hh; a.C_lo = sp ? Hh + pD : nullptr; a.ldch = dffn;
+                    a.bias = params + lo[5]; a.act = 1;
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                {   // Rout = Rmid + Hf W_2^T + b_2
+                    TmaGemmArgs a = tma_nt_args(Hh, sp ? Hh + pD : nullptr, dffn, whi + lo[6], wlo + lo[6], dffn, Rout, N, PTi, N, dffn);
+                    a.bias = params + lo[7]; a.accumulate = 1; a.Cin = Rmid;
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                continue;
+            }
             CK(launch_add_ln(Rin, nullptr, nullptr, U1, nullptr, params + lo[8], params + lo[9], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st)); ++nl;
             {
                 GemmNtArgs a = nt_args(U1, N, whi + lo[0], wlo + lo[0], N, 0, QKV, 3 * N, PTi, 3 * N, N);
@@ -283,6 +344,8 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
     const size_t flat = ((size_t)h->n_params * 2 + 255) & ~(size_t)255;
     const __nv_bfloat16* whi = reinterpret_cast<const __nv_bfloat16*>(pack);
     const __nv_bfloat16* wlo = reinterpret_cast<const __nv_bfloat16*>(static_cast<const char*>(pack) + flat);
+    const __nv_bfloat16* thi = reinterpret_cast<const __nv_bfloat16*>(static_cast<const char*>(pack) + 2 * flat);   // transposed layer weights
+    const __nv_bfloat16* tlo = reinterpret_cast<const __nv_bfloat16*>(static_cast<const char*>(pack) + 3 * flat);
     const int PTi = (int)g.PT, BLi = (int)g.BL, rows = BLi * spk;
     const long long nPN = g.PT * N;
     int nl = 0;
@@ -370,6 +433,7 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
         const int64_t* fo = po + 1 + PER_LAYER * layers;
         const SeqMap m = seq_map(g, B, path);
         const TPath& tp = l.path[pi];
+        const bool tma = train_tma(N, dffn);
         float* Uf = at<float>(ws, tp.Uf);
         float* mr = at<float>(ws, tp.mr);
         // X_out = Xin + gLN(Uf): gLN backward -> dU (d Uf); the residual branch keeps dX
@@ -381,6 +445,63 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
         for (int ly = layers - 1; ly >= 0; --ly) {
             const int64_t* lo = po + 1 + PER_LAYER * ly;
             const TLayer& t = l.layer[tp.first_layer + ly];
+            if (tma) {
+                const long long pN = g.PT * N, pD = g.PT * dffn, pQ = g.PT * 3 * N;
+                float* Hfm = at<float>(ws, t.Hf);
+                const __nv_bfloat16* U1h = at<__nv_bfloat16>(ws, t.U1hl);
+                const __nv_bfloat16* Oh = at<__nv_bfloat16>(ws, t.Oahl);
+                const __nv_bfloat16* U2h = at<__nv_bfloat16>(ws, t.U2hl);
+                const __nv_bfloat16* Hh = at<__nv_bfloat16>(ws, t.Hfhl);
+                __nv_bfloat16* dRh = at<__nv_bfloat16>(ws, l.dRhl);
+                __nv_bfloat16* dHh = at<__nv_bfloat16>(ws, l.dHfhl);
+                __nv_bfloat16* dQh = at<__nv_bfloat16>(ws, l.dQKVhl);
+                auto wgrad = [&](const __nv_bfloat16* A, long long plA, int lda, int Mo, const __nv_bfloat16* Bm, long long plB, int ldb, int nb,
+                                 float* C, int ldc, int transpose) {
+                    TmaWgradArgs w;
+                    memset(&w, 0, sizeof(w));
+                    w.A_hi = A; w.A_lo = A + plA; w.lda = lda; w.Mo = Mo;
+                    w.B0_hi = Bm; w.B0_lo = Bm + plB; w.ldb0 = ldb; w.nb0 = nb;
+                    w.C0 = C; w.ldc0 = ldc; w.transpose0 = transpose; w.P = PTi; w.scale = 1.f;
+                    return launch_gemm_tma_tn(w, sp, st);
+                };
+                // FFN: out = Rmid + relu(U2 W1^T + b1) W2^T + b2
+                CK(launch_split_rows(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, 0, st)); ++nl;
+                {   // dHf = (dR W2) where Hf > 0, as fp32 (bias gradient) and planes
+                    TmaGemmArgs a = tma_nt_args(dRh, sp ? dRh + pN : nullptr, N, thi + lo[6], tlo + lo[6], N, dHf, dffn, PTi, dffn, N);
+                    a.C_hi = dHh; a.C_lo = sp ? dHh + pD : nullptr; a.ldch = dffn;
+                    a.mask = Hfm; a.ldmask = dffn;
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                CK(wgrad(Hh, pD, dffn, dffn, dRh, pN, N, N, grads + lo[6], dffn, 1)); ++nl;          // dW2 = dR^T Hf, as Hf^T dR stored transposed
+                CK(launch_colsum_any(dR, N, PTi, N, 1.f, grads + lo[7], st)); ++nl;
+                {
+                    TmaGemmArgs a = tma_nt_args(dHh, sp ? dHh + pD : nullptr, dffn, thi + lo[4], tlo + lo[4], dffn, dU, N, PTi, N, dffn);
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                CK(wgrad(dHh, pD, dffn, dffn, U2h, pN, N, N, grads + lo[4], N, 0)); ++nl;             // dW1 = dHf^T U2
+                CK(launch_colsum_any(dHf, dffn, PTi, dffn, 1.f, grads + lo[5], st)); ++nl;
+                // LayerNorm 2 (input Rmid): dR += d Rmid
+                CK(launch_ln_bwd(dU, at<float>(ws, t.Rmid), dU, dR, params + lo[10], g.PT, N, 1e-6f, grads + lo[10], grads + lo[11], st)); ++nl;
+                // attention branch: Rmid = Rin + attn(U1) W_o^T + b_o
+                CK(launch_split_rows(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, 0, st)); ++nl;
+                {
+                    TmaGemmArgs a = tma_nt_args(dRh, sp ? dRh + pN : nullptr, N, thi + lo[2], tlo + lo[2], N, dOa, N, PTi, N, N);
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                CK(wgrad(dRh, pN, N, N, Oh, pN, N, N, grads + lo[2], N, 0)); ++nl;                      // dWo = dR^T O
+                CK(launch_colsum_any(dR, N, PTi, N, 1.f, grads + lo[3], st)); ++nl;
+                CK(launch_attn_bwd(at<float>(ws, t.QKV), at<float>(ws, t.Oa), at<float>(ws, t.LSE), dOa, dQKV, N, heads, m, st)); ++nl;
+                CK(launch_split_rows(dQKV, 3 * N, dQh, sp ? dQh + pQ : nullptr, g.PT, 3 * N, 0, st)); ++nl;
+                {
+                    TmaGemmArgs a = tma_nt_args(dQh, sp ? dQh + pQ : nullptr, 3 * N, thi + lo[0], tlo + lo[0], 3 * N, dU, N, PTi, N, 3 * N);
+                    CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                CK(wgrad(dQh, pQ, 3 * N, 3 * N, U1h, pN, N, N, grads + lo[0], N, 0)); ++nl;            // dWin = dQKV^T U1
+                CK(launch_colsum_any(dQKV, 3 * N, PTi, 3 * N, 1.f, grads + lo[1], st)); ++nl;
+                // LayerNorm 1 (input Rin): dR += d Rin
+                CK(launch_ln_bwd(dU, at<float>(ws, t.Rin), dU, dR, params + lo[8], g.PT, N, 1e-6f, grads + lo[8], grads + lo[9], st)); ++nl;
+                continue;
+            }
             float* Hf = at<float>(ws, t.Hf);
             // FFN: out = Rmid + relu(U2 W1^T + b1) W2^T + b2
             {

@@ -156,3 +156,60 @@ def test_training_batch2_and_optimizer_step(manifest):
         losses.append(loss.item())
     assert losses[-1] < losses[0]
     assert m._flat_is_valid(x.device)
+
+
+def test_training_tma_path_gradients_match_oracle():
+    """enc_dim = 128 / d_ffn = 256 layers run the training forward and backward on the TMA-fed tcgen05 GEMMs (operand planes,
+    transposed weight planes, tcgen05 attention forward): loss and gradients against autograd through the oracle and against the
+    mma.sync engine (dp_set_gemm_backend(0)) on the same weights."""
+    from audio_only_speech_separation_b200 import _lib
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+    from audio_only_speech_separation_b200.models import Sepformer
+
+    cfg = dict(encoder_out_nchannels=128, intra_dffn=256, inter_dffn=256, intra_nhead=4, inter_nhead=4, intra_numlayers=2, inter_numlayers=1,
+               masknet_chunksize=50, masknet_numlayers=1)
+    torch.manual_seed(5)
+    m = Sepformer(sample_rate=8000, **cfg)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda().train()
+    m.dropout = 0.0
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 2400, generator=g) * 0.1
+    tgt = torch.randn(2, 2, 2400, generator=g) * 0.1
+    leaf = {k: v.clone().requires_grad_(not k.endswith("pos_enc.pe")) for k, v in sd.items()}
+    ref_loss = O.pit_loss(SO.sepformer_forward(leaf, x, **cfg), tgt, "snr", False)
+    ref_loss.backward()
+    lossf = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)
+
+    def run(backend):
+        _lib.check(_lib.lib().dp_set_gemm_backend(backend))
+        try:
+            for p in m.parameters():
+                p.grad = None
+            loss = lossf(m(x.cuda()), tgt.cuda())
+            loss.backward()
+            return loss.item(), {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+        finally:
+            _lib.check(_lib.lib().dp_set_gemm_backend(2))
+
+    loss_t, gt = run(2)
+    loss_m, gm = run(0)
+    assert abs(loss_t - ref_loss.item()) < 1e-4 * max(1.0, abs(ref_loss.item()))
+    assert abs(loss_t - loss_m) < 1e-4 * max(1.0, abs(loss_m))
+
+    def summary(grads):
+        errs = sorted(rel_l2(grads[k], leaf[k].grad) for k in grads)
+        num = sum(float((grads[k].cpu().double() - leaf[k].grad.double()).pow(2).sum()) for k in grads)
+        den = sum(float(leaf[k].grad.double().pow(2).sum()) for k in grads)
+        return errs[len(errs) // 2], (num / den) ** 0.5, errs[-1]
+
+    med_t, tot_t, worst_t = summary(gt)
+    med_m, tot_m, worst_m = summary(gm)
+    record("sepformer_grads_tma", median=med_t, total=tot_t, worst=worst_t, median_mma=med_m, total_mma=tot_m, worst_mma=worst_m)
+    assert med_t < 1e-4 and tot_t < 5e-3 and worst_t < 5e-2    # same ReLU-flip conditioning as the tests above
+    # bf16 mode: runs, finite, close to the fp32 loss
+    m.precision = "bf16"
+    loss_b, gb = run(2)
+    m.precision = "fp32"
+    assert abs(loss_b - loss_t) < 5e-2 * max(1.0, abs(loss_t))
+    assert all(torch.isfinite(v).all() for v in gb.values())
