@@ -351,3 +351,58 @@ def test_adam_clip_matches_oracle():
                                       stream_ptr()))
         assert abs(float(norm2.sqrt()) - total) < 1e-4 * total
         assert torch.allclose(p.cpu(), p_ref[0], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------- torch.library operators (dualpath::)
+def test_torch_library_ops_forward_and_autograd():
+    """torch.ops.dualpath.*: values equal the plain operator functions; registered backwards against torch autograd references."""
+    from audio_only_speech_separation_b200 import torch_ops  # noqa: F401  (registers the operators)
+
+    g = torch.Generator().manual_seed(3)
+    # segmentation / overlap-add: bit-exact forward, and each is the other's adjoint: <seg(x), y> == <x, ola(y)>
+    x = torch.randn(2, 8, 1003, generator=g).cuda().requires_grad_(True)
+    y = torch.ops.dualpath.segment(x, 50)
+    ref, rest = O.split_feature(x.detach().cpu(), 50)
+    assert torch.equal(y.detach().cpu(), ref)
+    w = torch.randn(*y.shape, generator=g).cuda()
+    (y * w).sum().backward()
+    assert torch.equal(x.grad.cpu(), O.merge_feature(w.cpu(), rest))
+    wl = w.clone().requires_grad_(True)
+    z = torch.ops.dualpath.overlap_add(wl, rest)
+    v = torch.randn(*z.shape, generator=g).cuda()
+    (z * v).sum().backward()
+    assert torch.equal(wl.grad.cpu(), O.split_feature(v.cpu(), 50)[0])
+    # attention core against torch SDPA (fp32 math), forward and gradient
+    B, S, K, E, H = 1, 5, 37, 64, 4
+    qkv = (torch.randn(B, S, K, 3 * E, generator=g) * 0.5).cuda().requires_grad_(True)
+    o, _ = torch.ops.dualpath.attention(qkv, H, "intra")
+    go = torch.randn(B, S, K, E, generator=g).cuda()
+    (o * go).sum().backward()
+    q2 = qkv.detach().double().cpu().requires_grad_(True)
+    q, k, vv = (t.reshape(B * S, K, H, E // H).transpose(1, 2) for t in q2.split(E, dim=-1))
+    ro = torch.nn.functional.scaled_dot_product_attention(q, k, vv).transpose(1, 2).reshape(B, S, K, E)
+    (ro * go.double().cpu()).sum().backward()
+    assert rel_l2(o.detach(), ro.detach()) < 1e-5 and rel_l2(qkv.grad, q2.grad) < 1e-5
+    # residual add + LayerNorm
+    a = torch.randn(300, 64, generator=g).cuda().requires_grad_(True)
+    b = torch.randn(300, 64, generator=g).cuda().requires_grad_(True)
+    gam = (1 + 0.1 * torch.randn(64, generator=g)).cuda().requires_grad_(True)
+    bet = (0.1 * torch.randn(64, generator=g)).cuda().requires_grad_(True)
+    out, _ = torch.ops.dualpath.add_layernorm(a, b, gam, bet, 1e-5)
+    gout = torch.randn(300, 64, generator=g).cuda()
+    (out * gout).sum().backward()
+    a2, b2, g2, be2 = (t.detach().double().cpu().requires_grad_(True) for t in (a, b, gam, bet))
+    r = torch.nn.functional.layer_norm(a2 + b2, (64,), g2, be2, 1e-5)
+    (r * gout.double().cpu()).sum().backward()
+    assert rel_l2(out.detach(), r.detach()) < 1e-5
+    for got, want in ((a.grad, a2.grad), (b.grad, b2.grad), (gam.grad, g2.grad), (bet.grad, be2.grad)):
+        assert rel_l2(got, want) < 1e-5
+    # fused PIT loss against the oracle, with gradient
+    est = (torch.randn(3, 2, 2000, generator=g) * 0.1).cuda().requires_grad_(True)
+    tgt = (torch.randn(3, 2, 2000, generator=g) * 0.1).cuda()
+    loss, perm, _ = torch.ops.dualpath.pit_sdr_loss(est, tgt, "sisdr", False)
+    loss.backward()
+    e2 = est.detach().cpu().requires_grad_(True)
+    rl = O.pit_loss(e2, tgt.cpu(), "sisdr", False)
+    rl.backward()
+    assert abs(loss.item() - rl.item()) < 1e-4 * max(1.0, abs(rl.item())) and rel_l2(est.grad, e2.grad) < 1e-4

@@ -138,3 +138,25 @@ def test_shard_range_partitions_batch():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+def test_torch_library_operators_registered():
+    """dualpath:: custom operators (SURVEY 8b): schemas exist, fake (meta) shapes follow the reference, CUDA dispatch key only."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    from audio_only_speech_separation_b200 import torch_ops
+
+    for name in torch_ops.OP_NAMES:
+        assert hasattr(torch.ops.dualpath, name), name
+    assert "Tensor x, SymInt block_size" in str(torch.ops.dualpath.segment.default._schema)
+    with FakeTensorMode():
+        x = torch.empty(2, 64, 4002, device="cuda")
+        y = torch.ops.dualpath.segment(x, 100)
+        assert tuple(y.shape) == (2, 64, 100, O.num_chunks(4002, 100))
+        assert tuple(torch.ops.dualpath.overlap_add(y, O.seg_rest(4002, 100)).shape) == (2, 64, 4002)
+        o, lse = torch.ops.dualpath.attention(torch.empty(1, 82, 100, 192, device="cuda"), 4, "intra")
+        assert tuple(o.shape) == (1, 82, 100, 64) and tuple(lse.shape) == (8200, 4)
+        loss, perm, _ = torch.ops.dualpath.pit_sdr_loss(torch.empty(4, 2, 800, device="cuda"), torch.empty(4, 2, 800, device="cuda"), "snr", False)
+        assert loss.ndim == 0 and tuple(perm.shape) == (4,)
+    with pytest.raises(NotImplementedError):   # no CPU kernel is registered
+        torch.ops.dualpath.segment(torch.zeros(1, 4, 100), 10)
