@@ -63,6 +63,7 @@ PROTOTYPES = {
     "dp_groupnorm_residual_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),
     "dp_attention_forward_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _p]),
     "dp_attention_backward_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _p]),
+    "dp_attention_backward_tc_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "dp_attention_forward_planes_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "dp_add_layernorm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _p]),
     "dp_layernorm_backward_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _f, _p, _p, _p]),

@@ -307,6 +307,13 @@ int dp_attention_forward_f32(const float* qkv, float* o, float* lse, int E, int 
     CK(launch_attn_fwd(qkv, o, lse, E, heads, m, S(stream)));
     return 0;
 }
+int dp_attention_backward_tc_f32(const float* qkv, const float* o, const float* lse, const float* d_o, float* d_qkv, int E, int heads, int nseq,
+                                 int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int precision, void* stream) {
+    SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
+    if (!attn_bwd_mma_supported(E, heads, m)) return fail("dp_attention_backward_tc_f32: head width E/heads must be 16 or 32 and the sequence length <= 256");
+    CK(launch_attn_bwd_mma(qkv, o, lse, d_o, d_qkv, E, heads, m, is_split(precision), S(stream)));
+    return 0;
+}
 int dp_attention_backward_f32(const float* qkv, const float* o, const float* lse, const float* d_o, float* d_qkv, int E, int heads, int nseq,
                               int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, void* stream) {
     if (heads <= 0 || E % heads || (E / heads != 16 && E / heads != 32)) return fail("dp_attention_backward_f32: head width E/heads must be 16 or 32");
@@ -1008,7 +1015,11 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
                 CK(launch_gemm_tn(t, sp, st)); ++nl;
                 CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[15], nullptr, st)); ++nl;
             }
-            CK(launch_attn_bwd(QKV, Oa, at<float>(ws, l.LSE[pp]), dOa, dQKV, 64, 4, m, st)); ++nl;
+            if (g_backend == 2 && attn_bwd_mma_supported(64, 4, m)) {
+                CK(launch_attn_bwd_mma(QKV, Oa, at<float>(ws, l.LSE[pp]), dOa, dQKV, 64, 4, m, sp, st)); ++nl;
+            } else {
+                CK(launch_attn_bwd(QKV, Oa, at<float>(ws, l.LSE[pp]), dOa, dQKV, 64, 4, m, st)); ++nl;
+            }
             {   // in_proj
                 GemmNtArgs a = nt_args(dQKV, 192, whi + po[12], wlo + po[12], 64, 1, dXs, 64, PTi, 64, 192);
                 a.accumulate = 1;

@@ -251,6 +251,11 @@ cudaError_t launch_attn_bwd(const float* QKV, const float* O, const float* LSE, 
 // The same attention on tcgen05 (attention_tc5.cu): QKV given as bf16 hi/lo planes [P,3E] (what the QKV GEMM writes), TMA-fed;
 // S and P live in tensor memory.  Sequences up to 256 long; geometry as for the fused LSTM kernel (gm.nseq sequences).
 bool attn_tc5_supported(int E, int heads, const LstmFusedGeom& gm);
+// attention backward on the warp-level tensor cores (attention_bwd_mma.cu): sequences <= 256, head width 16 / 32;
+// split = bf16x3 products (fp32-parity mode), otherwise single bf16 products.  Same arguments as launch_attn_bwd.
+bool attn_bwd_mma_supported(int E, int heads, const SeqMap& m);
+cudaError_t launch_attn_bwd_mma(const float* QKV, const float* O, const float* LSE, const float* dO, float* dQKV, int E, int heads,
+                                const SeqMap& m, bool split, cudaStream_t st);
 cudaError_t launch_attn_fwd_tc5(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, float* O, __nv_bfloat16* O_hi, __nv_bfloat16* O_lo,
                                 float* LSE, int E, int heads, const LstmFusedGeom& gm, bool split, cudaStream_t st);
 // z = a (+ b) [-> zout]; out = (res ? res : 0) + LayerNorm_E(z) * gamma + beta; then optional unfold affine + PReLU.

@@ -490,7 +490,11 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
                 }
                 CK(wgrad(dRh, pN, N, N, Oh, pN, N, N, grads + lo[2], N, 0)); ++nl;                      // dWo = dR^T O
                 CK(launch_colsum_any(dR, N, PTi, N, 1.f, grads + lo[3], st)); ++nl;
-                CK(launch_attn_bwd(at<float>(ws, t.QKV), at<float>(ws, t.Oa), at<float>(ws, t.LSE), dOa, dQKV, N, heads, m, st)); ++nl;
+                if (attn_bwd_mma_supported(N, heads, m)) {
+                    CK(launch_attn_bwd_mma(at<float>(ws, t.QKV), at<float>(ws, t.Oa), at<float>(ws, t.LSE), dOa, dQKV, N, heads, m, sp, st)); ++nl;
+                } else {
+                    CK(launch_attn_bwd(at<float>(ws, t.QKV), at<float>(ws, t.Oa), at<float>(ws, t.LSE), dOa, dQKV, N, heads, m, st)); ++nl;
+                }
                 CK(launch_split_rows(dQKV, 3 * N, dQh, sp ? dQh + pQ : nullptr, g.PT, 3 * N, 0, st)); ++nl;
                 {
                     TmaGemmArgs a = tma_nt_args(dQh, sp ? dQh + pQ : nullptr, 3 * N, thi + lo[0], tlo + lo[0], 3 * N, dU, N, PTi, N, 3 * N);

@@ -232,11 +232,17 @@ def attention(qkv: torch.Tensor, heads: int, layout: str, *, save=False):
     return o, lse
 
 
-def attention_backward(qkv, o, lse, d_o, heads: int, layout: str):
+def attention_backward(qkv, o, lse, d_o, heads: int, layout: str, *, tensor_cores=False, precision="fp32"):
+    """Backward of :func:`attention` from the saved log-sum-exp.  ``tensor_cores``: the mma.sync kernel the engines use
+    (sequences <= 256; bf16x3 products in fp32 mode), otherwise the exact fp32 CUDA-core kernel."""
     require_cuda(d_o, "d_o")
     B, S, K, E3 = qkv.shape
     d_qkv = torch.empty_like(qkv)
     nseq, ln, qdiv, s_hi, s_lo, s_t = _seq_map(layout, B, S, K)
+    if tensor_cores:
+        check(lib().dp_attention_backward_tc_f32(ptr(qkv), ptr(o), ptr(lse), ptr(d_o), ptr(d_qkv), E3 // 3, heads, nseq, ln, qdiv, s_hi, s_lo,
+                                                 s_t, _prec(precision), stream_ptr()), "dp_attention_backward_tc_f32")
+        return d_qkv
     check(lib().dp_attention_backward_f32(ptr(qkv), ptr(o), ptr(lse), ptr(d_o), ptr(d_qkv), E3 // 3, heads, nseq, ln, qdiv, s_hi, s_lo, s_t,
                                           stream_ptr()), "dp_attention_backward_f32")
     return d_qkv

@@ -205,6 +205,34 @@ def test_attention_forward_backward_vs_torch(E, heads, B, S, K, layout):
     assert e_f < 1e-5 and e_b < 1e-5
 
 
+@pytest.mark.parametrize("E,heads,B,S,K", [(64, 4, 2, 6, 100), (64, 4, 1, 82, 10), (64, 4, 1, 3, 1), (256, 8, 1, 5, 250), (256, 8, 1, 130, 3),
+                                           (256, 8, 1, 3, 256), (128, 4, 2, 7, 65)])
+@pytest.mark.parametrize("layout", ["intra", "inter"])
+def test_attention_backward_tensor_cores_vs_torch(E, heads, B, S, K, layout):
+    """The mma.sync attention backward the engines use (probabilities recomputed from the saved log-sum-exp, bf16x3 products) against
+    fp64 autograd through torch, on ragged lengths (1, 3, 65, 130, 250, 256) and both head widths; bf16 mode within its budget."""
+    from audio_only_speech_separation_b200 import ops
+
+    if (layout == "intra" and K > 256) or (layout == "inter" and S > 256):
+        pytest.skip("tensor-core backward covers sequences up to 256")
+    g = torch.Generator().manual_seed(E + S + K)
+    qkv = torch.randn(B, S, K, 3 * E, generator=g)
+    d_o = torch.randn(B, S, K, E, generator=g)
+    ref_in = qkv.double().requires_grad_(True)
+    if layout == "intra":
+        ref = _torch_mha_core(ref_in.reshape(B * S, K, 3 * E), heads).reshape(B, S, K, E)
+    else:
+        ref = _torch_mha_core(ref_in.permute(0, 2, 1, 3).reshape(B * K, S, 3 * E), heads).reshape(B, K, S, E).permute(0, 2, 1, 3)
+    ref.backward(d_o.double())
+    o, lse = ops.attention(qkv.cuda(), heads, layout, save=True)
+    exact = ops.attention_backward(qkv.cuda(), o, lse, d_o.cuda(), heads, layout)
+    dq = ops.attention_backward(qkv.cuda(), o, lse, d_o.cuda(), heads, layout, tensor_cores=True)
+    dq16 = ops.attention_backward(qkv.cuda(), o, lse, d_o.cuda(), heads, layout, tensor_cores=True, precision="bf16")
+    e32, e16, ex = rel_l2(dq, ref_in.grad), rel_l2(dq16, ref_in.grad), rel_l2(exact, ref_in.grad)
+    record("attention_bwd_tc", E=E, heads=heads, S=S, K=K, layout=layout, fp32=e32, bf16=e16, exact_kernel=ex)
+    assert e32 < 3e-5 and e16 < 2e-2
+
+
 @pytest.mark.parametrize("E,rows", [(64, 1), (64, 777), (128, 50), (256, 1001)])
 def test_add_layernorm_forward_backward_vs_torch(E, rows):
     from audio_only_speech_separation_b200 import ops
