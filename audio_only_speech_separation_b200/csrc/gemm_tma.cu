@@ -190,6 +190,20 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                             v[j + 2] = o.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = o.w > 0.f ? v[j + 3] : 0.f;
                         }
                     }
+                    if (p.mask_hi) {
+                        const uint4* mk = reinterpret_cast<const uint4*>(p.mask_hi + (size_t)row * p.ldmask_hi + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 o = mk[j];
+                            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {   // bf16 > 0  <=>  sign bit clear and not (+-)zero
+                                const uint32_t lo16 = w[t] & 0xffffu, hi16 = w[t] >> 16;
+                                if (lo16 == 0u || lo16 >= 0x8000u) v[8 * j + 2 * t] = 0.f;
+                                if (hi16 == 0u || hi16 >= 0x8000u) v[8 * j + 2 * t + 1] = 0.f;
+                            }
+                        }
+                    }
                     if (dst && !tma_store) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -323,6 +337,7 @@ bool gemm_tma_nt_supported(const TmaGemmArgs& a) {
     if ((a.lda & 7) || (a.ldw & 7)) return false;
     if (a.C && (a.ldc & 3)) return false;
     if (a.C_hi && (a.ldch & 7)) return false;
+    if (a.mask_hi && (a.ldmask_hi & 7)) return false;
     if ((a.accumulate || a.mul_c) && !a.C) return false;
     if (!a.C && !a.C_hi) return false;
     return encode_fn() != nullptr;
@@ -538,7 +553,122 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float4* __restric
         if (lo) lo[i] = l;
     }
 }
+// column sums of a pair of planes: thread = (8-column group, row lane)
+__global__ void __launch_bounds__(256) colsum_planes_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo, long long rows, int C8,
+                                                            float* __restrict__ out, int rows_per_cta) {
+    __shared__ float sh[256][9];
+    const int lanes = 256 / C8;
+    const int c = threadIdx.x % C8, rl = threadIdx.x / C8;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    auto add = [&](const uint4& v) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            acc[2 * t] += __uint_as_float(w[t] << 16);
+            acc[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+        }
+    };
+    if (rl < lanes) {
+        long long r = r0 + rl;
+        if (lo) {
+            for (; r + 3 * lanes < r1; r += 4 * lanes) {   // eight independent 128-bit loads in flight per thread
+                const uint4 a0 = hi[r * C8 + c], a1 = hi[(r + lanes) * C8 + c], a2 = hi[(r + 2 * lanes) * C8 + c], a3 = hi[(r + 3 * lanes) * C8 + c];
+                const uint4 b0 = lo[r * C8 + c], b1 = lo[(r + lanes) * C8 + c], b2 = lo[(r + 2 * lanes) * C8 + c], b3 = lo[(r + 3 * lanes) * C8 + c];
+                add(a0); add(a1); add(a2); add(a3); add(b0); add(b1); add(b2); add(b3);
+            }
+        } else {
+            for (; r + 7 * lanes < r1; r += 8 * lanes) {
+                uint4 a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = hi[(r + u * lanes) * C8 + c];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) add(a[u]);
+            }
+        }
+        for (; r < r1; r += lanes) {
+            add(hi[r * C8 + c]);
+            if (lo) add(lo[r * C8 + c]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sh[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < C8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float t = 0.f;
+            for (int l = 0; l < lanes; ++l) t += sh[l * C8 + threadIdx.x][i];
+            atomicAdd(out + (size_t)threadIdx.x * 8 + i, t);
+        }
+    }
+}
+
+// planes + column sums of the same rows in one pass (bias gradients of the layers whose output gradient is split anyway):
+// thread = (float4 column, row lane); a CTA walks a contiguous row range and adds its partial sums with one atomic per column
+__global__ void __launch_bounds__(256) split_rows_colsum_kernel(const float4* __restrict__ src, long long ld4, uint2* __restrict__ hi,
+                                                                uint2* __restrict__ lo, long long rows, int C4, float* __restrict__ colsum,
+                                                                int rows_per_cta) {
+    __shared__ float4 sh[256];
+    const int lanes = 256 / C4;
+    const int c = threadIdx.x % C4, rl = threadIdx.x / C4;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < lanes) {
+        auto emit = [&](long long r, const float4& v) {
+            uint2 h, l;
+            split_pair(v.x, v.y, h.x, l.x);
+            split_pair(v.z, v.w, h.y, l.y);
+            hi[r * C4 + c] = h;
+            if (lo) lo[r * C4 + c] = l;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        };
+        long long r = r0 + rl;
+        for (; r + 3 * lanes < r1; r += 4 * lanes) {  // four independent 128-bit loads in flight per thread
+            const float4 v0 = ldg_stream(src + r * ld4 + c), v1 = ldg_stream(src + (r + lanes) * ld4 + c);
+            const float4 v2 = ldg_stream(src + (r + 2 * lanes) * ld4 + c), v3 = ldg_stream(src + (r + 3 * lanes) * ld4 + c);
+            emit(r, v0); emit(r + lanes, v1); emit(r + 2 * lanes, v2); emit(r + 3 * lanes, v3);
+        }
+        for (; r < r1; r += lanes) emit(r, ldg_stream(src + r * ld4 + c));
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < C4) {
+        float4 t = sh[threadIdx.x];
+        for (int l = 1; l < lanes; ++l) {
+            const float4 v = sh[l * C4 + threadIdx.x];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        float* o = colsum + (size_t)threadIdx.x * 4;
+        atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
+    }
+}
 }  // namespace
+
+cudaError_t launch_colsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long rows, int C, float* out, cudaStream_t st) {
+    if (rows <= 0) return cudaSuccess;
+    if ((C & 7) || C > 2048) return cudaErrorInvalidValue;
+    const int lanes = 256 / (C / 8) < 1 ? 1 : 256 / (C / 8);
+    int rows_per_cta = (int)ceil_div_ll(rows, 148LL * 4);   // few CTAs: every CTA ends with one atomic per column on the same C addresses
+    if (rows_per_cta < 16 * lanes) rows_per_cta = 16 * lanes;
+    colsum_planes_kernel<<<(unsigned)ceil_div_ll(rows, rows_per_cta), 256, 0, st>>>(reinterpret_cast<const uint4*>(hi), reinterpret_cast<const uint4*>(lo),
+                                                                                   rows, C / 8, out, rows_per_cta);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_split_rows_colsum(const float* src, long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo, long long rows, int C,
+                                     float* colsum, cudaStream_t st) {
+    if (rows <= 0) return cudaSuccess;
+    if ((C & 3) || (ld & 3) || C > 1024) return cudaErrorInvalidValue;
+    const int lanes = 256 / (C / 4) < 1 ? 1 : 256 / (C / 4);
+    int rows_per_cta = (int)ceil_div_ll(rows, 148LL * 4);   // few CTAs: every CTA ends with one atomic per column on the same C addresses
+    if (rows_per_cta < 16 * lanes) rows_per_cta = 16 * lanes;
+    split_rows_colsum_kernel<<<(unsigned)ceil_div_ll(rows, rows_per_cta), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(src), ld / 4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), rows, C / 4, colsum, rows_per_cta);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_split_rows(const float* src, long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo, long long rows, int C, int relu,
                               cudaStream_t st) {

@@ -64,6 +64,8 @@ struct TmaGemmArgs {
     int rows_per_group;
     const float* mask;  // optional [M, ldmask]: zero where mask <= 0
     int ldmask;
+    const __nv_bfloat16* mask_hi;  // the same mask given as a bf16 plane (the hi plane of a ReLU output): zero where <= 0
+    int ldmask_hi;
 };
 bool gemm_tma_nt_supported(const TmaGemmArgs& a);
 cudaError_t launch_gemm_tma_nt(const TmaGemmArgs& a, bool split, cudaStream_t st);
@@ -96,6 +98,12 @@ cudaError_t launch_gemm_tma_tn(const TmaWgradArgs& a, bool split, cudaStream_t s
 // fp32 rows [rows, C] (row stride ld) -> bf16 hi / lo planes [rows, C] (lo optional); relu applies max(x, 0) first
 cudaError_t launch_split_rows(const float* src, long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo, long long rows, int C, int relu,
                               cudaStream_t st);
+
+// out[c] += sum over rows of (hi + lo)[row, c] for a pair of planes (lo optional): bias gradients of tensors that exist as planes only
+cudaError_t launch_colsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long rows, int C, float* out, cudaStream_t st);
+// launch_split_rows (no ReLU) that also accumulates the column sums of the rows into colsum[C] (atomics): bias gradients
+cudaError_t launch_split_rows_colsum(const float* src, long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo, long long rows, int C,
+                                     float* colsum, cudaStream_t st);
 
 // C[Mo,No] += scale * sum_p A[p,Mo]^T * B[p',No]   (fp32 atomics), p' = p + shift when the time index allows.
 struct GemmTnArgs {

@@ -245,7 +245,8 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
                 CK(launch_add_ln(Rmid, nullptr, nullptr, nullptr, nullptr, params + lo[10], params + lo[11], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st,
                                  U2h, sp ? U2h + pN : nullptr)); ++nl;
                 {
-                    TmaGemmArgs a = tma_nt_args(U2h, sp ? U2h + pN : nullptr, N, whi + lo[4], wlo + lo[4], N, Hf, dffn, PTi, dffn, N);
+                    // the FFN hidden exists as operand planes only: they feed FFN 2, the dW2 GEMM and (hi plane) the ReLU mask of the backward
+                    TmaGemmArgs a = tma_nt_args(U2h, sp ? U2h + pN : nullptr, N, whi + lo[4], wlo + lo[4], N, nullptr, 0, PTi, dffn, N);
                     a.C_hi = Hh; a.C_lo = sp ? Hh + pD : nullptr; a.ldch = dffn;
                     a.bias = params + lo[5]; a.act = 1;
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
@@ -447,7 +448,6 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
             const TLayer& t = l.layer[tp.first_layer + ly];
             if (tma) {
                 const long long pN = g.PT * N, pD = g.PT * dffn, pQ = g.PT * 3 * N;
-                float* Hfm = at<float>(ws, t.Hf);
                 const __nv_bfloat16* U1h = at<__nv_bfloat16>(ws, t.U1hl);
                 const __nv_bfloat16* Oh = at<__nv_bfloat16>(ws, t.Oahl);
                 const __nv_bfloat16* U2h = at<__nv_bfloat16>(ws, t.U2hl);
@@ -465,43 +465,40 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
                     return launch_gemm_tma_tn(w, sp, st);
                 };
                 // FFN: out = Rmid + relu(U2 W1^T + b1) W2^T + b2
-                CK(launch_split_rows(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, 0, st)); ++nl;
-                {   // dHf = (dR W2) where Hf > 0, as fp32 (bias gradient) and planes
-                    TmaGemmArgs a = tma_nt_args(dRh, sp ? dRh + pN : nullptr, N, thi + lo[6], tlo + lo[6], N, dHf, dffn, PTi, dffn, N);
+                CK(launch_split_rows_colsum(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, grads + lo[7], st)); ++nl;   // planes of dR + db2
+                {   // dHf = (dR W2) where Hf > 0, as planes
+                    TmaGemmArgs a = tma_nt_args(dRh, sp ? dRh + pN : nullptr, N, thi + lo[6], tlo + lo[6], N, nullptr, 0, PTi, dffn, N);
                     a.C_hi = dHh; a.C_lo = sp ? dHh + pD : nullptr; a.ldch = dffn;
-                    a.mask = Hfm; a.ldmask = dffn;
+                    a.mask_hi = Hh; a.ldmask_hi = dffn;
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
                 CK(wgrad(Hh, pD, dffn, dffn, dRh, pN, N, N, grads + lo[6], dffn, 1)); ++nl;          // dW2 = dR^T Hf, as Hf^T dR stored transposed
-                CK(launch_colsum_any(dR, N, PTi, N, 1.f, grads + lo[7], st)); ++nl;
                 {
                     TmaGemmArgs a = tma_nt_args(dHh, sp ? dHh + pD : nullptr, dffn, thi + lo[4], tlo + lo[4], dffn, dU, N, PTi, N, dffn);
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
                 CK(wgrad(dHh, pD, dffn, dffn, U2h, pN, N, N, grads + lo[4], N, 0)); ++nl;             // dW1 = dHf^T U2
-                CK(launch_colsum_any(dHf, dffn, PTi, dffn, 1.f, grads + lo[5], st)); ++nl;
+                CK(launch_colsum_planes(dHh, sp ? dHh + pD : nullptr, g.PT, dffn, grads + lo[5], st)); ++nl;
                 // LayerNorm 2 (input Rmid): dR += d Rmid
                 CK(launch_ln_bwd(dU, at<float>(ws, t.Rmid), dU, dR, params + lo[10], g.PT, N, 1e-6f, grads + lo[10], grads + lo[11], st)); ++nl;
                 // attention branch: Rmid = Rin + attn(U1) W_o^T + b_o
-                CK(launch_split_rows(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, 0, st)); ++nl;
+                CK(launch_split_rows_colsum(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, grads + lo[3], st)); ++nl;   // planes of dR + dbo
                 {
                     TmaGemmArgs a = tma_nt_args(dRh, sp ? dRh + pN : nullptr, N, thi + lo[2], tlo + lo[2], N, dOa, N, PTi, N, N);
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
                 CK(wgrad(dRh, pN, N, N, Oh, pN, N, N, grads + lo[2], N, 0)); ++nl;                      // dWo = dR^T O
-                CK(launch_colsum_any(dR, N, PTi, N, 1.f, grads + lo[3], st)); ++nl;
                 if (attn_bwd_mma_supported(N, heads, m)) {
                     CK(launch_attn_bwd_mma(at<float>(ws, t.QKV), at<float>(ws, t.Oa), at<float>(ws, t.LSE), dOa, dQKV, N, heads, m, sp, st)); ++nl;
                 } else {
                     CK(launch_attn_bwd(at<float>(ws, t.QKV), at<float>(ws, t.Oa), at<float>(ws, t.LSE), dOa, dQKV, N, heads, m, st)); ++nl;
                 }
-                CK(launch_split_rows(dQKV, 3 * N, dQh, sp ? dQh + pQ : nullptr, g.PT, 3 * N, 0, st)); ++nl;
+                CK(launch_split_rows_colsum(dQKV, 3 * N, dQh, sp ? dQh + pQ : nullptr, g.PT, 3 * N, grads + lo[1], st)); ++nl;  // + db_in
                 {
                     TmaGemmArgs a = tma_nt_args(dQh, sp ? dQh + pQ : nullptr, 3 * N, thi + lo[0], tlo + lo[0], 3 * N, dU, N, PTi, N, 3 * N);
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
                 CK(wgrad(dQh, pQ, 3 * N, 3 * N, U1h, pN, N, N, grads + lo[0], N, 0)); ++nl;            // dWin = dQKV^T U1
-                CK(launch_colsum_any(dQKV, 3 * N, PTi, 3 * N, 1.f, grads + lo[1], st)); ++nl;
                 // LayerNorm 1 (input Rin): dR += d Rin
                 CK(launch_ln_bwd(dU, at<float>(ws, t.Rin), dU, dR, params + lo[8], g.PT, N, 1e-6f, grads + lo[8], grads + lo[9], st)); ++nl;
                 continue;
