@@ -48,7 +48,8 @@ template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(320, 1)
 gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
-                   const __grid_constant__ CUtensorMap tmC, const TmaGemmArgs p, const int tma_store) {
+                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCh, const __grid_constant__ CUtensorMap tmCl,
+                   const TmaGemmArgs p, const int tma_store, const int tma_planes) {
     using Cfg = NtCfg<BN, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -208,7 +209,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
-                    if (p.C_hi) {
+                    if (p.C_hi && !tma_planes) {
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
@@ -246,6 +247,36 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                         asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
                     }
                 }
+                if (tma_planes) {
+                    // plane outputs through shared memory and TMA stores as well: [128 rows x 32 bf16] tiles (64-byte rows, 64-byte
+                    // swizzle), hi at +0 and lo at +8 KB of this warp set's staging area (never used together with the fp32 staging)
+                    uint8_t* stg = out_stage + half * (128 * 128);
+                    const int bar_id = 1 + half;
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+                    if ((warp & 3) == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous stores drained
+                    asm volatile("bar.sync %0, 128;\n" ::"r"(bar_id) : "memory");
+                    const int rl = q * 32 + lane, sw = (rl >> 1) & 3;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        *reinterpret_cast<uint4*>(stg + rl * 64 + ((j ^ sw) << 4)) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        if (p.C_lo)
+                            *reinterpret_cast<uint4*>(stg + 8192 + rl * 64 + ((j ^ sw) << 4)) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                    }
+                    proxy_fence_async();
+                    asm volatile("bar.sync %0, 128;\n" ::"r"(bar_id) : "memory");
+                    if ((warp & 3) == 2 && lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(&tmCh),
+                                     "r"(smem_u32(stg)), "r"(n0 + c0), "r"(m0)
+                                     : "memory");
+                        if (p.C_lo)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(&tmCl),
+                                         "r"(smem_u32(stg + 8192)), "r"(n0 + c0), "r"(m0)
+                                         : "memory");
+                        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -264,7 +295,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
-        if (tma_store && (warp & 3) == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+        if ((tma_store || tma_planes) && (warp & 3) == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -308,10 +339,22 @@ bool make_map_c(CUtensorMap* map, const void* base, long long M, long long N, lo
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// bf16 plane output [M, N] (row stride ldch): box = 128 rows x 32 columns (64 bytes), 64-byte swizzle
+bool make_map_p(CUtensorMap* map, const void* base, long long M, long long N, long long ldch) {
+    auto fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t gstr[1] = {(cuuint64_t)ldch * 2};
+    cuuint32_t box[2] = {32u, 128u};
+    cuuint32_t estr[2] = {1u, 1u};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN, bool SPLIT>
 cudaError_t launch_nt(const TmaGemmArgs& a, cudaStream_t st) {
     using Cfg = NtCfg<BN, SPLIT>;
-    CUtensorMap mAh, mAl, mWh, mWl, mC;
+    CUtensorMap mAh, mAl, mWh, mWl, mC, mCh, mCl;
     if (!make_map(&mAh, a.A_hi, a.M, a.K, a.lda, BM) || !make_map(&mWh, a.W_hi, a.N, a.K, a.ldw, BN)) return cudaErrorInvalidValue;
     if (SPLIT) {
         if (!make_map(&mAl, a.A_lo, a.M, a.K, a.lda, BM) || !make_map(&mWl, a.W_lo, a.N, a.K, a.ldw, BN)) return cudaErrorInvalidValue;
@@ -322,11 +365,17 @@ cudaError_t launch_nt(const TmaGemmArgs& a, cudaStream_t st) {
     int tma_store = a.C != nullptr && !a.accumulate && !a.mul_c && !a.mask && (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0;
     mC = mAh;
     if (tma_store && !make_map_c(&mC, a.C, a.M, a.N, a.ldc)) tma_store = 0;
+    // plane outputs share the staging area with the fp32 stores: staged when the fp32 output is absent or takes the direct path
+    int tma_planes = a.C_hi != nullptr && !tma_store && (a.ldch & 7) == 0 && (reinterpret_cast<uintptr_t>(a.C_hi) & 15) == 0 &&
+                     (a.C_lo == nullptr || (reinterpret_cast<uintptr_t>(a.C_lo) & 15) == 0);
+    mCh = mAh; mCl = mAh;
+    if (tma_planes && !make_map_p(&mCh, a.C_hi, a.M, a.N, a.ldch)) tma_planes = 0;
+    if (tma_planes && a.C_lo && !make_map_p(&mCl, a.C_lo, a.M, a.N, a.ldch)) tma_planes = 0;
     cudaError_t e = cudaFuncSetAttribute(gemm_tma_nt_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return e;
     const int tiles = ceil_div(a.M, BM) * (a.N / BN);
     const int grid = tiles < 148 ? tiles : 148;
-    gemm_tma_nt_kernel<BN, SPLIT><<<grid, 320, Cfg::SMEM, st>>>(mAh, mAl, mWh, mWl, mC, a, tma_store);
+    gemm_tma_nt_kernel<BN, SPLIT><<<grid, 320, Cfg::SMEM, st>>>(mAh, mAl, mWh, mWl, mC, mCh, mCl, a, tma_store, tma_planes);
     return cudaGetLastError();
 }
 
