@@ -1,0 +1,120 @@
+"""Evaluation loop and metrics of the reference on the fused loss kernels.
+
+``MetricsTracker`` keeps the interface of look2hear/metrics/wrapper.py:18-80 (``tracker(mix, clean, estimate, key)``, ``update()``,
+``final()``, the ``metrics.csv`` columns).  SI-SNR and SI-SNRi come from the fused pairwise SI-SDR + PIT kernel (the same
+``PITLossWrapper(PairwiseNegSDR("sisdr"))`` the reference builds, wrapper.py:28,33-36) and stay on the device: nothing is synchronised
+per utterance (the reference calls ``.item()`` six times per utterance); rows are materialised in ``update()`` / ``final()``.
+
+The ``sdr`` / ``sdr_i`` columns of the reference come from ``fast_bss_eval.sdr_pit_loss`` (BSS-eval SDR with a 512-tap distortion
+filter), a third-party package that is neither vendored in the reference nor installed in this image; they are written as ``nan``
+rather than restated without anything to pin them against.
+
+``evaluate`` is ``audio_test.py:72-81`` with utterances of equal length batched together (every utterance is independent through the
+network -- DESIGN.md section 6 -- so a batch of equal-length mixtures gives the per-utterance results of the reference's one-by-one loop).
+"""
+from __future__ import annotations
+
+import csv
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .losses.matrix import pit_sdr_forward
+
+CSV_COLUMNS = ["snt_id", "sdr", "sdr_i", "si-snr", "si-snr_i"]
+
+
+def pit_si_snr(estimates: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    """Per-utterance permutation-invariant SI-SNR in dB (``[B]``, device tensor): ``-min_perm mean_i pairwise_neg_sisdr``."""
+    _, pw, _, _ = pit_sdr_forward(estimates.contiguous(), targets.contiguous(), "sisdr", False)
+    # pw[b, est, tgt]; n_src = 2: identity vs swapped assignment (pit_wrapper.py:96-131)
+    ident = 0.5 * (pw[:, 0, 0] + pw[:, 1, 1])
+    swap = 0.5 * (pw[:, 1, 0] + pw[:, 0, 1])
+    return -torch.minimum(ident, swap)
+
+
+class MetricsTracker:
+    def __init__(self, save_file: str = ""):
+        self.all_sdrs: List[float] = []
+        self.all_sdrs_i: List[float] = []
+        self.all_sisnrs: List[float] = []
+        self.all_sisnrs_i: List[float] = []
+        self.results_csv = open(save_file, "w") if save_file else None
+        self.writer = csv.DictWriter(self.results_csv, fieldnames=CSV_COLUMNS) if self.results_csv else None
+        if self.writer:
+            self.writer.writeheader()
+        self._pending: List[Tuple[Sequence[str], torch.Tensor, torch.Tensor]] = []   # (keys, si_snr[B], si_snr_i[B]) on the device
+
+    # -- reference interface: one utterance -------------------------------------------------------------------------------
+    def __call__(self, mix: torch.Tensor, clean: torch.Tensor, estimate: torch.Tensor, key: str):
+        """``mix [T]``, ``clean [n_src, T]``, ``estimate [n_src, T]`` (wrapper.py:31)."""
+        self.add_batch(mix.unsqueeze(0), clean.unsqueeze(0), estimate.unsqueeze(0), [key])
+
+    # -- batched entry point ------------------------------------------------------------------------------------------------
+    def add_batch(self, mix: torch.Tensor, clean: torch.Tensor, estimate: torch.Tensor, keys: Sequence[str]):
+        """``mix [B,T]``, ``clean [B,n_src,T]``, ``estimate [B,n_src,T]``; no host synchronisation."""
+        if clean.shape != estimate.shape or clean.ndim != 3 or mix.shape != (clean.shape[0], clean.shape[2]):
+            raise TypeError(f"expected mix [B,T], clean/estimate [B,n_src,T]; got {tuple(mix.shape)}, {tuple(clean.shape)}, {tuple(estimate.shape)}")
+        si = pit_si_snr(estimate, clean)
+        base = pit_si_snr(mix.unsqueeze(1).expand(-1, clean.shape[1], -1).contiguous(), clean)   # the mixture as every estimate (wrapper.py:34)
+        self._pending.append((list(keys), si, si - base))
+
+    def _flush(self):
+        for keys, si, si_i in self._pending:
+            si_h, si_i_h = si.detach().cpu().tolist(), si_i.detach().cpu().tolist()
+            for k, a, b in zip(keys, si_h, si_i_h):
+                row = {"snt_id": k, "sdr": float("nan"), "sdr_i": float("nan"), "si-snr": a, "si-snr_i": b}
+                if self.writer:
+                    self.writer.writerow(row)
+                self.all_sdrs.append(float("nan"))
+                self.all_sdrs_i.append(float("nan"))
+                self.all_sisnrs.append(a)
+                self.all_sisnrs_i.append(b)
+        self._pending = []
+
+    def update(self):
+        self._flush()
+        return {"sdr_i": float(np.array(self.all_sdrs_i).mean()) if self.all_sdrs_i else float("nan"),
+                "si-snr_i": float(np.array(self.all_sisnrs_i).mean()) if self.all_sisnrs_i else float("nan")}
+
+    def final(self):
+        self._flush()
+        for name, fn in (("avg", np.mean), ("std", np.std)):
+            row = {"snt_id": name, "sdr": float(fn(np.array(self.all_sdrs))), "sdr_i": float(fn(np.array(self.all_sdrs_i))),
+                   "si-snr": float(fn(np.array(self.all_sisnrs))), "si-snr_i": float(fn(np.array(self.all_sisnrs_i)))}
+            if self.writer:
+                self.writer.writerow(row)
+        if self.results_csv:
+            self.results_csv.close()
+            self.results_csv = None
+        return {"si-snr": float(np.mean(self.all_sisnrs)), "si-snr_i": float(np.mean(self.all_sisnrs_i))}
+
+
+@torch.no_grad()
+def evaluate(model, test_set: Iterable, metrics: Optional[MetricsTracker] = None, batch_size: int = 16, device="cuda"):
+    """``audio_test.py:72-81``: forward every ``(mix [T], sources [n_src, T], key)`` of ``test_set`` and track the metrics.
+
+    Utterances are grouped by exact length and run ``batch_size`` at a time (equal-length utterances share a batch without changing
+    any utterance's result; different lengths are never padded together, which would change the normalisation statistics).
+    Returns the tracker.
+    """
+    metrics = metrics if metrics is not None else MetricsTracker()
+    buckets = {}
+
+    def run(items):
+        mix = torch.stack([m for m, _, _ in items]).to(device, non_blocking=True)
+        src = torch.stack([s for _, s, _ in items]).to(device, non_blocking=True)
+        est = model(mix)
+        metrics.add_batch(mix, src, est, [k for _, _, k in items])
+
+    for mix, sources, key in test_set:
+        items = buckets.setdefault(int(mix.shape[-1]), [])
+        items.append((mix, sources, key))
+        if len(items) == batch_size:
+            run(items)
+            items.clear()
+    for items in buckets.values():
+        if items:
+            run(items)
+    return metrics
