@@ -1,0 +1,64 @@
+"""Training shell: scheduler / early-stop semantics on CPU, a short end-to-end run on the GPU."""
+import os
+
+import pytest
+import torch
+
+CONFIG = {   # configs/dprnn_wsj0.yml of the reference, model shrunk to 1 layer for the test
+    "audionet": {"audionet_name": "TasNet", "audionet_config": dict(enc_dim=64, bn_dim=64, hidden_dim=128, win=16, layer=1, num_spk=2,
+                                                                     module="DPRNN", group_size=1, block_size=100, unfold=False)},
+    "loss": {"train": {"loss_func": "PITLossWrapper", "sdr_type": "pairwise_neg_snr", "config": {"pit_from": "pw_mtx", "threshold_byloss": False}},
+             "val": {"loss_func": "PITLossWrapper", "sdr_type": "pairwise_neg_sisdr", "config": {"pit_from": "pw_mtx", "threshold_byloss": False}}},
+    "training": {"epochs": 500, "early_stop": {"monitor": "val_loss/dataloader_idx_0", "mode": "min", "patience": 30, "verbose": True}},
+    "optimizer": {"optim_name": "adam", "lr": 0.001, "weight_decay": 0},
+    "scheduler": {"sche_name": "ReduceLROnPlateau", "sche_config": {"patience": 15, "factor": 0.5}},
+    "datamodule": {"data_name": "LRS2DataModule", "data_config": {"sample_rate": 8000, "segment": 4.0, "batch_size": 2}},
+}
+
+
+def test_plateau_scheduler_matches_torch():
+    from audio_only_speech_separation_b200.fit import PlateauScheduler
+
+    class T:
+        lr = 1e-3
+
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=1e-3)
+    ref = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, patience=2, factor=0.5)
+    mine = PlateauScheduler(T(), patience=2, factor=0.5)
+    g = torch.Generator().manual_seed(0)
+    metrics = [1.0, 0.9, 0.95, 0.91, 0.92, 0.93, 0.5, 0.50001, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1] + torch.rand(40, generator=g).tolist()
+    for m in metrics:
+        ref.step(m)
+        assert mine.step(m) == pytest.approx(opt.param_groups[0]["lr"], rel=1e-12), m
+
+
+def test_early_stopping_and_config_lookup():
+    from audio_only_speech_separation_b200.fit import EarlyStopping, build_from_config
+
+    es = EarlyStopping(patience=3)
+    assert [es.step(v) for v in [1.0, 0.9, 0.95, 0.93, 0.8, 0.81, 0.82, 0.83]] == [False, False, False, False, False, False, False, True]
+    model, tr, va = build_from_config(CONFIG)
+    assert model.model_name == "DPRNN" and model.sample_rate() == 8000
+    assert tr.loss_func.sdr_type == "snr" and va.loss_func.sdr_type == "sisdr" and tr.threshold_byloss is False
+    bad = {**CONFIG, "audionet": {"audionet_name": "NoSuchNet", "audionet_config": {}}}
+    with pytest.raises(ValueError):
+        build_from_config(bad)
+
+
+@pytest.mark.gpu
+def test_fit_runs_saves_best_checkpoint_and_lowers_the_loss(tmp_path):
+    from audio_only_speech_separation_b200.fit import fit
+    from audio_only_speech_separation_b200.models import BaseModel
+
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(8, 2, 4000, generator=g) * 0.1
+    data = [(src[i:i + 2].sum(1), src[i:i + 2], [f"u{i}", f"u{i + 1}"]) for i in range(0, 8, 2)]
+    hist = fit(CONFIG, lambda e: data[:3], lambda e: data[3:], str(tmp_path), max_epochs=6, log=lambda s: None)
+    assert len(hist) == 6 and hist[-1]["train_loss"] < hist[0]["train_loss"]
+    assert all(h["lr"] == 1e-3 for h in hist)
+    for f in ("best_model.pth", "conf.yml", "history.json"):
+        assert os.path.exists(tmp_path / f), f
+    m = BaseModel.from_pretrain(str(tmp_path / "best_model.pth"), sample_rate=8000, **CONFIG["audionet"]["audionet_config"]).cuda().eval()
+    with torch.no_grad():
+        assert m(data[0][0].cuda()).shape == (2, 2, 4000)
