@@ -88,6 +88,7 @@ PROTOTYPES = {
     "dp_sepformer_forward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "dp_sepformer_last_launches": (_i, [_p]),
     "dp_sepformer_train_workspace_bytes": (_i64, [_p, _i, _i]),
+    "dp_sepformer_set_dropout": (_i, [_p, _f, C.c_uint32]),
     "dp_sepformer_forward_train": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "dp_sepformer_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
 }

@@ -45,10 +45,11 @@ __device__ __forceinline__ void load_a_rows(const __nv_bfloat16* base, int strid
     ldmatrix_x4(a, smem_u32(base + (m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * stride + k0 + (lane >> 4) * 8));
 }
 
-template <int D, bool SPLIT>
+template <int D, bool SPLIT, bool DROP>
 __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict__ O,
                                                               const float* __restrict__ LSE, const float* __restrict__ dO,
-                                                              float* __restrict__ dQKV, int E, int heads, SeqMap m, float scale) {
+                                                              float* __restrict__ dQKV, int E, int heads, SeqMap m, float scale,
+                                                              const unsigned drop_thr, const unsigned drop_key, const float drop_scale) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int RS = D + 8;      // bf16 row stride: 16-byte aligned rows, conflict-free ldmatrix
     constexpr int KS = D / 16;     // k-steps over the head width
@@ -131,6 +132,9 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(const float* __res
             }
         }
         const float l0 = lse[r0 + g], l1 = lse[r0 + g + 8], d0 = dlt[r0 + g], d1 = dlt[r0 + g + 8];
+        // dropout mask rows of this thread's two queries: (stream position * heads + head)
+        const uint32_t drow0 = (uint32_t)(base + (long long)(r0 + g) * m.s_t) * (uint32_t)heads + (uint32_t)h;
+        const uint32_t drow1 = (uint32_t)(base + (long long)(r0 + g + 8) * m.s_t) * (uint32_t)heads + (uint32_t)h;
         float dq[DN][4];
 #pragma unroll
         for (int n = 0; n < DN; ++n)
@@ -157,6 +161,13 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(const float* __res
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
                 const float kb0 = kbias[j0 + n * 8 + 2 * c], kb1 = kbias[j0 + n * 8 + 2 * c + 1];
+                if (DROP) {  // dP = (dO V^T) masked like the forward's probabilities; the softmax backward uses the un-dropped P
+                    const uint32_t jc = (uint32_t)(j0 + n * 8 + 2 * c);
+                    dp[n][0] = drop_keep(drop_key, drow0, jc, drop_thr) ? dp[n][0] * drop_scale : 0.f;
+                    dp[n][1] = drop_keep(drop_key, drow0, jc + 1, drop_thr) ? dp[n][1] * drop_scale : 0.f;
+                    dp[n][2] = drop_keep(drop_key, drow1, jc, drop_thr) ? dp[n][2] * drop_scale : 0.f;
+                    dp[n][3] = drop_keep(drop_key, drow1, jc + 1, drop_thr) ? dp[n][3] * drop_scale : 0.f;
+                }
                 s[n][0] = ex2_approx(fmaf(s[n][0], c2, kb0 - l0)) * (dp[n][0] - d0);
                 s[n][1] = ex2_approx(fmaf(s[n][1], c2, kb1 - l0)) * (dp[n][1] - d0);
                 s[n][2] = ex2_approx(fmaf(s[n][2], c2, kb0 - l1)) * (dp[n][2] - d1);
@@ -229,10 +240,21 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(const float* __res
             for (int n = 0; n < 8; ++n) {
                 const int i = i0 + n * 8 + 2 * c;
                 const float la = lse[i], lb = lse[i + 1], da = dlt[i], db = dlt[i + 1];
-                s[n][0] = ex2_approx(fmaf(s[n][0], c2, -la)); dp[n][0] = s[n][0] * (dp[n][0] - da);
-                s[n][1] = ex2_approx(fmaf(s[n][1], c2, -lb)); dp[n][1] = s[n][1] * (dp[n][1] - db);
-                s[n][2] = ex2_approx(fmaf(s[n][2], c2, -la)); dp[n][2] = s[n][2] * (dp[n][2] - da);
-                s[n][3] = ex2_approx(fmaf(s[n][3], c2, -lb)); dp[n][3] = s[n][3] * (dp[n][3] - db);
+                float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;   // mask * 1/(1-p) of (query = column, key = row)
+                if (DROP) {
+                    const uint32_t qa = (uint32_t)(base + (long long)i * m.s_t) * (uint32_t)heads + (uint32_t)h;
+                    const uint32_t qb = (uint32_t)(base + (long long)(i + 1) * m.s_t) * (uint32_t)heads + (uint32_t)h;
+                    const uint32_t ka = (uint32_t)(r0 + g), kb = (uint32_t)(r0 + g + 8);
+                    m0 = drop_keep(drop_key, qa, ka, drop_thr) ? drop_scale : 0.f;
+                    m1 = drop_keep(drop_key, qb, ka, drop_thr) ? drop_scale : 0.f;
+                    m2 = drop_keep(drop_key, qa, kb, drop_thr) ? drop_scale : 0.f;
+                    m3 = drop_keep(drop_key, qb, kb, drop_thr) ? drop_scale : 0.f;
+                }
+                float pv;
+                pv = ex2_approx(fmaf(s[n][0], c2, -la)); dp[n][0] = pv * (dp[n][0] * m0 - da); s[n][0] = pv * m0;
+                pv = ex2_approx(fmaf(s[n][1], c2, -lb)); dp[n][1] = pv * (dp[n][1] * m1 - db); s[n][1] = pv * m1;
+                pv = ex2_approx(fmaf(s[n][2], c2, -la)); dp[n][2] = pv * (dp[n][2] * m2 - da); s[n][2] = pv * m2;
+                pv = ex2_approx(fmaf(s[n][3], c2, -lb)); dp[n][3] = pv * (dp[n][3] * m3 - db); s[n][3] = pv * m3;
             }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -274,12 +296,20 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(const float* __res
 
 template <int D, bool SPLIT>
 cudaError_t launch_one(const float* QKV, const float* O, const float* LSE, const float* dO, float* dQKV, int E, int heads, const SeqMap& m,
-                       cudaStream_t st) {
+                       cudaStream_t st, unsigned drop_thr, unsigned drop_key, float drop_scale) {
     const int LP = (m.len + 63) & ~63;
     const size_t smem = (size_t)8 * LP * (D + 8) * sizeof(__nv_bfloat16) + (size_t)3 * LP * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_mma_kernel<D, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attn_bwd_mma_kernel<D, SPLIT><<<dim3(m.nseq, heads), 256, smem, st>>>(QKV, O, LSE, dO, dQKV, E, heads, m, 1.0f / sqrtf((float)D));
+    const float scale = 1.0f / sqrtf((float)D);
+    cudaError_t e;
+    if (drop_thr) {
+        e = cudaFuncSetAttribute(attn_bwd_mma_kernel<D, SPLIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attn_bwd_mma_kernel<D, SPLIT, true><<<dim3(m.nseq, heads), 256, smem, st>>>(QKV, O, LSE, dO, dQKV, E, heads, m, scale, drop_thr, drop_key, drop_scale);
+    } else {
+        e = cudaFuncSetAttribute(attn_bwd_mma_kernel<D, SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attn_bwd_mma_kernel<D, SPLIT, false><<<dim3(m.nseq, heads), 256, smem, st>>>(QKV, O, LSE, dO, dQKV, E, heads, m, scale, 0u, 0u, 1.f);
+    }
     return cudaGetLastError();
 }
 
@@ -292,12 +322,14 @@ bool attn_bwd_mma_supported(int E, int heads, const SeqMap& m) {
 }
 
 cudaError_t launch_attn_bwd_mma(const float* QKV, const float* O, const float* LSE, const float* dO, float* dQKV, int E, int heads,
-                                const SeqMap& m, bool split, cudaStream_t st) {
+                                const SeqMap& m, bool split, cudaStream_t st, unsigned drop_thr, unsigned drop_key, float drop_scale) {
     if (m.nseq <= 0 || m.len <= 0) return cudaSuccess;
     if (!attn_bwd_mma_supported(E, heads, m)) return cudaErrorInvalidValue;
     const int D = E / heads;
-    if (D == 16) return split ? launch_one<16, true>(QKV, O, LSE, dO, dQKV, E, heads, m, st) : launch_one<16, false>(QKV, O, LSE, dO, dQKV, E, heads, m, st);
-    return split ? launch_one<32, true>(QKV, O, LSE, dO, dQKV, E, heads, m, st) : launch_one<32, false>(QKV, O, LSE, dO, dQKV, E, heads, m, st);
+#define DP_AB(DD, SP) launch_one<DD, SP>(QKV, O, LSE, dO, dQKV, E, heads, m, st, drop_thr, drop_key, drop_scale)
+    if (D == 16) return split ? DP_AB(16, true) : DP_AB(16, false);
+    return split ? DP_AB(32, true) : DP_AB(32, false);
+#undef DP_AB
 }
 
 }  // namespace dp

@@ -66,10 +66,12 @@ struct AttnTcArgs {
     int inter, len, nseq_or_K, S, B;
     long long s_t;
     float scale_log2;
+    unsigned drop_thr, drop_key;   // attention-probability dropout (0 = off): mask element (query position * heads + head, key index)
+    float drop_scale;
 };
 
 // LMAX: 128 or 256 keys / queries per sequence at most (tensor-memory columns of S)
-template <int D, int LMAX, bool SPLIT>
+template <int D, int LMAX, bool SPLIT, bool DROP>
 __global__ void __launch_bounds__(160, 1)
 attn_tc5_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL, const AttnTcArgs p) {
     constexpr int ROWB = D * 2;                       // bytes per tile row
@@ -184,6 +186,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
                     if (c0 + j < L) mx = fmaxf(mx, v[j]);
             }
             const float mxs = mx * p.scale_log2;
+            const uint32_t drow = (uint32_t)(base + (long long)qi * p.s_t) * (uint32_t)p.heads + (uint32_t)h;
             float sum = 0.f;
             for (int c0 = 0; c0 < Lp; c0 += 32) {
                 float v[32];
@@ -191,9 +194,13 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
                 uint32_t ph[16], plo[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const float e0 = (c0 + j < L) ? exp2f(fmaf(v[j], p.scale_log2, -mxs)) : 0.f;
-                    const float e1 = (c0 + j + 1 < L) ? exp2f(fmaf(v[j + 1], p.scale_log2, -mxs)) : 0.f;
-                    sum += e0 + e1;
+                    float e0 = (c0 + j < L) ? exp2f(fmaf(v[j], p.scale_log2, -mxs)) : 0.f;
+                    float e1 = (c0 + j + 1 < L) ? exp2f(fmaf(v[j + 1], p.scale_log2, -mxs)) : 0.f;
+                    sum += e0 + e1;   // the softmax denominator is that of the un-dropped probabilities
+                    if (DROP) {
+                        if (!drop_keep(p.drop_key, drow, (uint32_t)(c0 + j), p.drop_thr)) e0 = 0.f;
+                        if (!drop_keep(p.drop_key, drow, (uint32_t)(c0 + j + 1), p.drop_thr)) e1 = 0.f;
+                    }
                     split_pair(e0, e1, ph[j >> 1], plo[j >> 1]);
                 }
                 tmem_st16(lane_addr + COL_PH + (c0 >> 1), ph);
@@ -210,7 +217,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
             tc_fence_before();
             mbar_arrive(o_read);
             if (qi < L) {
-                const float inv = 1.0f / sum;
+                const float inv = (DROP ? p.drop_scale : 1.0f) / sum;
                 const size_t pos = (size_t)(base + (long long)qi * p.s_t);
                 if (p.O != nullptr) {
                     float4* dst = reinterpret_cast<float4*>(p.O + pos * p.E + h * D);
@@ -274,10 +281,17 @@ bool make_qkv_map(CUtensorMap* map, const void* base, int E, int D, const LstmFu
 template <int D, int LMAX, bool SPLIT>
 cudaError_t launch(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcArgs& a, int nseq, cudaStream_t st) {
     const int smem = 3 * (SPLIT ? 2 : 1) * LMAX * D * 2 + 1024 + 256;
-    cudaError_t e = cudaFuncSetAttribute(attn_tc5_kernel<D, LMAX, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
     dim3 grid(nseq, a.heads);
-    attn_tc5_kernel<D, LMAX, SPLIT><<<grid, 160, smem, st>>>(mh, ml, a);
+    cudaError_t e;
+    if (a.drop_thr) {
+        e = cudaFuncSetAttribute(attn_tc5_kernel<D, LMAX, SPLIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attn_tc5_kernel<D, LMAX, SPLIT, true><<<grid, 160, smem, st>>>(mh, ml, a);
+    } else {
+        e = cudaFuncSetAttribute(attn_tc5_kernel<D, LMAX, SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attn_tc5_kernel<D, LMAX, SPLIT, false><<<grid, 160, smem, st>>>(mh, ml, a);
+    }
     return cudaGetLastError();
 }
 
@@ -292,7 +306,8 @@ bool attn_tc5_supported(int E, int heads, const LstmFusedGeom& gm) {
 }
 
 cudaError_t launch_attn_fwd_tc5(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, float* O, __nv_bfloat16* O_hi, __nv_bfloat16* O_lo,
-                                float* LSE, int E, int heads, const LstmFusedGeom& gm, bool split, cudaStream_t st) {
+                                float* LSE, int E, int heads, const LstmFusedGeom& gm, bool split, cudaStream_t st, unsigned drop_thr,
+                                unsigned drop_key, float drop_scale) {
     if (!attn_tc5_supported(E, heads, gm)) return cudaErrorInvalidValue;
     if (split && !qkv_lo) return cudaErrorInvalidValue;
     const int D = E / heads;
@@ -306,6 +321,7 @@ cudaError_t launch_attn_fwd_tc5(const __nv_bfloat16* qkv_hi, const __nv_bfloat16
     a.inter = gm.inter; a.len = gm.len; a.nseq_or_K = gm.inter ? gm.K : gm.nseq; a.S = gm.S; a.B = gm.B;
     a.s_t = gm.inter ? gm.K : 1;
     a.scale_log2 = kLog2e / sqrtf((float)D);
+    a.drop_thr = drop_thr; a.drop_key = drop_key; a.drop_scale = drop_scale;
     const bool big = gm.len > 128;
 #define DP_ATT(DD)                                                                                                   \
     (big ? (split ? launch<DD, 256, true>(mh, ml, a, gm.nseq, st) : launch<DD, 256, false>(mh, ml, a, gm.nseq, st))  \

@@ -151,6 +151,20 @@ __device__ __forceinline__ void stg_pred(uint2* p, const uint2& v, bool pred) {
                  : "memory");
 }
 
+// ---- counter-based dropout masks ---------------------------------------------------------------------------------------
+// keep(key, row, col) is a pure function of the element's indices and a per-(step, layer, site) key, so the backward regenerates the
+// forward's mask instead of storing it (tests replay the same function in numpy: tests/dropout_ref.py).  thr24 = p * 2^24.
+__host__ __device__ inline uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ inline uint32_t drop_site_key(uint32_t seed, int layer, int site) {
+    return hash32(seed ^ (0x9E3779B1u * (uint32_t)(layer * 4 + site + 1)));
+}
+__device__ __forceinline__ bool drop_keep(uint32_t key, uint32_t row, uint32_t col, uint32_t thr24) {
+    return (hash32(row * 0x9E3779B1u + col * 0x85EBCA77u + key) >> 8) >= thr24;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -44,7 +44,7 @@ struct NtCfg {
     static constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 };
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool DROP>
 __global__ void __launch_bounds__(320, 1)
 gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
@@ -157,7 +157,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                         }
                     }
                     float* dst = p.C ? p.C + (size_t)row * p.ldc + col : nullptr;
-                    if (p.accumulate) {
+                    if (p.accumulate && !(DROP && p.drop_thr)) {
                         const float* rsrc = p.Cin ? p.Cin + (size_t)row * p.ldc + col : dst;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -174,6 +174,19 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                     } else if (p.act == 3) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
+                    }
+                    if (DROP && p.drop_thr) {  // dropout on the sub-layer output, then (if any) the residual
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            v[j] = drop_keep(p.drop_key, (uint32_t)row, (uint32_t)(col + j), p.drop_thr) ? v[j] * p.drop_scale : 0.f;
+                        if (p.accumulate) {
+                            const float* rsrc = p.Cin ? p.Cin + (size_t)row * p.ldc + col : dst;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 o = *reinterpret_cast<const float4*>(rsrc + j);
+                                v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+                            }
+                        }
                     }
                     if (p.mul_c) {
 #pragma unroll
@@ -204,6 +217,10 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                                 if (hi16 == 0u || hi16 >= 0x8000u) v[8 * j + 2 * t + 1] = 0.f;
                             }
                         }
+                    }
+                    if (p.out_scale != 0.f) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
                     }
                     if (dst && !tma_store) {
 #pragma unroll
@@ -371,11 +388,18 @@ cudaError_t launch_nt(const TmaGemmArgs& a, cudaStream_t st) {
     mCh = mAh; mCl = mAh;
     if (tma_planes && !make_map_p(&mCh, a.C_hi, a.M, a.N, a.ldch)) tma_planes = 0;
     if (tma_planes && a.C_lo && !make_map_p(&mCl, a.C_lo, a.M, a.N, a.ldch)) tma_planes = 0;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tma_nt_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (e != cudaSuccess) return e;
     const int tiles = ceil_div(a.M, BM) * (a.N / BN);
     const int grid = tiles < 148 ? tiles : 148;
-    gemm_tma_nt_kernel<BN, SPLIT><<<grid, 320, Cfg::SMEM, st>>>(mAh, mAl, mWh, mWl, mC, mCh, mCl, a, tma_store, tma_planes);
+    cudaError_t e;
+    if (a.drop_thr) {   // the dropout epilogue is a separate instantiation: the plain one keeps its register budget
+        e = cudaFuncSetAttribute(gemm_tma_nt_kernel<BN, SPLIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        gemm_tma_nt_kernel<BN, SPLIT, true><<<grid, 320, Cfg::SMEM, st>>>(mAh, mAl, mWh, mWl, mC, mCh, mCl, a, tma_store, tma_planes);
+    } else {
+        e = cudaFuncSetAttribute(gemm_tma_nt_kernel<BN, SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        gemm_tma_nt_kernel<BN, SPLIT, false><<<grid, 320, Cfg::SMEM, st>>>(mAh, mAl, mWh, mWl, mC, mCh, mCl, a, tma_store, tma_planes);
+    }
     return cudaGetLastError();
 }
 
@@ -659,14 +683,21 @@ __global__ void __launch_bounds__(256) colsum_planes_kernel(const uint4* __restr
 // thread = (float4 column, row lane); a CTA walks a contiguous row range and adds its partial sums with one atomic per column
 __global__ void __launch_bounds__(256) split_rows_colsum_kernel(const float4* __restrict__ src, long long ld4, uint2* __restrict__ hi,
                                                                 uint2* __restrict__ lo, long long rows, int C4, float* __restrict__ colsum,
-                                                                int rows_per_cta) {
+                                                                int rows_per_cta, unsigned drop_thr, unsigned drop_key, float drop_scale) {
     __shared__ float4 sh[256];
     const int lanes = 256 / C4;
     const int c = threadIdx.x % C4, rl = threadIdx.x / C4;
     const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (rl < lanes) {
-        auto emit = [&](long long r, const float4& v) {
+        auto emit = [&](long long r, float4 v) {
+            if (drop_thr) {  // gradient of a dropped sub-layer output: the forward's mask of element (row, column)
+                const uint32_t c0 = 4u * (uint32_t)c;
+                v.x = drop_keep(drop_key, (uint32_t)r, c0, drop_thr) ? v.x * drop_scale : 0.f;
+                v.y = drop_keep(drop_key, (uint32_t)r, c0 + 1, drop_thr) ? v.y * drop_scale : 0.f;
+                v.z = drop_keep(drop_key, (uint32_t)r, c0 + 2, drop_thr) ? v.z * drop_scale : 0.f;
+                v.w = drop_keep(drop_key, (uint32_t)r, c0 + 3, drop_thr) ? v.w * drop_scale : 0.f;
+            }
             uint2 h, l;
             split_pair(v.x, v.y, h.x, l.x);
             split_pair(v.z, v.w, h.y, l.y);
@@ -708,14 +739,15 @@ cudaError_t launch_colsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* l
 }
 
 cudaError_t launch_split_rows_colsum(const float* src, long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo, long long rows, int C,
-                                     float* colsum, cudaStream_t st) {
+                                     float* colsum, cudaStream_t st, unsigned drop_thr, unsigned drop_key, float drop_scale) {
     if (rows <= 0) return cudaSuccess;
     if ((C & 3) || (ld & 3) || C > 1024) return cudaErrorInvalidValue;
     const int lanes = 256 / (C / 4) < 1 ? 1 : 256 / (C / 4);
     int rows_per_cta = (int)ceil_div_ll(rows, 148LL * 4);   // few CTAs: every CTA ends with one atomic per column on the same C addresses
     if (rows_per_cta < 16 * lanes) rows_per_cta = 16 * lanes;
     split_rows_colsum_kernel<<<(unsigned)ceil_div_ll(rows, rows_per_cta), 256, 0, st>>>(
-        reinterpret_cast<const float4*>(src), ld / 4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), rows, C / 4, colsum, rows_per_cta);
+        reinterpret_cast<const float4*>(src), ld / 4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), rows, C / 4, colsum, rows_per_cta,
+        drop_thr, drop_key, drop_scale);
     return cudaGetLastError();
 }
 

@@ -66,6 +66,11 @@ struct TmaGemmArgs {
     int ldmask;
     const __nv_bfloat16* mask_hi;  // the same mask given as a bf16 plane (the hi plane of a ReLU output): zero where <= 0
     int ldmask_hi;
+    // dropout on act(A W^T + bias) BEFORE the residual is added (nn.Dropout on a sub-layer output): kept elements * drop_scale.
+    // drop_thr = p * 2^24 (0 = off); element (row, col) of the output is kept iff drop_keep(drop_key, row, col, drop_thr)
+    unsigned drop_thr, drop_key;
+    float drop_scale;
+    float out_scale;   // 0 = none: multiplies the final value (after the masks)
 };
 bool gemm_tma_nt_supported(const TmaGemmArgs& a);
 cudaError_t launch_gemm_tma_nt(const TmaGemmArgs& a, bool split, cudaStream_t st);
@@ -102,8 +107,9 @@ cudaError_t launch_split_rows(const float* src, long long ld, __nv_bfloat16* hi,
 // out[c] += sum over rows of (hi + lo)[row, c] for a pair of planes (lo optional): bias gradients of tensors that exist as planes only
 cudaError_t launch_colsum_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long rows, int C, float* out, cudaStream_t st);
 // launch_split_rows (no ReLU) that also accumulates the column sums of the rows into colsum[C] (atomics): bias gradients
+// drop_thr != 0: the rows pass through the dropout mask of (drop_key, row, col) first (gradient of a dropped sub-layer output)
 cudaError_t launch_split_rows_colsum(const float* src, long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo, long long rows, int C,
-                                     float* colsum, cudaStream_t st);
+                                     float* colsum, cudaStream_t st, unsigned drop_thr = 0, unsigned drop_key = 0, float drop_scale = 1.f);
 
 // C[Mo,No] += scale * sum_p A[p,Mo]^T * B[p',No]   (fp32 atomics), p' = p + shift when the time index allows.
 struct GemmTnArgs {
@@ -262,10 +268,13 @@ bool attn_tc5_supported(int E, int heads, const LstmFusedGeom& gm);
 // attention backward on the warp-level tensor cores (attention_bwd_mma.cu): sequences <= 256, head width 16 / 32;
 // split = bf16x3 products (fp32-parity mode), otherwise single bf16 products.  Same arguments as launch_attn_bwd.
 bool attn_bwd_mma_supported(int E, int heads, const SeqMap& m);
+// drop_thr != 0: attention-probability dropout, mask element (position of the query * heads + head, key index)
 cudaError_t launch_attn_bwd_mma(const float* QKV, const float* O, const float* LSE, const float* dO, float* dQKV, int E, int heads,
-                                const SeqMap& m, bool split, cudaStream_t st);
+                                const SeqMap& m, bool split, cudaStream_t st, unsigned drop_thr = 0, unsigned drop_key = 0,
+                                float drop_scale = 1.f);
 cudaError_t launch_attn_fwd_tc5(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, float* O, __nv_bfloat16* O_hi, __nv_bfloat16* O_lo,
-                                float* LSE, int E, int heads, const LstmFusedGeom& gm, bool split, cudaStream_t st);
+                                float* LSE, int E, int heads, const LstmFusedGeom& gm, bool split, cudaStream_t st, unsigned drop_thr = 0,
+                                unsigned drop_key = 0, float drop_scale = 1.f);
 // z = a (+ b) [-> zout]; out = (res ? res : 0) + LayerNorm_E(z) * gamma + beta; then optional unfold affine + PReLU.
 cudaError_t launch_add_ln(const float* a, const float* b, float* zout, float* out, const float* res, const float* gamma, const float* beta,
                           long long rows, int E, float eps, const float* cw, const float* cb, const float* slope, cudaStream_t st,

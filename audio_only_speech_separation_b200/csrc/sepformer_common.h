@@ -10,6 +10,8 @@ struct dp_sepformer {
     std::vector<int64_t> off;
     int64_t n_params;
     int launches;
+    float drop_p = 0.f;        // training-time dropout of the transformer layers (dp_sepformer_set_dropout); 0 = off
+    uint32_t drop_seed = 0;
 };
 
 namespace {

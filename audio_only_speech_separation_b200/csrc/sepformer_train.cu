@@ -131,6 +131,13 @@ int check_trainable(const dp_sepformer* h) {
 
 extern "C" {
 
+int dp_sepformer_set_dropout(dp_sepformer* h, float p, uint32_t seed) {
+    if (!(p >= 0.f && p < 1.f)) return fail("dp_sepformer_set_dropout: need 0 <= p < 1 (got %g)", (double)p);
+    h->drop_p = p;
+    h->drop_seed = seed;
+    return 0;
+}
+
 int64_t dp_sepformer_train_workspace_bytes(const dp_sepformer* h, int B, int T) {
     SGeo g;
     if (sep_geo(h, B, T, g)) return -1;
@@ -156,6 +163,10 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
     const __nv_bfloat16* wlo = reinterpret_cast<const __nv_bfloat16*>(static_cast<const char*>(pack) + flat);
     const int PTi = (int)g.PT, BLi = (int)g.BL;
     int nl = 0;
+    // dropout of the transformer layers (sepformer.py:124-128,261,318-319): sites 0 attention probabilities, 1 attention output,
+    // 2 FFN hidden, 3 FFN output; masks are a pure function of (seed, layer, site, element) and regenerated by the backward
+    const unsigned drop_thr = (unsigned)(h->drop_p * 16777216.0f);
+    const float drop_scale = 1.0f / (1.0f - h->drop_p);
 
     float* E = at<float>(ws, l.E);
     double* stats = at<double>(ws, l.stats);
@@ -195,6 +206,8 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
         LstmFusedGeom gm;
         gm.inter = path; gm.len = m.len; gm.nseq = m.nseq; gm.K = g.K; gm.S = g.Sc; gm.B = B;
         const bool tc_attn = tma && attn_tc5_supported(N, heads, gm);
+        if (drop_thr && !(tma && tc_attn))
+            return fail("dp_sepformer_forward_train: dropout needs the TMA backend (dp_set_gemm_backend(2)), enc_dim in {128, 256}, d_ffn %% 128 == 0 and sequences <= 256");
         float* Xin = at<float>(ws, l.X[pi]);
         float* R0 = at<float>(ws, l.layer[tp.first_layer].Rin);
         if (use_pe) {
@@ -232,14 +245,17 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
                     a.bias = params + lo[1];
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
+                const int li = tp.first_layer + ly;
                 if (tc_attn) {
-                    CK(launch_attn_fwd_tc5(Qh, sp ? Qh + pQ : nullptr, Oa, Oh, sp ? Oh + pN : nullptr, at<float>(ws, t.LSE), N, heads, gm, sp, st)); ++nl;
+                    CK(launch_attn_fwd_tc5(Qh, sp ? Qh + pQ : nullptr, Oa, Oh, sp ? Oh + pN : nullptr, at<float>(ws, t.LSE), N, heads, gm, sp, st,
+                                           drop_thr, drop_site_key(h->drop_seed, li, 0), drop_scale)); ++nl;
                 } else {
                     CK(launch_attn_fwd(QKV, Oa, at<float>(ws, t.LSE), N, heads, m, st, Oh, sp ? Oh + pN : nullptr)); ++nl;
                 }
                 {   // Rmid = Rin + O W_o^T + b_o
                     TmaGemmArgs a = tma_nt_args(Oh, sp ? Oh + pN : nullptr, N, whi + lo[2], wlo + lo[2], N, Rmid, N, PTi, N, N);
                     a.bias = params + lo[3]; a.accumulate = 1; a.Cin = Rin;
+                    a.drop_thr = drop_thr; a.drop_key = drop_site_key(h->drop_seed, li, 1); a.drop_scale = drop_scale;
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
                 CK(launch_add_ln(Rmid, nullptr, nullptr, nullptr, nullptr, params + lo[10], params + lo[11], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st,
@@ -249,11 +265,13 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
                     TmaGemmArgs a = tma_nt_args(U2h, sp ? U2h + pN : nullptr, N, whi + lo[4], wlo + lo[4], N, nullptr, 0, PTi, dffn, N);
                     a.C_hi = Hh; a.C_lo = sp ? Hh + pD : nullptr; a.ldch = dffn;
                     a.bias = params + lo[5]; a.act = 1;
+                    a.drop_thr = drop_thr; a.drop_key = drop_site_key(h->drop_seed, li, 2); a.drop_scale = drop_scale;
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
                 {   // Rout = Rmid + Hf W_2^T + b_2
                     TmaGemmArgs a = tma_nt_args(Hh, sp ? Hh + pD : nullptr, dffn, whi + lo[6], wlo + lo[6], dffn, Rout, N, PTi, N, dffn);
                     a.bias = params + lo[7]; a.accumulate = 1; a.Cin = Rmid;
+                    a.drop_thr = drop_thr; a.drop_key = drop_site_key(h->drop_seed, li, 3); a.drop_scale = drop_scale;
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
                 continue;
@@ -350,6 +368,8 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
     const int PTi = (int)g.PT, BLi = (int)g.BL, rows = BLi * spk;
     const long long nPN = g.PT * N;
     int nl = 0;
+    const unsigned drop_thr = (unsigned)(h->drop_p * 16777216.0f);
+    const float drop_scale = 1.0f / (1.0f - h->drop_p);
 
     float* E = at<float>(ws, l.E);
     float* dX = at<float>(ws, l.dX);
@@ -435,6 +455,8 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
         const SeqMap m = seq_map(g, B, path);
         const TPath& tp = l.path[pi];
         const bool tma = train_tma(N, dffn);
+        if (drop_thr && !(tma && attn_bwd_mma_supported(N, heads, m)))
+            return fail("dp_sepformer_backward: dropout needs the TMA backend, enc_dim in {128, 256}, d_ffn %% 128 == 0 and sequences <= 256");
         float* Uf = at<float>(ws, tp.Uf);
         float* mr = at<float>(ws, tp.mr);
         // X_out = Xin + gLN(Uf): gLN backward -> dU (d Uf); the residual branch keeps dX
@@ -465,11 +487,15 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
                     return launch_gemm_tma_tn(w, sp, st);
                 };
                 // FFN: out = Rmid + relu(U2 W1^T + b1) W2^T + b2
-                CK(launch_split_rows_colsum(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, grads + lo[7], st)); ++nl;   // planes of dR + db2
+                const int li = tp.first_layer + ly;
+                // gradient of the (dropped) FFN output: planes of dR masked like the forward + db2
+                CK(launch_split_rows_colsum(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, grads + lo[7], st, drop_thr, drop_site_key(h->drop_seed, li, 3),
+                                            drop_scale)); ++nl;
                 {   // dHf = (dR W2) where Hf > 0, as planes
                     TmaGemmArgs a = tma_nt_args(dRh, sp ? dRh + pN : nullptr, N, thi + lo[6], tlo + lo[6], N, nullptr, 0, PTi, dffn, N);
                     a.C_hi = dHh; a.C_lo = sp ? dHh + pD : nullptr; a.ldch = dffn;
-                    a.mask_hi = Hh; a.ldmask_hi = dffn;
+                    a.mask_hi = Hh; a.ldmask_hi = dffn;   // the saved hidden is zero where the ReLU was inactive or the element was dropped
+                    if (drop_thr) a.out_scale = drop_scale;
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
                 CK(wgrad(Hh, pD, dffn, dffn, dRh, pN, N, N, grads + lo[6], dffn, 1)); ++nl;          // dW2 = dR^T Hf, as Hf^T dR stored transposed
@@ -482,14 +508,16 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
                 // LayerNorm 2 (input Rmid): dR += d Rmid
                 CK(launch_ln_bwd(dU, at<float>(ws, t.Rmid), dU, dR, params + lo[10], g.PT, N, 1e-6f, grads + lo[10], grads + lo[11], st)); ++nl;
                 // attention branch: Rmid = Rin + attn(U1) W_o^T + b_o
-                CK(launch_split_rows_colsum(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, grads + lo[3], st)); ++nl;   // planes of dR + dbo
+                CK(launch_split_rows_colsum(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, grads + lo[3], st, drop_thr, drop_site_key(h->drop_seed, li, 1),
+                                            drop_scale)); ++nl;   // planes of the (masked) dR + dbo
                 {
                     TmaGemmArgs a = tma_nt_args(dRh, sp ? dRh + pN : nullptr, N, thi + lo[2], tlo + lo[2], N, dOa, N, PTi, N, N);
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
                 CK(wgrad(dRh, pN, N, N, Oh, pN, N, N, grads + lo[2], N, 0)); ++nl;                      // dWo = dR^T O
                 if (attn_bwd_mma_supported(N, heads, m)) {
-                    CK(launch_attn_bwd_mma(at<float>(ws, t.QKV), at<float>(ws, t.Oa), at<float>(ws, t.LSE), dOa, dQKV, N, heads, m, sp, st)); ++nl;
+                    CK(launch_attn_bwd_mma(at<float>(ws, t.QKV), at<float>(ws, t.Oa), at<float>(ws, t.LSE), dOa, dQKV, N, heads, m, sp, st, drop_thr,
+                                           drop_site_key(h->drop_seed, li, 0), drop_scale)); ++nl;
                 } else {
                     CK(launch_attn_bwd(at<float>(ws, t.QKV), at<float>(ws, t.Oa), at<float>(ws, t.LSE), dOa, dQKV, N, heads, m, st)); ++nl;
                 }

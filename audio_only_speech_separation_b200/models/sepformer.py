@@ -11,8 +11,10 @@ buffer that the engine reads through an offset table (include/dualpath_b200.h).
 The engine covers inference (``model.eval()`` / ``torch.no_grad()``, TMA-fed tcgen05 GEMMs and attention, fp32-parity and bf16
 modes) and training for pre-norm layers: forward + backward are two engine calls behind one autograd node, gradients are
 checked against autograd through the reference algorithm.  The reference trains with dropout 0.1 in four places per layer
-(SURVEY A.4 #15); those sites are not implemented yet, so a training forward requires the explicit opt-in
-``model.dropout = 0.0`` (the default 0.1, like the reference, raises ``NotImplementedError``).
+(attention probabilities, attention output, FFN hidden, FFN output); ``model.dropout`` (default 0.1, like the
+reference) applies them in ``train()`` mode on the TMA engine (enc_dim 128 / 256): masks are a counter-based function of a seed drawn
+from torch's generator per forward, regenerated -- not stored -- by the backward; smaller layers, which run on the mma.sync engine,
+raise unless ``model.dropout = 0.0``.
 Reference quirk kept on purpose: for batch > 1 the output rows are the reference's ``reshape`` of (spk, batch)-ordered
 decoder rows (sepformer.py:1004), identity only for batch 1 (the YAML's ``batch_size: 1``).
 """
@@ -135,8 +137,13 @@ class _SepformerFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, mixture, *params):
+        # dropout masks are a function of (seed, layer, site, element): draw one seed per forward from torch's generator and hand the
+        # same (p, seed) to the backward, which regenerates the masks
+        p = float(model.dropout) if model.training else 0.0
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if p > 0.0 else 0
+        check(lib().dp_sepformer_set_dropout(model._handle, p, seed), "dp_sepformer_set_dropout")
         est, ws = model._engine_forward_train(mixture)
-        ctx.model, ctx.ws, ctx.dims = model, ws, mixture.shape
+        ctx.model, ctx.ws, ctx.dims, ctx.drop = model, ws, mixture.shape, (p, seed)
         return est
 
     @staticmethod
@@ -146,6 +153,7 @@ class _SepformerFunction(torch.autograd.Function):
             raise RuntimeError("Sepformer backward: the saved workspace was already consumed")
         gflat = torch.zeros_like(model._flat)
         B, T = ctx.dims
+        check(lib().dp_sepformer_set_dropout(model._handle, ctx.drop[0], ctx.drop[1]), "dp_sepformer_set_dropout")
         check(lib().dp_sepformer_backward(model._handle, ptr(model._flat), ptr(model._pack), ptr(d_est.contiguous().float()), ptr(gflat),
                                           ptr(ctx.ws), B, T, model._prec(), stream_ptr()), "dp_sepformer_backward")
         ctx.ws = None
@@ -233,10 +241,6 @@ class Sepformer(BaseModel):
         self._sync_flat(xin.device)
         params = [e for e in self._views if not isinstance(e, tuple)]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            if self.training and self.dropout != 0.0:
-                raise NotImplementedError(
-                    "Sepformer training: the reference's dropout (0.1 in every layer) is not implemented; set model.dropout = 0.0 to "
-                    "train without it, or use model.eval() / torch.no_grad() for inference")
             est = _SepformerFunction.apply(self, xin, *params)
         else:
             est = self._engine_forward(xin)

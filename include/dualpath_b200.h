@@ -223,9 +223,13 @@ int dp_sepformer_pack(dp_sepformer* h, const float* params, void* pack, void* st
 int dp_sepformer_forward(dp_sepformer* h, const float* params, const void* pack, const float* mixture, float* est, void* workspace,
                          int B, int T, int precision, void* stream);
 int dp_sepformer_last_launches(const dp_sepformer* h);
-/* Training (pre-norm layers; the reference's dropout sites are NOT applied: the caller opts in, see models/sepformer.py):
- * a forward that keeps in its workspace what the backward needs, and the backward into a flat gradient buffer laid out like
- * params (ACCUMULATED into).  Same pack as the inference engine. */
+/* Training (pre-norm layers): a forward that keeps in its workspace what the backward needs, and the backward into a flat gradient
+ * buffer laid out like params (ACCUMULATED into).  Same pack as the inference engine.
+ * dp_sepformer_set_dropout: the transformer layers' training-time dropout (sepformer.py:124-128,261,318-319: attention
+ * probabilities, attention output, FFN hidden, FFN output; the reference default is 0.1).  Masks are a counter-based function of
+ * (seed, layer, site, element): the backward regenerates them, so call it with the SAME p and seed before the forward and the
+ * matching backward.  p = 0 switches the sites off.  Needs the TMA backend. */
+int dp_sepformer_set_dropout(dp_sepformer* h, float p, uint32_t seed);
 int64_t dp_sepformer_train_workspace_bytes(const dp_sepformer* h, int B, int T);
 int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void* pack, const float* mixture, float* est, void* workspace,
                                int B, int T, int precision, void* stream);

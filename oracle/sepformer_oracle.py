@@ -40,7 +40,7 @@ def positional_encoding(L: int, E: int, dtype=torch.float32) -> Tensor:
     return pe.to(dtype)
 
 
-def mha(x: Tensor, sd: StateDict, prefix: str, heads: int) -> Tensor:
+def mha(x: Tensor, sd: StateDict, prefix: str, heads: int, drop=None) -> Tensor:
     """``nn.MultiheadAttention`` self-attention on batch-first ``[Nb, L, E]`` (the wrapper at sepformer.py:83-215
     permutes to seq-first and back), no mask; the averaged weights it also returns are discarded (sepformer.py:554)."""
     Nb, L, E = x.shape
@@ -48,32 +48,37 @@ def mha(x: Tensor, sd: StateDict, prefix: str, heads: int) -> Tensor:
     qkv = x.reshape(Nb * L, E) @ sd[prefix + "in_proj_weight"].t() + sd[prefix + "in_proj_bias"]
     q, k, v = qkv.reshape(Nb, L, 3, heads, d).permute(2, 0, 3, 1, 4)  # each [Nb, h, L, d]
     att = torch.softmax((q * (1.0 / math.sqrt(d))) @ k.transpose(-1, -2), dim=-1)
+    if drop is not None:
+        att = drop(0, att)  # nn.MultiheadAttention(dropout=p): dropout on the probabilities (sepformer.py:124-128)
     o = (att @ v).permute(0, 2, 1, 3).reshape(Nb * L, E)
     o = o @ sd[prefix + "out_proj.weight"].t() + sd[prefix + "out_proj.bias"]
     return o.reshape(Nb, L, E)
 
 
-def encoder_layer(x: Tensor, sd: StateDict, prefix: str, heads: int, norm_before: bool) -> Tensor:
-    """``TransformerEncoderLayer.forward`` (sepformer.py:320-370), dropout inactive (eval)."""
+def encoder_layer(x: Tensor, sd: StateDict, prefix: str, heads: int, norm_before: bool, drop=None) -> Tensor:
+    """``TransformerEncoderLayer.forward`` (sepformer.py:320-370).  ``drop(site, tensor)`` (optional) applies the training-time
+    dropout of site 0 (attention probabilities), 1 (``dropout1``, :355), 2 (FFN hidden, :261), 3 (``dropout2``, :366) with an
+    explicit mask; ``None`` = eval."""
+    ident = (lambda site, t: t) if drop is None else drop
     src1 = layer_norm(x, sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"], 1e-6) if norm_before else x
-    x = x + mha(src1, sd, prefix + "self_att.att.", heads)
+    x = x + ident(1, mha(src1, sd, prefix + "self_att.att.", heads, drop))
     if not norm_before:
         x = layer_norm(x, sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"], 1e-6)
     src1 = layer_norm(x, sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"], 1e-6) if norm_before else x
-    h = torch.relu(src1 @ sd[prefix + "pos_ffn.ffn.0.weight"].t() + sd[prefix + "pos_ffn.ffn.0.bias"])  # sepformer.py:258-263
-    x = x + (h @ sd[prefix + "pos_ffn.ffn.3.weight"].t() + sd[prefix + "pos_ffn.ffn.3.bias"])
+    h = ident(2, torch.relu(src1 @ sd[prefix + "pos_ffn.ffn.0.weight"].t() + sd[prefix + "pos_ffn.ffn.0.bias"]))  # sepformer.py:258-263
+    x = x + ident(3, h @ sd[prefix + "pos_ffn.ffn.3.weight"].t() + sd[prefix + "pos_ffn.ffn.3.bias"])
     if not norm_before:
         x = layer_norm(x, sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"], 1e-6)
     return x
 
 
-def transformer_block(x: Tensor, sd: StateDict, prefix: str, layers: int, heads: int, norm_before: bool, use_pe: bool) -> Tensor:
+def transformer_block(x: Tensor, sd: StateDict, prefix: str, layers: int, heads: int, norm_before: bool, use_pe: bool, drop=None) -> Tensor:
     """``TransformerBlock.forward`` (sepformer.py:541-556) + ``TransformerEncoder.forward`` (:438-467): PE added once,
     ``layers`` encoder layers, final LayerNorm."""
     if use_pe:
         x = x + sd[prefix + "pos_enc.pe"][:, : x.shape[1]]
     for l in range(layers):
-        x = encoder_layer(x, sd, f"{prefix}mdl.layers.{l}.", heads, norm_before)
+        x = encoder_layer(x, sd, f"{prefix}mdl.layers.{l}.", heads, norm_before, None if drop is None else (lambda site, t, l=l: drop(l, site, t)))
     return layer_norm(x, sd[prefix + "mdl.norm.weight"], sd[prefix + "mdl.norm.bias"], 1e-6)
 
 
@@ -82,17 +87,18 @@ def global_ln(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-8) -> Tens
     return group_norm1(x, gamma, beta, eps)
 
 
-def dual_block(x: Tensor, sd: StateDict, prefix: str, cfg: dict) -> Tensor:
-    """``Dual_Computation_Block.forward`` (sepformer.py:600-642).  ``x``: [B, N, K, S]."""
+def dual_block(x: Tensor, sd: StateDict, prefix: str, cfg: dict, drop=None) -> Tensor:
+    """``Dual_Computation_Block.forward`` (sepformer.py:600-642).  ``x``: [B, N, K, S].  ``drop(path, layer, site, tensor)``: see
+    :func:`encoder_layer` (path 0 = intra, rows ``(b, s)`` along ``k``; 1 = inter, rows ``(b, k)`` along ``s``)."""
     B, N, K, S = x.shape
     intra = x.permute(0, 3, 2, 1).reshape(B * S, K, N)
     intra = transformer_block(intra, sd, prefix + "intra_mdl.", cfg["intra_numlayers"], cfg["intra_nhead"], cfg["intra_norm_before"],
-                              cfg["intra_use_positional"])
+                              cfg["intra_use_positional"], None if drop is None else (lambda l, site, t: drop(0, l, site, t)))
     intra = intra.reshape(B, S, K, N).permute(0, 3, 2, 1)
     intra = global_ln(intra, sd[prefix + "intra_norm.gamma"], sd[prefix + "intra_norm.beta"]) + x
     inter = intra.permute(0, 2, 3, 1).reshape(B * K, S, N)
     inter = transformer_block(inter, sd, prefix + "inter_mdl.", cfg["inter_numlayers"], cfg["inter_nhead"], cfg["inter_norm_before"],
-                              cfg["inter_use_positional"])
+                              cfg["inter_use_positional"], None if drop is None else (lambda l, site, t: drop(1, l, site, t)))
     inter = inter.reshape(B, K, S, N).permute(0, 3, 1, 2)
     return global_ln(inter, sd[prefix + "inter_norm.gamma"], sd[prefix + "inter_norm.beta"]) + intra
 
@@ -103,8 +109,10 @@ DEFAULTS = dict(encoder_kernel_size=16, encoder_in_nchannels=1, encoder_out_ncha
                 intra_causal=False, inter_causal=False)
 
 
-def sepformer_forward(sd: StateDict, mix: Tensor, taps: Optional[dict] = None, **config) -> Tensor:
-    """``Sepformer.forward`` (sepformer.py:986-1016) with ``Dual_Path_Model.forward`` (:706-760)."""
+def sepformer_forward(sd: StateDict, mix: Tensor, taps: Optional[dict] = None, dropout=None, **config) -> Tensor:
+    """``Sepformer.forward`` (sepformer.py:986-1016) with ``Dual_Path_Model.forward`` (:706-760).
+
+    ``dropout(block, path, layer, site, tensor)`` (optional): training-time dropout with explicit masks, see :func:`encoder_layer`."""
     cfg = dict(DEFAULTS, **config)
     assert cfg["masknet_norm"] == "gLN" and not cfg["intra_causal"] and not cfg["inter_causal"] and cfg["encoder_in_nchannels"] == 1
     was_one_d = mix.ndim == 1
@@ -123,7 +131,7 @@ def sepformer_forward(sd: StateDict, mix: Tensor, taps: Optional[dict] = None, *
     h = (h.permute(0, 2, 1).reshape(B * L, N) @ sd["masknet.conv1d.weight"].reshape(N, N).t()).reshape(B, L, N).permute(0, 2, 1)
     blocks, gap = split_feature(h, K)  # _Segmentation == split_feature (verified bit-equal)
     for j in range(cfg["masknet_numlayers"]):
-        blocks = dual_block(blocks, sd, f"masknet.dual_mdl.{j}.", cfg)
+        blocks = dual_block(blocks, sd, f"masknet.dual_mdl.{j}.", cfg, None if dropout is None else (lambda path, l, site, t, j=j: dropout(j, path, l, site, t)))
     y = prelu(blocks, sd["masknet.prelu.weight"])                                   # :736
     Kc, S = y.shape[2], y.shape[3]
     y = y.permute(0, 2, 3, 1).reshape(-1, N) @ sd["masknet.conv2d.weight"].reshape(N * spk, N).t() + sd["masknet.conv2d.bias"]  # :739

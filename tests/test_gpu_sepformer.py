@@ -89,9 +89,12 @@ def test_training_needs_dropout_opt_in_and_gradients_match_oracle(manifest):
     m, sd, cfg = _model(manifest, "sepformer_small_b2_t3000")
     z = load_npz("grads_sepformer_small.npz")
     x, tgt = torch.from_numpy(z["x"]), torch.from_numpy(z["tgt"])
+    from audio_only_speech_separation_b200 import _lib
+
     m.train()
-    with pytest.raises(NotImplementedError):
-        m(x.cuda())                       # the reference's dropout 0.1 is not implemented: explicit opt-in required
+    assert m.dropout == 0.1               # the reference's default (sepformer.py:507)
+    with pytest.raises(_lib.DualPathError):
+        m(x.cuda())                       # enc_dim = 64 layers run on the mma.sync engine, which has no dropout: fails loudly
     m.dropout = 0.0
     leaf = {k: v.clone().requires_grad_(not k.endswith("pos_enc.pe")) for k, v in sd.items()}
     ref_loss = O.pit_loss(SO.sepformer_forward(leaf, x, **cfg), tgt, "snr", False)
@@ -213,3 +216,50 @@ def test_training_tma_path_gradients_match_oracle():
     m.precision = "fp32"
     assert abs(loss_b - loss_t) < 5e-2 * max(1.0, abs(loss_t))
     assert all(torch.isfinite(v).all() for v in gb.values())
+
+
+def test_training_with_dropout_matches_oracle_given_the_same_masks():
+    """The reference's four dropout sites per layer (attention probabilities, attention output, FFN hidden, FFN output; p = 0.1) on the
+    TMA engine.  The masks are a counter-based function of (seed, layer, site, element); tests/dropout_ref.py replays it in numpy, so the
+    oracle runs with the SAME masks and the loss and every gradient can be compared exactly (the backward regenerates the masks)."""
+    import dropout_ref as DR
+    from audio_only_speech_separation_b200 import _lib
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+    from audio_only_speech_separation_b200.models import Sepformer
+
+    cfg = dict(encoder_out_nchannels=128, intra_dffn=256, inter_dffn=256, intra_nhead=4, inter_nhead=4, intra_numlayers=2, inter_numlayers=1,
+               masknet_chunksize=50, masknet_numlayers=2)
+    torch.manual_seed(5)
+    m = Sepformer(sample_rate=8000, **cfg)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda().train()
+    assert m.dropout == 0.1
+    g = torch.Generator().manual_seed(21)
+    B, T, K = 2, 2400, 50
+    x = torch.randn(B, T, generator=g) * 0.1
+    tgt = torch.randn(B, 2, T, generator=g) * 0.1
+    torch.manual_seed(77)
+    seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())      # the draw Sepformer.forward makes
+    _, S = _lib.seg_geometry((T - 16) // 8 + 1, K)
+    cb = DR.oracle_dropout(0.1, seed, B, S, K, 4, 4, 2, 1)
+    leaf = {k: v.clone().requires_grad_(not k.endswith("pos_enc.pe")) for k, v in sd.items()}
+    ref_loss = O.pit_loss(SO.sepformer_forward(leaf, x, dropout=cb, **cfg), tgt, "snr", False)
+    ref_loss.backward()
+    nodrop = O.pit_loss(SO.sepformer_forward(sd, x, **cfg), tgt, "snr", False).item()
+    lossf = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)
+    torch.manual_seed(77)
+    loss = lossf(m(x.cuda()), tgt.cuda())
+    loss.backward()
+    assert abs(ref_loss.item() - nodrop) > 1e-3 * abs(nodrop)                 # the masks do change the loss ...
+    assert abs(loss.item() - ref_loss.item()) < 1e-4 * max(1.0, abs(ref_loss.item()))   # ... and the engine applies the same ones
+    errs = sorted(rel_l2(p.grad, leaf[k].grad) for k, p in m.named_parameters())
+    num = sum(float((p.grad.cpu().double() - leaf[k].grad.double()).pow(2).sum()) for k, p in m.named_parameters())
+    den = sum(float(leaf[k].grad.double().pow(2).sum()) for k, _ in m.named_parameters())
+    record("sepformer_grads_dropout", median=errs[len(errs) // 2], total=(num / den) ** 0.5, worst=errs[-1], loss=loss.item(), loss_nodrop=nodrop)
+    assert errs[len(errs) // 2] < 1e-4 and (num / den) ** 0.5 < 5e-3 and errs[-1] < 5e-2   # same ReLU-flip conditioning as above
+    # a different seed gives different masks; eval mode ignores dropout
+    torch.manual_seed(78)
+    assert abs(lossf(m(x.cuda()), tgt.cuda()).item() - loss.item()) > 1e-4 * abs(loss.item())
+    m.eval()
+    with torch.no_grad():
+        assert abs(lossf(m(x.cuda()), tgt.cuda()).item() - nodrop) < 1e-4 * max(1.0, abs(nodrop))

@@ -4,7 +4,7 @@
 
 TasNet models: ``DualPathTrainer.step`` (forward + PIT loss + backward + clip + Adam fused).  Sepformer: the autograd path the
 reference's Lightning module uses (``loss.backward()`` through the single engine node, ``clip_grad_norm_`` + ``torch.optim.Adam``),
-with the dropout sites off (``model.dropout = 0``).
+with the reference's dropout 0.1 (``DROPOUT=0`` in the environment switches the sites off).
 """
 import json
 import os
@@ -25,7 +25,7 @@ src = torch.randn(B, 2, T, generator=g) * 0.1
 mix, tgt = src.sum(1).cuda(), src.cuda()
 if name == "sepformer":
     m = Sepformer(sample_rate=sr).cuda().train()
-    m.dropout = 0.0
+    m.dropout = float(os.environ.get("DROPOUT", "0.1"))   # the reference's default; DROPOUT=0 switches the four sites off
     m.precision = prec
     loss_fn = PITLossWrapper(pairwise_neg_sisdr, pit_from="pw_mtx", threshold_byloss=True)
     opt = torch.optim.Adam(m.parameters(), lr=1.5e-4)
