@@ -29,8 +29,8 @@ import torch  # noqa: E402
 SR, SECONDS, BATCH = 8000, 4.0, 16
 CFG = dict(enc_dim=64, bn_dim=64, hidden_dim=128, win=16, layer=6, num_spk=2, module="DPRNN", group_size=1, block_size=100, unfold=False)
 # dram__bytes_read.sum + dram__bytes_write.sum of one lstm_fwd_kernel launch (ncu --set full capture under profiles/), by batch
-TRAFFIC_BYTES_PER_LAUNCH = {16: 806841600 + 488006912}      # lstm_bwd_kernel, filled from profiles/r1_lstm_bwd_v9_full.summary.txt
-TRAFFIC_FWD_BYTES_PER_LAUNCH = {16: 537961984 + 751281920}  # lstm_fwd_pipe_kernel, profiles/r1_lstm_fwd_v9_full.summary.txt
+TRAFFIC_BYTES_PER_LAUNCH = {16: 1294316032}      # lstm_bwd_ks_kernel, profiles/r1_lstm_bwd_v11_full.summary.txt (dram read + write)
+TRAFFIC_FWD_BYTES_PER_LAUNCH = {16: 1287374592}  # lstm_fwd_pipe_kernel, profiles/r1_lstm_fwd_v11_full.summary.txt
 METRIC = "train samples/sec (DPRNN wsj0, batch 16/GPU, 4 s @ 8 kHz, fwd + PIT-SNR loss + bwd + clip + Adam)"
 
 
@@ -299,7 +299,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * sec_e2e / args.steps, "loss": last.get("loss")},
             "gpu_launches": trainer.launches_per_step * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "lstm_bwd_kernel (persistent BiLSTM BPTT recurrence, intra-chunk pass; largest single share of the step: "
+            "roofline": {"kernel": "lstm_bwd_ks_kernel (persistent BiLSTM BPTT recurrence, intra-chunk pass; largest single share of the step: "
                                    "the recurrence kernels fwd + bwd are ~57% of it)", "bound": "hbm",
                          "achieved": k_hbm / k_sec / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": k_hbm / k_sec / 1e9 / pk["hbm_gbs"],
                          "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.batch),
