@@ -46,7 +46,7 @@ __device__ __forceinline__ void load_a_rows(const __nv_bfloat16* base, int strid
 }
 
 template <int D, bool SPLIT, bool DROP>
-__global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict__ O,
+__global__ void __launch_bounds__(256, (D == 16 ? 2 : 1)) attn_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict__ O,
                                                               const float* __restrict__ LSE, const float* __restrict__ dO,
                                                               float* __restrict__ dQKV, int E, int heads, SeqMap m, float scale,
                                                               const unsigned drop_thr, const unsigned drop_key, const float drop_scale) {

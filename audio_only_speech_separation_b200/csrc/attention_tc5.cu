@@ -72,7 +72,7 @@ struct AttnTcArgs {
 
 // LMAX: 128 or 256 keys / queries per sequence at most (tensor-memory columns of S)
 template <int D, int LMAX, bool SPLIT, bool DROP>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(160, (LMAX == 128 ? 2 : 1))   // 256 tensor-memory columns per CTA at LMAX = 128: two CTAs share an SM
 attn_tc5_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL, const AttnTcArgs p) {
     constexpr int ROWB = D * 2;                       // bytes per tile row
     constexpr uint32_t LAYOUT = D == 32 ? 4u : 6u;    // SWIZZLE_64B / SWIZZLE_32B
