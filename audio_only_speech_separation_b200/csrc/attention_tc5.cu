@@ -72,7 +72,7 @@ struct AttnTcArgs {
 
 // LMAX: 128 or 256 keys / queries per sequence at most (tensor-memory columns of S)
 template <int D, int LMAX, bool SPLIT, bool DROP>
-__global__ void __launch_bounds__(160, (LMAX == 128 ? 2 : 1))   // 256 tensor-memory columns per CTA at LMAX = 128: two CTAs share an SM
+__global__ void __launch_bounds__(288, (LMAX == 128 ? 2 : 1))   // 256 tensor-memory columns per CTA at LMAX = 128: two CTAs share an SM
 attn_tc5_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmL, const AttnTcArgs p) {
     constexpr int ROWB = D * 2;                       // bytes per tile row
     constexpr uint32_t LAYOUT = D == 32 ? 4u : 6u;    // SWIZZLE_64B / SWIZZLE_32B
@@ -93,6 +93,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
     uint64_t* o_full = p_ready + 1;
     uint64_t* o_read = o_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_read + 1);
+    float* xch = reinterpret_cast<float*>(tmem_slot + 2);   // [2 halves][2 (max, sum)][128 rows]: the two threads of a row exchange through it
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x, h = blockIdx.y;
@@ -105,7 +106,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
     else { const int b = q / p.nseq_or_K, k = q % p.nseq_or_K; c1 = k; c2 = 0; c3 = b; base = (long long)b * p.S * p.nseq_or_K + k; }
 
     if (threadIdx.x == 0) {
-        mbar_init(ld_full, 1); mbar_init(s_full, 1); mbar_init(p_ready, 128); mbar_init(o_full, 1); mbar_init(o_read, 128);
+        mbar_init(ld_full, 1); mbar_init(s_full, 1); mbar_init(p_ready, 256); mbar_init(o_full, 1); mbar_init(o_read, 128);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         prefetch_tmap(&tmH);
         if (SPLIT) prefetch_tmap(&tmL);
@@ -169,8 +170,10 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
             umma_commit_w(o_full);
         }
     } else {
-        // ===================== softmax + output: thread = query row =====================
+        // ===================== softmax + output: TWO threads per query row (warps w and w + 4 share a tensor-memory lane quarter and
+        // take alternate 32-column chunks of the row; maximum and sum are exchanged through shared memory) =====================
         const int qd = warp & 3, r = qd * 32 + lane;
+        const int half = (warp - 1) >> 2;                 // warps 1-4: chunks 0, 2, ...; warps 5-8: chunks 1, 3, ...
         const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16);
         const int nmt = (L + 127) / 128;
         for (int mt = 0; mt < nmt; ++mt) {
@@ -178,17 +181,20 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
             mbar_wait(s_full, mt & 1);
             tc_fence_after();
             float mx = -INFINITY;
-            for (int c0 = 0; c0 < Lp; c0 += 32) {
+            for (int c0 = half * 32; c0 < Lp; c0 += 64) {
                 float v[32];
                 tmem_ld32_nowait(lane_addr + COL_S + c0, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (c0 + j < L) mx = fmaxf(mx, v[j]);
             }
+            xch[(half * 2 + 0) * 128 + r] = mx;
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            mx = fmaxf(mx, xch[((half ^ 1) * 2 + 0) * 128 + r]);
             const float mxs = mx * p.scale_log2;
             const uint32_t drow = (uint32_t)(base + (long long)qi * p.s_t) * (uint32_t)p.heads + (uint32_t)h;
             float sum = 0.f;
-            for (int c0 = 0; c0 < Lp; c0 += 32) {
+            for (int c0 = half * 32; c0 < Lp; c0 += 64) {
                 float v[32];
                 tmem_ld32_nowait(lane_addr + COL_S + c0, v);
                 uint32_t ph[16], plo[16];
@@ -206,9 +212,13 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
                 tmem_st16(lane_addr + COL_PH + (c0 >> 1), ph);
                 if (SPLIT) tmem_st16(lane_addr + COL_PL + (c0 >> 1), plo);
             }
+            xch[(half * 2 + 1) * 128 + r] = sum;
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(p_ready);
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            if (half) continue;   // the first thread of the pair writes the output row
+            sum += xch[(1 * 2 + 1) * 128 + r];
             // ---- O row
             mbar_wait(o_full, mt & 1);
             tc_fence_after();
@@ -280,17 +290,17 @@ bool make_qkv_map(CUtensorMap* map, const void* base, int E, int D, const LstmFu
 
 template <int D, int LMAX, bool SPLIT>
 cudaError_t launch(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcArgs& a, int nseq, cudaStream_t st) {
-    const int smem = 3 * (SPLIT ? 2 : 1) * LMAX * D * 2 + 1024 + 256;
+    const int smem = 3 * (SPLIT ? 2 : 1) * LMAX * D * 2 + 1024 + 256 + 2 * 2 * 128 * 4;
     dim3 grid(nseq, a.heads);
     cudaError_t e;
     if (a.drop_thr) {
         e = cudaFuncSetAttribute(attn_tc5_kernel<D, LMAX, SPLIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attn_tc5_kernel<D, LMAX, SPLIT, true><<<grid, 160, smem, st>>>(mh, ml, a);
+        attn_tc5_kernel<D, LMAX, SPLIT, true><<<grid, 288, smem, st>>>(mh, ml, a);
     } else {
         e = cudaFuncSetAttribute(attn_tc5_kernel<D, LMAX, SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attn_tc5_kernel<D, LMAX, SPLIT, false><<<grid, 160, smem, st>>>(mh, ml, a);
+        attn_tc5_kernel<D, LMAX, SPLIT, false><<<grid, 288, smem, st>>>(mh, ml, a);
     }
     return cudaGetLastError();
 }
