@@ -62,3 +62,29 @@ def test_fit_runs_saves_best_checkpoint_and_lowers_the_loss(tmp_path):
     m = BaseModel.from_pretrain(str(tmp_path / "best_model.pth"), sample_rate=8000, **CONFIG["audionet"]["audionet_config"]).cuda().eval()
     with torch.no_grad():
         assert m(data[0][0].cuda()).shape == (2, 2, 4000)
+
+
+@pytest.mark.gpu
+def test_end_to_end_wav_corpus_to_metrics(tmp_path):
+    """configs/dprnn_wsj0.yml end to end in this image: WAV lists -> PinnedLoader -> fit() -> best_model.pth -> evaluate() -> metrics.csv."""
+    from test_data import _make_corpus
+
+    from audio_only_speech_separation_b200.data import make_loaders
+    from audio_only_speech_separation_b200.fit import fit
+    from audio_only_speech_separation_b200.metrics import MetricsTracker, evaluate
+    from audio_only_speech_separation_b200.models import BaseModel
+
+    corpus = str(tmp_path / "wav")
+    _make_corpus(corpus, [6000, 7000, 5000, 8000, 6500, 9000])
+    cfg = {**CONFIG, "datamodule": {"data_name": "LRS2DataModule", "data_config": dict(
+        train_dir=corpus, valid_dir=corpus, test_dir=corpus, n_src=2, sample_rate=8000, fps=25, segment=0.5, normalize_audio=False, batch_size=2,
+        num_workers=2, pin_memory=True, persistent_workers=False, audio_only=True)}}
+    train, val, test = make_loaders(cfg["datamodule"]["data_config"])
+    exp = str(tmp_path / "exp")
+    hist = fit(cfg, lambda e: train, lambda e: val, exp, max_epochs=2, log=lambda s: None)
+    assert len(hist) == 2 and all(torch.isfinite(torch.tensor([h["train_loss"], h["val_loss"]])).all() for h in hist)
+    model = BaseModel.from_pretrain(os.path.join(exp, "best_model.pth"), sample_rate=8000, **cfg["audionet"]["audionet_config"]).cuda().eval()
+    tracker = evaluate(model, (test[i] for i in range(len(test))), MetricsTracker(os.path.join(exp, "metrics.csv")), batch_size=4)
+    res = tracker.final()
+    assert len(tracker.all_sisnrs) == 6 and all(map(lambda v: v == v, tracker.all_sisnrs_i)) and "si-snr_i" in res
+    assert os.path.exists(os.path.join(exp, "metrics.csv"))
