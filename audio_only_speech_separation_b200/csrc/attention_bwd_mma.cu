@@ -46,7 +46,7 @@ __device__ __forceinline__ void load_a_rows(const __nv_bfloat16* base, int strid
 }
 
 template <int D, bool SPLIT, bool DROP>
-__global__ void __launch_bounds__(256, (D == 16 ? 2 : 1)) attn_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict__ O,
+__global__ void __launch_bounds__(256, ((D == 16 || !SPLIT) ? 2 : 1)) attn_bwd_mma_kernel(const float* __restrict__ QKV, const float* __restrict__ O,
                                                               const float* __restrict__ LSE, const float* __restrict__ dO,
                                                               float* __restrict__ dQKV, int E, int heads, SeqMap m, float scale,
                                                               const unsigned drop_thr, const unsigned drop_key, const float drop_scale) {
@@ -56,15 +56,16 @@ __global__ void __launch_bounds__(256, (D == 16 ? 2 : 1)) attn_bwd_mma_kernel(co
     constexpr int DN = D / 8;      // n-tiles over the head width
     const int L = m.len;
     const int LP = (L + 63) & ~63;  // rows allocated / visited (multiple of the 64-wide blocks)
+    // hi planes of Q, K, V, dO, then (fp32-parity mode only) their lo planes: bf16 mode needs half the shared memory, two CTAs per SM
     __nv_bfloat16* Qh = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-    __nv_bfloat16* Ql = Qh + LP * RS;
-    __nv_bfloat16* Kh = Ql + LP * RS;
-    __nv_bfloat16* Kl = Kh + LP * RS;
-    __nv_bfloat16* Vh = Kl + LP * RS;
-    __nv_bfloat16* Vl = Vh + LP * RS;
-    __nv_bfloat16* Gh = Vl + LP * RS;
-    __nv_bfloat16* Gl = Gh + LP * RS;
-    float* lse = reinterpret_cast<float*>(Gl + LP * RS);   // [LP]  +big for padded rows: their probabilities vanish
+    __nv_bfloat16* Kh = Qh + LP * RS;
+    __nv_bfloat16* Vh = Kh + LP * RS;
+    __nv_bfloat16* Gh = Vh + LP * RS;
+    __nv_bfloat16* Ql = Gh + LP * RS;
+    __nv_bfloat16* Kl = SPLIT ? Ql + LP * RS : Ql;
+    __nv_bfloat16* Vl = SPLIT ? Kl + LP * RS : Ql;
+    __nv_bfloat16* Gl = SPLIT ? Vl + LP * RS : Ql;
+    float* lse = reinterpret_cast<float*>(SPLIT ? Gl + LP * RS : Ql);   // [LP]  +big for padded rows: their probabilities vanish
     float* dlt = lse + LP;                                 // [LP]  delta_i = dO_i . O_i
     float* kbias = dlt + LP;                               // [LP]  0 for real keys, -big for padded ones
 
@@ -90,13 +91,13 @@ __global__ void __launch_bounds__(256, (D == 16 ? 2 : 1)) attn_bwd_mma_kernel(co
         uint2 hi, lo;
         const int o = j * RS + cc * 4;
         split_pair(qv.x, qv.y, hi.x, lo.x); split_pair(qv.z, qv.w, hi.y, lo.y);
-        *reinterpret_cast<uint2*>(Qh + o) = hi; *reinterpret_cast<uint2*>(Ql + o) = lo;
+        *reinterpret_cast<uint2*>(Qh + o) = hi; if (SPLIT) *reinterpret_cast<uint2*>(Ql + o) = lo;
         split_pair(kv.x, kv.y, hi.x, lo.x); split_pair(kv.z, kv.w, hi.y, lo.y);
-        *reinterpret_cast<uint2*>(Kh + o) = hi; *reinterpret_cast<uint2*>(Kl + o) = lo;
+        *reinterpret_cast<uint2*>(Kh + o) = hi; if (SPLIT) *reinterpret_cast<uint2*>(Kl + o) = lo;
         split_pair(vv.x, vv.y, hi.x, lo.x); split_pair(vv.z, vv.w, hi.y, lo.y);
-        *reinterpret_cast<uint2*>(Vh + o) = hi; *reinterpret_cast<uint2*>(Vl + o) = lo;
+        *reinterpret_cast<uint2*>(Vh + o) = hi; if (SPLIT) *reinterpret_cast<uint2*>(Vl + o) = lo;
         split_pair(gv.x, gv.y, hi.x, lo.x); split_pair(gv.z, gv.w, hi.y, lo.y);
-        *reinterpret_cast<uint2*>(Gh + o) = hi; *reinterpret_cast<uint2*>(Gl + o) = lo;
+        *reinterpret_cast<uint2*>(Gh + o) = hi; if (SPLIT) *reinterpret_cast<uint2*>(Gl + o) = lo;
     }
     for (int i = tid; i < LP; i += 256) {
         float a = 0.f, l = 1e30f;
@@ -298,7 +299,7 @@ template <int D, bool SPLIT>
 cudaError_t launch_one(const float* QKV, const float* O, const float* LSE, const float* dO, float* dQKV, int E, int heads, const SeqMap& m,
                        cudaStream_t st, unsigned drop_thr, unsigned drop_key, float drop_scale) {
     const int LP = (m.len + 63) & ~63;
-    const size_t smem = (size_t)8 * LP * (D + 8) * sizeof(__nv_bfloat16) + (size_t)3 * LP * sizeof(float);
+    const size_t smem = (size_t)(SPLIT ? 8 : 4) * LP * (D + 8) * sizeof(__nv_bfloat16) + (size_t)3 * LP * sizeof(float);
     const float scale = 1.0f / sqrtf((float)D);
     cudaError_t e;
     if (drop_thr) {
