@@ -58,6 +58,7 @@ PROTOTYPES = {
     "dp_lstm_pack": (_i, [_p] * 10),
     "dp_bilstm_forward_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i64, _i64, _i64, _i, _i, _p]),
     "dp_lstm_recurrence_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i, _i, _p]),
+    "dp_lstm_recurrence_planes_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i, _i, _p]),
     "dp_bilstm_backward_f32": (_i, [_p, _p, _p, _p, _p, _i, _p, _i64, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "dp_groupnorm_finalize": (_i, [_p, _p, _i, _d, _d, _p]),
     "dp_groupnorm_residual_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),

@@ -276,6 +276,16 @@ int dp_lstm_recurrence_f32(const void* pack, float* G, float* H, float* Cst, int
     CK(launch_lstm_fwd(v.rec, G, H, Cst, m, is_split(precision), save != 0, S(stream)));
     return 0;
 }
+int dp_lstm_recurrence_planes_f32(const void* pack, float* G, float* H, float* Cst, void* h_hi, void* h_lo, void* hp_hi, void* hp_lo, int nseq,
+                                  int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int save, int precision, void* stream) {
+    LstmPackView v = view_pack(pack);
+    SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
+    LstmPlanes pl;
+    pl.h_hi = static_cast<__nv_bfloat16*>(h_hi); pl.h_lo = static_cast<__nv_bfloat16*>(h_lo);
+    pl.hp_hi = static_cast<__nv_bfloat16*>(hp_hi); pl.hp_lo = static_cast<__nv_bfloat16*>(hp_lo);
+    CK(launch_lstm_fwd(v.rec, G, H, Cst, m, is_split(precision), save != 0, S(stream), &pl));
+    return 0;
+}
 int dp_bilstm_backward_f32(const void* pack, float* G, const float* Cst, const float* dH, float* dx, int accumulate_dx, float* dbias,
                            int64_t P, int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int precision, void* stream) {
     LstmPackView v = view_pack(pack);

@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_pipe_kernel(const LstmPack w,
         pipe_block<NTB, NTA, SPLIT, SAVE>(accB, ahi, alo, hs_hi + RA * HST, hs_lo + RA * HST, accA, ga, hs_hi, hs_lo, (unsigned)t * st256,
                                           true, G, H, Cst, warp, lane);
     }
+    __syncthreads();  // every warp is done reading h_B of the step before (the last block's products) before anyone overwrites it
     {   // group B's last cell update
         const unsigned tl = (unsigned)(dir ? 0 : m.len - 1) * st256;
 #pragma unroll

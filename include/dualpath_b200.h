@@ -95,6 +95,11 @@ int dp_bilstm_forward_f32(const void* pack, const float* x, float* G, float* H, 
 /* the recurrence alone on precomputed gate pre-activations G (what dp_bilstm_forward_f32 runs after its GEMM) */
 int dp_lstm_recurrence_f32(const void* pack, float* G, float* H, float* Cst, int nseq, int len, int qdiv, int64_t s_hi,
                            int64_t s_lo, int64_t s_t, int save, int precision, void* stream);
+/* dp_lstm_recurrence_f32 with the operand planes the engines' GEMMs consume (any of them may be NULL, and so may H): h_hi / h_lo =
+ * bf16 hi / lo of h_t at every position [P,256]; hp_hi / hp_lo = "h_prev": the previous step's h of the same sequence at every
+ * position (zeros at a sequence's first step), the B operand of the dW_hh gradient GEMM. */
+int dp_lstm_recurrence_planes_f32(const void* pack, float* G, float* H, float* Cst, void* h_hi, void* h_lo, void* hp_hi, void* hp_lo, int nseq,
+                                  int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int save, int precision, void* stream);
 /* dH[P,256] -> G becomes d(pre-activations) [P,1024] (packed column order); dx[P,64] (=|+=) dG W_ih; dbias (optional,
  * [1024] packed order) += column sums of dG (= d b_ih = d b_hh). Weight grads via dp_linear_wgrad_f32 on G. */
 int dp_bilstm_backward_f32(const void* pack, float* G, const float* Cst, const float* dH, float* dx, int accumulate_dx,

@@ -270,3 +270,39 @@ def test_fused_tcgen05_lstm_matches_unfused_engine(manifest, precision):
         assert e[0] < 5e-5 and e[1] < 5e-5 and e[2] < 2e-3
     else:
         assert e[0] < 3e-2 and e[1] < 3e-2 and e[2] < 2e-1
+
+
+def test_multi_wave_batch_properties(manifest):
+    """B = 40 at T = 32000 (BASELINE configs[2] is B = 32): 3 280 / 4 000 sequences per pass, more than one wave of 24-sequence
+    tiles in the recurrence kernels.  Per-utterance independence at that size, forward (golden utterance embedded) and gradients
+    (the gradient of a batch-summed loss is the sum of per-utterance gradients)."""
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+
+    m, _, _ = _model(manifest, "dprnn_wsj0_b2_t8001")
+    g = torch.Generator().manual_seed(99)
+    x = (torch.randn(40, 32000, generator=g) * 0.1).cuda()
+    z = load_npz("model_dprnn_wsj0_b1_t32000.npz")
+    x[37] = torch.from_numpy(z["x"][0]).cuda()
+    with torch.no_grad():
+        y = m(x)
+        y7 = m(x[7:8])
+    # B = 1 runs the 16-warp recurrence kernel, B = 40 the pipelined one: same products, another summation order (~1e-5 after 12 layers)
+    assert bool(torch.isfinite(y).all()) and rel_l2(y[7:8], y7) < 3e-5
+    assert rel_l2(y[37], torch.from_numpy(z["y"][0])) < FP32_TOL
+    # training: mean loss over 40 utterances = mean of two half-batch losses; same for the gradients
+    m.train()
+    tgt = (torch.randn(40, 2, 32000, generator=g) * 0.1).cuda()
+    lossf = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)
+
+    def grads(sl):
+        for p in m.parameters():
+            p.grad = None
+        loss = lossf(m(x[sl]), tgt[sl])
+        loss.backward()
+        return loss.item(), torch.cat([p.grad.flatten() for p in m.parameters()]).clone()
+
+    l_all, g_all = grads(slice(0, 40))
+    l_a, g_a = grads(slice(0, 20))
+    l_b, g_b = grads(slice(20, 40))
+    assert abs(l_all - 0.5 * (l_a + l_b)) < 1e-5 * max(1.0, abs(l_all))
+    assert rel_l2(g_all, 0.5 * (g_a + g_b)) < 2e-5

@@ -406,3 +406,46 @@ def test_torch_library_ops_forward_and_autograd():
     rl = O.pit_loss(e2, tgt.cpu(), "sisdr", False)
     rl.backward()
     assert abs(loss.item() - rl.item()) < 1e-4 * max(1.0, abs(rl.item())) and rel_l2(est.grad, e2.grad) < 1e-4
+
+
+@pytest.mark.parametrize("layout", ["intra", "inter"])
+@pytest.mark.parametrize("mode", [0, 2, 3])
+def test_recurrence_plane_outputs_two_waves(ops, layout, mode):
+    """The operand planes the engines consume (h = hi + lo of every step, h_prev = the previous step's h, zeros at a sequence's first
+    step) from every forward kernel variant, at B = 24 (1 968 / 2 400 sequences: more than one wave of full 24-sequence tiles --
+    the size at which a missing barrier before the last cell update of the pipelined kernel showed), inference and training mode."""
+    from audio_only_speech_separation_b200 import _lib
+
+    lstm, sd, pack = _lstm_and_pack(ops, seed=4)
+    B, S, K = 24, 82, 100
+    P = B * S * K
+    g = torch.Generator().manual_seed(11)
+    G0 = (torch.randn(P, 1024, generator=g) * 0.5).cuda()
+    nseq, ln, qdiv, s_hi, s_lo, s_t = (B * S, K, 1 << 30, 0, K, 1) if layout == "intra" else (B * K, S, K, S * K, 1, K)
+    L = _lib.lib()
+    try:
+        _lib.check(L.dp_set_lstm_pipeline(0))
+        Gr, Href = G0.clone(), torch.empty(P, 256, device="cuda")
+        _lib.check(L.dp_lstm_recurrence_f32(_lib.ptr(pack.buf), _lib.ptr(Gr), _lib.ptr(Href), None, nseq, ln, qdiv, s_hi, s_lo, s_t, 0, 0, _lib.stream_ptr()))
+        # h_prev reference: h shifted by one step along the sequence, per direction (forward: t - 1, backward: t + 1)
+        Hs = Href.reshape(B, S, K, 256)
+        ax = 2 if layout == "intra" else 1
+        prev = torch.zeros_like(Hs)
+        sl = [slice(None)] * 4
+        a, b = list(sl), list(sl)
+        a[ax], b[ax] = slice(1, None), slice(0, -1)
+        prev[tuple(a)][..., :128] = Hs[tuple(b)][..., :128]
+        prev[tuple(b)][..., 128:] = Hs[tuple(a)][..., 128:]
+        _lib.check(L.dp_set_lstm_pipeline(mode))
+        for rep in range(2):
+            for save in (0, 1):
+                Gw, C = G0.clone(), torch.empty(P, 256, device="cuda")
+                hh, hl, ph, plo = (torch.full((P, 256), float("nan"), device="cuda", dtype=torch.bfloat16) for _ in range(4))
+                _lib.check(L.dp_lstm_recurrence_planes_f32(_lib.ptr(pack.buf), _lib.ptr(Gw), None, _lib.ptr(C) if save else None, _lib.ptr(hh), _lib.ptr(hl),
+                                                          _lib.ptr(ph) if save else None, _lib.ptr(plo) if save else None, nseq, ln, qdiv, s_hi, s_lo,
+                                                          s_t, save, 0, _lib.stream_ptr()))
+                assert float(((hh.float() + hl.float()) - Href).abs().max()) < 1e-5, (mode, save, rep)
+                if save:
+                    assert float(((ph.float() + plo.float()).reshape(B, S, K, 256) - prev).abs().max()) < 1e-5, (mode, save, rep)
+    finally:
+        _lib.check(L.dp_set_lstm_pipeline(1))
