@@ -289,6 +289,14 @@ def test_multi_wave_batch_properties(manifest):
     # B = 1 runs the 16-warp recurrence kernel, B = 40 the pipelined one: same products, another summation order (~1e-5 after 12 layers)
     assert bool(torch.isfinite(y).all()) and rel_l2(y[7:8], y7) < 3e-5
     assert rel_l2(y[37], torch.from_numpy(z["y"][0])) < FP32_TOL
+    # bf16 mode (fused tcgen05 LSTM kernel / 16-warp kernels) at the same size
+    m.precision = "bf16"
+    with torch.no_grad():
+        yb = m(x)
+        yb7, yb39 = m(x[7:8]), m(x[39:40])
+        yb2 = m(x)
+    m.precision = "fp32"
+    assert rel_l2(yb, yb2) == 0.0 and rel_l2(yb[7:8], yb7) < 1e-4 and rel_l2(yb[39:40], yb39) < 1e-4
     # training: mean loss over 40 utterances = mean of two half-batch losses; same for the gradients
     m.train()
     tgt = (torch.randn(40, 2, 32000, generator=g) * 0.1).cuda()
