@@ -282,3 +282,37 @@ def test_tcgen05_attention_vs_torch(E, heads, B, S, K, layout, precision):
     else:
         assert err < 2e-2
         assert rel_l2(oh.float(), o.reshape(-1, E)) < 1e-2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_batch_properties(precision):
+    """BASELINE shape (T = 32000) at B = 20 (multi-wave LSTM passes, 1 640 x 4 attention CTAs): run-to-run determinism, per-utterance
+    independence in the forward, and the gradient of a batch as the mean of its halves."""
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+    from audio_only_speech_separation_b200.models import TasNet
+
+    torch.manual_seed(3)
+    m = TasNet(sample_rate=8000, module="DPTNet").cuda().eval()
+    m.precision = precision
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(20, 32000, generator=g) * 0.1).cuda()
+    tgt = (torch.randn(20, 2, 32000, generator=g) * 0.1).cuda()
+    with torch.no_grad():
+        y, y2, y5 = m(x), m(x), m(x[5:6])
+    tol = 3e-5 if precision == "fp32" else 1e-3
+    assert bool(torch.isfinite(y).all()) and rel_l2(y, y2) == 0.0 and rel_l2(y[5:6], y5) < tol
+    m.train()
+    lossf = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)
+
+    def grads(sl):
+        for p in m.parameters():
+            p.grad = None
+        loss = lossf(m(x[sl]), tgt[sl])
+        loss.backward()
+        return loss.item(), torch.cat([p.grad.flatten() for p in m.parameters()]).clone()
+
+    l_all, g_all = grads(slice(0, 20))
+    l_a, g_a = grads(slice(0, 10))
+    l_b, g_b = grads(slice(10, 20))
+    assert abs(l_all - 0.5 * (l_a + l_b)) < 1e-4 * max(1.0, abs(l_all))
+    assert rel_l2(g_all, 0.5 * (g_a + g_b)) < (1e-3 if precision == "fp32" else 3e-2)

@@ -263,3 +263,37 @@ def test_training_with_dropout_matches_oracle_given_the_same_masks():
     m.eval()
     with torch.no_grad():
         assert abs(lossf(m(x.cuda()), tgt.cuda()).item() - nodrop) < 1e-4 * max(1.0, abs(nodrop))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_base_config_long_input_batch_properties(precision):
+    """configs/sepformer_base.yml at 8 s, B = 2: determinism, forward independence of the two utterances (up to the reference's
+    (spk, batch) row scramble, SURVEY A.4 #7), gradients without dropout as the mean of the per-utterance gradients."""
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+    from audio_only_speech_separation_b200.models import Sepformer
+
+    torch.manual_seed(2)
+    m = Sepformer(sample_rate=8000).cuda().eval()
+    m.precision = precision
+    g = torch.Generator().manual_seed(9)
+    x = (torch.randn(2, 64000, generator=g) * 0.1).cuda()
+    with torch.no_grad():
+        y, y2 = m(x), m(x)
+        singles = torch.cat([m(x[i : i + 1]) for i in range(2)])          # [2, 2, T]: rows (b, spk)
+    assert bool(torch.isfinite(y).all()) and rel_l2(y, y2) == 0.0
+    # batch-2 rows are the reference's reshape of (spk, b)-ordered rows: row r of the flattened output holds (spk, b) = divmod(r, 2)
+    scr = torch.stack([singles[b, s] for s in range(2) for b in range(2)]).reshape(2, 2, -1)
+    assert rel_l2(y, scr) < (3e-5 if precision == "fp32" else 2e-3)
+    m.train()
+    m.dropout = 0.0
+    tgt = (torch.randn(2, 2, 64000, generator=g) * 0.1).cuda()
+
+    def grad_of(fn):
+        for p in m.parameters():
+            p.grad = None
+        fn().backward()
+        return torch.cat([p.grad.flatten() for p in m.parameters()]).clone()
+
+    g1 = grad_of(lambda: m(x).pow(2).mean())
+    g2 = grad_of(lambda: 0.5 * (m(x[0:1]).pow(2).mean() + m(x[1:2]).pow(2).mean()))
+    assert rel_l2(g1, g2) < (1e-3 if precision == "fp32" else 3e-2)
