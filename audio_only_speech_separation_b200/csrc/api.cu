@@ -320,7 +320,7 @@ int dp_attention_forward_f32(const float* qkv, float* o, float* lse, int E, int 
 int dp_attention_backward_tc_f32(const float* qkv, const float* o, const float* lse, const float* d_o, float* d_qkv, int E, int heads, int nseq,
                                  int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int precision, void* stream) {
     SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
-    if (!attn_bwd_mma_supported(E, heads, m)) return fail("dp_attention_backward_tc_f32: head width E/heads must be 16 or 32 and the sequence length <= 256");
+    if (!attn_bwd_mma_supported(E, heads, m)) return fail("dp_attention_backward_tc_f32: head width E/heads must be 16 or 32 and the sequence length <= 320");
     CK(launch_attn_bwd_mma(qkv, o, lse, d_o, d_qkv, E, heads, m, is_split(precision), S(stream)));
     return 0;
 }

@@ -1,4 +1,4 @@
-// Self-attention backward on the warp-level tensor cores (sm_100a), for sequences of up to 256 positions and head widths 16 / 32.
+// Self-attention backward on the warp-level tensor cores (sm_100a), for sequences of up to 320 positions and head widths 16 / 32.
 //
 // Replaces autograd through nn.MultiheadAttention's core (look2hear/models/utils/dptnet.py:48, sepformer.py:124-133: bmm +
 // softmax + bmm with the [B*S*h, L, L] probabilities materialised) for the dual-path layouts.  One CTA = one (sequence, head):
@@ -16,7 +16,7 @@ namespace dp {
 namespace {
 
 constexpr float kLog2eB = 1.4426950408889634f;
-constexpr int LMAX = 256;
+constexpr int LMAX = 320;   // shared memory: 8 planes x 320 rows x 80 B (head width 32, fp32-parity mode) = 205 KB
 
 __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));

@@ -259,7 +259,8 @@ cudaError_t launch_dec_ola_general(const float* D, float* out, int B, int nspk, 
 // LSE (optional, [P,heads], log2 domain) is what the backward needs.  Head width E/heads must be 16 or 32.
 // O may be null when only the bf16 hi/lo planes (O_hi, O_lo: operands of the out-projection GEMM) are wanted.
 cudaError_t launch_attn_fwd(const float* QKV, float* O, float* LSE, int E, int heads, const SeqMap& m, cudaStream_t st,
-                            __nv_bfloat16* O_hi = nullptr, __nv_bfloat16* O_lo = nullptr);
+                            __nv_bfloat16* O_hi = nullptr, __nv_bfloat16* O_lo = nullptr, unsigned drop_thr = 0, unsigned drop_key = 0,
+                            float drop_scale = 1.f);
 cudaError_t launch_attn_bwd(const float* QKV, const float* O, const float* LSE, const float* dO, float* dQKV, int E, int heads,
                             const SeqMap& m, cudaStream_t st);
 // The same attention on tcgen05 (attention_tc5.cu): QKV given as bf16 hi/lo planes [P,3E] (what the QKV GEMM writes), TMA-fed;

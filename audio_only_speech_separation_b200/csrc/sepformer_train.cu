@@ -206,8 +206,8 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
         LstmFusedGeom gm;
         gm.inter = path; gm.len = m.len; gm.nseq = m.nseq; gm.K = g.K; gm.S = g.Sc; gm.B = B;
         const bool tc_attn = tma && attn_tc5_supported(N, heads, gm);
-        if (drop_thr && !(tma && tc_attn))
-            return fail("dp_sepformer_forward_train: dropout needs the TMA backend (dp_set_gemm_backend(2)), enc_dim in {128, 256}, d_ffn %% 128 == 0 and sequences <= 256");
+        if (drop_thr && !tma)
+            return fail("dp_sepformer_forward_train: dropout needs the TMA backend (dp_set_gemm_backend(2)), enc_dim in {128, 256} and d_ffn %% 128 == 0");
         float* Xin = at<float>(ws, l.X[pi]);
         float* R0 = at<float>(ws, l.layer[tp.first_layer].Rin);
         if (use_pe) {
@@ -250,7 +250,9 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
                     CK(launch_attn_fwd_tc5(Qh, sp ? Qh + pQ : nullptr, Oa, Oh, sp ? Oh + pN : nullptr, at<float>(ws, t.LSE), N, heads, gm, sp, st,
                                            drop_thr, drop_site_key(h->drop_seed, li, 0), drop_scale)); ++nl;
                 } else {
-                    CK(launch_attn_fwd(QKV, Oa, at<float>(ws, t.LSE), N, heads, m, st, Oh, sp ? Oh + pN : nullptr)); ++nl;
+                    // sequences beyond the tcgen05 kernel's 256 positions (16 s at 16 kHz: 258 chunks): exact CUDA-core kernel, same dropout masks
+                    CK(launch_attn_fwd(QKV, Oa, at<float>(ws, t.LSE), N, heads, m, st, Oh, sp ? Oh + pN : nullptr, drop_thr,
+                                       drop_site_key(h->drop_seed, li, 0), drop_scale)); ++nl;
                 }
                 {   // Rmid = Rin + O W_o^T + b_o
                     TmaGemmArgs a = tma_nt_args(Oh, sp ? Oh + pN : nullptr, N, whi + lo[2], wlo + lo[2], N, Rmid, N, PTi, N, N);
@@ -456,7 +458,7 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
         const TPath& tp = l.path[pi];
         const bool tma = train_tma(N, dffn);
         if (drop_thr && !(tma && attn_bwd_mma_supported(N, heads, m)))
-            return fail("dp_sepformer_backward: dropout needs the TMA backend, enc_dim in {128, 256}, d_ffn %% 128 == 0 and sequences <= 256");
+            return fail("dp_sepformer_backward: dropout needs the TMA backend, enc_dim in {128, 256}, d_ffn %% 128 == 0 and sequences <= 320");
         float* Uf = at<float>(ws, tp.Uf);
         float* mr = at<float>(ws, tp.mr);
         // X_out = Xin + gLN(Uf): gLN backward -> dU (d Uf); the residual branch keeps dX

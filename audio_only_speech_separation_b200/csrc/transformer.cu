@@ -29,7 +29,8 @@ __device__ __forceinline__ long long seq_base(const SeqMap& m, int q) {
 template <int D>
 __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ QKV, float* __restrict__ O, float* __restrict__ LSE,
                                                        int E, int heads, SeqMap m, float scale_log2, __nv_bfloat16* __restrict__ O_hi,
-                                                       __nv_bfloat16* __restrict__ O_lo) {
+                                                       __nv_bfloat16* __restrict__ O_lo, const unsigned drop_thr, const unsigned drop_key,
+                                                       const float drop_scale) {
     extern __shared__ __align__(16) float sm_att[];
     constexpr int DS = D + 4;  // padded row stride
     const int L = m.len;
@@ -86,8 +87,9 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
             for (int u = 0; u < 4; ++u) {
                 const int j = j0 + u;
                 if (j < L) {
-                    const float pj = exp2f(s[u] - cm);
-                    l += pj;
+                    float pj = exp2f(s[u] - cm);
+                    l += pj;   // the denominator is that of the un-dropped probabilities
+                    if (drop_thr && !drop_keep(drop_key, (uint32_t)p * (uint32_t)heads + (uint32_t)h, (uint32_t)j, drop_thr)) pj = 0.f;
                     const float4* vr = reinterpret_cast<const float4*>(Vs + j * DS);
 #pragma unroll
                     for (int c = 0; c < D / 4; ++c) {
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
             }
             mx = cm;
         }
-        const float inv = 1.0f / l;
+        const float inv = (drop_thr ? drop_scale : 1.0f) / l;
 #pragma unroll
         for (int d = 0; d < D; ++d) acc[d] *= inv;
         if (O != nullptr) {
@@ -458,7 +460,7 @@ inline int ln_grid(long long rows, int rpw) {
 }  // namespace
 
 cudaError_t launch_attn_fwd(const float* QKV, float* O, float* LSE, int E, int heads, const SeqMap& m, cudaStream_t st,
-                            __nv_bfloat16* O_hi, __nv_bfloat16* O_lo) {
+                            __nv_bfloat16* O_hi, __nv_bfloat16* O_lo, unsigned drop_thr, unsigned drop_key, float drop_scale) {
     if (m.nseq <= 0 || m.len <= 0) return cudaSuccess;
     const int D = E / heads;
     if (E % heads || (D != 16 && D != 32)) return cudaErrorInvalidValue;
@@ -471,11 +473,11 @@ cudaError_t launch_attn_fwd(const float* QKV, float* O, float* LSE, int E, int h
     if (D == 16) {
         e = cudaFuncSetAttribute(attn_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attn_fwd_kernel<16><<<grid, threads, smem, st>>>(QKV, O, LSE, E, heads, m, scale_log2, O_hi, O_lo);
+        attn_fwd_kernel<16><<<grid, threads, smem, st>>>(QKV, O, LSE, E, heads, m, scale_log2, O_hi, O_lo, drop_thr, drop_key, drop_scale);
     } else {
         e = cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attn_fwd_kernel<32><<<grid, threads, smem, st>>>(QKV, O, LSE, E, heads, m, scale_log2, O_hi, O_lo);
+        attn_fwd_kernel<32><<<grid, threads, smem, st>>>(QKV, O, LSE, E, heads, m, scale_log2, O_hi, O_lo, drop_thr, drop_key, drop_scale);
     }
     return cudaGetLastError();
 }

@@ -123,7 +123,7 @@ int dp_attention_forward_f32(const float* qkv, float* o, float* lse, int E, int 
 int dp_attention_backward_f32(const float* qkv, const float* o, const float* lse, const float* d_o, float* d_qkv, int E, int heads,
                               int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, void* stream);
 /* dp_attention_backward_f32 on the warp-level tensor cores (probabilities recomputed from lse, never stored; bf16x3 products in
- * fp32 mode, single bf16 products in bf16 mode).  Sequence length <= 256.  What the DPTNet / SepFormer engines use (TMA backend). */
+ * fp32 mode, single bf16 products in bf16 mode).  Sequence length <= 320.  What the DPTNet / SepFormer engines use (TMA backend). */
 int dp_attention_backward_tc_f32(const float* qkv, const float* o, const float* lse, const float* d_o, float* d_qkv, int E, int heads,
                                  int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int precision, void* stream);
 /* The same attention on the 5th-generation tensor cores: qkv given as bf16 hi/lo planes [P,3E] on a dual-path stream [B,S,K,.]

@@ -218,7 +218,8 @@ def test_training_tma_path_gradients_match_oracle():
     assert all(torch.isfinite(v).all() for v in gb.values())
 
 
-def test_training_with_dropout_matches_oracle_given_the_same_masks():
+@pytest.mark.parametrize("chunk,T", [(50, 2400), (8, 8800)])   # (8, 8800): inter-chunk sequences of 276 positions, beyond the tcgen05 attention
+def test_training_with_dropout_matches_oracle_given_the_same_masks(chunk, T):
     """The reference's four dropout sites per layer (attention probabilities, attention output, FFN hidden, FFN output; p = 0.1) on the
     TMA engine.  The masks are a counter-based function of (seed, layer, site, element); tests/dropout_ref.py replays it in numpy, so the
     oracle runs with the SAME masks and the loss and every gradient can be compared exactly (the backward regenerates the masks)."""
@@ -228,14 +229,14 @@ def test_training_with_dropout_matches_oracle_given_the_same_masks():
     from audio_only_speech_separation_b200.models import Sepformer
 
     cfg = dict(encoder_out_nchannels=128, intra_dffn=256, inter_dffn=256, intra_nhead=4, inter_nhead=4, intra_numlayers=2, inter_numlayers=1,
-               masknet_chunksize=50, masknet_numlayers=2)
+               masknet_chunksize=chunk, masknet_numlayers=2)
     torch.manual_seed(5)
     m = Sepformer(sample_rate=8000, **cfg)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     m = m.cuda().train()
     assert m.dropout == 0.1
     g = torch.Generator().manual_seed(21)
-    B, T, K = 2, 2400, 50
+    B, K = 2, chunk
     x = torch.randn(B, T, generator=g) * 0.1
     tgt = torch.randn(B, 2, T, generator=g) * 0.1
     torch.manual_seed(77)
