@@ -42,6 +42,7 @@ PROTOTYPES = {
     "dp_set_gemm_backend": (_i, [_i]),
     "dp_set_fused_lstm": (_i, [_i]),
     "dp_set_lstm_pipeline": (_i, [_i]),
+    "dp_set_attention_forward": (_i, [_i]),
     "dp_seg_geometry": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "dp_wave_geometry": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "dp_segment_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
@@ -64,6 +65,7 @@ PROTOTYPES = {
     "dp_groupnorm_residual_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p]),
     "dp_attention_forward_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _p]),
     "dp_attention_backward_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _p]),
+    "dp_attention_forward_tc_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "dp_attention_backward_tc_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "dp_attention_forward_planes_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "dp_add_layernorm_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _p]),

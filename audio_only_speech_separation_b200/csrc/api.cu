@@ -149,6 +149,10 @@ int dp_set_fused_lstm(int mode) {
     g_fused_lstm = mode;
     return 0;
 }
+int dp_set_attention_forward(int mode) {
+    if (attn_fwd_set_mode(mode) != 0) return fail("dp_set_attention_forward: 0 (automatic), 1 (tcgen05 kernel) or 2 (warp-level tensor-core kernel)");
+    return 0;
+}
 int dp_set_lstm_pipeline(int mode) {
     if (lstm_set_pipeline(mode) != 0) return fail("dp_set_lstm_pipeline: 0 (plain 8-warp kernels), 1 (automatic), 2 (pipelined sequence groups) or 3 (16-warp kernel)");
     return 0;
@@ -315,6 +319,13 @@ int dp_attention_forward_f32(const float* qkv, float* o, float* lse, int E, int 
     if (heads <= 0 || E % heads || (E / heads != 16 && E / heads != 32)) return fail("dp_attention_forward_f32: head width E/heads must be 16 or 32");
     SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
     CK(launch_attn_fwd(qkv, o, lse, E, heads, m, S(stream)));
+    return 0;
+}
+int dp_attention_forward_tc_f32(const float* qkv, float* o, void* o_hi, void* o_lo, float* lse, int E, int heads, int nseq, int len, int qdiv,
+                                int64_t s_hi, int64_t s_lo, int64_t s_t, int precision, void* stream) {
+    SeqMap m{nseq, len, qdiv, s_hi, s_lo, s_t};
+    if (!attn_bwd_mma_supported(E, heads, m)) return fail("dp_attention_forward_tc_f32: head width E/heads must be 16 or 32 and the sequence length <= 320");
+    CK(launch_attn_fwd_mma(qkv, o, static_cast<__nv_bfloat16*>(o_hi), static_cast<__nv_bfloat16*>(o_lo), lse, E, heads, m, is_split(precision), S(stream)));
     return 0;
 }
 int dp_attention_backward_tc_f32(const float* qkv, const float* o, const float* lse, const float* d_o, float* d_qkv, int E, int heads, int nseq,
@@ -702,7 +713,7 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
                 const long long plQ = g.PT * 192;
                 LstmFusedGeom gm;
                 gm.inter = pp & 1; gm.len = m.len; gm.nseq = m.nseq; gm.K = g.K; gm.S = g.Sc; gm.B = B;
-                const bool tc_attn = attn_tc5_supported(64, 4, gm);
+                const bool tc_attn = attn_tc5_supported(64, 4, gm) && !attn_fwd_prefers_mma(64, 4, m.len, sp);
                 {   // in_proj: [q|k|v] = x W_in^T + b_in
                     TmaGemmArgs a = tma_args(Xh, plX, 64, whi + po[12], wlo + po[12], 64, (train || !tc_attn) ? QKV : nullptr, 192, (int)g.PT, 192, 64);
                     if (tc_attn) { a.C_hi = Qh; a.C_lo = sp ? Qh + plQ : nullptr; a.ldch = 192; }
@@ -713,7 +724,12 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
                     CK(launch_attn_fwd_tc5(Qh, sp ? Qh + plQ : nullptr, train ? Oa : nullptr, Oh, sp ? Oh + plX : nullptr,
                                            train ? at<float>(ws, l.LSE[pp]) : nullptr, 64, 4, gm, sp, st)); ++nl;
                 } else {
-                    CK(launch_attn_fwd(QKV, train ? Oa : nullptr, train ? at<float>(ws, l.LSE[pp]) : nullptr, 64, 4, m, st, Oh, sp ? Oh + plX : nullptr)); ++nl;
+                    if (attn_bwd_mma_supported(64, 4, m)) {   // warp-level tensor cores (online softmax) on the fp32 QKV
+                        CK(launch_attn_fwd_mma(QKV, train ? Oa : nullptr, Oh, sp ? Oh + plX : nullptr, train ? at<float>(ws, l.LSE[pp]) : nullptr, 64, 4, m,
+                                               sp, st)); ++nl;
+                    } else {
+                        CK(launch_attn_fwd(QKV, train ? Oa : nullptr, train ? at<float>(ws, l.LSE[pp]) : nullptr, 64, 4, m, st, Oh, sp ? Oh + plX : nullptr)); ++nl;
+                    }
                 }
                 {   // out_proj
                     TmaGemmArgs a = tma_args(Oh, plX, 64, whi + po[14], wlo + po[14], 64, Y, 64, (int)g.PT, 64, 64);

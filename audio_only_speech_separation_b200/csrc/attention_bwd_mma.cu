@@ -295,6 +295,175 @@ __global__ void __launch_bounds__(256, ((D == 16 || !SPLIT) ? 2 : 1)) attn_bwd_m
     }
 }
 
+// ------------------------------------------------------------------------------------------------ forward (same machinery)
+// softmax(q k^T / sqrt(d)) v for sequences the tcgen05 kernel does not take (257..320 positions; 16 s at 16 kHz gives 258 chunks).
+// One CTA = one (sequence, head); K, V (all rows) and Q as bf16 hi / lo rows in shared memory; a warp owns 16-query tiles and walks
+// the keys in blocks of 64 with an online softmax (running row maximum / sum per thread quad), P re-used from the accumulator
+// fragments as the A operand of P V.  Outputs like the other forward kernels: O fp32 and / or planes, log-sum-exp (log2 domain).
+template <int D, bool SPLIT, bool DROP>
+__global__ void __launch_bounds__(256, (SPLIT ? 1 : 2)) attn_fwd_mma_kernel(const float* __restrict__ QKV, float* __restrict__ O,
+                                                                            __nv_bfloat16* __restrict__ O_hi, __nv_bfloat16* __restrict__ O_lo,
+                                                                            float* __restrict__ LSE, int E, int heads, SeqMap m, float scale,
+                                                                            const unsigned drop_thr, const unsigned drop_key, const float drop_scale) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int RS = D + 8, KS = D / 16, DN = D / 8;
+    const int L = m.len;
+    const int LP = (L + 63) & ~63;
+    __nv_bfloat16* Qh = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+    __nv_bfloat16* Kh = Qh + LP * RS;
+    __nv_bfloat16* Vh = Kh + LP * RS;
+    __nv_bfloat16* Ql = Vh + LP * RS;
+    __nv_bfloat16* Kl = SPLIT ? Ql + LP * RS : Ql;
+    __nv_bfloat16* Vl = SPLIT ? Kl + LP * RS : Ql;
+    float* kbias = reinterpret_cast<float*>(SPLIT ? Vl + LP * RS : Ql);   // [LP] 0 for real keys, -big for padded ones
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int q = blockIdx.x, h = blockIdx.y;
+    const long long base = (long long)(q / m.qdiv) * m.s_hi + (long long)(q % m.qdiv) * m.s_lo;
+    const int ld = 3 * E;
+    const float c2 = scale * kLog2eB;
+    for (int idx = tid; idx < LP * (D / 4); idx += 256) {
+        const int j = idx / (D / 4), cc = idx % (D / 4);
+        float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), kv = qv, vv = qv;
+        if (j < L) {
+            const float* row = QKV + (base + (long long)j * m.s_t) * ld + h * D + cc * 4;
+            qv = *reinterpret_cast<const float4*>(row);
+            kv = *reinterpret_cast<const float4*>(row + E);
+            vv = *reinterpret_cast<const float4*>(row + 2 * E);
+        }
+        uint2 hi, lo;
+        const int o = j * RS + cc * 4;
+        split_pair(qv.x, qv.y, hi.x, lo.x); split_pair(qv.z, qv.w, hi.y, lo.y);
+        *reinterpret_cast<uint2*>(Qh + o) = hi; if (SPLIT) *reinterpret_cast<uint2*>(Ql + o) = lo;
+        split_pair(kv.x, kv.y, hi.x, lo.x); split_pair(kv.z, kv.w, hi.y, lo.y);
+        *reinterpret_cast<uint2*>(Kh + o) = hi; if (SPLIT) *reinterpret_cast<uint2*>(Kl + o) = lo;
+        split_pair(vv.x, vv.y, hi.x, lo.x); split_pair(vv.z, vv.w, hi.y, lo.y);
+        *reinterpret_cast<uint2*>(Vh + o) = hi; if (SPLIT) *reinterpret_cast<uint2*>(Vl + o) = lo;
+    }
+    for (int i = tid; i < LP; i += 256) kbias[i] = i < L ? 0.f : -1e30f;
+    __syncthreads();
+
+    const int ntile = (L + 15) >> 4;
+    for (int mt = warp; mt < ntile; mt += 8) {
+        const int r0 = mt * 16;
+        uint32_t qa_h[KS][4], qa_l[KS][4];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            load_a_rows(Qh, RS, r0, ks * 16, lane, qa_h[ks]);
+            if (SPLIT) load_a_rows(Ql, RS, r0, ks * 16, lane, qa_l[ks]);
+        }
+        const uint32_t drow0 = (uint32_t)(base + (long long)(r0 + g) * m.s_t) * (uint32_t)heads + (uint32_t)h;
+        const uint32_t drow1 = (uint32_t)(base + (long long)(r0 + g + 8) * m.s_t) * (uint32_t)heads + (uint32_t)h;
+        float mx0 = -1e30f, mx1 = -1e30f, l0 = 0.f, l1 = 0.f;   // running maxima (log2 domain) and this thread's partial row sums
+        float o[DN][4];
+#pragma unroll
+        for (int n = 0; n < DN; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[n][e] = 0.f;
+        for (int j0 = 0; j0 < LP; j0 += 64) {
+            float s[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[n][e] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    uint32_t bh[2], bl[2];
+                    load_b_rows(Kh, RS, j0 + n * 8, ks * 16, lane, bh);
+                    if (SPLIT) load_b_rows(Kl, RS, j0 + n * 8, ks * 16, lane, bl);
+                    mma3<SPLIT>(s[n], qa_h[ks], qa_l[ks], bh, bl);
+                }
+            }
+            float b0 = -1e30f, b1 = -1e30f;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const float kb0 = kbias[j0 + n * 8 + 2 * c], kb1 = kbias[j0 + n * 8 + 2 * c + 1];
+                s[n][0] = fmaf(s[n][0], c2, kb0); s[n][1] = fmaf(s[n][1], c2, kb1);
+                s[n][2] = fmaf(s[n][2], c2, kb0); s[n][3] = fmaf(s[n][3], c2, kb1);
+                b0 = fmaxf(b0, fmaxf(s[n][0], s[n][1])); b1 = fmaxf(b1, fmaxf(s[n][2], s[n][3]));
+            }
+            b0 = fmaxf(b0, __shfl_xor_sync(0xffffffffu, b0, 1)); b0 = fmaxf(b0, __shfl_xor_sync(0xffffffffu, b0, 2));
+            b1 = fmaxf(b1, __shfl_xor_sync(0xffffffffu, b1, 1)); b1 = fmaxf(b1, __shfl_xor_sync(0xffffffffu, b1, 2));
+            const float n0 = fmaxf(mx0, b0), n1 = fmaxf(mx1, b1);
+            const float f0 = ex2_approx(mx0 - n0), f1 = ex2_approx(mx1 - n1);
+            mx0 = n0; mx1 = n1;
+            l0 *= f0; l1 *= f1;
+#pragma unroll
+            for (int n = 0; n < DN; ++n) { o[n][0] *= f0; o[n][1] *= f0; o[n][2] *= f1; o[n][3] *= f1; }
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                s[n][0] = ex2_approx(s[n][0] - mx0); s[n][1] = ex2_approx(s[n][1] - mx0);
+                s[n][2] = ex2_approx(s[n][2] - mx1); s[n][3] = ex2_approx(s[n][3] - mx1);
+                l0 += s[n][0] + s[n][1]; l1 += s[n][2] + s[n][3];   // denominators of the un-dropped probabilities
+                if (DROP) {
+                    const uint32_t jc = (uint32_t)(j0 + n * 8 + 2 * c);
+                    if (!drop_keep(drop_key, drow0, jc, drop_thr)) s[n][0] = 0.f;
+                    if (!drop_keep(drop_key, drow0, jc + 1, drop_thr)) s[n][1] = 0.f;
+                    if (!drop_keep(drop_key, drow1, jc, drop_thr)) s[n][2] = 0.f;
+                    if (!drop_keep(drop_key, drow1, jc + 1, drop_thr)) s[n][3] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                uint32_t ah[4], al[4];
+                split_pair(s[2 * kk][0], s[2 * kk][1], ah[0], al[0]);
+                split_pair(s[2 * kk][2], s[2 * kk][3], ah[1], al[1]);
+                split_pair(s[2 * kk + 1][0], s[2 * kk + 1][1], ah[2], al[2]);
+                split_pair(s[2 * kk + 1][2], s[2 * kk + 1][3], ah[3], al[3]);
+#pragma unroll
+                for (int n = 0; n < DN; ++n) {
+                    uint32_t bh[2], bl[2];
+                    load_b_cols(Vh, RS, j0 + kk * 16, n * 8, lane, bh);
+                    if (SPLIT) load_b_cols(Vl, RS, j0 + kk * 16, n * 8, lane, bl);
+                    mma3<SPLIT>(o[n], ah, al, bh, bl);
+                }
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int i = r0 + g + 8 * hh;
+            if (i >= L) continue;
+            const float lsum = hh ? l1 : l0, inv = (DROP ? drop_scale : 1.0f) / lsum;
+            const size_t pos = (size_t)(base + (long long)i * m.s_t);
+#pragma unroll
+            for (int n = 0; n < DN; ++n) {
+                const float v0 = o[n][2 * hh] * inv, v1 = o[n][2 * hh + 1] * inv;
+                const size_t off = pos * E + h * D + n * 8 + 2 * c;
+                if (O != nullptr) *reinterpret_cast<float2*>(O + off) = make_float2(v0, v1);
+                if (O_hi != nullptr) {
+                    uint32_t ph, pl;
+                    split_pair(v0, v1, ph, pl);
+                    *reinterpret_cast<uint32_t*>(O_hi + off) = ph;
+                    if (O_lo != nullptr) *reinterpret_cast<uint32_t*>(O_lo + off) = pl;
+                }
+            }
+            if (LSE != nullptr && c == 0) LSE[pos * heads + h] = (hh ? mx1 : mx0) + log2f(lsum);
+        }
+    }
+}
+
+template <int D, bool SPLIT>
+cudaError_t launch_fwd_one(const float* QKV, float* O, __nv_bfloat16* O_hi, __nv_bfloat16* O_lo, float* LSE, int E, int heads, const SeqMap& m,
+                           cudaStream_t st, unsigned drop_thr, unsigned drop_key, float drop_scale) {
+    const int LP = (m.len + 63) & ~63;
+    const size_t smem = (size_t)(SPLIT ? 6 : 3) * LP * (D + 8) * sizeof(__nv_bfloat16) + (size_t)LP * sizeof(float);
+    const float scale = 1.0f / sqrtf((float)D);
+    cudaError_t e;
+    if (drop_thr) {
+        e = cudaFuncSetAttribute(attn_fwd_mma_kernel<D, SPLIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attn_fwd_mma_kernel<D, SPLIT, true><<<dim3(m.nseq, heads), 256, smem, st>>>(QKV, O, O_hi, O_lo, LSE, E, heads, m, scale, drop_thr, drop_key, drop_scale);
+    } else {
+        e = cudaFuncSetAttribute(attn_fwd_mma_kernel<D, SPLIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attn_fwd_mma_kernel<D, SPLIT, false><<<dim3(m.nseq, heads), 256, smem, st>>>(QKV, O, O_hi, O_lo, LSE, E, heads, m, scale, 0u, 0u, 1.f);
+    }
+    return cudaGetLastError();
+}
+
 template <int D, bool SPLIT>
 cudaError_t launch_one(const float* QKV, const float* O, const float* LSE, const float* dO, float* dQKV, int E, int heads, const SeqMap& m,
                        cudaStream_t st, unsigned drop_thr, unsigned drop_key, float drop_scale) {
@@ -316,6 +485,25 @@ cudaError_t launch_one(const float* QKV, const float* O, const float* LSE, const
 
 }  // namespace
 
+namespace {
+int g_attn_fwd_mode = 0;   // 0 automatic, 1 tcgen05 kernel wherever it applies, 2 warp-level kernel wherever it applies
+}
+int attn_fwd_set_mode(int mode) {
+    if (mode < 0 || mode > 2) return -1;
+    g_attn_fwd_mode = mode;
+    return 0;
+}
+// Measured on B200 (tests/tools/time_attention.py, forward, one layer): bf16 mode 86 / 90 us (warp-level) against 120 / 163 us (tcgen05)
+// for SepFormer's 250 / 130-position sequences, 98 / 113 against 112 / 130 us for DPTNet; fp32-parity mode 159 against 136 us at 250
+// positions (three split products on the legacy pipe), but 174 / 112 / 131 against 182 / 128 / 152 us for the shorter ones.
+bool attn_fwd_prefers_mma(int E, int heads, int len, bool split) {
+    SeqMap m{1, len, 1, 0, 0, 1};
+    if (!attn_bwd_mma_supported(E, heads, m)) return false;
+    if (g_attn_fwd_mode == 1) return false;
+    if (g_attn_fwd_mode == 2) return true;
+    return !split || len <= 192;
+}
+
 bool attn_bwd_mma_supported(int E, int heads, const SeqMap& m) {
     if (heads <= 0 || E % heads) return false;
     const int D = E / heads;
@@ -331,6 +519,17 @@ cudaError_t launch_attn_bwd_mma(const float* QKV, const float* O, const float* L
     if (D == 16) return split ? DP_AB(16, true) : DP_AB(16, false);
     return split ? DP_AB(32, true) : DP_AB(32, false);
 #undef DP_AB
+}
+
+cudaError_t launch_attn_fwd_mma(const float* QKV, float* O, __nv_bfloat16* O_hi, __nv_bfloat16* O_lo, float* LSE, int E, int heads,
+                                const SeqMap& m, bool split, cudaStream_t st, unsigned drop_thr, unsigned drop_key, float drop_scale) {
+    if (m.nseq <= 0 || m.len <= 0) return cudaSuccess;
+    if (!attn_bwd_mma_supported(E, heads, m)) return cudaErrorInvalidValue;
+    const int D = E / heads;
+#define DP_AF(DD, SP) launch_fwd_one<DD, SP>(QKV, O, O_hi, O_lo, LSE, E, heads, m, st, drop_thr, drop_key, drop_scale)
+    if (D == 16) return split ? DP_AF(16, true) : DP_AF(16, false);
+    return split ? DP_AF(32, true) : DP_AF(32, false);
+#undef DP_AF
 }
 
 }  // namespace dp

@@ -269,6 +269,13 @@ bool attn_tc5_supported(int E, int heads, const LstmFusedGeom& gm);
 // attention backward on the warp-level tensor cores (attention_bwd_mma.cu): sequences <= 256, head width 16 / 32;
 // split = bf16x3 products (fp32-parity mode), otherwise single bf16 products.  Same arguments as launch_attn_bwd.
 bool attn_bwd_mma_supported(int E, int heads, const SeqMap& m);
+// which forward kernel the engines use where both apply (0 automatic from measurements, 1 tcgen05, 2 warp-level)
+int attn_fwd_set_mode(int mode);
+bool attn_fwd_prefers_mma(int E, int heads, int len, bool split);
+// forward on the same machinery (online softmax): O fp32 and / or planes, log-sum-exp; same shape limits as the backward
+cudaError_t launch_attn_fwd_mma(const float* QKV, float* O, __nv_bfloat16* O_hi, __nv_bfloat16* O_lo, float* LSE, int E, int heads,
+                                const SeqMap& m, bool split, cudaStream_t st, unsigned drop_thr = 0, unsigned drop_key = 0,
+                                float drop_scale = 1.f);
 // drop_thr != 0: attention-probability dropout, mask element (position of the query * heads + head, key index)
 cudaError_t launch_attn_bwd_mma(const float* QKV, const float* O, const float* LSE, const float* dO, float* dQKV, int E, int heads,
                                 const SeqMap& m, bool split, cudaStream_t st, unsigned drop_thr = 0, unsigned drop_key = 0,

@@ -200,7 +200,7 @@ int dp_sepformer_forward(dp_sepformer* h, const float* params, const void* pack,
             const bool tma = gemm_backend() == 2 && dffn % 64 == 0;
             LstmFusedGeom gm;
             gm.inter = path; gm.len = m.len; gm.nseq = m.nseq; gm.K = g.K; gm.S = g.Sc; gm.B = B;
-            const bool tc_attn = tma && attn_tc5_supported(N, heads, gm);
+            const bool tc_attn = tma && attn_tc5_supported(N, heads, gm) && !attn_fwd_prefers_mma(N, heads, m.len, sp);
             __nv_bfloat16* Uh = at<__nv_bfloat16>(ws, l.Uhl);
             __nv_bfloat16* Ul = sp ? Uh + g.PT * N : nullptr;
             __nv_bfloat16* Oh = at<__nv_bfloat16>(ws, l.Ohl);
@@ -225,7 +225,11 @@ int dp_sepformer_forward(dp_sepformer* h, const float* params, const void* pack,
                     TmaGemmArgs a = tma_nt_args(Uh, Ul, N, whi + lo[0], wlo + lo[0], N, QKV, 3 * N, PTi, 3 * N, N);
                     a.bias = params + lo[1];
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
-                    CK(launch_attn_fwd(QKV, nullptr, nullptr, N, heads, m, st, Oh, Ol)); ++nl;
+                    if (attn_bwd_mma_supported(N, heads, m)) {   // 257..320 positions: warp-level tensor cores
+                        CK(launch_attn_fwd_mma(QKV, nullptr, Oh, Ol, nullptr, N, heads, m, sp, st)); ++nl;
+                    } else {
+                        CK(launch_attn_fwd(QKV, nullptr, nullptr, N, heads, m, st, Oh, Ol)); ++nl;
+                    }
                 }
                 {
                     TmaGemmArgs a = tma_nt_args(Oh, Ol, N, whi + lo[2], wlo + lo[2], N, pre ? R : U, N, PTi, N, N);

@@ -205,7 +205,7 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
         const bool tma = train_tma(N, dffn);
         LstmFusedGeom gm;
         gm.inter = path; gm.len = m.len; gm.nseq = m.nseq; gm.K = g.K; gm.S = g.Sc; gm.B = B;
-        const bool tc_attn = tma && attn_tc5_supported(N, heads, gm);
+        const bool tc_attn = tma && attn_tc5_supported(N, heads, gm) && !attn_fwd_prefers_mma(N, heads, m.len, sp);
         if (drop_thr && !tma)
             return fail("dp_sepformer_forward_train: dropout needs the TMA backend (dp_set_gemm_backend(2)), enc_dim in {128, 256} and d_ffn %% 128 == 0");
         float* Xin = at<float>(ws, l.X[pi]);
@@ -251,8 +251,13 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
                                            drop_thr, drop_site_key(h->drop_seed, li, 0), drop_scale)); ++nl;
                 } else {
                     // sequences beyond the tcgen05 kernel's 256 positions (16 s at 16 kHz: 258 chunks): exact CUDA-core kernel, same dropout masks
-                    CK(launch_attn_fwd(QKV, Oa, at<float>(ws, t.LSE), N, heads, m, st, Oh, sp ? Oh + pN : nullptr, drop_thr,
-                                       drop_site_key(h->drop_seed, li, 0), drop_scale)); ++nl;
+                    if (attn_bwd_mma_supported(N, heads, m)) {
+                        CK(launch_attn_fwd_mma(QKV, Oa, Oh, sp ? Oh + pN : nullptr, at<float>(ws, t.LSE), N, heads, m, sp, st, drop_thr,
+                                               drop_site_key(h->drop_seed, li, 0), drop_scale)); ++nl;
+                    } else {
+                        CK(launch_attn_fwd(QKV, Oa, at<float>(ws, t.LSE), N, heads, m, st, Oh, sp ? Oh + pN : nullptr, drop_thr,
+                                           drop_site_key(h->drop_seed, li, 0), drop_scale)); ++nl;
+                    }
                 }
                 {   // Rmid = Rin + O W_o^T + b_o
                     TmaGemmArgs a = tma_nt_args(Oh, sp ? Oh + pN : nullptr, N, whi + lo[2], wlo + lo[2], N, Rmid, N, PTi, N, N);

@@ -24,6 +24,7 @@ __all__ = [
     "groupnorm_residual",
     "attention",
     "attention_backward",
+    "attention_tensor_cores",
     "add_layernorm",
     "layernorm_backward",
     "split_rows",
@@ -229,6 +230,19 @@ def attention(qkv: torch.Tensor, heads: int, layout: str, *, save=False):
     nseq, ln, qdiv, s_hi, s_lo, s_t = _seq_map(layout, B, S, K)
     check(lib().dp_attention_forward_f32(ptr(qkv), ptr(o), ptr(lse), E, heads, nseq, ln, qdiv, s_hi, s_lo, s_t, stream_ptr()),
           "dp_attention_forward_f32")
+    return o, lse
+
+
+def attention_tensor_cores(qkv: torch.Tensor, heads: int, layout: str, *, precision="fp32", save=False):
+    """:func:`attention` on the warp-level tensor cores (online softmax; sequences <= 320): returns ``(o, lse)``."""
+    require_cuda(qkv, "qkv")
+    B, S, K, E3 = qkv.shape
+    E = E3 // 3
+    o = torch.empty(B, S, K, E, device=qkv.device, dtype=torch.float32)
+    lse = torch.empty(B * S * K, heads, device=qkv.device, dtype=torch.float32) if save else None
+    nseq, ln, qdiv, s_hi, s_lo, s_t = _seq_map(layout, B, S, K)
+    check(lib().dp_attention_forward_tc_f32(ptr(qkv), ptr(o), None, None, ptr(lse), E, heads, nseq, ln, qdiv, s_hi, s_lo, s_t, _prec(precision),
+                                            stream_ptr()), "dp_attention_forward_tc_f32")
     return o, lse
 
 

@@ -38,6 +38,10 @@ int dp_set_fused_lstm(int mode);
  * 3 = 16-warp kernel (8 hidden units per warp, 128 registers, four warps per scheduler); 1 (default) = automatic by pass size and
  * precision.  All variants perform the same arithmetic in the same order per cell. */
 int dp_set_lstm_pipeline(int mode);
+/* Attention forward kernel of the DPTNet / SepFormer engines where both apply (sequences <= 256): 1 = tcgen05 kernel (TMA-fed, scores in
+ * tensor memory), 2 = warp-level tensor-core kernel (online softmax, fp32 QKV in), 0 (default) = the faster one per shape and precision
+ * as measured (tests/tools/time_attention.py). */
+int dp_set_attention_forward(int mode);
 
 /* ---- geometry (integer index maps) --------------------------------------------------------------------- */
 /* gc3_basics.py:63-76 pad_segment: rest and chunk count S for L frames and chunk size K (K even). */
@@ -122,8 +126,11 @@ int dp_attention_forward_f32(const float* qkv, float* o, float* lse, int E, int 
                              int64_t s_lo, int64_t s_t, void* stream);
 int dp_attention_backward_f32(const float* qkv, const float* o, const float* lse, const float* d_o, float* d_qkv, int E, int heads,
                               int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, void* stream);
-/* dp_attention_backward_f32 on the warp-level tensor cores (probabilities recomputed from lse, never stored; bf16x3 products in
+/* dp_attention_forward_f32 / dp_attention_backward_f32 on the warp-level tensor cores (forward: online softmax over 64-key blocks;
+ * o fp32 and / or o_hi / o_lo planes, lse optional).  Backward: (probabilities recomputed from lse, never stored; bf16x3 products in
  * fp32 mode, single bf16 products in bf16 mode).  Sequence length <= 320.  What the DPTNet / SepFormer engines use (TMA backend). */
+int dp_attention_forward_tc_f32(const float* qkv, float* o, void* o_hi, void* o_lo, float* lse, int E, int heads, int nseq, int len, int qdiv,
+                                int64_t s_hi, int64_t s_lo, int64_t s_t, int precision, void* stream);
 int dp_attention_backward_tc_f32(const float* qkv, const float* o, const float* lse, const float* d_o, float* d_qkv, int E, int heads,
                                  int nseq, int len, int qdiv, int64_t s_hi, int64_t s_lo, int64_t s_t, int precision, void* stream);
 /* The same attention on the 5th-generation tensor cores: qkv given as bf16 hi/lo planes [P,3E] on a dual-path stream [B,S,K,.]

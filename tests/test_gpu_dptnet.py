@@ -225,6 +225,13 @@ def test_attention_backward_tensor_cores_vs_torch(E, heads, B, S, K, layout):
         ref = _torch_mha_core(ref_in.permute(0, 2, 1, 3).reshape(B * K, S, 3 * E), heads).reshape(B, K, S, E).permute(0, 2, 1, 3)
     ref.backward(d_o.double())
     o, lse = ops.attention(qkv.cuda(), heads, layout, save=True)
+    # the forward on the same machinery (online softmax), then the backward from ITS output / log-sum-exp
+    o_tc, lse_tc = ops.attention_tensor_cores(qkv.cuda(), heads, layout, save=True)
+    o_16, _ = ops.attention_tensor_cores(qkv.cuda(), heads, layout, precision="bf16")
+    ef, ef16 = rel_l2(o_tc, ref.detach()), rel_l2(o_16, ref.detach())
+    record("attention_fwd_tc", E=E, heads=heads, S=S, K=K, layout=layout, fp32=ef, bf16=ef16)
+    assert ef < 2e-5 and ef16 < 2e-2 and float((lse_tc - lse).abs().max()) < 1e-4
+    o, lse = o_tc, lse_tc
     exact = ops.attention_backward(qkv.cuda(), o, lse, d_o.cuda(), heads, layout)
     dq = ops.attention_backward(qkv.cuda(), o, lse, d_o.cuda(), heads, layout, tensor_cores=True)
     dq16 = ops.attention_backward(qkv.cuda(), o, lse, d_o.cuda(), heads, layout, tensor_cores=True, precision="bf16")
@@ -316,3 +323,34 @@ def test_full_size_batch_properties(precision):
     l_b, g_b = grads(slice(10, 20))
     assert abs(l_all - 0.5 * (l_a + l_b)) < 1e-4 * max(1.0, abs(l_all))
     assert rel_l2(g_all, 0.5 * (g_a + g_b)) < (1e-3 if precision == "fp32" else 3e-2)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_engine_attention_forward_kernels_agree(manifest, mode):
+    """DPTNet engine with the tcgen05 (1) / warp-level (2) attention forward: forward against the oracle, gradients against each other."""
+    from audio_only_speech_separation_b200 import _lib
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+
+    m, sd, cfg = _model(manifest, layer=2)
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 4000, generator=g) * 0.1
+    tgt = torch.randn(2, 2, 4000, generator=g) * 0.1
+    with torch.no_grad():
+        ref = O.tasnet_forward(sd, x, module="DPTNet", layer=2)
+    lossf = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)
+    out = {}
+    for md in (mode, 0):
+        _lib.check(_lib.lib().dp_set_attention_forward(md))
+        try:
+            m.eval()
+            with torch.no_grad():
+                y = m(x.cuda())
+            m.train()
+            for p in m.parameters():
+                p.grad = None
+            lossf(m(x.cuda()), tgt.cuda()).backward()
+            out[md] = (y, torch.cat([p.grad.flatten() for p in m.parameters()]).clone())
+        finally:
+            _lib.check(_lib.lib().dp_set_attention_forward(0))
+    assert rel_l2(out[mode][0], ref) < 1e-4
+    assert rel_l2(out[mode][1], out[0][1]) < 2e-3

@@ -298,3 +298,26 @@ def test_base_config_long_input_batch_properties(precision):
     g1 = grad_of(lambda: m(x).pow(2).mean())
     g2 = grad_of(lambda: 0.5 * (m(x[0:1]).pow(2).mean() + m(x[1:2]).pow(2).mean()))
     assert rel_l2(g1, g2) < (1e-3 if precision == "fp32" else 3e-2)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_engine_attention_forward_kernels_agree_with_reference(manifest, mode):
+    """dp_set_attention_forward: the tcgen05 kernel (1) and the warp-level tensor-core kernel (2) inside the engines, both against the
+    reference golden (fp32 mode) and within the bf16 budget; the default picks per shape / precision from measurements."""
+    from audio_only_speech_separation_b200 import _lib
+
+    case = "sepformer_base_b1_t16000"
+    m, _, _ = _model(manifest, case)
+    z = load_npz(f"model_{case}.npz")
+    _lib.check(_lib.lib().dp_set_attention_forward(mode))
+    try:
+        with torch.no_grad():
+            y = m(torch.from_numpy(z["x"]).cuda())
+            m.precision = "bf16"
+            y16 = m(torch.from_numpy(z["x"]).cuda())
+            m.precision = "fp32"
+    finally:
+        _lib.check(_lib.lib().dp_set_attention_forward(0))
+    ref = torch.from_numpy(z["y"])
+    record("sepformer_fwd_attention_mode", mode=mode, fp32=rel_l2(y, ref), bf16=rel_l2(y16, ref))
+    assert rel_l2(y, ref) < FP32_TOL and rel_l2(y16, ref) < 3e-2
