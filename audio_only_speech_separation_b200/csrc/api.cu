@@ -823,7 +823,10 @@ int dp_tasnet_forward(dp_tasnet* h, const float* params, const void* pack, const
             pl.h_hi = Hhl; pl.h_lo = sp ? Hhl + plH : nullptr;
             pl.hp_hi = train ? at<__nv_bfloat16>(ws, l.Hphl[pp]) : nullptr;
             pl.hp_lo = (train && sp) ? pl.hp_hi + plH : nullptr;
-            if (g_fused_lstm == 2 || (g_fused_lstm == 1 && !sp)) {
+            // automatic: bf16 mode and at least ~one wave of sequences.  Measured (tests/tools/time_lstm.py, DPRNN forward): B = 16 bf16
+            // 5.92 ms fused vs 5.95 ms unfused; B = 1 bf16 5.30 vs 1.42 ms (the fused kernel's 64-sequence tiles leave most SMs idle)
+            const int nseq_path = (pp & 1) ? B * g.K : B * g.Sc;
+            if (g_fused_lstm == 2 || (g_fused_lstm == 1 && !sp && nseq_path >= 1312)) {
                 // input projection + recurrence in one tcgen05 kernel: the [P,1024] gate pre-activations never exist in HBM
                 LstmFusedGeom gm;
                 gm.inter = pp & 1; gm.len = (pp & 1) ? g.Sc : g.K; gm.nseq = (pp & 1) ? B * g.K : B * g.Sc; gm.K = g.K; gm.S = g.Sc; gm.B = B;

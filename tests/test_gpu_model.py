@@ -296,7 +296,9 @@ def test_multi_wave_batch_properties(manifest):
         yb7, yb39 = m(x[7:8]), m(x[39:40])
         yb2 = m(x)
     m.precision = "fp32"
-    assert rel_l2(yb, yb2) == 0.0 and rel_l2(yb[7:8], yb7) < 1e-4 and rel_l2(yb[39:40], yb39) < 1e-4
+    # B = 40 runs the fused tcgen05 LSTM kernel, B = 1 the 16-warp kernels: two bf16 algorithms, equal to bf16 accuracy only
+    assert rel_l2(yb, yb2) == 0.0 and rel_l2(yb[7:8], yb7) < 2e-2 and rel_l2(yb[39:40], yb39) < 2e-2
+    assert rel_l2(yb[7:8], y7) < 2e-2
     # training: mean loss over 40 utterances = mean of two half-batch losses; same for the gradients
     m.train()
     tgt = (torch.randn(40, 2, 32000, generator=g) * 0.1).cuda()
