@@ -122,8 +122,12 @@ SeqMap seq_map(const SGeo& g, int B, int path) {
 bool train_tma(int N, int dffn) { return gemm_backend() == 2 && N % 128 == 0 && N <= 256 && dffn % 128 == 0; }
 
 int check_trainable(const dp_sepformer* h) {
-    if (!h->cfg.intra_norm_before || !h->cfg.inter_norm_before)
-        return fail("SepFormer training engine covers pre-norm layers (configs/sepformer_base.yml); post-norm is inference only");
+    const dp_sepformer_config& c = h->cfg;
+    if (c.intra_norm_before && c.inter_norm_before) return 0;
+    const bool tma_all = train_tma(c.enc_dim, c.intra_dffn) && train_tma(c.enc_dim, c.inter_dffn);
+    if (!tma_all)
+        return fail("SepFormer training with post-norm layers needs the TMA backend (enc_dim in {128, 256}, d_ffn %% 128 == 0); the mma.sync "
+                    "engine covers pre-norm layers (configs/sepformer_base.yml)");
     return 0;
 }
 
@@ -203,6 +207,7 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
         const SeqMap m = seq_map(g, B, path);
         const TPath& tp = l.path[pi];
         const bool tma = train_tma(N, dffn);
+        const bool pre = (path ? c.inter_norm_before : c.intra_norm_before) != 0;
         LstmFusedGeom gm;
         gm.inter = path; gm.len = m.len; gm.nseq = m.nseq; gm.K = g.K; gm.S = g.Sc; gm.B = B;
         const bool tc_attn = tma && attn_tc5_supported(N, heads, gm) && !attn_fwd_prefers_mma(N, heads, m.len, sp);
@@ -237,8 +242,12 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
                 __nv_bfloat16* U2h = at<__nv_bfloat16>(ws, t.U2hl);
                 __nv_bfloat16* Hh = at<__nv_bfloat16>(ws, t.Hfhl);
                 __nv_bfloat16* Qh = at<__nv_bfloat16>(ws, l.QKVhl);
-                CK(launch_add_ln(Rin, nullptr, nullptr, nullptr, nullptr, params + lo[8], params + lo[9], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st,
-                                 U1h, sp ? U1h + pN : nullptr)); ++nl;
+                if (pre) {
+                    CK(launch_add_ln(Rin, nullptr, nullptr, nullptr, nullptr, params + lo[8], params + lo[9], g.PT, N, 1e-6f, nullptr, nullptr, nullptr,
+                                     st, U1h, sp ? U1h + pN : nullptr)); ++nl;
+                } else if (ly == 0) {   // post-norm: the first GEMM reads the stream itself (later layers get these planes from the previous norm2)
+                    CK(launch_split_rows(Rin, N, U1h, sp ? U1h + pN : nullptr, g.PT, N, 0, st)); ++nl;
+                }
                 {
                     TmaGemmArgs a = tma_nt_args(U1h, sp ? U1h + pN : nullptr, N, whi + lo[0], wlo + lo[0], N, QKV, 3 * N, PTi, 3 * N, N);
                     if (tc_attn) { a.C_hi = Qh; a.C_lo = sp ? Qh + pQ : nullptr; a.ldch = 3 * N; }
@@ -265,8 +274,13 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
                     a.drop_thr = drop_thr; a.drop_key = drop_site_key(h->drop_seed, li, 1); a.drop_scale = drop_scale;
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
-                CK(launch_add_ln(Rmid, nullptr, nullptr, nullptr, nullptr, params + lo[10], params + lo[11], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st,
-                                 U2h, sp ? U2h + pN : nullptr)); ++nl;
+                if (pre) {
+                    CK(launch_add_ln(Rmid, nullptr, nullptr, nullptr, nullptr, params + lo[10], params + lo[11], g.PT, N, 1e-6f, nullptr, nullptr, nullptr,
+                                     st, U2h, sp ? U2h + pN : nullptr)); ++nl;
+                } else {   // post-norm: Rmid holds z1 = x + dropout(attn); r1 = norm1(z1) as fp32 (residual of the FFN) and planes
+                    CK(launch_add_ln(Rmid, nullptr, nullptr, U1, nullptr, params + lo[8], params + lo[9], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st,
+                                     U2h, sp ? U2h + pN : nullptr)); ++nl;
+                }
                 {
                     // the FFN hidden exists as operand planes only: they feed FFN 2, the dW2 GEMM and (hi plane) the ReLU mask of the backward
                     TmaGemmArgs a = tma_nt_args(U2h, sp ? U2h + pN : nullptr, N, whi + lo[4], wlo + lo[4], N, nullptr, 0, PTi, dffn, N);
@@ -275,11 +289,16 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
                     a.drop_thr = drop_thr; a.drop_key = drop_site_key(h->drop_seed, li, 2); a.drop_scale = drop_scale;
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
-                {   // Rout = Rmid + Hf W_2^T + b_2
-                    TmaGemmArgs a = tma_nt_args(Hh, sp ? Hh + pD : nullptr, dffn, whi + lo[6], wlo + lo[6], dffn, Rout, N, PTi, N, dffn);
-                    a.bias = params + lo[7]; a.accumulate = 1; a.Cin = Rmid;
+                {   // pre: Rout = Rmid + Hf W_2^T + b_2 ; post: z2 (U2 buffer) = r1 + Hf W_2^T + b_2, Rout = norm2(z2)
+                    TmaGemmArgs a = tma_nt_args(Hh, sp ? Hh + pD : nullptr, dffn, whi + lo[6], wlo + lo[6], dffn, pre ? Rout : U2, N, PTi, N, dffn);
+                    a.bias = params + lo[7]; a.accumulate = 1; a.Cin = pre ? Rmid : U1;
                     a.drop_thr = drop_thr; a.drop_key = drop_site_key(h->drop_seed, li, 3); a.drop_scale = drop_scale;
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
+                }
+                if (!pre) {   // the next layer's first GEMM reads these planes
+                    __nv_bfloat16* nh = (ly + 1 < layers) ? at<__nv_bfloat16>(ws, l.layer[tp.first_layer + ly + 1].U1hl) : nullptr;
+                    CK(launch_add_ln(U2, nullptr, nullptr, Rout, nullptr, params + lo[10], params + lo[11], g.PT, N, 1e-6f, nullptr, nullptr, nullptr, st,
+                                     nh, (nh && sp) ? nh + pN : nullptr)); ++nl;
                 }
                 continue;
             }
@@ -462,6 +481,7 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
         const SeqMap m = seq_map(g, B, path);
         const TPath& tp = l.path[pi];
         const bool tma = train_tma(N, dffn);
+        const bool pre = (path ? c.inter_norm_before : c.intra_norm_before) != 0;
         if (drop_thr && !(tma && attn_bwd_mma_supported(N, heads, m)))
             return fail("dp_sepformer_backward: dropout needs the TMA backend, enc_dim in {128, 256}, d_ffn %% 128 == 0 and sequences <= 320");
         float* Uf = at<float>(ws, tp.Uf);
@@ -495,33 +515,45 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
                 };
                 // FFN: out = Rmid + relu(U2 W1^T + b1) W2^T + b2
                 const int li = tp.first_layer + ly;
-                // gradient of the (dropped) FFN output: planes of dR masked like the forward + db2
-                CK(launch_split_rows_colsum(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, grads + lo[7], st, drop_thr, drop_site_key(h->drop_seed, li, 3),
+                // post-norm: dR is the gradient of norm2(z2): first through norm2 (dU <- d z2); pre-norm: dR is already d(Rmid + FFN)
+                const float* dF = dR;   // gradient of the (dropped) FFN output
+                if (!pre) {
+                    CK(launch_ln_bwd(dR, at<float>(ws, t.U2), dU, nullptr, params + lo[10], g.PT, N, 1e-6f, grads + lo[10], grads + lo[11], st)); ++nl;
+                    dF = dU;
+                }
+                // planes of dF masked like the forward + db2
+                CK(launch_split_rows_colsum(dF, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, grads + lo[7], st, drop_thr, drop_site_key(h->drop_seed, li, 3),
                                             drop_scale)); ++nl;
-                {   // dHf = (dR W2) where Hf > 0, as planes
+                {   // dHf = (dF W2) where Hf > 0, as planes
                     TmaGemmArgs a = tma_nt_args(dRh, sp ? dRh + pN : nullptr, N, thi + lo[6], tlo + lo[6], N, nullptr, 0, PTi, dffn, N);
                     a.C_hi = dHh; a.C_lo = sp ? dHh + pD : nullptr; a.ldch = dffn;
                     a.mask_hi = Hh; a.ldmask_hi = dffn;   // the saved hidden is zero where the ReLU was inactive or the element was dropped
                     if (drop_thr) a.out_scale = drop_scale;
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
-                CK(wgrad(Hh, pD, dffn, dffn, dRh, pN, N, N, grads + lo[6], dffn, 1)); ++nl;          // dW2 = dR^T Hf, as Hf^T dR stored transposed
-                {
-                    TmaGemmArgs a = tma_nt_args(dHh, sp ? dHh + pD : nullptr, dffn, thi + lo[4], tlo + lo[4], dffn, dU, N, PTi, N, dffn);
+                CK(wgrad(Hh, pD, dffn, dffn, dRh, pN, N, N, grads + lo[6], dffn, 1)); ++nl;          // dW2 = dF^T Hf, as Hf^T dF stored transposed
+                {   // pre: dU = dHf W1 (gradient of norm2's output) ; post: dR = d z2 + dHf W1 (gradient of r1)
+                    TmaGemmArgs a = tma_nt_args(dHh, sp ? dHh + pD : nullptr, dffn, thi + lo[4], tlo + lo[4], dffn, pre ? dU : dR, N, PTi, N, dffn);
+                    if (!pre) { a.accumulate = 1; a.Cin = dU; }
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
-                CK(wgrad(dHh, pD, dffn, dffn, U2h, pN, N, N, grads + lo[4], N, 0)); ++nl;             // dW1 = dHf^T U2
+                CK(wgrad(dHh, pD, dffn, dffn, U2h, pN, N, N, grads + lo[4], N, 0)); ++nl;             // dW1 = dHf^T (FFN input)
                 CK(launch_colsum_planes(dHh, sp ? dHh + pD : nullptr, g.PT, dffn, grads + lo[5], st)); ++nl;
-                // LayerNorm 2 (input Rmid): dR += d Rmid
-                CK(launch_ln_bwd(dU, at<float>(ws, t.Rmid), dU, dR, params + lo[10], g.PT, N, 1e-6f, grads + lo[10], grads + lo[11], st)); ++nl;
-                // attention branch: Rmid = Rin + attn(U1) W_o^T + b_o
-                CK(launch_split_rows_colsum(dR, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, grads + lo[3], st, drop_thr, drop_site_key(h->drop_seed, li, 1),
-                                            drop_scale)); ++nl;   // planes of the (masked) dR + dbo
+                const float* dA = dR;   // gradient of the (dropped) attention output
+                if (pre) {   // LayerNorm 2 (input Rmid): dR += d Rmid
+                    CK(launch_ln_bwd(dU, at<float>(ws, t.Rmid), dU, dR, params + lo[10], g.PT, N, 1e-6f, grads + lo[10], grads + lo[11], st)); ++nl;
+                } else {     // norm1 (input z1 = Rmid): dU <- d z1
+                    CK(launch_ln_bwd(dR, at<float>(ws, t.Rmid), dU, nullptr, params + lo[8], g.PT, N, 1e-6f, grads + lo[8], grads + lo[9], st)); ++nl;
+                    dA = dU;
+                }
+                // attention branch: z1 / Rmid = Rin + dropout(attn(.) W_o^T + b_o)
+                CK(launch_split_rows_colsum(dA, N, dRh, sp ? dRh + pN : nullptr, g.PT, N, grads + lo[3], st, drop_thr, drop_site_key(h->drop_seed, li, 1),
+                                            drop_scale)); ++nl;   // planes of the (masked) gradient + dbo
                 {
                     TmaGemmArgs a = tma_nt_args(dRh, sp ? dRh + pN : nullptr, N, thi + lo[2], tlo + lo[2], N, dOa, N, PTi, N, N);
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
-                CK(wgrad(dRh, pN, N, N, Oh, pN, N, N, grads + lo[2], N, 0)); ++nl;                      // dWo = dR^T O
+                CK(wgrad(dRh, pN, N, N, Oh, pN, N, N, grads + lo[2], N, 0)); ++nl;                      // dWo = dA^T O
                 if (attn_bwd_mma_supported(N, heads, m)) {
                     CK(launch_attn_bwd_mma(at<float>(ws, t.QKV), at<float>(ws, t.Oa), at<float>(ws, t.LSE), dOa, dQKV, N, heads, m, sp, st, drop_thr,
                                            drop_site_key(h->drop_seed, li, 0), drop_scale)); ++nl;
@@ -529,13 +561,15 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
                     CK(launch_attn_bwd(at<float>(ws, t.QKV), at<float>(ws, t.Oa), at<float>(ws, t.LSE), dOa, dQKV, N, heads, m, st)); ++nl;
                 }
                 CK(launch_split_rows_colsum(dQKV, 3 * N, dQh, sp ? dQh + pQ : nullptr, g.PT, 3 * N, grads + lo[1], st)); ++nl;  // + db_in
-                {
-                    TmaGemmArgs a = tma_nt_args(dQh, sp ? dQh + pQ : nullptr, 3 * N, thi + lo[0], tlo + lo[0], 3 * N, dU, N, PTi, N, 3 * N);
+                {   // pre: dU = dQKV Win (gradient of norm1's output) ; post: dR = d z1 + dQKV Win (gradient of the layer input)
+                    TmaGemmArgs a = tma_nt_args(dQh, sp ? dQh + pQ : nullptr, 3 * N, thi + lo[0], tlo + lo[0], 3 * N, pre ? dU : dR, N, PTi, N, 3 * N);
+                    if (!pre) { a.accumulate = 1; a.Cin = dU; }
                     CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 }
-                CK(wgrad(dQh, pQ, 3 * N, 3 * N, U1h, pN, N, N, grads + lo[0], N, 0)); ++nl;            // dWin = dQKV^T U1
-                // LayerNorm 1 (input Rin): dR += d Rin
-                CK(launch_ln_bwd(dU, at<float>(ws, t.Rin), dU, dR, params + lo[8], g.PT, N, 1e-6f, grads + lo[8], grads + lo[9], st)); ++nl;
+                CK(wgrad(dQh, pQ, 3 * N, 3 * N, U1h, pN, N, N, grads + lo[0], N, 0)); ++nl;            // dWin = dQKV^T (layer input / its norm)
+                if (pre) {   // LayerNorm 1 (input Rin): dR += d Rin
+                    CK(launch_ln_bwd(dU, at<float>(ws, t.Rin), dU, dR, params + lo[8], g.PT, N, 1e-6f, grads + lo[8], grads + lo[9], st)); ++nl;
+                }
                 continue;
             }
             float* Hf = at<float>(ws, t.Hf);

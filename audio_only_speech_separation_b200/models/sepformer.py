@@ -9,7 +9,8 @@ same recursive reset, so the default initialisation is reproduced bit for bit un
 buffer that the engine reads through an offset table (include/dualpath_b200.h).
 
 The engine covers inference (``model.eval()`` / ``torch.no_grad()``, TMA-fed tcgen05 GEMMs and attention, fp32-parity and bf16
-modes) and training for pre-norm layers: forward + backward are two engine calls behind one autograd node, gradients are
+modes) and training (pre-norm layers on both engines, post-norm layers on the TMA engine): forward + backward are two engine calls behind
+one autograd node, gradients are
 checked against autograd through the reference algorithm.  The reference trains with dropout 0.1 in four places per layer
 (attention probabilities, attention output, FFN hidden, FFN output); ``model.dropout`` (default 0.1, like the
 reference) applies them in ``train()`` mode on the TMA engine (enc_dim 128 / 256): masks are a counter-based function of a seed drawn
