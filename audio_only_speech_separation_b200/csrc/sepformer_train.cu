@@ -32,6 +32,8 @@ struct TLayout {
     size_t total;
 };
 
+bool train_tma(int N, int dffn);
+
 void train_layout(const dp_sepformer* h, const SGeo& g, TLayout& l) {
     Carver c;
     const size_t f = sizeof(float);
@@ -65,7 +67,8 @@ void train_layout(const dp_sepformer* h, const SGeo& g, TLayout& l) {
             t.Oa = c.take(g.PT * N * f);
             t.Rmid = c.take(g.PT * N * f);
             t.U2 = c.take(g.PT * N * f);
-            t.Hf = c.take(g.PT * dffn * f);
+            // the fp32 FFN hidden exists on the mma.sync engine only (the TMA engine keeps it as planes): 133 MB per layer at 16 s
+            t.Hf = train_tma(N, dffn) ? t.U2 : c.take(g.PT * dffn * f);
             // operand planes (hi | lo) of what the backward's weight-gradient GEMMs read (TMA backend)
             t.U1hl = c.take(g.PT * N * 4);
             t.Oahl = c.take(g.PT * N * 4);
@@ -89,7 +92,7 @@ void train_layout(const dp_sepformer* h, const SGeo& g, TLayout& l) {
     l.dX = c.take(g.PT * N * f);
     l.dR = c.take(g.PT * N * f);
     l.dU = c.take(g.PT * N * f);
-    l.dHf = c.take(g.PT * dmax * f);
+    l.dHf = (train_tma(N, cf.intra_dffn) && train_tma(N, cf.inter_dffn)) ? l.dU : c.take(g.PT * dmax * f);   // planes only on the TMA engine
     l.dOa = c.take(g.PT * N * f);
     l.dQKV = c.take(g.PT * 3 * N * f);
     l.dD = c.take(g.BL * spk * cf.win * f);
