@@ -29,6 +29,11 @@ class TasnetConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("enc_dim", "bn_dim", "hidden_dim", "win", "layer", "num_spk", "block_size", "unfold", "module")]
 
 
+class GcTasnetConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("enc_dim", "bn_dim", "hidden_dim", "win", "layer", "num_spk", "context_size", "group_size",
+                                       "block_size")]
+
+
 class SepformerConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("enc_dim", "win", "chunk", "num_blocks", "num_spk", "intra_layers", "inter_layers", "intra_heads",
                                        "inter_heads", "intra_dffn", "inter_dffn", "intra_pe", "inter_pe", "intra_norm_before",
@@ -83,6 +88,12 @@ PROTOTYPES = {
     "dp_tasnet_forward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "dp_tasnet_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "dp_tasnet_last_launches": (_i, [_p]),
+    "dp_gctasnet_n_offsets": (_i, [_i]),
+    "dp_gctasnet_create": (_i, [C.POINTER(GcTasnetConfig), C.POINTER(_i64), _i, _i64, C.POINTER(_p)]),
+    "dp_gctasnet_destroy": (None, [_p]),
+    "dp_gctasnet_workspace_bytes": (_i64, [_p, _i, _i]),
+    "dp_gctasnet_forward": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
+    "dp_gctasnet_last_launches": (_i, [_p]),
     "dp_sepformer_create": (_i, [C.POINTER(SepformerConfig), C.POINTER(_i64), _i, _i64, C.POINTER(_p)]),
     "dp_sepformer_destroy": (None, [_p]),
     "dp_sepformer_pack_bytes": (_i64, [_p]),

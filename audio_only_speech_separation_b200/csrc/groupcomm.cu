@@ -1,0 +1,583 @@
+// GroupComm TasNet engine (inference): look2hear/models/gc3_network.py:133-184 with group_size > 1 and module "DPRNN" --
+// context encoder / decoder (GC_RNN, groupcomm.py:10-45), TAC (gc3_basics.py:28-60), the grouped DPRNN stack (dprnn.py:53-88) and
+// the grouped mask head.  The C-ABI is declared in include/dualpath_b200.h (dp_gctasnet_*).
+//
+// With G groups every per-group operator is tiny (bn_dim / G = 4 or 8 features, hidden_dim / G = 8 or 16 LSTM units, shared by all
+// groups), far below a tensor-core tile: the work is HBM / latency bound fp32 CUDA-core arithmetic, one thread per (position, group)
+// -- or per (sequence, LSTM unit) in the recurrence -- with the per-group weights in registers or shared memory.
+//
+// Data layout in HBM (fp32): every activation is "group-channel-last" [positions, G, n] (C = G*n = bn_dim contiguous floats per
+// position), so the reference's view / permute / contiguous pairs around TAC, the RNNs and the norms (gc3_basics.py:45-57,
+// groupcomm.py:33-43, dprnn.py:64-82) do not exist:
+//   frames   enc [B*F, E]   feat / un [B*F, C]   mask [B*F, G, spk*E/G]
+//   context  Xc, A, Y [B*Lc, ctx, C]   (position = (b*Lc + l)*ctx + t ; sequences walk t)
+//   DPRNN    A, Y [B, S2, K, C]        (position = (b*S2 + s)*K + k ; row sequences walk k, col sequences walk s)
+//   LSTM out Hh [positions, G, 2h]
+// GroupNorm statistics are double-precision (sum, sum of squares) pairs accumulated with atomics by the producing kernel and consumed
+// by the residual kernel that follows; all slots are cleared by one memset at the start of a forward.
+#include <new>
+#include <vector>
+
+#include "../../include/dualpath_b200.h"
+#include "common.cuh"
+#include "engine_common.h"
+#include "kernels.h"
+
+using namespace dp;
+
+struct dp_gctasnet {
+    dp_gctasnet_config cfg;
+    std::vector<int64_t> off;
+    int64_t n_params;
+    int launches;
+};
+
+namespace {
+
+constexpr int HEAD = 9, TAC_N = 11, RNN_N = 12, GC_LAYER = TAC_N + RNN_N, GC_BLOCK = 2 * GC_LAYER, DP_LAYER = TAC_N + 2 * RNN_N;
+enum { P_ENC_W, P_BN_G, P_BN_B, P_BN_W, P_OUT_W, P_OUT_B, P_MASK_W, P_MASK_B, P_DEC_W };
+
+struct TacW { const float *w1, *b1, *a1, *w2, *b2, *a2, *w3, *b3, *a3, *gamma, *beta; };
+struct RnnW { const float *wih[2], *whh[2], *bih[2], *bhh[2], *pw, *pb, *gamma, *beta; };
+
+__device__ __forceinline__ float prelu1(float v, float a) { return v >= 0.f ? v : a * v; }
+
+// (sum, sum of squares) of one thread's outputs into the statistics slot of its (sample, group).  Lanes of a warp that hold the same
+// group of the same sample are combined first (positions of a warp are consecutive, so this is the common case).
+__device__ __forceinline__ void stats_add(double* stats, float s, float ss, bool active, long long pos, long long pos_lane0, long long npos,
+                                          int G, int g, int pps) {
+    const int lane = threadIdx.x & 31;
+    long long last = pos_lane0 + 32 / G - 1;
+    if (last > npos - 1) last = npos - 1;
+    const bool uniform = (pos_lane0 / pps) == (last / pps);   // warp-uniform: lane 0's position is the same for the whole warp
+    double ds = active ? (double)s : 0.0, dss = active ? (double)ss : 0.0;
+    if (uniform) {
+        for (int o = G; o < 32; o <<= 1) {
+            ds += __shfl_xor_sync(0xffffffffu, ds, o);
+            dss += __shfl_xor_sync(0xffffffffu, dss, o);
+        }
+        if (lane < G && pos_lane0 < npos) {
+            double* d = stats + 2 * ((pos_lane0 / pps) * G + g);
+            atomicAdd(d, ds);
+            atomicAdd(d + 1, dss);
+        }
+    } else if (active) {
+        double* d = stats + 2 * ((pos / pps) * G + g);
+        atomicAdd(d, ds);
+        atomicAdd(d + 1, dss);
+    }
+}
+
+// ---- TAC: transform, average over the groups, concatenate (gc3_basics.py:38-55); the GroupNorm + residual follow in gn_res ----------
+template <int NG, int HG>
+__global__ void __launch_bounds__(256) gc_tac_kernel(const float* __restrict__ X, float* __restrict__ Y, double* __restrict__ stats, TacW w,
+                                                     long long npos, int G, int pps) {
+    constexpr int TH = 3 * HG, KMAX = (TH + 7) / 8, LD2 = TH + 1;
+    __shared__ float s_w1[TH * NG], s_b1[TH], s_w2[TH * LD2], s_b2[TH], s_w3[NG * 2 * TH], s_b3[NG];
+    for (int i = threadIdx.x; i < TH * NG; i += blockDim.x) s_w1[i] = w.w1[i];
+    for (int i = threadIdx.x; i < TH * TH; i += blockDim.x) s_w2[(i / TH) * LD2 + i % TH] = w.w2[i];
+    for (int i = threadIdx.x; i < NG * 2 * TH; i += blockDim.x) s_w3[i] = w.w3[i];
+    for (int i = threadIdx.x; i < TH; i += blockDim.x) { s_b1[i] = w.b1[i]; s_b2[i] = w.b2[i]; }
+    if (threadIdx.x < NG) s_b3[threadIdx.x] = w.b3[threadIdx.x];
+    __syncthreads();
+    const float a1 = __ldg(w.a1), a2 = __ldg(w.a2), a3 = __ldg(w.a3);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long pos = i / G, pos0 = (i - (threadIdx.x & 31)) / G;
+    const int g = (int)(i % G);
+    const bool active = pos < npos;
+    float x[NG];
+#pragma unroll
+    for (int j = 0; j < NG; j += 4) {
+        float4 v = active ? *reinterpret_cast<const float4*>(X + i * NG + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[j] = v.x; x[j + 1] = v.y; x[j + 2] = v.z; x[j + 3] = v.w;
+    }
+    float y[TH], ym[TH];
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+        float acc = s_b1[r];
+#pragma unroll
+        for (int j = 0; j < NG; ++j) acc = fmaf(s_w1[r * NG + j], x[j], acc);
+        y[r] = prelu1(acc, a1);
+        float v = y[r];
+        for (int o = G >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        ym[r] = v / (float)G;
+    }
+    // TAC_mean: its TH rows are spread over the G lanes of a position (row r on lane r % G), then gathered in the output sum
+    float ms[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int r = g + k * G;
+        float acc = 0.f;
+        if (r < TH) {
+            acc = s_b2[r];
+#pragma unroll
+            for (int c = 0; c < TH; ++c) acc = fmaf(s_w2[r * LD2 + c], ym[c], acc);
+            acc = prelu1(acc, a2);
+        }
+        ms[k] = acc;
+    }
+    float out[NG];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+        float acc = s_b3[j];
+#pragma unroll
+        for (int r = 0; r < TH; ++r) acc = fmaf(s_w3[j * 2 * TH + r], y[r], acc);
+        out[j] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+        for (int src = 0; src < G; ++src) {
+            const float v = __shfl_sync(0xffffffffu, ms[k], src, G);
+            const int r = src + k * G;
+            if (r < TH) {
+#pragma unroll
+                for (int j = 0; j < NG; ++j) out[j] = fmaf(s_w3[j * 2 * TH + TH + r], v, out[j]);
+            }
+        }
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+        out[j] = prelu1(out[j], a3);
+        s += out[j];
+        ss = fmaf(out[j], out[j], ss);
+    }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < NG; j += 4) *reinterpret_cast<float4*>(Y + i * NG + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+    }
+    stats_add(stats, s, ss, active, pos, pos0, npos, G, g, pps);
+}
+
+// ---- out = res + GroupNorm(1, n)(y): statistics per (sample, group) over n x (positions of the sample) ------------------------------
+template <int NG>
+__global__ void __launch_bounds__(256) gc_gn_res_kernel(const float* __restrict__ Y, const float* __restrict__ R, float* __restrict__ Out,
+                                                        const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, long long total, int G, int pps, double eps) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long pos = i / G;
+    const int g = (int)(i % G);
+    const double* d = stats + 2 * ((pos / pps) * G + g);
+    const double inv = 1.0 / ((double)pps * NG);
+    const double mean = d[0] * inv;
+    double var = d[1] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + eps));
+#pragma unroll
+    for (int j = 0; j < NG; j += 4) {
+        const float4 y = *reinterpret_cast<const float4*>(Y + i * NG + j);
+        const float4 r = *reinterpret_cast<const float4*>(R + i * NG + j);
+        float4 o;
+        o.x = r.x + ((y.x - mu) * rstd * __ldg(gamma + j) + __ldg(beta + j));
+        o.y = r.y + ((y.y - mu) * rstd * __ldg(gamma + j + 1) + __ldg(beta + j + 1));
+        o.z = r.z + ((y.z - mu) * rstd * __ldg(gamma + j + 2) + __ldg(beta + j + 2));
+        o.w = r.w + ((y.w - mu) * rstd * __ldg(gamma + j + 3) + __ldg(beta + j + 3));
+        *reinterpret_cast<float4*>(Out + i * NG + j) = o;
+    }
+}
+
+// ---- BiLSTM recurrence of a ProjRNN at group width (gc3_basics.py:19-24): one thread per (sequence, unit), h exchanged by shuffles ---
+// sequence (o, g): positions (o / qdiv) * s_hi + (o % qdiv) * s_lo + t * s_t ; blockIdx.y = direction.  Gate rows i, f, g, o.
+template <int NG, int HG>
+__global__ void __launch_bounds__(128) gc_lstm_kernel(const float* __restrict__ X, float* __restrict__ Hh, RnnW w, long long nouter, int G,
+                                                      int len, int qdiv, long long s_hi, long long s_lo, long long s_t) {
+    const int dir = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (int)(i % HG);
+    const long long q = i / HG;
+    const bool active = q < nouter * G;
+    const long long qc = active ? q : nouter * G - 1;
+    const int g = (int)(qc % G);
+    const long long o = qc / G;
+    const long long bp = (o / qdiv) * s_hi + (o % qdiv) * s_lo;
+    float wi[4][NG], wh[4][HG], b[4];
+#pragma unroll
+    for (int gt = 0; gt < 4; ++gt) {
+        const int row = gt * HG + j;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) wi[gt][k] = __ldg(w.wih[dir] + row * NG + k);
+#pragma unroll
+        for (int k = 0; k < HG; ++k) wh[gt][k] = __ldg(w.whh[dir] + row * HG + k);
+        b[gt] = __ldg(w.bih[dir] + row) + __ldg(w.bhh[dir] + row);
+    }
+    const int C = G * NG, C2 = G * 2 * HG;
+    float h = 0.f, c = 0.f;
+    int t = dir ? len - 1 : 0;
+    const int dt = dir ? -1 : 1;
+    float x[NG], xn[NG];
+    {
+        const float* xp = X + (bp + (long long)t * s_t) * C + g * NG;
+#pragma unroll
+        for (int k = 0; k < NG; k += 4) { float4 v = *reinterpret_cast<const float4*>(xp + k); xn[k] = v.x; xn[k + 1] = v.y; xn[k + 2] = v.z; xn[k + 3] = v.w; }
+    }
+    for (int step = 0; step < len; ++step, t += dt) {
+#pragma unroll
+        for (int k = 0; k < NG; ++k) x[k] = xn[k];
+        if (step + 1 < len) {
+            const float* xp = X + (bp + (long long)(t + dt) * s_t) * C + g * NG;
+#pragma unroll
+            for (int k = 0; k < NG; k += 4) { float4 v = *reinterpret_cast<const float4*>(xp + k); xn[k] = v.x; xn[k + 1] = v.y; xn[k + 2] = v.z; xn[k + 3] = v.w; }
+        }
+        float a[4] = {b[0], b[1], b[2], b[3]};
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt) a[gt] = fmaf(wi[gt][k], x[k], a[gt]);
+        }
+#pragma unroll
+        for (int k = 0; k < HG; ++k) {
+            const float hk = __shfl_sync(0xffffffffu, h, k, HG);
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt) a[gt] = fmaf(wh[gt][k], hk, a[gt]);
+        }
+        const float ig = 1.f / (1.f + expf(-a[0])), fg = 1.f / (1.f + expf(-a[1])), gg = tanhf(a[2]), og = 1.f / (1.f + expf(-a[3]));
+        c = fmaf(fg, c, ig * gg);
+        h = og * tanhf(c);
+        if (active) Hh[(bp + (long long)t * s_t) * C2 + g * 2 * HG + dir * HG + j] = h;
+    }
+}
+
+// ---- Linear(2h -> n) of the ProjRNN + statistics of the GroupNorm that follows ------------------------------------------------------
+template <int NG, int HG>
+__global__ void __launch_bounds__(256) gc_proj_kernel(const float* __restrict__ Hh, float* __restrict__ Y, double* __restrict__ stats, RnnW w,
+                                                      long long npos, int G, int pps) {
+    __shared__ float s_w[NG * 2 * HG], s_b[NG];
+    for (int i = threadIdx.x; i < NG * 2 * HG; i += blockDim.x) s_w[i] = w.pw[i];
+    if (threadIdx.x < NG) s_b[threadIdx.x] = w.pb[threadIdx.x];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long pos = i / G, pos0 = (i - (threadIdx.x & 31)) / G;
+    const int g = (int)(i % G);
+    const bool active = pos < npos;
+    float out[NG];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) out[j] = s_b[j];
+#pragma unroll
+    for (int k = 0; k < 2 * HG; k += 4) {
+        const float4 v = active ? *reinterpret_cast<const float4*>(Hh + i * 2 * HG + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+            out[j] = fmaf(s_w[j * 2 * HG + k], v.x, out[j]);
+            out[j] = fmaf(s_w[j * 2 * HG + k + 1], v.y, out[j]);
+            out[j] = fmaf(s_w[j * 2 * HG + k + 2], v.z, out[j]);
+            out[j] = fmaf(s_w[j * 2 * HG + k + 3], v.w, out[j]);
+        }
+    }
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) { s += out[j]; ss = fmaf(out[j], out[j], ss); }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < NG; j += 4) *reinterpret_cast<float4*>(Y + i * NG + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+    }
+    stats_add(stats, s, ss, active, pos, pos0, npos, G, g, pps);
+}
+
+// ---- per-group Linear(n -> nout) shared by the groups: the DPRNN output conv (dprnn.py:85) and the mask conv + ReLU -----------------
+template <int NG>
+__global__ void __launch_bounds__(256) gc_group_linear_kernel(const float* __restrict__ X, float* __restrict__ Y, const float* __restrict__ W,
+                                                              const float* __restrict__ bias, long long total, int nout, int relu) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float x[NG];
+#pragma unroll
+    for (int j = 0; j < NG; j += 4) { float4 v = *reinterpret_cast<const float4*>(X + i * NG + j); x[j] = v.x; x[j + 1] = v.y; x[j + 2] = v.z; x[j + 3] = v.w; }
+    for (int o = 0; o < nout; ++o) {
+        float acc = __ldg(bias + o);
+#pragma unroll
+        for (int j = 0; j < NG; ++j) acc = fmaf(__ldg(W + o * NG + j), x[j], acc);
+        Y[i * nout + o] = relu ? fmaxf(acc, 0.f) : acc;
+    }
+}
+
+// ---- waveform encoder Conv1d(1, E, win, stride = win/2, no bias) on the zero-padded input + statistics of the bottleneck norm ---------
+__global__ void __launch_bounds__(256) gc_encoder_kernel(const float* __restrict__ x, const float* __restrict__ W, float* __restrict__ enc,
+                                                         double* __restrict__ stats, int T, int F, int E, int win) {
+    const int fpb = blockDim.x / E, fl = threadIdx.x / E, e = threadIdx.x % E, b = blockIdx.y;
+    const int f = blockIdx.x * fpb + fl, stride = win / 2;
+    float acc = 0.f;
+    if (f < F) {
+        const float* xb = x + (size_t)b * T;
+        for (int k = 0; k < win; ++k) {
+            const int t = f * stride + k - stride;   // the padded signal starts with `stride` zeros (gc3_network.py:128-129)
+            if (t >= 0 && t < T) acc = fmaf(__ldg(W + e * win + k), __ldg(xb + t), acc);
+        }
+        enc[((size_t)b * F + f) * E + e] = acc;
+    }
+    double s = warp_sum_d((double)acc), ss = warp_sum_d((double)acc * acc);
+    if ((threadIdx.x & 31) == 0 && f < F) { atomicAdd(stats + 2 * b, s); atomicAdd(stats + 2 * b + 1, ss); }
+}
+
+// ---- bottleneck: GroupNorm(1, E, eps = fp32 eps) + Conv1d(E, C, 1, no bias) ------------------------------------------------------------
+__global__ void __launch_bounds__(256) gc_bottleneck_kernel(const float* __restrict__ enc, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const float* __restrict__ W,
+                                                            const double* __restrict__ stats, float* __restrict__ feat, int F, int E, int C,
+                                                            double eps) {
+    extern __shared__ float sm[];
+    float* wt = sm;              // [E][C]: the weight transposed, so the threads of a frame read consecutive words
+    float* row = sm + E * C;     // [fpb][E]
+    const int fpb = blockDim.x / E, fl = threadIdx.x / E, e = threadIdx.x % E, b = blockIdx.y;
+    const int f = blockIdx.x * fpb + fl;
+    for (int i = threadIdx.x; i < E * C; i += blockDim.x) wt[(i % E) * C + i / E] = W[i];
+    const double inv = 1.0 / ((double)F * E), mean = stats[2 * b] * inv;
+    double var = stats[2 * b + 1] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + eps));
+    row[fl * E + e] = f < F ? (enc[((size_t)b * F + f) * E + e] - mu) * rstd * __ldg(gamma + e) + __ldg(beta + e) : 0.f;
+    __syncthreads();
+    if (f >= F) return;
+    for (int c = e; c < C; c += E) {
+        float acc = 0.f;
+        for (int k = 0; k < E; ++k) acc = fmaf(wt[k * C + c], row[fl * E + k], acc);
+        feat[((size_t)b * F + f) * C + c] = acc;
+    }
+}
+
+// mean over the context window (gc3_network.py:150)
+__global__ void __launch_bounds__(256) gc_ctx_mean_kernel(const float* __restrict__ A, float* __restrict__ out, long long total, int ctx, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long bl = i / C;
+    const int c = (int)(i % C);
+    float s = 0.f;
+    for (int t = 0; t < ctx; ++t) s += A[(bl * ctx + t) * C + c];
+    out[i] = s / (float)ctx;
+}
+
+// feature_map.unsqueeze(2) + squeeze_block (gc3_network.py:161)
+__global__ void __launch_bounds__(256) gc_bcast_add_kernel(const float* __restrict__ fmap, const float* Xc, float* out,
+                                                           long long total, int ctx, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long bl = i / ((long long)ctx * C);
+    out[i] = Xc[i] + fmap[bl * C + i % C];
+}
+
+// mask * encoder output, ConvTranspose1d(E, 1, win, stride) and the trim of gc3_network.py:174-179, one thread per output sample
+__global__ void __launch_bounds__(256) gc_decoder_kernel(const float* __restrict__ Mk, const float* __restrict__ enc, const float* __restrict__ Wd,
+                                                         float* __restrict__ est, int B, int spk, int T, int F, int E, int G, int win) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * spk * T) return;
+    const int t = (int)(i % T), s = (int)((i / T) % spk), b = (int)(i / ((long long)T * spk));
+    const int stride = win / 2, eg = E / G, pos = t + stride;
+    float acc = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int f = pos / stride - half, k = pos % stride + half * stride;
+        if (f < 0 || f >= F) continue;
+        const float* er = enc + ((size_t)b * F + f) * E;
+        const float* mr = Mk + ((size_t)b * F + f) * (size_t)(spk * E);
+        for (int e = 0; e < E; ++e) acc = fmaf(__ldg(Wd + e * win + k) * mr[(e / eg) * (spk * eg) + s * eg + e % eg], er[e], acc);
+    }
+    est[i] = acc;
+}
+
+struct GGeo {
+    int B, T, F, Lc, S2, K, ctx, G, n, h, C, E, spk;
+    long long PC, PD, PM;   // context positions, DPRNN positions, max
+};
+bool gc_geometry(const dp_gctasnet* h, int B, int T, GGeo& g) {
+    const auto& c = h->cfg;
+    if (B <= 0 || T <= 0) return false;
+    int rest, frames, crest, drest;
+    if (dp_wave_geometry(T, c.win, &rest, &frames)) return false;
+    g.B = B; g.T = T; g.F = frames; g.ctx = c.context_size; g.K = c.block_size; g.G = c.group_size;
+    g.n = c.bn_dim / c.group_size; g.h = c.hidden_dim / c.group_size; g.C = c.bn_dim; g.E = c.enc_dim; g.spk = c.num_spk;
+    if (dp_seg_geometry(g.F, g.ctx, &crest, &g.Lc)) return false;
+    if (dp_seg_geometry(g.Lc, g.K, &drest, &g.S2)) return false;
+    g.PC = (long long)B * g.Lc * g.ctx;
+    g.PD = (long long)B * g.S2 * g.K;
+    g.PM = g.PC > g.PD ? g.PC : g.PD;
+    return true;
+}
+struct GLayout { size_t enc, feat, Xc, A, Y, Hh, sqm, fmap, Mk, stats, stats_bytes, total; };
+void gc_layout(const dp_gctasnet* h, const GGeo& g, GLayout& l) {
+    Carver c;
+    const size_t f = sizeof(float);
+    l.enc = c.take((size_t)g.B * g.F * g.E * f);
+    l.feat = c.take((size_t)g.B * g.F * g.C * f);
+    l.Xc = c.take(g.PC * g.C * f);
+    l.A = c.take(g.PM * g.C * f);
+    l.Y = c.take(g.PM * g.C * f);
+    l.Hh = c.take(g.PM * g.G * 2 * g.h * f);
+    l.sqm = c.take((size_t)g.B * g.Lc * g.C * f);
+    l.fmap = c.take((size_t)g.B * g.Lc * g.C * f);
+    l.Mk = c.take((size_t)g.B * g.F * g.spk * g.E * f);
+    l.stats_bytes = ((size_t)g.B + 8 * (size_t)g.B * g.Lc * g.G + 3 * (size_t)h->cfg.layer * g.B * g.G) * 2 * sizeof(double);
+    l.stats = c.take(l.stats_bytes);
+    l.total = c.off;
+}
+
+inline unsigned blocks_for(long long total, int per = 256) { return (unsigned)ceil_div_ll(total, per); }
+
+TacW tac_w(const dp_gctasnet* h, const float* p, int base) {
+    const float* q[TAC_N];
+    for (int i = 0; i < TAC_N; ++i) q[i] = p + h->off[base + i];
+    return TacW{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], q[10]};
+}
+RnnW rnn_w(const dp_gctasnet* h, const float* p, int base) {
+    RnnW w;
+    for (int d = 0; d < 2; ++d) {
+        w.wih[d] = p + h->off[base + 4 * d];
+        w.whh[d] = p + h->off[base + 4 * d + 1];
+        w.bih[d] = p + h->off[base + 4 * d + 2];
+        w.bhh[d] = p + h->off[base + 4 * d + 3];
+    }
+    w.pw = p + h->off[base + 8]; w.pb = p + h->off[base + 9]; w.gamma = p + h->off[base + 10]; w.beta = p + h->off[base + 11];
+    return w;
+}
+
+struct SeqWalk { long long nouter; int len, qdiv; long long s_hi, s_lo, s_t; };
+
+template <int NG, int HG>
+struct Ops {
+    static cudaError_t tac(dp_gctasnet* h, const float* X, float* Y, float* Out, double* st, const TacW& w, long long npos, int G, int pps,
+                           cudaStream_t s) {
+        gc_tac_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(X, Y, st, w, npos, G, pps);
+        gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, X, Out, st, w.gamma, w.beta, npos * G, G, pps, 1e-5);
+        h->launches += 2;
+        return cudaGetLastError();
+    }
+    static cudaError_t rnn(dp_gctasnet* h, float* A, float* Y, float* Hh, double* st, const RnnW& w, long long npos, int G, int pps,
+                           const SeqWalk& q, double eps, cudaStream_t s) {
+        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
+        gc_lstm_kernel<NG, HG><<<grid, 128, 0, s>>>(A, Hh, w, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t);
+        gc_proj_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Y, st, w, npos, G, pps);
+        gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, A, A, st, w.gamma, w.beta, npos * G, G, pps, eps);
+        h->launches += 3;
+        return cudaGetLastError();
+    }
+    static cudaError_t group_linear(dp_gctasnet* h, const float* X, float* Y, const float* W, const float* b, long long total, int nout, int relu,
+                                    cudaStream_t s) {
+        gc_group_linear_kernel<NG><<<blocks_for(total), 256, 0, s>>>(X, Y, W, b, total, nout, relu);
+        h->launches += 1;
+        return cudaGetLastError();
+    }
+
+    // GC_RNN.forward (groupcomm.py:26-45): `in` is read by the first TAC only (the context blocks stay intact for the decoder)
+    static int gc_rnn(dp_gctasnet* h, const float* p, int base, const float* in, float* A, float* Y, float* Hh, double*& st, const GGeo& g,
+                      cudaStream_t s) {
+        const long long npos = g.PC;
+        const SeqWalk q{(long long)g.B * g.Lc, g.ctx, 1, (long long)g.ctx, 0, 1};
+        const size_t slot = (size_t)g.B * g.Lc * g.G * 2;
+        for (int i = 0; i < 2; ++i) {
+            CK(tac(h, i == 0 ? in : A, Y, A, st, tac_w(h, p, base + i * GC_LAYER), npos, g.G, g.ctx, s));
+            st += slot;
+            CK(rnn(h, A, Y, Hh, st, rnn_w(h, p, base + i * GC_LAYER + TAC_N), npos, g.G, g.ctx, q, 1e-5, s));
+            st += slot;
+        }
+        return 0;
+    }
+
+    static int forward(dp_gctasnet* h, const float* p, const float* mix, float* est, void* ws, const GGeo& g, cudaStream_t s) {
+        const auto& c = h->cfg;
+        GLayout l;
+        gc_layout(h, g, l);
+        float *enc = at<float>(ws, l.enc), *feat = at<float>(ws, l.feat), *Xc = at<float>(ws, l.Xc), *A = at<float>(ws, l.A);
+        float *Y = at<float>(ws, l.Y), *Hh = at<float>(ws, l.Hh), *sqm = at<float>(ws, l.sqm), *fmap = at<float>(ws, l.fmap);
+        float* Mk = at<float>(ws, l.Mk);
+        double* st = at<double>(ws, l.stats);
+        h->launches = 0;
+        CK(cudaMemsetAsync(st, 0, l.stats_bytes, s));
+        const int fpb = 256 / g.E;
+        dim3 fgrid(ceil_div(g.F, fpb), g.B);
+        gc_encoder_kernel<<<fgrid, 256, 0, s>>>(mix, p + h->off[P_ENC_W], enc, st, g.T, g.F, g.E, c.win);
+        const size_t smem = ((size_t)g.E * g.C + (size_t)fpb * g.E) * sizeof(float);
+        gc_bottleneck_kernel<<<fgrid, 256, smem, s>>>(enc, p + h->off[P_BN_G], p + h->off[P_BN_B], p + h->off[P_BN_W], st, feat, g.F, g.E, g.C,
+                                                      (double)1.1920928955078125e-07f);
+        CK(cudaGetLastError());
+        st += 2 * (size_t)g.B;
+        h->launches += 2;
+        // context encoding (gc3_network.py:145-151)
+        CK(launch_segment_cl(feat, Xc, g.B, g.F, g.ctx, g.Lc, g.C, s));
+        if (gc_rnn(h, p, HEAD, Xc, A, Y, Hh, st, g, s)) return 1;
+        gc_ctx_mean_kernel<<<blocks_for((long long)g.B * g.Lc * g.C), 256, 0, s>>>(A, sqm, (long long)g.B * g.Lc * g.C, g.ctx, g.C);
+        CK(cudaGetLastError());
+        // DP_Wrapper + grouped DPRNN (groupcomm.py:100-114, dprnn.py:53-88)
+        CK(launch_segment_cl(sqm, A, g.B, g.Lc, g.K, g.S2, g.C, s));
+        h->launches += 3;
+        const int pps = g.S2 * g.K;
+        const SeqWalk row{(long long)g.B * g.S2, g.K, 1, (long long)g.K, 0, 1};
+        const SeqWalk col{(long long)g.B * g.K, g.S2, g.K, (long long)g.S2 * g.K, 1, (long long)g.K};
+        const size_t dslot = (size_t)g.B * g.G * 2;
+        for (int i = 0; i < c.layer; ++i) {
+            const int base = HEAD + 2 * GC_BLOCK + i * DP_LAYER;
+            CK(tac(h, A, Y, A, st, tac_w(h, p, base), g.PD, g.G, pps, s));
+            st += dslot;
+            CK(rnn(h, A, Y, Hh, st, rnn_w(h, p, base + TAC_N), g.PD, g.G, pps, row, 1e-8, s));
+            st += dslot;
+            CK(rnn(h, A, Y, Hh, st, rnn_w(h, p, base + TAC_N + RNN_N), g.PD, g.G, pps, col, 1e-8, s));
+            st += dslot;
+        }
+        CK(group_linear(h, A, Y, p + h->off[P_OUT_W], p + h->off[P_OUT_B], g.PD * g.G, g.n, 0, s));
+        CK(launch_overlap_add_cl(Y, fmap, g.B, g.Lc, g.K, g.S2, g.C, s));
+        // context decoding (gc3_network.py:160-166)
+        gc_bcast_add_kernel<<<blocks_for(g.PC * g.C), 256, 0, s>>>(fmap, Xc, Xc, g.PC * g.C, g.ctx, g.C);   // in place: the blocks are dead after it
+        CK(cudaGetLastError());
+        float* Din = Xc;
+        if (gc_rnn(h, p, HEAD + GC_BLOCK, Din, A, Y, Hh, st, g, s)) return 1;
+        CK(launch_overlap_add_cl(A, feat, g.B, g.F, g.ctx, g.Lc, g.C, s));
+        // grouped mask, masking and the decoder (gc3_network.py:169-181)
+        CK(group_linear(h, feat, Mk, p + h->off[P_MASK_W], p + h->off[P_MASK_B], (long long)g.B * g.F * g.G, g.spk * g.E / g.G, 1, s));
+        gc_decoder_kernel<<<blocks_for((long long)g.B * g.spk * g.T), 256, 0, s>>>(Mk, enc, p + h->off[P_DEC_W], est, g.B, g.spk, g.T, g.F, g.E,
+                                                                                   g.G, c.win);
+        CK(cudaGetLastError());
+        h->launches += 5;
+        return 0;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int dp_gctasnet_n_offsets(int layer) { return HEAD + 2 * GC_BLOCK + layer * DP_LAYER; }
+
+int dp_gctasnet_create(const dp_gctasnet_config* cfg, const int64_t* offsets, int n_offsets, int64_t n_params, dp_gctasnet** out) {
+    if (!cfg || !offsets || !out) return fail("dp_gctasnet_create: null argument");
+    const int G = cfg->group_size;
+    if (G != 8 && G != 16 && G != 32) return fail("dp_gctasnet_create: group_size must be 8, 16 or 32 (got %d)", G);
+    if (cfg->bn_dim % G || cfg->hidden_dim % G || cfg->enc_dim % G) return fail("dp_gctasnet_create: group_size must divide enc_dim, bn_dim and hidden_dim");
+    const int n = cfg->bn_dim / G, hh = cfg->hidden_dim / G;
+    if (!((n == 4 && hh == 8) || (n == 8 && hh == 16)))
+        return fail("dp_gctasnet_create: per-group widths (bn_dim / G, hidden_dim / G) must be (4, 8) or (8, 16), got (%d, %d)", n, hh);
+    if (cfg->enc_dim % 32 || 256 % cfg->enc_dim) return fail("dp_gctasnet_create: enc_dim must be 32, 64, 128 or 256 (got %d)", cfg->enc_dim);
+    if ((size_t)(cfg->enc_dim * cfg->bn_dim + 256) * sizeof(float) > 48 * 1024) return fail("dp_gctasnet_create: enc_dim * bn_dim too large");
+    if (cfg->win <= 0 || (cfg->win & 1)) return fail("dp_gctasnet_create: win must be even and positive");
+    if (cfg->context_size <= 0 || (cfg->context_size & 1) || cfg->block_size <= 0 || (cfg->block_size & 1))
+        return fail("dp_gctasnet_create: context_size and block_size must be even and positive");
+    if (cfg->layer < 1 || cfg->num_spk < 1) return fail("dp_gctasnet_create: layer and num_spk must be >= 1");
+    if (n_offsets != dp_gctasnet_n_offsets(cfg->layer)) return fail("dp_gctasnet_create: expected %d parameter offsets, got %d", dp_gctasnet_n_offsets(cfg->layer), n_offsets);
+    for (int i = 0; i < n_offsets; ++i)
+        if (offsets[i] < 0 || offsets[i] >= n_params || (offsets[i] & 3)) return fail("dp_gctasnet_create: offset %d out of range or not 16-byte aligned", i);
+    dp_gctasnet* h = new (std::nothrow) dp_gctasnet;
+    if (!h) return fail("dp_gctasnet_create: out of memory");
+    h->cfg = *cfg;
+    h->off.assign(offsets, offsets + n_offsets);
+    h->n_params = n_params;
+    h->launches = 0;
+    *out = h;
+    return 0;
+}
+
+void dp_gctasnet_destroy(dp_gctasnet* h) { delete h; }
+
+int64_t dp_gctasnet_workspace_bytes(const dp_gctasnet* h, int B, int T) {
+    GGeo g;
+    if (!h || !gc_geometry(h, B, T, g)) { fail("dp_gctasnet_workspace_bytes: bad arguments"); return -1; }
+    GLayout l;
+    gc_layout(h, g, l);
+    return (int64_t)l.total;
+}
+
+int dp_gctasnet_forward(dp_gctasnet* h, const float* params, const float* mixture, float* est, void* workspace, int B, int T, void* stream) {
+    if (!h || !params || !mixture || !est || !workspace) return fail("dp_gctasnet_forward: null argument");
+    GGeo g;
+    if (!gc_geometry(h, B, T, g)) return fail("dp_gctasnet_forward: bad batch / length (B=%d, T=%d)", B, T);
+    if (g.n == 4) return Ops<4, 8>::forward(h, params, mixture, est, workspace, g, S(stream));
+    return Ops<8, 16>::forward(h, params, mixture, est, workspace, g, S(stream));
+}
+
+int dp_gctasnet_last_launches(const dp_gctasnet* h) { return h ? h->launches : -1; }
+
+}  // extern "C"

@@ -9,8 +9,9 @@ construction order so the default initialisation is reproduced bit for bit under
 the fused Adam step and the single NCCL gradient all-reduce operate on.
 
 Supported on this path: ``module="DPRNN"`` and ``module="DPTNet"``, ``group_size=1``, ``enc_dim=bn_dim=64``,
-``hidden_dim=128``, ``win=16`` (every DPRNN / DPTNet config of the reference), ``unfold`` True or False.  Anything else
-raises.
+``hidden_dim=128``, ``win=16`` (every DPRNN / DPTNet config of the reference), ``unfold`` True or False; and the GroupComm
+variant ``module="DPRNN", group_size in (8, 16, 32)`` with per-group widths (bn_dim/G, hidden_dim/G) = (4, 8) or (8, 16)
+(``unit_tests.py:79-80`` of the reference), inference only, on its own fp32 engine (csrc/groupcomm.cu).  Anything else raises.
 """
 from __future__ import annotations
 
@@ -35,11 +36,41 @@ class _ProjRNN(nn.Module):
         self.proj = nn.Linear(hidden_size * (int(bidirectional) + 1), input_size)
 
 
-class _DPRNN(nn.Module):
-    """Parameter container with the keys of ``DPRNN`` (dprnn.py:7-51), ``num_group == 1``."""
+class _TAC(nn.Module):
+    """Parameter container with the keys of ``TAC`` (gc3_basics.py:28-36)."""
 
-    def __init__(self, input_size, hidden_size, output_size, num_layers, unfold):
+    def __init__(self, input_size, hidden_size):
         super().__init__()
+        self.TAC_input = nn.Sequential(nn.Linear(input_size, hidden_size), nn.PReLU())
+        self.TAC_mean = nn.Sequential(nn.Linear(hidden_size, hidden_size), nn.PReLU())
+        self.TAC_output = nn.Sequential(nn.Linear(hidden_size * 2, input_size), nn.PReLU())
+        self.TAC_norm = nn.GroupNorm(1, input_size)
+
+
+class _GCRNN(nn.Module):
+    """Parameter container with the keys of ``GC_RNN`` (groupcomm.py:10-24): ``TAC.i.*``, ``rnn.i.*``, ``LN.i.*``."""
+
+    def __init__(self, input_size, hidden_size, num_group, num_layers):
+        super().__init__()
+        self.TAC = nn.ModuleList([])
+        self.rnn = nn.ModuleList([])
+        self.LN = nn.ModuleList([])
+        for _ in range(num_layers):
+            self.TAC.append(_TAC(input_size // num_group, hidden_size * 3 // num_group))
+            self.rnn.append(_ProjRNN(input_size // num_group, hidden_size // num_group))
+            self.LN.append(nn.GroupNorm(1, input_size // num_group))
+
+
+class _DPRNN(nn.Module):
+    """Parameter container with the keys of ``DPRNN`` (dprnn.py:7-51); ``num_group > 1`` adds ``TAC.i.*`` and narrows everything to
+    ``input_size // num_group`` (shared by the groups)."""
+
+    def __init__(self, input_size, hidden_size, output_size, num_layers, unfold, num_group=1):
+        super().__init__()
+        if num_group > 1:
+            self.TAC = nn.ModuleList([])
+            tac_in, tac_hid = input_size // num_group, hidden_size * 3 // num_group
+            input_size, hidden_size, output_size = input_size // num_group, hidden_size // num_group, output_size // num_group
         self.row_rnn = nn.ModuleList([])
         self.col_rnn = nn.ModuleList([])
         self.row_norm = nn.ModuleList([])
@@ -51,6 +82,8 @@ class _DPRNN(nn.Module):
             col_norm = nn.GroupNorm(1, input_size, eps=1e-8)
             self.concat_block = nn.Sequential(nn.Conv2d(input_size, input_size, 1, 1, groups=input_size), nn.PReLU())
         for _ in range(num_layers):
+            if num_group > 1:
+                self.TAC.append(_TAC(tac_in, tac_hid))
             self.row_rnn.append(row_rnn if unfold else _ProjRNN(input_size, hidden_size))
             self.col_rnn.append(col_rnn if unfold else _ProjRNN(input_size, hidden_size))
             self.row_norm.append(row_norm if unfold else nn.GroupNorm(1, input_size, eps=1e-8))
@@ -99,10 +132,13 @@ class _DPTNet(nn.Module):
 class _DPWrapper(nn.Module):
     """Key prefix of ``DP_Wrapper`` (groupcomm.py:49-98): ``seq_model.*``."""
 
-    def __init__(self, input_dim, hidden_dim, output_dim, layer, unfold, module="DPRNN"):
+    def __init__(self, input_dim, hidden_dim, output_dim, layer, unfold, module="DPRNN", num_group=1):
         super().__init__()
-        cls = _DPRNN if module == "DPRNN" else _DPTNet
-        self.seq_model = cls(input_dim, hidden_dim, output_dim, layer, unfold)
+        if num_group > 1:
+            self.seq_model = _DPRNN(input_dim, hidden_dim, output_dim, layer, unfold, num_group)
+        else:
+            cls = _DPRNN if module == "DPRNN" else _DPTNet
+            self.seq_model = cls(input_dim, hidden_dim, output_dim, layer, unfold)
 
 
 class _TasNetFunction(torch.autograd.Function):
@@ -148,8 +184,8 @@ class TasNet(BaseModel):
         if module not in ("DPRNN", "DPTNet"):
             raise NotImplementedError(f"module={module!r}: this build accelerates the dual-path modules 'DPRNN' and 'DPTNet' "
                                       "(see DESIGN.md scope table)")
-        if group_size != 1:
-            raise NotImplementedError("group_size > 1 (GroupComm/TAC) is not on the accelerated path (DESIGN.md scope table)")
+        if group_size != 1 and (module != "DPRNN" or unfold):
+            raise NotImplementedError("group_size > 1 (GroupComm) is built for module='DPRNN', unfold=False (DESIGN.md scope table)")
         self.num_spk = num_spk
         self.enc_dim = enc_dim
         self.bn_dim = bn_dim
@@ -172,8 +208,13 @@ class TasNet(BaseModel):
             nn.GroupNorm(1, self.enc_dim, eps=torch.finfo(torch.float32).eps),
             nn.Conv1d(self.enc_dim, self.bn_dim, 1, bias=False),
         )
-        self.seq_model = _DPWrapper(self.bn_dim, self.hidden_dim, self.bn_dim, layer, unfold, module)
-        self.mask = nn.Sequential(nn.Conv1d(self.bn_dim, self.enc_dim * self.num_spk, 1), nn.ReLU(inplace=True))
+        if self.group_size > 1:  # context encoder / decoder (gc3_network.py:59-61)
+            self.context_enc = _GCRNN(self.bn_dim, self.hidden_dim, self.group_size, 2)
+            self.context_dec = _GCRNN(self.bn_dim, self.hidden_dim, self.group_size, 2)
+        self.seq_model = _DPWrapper(self.bn_dim, self.hidden_dim, self.bn_dim, layer, unfold, module, self.group_size)
+        self.mask = nn.Sequential(
+            nn.Conv1d(self.bn_dim // self.group_size, self.enc_dim * self.num_spk // self.group_size, 1), nn.ReLU(inplace=True)
+        )
         self.decoder = nn.ConvTranspose1d(self.enc_dim, 1, self.win, bias=False, stride=self.stride)
         torch.nn.init.xavier_uniform_(self.decoder.weight)
 
@@ -205,7 +246,10 @@ class TasNet(BaseModel):
         _lib.require_cuda(x.contiguous(), "TasNet input")
         xin = x.contiguous().float()
         self._sync_flat(xin.device)
-        est = _TasNetFunction.apply(self, xin, *self._uniq)
+        if self.group_size > 1:
+            est = self._gc_forward(xin)
+        else:
+            est = _TasNetFunction.apply(self, xin, *self._uniq)
         if est.dtype != input.dtype and input.dtype.is_floating_point:
             est = est.to(input.dtype)
         return est.squeeze(0) if was_one_d else est
@@ -214,7 +258,52 @@ class TasNet(BaseModel):
         return {"n_src": 2}  # gc3_network.py:186-188
 
     # ------------------------------------------------------------------ flat parameters / engine
+    @staticmethod
+    def _tac_params(t):
+        return [t.TAC_input[0].weight, t.TAC_input[0].bias, t.TAC_input[1].weight, t.TAC_mean[0].weight, t.TAC_mean[0].bias,
+                t.TAC_mean[1].weight, t.TAC_output[0].weight, t.TAC_output[0].bias, t.TAC_output[1].weight, t.TAC_norm.weight,
+                t.TAC_norm.bias]
+
+    @staticmethod
+    def _rnn_params(rnn, norm):
+        r = rnn.rnn
+        return [r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, r.weight_ih_l0_reverse, r.weight_hh_l0_reverse,
+                r.bias_ih_l0_reverse, r.bias_hh_l0_reverse, rnn.proj.weight, rnn.proj.bias, norm.weight, norm.bias]
+
+    def _gc_param_table(self):
+        """Order of the dp_gctasnet parameter table (include/dualpath_b200.h)."""
+        sm = self.seq_model.seq_model
+        table = [self.encoder.weight, self.bottleneck[0].weight, self.bottleneck[0].bias, self.bottleneck[1].weight, sm.output.weight,
+                 sm.output.bias, self.mask[0].weight, self.mask[0].bias, self.decoder.weight]
+        for gc in (self.context_enc, self.context_dec):
+            for i in range(2):
+                table += self._tac_params(gc.TAC[i]) + self._rnn_params(gc.rnn[i], gc.LN[i])
+        for i in range(self.layer):
+            table += self._tac_params(sm.TAC[i]) + self._rnn_params(sm.row_rnn[i], sm.row_norm[i]) + self._rnn_params(sm.col_rnn[i], sm.col_norm[i])
+        return table
+
+    def _gc_forward(self, xin):
+        """GroupComm engine: inference only (the training backward of this path is not built; it fails loudly instead of falling back)."""
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self._uniq):
+            raise NotImplementedError("TasNet(group_size > 1): the GroupComm engine is inference-only (call model.eval(); DESIGN.md scope table)")
+        B, T = xin.shape
+        nbytes = lib().dp_gctasnet_workspace_bytes(self._handle, B, T)
+        if nbytes < 0:
+            check(1, "dp_gctasnet_workspace_bytes")
+        ws = torch.empty(nbytes, device=xin.device, dtype=torch.uint8)
+        est = torch.empty(B, self.num_spk, T, device=xin.device, dtype=torch.float32)
+        check(lib().dp_gctasnet_forward(self._handle, ptr(self._flat), ptr(xin), ptr(est), ptr(ws), B, T, stream_ptr()), "dp_gctasnet_forward")
+        self.last_launches = lib().dp_gctasnet_last_launches(self._handle)
+        return est
+
+    def _destroy_handle(self):
+        if self._handle is not None:
+            (lib().dp_gctasnet_destroy if self.group_size > 1 else lib().dp_tasnet_destroy)(self._handle)
+            self._handle = None
+
     def _param_table(self):
+        if self.group_size > 1:
+            return self._gc_param_table()
         sm = self.seq_model.seq_model
         cat = sm.concat_block if self.unfold else None
         table = [
@@ -284,9 +373,15 @@ class TasNet(BaseModel):
                 p.data = flat[o : o + p.numel()].view(p.shape)
         self._flat, self._uniq, self._uniq_off = flat, uniq, offs
         offsets = [(-1 if p is None else seen[id(p)]) for p in table]
-        if self._handle is not None:
-            lib().dp_tasnet_destroy(self._handle)
-            self._handle = None
+        self._destroy_handle()
+        if self.group_size > 1:
+            cfg = _lib.GcTasnetConfig(self.enc_dim, self.bn_dim, self.hidden_dim, self.win, self.layer, self.num_spk, self.context_size,
+                                      self.group_size, self.block_size)
+            arr = (C.c_int64 * len(offsets))(*offsets)
+            h = C.c_void_p()
+            check(lib().dp_gctasnet_create(C.byref(cfg), arr, len(offsets), total, C.byref(h)), "dp_gctasnet_create")
+            self._handle = h
+            return
         cfg = _lib.TasnetConfig(self.enc_dim, self.bn_dim, self.hidden_dim, self.win, self.layer, self.num_spk, self.block_size,
                                 int(self.unfold), _lib.MODULE_DPTNET if self.model_name == "DPTNet" else _lib.MODULE_DPRNN)
         arr = (C.c_int64 * len(offsets))(*offsets)
@@ -298,8 +393,7 @@ class TasNet(BaseModel):
 
     def __del__(self):
         try:
-            if self._handle is not None:
-                lib().dp_tasnet_destroy(self._handle)
+            self._destroy_handle()
         except Exception:
             pass
 

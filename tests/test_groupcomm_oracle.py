@@ -1,0 +1,60 @@
+"""CPU tests of the GroupComm path: the oracle against the reference's golden outputs, and the drop-in model's parameter containers
+(state-dict keys, shapes and default initialisation of the reference)."""
+import json
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN, load_npz, rel_l2
+from oracle import groupcomm_oracle as GO
+
+GC_MANIFEST = json.load(open(os.path.join(GOLDEN, "groupcomm_manifest.json")))
+
+
+def _model(case):
+    from audio_only_speech_separation_b200.models import TasNet
+
+    c = GC_MANIFEST["cases"][case]
+    torch.manual_seed(c["seed"])
+    return TasNet(**c["kwargs"]), c
+
+
+@pytest.mark.parametrize("case", ["g16_b1_t300", "g16_b1_t3999_1d", "g8_l2_b2_t4000"])
+def test_oracle_matches_reference_golden(case):
+    m, c = _model(case)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    z = load_npz(f"groupcomm_{case}.npz")
+    taps = {}
+    with torch.no_grad():
+        y = GO.tasnet_gc_forward(sd, torch.from_numpy(z["x"]), group_size=c["kwargs"]["group_size"], layer=c["kwargs"].get("layer", 6),
+                                 lstm_impl="loop", taps=taps)
+    assert rel_l2(y, torch.from_numpy(z["y"])) < 5e-6
+    assert rel_l2(taps["squeeze_mean"], torch.from_numpy(z["squeeze_mean"])) < 5e-6
+    assert rel_l2(taps["feature_map"], torch.from_numpy(z["feature_map"])) < 5e-6
+
+
+@pytest.mark.parametrize("case", ["g16_b2_t8001", "g8_l2_b2_t4000"])
+def test_state_dict_is_the_reference_one(case):
+    m, c = _model(case)
+    sd, ref = m.state_dict(), GC_MANIFEST["state_dicts"][case]
+    assert list(sd.keys()) == list(ref.keys())
+    for k, v in sd.items():
+        assert list(v.shape) == ref[k][2:], k
+        assert abs(float(v.double().sum()) - ref[k][0]) <= 1e-9 * max(1.0, abs(ref[k][0])), k
+        assert abs(float(v.double().abs().sum()) - ref[k][1]) <= 1e-9 * max(1.0, ref[k][1]), k
+    assert sum(p.numel() for p in m.parameters()) == c["n_params"]
+    from audio_only_speech_separation_b200 import _lib
+
+    assert len(m._gc_param_table()) == 9 + 4 * 23 + 35 * c["kwargs"].get("layer", 6)
+
+
+def test_unsupported_variants_raise():
+    from audio_only_speech_separation_b200.models import TasNet
+
+    with pytest.raises(NotImplementedError):
+        TasNet(module="DPTNet", group_size=16)
+    with pytest.raises(NotImplementedError):
+        TasNet(module="DPRNN", group_size=16, unfold=True)
+    with pytest.raises(RuntimeError):   # CUDA-only: CPU tensors are refused, there is no CPU path
+        TasNet(module="DPRNN", group_size=16).eval()(torch.zeros(1, 800))
