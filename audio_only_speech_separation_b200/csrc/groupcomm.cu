@@ -72,8 +72,8 @@ __device__ __forceinline__ void stats_add(double* stats, float s, float ss, bool
 template <int NG, int HG>
 __global__ void __launch_bounds__(256) gc_tac_kernel(const float* __restrict__ X, float* __restrict__ Y, double* __restrict__ stats, TacW w,
                                                      long long npos, int G, int pps) {
-    constexpr int TH = 3 * HG, KMAX = (TH + 7) / 8, LD2 = TH + 1;
-    __shared__ float s_w1[TH * NG], s_b1[TH], s_w2[TH * LD2], s_b2[TH], s_w3[NG * 2 * TH], s_b3[NG];
+    constexpr int TH = 3 * HG, KMAX = (TH + 7) / 8, LD2 = TH + 1;   // odd row pitch: the lanes' column reads hit distinct banks
+    __shared__ __align__(16) float s_w1[TH * NG], s_b1[TH], s_w2[TH * LD2], s_b2[TH], s_w3[NG * 2 * TH], s_b3[NG];
     for (int i = threadIdx.x; i < TH * NG; i += blockDim.x) s_w1[i] = w.w1[i];
     for (int i = threadIdx.x; i < TH * TH; i += blockDim.x) s_w2[(i / TH) * LD2 + i % TH] = w.w2[i];
     for (int i = threadIdx.x; i < NG * 2 * TH; i += blockDim.x) s_w3[i] = w.w3[i];
@@ -91,7 +91,12 @@ __global__ void __launch_bounds__(256) gc_tac_kernel(const float* __restrict__ X
         float4 v = active ? *reinterpret_cast<const float4*>(X + i * NG + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         x[j] = v.x; x[j + 1] = v.y; x[j + 2] = v.z; x[j + 3] = v.w;
     }
-    float y[TH], ym[TH];
+    // TAC_mean: its TH rows are spread over the G lanes of a position (row r on lane r % G) and gathered in the output sum below;
+    // each group-mean value is folded into those rows as soon as its reduction over the groups is done
+    float y[TH], ms[KMAX];
+    const float inv_g = 1.f / (float)G;   // G is a power of two: exact
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) ms[k] = (g + k * G < TH) ? s_b2[g + k * G] : 0.f;
 #pragma unroll
     for (int r = 0; r < TH; ++r) {
         float acc = s_b1[r];
@@ -100,22 +105,13 @@ __global__ void __launch_bounds__(256) gc_tac_kernel(const float* __restrict__ X
         y[r] = prelu1(acc, a1);
         float v = y[r];
         for (int o = G >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        ym[r] = v / (float)G;
-    }
-    // TAC_mean: its TH rows are spread over the G lanes of a position (row r on lane r % G), then gathered in the output sum
-    float ms[KMAX];
+        v *= inv_g;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-        const int r = g + k * G;
-        float acc = 0.f;
-        if (r < TH) {
-            acc = s_b2[r];
-#pragma unroll
-            for (int c = 0; c < TH; ++c) acc = fmaf(s_w2[r * LD2 + c], ym[c], acc);
-            acc = prelu1(acc, a2);
-        }
-        ms[k] = acc;
+        for (int k = 0; k < KMAX; ++k)
+            if (g + k * G < TH) ms[k] = fmaf(s_w2[(g + k * G) * LD2 + r], v, ms[k]);
     }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) ms[k] = prelu1(ms[k], a2);
     float out[NG];
 #pragma unroll
     for (int j = 0; j < NG; ++j) {
@@ -230,9 +226,10 @@ __global__ void __launch_bounds__(128) gc_lstm_kernel(const float* __restrict__ 
 #pragma unroll
             for (int gt = 0; gt < 4; ++gt) a[gt] = fmaf(wh[gt][k], hk, a[gt]);
         }
-        const float ig = 1.f / (1.f + expf(-a[0])), fg = 1.f / (1.f + expf(-a[1])), gg = tanhf(a[2]), og = 1.f / (1.f + expf(-a[3]));
+        // ex2.approx / rcp.approx cell functions of the main recurrence engine (common.cuh): ~1e-7 absolute error per evaluation
+        const float ig = sigmoid_cell<true>(a[0]), fg = sigmoid_cell<true>(a[1]), gg = tanh_cell<true>(a[2]), og = sigmoid_cell<true>(a[3]);
         c = fmaf(fg, c, ig * gg);
-        h = og * tanhf(c);
+        h = og * tanh_cell<true>(c);
         if (active) Hh[(bp + (long long)t * s_t) * C2 + g * 2 * HG + dir * HG + j] = h;
     }
 }
@@ -291,21 +288,33 @@ __global__ void __launch_bounds__(256) gc_group_linear_kernel(const float* __res
 }
 
 // ---- waveform encoder Conv1d(1, E, win, stride = win/2, no bias) on the zero-padded input + statistics of the bottleneck norm ---------
+constexpr int FRAMES_PER_CTA = 32;
 __global__ void __launch_bounds__(256) gc_encoder_kernel(const float* __restrict__ x, const float* __restrict__ W, float* __restrict__ enc,
                                                          double* __restrict__ stats, int T, int F, int E, int win) {
+    __shared__ double red[16];
     const int fpb = blockDim.x / E, fl = threadIdx.x / E, e = threadIdx.x % E, b = blockIdx.y;
-    const int f = blockIdx.x * fpb + fl, stride = win / 2;
-    float acc = 0.f;
-    if (f < F) {
-        const float* xb = x + (size_t)b * T;
+    const int stride = win / 2, f0 = blockIdx.x * FRAMES_PER_CTA;
+    const float* xb = x + (size_t)b * T;
+    float sf = 0.f, ssf = 0.f;   // at most FRAMES_PER_CTA / fpb values per thread: fp32 partials, fp64 from the warp reduction on
+    for (int f = f0 + fl; f < min(f0 + FRAMES_PER_CTA, F); f += fpb) {
+        float acc = 0.f;
         for (int k = 0; k < win; ++k) {
             const int t = f * stride + k - stride;   // the padded signal starts with `stride` zeros (gc3_network.py:128-129)
             if (t >= 0 && t < T) acc = fmaf(__ldg(W + e * win + k), __ldg(xb + t), acc);
         }
         enc[((size_t)b * F + f) * E + e] = acc;
+        sf += acc;
+        ssf = fmaf(acc, acc, ssf);
     }
-    double s = warp_sum_d((double)acc), ss = warp_sum_d((double)acc * acc);
-    if ((threadIdx.x & 31) == 0 && f < F) { atomicAdd(stats + 2 * b, s); atomicAdd(stats + 2 * b + 1, ss); }
+    const double s = warp_sum_d((double)sf), ss = warp_sum_d((double)ssf);
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[2 * warp] = s; red[2 * warp + 1] = ss; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[2 * w + threadIdx.x];
+        atomicAdd(stats + 2 * b + threadIdx.x, v);
+    }
 }
 
 // ---- bottleneck: GroupNorm(1, E, eps = fp32 eps) + Conv1d(E, C, 1, no bias) ------------------------------------------------------------
@@ -314,22 +323,29 @@ __global__ void __launch_bounds__(256) gc_bottleneck_kernel(const float* __restr
                                                             const double* __restrict__ stats, float* __restrict__ feat, int F, int E, int C,
                                                             double eps) {
     extern __shared__ float sm[];
-    float* wt = sm;              // [E][C]: the weight transposed, so the threads of a frame read consecutive words
-    float* row = sm + E * C;     // [fpb][E]
+    const int LDW = C + 1;         // padded: the transposing stores below hit distinct banks
+    float* wt = sm;                // [E][C + 1]: the weight transposed, so the threads of a frame read consecutive words
+    float* row = sm + E * LDW;     // [fpb][E]
     const int fpb = blockDim.x / E, fl = threadIdx.x / E, e = threadIdx.x % E, b = blockIdx.y;
-    const int f = blockIdx.x * fpb + fl;
-    for (int i = threadIdx.x; i < E * C; i += blockDim.x) wt[(i % E) * C + i / E] = W[i];
+    const int f0 = blockIdx.x * FRAMES_PER_CTA;
+    for (int i = threadIdx.x; i < E * C; i += blockDim.x) wt[(i % E) * LDW + i / E] = W[i];
     const double inv = 1.0 / ((double)F * E), mean = stats[2 * b] * inv;
     double var = stats[2 * b + 1] * inv - mean * mean;
     if (var < 0.0) var = 0.0;
     const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + eps));
-    row[fl * E + e] = f < F ? (enc[((size_t)b * F + f) * E + e] - mu) * rstd * __ldg(gamma + e) + __ldg(beta + e) : 0.f;
-    __syncthreads();
-    if (f >= F) return;
-    for (int c = e; c < C; c += E) {
-        float acc = 0.f;
-        for (int k = 0; k < E; ++k) acc = fmaf(wt[k * C + c], row[fl * E + k], acc);
-        feat[((size_t)b * F + f) * C + c] = acc;
+    const float ga = __ldg(gamma + e) * rstd, be = __ldg(beta + e) - mu * rstd * __ldg(gamma + e);
+    for (int fb = f0; fb < min(f0 + FRAMES_PER_CTA, F); fb += fpb) {
+        const int f = fb + fl;
+        __syncthreads();
+        row[fl * E + e] = f < F ? fmaf(enc[((size_t)b * F + f) * E + e], ga, be) : 0.f;
+        __syncthreads();
+        if (f >= F) continue;
+        for (int c = e; c < C; c += E) {
+            float acc = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < E; ++k) acc = fmaf(wt[k * LDW + c], row[fl * E + k], acc);
+            feat[((size_t)b * F + f) * C + c] = acc;
+        }
     }
 }
 
@@ -367,7 +383,10 @@ __global__ void __launch_bounds__(256) gc_decoder_kernel(const float* __restrict
         if (f < 0 || f >= F) continue;
         const float* er = enc + ((size_t)b * F + f) * E;
         const float* mr = Mk + ((size_t)b * F + f) * (size_t)(spk * E);
-        for (int e = 0; e < E; ++e) acc = fmaf(__ldg(Wd + e * win + k) * mr[(e / eg) * (spk * eg) + s * eg + e % eg], er[e], acc);
+        for (int g = 0, e = 0; g < G; ++g) {
+            const float* mg = mr + g * (spk * eg) + s * eg;
+            for (int j = 0; j < eg; ++j, ++e) acc = fmaf(__ldg(Wd + e * win + k) * mg[j], er[e], acc);
+        }
     }
     est[i] = acc;
 }
@@ -480,9 +499,9 @@ struct Ops {
         h->launches = 0;
         CK(cudaMemsetAsync(st, 0, l.stats_bytes, s));
         const int fpb = 256 / g.E;
-        dim3 fgrid(ceil_div(g.F, fpb), g.B);
+        dim3 fgrid(ceil_div(g.F, FRAMES_PER_CTA), g.B);
         gc_encoder_kernel<<<fgrid, 256, 0, s>>>(mix, p + h->off[P_ENC_W], enc, st, g.T, g.F, g.E, c.win);
-        const size_t smem = ((size_t)g.E * g.C + (size_t)fpb * g.E) * sizeof(float);
+        const size_t smem = ((size_t)g.E * (g.C + 1) + (size_t)fpb * g.E) * sizeof(float);
         gc_bottleneck_kernel<<<fgrid, 256, smem, s>>>(enc, p + h->off[P_BN_G], p + h->off[P_BN_B], p + h->off[P_BN_W], st, feat, g.F, g.E, g.C,
                                                       (double)1.1920928955078125e-07f);
         CK(cudaGetLastError());
@@ -542,7 +561,7 @@ int dp_gctasnet_create(const dp_gctasnet_config* cfg, const int64_t* offsets, in
     if (!((n == 4 && hh == 8) || (n == 8 && hh == 16)))
         return fail("dp_gctasnet_create: per-group widths (bn_dim / G, hidden_dim / G) must be (4, 8) or (8, 16), got (%d, %d)", n, hh);
     if (cfg->enc_dim % 32 || 256 % cfg->enc_dim) return fail("dp_gctasnet_create: enc_dim must be 32, 64, 128 or 256 (got %d)", cfg->enc_dim);
-    if ((size_t)(cfg->enc_dim * cfg->bn_dim + 256) * sizeof(float) > 48 * 1024) return fail("dp_gctasnet_create: enc_dim * bn_dim too large");
+    if ((size_t)(cfg->enc_dim * (cfg->bn_dim + 1) + 256) * sizeof(float) > 48 * 1024) return fail("dp_gctasnet_create: enc_dim * bn_dim too large");
     if (cfg->win <= 0 || (cfg->win & 1)) return fail("dp_gctasnet_create: win must be even and positive");
     if (cfg->context_size <= 0 || (cfg->context_size & 1) || cfg->block_size <= 0 || (cfg->block_size & 1))
         return fail("dp_gctasnet_create: context_size and block_size must be even and positive");
