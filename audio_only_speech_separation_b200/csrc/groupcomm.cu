@@ -234,6 +234,107 @@ __global__ void __launch_bounds__(128) gc_lstm_kernel(const float* __restrict__ 
     }
 }
 
+// ---- context stage of GC_RNN fused (groupcomm.py:38-42): BiLSTM + Linear(2h -> n) + GroupNorm(1, n) + residual of one (block, group)
+// unit by the 2h lanes of a warp segment.  The norm of this stage spans only ctx x n values of one unit, so nothing has to leave the
+// CTA: x and h of the unit sit in shared memory, the norm statistics are shuffle reductions (two-pass variance), A is updated in place.
+template <int NG, int HG>
+__global__ void __launch_bounds__(128) gc_ctx_rnn_kernel(float* A, RnnW w, long long nunits, int G, int ctx, float eps) {
+    constexpr int UL = 2 * HG, UPB = 128 / UL, LDH = UL + 1, MAXO = 8;
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                       // [UPB][ctx][NG]
+    float* hs = sm + UPB * ctx * NG;      // [UPB][ctx][LDH]
+    __shared__ float s_pw[NG * LDH], s_pb[NG], s_ga[NG], s_be[NG];   // odd row pitch: lanes with different output features hit distinct banks
+    for (int i = threadIdx.x; i < NG * UL; i += blockDim.x) s_pw[(i / UL) * LDH + i % UL] = w.pw[i];
+    if (threadIdx.x < NG) { s_pb[threadIdx.x] = w.pb[threadIdx.x]; s_ga[threadIdx.x] = w.gamma[threadIdx.x]; s_be[threadIdx.x] = w.beta[threadIdx.x]; }
+    const int C = G * NG;
+    // stage the units' inputs: for a fixed frame the units of a CTA are adjacent groups, i.e. contiguous floats
+    for (int idx = threadIdx.x; idx < UPB * ctx * (NG / 4); idx += blockDim.x) {
+        const int k4 = idx % (NG / 4), uu = (idx / (NG / 4)) % UPB, t = idx / ((NG / 4) * UPB);
+        long long qq = (long long)blockIdx.x * UPB + uu;
+        if (qq >= nunits) qq = nunits - 1;
+        const float4 v = *reinterpret_cast<const float4*>(A + ((qq / G) * ctx + t) * C + (qq % G) * NG + k4 * 4);
+        *reinterpret_cast<float4*>(xs + (uu * ctx + t) * NG + k4 * 4) = v;
+    }
+    const int u = threadIdx.x / UL, l = threadIdx.x % UL, dir = l / HG, j = l % HG;
+    const long long q = (long long)blockIdx.x * UPB + u;
+    const bool active = q < nunits;
+    float wi[4][NG], wh[4][HG], b[4];
+#pragma unroll
+    for (int gt = 0; gt < 4; ++gt) {
+        const int row = gt * HG + j;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) wi[gt][k] = __ldg(w.wih[dir] + row * NG + k);
+#pragma unroll
+        for (int k = 0; k < HG; ++k) wh[gt][k] = __ldg(w.whh[dir] + row * HG + k);
+        b[gt] = __ldg(w.bih[dir] + row) + __ldg(w.bhh[dir] + row);
+    }
+    __syncthreads();
+    float h = 0.f, c = 0.f;
+    int t = dir ? ctx - 1 : 0;
+    const int dt = dir ? -1 : 1;
+    for (int step = 0; step < ctx; ++step, t += dt) {
+        float x[NG];
+#pragma unroll
+        for (int k = 0; k < NG; k += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(xs + (u * ctx + t) * NG + k);
+            x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+        }
+        float a[4] = {b[0], b[1], b[2], b[3]};
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt) a[gt] = fmaf(wi[gt][k], x[k], a[gt]);
+        }
+#pragma unroll
+        for (int k = 0; k < HG; ++k) {
+            const float hk = __shfl_sync(0xffffffffu, h, k, HG);
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt) a[gt] = fmaf(wh[gt][k], hk, a[gt]);
+        }
+        const float ig = sigmoid_cell<true>(a[0]), fg = sigmoid_cell<true>(a[1]), gg = tanh_cell<true>(a[2]), og = sigmoid_cell<true>(a[3]);
+        c = fmaf(fg, c, ig * gg);
+        h = og * tanh_cell<true>(c);
+        hs[(u * ctx + t) * LDH + l] = h;
+    }
+    __syncwarp();   // a unit's 2h lanes live in one warp
+    const int nout = ctx * NG;
+    float y[MAXO], s = 0.f;
+#pragma unroll
+    for (int m = 0; m < MAXO; ++m) {
+        const int o = l + m * UL;
+        y[m] = 0.f;
+        if (o < nout) {
+            const int tt = o / NG, k = o % NG;
+            float acc = s_pb[k];
+#pragma unroll
+            for (int cc = 0; cc < UL; ++cc) acc = fmaf(s_pw[k * LDH + cc], hs[(u * ctx + tt) * LDH + cc], acc);
+            y[m] = acc;
+            s += acc;
+        }
+    }
+#pragma unroll
+    for (int o = UL >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)nout;
+    float ss = 0.f;
+#pragma unroll
+    for (int m = 0; m < MAXO; ++m)
+        if (l + m * UL < nout) ss = fmaf(y[m] - mean, y[m] - mean, ss);
+#pragma unroll
+    for (int o = UL >> 1; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = 1.f / sqrtf(ss / (float)nout + eps);
+    if (active) {
+        float* base = A + (q / G) * ctx * C + (q % G) * NG;
+#pragma unroll
+        for (int m = 0; m < MAXO; ++m) {
+            const int o = l + m * UL;
+            if (o < nout) {
+                const int tt = o / NG, k = o % NG;
+                base[(long long)tt * C + k] = xs[(u * ctx + tt) * NG + k] + ((y[m] - mean) * rstd * s_ga[k] + s_be[k]);
+            }
+        }
+    }
+}
+
 // ---- Linear(2h -> n) of the ProjRNN + statistics of the GroupNorm that follows ------------------------------------------------------
 template <int NG, int HG>
 __global__ void __launch_bounds__(256) gc_proj_kernel(const float* __restrict__ Hh, float* __restrict__ Y, double* __restrict__ stats, RnnW w,
@@ -292,6 +393,9 @@ constexpr int FRAMES_PER_CTA = 32;
 __global__ void __launch_bounds__(256) gc_encoder_kernel(const float* __restrict__ x, const float* __restrict__ W, float* __restrict__ enc,
                                                          double* __restrict__ stats, int T, int F, int E, int win) {
     __shared__ double red[16];
+    extern __shared__ float wsm[];   // [win][E]: tap-major, so the lanes (consecutive channels) read consecutive words
+    for (int i = threadIdx.x; i < E * win; i += blockDim.x) wsm[(i % win) * E + i / win] = W[i];
+    __syncthreads();
     const int fpb = blockDim.x / E, fl = threadIdx.x / E, e = threadIdx.x % E, b = blockIdx.y;
     const int stride = win / 2, f0 = blockIdx.x * FRAMES_PER_CTA;
     const float* xb = x + (size_t)b * T;
@@ -300,7 +404,7 @@ __global__ void __launch_bounds__(256) gc_encoder_kernel(const float* __restrict
         float acc = 0.f;
         for (int k = 0; k < win; ++k) {
             const int t = f * stride + k - stride;   // the padded signal starts with `stride` zeros (gc3_network.py:128-129)
-            if (t >= 0 && t < T) acc = fmaf(__ldg(W + e * win + k), __ldg(xb + t), acc);
+            if (t >= 0 && t < T) acc = fmaf(wsm[k * E + e], __ldg(xb + t), acc);
         }
         enc[((size_t)b * F + f) * E + e] = acc;
         sf += acc;
@@ -466,6 +570,15 @@ struct Ops {
         h->launches += 3;
         return cudaGetLastError();
     }
+    // fused context stage (ctx * n / 2h <= 8 outputs per lane, i.e. context_size <= 32 for the built widths)
+    static bool ctx_fused(int ctx) { return (ctx * NG + 2 * HG - 1) / (2 * HG) <= 8; }
+    static cudaError_t ctx_rnn(dp_gctasnet* h, float* A, const RnnW& w, long long nunits, int G, int ctx, cudaStream_t s) {
+        constexpr int UPB = 128 / (2 * HG);
+        const size_t smem = (size_t)UPB * ctx * (NG + 2 * HG + 1) * sizeof(float);
+        gc_ctx_rnn_kernel<NG, HG><<<blocks_for(nunits, UPB), 128, smem, s>>>(A, w, nunits, G, ctx, 1e-5f);
+        h->launches += 1;
+        return cudaGetLastError();
+    }
     static cudaError_t group_linear(dp_gctasnet* h, const float* X, float* Y, const float* W, const float* b, long long total, int nout, int relu,
                                     cudaStream_t s) {
         gc_group_linear_kernel<NG><<<blocks_for(total), 256, 0, s>>>(X, Y, W, b, total, nout, relu);
@@ -482,7 +595,10 @@ struct Ops {
         for (int i = 0; i < 2; ++i) {
             CK(tac(h, i == 0 ? in : A, Y, A, st, tac_w(h, p, base + i * GC_LAYER), npos, g.G, g.ctx, s));
             st += slot;
-            CK(rnn(h, A, Y, Hh, st, rnn_w(h, p, base + i * GC_LAYER + TAC_N), npos, g.G, g.ctx, q, 1e-5, s));
+            if (ctx_fused(g.ctx))
+                CK(ctx_rnn(h, A, rnn_w(h, p, base + i * GC_LAYER + TAC_N), (long long)g.B * g.Lc * g.G, g.G, g.ctx, s));
+            else
+                CK(rnn(h, A, Y, Hh, st, rnn_w(h, p, base + i * GC_LAYER + TAC_N), npos, g.G, g.ctx, q, 1e-5, s));
             st += slot;
         }
         return 0;
@@ -500,7 +616,7 @@ struct Ops {
         CK(cudaMemsetAsync(st, 0, l.stats_bytes, s));
         const int fpb = 256 / g.E;
         dim3 fgrid(ceil_div(g.F, FRAMES_PER_CTA), g.B);
-        gc_encoder_kernel<<<fgrid, 256, 0, s>>>(mix, p + h->off[P_ENC_W], enc, st, g.T, g.F, g.E, c.win);
+        gc_encoder_kernel<<<fgrid, 256, (size_t)g.E * c.win * sizeof(float), s>>>(mix, p + h->off[P_ENC_W], enc, st, g.T, g.F, g.E, c.win);
         const size_t smem = ((size_t)g.E * (g.C + 1) + (size_t)fpb * g.E) * sizeof(float);
         gc_bottleneck_kernel<<<fgrid, 256, smem, s>>>(enc, p + h->off[P_BN_G], p + h->off[P_BN_B], p + h->off[P_BN_W], st, feat, g.F, g.E, g.C,
                                                       (double)1.1920928955078125e-07f);
@@ -562,7 +678,7 @@ int dp_gctasnet_create(const dp_gctasnet_config* cfg, const int64_t* offsets, in
         return fail("dp_gctasnet_create: per-group widths (bn_dim / G, hidden_dim / G) must be (4, 8) or (8, 16), got (%d, %d)", n, hh);
     if (cfg->enc_dim % 32 || 256 % cfg->enc_dim) return fail("dp_gctasnet_create: enc_dim must be 32, 64, 128 or 256 (got %d)", cfg->enc_dim);
     if ((size_t)(cfg->enc_dim * (cfg->bn_dim + 1) + 256) * sizeof(float) > 48 * 1024) return fail("dp_gctasnet_create: enc_dim * bn_dim too large");
-    if (cfg->win <= 0 || (cfg->win & 1)) return fail("dp_gctasnet_create: win must be even and positive");
+    if (cfg->win <= 0 || (cfg->win & 1) || cfg->win > 64) return fail("dp_gctasnet_create: win must be even, positive and at most 64");
     if (cfg->context_size <= 0 || (cfg->context_size & 1) || cfg->block_size <= 0 || (cfg->block_size & 1))
         return fail("dp_gctasnet_create: context_size and block_size must be even and positive");
     if (cfg->layer < 1 || cfg->num_spk < 1) return fail("dp_gctasnet_create: layer and num_spk must be >= 1");

@@ -55,6 +55,24 @@ def test_forward_matches_oracle_on_other_shapes(case, B, T):
     assert rel_l2(y[:1], y0) < 1e-6   # every utterance is independent through the path
 
 
+def test_other_context_and_block_sizes_match_oracle():
+    """context_size 40 takes the unfused context stage (LSTM / projection / norm as separate kernels), 16 the fused one; block_size 50."""
+    from audio_only_speech_separation_b200.models import TasNet
+
+    for ctx, G in ((40, 16), (16, 8)):
+        torch.manual_seed(3)
+        m = TasNet(module="DPRNN", enc_dim=64, bn_dim=64, group_size=G, context_size=ctx, block_size=50, layer=2)
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        m = m.cuda().eval()
+        x = torch.randn(2, 5003, generator=torch.Generator().manual_seed(5)) * 0.1
+        with torch.no_grad():
+            y = m(x.cuda())
+            ref = GO.tasnet_gc_forward(sd, x, group_size=G, layer=2, context_size=ctx, block_size=50)
+        err = rel_l2(y, ref)
+        record("groupcomm_fwd_oracle_ctx", context_size=ctx, group_size=G, rel_l2=err, launches=m.last_launches)
+        assert err < FP32_TOL
+
+
 def test_full_size_batch_properties():
     """4 s at 8 kHz, B = 16: finite, scale-equivariant in the way the path is (the bottleneck GroupNorm makes the masks invariant to
     the input gain up to its eps = 1.2e-7 against the frame variance, so est(a * x) = a * est(x) for unit-scale inputs), and
