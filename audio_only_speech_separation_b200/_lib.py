@@ -31,7 +31,7 @@ class TasnetConfig(C.Structure):
 
 class GcTasnetConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("enc_dim", "bn_dim", "hidden_dim", "win", "layer", "num_spk", "context_size", "group_size",
-                                       "block_size")]
+                                       "block_size", "unfold")]
 
 
 class SepformerConfig(C.Structure):

@@ -34,8 +34,8 @@ struct dp_gctasnet {
 
 namespace {
 
-constexpr int HEAD = 9, TAC_N = 11, RNN_N = 12, GC_LAYER = TAC_N + RNN_N, GC_BLOCK = 2 * GC_LAYER, DP_LAYER = TAC_N + 2 * RNN_N;
-enum { P_ENC_W, P_BN_G, P_BN_B, P_BN_W, P_OUT_W, P_OUT_B, P_MASK_W, P_MASK_B, P_DEC_W };
+constexpr int HEAD = 12, TAC_N = 11, RNN_N = 12, GC_LAYER = TAC_N + RNN_N, GC_BLOCK = 2 * GC_LAYER, DP_LAYER = TAC_N + 2 * RNN_N;
+enum { P_ENC_W, P_BN_G, P_BN_B, P_BN_W, P_OUT_W, P_OUT_B, P_MASK_W, P_MASK_B, P_DEC_W, P_CAT_W, P_CAT_B, P_CAT_A };
 
 struct TacW { const float *w1, *b1, *a1, *w2, *b2, *a2, *w3, *b3, *a3, *gamma, *beta; };
 struct RnnW { const float *wih[2], *whh[2], *bih[2], *bhh[2], *pw, *pb, *gamma, *beta; };
@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(256) gc_tac_kernel(const float* __restrict__ X
 template <int NG>
 __global__ void __launch_bounds__(256) gc_gn_res_kernel(const float* __restrict__ Y, const float* __restrict__ R, float* __restrict__ Out,
                                                         const double* __restrict__ stats, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, long long total, int G, int pps, double eps) {
+                                                        const float* __restrict__ beta, long long total, int G, int pps, double eps,
+                                                        const float* __restrict__ cat_w, const float* __restrict__ cat_b,
+                                                        const float* __restrict__ cat_a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const long long pos = i / G;
@@ -168,6 +170,13 @@ __global__ void __launch_bounds__(256) gc_gn_res_kernel(const float* __restrict_
         o.y = r.y + ((y.y - mu) * rstd * __ldg(gamma + j + 1) + __ldg(beta + j + 1));
         o.z = r.z + ((y.z - mu) * rstd * __ldg(gamma + j + 2) + __ldg(beta + j + 2));
         o.w = r.w + ((y.w - mu) * rstd * __ldg(gamma + j + 3) + __ldg(beta + j + 3));
+        if (cat_w) {   // unfold: depthwise 1x1 conv + PReLU of the shared concat_block (dprnn.py:31-34,82)
+            const float a = __ldg(cat_a);
+            o.x = prelu1(fmaf(o.x, __ldg(cat_w + j), __ldg(cat_b + j)), a);
+            o.y = prelu1(fmaf(o.y, __ldg(cat_w + j + 1), __ldg(cat_b + j + 1)), a);
+            o.z = prelu1(fmaf(o.z, __ldg(cat_w + j + 2), __ldg(cat_b + j + 2)), a);
+            o.w = prelu1(fmaf(o.w, __ldg(cat_w + j + 3), __ldg(cat_b + j + 3)), a);
+        }
         *reinterpret_cast<float4*>(Out + i * NG + j) = o;
     }
 }
@@ -557,16 +566,17 @@ struct Ops {
     static cudaError_t tac(dp_gctasnet* h, const float* X, float* Y, float* Out, double* st, const TacW& w, long long npos, int G, int pps,
                            cudaStream_t s) {
         gc_tac_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(X, Y, st, w, npos, G, pps);
-        gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, X, Out, st, w.gamma, w.beta, npos * G, G, pps, 1e-5);
+        gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, X, Out, st, w.gamma, w.beta, npos * G, G, pps, 1e-5, nullptr, nullptr, nullptr);
         h->launches += 2;
         return cudaGetLastError();
     }
     static cudaError_t rnn(dp_gctasnet* h, float* A, float* Y, float* Hh, double* st, const RnnW& w, long long npos, int G, int pps,
-                           const SeqWalk& q, double eps, cudaStream_t s) {
+                           const SeqWalk& q, double eps, cudaStream_t s, const float* cat_w = nullptr, const float* cat_b = nullptr,
+                           const float* cat_a = nullptr) {
         dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
         gc_lstm_kernel<NG, HG><<<grid, 128, 0, s>>>(A, Hh, w, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t);
         gc_proj_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Y, st, w, npos, G, pps);
-        gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, A, A, st, w.gamma, w.beta, npos * G, G, pps, eps);
+        gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, A, A, st, w.gamma, w.beta, npos * G, G, pps, eps, cat_w, cat_b, cat_a);
         h->launches += 3;
         return cudaGetLastError();
     }
@@ -641,7 +651,11 @@ struct Ops {
             st += dslot;
             CK(rnn(h, A, Y, Hh, st, rnn_w(h, p, base + TAC_N), g.PD, g.G, pps, row, 1e-8, s));
             st += dslot;
-            CK(rnn(h, A, Y, Hh, st, rnn_w(h, p, base + TAC_N + RNN_N), g.PD, g.G, pps, col, 1e-8, s));
+            if (c.unfold)
+                CK(rnn(h, A, Y, Hh, st, rnn_w(h, p, base + TAC_N + RNN_N), g.PD, g.G, pps, col, 1e-8, s, p + h->off[P_CAT_W], p + h->off[P_CAT_B],
+                       p + h->off[P_CAT_A]));
+            else
+                CK(rnn(h, A, Y, Hh, st, rnn_w(h, p, base + TAC_N + RNN_N), g.PD, g.G, pps, col, 1e-8, s));
             st += dslot;
         }
         CK(group_linear(h, A, Y, p + h->off[P_OUT_W], p + h->off[P_OUT_B], g.PD * g.G, g.n, 0, s));
@@ -683,8 +697,10 @@ int dp_gctasnet_create(const dp_gctasnet_config* cfg, const int64_t* offsets, in
         return fail("dp_gctasnet_create: context_size and block_size must be even and positive");
     if (cfg->layer < 1 || cfg->num_spk < 1) return fail("dp_gctasnet_create: layer and num_spk must be >= 1");
     if (n_offsets != dp_gctasnet_n_offsets(cfg->layer)) return fail("dp_gctasnet_create: expected %d parameter offsets, got %d", dp_gctasnet_n_offsets(cfg->layer), n_offsets);
-    for (int i = 0; i < n_offsets; ++i)
+    for (int i = 0; i < n_offsets; ++i) {
+        if (!cfg->unfold && i >= P_CAT_W && i <= P_CAT_A && offsets[i] == -1) continue;   // concat_block exists with unfold only
         if (offsets[i] < 0 || offsets[i] >= n_params || (offsets[i] & 3)) return fail("dp_gctasnet_create: offset %d out of range or not 16-byte aligned", i);
+    }
     dp_gctasnet* h = new (std::nothrow) dp_gctasnet;
     if (!h) return fail("dp_gctasnet_create: out of memory");
     h->cfg = *cfg;

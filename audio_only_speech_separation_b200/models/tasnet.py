@@ -10,7 +10,7 @@ the fused Adam step and the single NCCL gradient all-reduce operate on.
 
 Supported on this path: ``module="DPRNN"`` and ``module="DPTNet"``, ``group_size=1``, ``enc_dim=bn_dim=64``,
 ``hidden_dim=128``, ``win=16`` (every DPRNN / DPTNet config of the reference), ``unfold`` True or False; and the GroupComm
-variant ``module="DPRNN", group_size in (8, 16, 32)`` with per-group widths (bn_dim/G, hidden_dim/G) = (4, 8) or (8, 16)
+variant ``module="DPRNN", group_size in (8, 16, 32)`` (``unfold`` True or False) with per-group widths (bn_dim/G, hidden_dim/G) = (4, 8) or (8, 16)
 (``unit_tests.py:79-80`` of the reference), inference only, on its own fp32 engine (csrc/groupcomm.cu).  Anything else raises.
 """
 from __future__ import annotations
@@ -184,8 +184,8 @@ class TasNet(BaseModel):
         if module not in ("DPRNN", "DPTNet"):
             raise NotImplementedError(f"module={module!r}: this build accelerates the dual-path modules 'DPRNN' and 'DPTNet' "
                                       "(see DESIGN.md scope table)")
-        if group_size != 1 and (module != "DPRNN" or unfold):
-            raise NotImplementedError("group_size > 1 (GroupComm) is built for module='DPRNN', unfold=False (DESIGN.md scope table)")
+        if group_size != 1 and module != "DPRNN":
+            raise NotImplementedError("group_size > 1 (GroupComm) is built for module='DPRNN' (DESIGN.md scope table)")
         self.num_spk = num_spk
         self.enc_dim = enc_dim
         self.bn_dim = bn_dim
@@ -273,8 +273,11 @@ class TasNet(BaseModel):
     def _gc_param_table(self):
         """Order of the dp_gctasnet parameter table (include/dualpath_b200.h)."""
         sm = self.seq_model.seq_model
+        cat = sm.concat_block if self.unfold else None
         table = [self.encoder.weight, self.bottleneck[0].weight, self.bottleneck[0].bias, self.bottleneck[1].weight, sm.output.weight,
-                 sm.output.bias, self.mask[0].weight, self.mask[0].bias, self.decoder.weight]
+                 sm.output.bias, self.mask[0].weight, self.mask[0].bias, self.decoder.weight,
+                 cat[0].weight if cat is not None else None, cat[0].bias if cat is not None else None,
+                 cat[1].weight if cat is not None else None]
         for gc in (self.context_enc, self.context_dec):
             for i in range(2):
                 table += self._tac_params(gc.TAC[i]) + self._rnn_params(gc.rnn[i], gc.LN[i])
@@ -376,7 +379,7 @@ class TasNet(BaseModel):
         self._destroy_handle()
         if self.group_size > 1:
             cfg = _lib.GcTasnetConfig(self.enc_dim, self.bn_dim, self.hidden_dim, self.win, self.layer, self.num_spk, self.context_size,
-                                      self.group_size, self.block_size)
+                                      self.group_size, self.block_size, int(self.unfold))
             arr = (C.c_int64 * len(offsets))(*offsets)
             h = C.c_void_p()
             check(lib().dp_gctasnet_create(C.byref(cfg), arr, len(offsets), total, C.byref(h)), "dp_gctasnet_create")

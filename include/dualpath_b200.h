@@ -253,11 +253,12 @@ int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack
  * (utils/dprnn.py:53-88).  Inference (forward) only; fp32 CUDA-core arithmetic (the per-group operators are 4..16 wide). ---- */
 typedef struct dp_gctasnet dp_gctasnet;
 typedef struct {
-    int enc_dim, bn_dim, hidden_dim, win, layer, num_spk, context_size, group_size, block_size; /* gc3_network.py:8-22 */
+    int enc_dim, bn_dim, hidden_dim, win, layer, num_spk, context_size, group_size, block_size, unfold; /* gc3_network.py:8-22 */
 } dp_gctasnet_config;
 /* Parameter table (element offsets into one flat fp32 buffer, each a multiple of 4):
  *   0 encoder.weight  1 bottleneck.0.weight  2 bottleneck.0.bias  3 bottleneck.1.weight  4 seq.output.weight  5 seq.output.bias
- *   6 mask.0.weight  7 mask.0.bias  8 decoder.weight
+ *   6 mask.0.weight  7 mask.0.bias  8 decoder.weight  9 concat_block.0.weight  10 concat_block.0.bias  11 concat_block.1.weight
+ *   (9..11: -1 unless unfold; with unfold the shared row / col RNNs and norms simply repeat their offsets in every layer)
  *   then context_enc and context_dec (GC_RNN), each 2 layers x 23 entries:
  *     TAC: TAC_input.0.weight, .0.bias, .1.weight (PReLU), TAC_mean.0.weight, .0.bias, .1.weight, TAC_output.0.weight, .0.bias, .1.weight,
  *          TAC_norm.weight, TAC_norm.bias

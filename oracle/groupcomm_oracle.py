@@ -50,7 +50,7 @@ def gc_rnn(x: Tensor, sd: StateDict, prefix: str, G: int, layers: int, impl: str
     return out.reshape(B, dim, L)
 
 
-def dprnn_group_stack(x: Tensor, sd: StateDict, prefix: str, G: int, layers: int, impl: str = "aten") -> Tensor:
+def dprnn_group_stack(x: Tensor, sd: StateDict, prefix: str, G: int, layers: int, impl: str = "aten", unfold: bool = False) -> Tensor:
     """``DPRNN.forward`` with ``num_group > 1`` (dprnn.py:53-88; the wrapper's ``num_spk`` is 1).  ``x``: [B, N, d1, d2] -> same."""
     B, N, d1, d2 = x.shape
     n = N // G
@@ -63,6 +63,10 @@ def dprnn_group_stack(x: Tensor, sd: StateDict, prefix: str, G: int, layers: int
         col_in = out.permute(0, 2, 3, 1).reshape(B * G * d1, d2, n)
         col = proj_rnn(col_in, sd, f"{prefix}col_rnn.{i}.", impl, _mm).reshape(B * G, d1, d2, n).permute(0, 3, 1, 2)
         out = out + group_norm1(col, sd[f"{prefix}col_norm.{i}.weight"], sd[f"{prefix}col_norm.{i}.bias"], 1e-8)
+        if unfold:  # depthwise 1x1 conv + PReLU at group width; the RNNs / norms / this block are one shared instance (dprnn.py:26-34,82)
+            cw = sd[f"{prefix}concat_block.0.weight"].view(1, n, 1, 1)
+            cb = sd[f"{prefix}concat_block.0.bias"].view(1, n, 1, 1)
+            out = prelu(out * cw + cb, sd[f"{prefix}concat_block.1.weight"])
     w = sd[f"{prefix}output.weight"].reshape(-1, n)
     y = out.permute(0, 2, 3, 1).reshape(-1, n) @ w.t() + sd[f"{prefix}output.bias"]
     y = y.reshape(B, G, d1, d2, -1).permute(0, 1, 4, 2, 3)     # [B, G, n_out, d1, d2]; num_spk == 1: the transpose(1, 2) is a no-op
@@ -70,7 +74,7 @@ def dprnn_group_stack(x: Tensor, sd: StateDict, prefix: str, G: int, layers: int
 
 
 def tasnet_gc_forward(sd: StateDict, mixture: Tensor, *, enc_dim=64, bn_dim=64, win=16, layer=6, num_spk=2, context_size=24,
-                      group_size=16, block_size=100, lstm_impl="aten", taps: Optional[dict] = None) -> Tensor:
+                      group_size=16, block_size=100, unfold=False, lstm_impl="aten", taps: Optional[dict] = None) -> Tensor:
     """``TasNet.forward`` with ``group_size > 1`` (gc3_network.py:133-184)."""
     was_one_d = mixture.ndim == 1
     x = mixture.unsqueeze(0) if was_one_d else mixture
@@ -94,7 +98,7 @@ def tasnet_gc_forward(sd: StateDict, mixture: Tensor, *, enc_dim=64, bn_dim=64, 
     sq_mean = sq.mean(2).reshape(B, Lc, bn_dim).transpose(1, 2)
     # sequence modelling: DP_Wrapper (groupcomm.py:100-114)
     dblk, drest = split_feature(sq_mean, block_size)
-    dp = dprnn_group_stack(dblk, sd, "seq_model.seq_model.", G, layer, lstm_impl)
+    dp = dprnn_group_stack(dblk, sd, "seq_model.seq_model.", G, layer, lstm_impl, unfold)
     fmap = merge_feature(dp, drest).reshape(B, -1, Lc)
     # context decoding (gc3_network.py:160-166)
     fm = fmap.unsqueeze(2) + blk

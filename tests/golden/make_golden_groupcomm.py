@@ -2,7 +2,7 @@
 ``python -B tests/golden/make_golden_groupcomm.py``).
 
 Runs the unmodified ``look2hear.models.TasNet`` with the configuration of the reference's own ``unit_tests.py:79-80``
-(``module="DPRNN", enc_dim=64, bn_dim=64, group_size=16``) and a ``group_size=8`` variant, asserts that
+(``module="DPRNN", enc_dim=64, bn_dim=64, group_size=16``, and ``unfold=True`` of ``:85-86``) and a ``group_size=8`` variant, asserts that
 ``oracle/groupcomm_oracle.py`` reproduces it (rel-L2 <= 5e-6, explicit LSTM time loop) and stores inputs, outputs and intermediate
 taps of the oracle in ``tests/golden/groupcomm_*.npz`` plus ``groupcomm_manifest.json`` (per-key checksums of the default init).
 """
@@ -28,6 +28,7 @@ CASES = [
     ("g16_b2_t8001", dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16), 2, 8001, "2d"),
     ("g16_b1_t3999_1d", dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16), 1, 3999, "1d"),
     ("g16_b1_t300", dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16), 1, 300, "2d"),
+    ("g16_unfold_b2_t4001", dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16, unfold=True), 2, 4001, "2d"),
     ("g8_l2_b2_t4000", dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=8, layer=2, sample_rate=8000), 2, 4000, "3d"),
 ]
 
@@ -47,7 +48,8 @@ for name, kw, B, T, kind in CASES:
     taps = {}
     with torch.no_grad():
         y = m(xin)
-        yo = GO.tasnet_gc_forward(sd, xin, group_size=kw["group_size"], layer=kw.get("layer", 6), lstm_impl="loop", taps=taps)
+        yo = GO.tasnet_gc_forward(sd, xin, group_size=kw["group_size"], layer=kw.get("layer", 6), unfold=kw.get("unfold", False),
+                                  lstm_impl="loop", taps=taps)
     r = ((yo - y).norm() / y.norm()).item()
     assert r < 5e-6, (name, r)
     np.savez_compressed(os.path.join(HERE, f"groupcomm_{name}.npz"), x=xin.numpy(), y=y.numpy(),

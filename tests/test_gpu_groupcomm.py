@@ -39,7 +39,7 @@ def test_forward_matches_reference_golden(case):
     assert m.last_launches > 0
 
 
-@pytest.mark.parametrize("case,B,T", [("g16_b2_t8001", 3, 2777), ("g8_l2_b2_t4000", 2, 1601), ("g16_b2_t8001", 1, 97)])
+@pytest.mark.parametrize("case,B,T", [("g16_b2_t8001", 3, 2777), ("g16_unfold_b2_t4001", 2, 2500), ("g8_l2_b2_t4000", 2, 1601), ("g16_b2_t8001", 1, 97)])
 def test_forward_matches_oracle_on_other_shapes(case, B, T):
     """Ragged lengths (short last context block, a single DPRNN chunk pair) and batch independence."""
     m, sd, c = _model(case)
@@ -47,7 +47,7 @@ def test_forward_matches_oracle_on_other_shapes(case, B, T):
     x = torch.randn(B, T, generator=g) * 0.1
     with torch.no_grad():
         y = m(x.cuda())
-        ref = GO.tasnet_gc_forward(sd, x, group_size=c["kwargs"]["group_size"], layer=c["kwargs"].get("layer", 6))
+        ref = GO.tasnet_gc_forward(sd, x, group_size=c["kwargs"]["group_size"], layer=c["kwargs"].get("layer", 6), unfold=c["kwargs"].get("unfold", False))
         y0 = m(x[:1].cuda())
     err = rel_l2(y, ref)
     record("groupcomm_fwd_oracle", case=case, B=B, T=T, rel_l2=err)
@@ -100,8 +100,6 @@ def test_training_and_unsupported_configurations_fail_loudly():
         assert m(x).shape == (1, 2, 800)   # no graph requested: the inference engine serves it
     with pytest.raises(NotImplementedError):
         TasNet(module="DPTNet", group_size=16)
-    with pytest.raises(NotImplementedError):
-        TasNet(module="DPRNN", group_size=16, unfold=True)
     with pytest.raises(_lib.DualPathError):
         TasNet(module="DPRNN", group_size=4).cuda().eval()(x)   # per-group widths (16, 32): not built
     with pytest.raises(RuntimeError):
