@@ -31,7 +31,7 @@ class TasnetConfig(C.Structure):
 
 class GcTasnetConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("enc_dim", "bn_dim", "hidden_dim", "win", "layer", "num_spk", "context_size", "group_size",
-                                       "block_size", "unfold")]
+                                       "block_size", "unfold", "module")]
 
 
 class SepformerConfig(C.Structure):
@@ -88,7 +88,7 @@ PROTOTYPES = {
     "dp_tasnet_forward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "dp_tasnet_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "dp_tasnet_last_launches": (_i, [_p]),
-    "dp_gctasnet_n_offsets": (_i, [_i]),
+    "dp_gctasnet_n_offsets": (_i, [_i, _i]),
     "dp_gctasnet_create": (_i, [C.POINTER(GcTasnetConfig), C.POINTER(_i64), _i, _i64, C.POINTER(_p)]),
     "dp_gctasnet_destroy": (None, [_p]),
     "dp_gctasnet_workspace_bytes": (_i64, [_p, _i, _i]),

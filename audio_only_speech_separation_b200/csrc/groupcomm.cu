@@ -1,6 +1,6 @@
-// GroupComm TasNet engine (inference): look2hear/models/gc3_network.py:133-184 with group_size > 1 and module "DPRNN" --
-// context encoder / decoder (GC_RNN, groupcomm.py:10-45), TAC (gc3_basics.py:28-60), the grouped DPRNN stack (dprnn.py:53-88) and
-// the grouped mask head.  The C-ABI is declared in include/dualpath_b200.h (dp_gctasnet_*).
+// GroupComm TasNet engine (inference): look2hear/models/gc3_network.py:133-184 with group_size > 1 and module "DPRNN" or "DPTNet" --
+// context encoder / decoder (GC_RNN, groupcomm.py:10-45), TAC (gc3_basics.py:28-60), the grouped DPRNN stack (dprnn.py:53-88) or the
+// grouped DPTNet stack (dptnet.py:133-162: 4-head attention at width n + BiLSTM feed-forward) and the grouped mask head.  The C-ABI is declared in include/dualpath_b200.h (dp_gctasnet_*).
 //
 // With G groups every per-group operator is tiny (bn_dim / G = 4 or 8 features, hidden_dim / G = 8 or 16 LSTM units, shared by all
 // groups), far below a tensor-core tile: the work is HBM / latency bound fp32 CUDA-core arithmetic, one thread per (position, group)
@@ -34,11 +34,15 @@ struct dp_gctasnet {
 
 namespace {
 
-constexpr int HEAD = 12, TAC_N = 11, RNN_N = 12, GC_LAYER = TAC_N + RNN_N, GC_BLOCK = 2 * GC_LAYER, DP_LAYER = TAC_N + 2 * RNN_N;
+constexpr int HEAD = 12, TAC_N = 11, RNN_N = 12, XF_N = 18, GC_LAYER = TAC_N + RNN_N, GC_BLOCK = 2 * GC_LAYER, DP_LAYER = TAC_N + 2 * RNN_N,
+              DPT_LAYER = TAC_N + 2 * XF_N;
 enum { P_ENC_W, P_BN_G, P_BN_B, P_BN_W, P_OUT_W, P_OUT_B, P_MASK_W, P_MASK_B, P_DEC_W, P_CAT_W, P_CAT_B, P_CAT_A };
 
 struct TacW { const float *w1, *b1, *a1, *w2, *b2, *a2, *w3, *b3, *a3, *gamma, *beta; };
 struct RnnW { const float *wih[2], *whh[2], *bih[2], *bhh[2], *pw, *pb, *gamma, *beta; };
+// transformer layer of the grouped DPTNet (dptnet.py:45-56): `rnn` = linear1 (the BiLSTM feed-forward) with pw / pb = linear2 and
+// gamma / beta = norm2; then the attention projections and norm1
+struct XfW { RnnW rnn; const float *win, *bin, *wo, *bo, *g1, *b1; };
 
 __device__ __forceinline__ float prelu1(float v, float a) { return v >= 0.f ? v : a * v; }
 
@@ -380,6 +384,139 @@ __global__ void __launch_bounds__(256) gc_proj_kernel(const float* __restrict__ 
     stats_add(stats, s, ss, active, pos, pos0, npos, G, g, pps);
 }
 
+// ---- grouped DPTNet, first half of a transformer layer (dptnet.py:75-77): 4-head self-attention at width n (head width n/4 = 1 or 2),
+// out-projection, residual and LayerNorm(n).  One CTA per `spb` sequences; x, q, k, v, o of a sequence live in shared memory.
+template <int NG>
+__global__ void __launch_bounds__(128) gc_dpt_attn_kernel(const float* __restrict__ A, float* __restrict__ Z, XfW w, long long nouter, int G,
+                                                          int len, int spb, int qdiv, long long s_hi, long long s_lo, long long s_t) {
+    constexpr int HD = NG / 4;
+    extern __shared__ __align__(16) float sm[];
+    const int items = spb * len, C = G * NG;
+    float *xs = sm, *qs = xs + items * NG, *ks = qs + items * NG, *vs = ks + items * NG, *os = vs + items * NG;
+    const long long nseq = nouter * G, q0 = (long long)blockIdx.x * spb;
+    const float scale = HD == 1 ? 1.f : 0.70710678118654752f;   // head_dim ** -0.5
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const long long q = q0 + it / len;
+        if (q >= nseq) continue;
+        const int i = it % len, g = (int)(q % G);
+        const long long o = q / G, pos = (o / qdiv) * s_hi + (o % qdiv) * s_lo + (long long)i * s_t;
+        float x[NG];
+#pragma unroll
+        for (int k = 0; k < NG; k += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(A + pos * C + g * NG + k);
+            x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+        }
+#pragma unroll
+        for (int r = 0; r < 3 * NG; ++r) {
+            float acc = __ldg(w.bin + r);
+#pragma unroll
+            for (int k = 0; k < NG; ++k) acc = fmaf(__ldg(w.win + r * NG + k), x[k], acc);
+            if (r < NG) qs[it * NG + r] = acc * scale;
+            else if (r < 2 * NG) ks[it * NG + r - NG] = acc;
+            else vs[it * NG + r - 2 * NG] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < NG; ++k) xs[it * NG + k] = x[k];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < items * 4; idx += blockDim.x) {
+        const int it = idx >> 2, hh = idx & 3, sl = it / len;
+        if (q0 + sl >= nseq) continue;
+        const float* kb = ks + sl * len * NG + hh * HD;
+        const float* vb = vs + sl * len * NG + hh * HD;
+        float qv[HD], acc[HD], m = -INFINITY, den = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) { qv[d] = qs[it * NG + hh * HD + d] * 1.4426950408889634f; acc[d] = 0.f; }
+        for (int j = 0; j < len; ++j) {
+            float sc = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) sc = fmaf(qv[d], kb[j * NG + d], sc);
+            m = fmaxf(m, sc);
+        }
+        for (int j = 0; j < len; ++j) {
+            float sc = -m;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) sc = fmaf(qv[d], kb[j * NG + d], sc);
+            const float e = ex2_approx(sc);
+            den += e;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) acc[d] = fmaf(e, vb[j * NG + d], acc[d]);
+        }
+        const float inv = 1.f / den;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) os[it * NG + hh * HD + d] = acc[d] * inv;
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const long long q = q0 + it / len;
+        if (q >= nseq) continue;
+        const int i = it % len, g = (int)(q % G);
+        const long long o = q / G, pos = (o / qdiv) * s_hi + (o % qdiv) * s_lo + (long long)i * s_t;
+        float z[NG], mean = 0.f;
+#pragma unroll
+        for (int r = 0; r < NG; ++r) {
+            float acc = __ldg(w.bo + r);
+#pragma unroll
+            for (int k = 0; k < NG; ++k) acc = fmaf(__ldg(w.wo + r * NG + k), os[it * NG + k], acc);
+            z[r] = xs[it * NG + r] + acc;
+            mean += z[r];
+        }
+        mean *= 1.f / NG;
+        float var = 0.f;
+#pragma unroll
+        for (int r = 0; r < NG; ++r) var = fmaf(z[r] - mean, z[r] - mean, var);
+        const float rstd = 1.f / sqrtf(var * (1.f / NG) + 1e-5f);
+#pragma unroll
+        for (int r = 0; r < NG; r += 4)
+            *reinterpret_cast<float4*>(Z + pos * C + g * NG + r) =
+                make_float4((z[r] - mean) * rstd * __ldg(w.g1 + r) + __ldg(w.b1 + r), (z[r + 1] - mean) * rstd * __ldg(w.g1 + r + 1) + __ldg(w.b1 + r + 1),
+                            (z[r + 2] - mean) * rstd * __ldg(w.g1 + r + 2) + __ldg(w.b1 + r + 2), (z[r + 3] - mean) * rstd * __ldg(w.g1 + r + 3) + __ldg(w.b1 + r + 3));
+    }
+}
+
+// ---- second half (dptnet.py:79-82) after the BiLSTM: ReLU, Linear(4n -> n), residual, LayerNorm(n), then the residual of the dual-path
+// block (dptnet.py:150,157) and, with unfold after the column path, the shared concat_block
+template <int NG, int HG>
+__global__ void __launch_bounds__(256) gc_dpt_out_kernel(const float* __restrict__ Hh, const float* __restrict__ Z, float* A, XfW w, long long total,
+                                                         const float* __restrict__ cat_w, const float* __restrict__ cat_b,
+                                                         const float* __restrict__ cat_a) {
+    __shared__ float s_w[NG * 2 * HG], s_b[NG];
+    for (int i = threadIdx.x; i < NG * 2 * HG; i += blockDim.x) s_w[i] = w.rnn.pw[i];
+    if (threadIdx.x < NG) s_b[threadIdx.x] = w.rnn.pb[threadIdx.x];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float y[NG];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) y[j] = s_b[j];
+#pragma unroll
+    for (int k = 0; k < 2 * HG; k += 4) {
+        float4 v = *reinterpret_cast<const float4*>(Hh + i * 2 * HG + k);
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+            y[j] = fmaf(s_w[j * 2 * HG + k], v.x, y[j]);
+            y[j] = fmaf(s_w[j * 2 * HG + k + 1], v.y, y[j]);
+            y[j] = fmaf(s_w[j * 2 * HG + k + 2], v.z, y[j]);
+            y[j] = fmaf(s_w[j * 2 * HG + k + 3], v.w, y[j]);
+        }
+    }
+    float mean = 0.f;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) { y[j] += Z[i * NG + j]; mean += y[j]; }
+    mean *= 1.f / NG;
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) var = fmaf(y[j] - mean, y[j] - mean, var);
+    const float rstd = 1.f / sqrtf(var * (1.f / NG) + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+        float o = A[i * NG + j] + ((y[j] - mean) * rstd * __ldg(w.rnn.gamma + j) + __ldg(w.rnn.beta + j));
+        if (cat_w) o = prelu1(fmaf(o, __ldg(cat_w + j), __ldg(cat_b + j)), __ldg(cat_a));
+        A[i * NG + j] = o;
+    }
+}
+
 // ---- per-group Linear(n -> nout) shared by the groups: the DPRNN output conv (dprnn.py:85) and the mask conv + ReLU -----------------
 template <int NG>
 __global__ void __launch_bounds__(256) gc_group_linear_kernel(const float* __restrict__ X, float* __restrict__ Y, const float* __restrict__ W,
@@ -559,6 +696,14 @@ RnnW rnn_w(const dp_gctasnet* h, const float* p, int base) {
     return w;
 }
 
+XfW xf_w(const dp_gctasnet* h, const float* p, int base) {
+    XfW w;
+    w.rnn = rnn_w(h, p, base);   // linear1 (8), linear2.weight / bias, norm2.weight / bias
+    w.win = p + h->off[base + 12]; w.bin = p + h->off[base + 13]; w.wo = p + h->off[base + 14]; w.bo = p + h->off[base + 15];
+    w.g1 = p + h->off[base + 16]; w.b1 = p + h->off[base + 17];
+    return w;
+}
+
 struct SeqWalk { long long nouter; int len, qdiv; long long s_hi, s_lo, s_t; };
 
 template <int NG, int HG>
@@ -588,6 +733,22 @@ struct Ops {
         gc_ctx_rnn_kernel<NG, HG><<<blocks_for(nunits, UPB), 128, smem, s>>>(A, w, nunits, G, ctx, 1e-5f);
         h->launches += 1;
         return cudaGetLastError();
+    }
+    // one transformer layer of the grouped DPTNet along the walk `q`, added onto A (Z = scratch for the first half's output)
+    static int xfmr(dp_gctasnet* h, float* A, float* Z, float* Hh, const XfW& w, long long npos, int G, const SeqWalk& q, cudaStream_t s,
+                    const float* cat_w, const float* cat_b, const float* cat_a) {
+        int spb = 32 / q.len;
+        if (spb < 1) spb = 1;
+        const size_t smem = (size_t)spb * q.len * NG * 5 * sizeof(float);
+        if (smem > 200 * 1024) return fail("dp_gctasnet_forward: sequence of %d frames does not fit the attention kernel's shared memory", q.len);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gc_dpt_attn_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gc_dpt_attn_kernel<NG><<<blocks_for(q.nouter * G, spb), 128, smem, s>>>(A, Z, w, q.nouter, G, q.len, spb, q.qdiv, q.s_hi, q.s_lo, q.s_t);
+        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
+        gc_lstm_kernel<NG, HG><<<grid, 128, 0, s>>>(Z, Hh, w.rnn, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t);
+        gc_dpt_out_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Z, A, w, npos * G, cat_w, cat_b, cat_a);
+        h->launches += 3;
+        CK(cudaGetLastError());
+        return 0;
     }
     static cudaError_t group_linear(dp_gctasnet* h, const float* X, float* Y, const float* W, const float* b, long long total, int nout, int relu,
                                     cudaStream_t s) {
@@ -645,7 +806,16 @@ struct Ops {
         const SeqWalk row{(long long)g.B * g.S2, g.K, 1, (long long)g.K, 0, 1};
         const SeqWalk col{(long long)g.B * g.K, g.S2, g.K, (long long)g.S2 * g.K, 1, (long long)g.K};
         const size_t dslot = (size_t)g.B * g.G * 2;
-        for (int i = 0; i < c.layer; ++i) {
+        const float *cw = c.unfold ? p + h->off[P_CAT_W] : nullptr, *cb = c.unfold ? p + h->off[P_CAT_B] : nullptr;
+        const float* ca = c.unfold ? p + h->off[P_CAT_A] : nullptr;
+        for (int i = 0; i < c.layer && c.module == DP_MODULE_DPTNET; ++i) {   // dptnet.py:138-157
+            const int base = HEAD + 2 * GC_BLOCK + i * DPT_LAYER;
+            CK(tac(h, A, Y, A, st, tac_w(h, p, base), g.PD, g.G, pps, s));
+            st += dslot;
+            if (xfmr(h, A, Y, Hh, xf_w(h, p, base + TAC_N), g.PD, g.G, row, s, nullptr, nullptr, nullptr)) return 1;
+            if (xfmr(h, A, Y, Hh, xf_w(h, p, base + TAC_N + XF_N), g.PD, g.G, col, s, cw, cb, ca)) return 1;
+        }
+        for (int i = 0; i < c.layer && c.module != DP_MODULE_DPTNET; ++i) {
             const int base = HEAD + 2 * GC_BLOCK + i * DP_LAYER;
             CK(tac(h, A, Y, A, st, tac_w(h, p, base), g.PD, g.G, pps, s));
             st += dslot;
@@ -680,7 +850,7 @@ struct Ops {
 
 extern "C" {
 
-int dp_gctasnet_n_offsets(int layer) { return HEAD + 2 * GC_BLOCK + layer * DP_LAYER; }
+int dp_gctasnet_n_offsets(int layer, int module) { return HEAD + 2 * GC_BLOCK + layer * (module == DP_MODULE_DPTNET ? DPT_LAYER : DP_LAYER); }
 
 int dp_gctasnet_create(const dp_gctasnet_config* cfg, const int64_t* offsets, int n_offsets, int64_t n_params, dp_gctasnet** out) {
     if (!cfg || !offsets || !out) return fail("dp_gctasnet_create: null argument");
@@ -696,7 +866,9 @@ int dp_gctasnet_create(const dp_gctasnet_config* cfg, const int64_t* offsets, in
     if (cfg->context_size <= 0 || (cfg->context_size & 1) || cfg->block_size <= 0 || (cfg->block_size & 1))
         return fail("dp_gctasnet_create: context_size and block_size must be even and positive");
     if (cfg->layer < 1 || cfg->num_spk < 1) return fail("dp_gctasnet_create: layer and num_spk must be >= 1");
-    if (n_offsets != dp_gctasnet_n_offsets(cfg->layer)) return fail("dp_gctasnet_create: expected %d parameter offsets, got %d", dp_gctasnet_n_offsets(cfg->layer), n_offsets);
+    if (cfg->module != DP_MODULE_DPRNN && cfg->module != DP_MODULE_DPTNET) return fail("dp_gctasnet_create: module must be DP_MODULE_DPRNN or DP_MODULE_DPTNET");
+    if (n_offsets != dp_gctasnet_n_offsets(cfg->layer, cfg->module))
+        return fail("dp_gctasnet_create: expected %d parameter offsets, got %d", dp_gctasnet_n_offsets(cfg->layer, cfg->module), n_offsets);
     for (int i = 0; i < n_offsets; ++i) {
         if (!cfg->unfold && i >= P_CAT_W && i <= P_CAT_A && offsets[i] == -1) continue;   // concat_block exists with unfold only
         if (offsets[i] < 0 || offsets[i] >= n_params || (offsets[i] & 3)) return fail("dp_gctasnet_create: offset %d out of range or not 16-byte aligned", i);

@@ -10,8 +10,8 @@ the fused Adam step and the single NCCL gradient all-reduce operate on.
 
 Supported on this path: ``module="DPRNN"`` and ``module="DPTNet"``, ``group_size=1``, ``enc_dim=bn_dim=64``,
 ``hidden_dim=128``, ``win=16`` (every DPRNN / DPTNet config of the reference), ``unfold`` True or False; and the GroupComm
-variant ``module="DPRNN", group_size in (8, 16, 32)`` (``unfold`` True or False) with per-group widths (bn_dim/G, hidden_dim/G) = (4, 8) or (8, 16)
-(``unit_tests.py:79-80`` of the reference), inference only, on its own fp32 engine (csrc/groupcomm.cu).  Anything else raises.
+variant ``group_size in (8, 16, 32)`` (both modules, ``unfold`` True or False) with per-group widths (bn_dim/G, hidden_dim/G) = (4, 8) or (8, 16)
+(``unit_tests.py:69-86`` of the reference), inference only, on its own fp32 engine (csrc/groupcomm.cu).  Anything else raises.
 """
 from __future__ import annotations
 
@@ -115,8 +115,12 @@ class _SingleTransformer(nn.Module):
 class _DPTNet(nn.Module):
     """Parameter container with the keys of ``DPTNet`` (dptnet.py:99-131), ``num_group == 1``."""
 
-    def __init__(self, input_size, hidden_size, output_size, num_layers, unfold):
+    def __init__(self, input_size, hidden_size, output_size, num_layers, unfold, num_group=1):
         super().__init__()
+        if num_group > 1:   # dptnet.py:111-131: TAC per layer, everything else at width input_size // num_group
+            self.TAC = nn.ModuleList([])
+            tac_in, tac_hid = input_size // num_group, hidden_size * 3 // num_group
+            input_size, output_size = input_size // num_group, output_size // num_group
         self.row_xfmr = nn.ModuleList([])
         self.col_xfmr = nn.ModuleList([])
         if unfold:
@@ -124,6 +128,8 @@ class _DPTNet(nn.Module):
             col_xfmr = _SingleTransformer(input_size)
             self.concat_block = nn.Sequential(nn.Conv2d(input_size, input_size, 1, 1, groups=input_size), nn.PReLU())
         for _ in range(num_layers):
+            if num_group > 1:
+                self.TAC.append(_TAC(tac_in, tac_hid))
             self.row_xfmr.append(row_xfmr if unfold else _SingleTransformer(input_size))
             self.col_xfmr.append(col_xfmr if unfold else _SingleTransformer(input_size))
         self.output = nn.Conv2d(input_size, output_size, 1)
@@ -134,11 +140,8 @@ class _DPWrapper(nn.Module):
 
     def __init__(self, input_dim, hidden_dim, output_dim, layer, unfold, module="DPRNN", num_group=1):
         super().__init__()
-        if num_group > 1:
-            self.seq_model = _DPRNN(input_dim, hidden_dim, output_dim, layer, unfold, num_group)
-        else:
-            cls = _DPRNN if module == "DPRNN" else _DPTNet
-            self.seq_model = cls(input_dim, hidden_dim, output_dim, layer, unfold)
+        cls = _DPRNN if module == "DPRNN" else _DPTNet
+        self.seq_model = cls(input_dim, hidden_dim, output_dim, layer, unfold, num_group)
 
 
 class _TasNetFunction(torch.autograd.Function):
@@ -184,8 +187,6 @@ class TasNet(BaseModel):
         if module not in ("DPRNN", "DPTNet"):
             raise NotImplementedError(f"module={module!r}: this build accelerates the dual-path modules 'DPRNN' and 'DPTNet' "
                                       "(see DESIGN.md scope table)")
-        if group_size != 1 and module != "DPRNN":
-            raise NotImplementedError("group_size > 1 (GroupComm) is built for module='DPRNN' (DESIGN.md scope table)")
         self.num_spk = num_spk
         self.enc_dim = enc_dim
         self.bn_dim = bn_dim
@@ -282,7 +283,16 @@ class TasNet(BaseModel):
             for i in range(2):
                 table += self._tac_params(gc.TAC[i]) + self._rnn_params(gc.rnn[i], gc.LN[i])
         for i in range(self.layer):
-            table += self._tac_params(sm.TAC[i]) + self._rnn_params(sm.row_rnn[i], sm.row_norm[i]) + self._rnn_params(sm.col_rnn[i], sm.col_norm[i])
+            table += self._tac_params(sm.TAC[i])
+            if self.model_name == "DPTNet":
+                for x in (sm.row_xfmr[i].transformer, sm.col_xfmr[i].transformer):
+                    r = x.linear1
+                    table += [r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, r.weight_ih_l0_reverse, r.weight_hh_l0_reverse,
+                              r.bias_ih_l0_reverse, r.bias_hh_l0_reverse, x.linear2.weight, x.linear2.bias, x.norm2.weight, x.norm2.bias,
+                              x.self_attn.in_proj_weight, x.self_attn.in_proj_bias, x.self_attn.out_proj.weight, x.self_attn.out_proj.bias,
+                              x.norm1.weight, x.norm1.bias]
+            else:
+                table += self._rnn_params(sm.row_rnn[i], sm.row_norm[i]) + self._rnn_params(sm.col_rnn[i], sm.col_norm[i])
         return table
 
     def _gc_forward(self, xin):
@@ -379,7 +389,8 @@ class TasNet(BaseModel):
         self._destroy_handle()
         if self.group_size > 1:
             cfg = _lib.GcTasnetConfig(self.enc_dim, self.bn_dim, self.hidden_dim, self.win, self.layer, self.num_spk, self.context_size,
-                                      self.group_size, self.block_size, int(self.unfold))
+                                      self.group_size, self.block_size, int(self.unfold),
+                                      _lib.MODULE_DPTNET if self.model_name == "DPTNet" else _lib.MODULE_DPRNN)
             arr = (C.c_int64 * len(offsets))(*offsets)
             h = C.c_void_p()
             check(lib().dp_gctasnet_create(C.byref(cfg), arr, len(offsets), total, C.byref(h)), "dp_gctasnet_create")

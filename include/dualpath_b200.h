@@ -248,12 +248,13 @@ int dp_sepformer_forward_train(dp_sepformer* h, const float* params, const void*
 int dp_sepformer_backward(dp_sepformer* h, const float* params, const void* pack, const float* d_est, float* grads, void* workspace,
                           int B, int T, int precision, void* stream);
 
-/* ---- whole-model engine: TasNet.forward with group_size > 1 (GroupComm), module "DPRNN" -- look2hear/models/gc3_network.py:133-184
+/* ---- whole-model engine: TasNet.forward with group_size > 1 (GroupComm), module "DPRNN" or "DPTNet" -- look2hear/models/gc3_network.py:133-184
  * with the context encoder / decoder (GC_RNN, utils/groupcomm.py:10-45), TAC (utils/gc3_basics.py:28-60) and the grouped DPRNN stack
- * (utils/dprnn.py:53-88).  Inference (forward) only; fp32 CUDA-core arithmetic (the per-group operators are 4..16 wide). ---- */
+ * (utils/dprnn.py:53-88) or DPTNet stack (utils/dptnet.py:133-162).  Inference (forward) only; fp32 CUDA-core arithmetic (the per-group operators are 4..16 wide). ---- */
 typedef struct dp_gctasnet dp_gctasnet;
 typedef struct {
     int enc_dim, bn_dim, hidden_dim, win, layer, num_spk, context_size, group_size, block_size, unfold; /* gc3_network.py:8-22 */
+    int module; /* DP_MODULE_DPRNN or DP_MODULE_DPTNET */
 } dp_gctasnet_config;
 /* Parameter table (element offsets into one flat fp32 buffer, each a multiple of 4):
  *   0 encoder.weight  1 bottleneck.0.weight  2 bottleneck.0.bias  3 bottleneck.1.weight  4 seq.output.weight  5 seq.output.bias
@@ -263,8 +264,10 @@ typedef struct {
  *     TAC: TAC_input.0.weight, .0.bias, .1.weight (PReLU), TAC_mean.0.weight, .0.bias, .1.weight, TAC_output.0.weight, .0.bias, .1.weight,
  *          TAC_norm.weight, TAC_norm.bias
  *     rnn: weight_ih, weight_hh, bias_ih, bias_hh, the four _reverse, proj.weight, proj.bias, then LN.weight, LN.bias
- *   then per DPRNN layer 35 entries: TAC (11), row_rnn + row_norm (12, as above), col_rnn + col_norm (12). */
-int dp_gctasnet_n_offsets(int layer);
+ *   then per DPRNN layer 35 entries: TAC (11), row_rnn + row_norm (12, as above), col_rnn + col_norm (12);
+ *   DP_MODULE_DPTNET: per layer 47 entries: TAC (11), then row_xfmr and col_xfmr, 18 each in the order of DP_TASNET_PATH_PARAMS_DPTNET
+ *   above (linear1 BiLSTM 8, linear2.weight/.bias, norm2, self_attn.in_proj_weight/_bias, out_proj.weight/.bias, norm1). */
+int dp_gctasnet_n_offsets(int layer, int module);
 int dp_gctasnet_create(const dp_gctasnet_config* cfg, const int64_t* offsets, int n_offsets, int64_t n_params, dp_gctasnet** out);
 void dp_gctasnet_destroy(dp_gctasnet* h);
 int64_t dp_gctasnet_workspace_bytes(const dp_gctasnet* h, int B, int T);

@@ -1,4 +1,4 @@
-"""CPU oracle for the GroupComm path of ``TasNet`` (``group_size > 1``, ``module="DPRNN"``).
+"""CPU oracle for the GroupComm path of ``TasNet`` (``group_size > 1``, ``module="DPRNN"`` or ``"DPTNet"``).
 
 TEST INFRASTRUCTURE ONLY (same rule as ``oracle/dualpath_oracle.py``: only ``tests/``, ``smoke()`` and the bench's CPU legs may import
 it, as the checker).  Functional restatement on plain ``torch`` CPU tensors, citing the reference lines each function follows:
@@ -6,6 +6,7 @@ it, as the checker).  Functional restatement on plain ``torch`` CPU tensors, cit
 * ``TAC`` (transform - average - concatenate)     look2hear/models/utils/gc3_basics.py:28-60
 * ``GC_RNN`` (TAC + ProjRNN + GroupNorm per group) look2hear/models/utils/groupcomm.py:10-45
 * grouped ``DPRNN`` stack                          look2hear/models/utils/dprnn.py:53-88
+* grouped ``DPTNet`` stack                         look2hear/models/utils/dptnet.py:133-162
 * context encoder / decoder, grouped mask          look2hear/models/gc3_network.py:59-61,145-175
 
 Pinned by ``tests/golden/make_golden_groupcomm.py`` against the reference itself (``TasNet(..., group_size=16)``, the configuration
@@ -18,7 +19,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn.functional as F
 
-from .dualpath_oracle import group_norm1, merge_feature, prelu, proj_rnn, split_feature, wave_rest, _mm
+from .dualpath_oracle import dptnet_layer, group_norm1, merge_feature, prelu, proj_rnn, split_feature, wave_rest, _mm
 
 Tensor = torch.Tensor
 StateDict = Dict[str, Tensor]
@@ -73,8 +74,31 @@ def dprnn_group_stack(x: Tensor, sd: StateDict, prefix: str, G: int, layers: int
     return y.reshape(B, -1, d1, d2)
 
 
+def dptnet_group_stack(x: Tensor, sd: StateDict, prefix: str, G: int, layers: int, impl: str = "aten", unfold: bool = False) -> Tensor:
+    """``DPTNet.forward`` with ``num_group > 1`` (dptnet.py:133-162): TAC, then a transformer layer (4 heads at width n, a BiLSTM as the
+    feed-forward) along the chunk and across the chunks of every group.  ``x``: [B, N, d1, d2] -> same."""
+    B, N, d1, d2 = x.shape
+    n = N // G
+    out = x.reshape(B, G, n, d1, d2)
+    for i in range(layers):
+        out = tac(out.reshape(B, G, n, d1 * d2), sd, f"{prefix}TAC.{i}.").reshape(B * G, n, d1, d2)
+        row_in = out.permute(0, 3, 2, 1).reshape(B * G * d2, d1, n)
+        row = dptnet_layer(row_in.permute(1, 0, 2), sd, f"{prefix}row_xfmr.{i}.transformer.", impl, _mm).permute(1, 0, 2)
+        out = out + row.reshape(B * G, d2, d1, n).permute(0, 3, 2, 1)
+        col_in = out.permute(0, 2, 3, 1).reshape(B * G * d1, d2, n)
+        col = dptnet_layer(col_in.permute(1, 0, 2), sd, f"{prefix}col_xfmr.{i}.transformer.", impl, _mm).permute(1, 0, 2)
+        out = out + col.reshape(B * G, d1, d2, n).permute(0, 3, 1, 2)
+        if unfold:
+            cw = sd[f"{prefix}concat_block.0.weight"].view(1, n, 1, 1)
+            cb = sd[f"{prefix}concat_block.0.bias"].view(1, n, 1, 1)
+            out = prelu(out * cw + cb, sd[f"{prefix}concat_block.1.weight"])
+    w = sd[f"{prefix}output.weight"].reshape(-1, n)
+    y = out.permute(0, 2, 3, 1).reshape(-1, n) @ w.t() + sd[f"{prefix}output.bias"]
+    return y.reshape(B, G, d1, d2, -1).permute(0, 1, 4, 2, 3).reshape(B, -1, d1, d2)
+
+
 def tasnet_gc_forward(sd: StateDict, mixture: Tensor, *, enc_dim=64, bn_dim=64, win=16, layer=6, num_spk=2, context_size=24,
-                      group_size=16, block_size=100, unfold=False, lstm_impl="aten", taps: Optional[dict] = None) -> Tensor:
+                      group_size=16, block_size=100, unfold=False, module="DPRNN", lstm_impl="aten", taps: Optional[dict] = None) -> Tensor:
     """``TasNet.forward`` with ``group_size > 1`` (gc3_network.py:133-184)."""
     was_one_d = mixture.ndim == 1
     x = mixture.unsqueeze(0) if was_one_d else mixture
@@ -98,7 +122,8 @@ def tasnet_gc_forward(sd: StateDict, mixture: Tensor, *, enc_dim=64, bn_dim=64, 
     sq_mean = sq.mean(2).reshape(B, Lc, bn_dim).transpose(1, 2)
     # sequence modelling: DP_Wrapper (groupcomm.py:100-114)
     dblk, drest = split_feature(sq_mean, block_size)
-    dp = dprnn_group_stack(dblk, sd, "seq_model.seq_model.", G, layer, lstm_impl, unfold)
+    stack = dprnn_group_stack if module == "DPRNN" else dptnet_group_stack
+    dp = stack(dblk, sd, "seq_model.seq_model.", G, layer, lstm_impl, unfold)
     fmap = merge_feature(dp, drest).reshape(B, -1, Lc)
     # context decoding (gc3_network.py:160-166)
     fm = fmap.unsqueeze(2) + blk

@@ -29,6 +29,9 @@ CASES = [
     ("g16_b1_t3999_1d", dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16), 1, 3999, "1d"),
     ("g16_b1_t300", dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16), 1, 300, "2d"),
     ("g16_unfold_b2_t4001", dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16, unfold=True), 2, 4001, "2d"),
+    ("dpt_g16_b2_t4001", dict(module="DPTNet", enc_dim=64, bn_dim=64, group_size=16), 2, 4001, "2d"),
+    ("dpt_g16_unfold_b1_t2000", dict(module="DPTNet", enc_dim=64, bn_dim=64, group_size=16, unfold=True), 1, 2000, "2d"),
+    ("dpt_g8_l2_b1_t3000", dict(module="DPTNet", enc_dim=64, bn_dim=64, group_size=8, layer=2), 1, 3000, "2d"),
     ("g8_l2_b2_t4000", dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=8, layer=2, sample_rate=8000), 2, 4000, "3d"),
 ]
 
@@ -49,7 +52,7 @@ for name, kw, B, T, kind in CASES:
     with torch.no_grad():
         y = m(xin)
         yo = GO.tasnet_gc_forward(sd, xin, group_size=kw["group_size"], layer=kw.get("layer", 6), unfold=kw.get("unfold", False),
-                                  lstm_impl="loop", taps=taps)
+                                  module=kw["module"], lstm_impl="loop", taps=taps)
     r = ((yo - y).norm() / y.norm()).item()
     assert r < 5e-6, (name, r)
     np.savez_compressed(os.path.join(HERE, f"groupcomm_{name}.npz"), x=xin.numpy(), y=y.numpy(),

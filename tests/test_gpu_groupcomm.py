@@ -1,4 +1,4 @@
-"""GPU parity tests of the GroupComm path: drop-in ``TasNet(module="DPRNN", group_size > 1)`` forward (csrc/groupcomm.cu) against the
+"""GPU parity tests of the GroupComm path: drop-in ``TasNet(module="DPRNN" | "DPTNet", group_size > 1)`` forward (csrc/groupcomm.cu) against the
 reference's golden outputs and the CPU oracle (oracle/groupcomm_oracle.py)."""
 import json
 import os
@@ -39,7 +39,8 @@ def test_forward_matches_reference_golden(case):
     assert m.last_launches > 0
 
 
-@pytest.mark.parametrize("case,B,T", [("g16_b2_t8001", 3, 2777), ("g16_unfold_b2_t4001", 2, 2500), ("g8_l2_b2_t4000", 2, 1601), ("g16_b2_t8001", 1, 97)])
+@pytest.mark.parametrize("case,B,T", [("g16_b2_t8001", 3, 2777), ("g16_unfold_b2_t4001", 2, 2500), ("dpt_g16_b2_t4001", 2, 2777),
+                                      ("dpt_g8_l2_b1_t3000", 2, 30000), ("g8_l2_b2_t4000", 2, 1601), ("g16_b2_t8001", 1, 97)])
 def test_forward_matches_oracle_on_other_shapes(case, B, T):
     """Ragged lengths (short last context block, a single DPRNN chunk pair) and batch independence."""
     m, sd, c = _model(case)
@@ -47,7 +48,7 @@ def test_forward_matches_oracle_on_other_shapes(case, B, T):
     x = torch.randn(B, T, generator=g) * 0.1
     with torch.no_grad():
         y = m(x.cuda())
-        ref = GO.tasnet_gc_forward(sd, x, group_size=c["kwargs"]["group_size"], layer=c["kwargs"].get("layer", 6), unfold=c["kwargs"].get("unfold", False))
+        ref = GO.tasnet_gc_forward(sd, x, group_size=c["kwargs"]["group_size"], layer=c["kwargs"].get("layer", 6), unfold=c["kwargs"].get("unfold", False), module=c["kwargs"]["module"])
         y0 = m(x[:1].cuda())
     err = rel_l2(y, ref)
     record("groupcomm_fwd_oracle", case=case, B=B, T=T, rel_l2=err)
@@ -98,8 +99,6 @@ def test_training_and_unsupported_configurations_fail_loudly():
         m(x)
     with torch.no_grad():
         assert m(x).shape == (1, 2, 800)   # no graph requested: the inference engine serves it
-    with pytest.raises(NotImplementedError):
-        TasNet(module="DPTNet", group_size=16)
     with pytest.raises(_lib.DualPathError):
         TasNet(module="DPRNN", group_size=4).cuda().eval()(x)   # per-group widths (16, 32): not built
     with pytest.raises(RuntimeError):

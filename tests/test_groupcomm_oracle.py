@@ -20,7 +20,8 @@ def _model(case):
     return TasNet(**c["kwargs"]), c
 
 
-@pytest.mark.parametrize("case", ["g16_b1_t300", "g16_b1_t3999_1d", "g16_unfold_b2_t4001", "g8_l2_b2_t4000"])
+@pytest.mark.parametrize("case", ["g16_b1_t300", "g16_b1_t3999_1d", "g16_unfold_b2_t4001", "dpt_g16_unfold_b1_t2000", "dpt_g8_l2_b1_t3000",
+                                  "g8_l2_b2_t4000"])
 def test_oracle_matches_reference_golden(case):
     m, c = _model(case)
     sd = {k: v.detach() for k, v in m.state_dict().items()}
@@ -28,13 +29,13 @@ def test_oracle_matches_reference_golden(case):
     taps = {}
     with torch.no_grad():
         y = GO.tasnet_gc_forward(sd, torch.from_numpy(z["x"]), group_size=c["kwargs"]["group_size"], layer=c["kwargs"].get("layer", 6),
-                                 unfold=c["kwargs"].get("unfold", False), lstm_impl="loop", taps=taps)
+                                 unfold=c["kwargs"].get("unfold", False), module=c["kwargs"]["module"], lstm_impl="loop", taps=taps)
     assert rel_l2(y, torch.from_numpy(z["y"])) < 5e-6
     assert rel_l2(taps["squeeze_mean"], torch.from_numpy(z["squeeze_mean"])) < 5e-6
     assert rel_l2(taps["feature_map"], torch.from_numpy(z["feature_map"])) < 5e-6
 
 
-@pytest.mark.parametrize("case", ["g16_b2_t8001", "g16_unfold_b2_t4001", "g8_l2_b2_t4000"])
+@pytest.mark.parametrize("case", ["g16_b2_t8001", "g16_unfold_b2_t4001", "dpt_g16_b2_t4001", "dpt_g16_unfold_b1_t2000", "g8_l2_b2_t4000"])
 def test_state_dict_is_the_reference_one(case):
     m, c = _model(case)
     sd, ref = m.state_dict(), GC_MANIFEST["state_dicts"][case]
@@ -46,13 +47,12 @@ def test_state_dict_is_the_reference_one(case):
     assert sum(p.numel() for p in m.parameters()) == c["n_params"]
     from audio_only_speech_separation_b200 import _lib
 
-    assert len(m._gc_param_table()) == 12 + 4 * 23 + 35 * c["kwargs"].get("layer", 6)
+    per_layer = 47 if c["kwargs"]["module"] == "DPTNet" else 35
+    assert len(m._gc_param_table()) == 12 + 4 * 23 + per_layer * c["kwargs"].get("layer", 6)
 
 
 def test_unsupported_variants_raise():
     from audio_only_speech_separation_b200.models import TasNet
 
-    with pytest.raises(NotImplementedError):
-        TasNet(module="DPTNet", group_size=16)
     with pytest.raises(RuntimeError):   # CUDA-only: CPU tensors are refused, there is no CPU path
         TasNet(module="DPRNN", group_size=16).eval()(torch.zeros(1, 800))

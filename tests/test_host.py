@@ -94,7 +94,7 @@ def test_unsupported_configs_fail_loudly():
     with pytest.raises(NotImplementedError):
         TasNet(module="TCN")
     with pytest.raises(NotImplementedError):
-        TasNet(module="DPTNet", group_size=16)   # GroupComm is built for module="DPRNN" (tests/test_groupcomm_oracle.py)
+        TasNet(module="GC_TCN", group_size=16)
     with pytest.raises(AssertionError):
         TasNet(module="bogus")
 
