@@ -48,12 +48,13 @@ __device__ __forceinline__ float prelu1(float v, float a) { return v >= 0.f ? v 
 
 // (sum, sum of squares) of one thread's outputs into the statistics slot of its (sample, group).  Lanes of a warp that hold the same
 // group of the same sample are combined first (positions of a warp are consecutive, so this is the common case).
-__device__ __forceinline__ void stats_add(double* stats, float s, float ss, bool active, long long pos, long long pos_lane0, long long npos,
-                                          int G, int g, int pps) {
+__device__ __forceinline__ void stats_add(double* stats, float s, float ss, bool active, int pos, int pos_lane0, int npos, int G, int g,
+                                          int pps) {
     const int lane = threadIdx.x & 31;
-    long long last = pos_lane0 + 32 / G - 1;
+    int last = pos_lane0 + 32 / G - 1;
     if (last > npos - 1) last = npos - 1;
-    const bool uniform = (pos_lane0 / pps) == (last / pps);   // warp-uniform: lane 0's position is the same for the whole warp
+    const int smp0 = pos_lane0 / pps;
+    const bool uniform = smp0 == (last / pps);   // warp-uniform: lane 0's position is the same for the whole warp
     double ds = active ? (double)s : 0.0, dss = active ? (double)ss : 0.0;
     if (uniform) {
         for (int o = G; o < 32; o <<= 1) {
@@ -61,22 +62,23 @@ __device__ __forceinline__ void stats_add(double* stats, float s, float ss, bool
             dss += __shfl_xor_sync(0xffffffffu, dss, o);
         }
         if (lane < G && pos_lane0 < npos) {
-            double* d = stats + 2 * ((pos_lane0 / pps) * G + g);
+            double* d = stats + 2 * ((size_t)smp0 * G + g);
             atomicAdd(d, ds);
             atomicAdd(d + 1, dss);
         }
     } else if (active) {
-        double* d = stats + 2 * ((pos / pps) * G + g);
+        double* d = stats + 2 * ((size_t)(pos / pps) * G + g);
         atomicAdd(d, ds);
         atomicAdd(d + 1, dss);
     }
 }
 
 // ---- TAC: transform, average over the groups, concatenate (gc3_basics.py:38-55); the GroupNorm + residual follow in gn_res ----------
-template <int NG, int HG>
+template <int NG, int HG, int GT>
 __global__ void __launch_bounds__(256) gc_tac_kernel(const float* __restrict__ X, float* __restrict__ Y, double* __restrict__ stats, TacW w,
-                                                     long long npos, int G, int pps) {
-    constexpr int TH = 3 * HG, KMAX = (TH + 7) / 8, LD2 = TH + 1;   // odd row pitch: the lanes' column reads hit distinct banks
+                                                     int npos, int pps) {
+    constexpr int G = GT;   // compile-time group count: the lane reductions and the gather below unroll completely
+    constexpr int TH = 3 * HG, KMAX = (TH + GT - 1) / GT, LD2 = TH + 1;   // odd row pitch: the lanes' column reads hit distinct banks
     __shared__ __align__(16) float s_w1[TH * NG], s_b1[TH], s_w2[TH * LD2], s_b2[TH], s_w3[NG * 2 * TH], s_b3[NG];
     for (int i = threadIdx.x; i < TH * NG; i += blockDim.x) s_w1[i] = w.w1[i];
     for (int i = threadIdx.x; i < TH * TH; i += blockDim.x) s_w2[(i / TH) * LD2 + i % TH] = w.w2[i];
@@ -85,9 +87,9 @@ __global__ void __launch_bounds__(256) gc_tac_kernel(const float* __restrict__ X
     if (threadIdx.x < NG) s_b3[threadIdx.x] = w.b3[threadIdx.x];
     __syncthreads();
     const float a1 = __ldg(w.a1), a2 = __ldg(w.a2), a3 = __ldg(w.a3);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long pos = i / G, pos0 = (i - (threadIdx.x & 31)) / G;
-    const int g = (int)(i % G);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // element indices fit 31 bits (checked by the host)
+    const int pos = i / G, pos0 = (i - (threadIdx.x & 31)) / G;
+    const int g = i % G;
     const bool active = pos < npos;
     float x[NG];
 #pragma unroll
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(256) gc_tac_kernel(const float* __restrict__ X
     // TAC_mean: its TH rows are spread over the G lanes of a position (row r on lane r % G) and gathered in the output sum below;
     // each group-mean value is folded into those rows as soon as its reduction over the groups is done
     float y[TH], ms[KMAX];
-    const float inv_g = 1.f / (float)G;   // G is a power of two: exact
+    constexpr float inv_g = 1.f / (float)G;   // G is a power of two: exact
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) ms[k] = (g + k * G < TH) ? s_b2[g + k * G] : 0.f;
 #pragma unroll
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(256) gc_tac_kernel(const float* __restrict__ X
         for (int j = 0; j < NG; ++j) acc = fmaf(s_w1[r * NG + j], x[j], acc);
         y[r] = prelu1(acc, a1);
         float v = y[r];
+#pragma unroll
         for (int o = G >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         v *= inv_g;
 #pragma unroll
@@ -125,15 +128,11 @@ __global__ void __launch_bounds__(256) gc_tac_kernel(const float* __restrict__ X
         out[j] = acc;
     }
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-        for (int src = 0; src < G; ++src) {
-            const float v = __shfl_sync(0xffffffffu, ms[k], src, G);
-            const int r = src + k * G;
-            if (r < TH) {
+    for (int r = 0; r < TH; ++r) {
+        const float v = __shfl_sync(0xffffffffu, ms[r / G], r % G, G);
 #pragma unroll
-                for (int j = 0; j < NG; ++j) out[j] = fmaf(s_w3[j * 2 * TH + TH + r], v, out[j]);
-            }
-        }
+        for (int j = 0; j < NG; ++j) out[j] = fmaf(s_w3[j * 2 * TH + TH + r], v, out[j]);
+    }
     float s = 0.f, ss = 0.f;
 #pragma unroll
     for (int j = 0; j < NG; ++j) {
@@ -152,14 +151,15 @@ __global__ void __launch_bounds__(256) gc_tac_kernel(const float* __restrict__ X
 template <int NG>
 __global__ void __launch_bounds__(256) gc_gn_res_kernel(const float* __restrict__ Y, const float* __restrict__ R, float* __restrict__ Out,
                                                         const double* __restrict__ stats, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, long long total, int G, int pps, double eps,
+                                                        const float* __restrict__ beta, int total, int G, int pps, double eps,
                                                         const float* __restrict__ cat_w, const float* __restrict__ cat_b,
                                                         const float* __restrict__ cat_a) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // element indices fit 31 bits (checked by the host)
     if (i >= total) return;
-    const long long pos = i / G;
-    const int g = (int)(i % G);
-    const double* d = stats + 2 * ((pos / pps) * G + g);
+    const int gshift = 31 - __clz(G);   // G is a power of two
+    const int pos = i >> gshift;
+    const int g = i & (G - 1);
+    const double* d = stats + 2 * ((size_t)(pos / pps) * G + g);
     const double inv = 1.0 / ((double)pps * NG);
     const double mean = d[0] * inv;
     double var = d[1] * inv - mean * mean;
@@ -351,21 +351,22 @@ __global__ void __launch_bounds__(128) gc_ctx_rnn_kernel(float* A, RnnW w, long 
 // ---- Linear(2h -> n) of the ProjRNN + statistics of the GroupNorm that follows ------------------------------------------------------
 template <int NG, int HG>
 __global__ void __launch_bounds__(256) gc_proj_kernel(const float* __restrict__ Hh, float* __restrict__ Y, double* __restrict__ stats, RnnW w,
-                                                      long long npos, int G, int pps) {
+                                                      int npos, int G, int pps) {
     __shared__ float s_w[NG * 2 * HG], s_b[NG];
     for (int i = threadIdx.x; i < NG * 2 * HG; i += blockDim.x) s_w[i] = w.pw[i];
     if (threadIdx.x < NG) s_b[threadIdx.x] = w.pb[threadIdx.x];
     __syncthreads();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long pos = i / G, pos0 = (i - (threadIdx.x & 31)) / G;
-    const int g = (int)(i % G);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // element indices fit 31 bits (checked by the host)
+    const int gshift = 31 - __clz(G);                      // G is a power of two
+    const int pos = i >> gshift, pos0 = (i - (threadIdx.x & 31)) >> gshift;
+    const int g = i & (G - 1);
     const bool active = pos < npos;
     float out[NG];
 #pragma unroll
     for (int j = 0; j < NG; ++j) out[j] = s_b[j];
 #pragma unroll
     for (int k = 0; k < 2 * HG; k += 4) {
-        const float4 v = active ? *reinterpret_cast<const float4*>(Hh + i * 2 * HG + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v = active ? *reinterpret_cast<const float4*>(Hh + (size_t)i * 2 * HG + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < NG; ++j) {
             out[j] = fmaf(s_w[j * 2 * HG + k], v.x, out[j]);
@@ -657,6 +658,7 @@ bool gc_geometry(const dp_gctasnet* h, int B, int T, GGeo& g) {
     g.PC = (long long)B * g.Lc * g.ctx;
     g.PD = (long long)B * g.S2 * g.K;
     g.PM = g.PC > g.PD ? g.PC : g.PD;
+    if (g.PM * g.G * 2 * g.h >= (1LL << 31)) return false;   // the kernels index elements with 31 bits
     return true;
 }
 struct GLayout { size_t enc, feat, Xc, A, Y, Hh, sqm, fmap, Mk, stats, stats_bytes, total; };
@@ -710,8 +712,10 @@ template <int NG, int HG>
 struct Ops {
     static cudaError_t tac(dp_gctasnet* h, const float* X, float* Y, float* Out, double* st, const TacW& w, long long npos, int G, int pps,
                            cudaStream_t s) {
-        gc_tac_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(X, Y, st, w, npos, G, pps);
-        gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, X, Out, st, w.gamma, w.beta, npos * G, G, pps, 1e-5, nullptr, nullptr, nullptr);
+        if (G == 8) gc_tac_kernel<NG, HG, 8><<<blocks_for(npos * G), 256, 0, s>>>(X, Y, st, w, (int)npos, pps);
+        else if (G == 16) gc_tac_kernel<NG, HG, 16><<<blocks_for(npos * G), 256, 0, s>>>(X, Y, st, w, (int)npos, pps);
+        else gc_tac_kernel<NG, HG, 32><<<blocks_for(npos * G), 256, 0, s>>>(X, Y, st, w, (int)npos, pps);
+        gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, X, Out, st, w.gamma, w.beta, (int)(npos * G), G, pps, 1e-5, nullptr, nullptr, nullptr);
         h->launches += 2;
         return cudaGetLastError();
     }
@@ -720,8 +724,8 @@ struct Ops {
                            const float* cat_a = nullptr) {
         dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
         gc_lstm_kernel<NG, HG><<<grid, 128, 0, s>>>(A, Hh, w, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t);
-        gc_proj_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Y, st, w, npos, G, pps);
-        gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, A, A, st, w.gamma, w.beta, npos * G, G, pps, eps, cat_w, cat_b, cat_a);
+        gc_proj_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Y, st, w, (int)npos, G, pps);
+        gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, A, A, st, w.gamma, w.beta, (int)(npos * G), G, pps, eps, cat_w, cat_b, cat_a);
         h->launches += 3;
         return cudaGetLastError();
     }
