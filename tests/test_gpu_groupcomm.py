@@ -103,3 +103,23 @@ def test_training_and_unsupported_configurations_fail_loudly():
         TasNet(module="DPRNN", group_size=4).cuda().eval()(x)   # per-group widths (16, 32): not built
     with pytest.raises(RuntimeError):
         TasNet(module="DPRNN", group_size=16).eval()(x)          # parameters on the CPU: no CPU path
+
+
+def test_evaluation_loop_with_groupcomm_model():
+    """The evaluation loop (audio_test.py:72-81) over a GroupComm model: batched by length = one by one."""
+    import numpy as np
+
+    from audio_only_speech_separation_b200.metrics import MetricsTracker, evaluate
+
+    m, _, _ = _model("g16_b1_t300")
+    g = torch.Generator().manual_seed(5)
+    data = []
+    for i, T in enumerate([4000, 4000, 3000, 4000, 3000]):
+        src = torch.randn(2, T, generator=g) * 0.1
+        data.append((src.sum(0), src, f"utt{i}"))
+    one = evaluate(m, data, MetricsTracker(), batch_size=1)
+    one.final()
+    many = evaluate(m, data, MetricsTracker(), batch_size=4)
+    many.final()
+    assert np.isfinite(one.all_sisnrs_i).all()
+    assert np.allclose(sorted(one.all_sisnrs_i), sorted(many.all_sisnrs_i), atol=1e-4)
