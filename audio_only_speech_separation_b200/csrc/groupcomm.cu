@@ -189,7 +189,24 @@ __global__ void __launch_bounds__(256) gc_gn_res_kernel(const float* __restrict_
 // sequence (o, g): positions (o / qdiv) * s_hi + (o % qdiv) * s_lo + t * s_t ; blockIdx.y = direction.  Gate rows i, f, g, o.
 template <int NG, int HG>
 __global__ void __launch_bounds__(128) gc_lstm_kernel(const float* __restrict__ X, float* __restrict__ Hh, RnnW w, long long nouter, int G,
-                                                      int len, int qdiv, long long s_hi, long long s_lo, long long s_t) {
+                                                      int len, int qdiv, long long s_hi, long long s_lo, long long s_t, int staged) {
+    // staged: the inputs of the CTA's 128 / HG sequences are copied to shared memory first, so that a step never waits for a global
+    // load (with few CTAs per SM -- small batches -- the one-step-ahead register prefetch below is bound by the L2 latency)
+    extern __shared__ __align__(16) float xsm[];   // [128 / HG][len][NG]
+    if (staged) {
+        constexpr int SPB = 128 / HG, N4 = NG / 4;
+        const long long nseq = nouter * G, qb = (long long)blockIdx.x * SPB;
+        for (int idx = threadIdx.x; idx < SPB * len * N4; idx += blockDim.x) {
+            const int k4 = idx % N4, s2 = (idx / N4) % SPB, tt = idx / (N4 * SPB);   // adjacent sequences = adjacent groups: contiguous
+            long long qq = qb + s2;
+            if (qq >= nseq) qq = nseq - 1;
+            const long long oo = qq / G, bpp = (oo / qdiv) * s_hi + (oo % qdiv) * s_lo;
+            const float4 v = *reinterpret_cast<const float4*>(X + (bpp + (long long)tt * s_t) * (G * NG) + (qq % G) * NG + k4 * 4);
+            *reinterpret_cast<float4*>(xsm + ((size_t)s2 * len + tt) * NG + k4 * 4) = v;
+        }
+        __syncthreads();
+    }
+    const float* xloc = xsm + (size_t)(threadIdx.x / HG) * len * NG;
     const int dir = blockIdx.y;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int j = (int)(i % HG);
@@ -214,18 +231,23 @@ __global__ void __launch_bounds__(128) gc_lstm_kernel(const float* __restrict__ 
     int t = dir ? len - 1 : 0;
     const int dt = dir ? -1 : 1;
     float x[NG], xn[NG];
-    {
+    if (!staged) {
         const float* xp = X + (bp + (long long)t * s_t) * C + g * NG;
 #pragma unroll
         for (int k = 0; k < NG; k += 4) { float4 v = *reinterpret_cast<const float4*>(xp + k); xn[k] = v.x; xn[k + 1] = v.y; xn[k + 2] = v.z; xn[k + 3] = v.w; }
     }
     for (int step = 0; step < len; ++step, t += dt) {
+        if (staged) {
 #pragma unroll
-        for (int k = 0; k < NG; ++k) x[k] = xn[k];
-        if (step + 1 < len) {
-            const float* xp = X + (bp + (long long)(t + dt) * s_t) * C + g * NG;
+            for (int k = 0; k < NG; k += 4) { float4 v = *reinterpret_cast<const float4*>(xloc + t * NG + k); x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w; }
+        } else {
 #pragma unroll
-            for (int k = 0; k < NG; k += 4) { float4 v = *reinterpret_cast<const float4*>(xp + k); xn[k] = v.x; xn[k + 1] = v.y; xn[k + 2] = v.z; xn[k + 3] = v.w; }
+            for (int k = 0; k < NG; ++k) x[k] = xn[k];
+            if (step + 1 < len) {
+                const float* xp = X + (bp + (long long)(t + dt) * s_t) * C + g * NG;
+#pragma unroll
+                for (int k = 0; k < NG; k += 4) { float4 v = *reinterpret_cast<const float4*>(xp + k); xn[k] = v.x; xn[k + 1] = v.y; xn[k + 2] = v.z; xn[k + 3] = v.w; }
+            }
         }
         float a[4] = {b[0], b[1], b[2], b[3]};
 #pragma unroll
@@ -707,6 +729,7 @@ XfW xf_w(const dp_gctasnet* h, const float* p, int base) {
 }
 
 struct SeqWalk { long long nouter; int len, qdiv; long long s_hi, s_lo, s_t; };
+int g_lstm_staging = 1;   // dp_gctasnet_set_lstm_staging
 
 template <int NG, int HG>
 struct Ops {
@@ -719,11 +742,23 @@ struct Ops {
         h->launches += 2;
         return cudaGetLastError();
     }
+    static cudaError_t lstm(const float* X, float* Hh, const RnnW& w, int G, const SeqWalk& q, cudaStream_t s) {
+        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
+        size_t smem = (size_t)(128 / HG) * q.len * NG * sizeof(float);
+        int staged = g_lstm_staging && smem <= 200 * 1024;
+        if (!staged) smem = 0;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(gc_lstm_kernel<NG, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        gc_lstm_kernel<NG, HG><<<grid, 128, smem, s>>>(X, Hh, w, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t, staged);
+        return cudaGetLastError();
+    }
     static cudaError_t rnn(dp_gctasnet* h, float* A, float* Y, float* Hh, double* st, const RnnW& w, long long npos, int G, int pps,
                            const SeqWalk& q, double eps, cudaStream_t s, const float* cat_w = nullptr, const float* cat_b = nullptr,
                            const float* cat_a = nullptr) {
-        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
-        gc_lstm_kernel<NG, HG><<<grid, 128, 0, s>>>(A, Hh, w, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t);
+        cudaError_t e = lstm(A, Hh, w, G, q, s);
+        if (e != cudaSuccess) return e;
         gc_proj_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Y, st, w, (int)npos, G, pps);
         gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, A, A, st, w.gamma, w.beta, (int)(npos * G), G, pps, eps, cat_w, cat_b, cat_a);
         h->launches += 3;
@@ -747,8 +782,7 @@ struct Ops {
         if (smem > 200 * 1024) return fail("dp_gctasnet_forward: sequence of %d frames does not fit the attention kernel's shared memory", q.len);
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gc_dpt_attn_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gc_dpt_attn_kernel<NG><<<blocks_for(q.nouter * G, spb), 128, smem, s>>>(A, Z, w, q.nouter, G, q.len, spb, q.qdiv, q.s_hi, q.s_lo, q.s_t);
-        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
-        gc_lstm_kernel<NG, HG><<<grid, 128, 0, s>>>(Z, Hh, w.rnn, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t);
+        CK(lstm(Z, Hh, w.rnn, G, q, s));
         gc_dpt_out_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Z, A, w, npos * G, cat_w, cat_b, cat_a);
         h->launches += 3;
         CK(cudaGetLastError());
@@ -906,5 +940,11 @@ int dp_gctasnet_forward(dp_gctasnet* h, const float* params, const float* mixtur
 }
 
 int dp_gctasnet_last_launches(const dp_gctasnet* h) { return h ? h->launches : -1; }
+
+int dp_gctasnet_set_lstm_staging(int on) {
+    const int prev = g_lstm_staging;
+    g_lstm_staging = on ? 1 : 0;
+    return prev;
+}
 
 }  // extern "C"

@@ -274,6 +274,9 @@ int64_t dp_gctasnet_workspace_bytes(const dp_gctasnet* h, int B, int T);
 /* mixture[B,T] -> est[B,num_spk,T] */
 int dp_gctasnet_forward(dp_gctasnet* h, const float* params, const float* mixture, float* est, void* workspace, int B, int T, void* stream);
 int dp_gctasnet_last_launches(const dp_gctasnet* h);
+/* the narrow recurrence stages a CTA's input sequences in shared memory (default, sequences up to ~800 steps) or prefetches them from
+ * global memory one step ahead (longer sequences; 0 forces this path, for cross-checks).  Returns the previous setting. */
+int dp_gctasnet_set_lstm_staging(int on);
 
 #ifdef __cplusplus
 }

@@ -123,3 +123,21 @@ def test_evaluation_loop_with_groupcomm_model():
     many.final()
     assert np.isfinite(one.all_sisnrs_i).all()
     assert np.allclose(sorted(one.all_sisnrs_i), sorted(many.all_sisnrs_i), atol=1e-4)
+
+
+def test_staged_and_prefetching_recurrence_agree():
+    """The narrow recurrence with its inputs staged in shared memory (default) against the global-prefetch path kept for very long sequences."""
+    from audio_only_speech_separation_b200._lib import lib
+
+    for case in ("g16_b2_t8001", "dpt_g8_l2_b1_t3000"):
+        m, _, _ = _model(case)
+        x = (torch.randn(2, 6000, generator=torch.Generator().manual_seed(2)) * 0.1).cuda()
+        with torch.no_grad():
+            y1 = m(x)
+            prev = lib().dp_gctasnet_set_lstm_staging(0)
+            try:
+                y0 = m(x)
+            finally:
+                lib().dp_gctasnet_set_lstm_staging(prev)
+        assert prev == 1
+        assert rel_l2(y1, y0) < 1e-6
