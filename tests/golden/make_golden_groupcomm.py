@@ -62,5 +62,34 @@ for name, kw, B, T, kind in CASES:
                                "n_params": sum(p.numel() for p in m.parameters())}
     manifest["state_dicts"][name] = checksum(sd)
     print(name, "oracle rel-L2", r, "params", manifest["cases"][name]["n_params"])
+# ---------------------------------------------------------------- gradients (pins the oracle's autograd for the training backward of
+# this path, which the CUDA engine does not have yet): reference loss.backward() on the unit-test configuration, all gradients stored
+from look2hear.losses import PITLossWrapper, pairwise_neg_snr  # noqa: E402
+from oracle import dualpath_oracle as O  # noqa: E402
+
+for name, kw in [("g16", dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16, layer=2)),
+                 ("dpt_g16", dict(module="DPTNet", enc_dim=64, bn_dim=64, group_size=16, layer=2))]:
+    torch.manual_seed(0)
+    m = TasNet(**kw).train()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(2, 3000, generator=g) * 0.1
+    tgt = torch.randn(2, 2, 3000, generator=g) * 0.1
+    loss = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)(m(x), tgt)
+    m.zero_grad()
+    loss.backward()
+    ref_grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    lo = O.pit_loss(GO.tasnet_gc_forward(leaf, x, group_size=16, layer=2, module=kw["module"], lstm_impl="loop"), tgt, "snr", False)
+    lo.backward()
+    worst = max(((leaf[k].grad - ref_grads[k]).norm() / ref_grads[k].norm().clamp_min(1e-12)).item() for k in ref_grads)
+    assert abs(lo.item() - loss.item()) < 1e-5 and worst < 2e-3, (name, lo.item(), loss.item(), worst)
+    gnpz = {"x": x.numpy(), "tgt": tgt.numpy(), "loss": np.array(loss.item())}
+    for k, v in ref_grads.items():
+        gnpz["grad::" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, f"groupcomm_grads_{name}.npz"), **gnpz)
+    manifest["cases"][f"grads_{name}"] = {"kwargs": kw, "seed": 0, "oracle_worst_rel": worst, "loss": loss.item()}
+    print("grads", name, "loss", loss.item(), "worst oracle-vs-reference rel", worst)
+
 with open(os.path.join(HERE, "groupcomm_manifest.json"), "w") as f:
     json.dump(manifest, f, indent=1)

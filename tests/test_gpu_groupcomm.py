@@ -25,7 +25,7 @@ def _model(case):
     return m.cuda().eval(), sd, c
 
 
-@pytest.mark.parametrize("case", list(GC_MANIFEST["cases"]))
+@pytest.mark.parametrize("case", [c for c in GC_MANIFEST["cases"] if not c.startswith("grads_")])
 def test_forward_matches_reference_golden(case):
     m, _, _ = _model(case)
     z = load_npz(f"groupcomm_{case}.npz")

@@ -51,6 +51,25 @@ def test_state_dict_is_the_reference_one(case):
     assert len(m._gc_param_table()) == 12 + 4 * 23 + per_layer * c["kwargs"].get("layer", 6)
 
 
+@pytest.mark.parametrize("name", ["g16", "dpt_g16"])
+def test_oracle_autograd_matches_reference_gradients(name):
+    """Pins the oracle's backward for this path (the check the CUDA training backward will be held to): PIT-SNR loss and every
+    parameter gradient of the reference's own ``loss.backward()``."""
+    from oracle import dualpath_oracle as O
+
+    m, c = _model(f"grads_{name}")
+    z = load_npz(f"groupcomm_grads_{name}.npz")
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    kw = c["kwargs"]
+    est = GO.tasnet_gc_forward(leaf, torch.from_numpy(z["x"]), group_size=kw["group_size"], layer=kw["layer"], module=kw["module"])
+    loss = O.pit_loss(est, torch.from_numpy(z["tgt"]), "snr", False)
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) < 1e-5
+    for k, v in leaf.items():
+        ref = torch.from_numpy(z["grad::" + k])
+        assert rel_l2(v.grad, ref) < 1e-3, k
+
+
 def test_unsupported_variants_raise():
     from audio_only_speech_separation_b200.models import TasNet
 
