@@ -424,12 +424,19 @@ class TasNet(BaseModel):
         raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision!r}")
 
     def _ensure_pack(self):
+        self._require_training_engine()
         sig = tuple(p._version for p in self._uniq)
         if sig != self._pack_sig:
             check(lib().dp_tasnet_pack(self._handle, ptr(self._flat), ptr(self._pack), stream_ptr()), "dp_tasnet_pack")
             self._pack_sig = sig
 
+    def _require_training_engine(self):
+        if self.group_size > 1:  # the handle is a dp_gctasnet: never hand it to the dp_tasnet_* entry points
+            raise NotImplementedError("TasNet(group_size > 1): the GroupComm engine is inference-only; the fused training step "
+                                      "(DualPathTrainer / fit) needs group_size=1 (DESIGN.md scope table)")
+
     def _engine_forward(self, mixture, train: bool, est=None, ws=None):
+        self._require_training_engine()
         B, T = mixture.shape
         self._ensure_pack()
         nbytes = lib().dp_tasnet_workspace_bytes(self._handle, B, T, int(train))
@@ -448,6 +455,7 @@ class TasNet(BaseModel):
         return est, (ws if train else None)
 
     def _engine_backward(self, d_est, gflat, ws, B, T):
+        self._require_training_engine()
         check(
             lib().dp_tasnet_backward(self._handle, ptr(self._flat), ptr(self._pack), ptr(d_est), ptr(gflat), ptr(ws), B, T, self._prec(),
                                      stream_ptr()),

@@ -24,6 +24,8 @@ class DualPathTrainer:
                  process_group=None, distributed=False):
         if not isinstance(loss, PITLossWrapper) or not isinstance(loss.loss_func, PairwiseNegSDR) or loss.pit_from != "pw_mtx":
             raise NotImplementedError("DualPathTrainer needs PITLossWrapper(PairwiseNegSDR(...), pit_from='pw_mtx')")
+        if getattr(model, "group_size", 1) > 1:
+            raise NotImplementedError("DualPathTrainer: TasNet(group_size > 1) runs on the inference-only GroupComm engine (DESIGN.md scope table)")
         self.model, self.loss = model, loss
         self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.group, self.distributed = process_group, distributed

@@ -73,5 +73,16 @@ def test_oracle_autograd_matches_reference_gradients(name):
 def test_unsupported_variants_raise():
     from audio_only_speech_separation_b200.models import TasNet
 
+    gc = TasNet(module="DPRNN", group_size=16)
+    with pytest.raises(NotImplementedError):   # the fused training step must never reach the dual-path engine with a GroupComm handle
+        gc._engine_forward(torch.zeros(1, 800), True)
+    with pytest.raises(NotImplementedError):
+        gc._engine_backward(torch.zeros(1, 2, 800), None, None, 1, 800)
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+    from audio_only_speech_separation_b200.trainer import DualPathTrainer
+
+    with pytest.raises(NotImplementedError):
+        DualPathTrainer(gc, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False))
+
     with pytest.raises(RuntimeError):   # CUDA-only: CPU tensors are refused, there is no CPU path
         TasNet(module="DPRNN", group_size=16).eval()(torch.zeros(1, 800))
