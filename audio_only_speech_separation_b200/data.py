@@ -102,18 +102,35 @@ class PinnedLoader:
     whole test utterances)."""
 
     def __init__(self, dataset, batch_size: int, shuffle: bool = False, drop_last: bool = True, workers: int = 4, prefetch: int = 4,
-                 pin_memory: bool = True, seed: Optional[int] = None):
+                 pin_memory: bool = True, seed: Optional[int] = None, rank: int = 0, world: int = 1):
+        """``rank`` / ``world``: data-parallel sharding like Lightning's ``DistributedSampler`` (audio_train.py:126 trains under DDP):
+        every rank draws the SAME shuffled order (the seed must be shared, it is advanced once per epoch on every rank), the order is
+        padded by wrapping to a multiple of ``world`` and rank ``r`` takes items ``r, r + world, ...`` - an epoch is 1/world of the
+        single-process steps and no two ranks see the same item."""
         self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, batch_size, shuffle, drop_last
         self.workers, self.prefetch = max(1, workers), max(1, prefetch)
         self.pin = pin_memory and torch.cuda.is_available()
+        if not (0 <= rank < world):
+            raise ValueError(f"bad rank/world {rank}/{world}")
+        if world > 1 and shuffle and seed is None:
+            raise ValueError("PinnedLoader(world > 1, shuffle=True) needs a seed shared by all ranks")
+        self.rank, self.world = rank, world
         self.rng = np.random.default_rng(seed)
 
+    def _n_local(self) -> int:
+        return (len(self.dataset) + self.world - 1) // self.world
+
     def __len__(self):
-        n = len(self.dataset)
+        n = self._n_local()
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
     def _batches(self) -> List[List[int]]:
         order = self.rng.permutation(len(self.dataset)) if self.shuffle else np.arange(len(self.dataset))
+        if self.world > 1:
+            pad = self._n_local() * self.world - len(order)
+            if pad:
+                order = np.concatenate([order, order[:pad]])
+            order = order[self.rank::self.world]
         out = [order[i:i + self.batch_size].tolist() for i in range(0, len(order), self.batch_size)]
         if self.drop_last and out and len(out[-1]) < self.batch_size:
             out.pop()
@@ -177,9 +194,10 @@ class PinnedLoader:
                 cond.notify_all()
 
 
-def make_loaders(data_config: dict, workers: Optional[int] = None):
+def make_loaders(data_config: dict, workers: Optional[int] = None, rank: int = 0, world: int = 1, seed: Optional[int] = None):
     """``LRS2DataModule.setup`` + ``train/val/test_dataloader`` (lrs2datamodule.py:300-370) for the ``datamodule.data_config`` block of a
-    reference YAML: returns ``(train_loader, val_loader, test_set)``; the test set keeps whole utterances (``segment=None``)."""
+    reference YAML: returns ``(train_loader, val_loader, test_set)``; the test set keeps whole utterances (``segment=None``).
+    ``rank`` / ``world`` shard both loaders across data-parallel ranks (``seed`` is the shuffle seed every rank must share)."""
     c = dict(data_config)
     common = dict(n_src=c.get("n_src", 2), sample_rate=c.get("sample_rate", 8000), fps=c.get("fps", 25),
                   normalize_audio=c.get("normalize_audio", False), audio_only=c.get("audio_only", True))
@@ -188,5 +206,7 @@ def make_loaders(data_config: dict, workers: Optional[int] = None):
     test = LRS2Dataset(c["test_dir"], segment=None, **common)
     nw = c.get("num_workers", 4) if workers is None else workers
     bs = c.get("batch_size", 1)
-    return (PinnedLoader(train, bs, shuffle=True, drop_last=True, workers=nw, pin_memory=c.get("pin_memory", True)),
-            PinnedLoader(val, bs, shuffle=False, drop_last=True, workers=nw, pin_memory=c.get("pin_memory", True)), test)
+    if world > 1 and seed is None:
+        seed = 0
+    kw = dict(workers=nw, pin_memory=c.get("pin_memory", True), rank=rank, world=world)
+    return (PinnedLoader(train, bs, shuffle=True, drop_last=True, seed=seed, **kw), PinnedLoader(val, bs, shuffle=False, drop_last=True, **kw), test)

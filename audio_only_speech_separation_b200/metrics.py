@@ -97,10 +97,14 @@ def evaluate(model, test_set: Iterable, metrics: Optional[MetricsTracker] = None
 
     Utterances are grouped by exact length and run ``batch_size`` at a time (equal-length utterances share a batch without changing
     any utterance's result; different lengths are never padded together, which would change the normalisation statistics).
-    Returns the tracker.
+    ``Sepformer`` is the exception: the engine reproduces the reference's ``(spk, batch) -> (batch, spk)`` reshape quirk
+    (sepformer.py:1004), so for B > 1 row ``b`` of its output mixes utterances; like the reference's ``audio_test.py``
+    (one utterance per call) it is evaluated one utterance at a time.  Returns the tracker.
     """
     metrics = metrics if metrics is not None else MetricsTracker()
     buckets = {}
+    if getattr(model, "batch_rows_scrambled", False):
+        batch_size = 1
 
     def run(items):
         mix = torch.stack([m for m, _, _ in items]).to(device, non_blocking=True)

@@ -140,8 +140,9 @@ class _SepformerFunction(torch.autograd.Function):
     def forward(ctx, model, mixture, *params):
         # dropout masks are a function of (seed, layer, site, element): draw one seed per forward from torch's generator and hand the
         # same (p, seed) to the backward, which regenerates the masks
-        p = float(model.dropout) if model.training else 0.0
-        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if p > 0.0 else 0
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("Sepformer: the engine has no gradient with respect to the input waveform; detach the mixture")
+        p, seed = model._draw_dropout()
         check(lib().dp_sepformer_set_dropout(model._handle, p, seed), "dp_sepformer_set_dropout")
         est, ws = model._engine_forward_train(mixture)
         ctx.model, ctx.ws, ctx.dims, ctx.drop = model, ws, mixture.shape, (p, seed)
@@ -343,13 +344,43 @@ class Sepformer(BaseModel):
             check(lib().dp_sepformer_pack(self._handle, ptr(self._flat), ptr(self._pack), stream_ptr()), "dp_sepformer_pack")
             self._pack_sig = sig
 
-    def _engine_forward_train(self, mixture):
+    # est[b] of a B > 1 call holds rows of other utterances (the reference's reshape quirk, sepformer.py:1004): callers that pair est[b]
+    # with targets[b] (metrics.evaluate) must run one utterance per call
+    batch_rows_scrambled = True
+    # fused training interface (DualPathTrainer): the flat buffer also holds the pe buffers (their gradient stays zero)
+    flat_has_buffers = True
+
+    @property
+    def pack_launches(self) -> int:
+        return 2
+
+    def _draw_dropout(self):
+        """(p, seed): the masks are a pure function of (seed, layer, site, element); one seed per forward from torch's generator."""
+        p = float(self.dropout) if self.training else 0.0
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if p > 0.0 else 0
+        return p, seed
+
+    def _train_forward(self, mixture, ws=None):
+        drop = self._draw_dropout()
+        check(lib().dp_sepformer_set_dropout(self._handle, drop[0], drop[1]), "dp_sepformer_set_dropout")
+        est, ws = self._engine_forward_train(mixture, ws)
+        return est, (ws, drop)
+
+    def _train_backward(self, d_est, gflat, ctx, B, T):
+        ws, drop = ctx
+        check(lib().dp_sepformer_set_dropout(self._handle, drop[0], drop[1]), "dp_sepformer_set_dropout")
+        check(lib().dp_sepformer_backward(self._handle, ptr(self._flat), ptr(self._pack), ptr(d_est), ptr(gflat), ptr(ws), B, T, self._prec(),
+                                          stream_ptr()), "dp_sepformer_backward")
+        self.last_launches = lib().dp_sepformer_last_launches(self._handle)
+
+    def _engine_forward_train(self, mixture, ws=None):
         B, T = mixture.shape
         self._ensure_pack()
         nbytes = lib().dp_sepformer_train_workspace_bytes(self._handle, B, T)
         if nbytes < 0:
             check(1, "dp_sepformer_train_workspace_bytes")
-        ws = torch.empty(nbytes, device=mixture.device, dtype=torch.uint8)
+        if ws is None or ws.numel() < nbytes or ws.device != mixture.device:
+            ws = torch.empty(nbytes, device=mixture.device, dtype=torch.uint8)
         est = torch.empty(B, self.num_spks, T, device=mixture.device, dtype=torch.float32)
         check(lib().dp_sepformer_forward_train(self._handle, ptr(self._flat), ptr(self._pack), ptr(mixture), ptr(est), ptr(ws), B, T,
                                                self._prec(), stream_ptr()), "dp_sepformer_forward_train")

@@ -149,6 +149,9 @@ class _TasNetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, mixture, *params):
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("TasNet: the engine has no gradient with respect to the input waveform (the reference's training "
+                                      "step never asks for it); detach the mixture")
         train = any(ctx.needs_input_grad[2:])
         est, ws = model._engine_forward(mixture, train)
         ctx.model, ctx.ws, ctx.dims = model, ws, mixture.shape
@@ -453,6 +456,18 @@ class TasNet(BaseModel):
         )
         self.last_launches = lib().dp_tasnet_last_launches(self._handle)
         return est, (ws if train else None)
+
+    # fused training interface (DualPathTrainer): forward that saves, backward into a flat gradient buffer
+    @property
+    def pack_launches(self) -> int:
+        return 1 + 2 * self.layer
+
+    def _train_forward(self, mixture, ws=None):
+        est, ws = self._engine_forward(mixture, True, ws=ws)
+        return est, (ws,)
+
+    def _train_backward(self, d_est, gflat, ctx, B, T):
+        self._engine_backward(d_est, gflat, ctx[0], B, T)
 
     def _engine_backward(self, d_est, gflat, ws, B, T):
         self._require_training_engine()

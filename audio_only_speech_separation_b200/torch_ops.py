@@ -171,6 +171,8 @@ def _(ests, targets, sdr_type, threshold_byloss):
 @custom_op("dualpath::pit_sdr_loss_backward", mutates_args=(), device_types="cuda")
 def pit_sdr_loss_backward(ests: torch.Tensor, targets: torch.Tensor, ws: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     B, _, T = ests.shape
+    # the kernel reads raw pointers: saved tensors may be the caller's non-contiguous / non-fp32 views
+    ests, targets = ests.contiguous().float(), targets.contiguous().float()
     d = torch.empty_like(ests)
     check(lib().dp_pit_loss_backward(ptr(ests), ptr(targets), B, T, ptr(ws), 1.0, ptr(d), stream_ptr()), "dp_pit_loss_backward")
     return d * g   # the upstream gradient is a device scalar: folded in without a host sync
@@ -188,6 +190,8 @@ def _pit_setup(ctx, inputs, output):
 
 def _pit_backward(ctx, g, _d_perm, _d_ws):
     ests, targets, ws = ctx.saved_tensors
+    if ctx.needs_input_grad[1]:
+        raise NotImplementedError("dualpath::pit_sdr_loss has no gradient with respect to the targets (the reference never asks for it)")
     return torch.ops.dualpath.pit_sdr_loss_backward(ests, targets, ws, g), None, None, None
 
 

@@ -26,6 +26,11 @@ class DualPathTrainer:
             raise NotImplementedError("DualPathTrainer needs PITLossWrapper(PairwiseNegSDR(...), pit_from='pw_mtx')")
         if getattr(model, "group_size", 1) > 1:
             raise NotImplementedError("DualPathTrainer: TasNet(group_size > 1) runs on the inference-only GroupComm engine (DESIGN.md scope table)")
+        if not (hasattr(model, "_train_forward") and hasattr(model, "_train_backward")):
+            raise NotImplementedError(f"DualPathTrainer: {type(model).__name__} does not expose the fused training interface "
+                                      "(_train_forward / _train_backward into a flat gradient buffer)")
+        if weight_decay != 0.0 and getattr(model, "flat_has_buffers", False):
+            raise NotImplementedError("weight_decay != 0 with non-parameter tensors (Sepformer's pe buffers) in the flat buffer")
         self.model, self.loss = model, loss
         self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.group, self.distributed = process_group, distributed
@@ -44,6 +49,13 @@ class DualPathTrainer:
             self.gflat = torch.zeros(n, device=device)
             self.norm2 = torch.zeros(1, device=device, dtype=torch.float64)
             self._state_for = m._flat
+            if self.distributed:
+                # DDPStrategy broadcasts rank 0's parameters and buffers when it wraps the model (audio_train.py:126): replicas must not
+                # depend on every rank having drawn the same initial weights
+                import torch.distributed as dist
+
+                dist.broadcast(m._flat, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+                m.mark_params_dirty()
 
     def world_size(self) -> int:
         if not self.distributed:
@@ -57,14 +69,15 @@ class DualPathTrainer:
         m = self.model
         self._ensure_state(mixtures.device)
         B, T = mixtures.shape
-        est, self._ws = m._engine_forward(mixtures, True, ws=self._ws)
+        est, ctx = m._train_forward(mixtures, self._ws)
+        self._ws = ctx[0]
         launches = m.last_launches
         loss, _pw, _perm, lws = pit_sdr_forward(est, targets, self.loss.loss_func.sdr_type, self.loss.threshold_byloss)
         d_est = torch.empty_like(est)
         check(lib().dp_pit_loss_backward(ptr(est), ptr(targets), B, T, ptr(lws), 1.0, ptr(d_est), stream_ptr()), "dp_pit_loss_backward")
         launches += 4 + (1 if self.loss.loss_func.sdr_type == "sisdr" else 0)
         self.gflat.zero_()
-        m._engine_backward(d_est, self.gflat, self._ws, B, T)
+        m._train_backward(d_est, self.gflat, ctx, B, T)
         launches += m.last_launches
         gscale = 1.0
         if self.distributed:
@@ -80,7 +93,7 @@ class DualPathTrainer:
             "dp_adam_clip_step",
         )
         m.mark_params_dirty()
-        launches += 2 + 1 + 2 * m.layer  # sumsq + adam, and the re-pack of the weights the next forward triggers
+        launches += 2 + m.pack_launches  # sumsq + adam, and the re-pack of the weights the next forward triggers
         self.launches_per_step = launches
         return loss.reshape(())
 

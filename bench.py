@@ -1,17 +1,26 @@
 #!/usr/bin/env python
-"""Headline benchmark: DPRNN-wsj0 training step (configs/dprnn_wsj0.yml), batch 16 utterances of 4 s @ 8 kHz per GPU.
+"""Benchmark of the dual-path separation hot path (BASELINE.json: "separated audio-sec/sec (DPRNN wsj0 fwd) and train samples/sec").
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision fp32|bf16]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision fp32|bf16] [--no-configs] [--no-cpu-baseline]
 
-One "step" = forward + PIT neg-SNR loss + backward + (N>1: one NCCL all-reduce of the flat gradient buffer) +
-clip_grad_norm_(5.0) + Adam(1e-3) on synthetic data, random-init weights of the named architecture.
-* ``value``  : training samples/s over all ranks, inputs already resident in HBM, CUDA-event timed, max over ranks.
-* ``e2e``    : same metric through the public trainer call with HOST (pinned) inputs: per step H2D copy of the
-               mixtures and targets and a D2H read of the loss scalar inside the timed region.
-* ``roofline``: the dominant kernel (persistent LSTM BPTT recurrence; the forward member reported beside it), timed alone
-               with CUDA events in this process.
-* ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference (torch CPU, all host threads) on a bounded
-  sample of the same workload.  The reference itself is pure Python and cannot travel to the GPU box.
+Headline line (unchanged since round 1): configs[1], the DPRNN-wsj0 training step (configs/dprnn_wsj0.yml), 16 utterances of
+4 s @ 8 kHz per GPU.  One "step" = forward + PIT neg-SNR loss + backward + (N>1: one NCCL all-reduce of the flat gradient buffer) +
+clip_grad_norm_(5.0) + Adam(1e-3), synthetic data, reference default-init weights of the named architecture.
+
+* ``value``    : training samples/s over all ranks, inputs resident in HBM, CUDA events, max over ranks.
+* ``e2e``      : the same metric through the public trainer call with HOST (pinned) inputs: per step an H2D copy of mixtures and
+                 targets and a D2H read of the loss inside the timed region.
+* ``roofline`` : the dominant kernel of the headline step (BiLSTM recurrence), timed alone in this process.
+* ``configs``  : (N = 1 only) the other BASELINE.json configs, each with its own device-timed value, e2e with host copies, the
+                 roofline of its dominant kernel and the PARITY of this very run against goldens written by the real reference
+                 (tests/golden/headline_*.npz, model_dprnn_wsj0_b1_t32000.npz):
+                 C1 DPRNN forward B=1 (audio-s/s: the first half of the metric), C3 unfolded DPRNN B=32, C4 DPTNet bf16 (B=1, 16),
+                 C5 SepFormer 16 s bf16 inference + training step; plus ``eager_b200``: the UNMODIFIED reference modules run eagerly on
+                 the same B200 (cuDNN LSTM / cuBLAS, TF32 off) - the GPU bar of SURVEY 8d.
+* ``strong``   : (N > 1) the same step with the GLOBAL batch fixed at 16 (16/N utterances per rank): strong scaling.
+* ``cpu_baseline`` / ``--impl reference``: the reference's own CPU implementation on the host cores: the unmodified
+  ``look2hear.models.TasNet`` + ``PITLossWrapper`` staged under baseline/_ref (baseline/make_ref.py; git-ignored, shipped by gpurun),
+  ``kind: "reference"``; when the staged copy is missing it falls back to the oracle port (``kind: "port"``) and says so.
 """
 import argparse
 import json
@@ -23,13 +32,17 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(1, os.path.join(ROOT, "tests"))   # tests/headline.py: golden-fixture parity helpers (no oracle, no reference)
 
 import torch  # noqa: E402
 
 SR, SECONDS, BATCH = 8000, 4.0, 16
-CFG = dict(enc_dim=64, bn_dim=64, hidden_dim=128, win=16, layer=6, num_spk=2, module="DPRNN", group_size=1, block_size=100, unfold=False)
-# dram__bytes_read.sum + dram__bytes_write.sum of one lstm_fwd_kernel launch (ncu --set full capture under profiles/), by batch
-TRAFFIC_BYTES_PER_LAUNCH = {16: 1294316032}      # lstm_bwd_ks_kernel, profiles/r1_lstm_bwd_v11_full.summary.txt (dram read + write)
+T4S = int(SR * SECONDS)
+CFG_DPRNN = dict(enc_dim=64, bn_dim=64, hidden_dim=128, win=16, layer=6, num_spk=2, module="DPRNN", group_size=1, block_size=100, unfold=False)
+CFG_UNFOLD = dict(CFG_DPRNN, unfold=True)
+CFG_DPTNET = dict(CFG_DPRNN, module="DPTNet")
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full captures under profiles/), by batch
+TRAFFIC_BYTES_PER_LAUNCH = {16: 1294316032}      # lstm_bwd_ks_kernel, profiles/r1_lstm_bwd_v11_full.summary.txt
 TRAFFIC_FWD_BYTES_PER_LAUNCH = {16: 1287374592}  # lstm_fwd_pipe_kernel, profiles/r1_lstm_fwd_v11_full.summary.txt
 METRIC = "train samples/sec (DPRNN wsj0, batch 16/GPU, 4 s @ 8 kHz, fwd + PIT-SNR loss + bwd + clip + Adam)"
 
@@ -99,27 +112,59 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def synthetic(batch, seed):
+def synthetic(batch, seed, T=T4S):
     g = torch.Generator().manual_seed(seed)
-    T = int(SR * SECONDS)
     src = torch.randn(batch, 2, T, generator=g) * 0.1
     return src.sum(1).contiguous(), src.contiguous()
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
+def reference_modules():
+    """(models, losses, kind): the staged unmodified reference (baseline/_ref) or None."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import make_ref
+
+        M, L = make_ref.import_reference()
+        return M, L
+    except Exception:
+        return None
+
+
 def cpu_reference_step_fn(batch):
-    """Oracle port of the reference training step on the host cores (audio_litmodule.py:73-88 + audio_train.py:48,128)."""
+    """Training step of the reference on the host cores: (step function, kind).
+
+    kind "reference": the unmodified ``look2hear.models.TasNet`` + ``look2hear.losses.PITLossWrapper`` from baseline/_ref, with the
+    ~15-line restatement of the Lightning step BASELINE.md section 3 prescribes (audio_litmodule.py:73-88, audio_train.py:48,128:
+    zero_grad, forward, PIT neg-SNR, backward, clip_grad_norm_ 5.0, Adam 1e-3).  kind "port": the oracle port, when no staged copy exists."""
+    torch.set_num_threads(os.cpu_count())
+    mix, tgt = synthetic(batch, 1234)
+    ref = reference_modules()
+    if ref is not None:
+        M, L = ref
+        torch.manual_seed(0)
+        m = M.TasNet(sample_rate=SR, **CFG_DPRNN).train()
+        loss_fn = L.PITLossWrapper(L.pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=0.0)
+
+        def step():
+            opt.zero_grad()
+            loss = loss_fn(m(mix), tgt)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+            opt.step()
+            return loss.item()
+
+        return step, "reference"
     from audio_only_speech_separation_b200.models import TasNet
     from oracle import dualpath_oracle as O
 
-    torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
-    m = TasNet(sample_rate=SR, **CFG)
+    m = TasNet(sample_rate=SR, **CFG_DPRNN)
     params = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
     keys = [k for k, _ in m.named_parameters()]
     ea = [torch.zeros_like(params[k]) for k in keys]
     es = [torch.zeros_like(params[k]) for k in keys]
-    mix, tgt = synthetic(batch, 1234)
     state = {"step": 0}
 
     def step():
@@ -132,36 +177,42 @@ def cpu_reference_step_fn(batch):
             O.adam_clip_step([params[k] for k in keys], [params[k].grad for k in keys], ea, es, state["step"])
         return loss.item()
 
-    return step
+    return step, "port"
 
 
 def run_reference(args):
+    """The reference arm: the SAME config as the headline (B = 16 utterances per step) on all host cores.  A step takes tens of seconds,
+    so the run is capped at 1 warm-up + at most 2 timed steps (said in ``sample``) to end within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = 1
-    step = cpu_reference_step_fn(sample_b)
-    for _ in range(min(args.warmup, 2)):
+    step, kind = cpu_reference_step_fn(args.batch)
+    warm = 1
+    steps = max(1, min(args.steps, 2))
+    for _ in range(warm):
         step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    val = sample_b * args.steps / dt
+    val = args.batch * steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs/dprnn_wsj0.yml DPRNN training step, 4 s @ 8 kHz", "batch_per_step_sample": sample_b},
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{args.steps} training steps of {sample_b} utterance(s) (oracle port of the reference, torch CPU, "
-                                   f"{os.cpu_count()} threads)"},
+        "config": {"workload": "configs/dprnn_wsj0.yml DPRNN training step, 4 s @ 8 kHz (configs[1])", "batch_per_gpu": args.batch,
+                   "global_batch": args.batch, "samples": T4S, "same_config_as_ours": True,
+                   "capped": f"requested steps={args.steps} warmup={args.warmup}; ran {steps} timed step(s) after {warm} warm-up (a step is tens of seconds)"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": kind,
+                         "sample": f"{steps} training step(s) of {args.batch} utterances after {warm} warm-up; "
+                                   + ("unmodified look2hear TasNet + PITLossWrapper from baseline/_ref" if kind == "reference"
+                                      else "oracle port (baseline/_ref not staged)") + f", torch CPU, {os.cpu_count()} threads"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------------ our arm
+# ------------------------------------------------------------------------------------------------ our arm: helpers
 def time_recurrence(model, B, precision):
     """Average duration of the dominant kernel family (persistent BiLSTM recurrence, intra-chunk pass at the bench shape,
     training mode), each member timed alone with CUDA events on the launching stream: the forward kernel (reads the gate
@@ -181,7 +232,7 @@ def time_recurrence(model, B, precision):
     dbias = torch.zeros(1024, device=dev)
     prec = _lib.PREC_FP32 if precision == "fp32" else _lib.PREC_BF16
     L = _lib.lib()
-    tf, tb = [], []
+    tf, tb, ti = [], [], []
     for it in range(6):
         G.copy_(G0)  # every timed launch starts from a cold L2
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -192,13 +243,316 @@ def time_recurrence(model, B, precision):
         _lib.check(L.dp_bilstm_backward_f32(_lib.ptr(pack.buf), _lib.ptr(G), _lib.ptr(Cst), _lib.ptr(dH), None, 0, _lib.ptr(dbias), P, B * S, K,
                                             1 << 30, 0, K, 1, prec, _lib.stream_ptr()))
         e2.record()
+        G.copy_(G0)
+        e3, e4 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        e3.record()   # inference mode: reads G, writes H only
+        _lib.check(L.dp_lstm_recurrence_f32(_lib.ptr(pack.buf), _lib.ptr(G), _lib.ptr(H), None, B * S, K, 1 << 30, 0, K, 1, 0, prec,
+                                            _lib.stream_ptr()))
+        e4.record()
         torch.cuda.synchronize()
         if it >= 2:
             tf.append(e0.elapsed_time(e1) * 1e-3)
             tb.append(e1.elapsed_time(e2) * 1e-3)
+            ti.append(e3.elapsed_time(e4) * 1e-3)
     flops = 2.0 * 512 * 128 * (B * S) * K * 2   # one recurrent product per step, both directions (algorithmic: one product per MAC)
-    hbm = P * (1024 + 1024 + 256 + 256) * 4.0   # 84 MB per utterance for either kernel
-    return sum(tf) / len(tf), sum(tb) / len(tb), flops, hbm
+    hbm = P * (1024 + 1024 + 256 + 256) * 4.0   # 84 MB per utterance for either training kernel
+    hbm_inf = P * (1024 + 256) * 4.0            # inference: G in, H out (42 MB per utterance)
+    mean = lambda v: sum(v) / len(v)  # noqa: E731
+    return mean(tf), mean(tb), mean(ti), flops, hbm, hbm_inf
+
+
+def time_ffn_gemm(P, precision="bf16"):
+    """SepFormer's dominant kernel: the FFN GEMMs [P,256] x [256,1024] (+ReLU, planes out) and [P,1024] x [1024,256] on the TMA-fed tcgen05
+    kernel, timed alone (CUDA events, operands 2 x 33-133 MB: larger than what stays in L2 between the two).  Returns (s, flops)."""
+    from audio_only_speech_separation_b200 import ops
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    a = torch.randn(P, 256, device=dev)
+    w1 = torch.randn(1024, 256, device=dev) / 16
+    w2 = torch.randn(256, 1024, device=dev) / 32
+    ah, al = ops.split_rows(a)
+    w1h, w1l = ops.split_rows(w1)
+    w2h, w2l = ops.split_rows(w2)
+    hid = torch.empty(P, 1024, device=dev)
+    out = torch.empty(P, 256, device=dev)
+    ts = []
+    for it in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, hp = ops.linear_planes(ah, al, w1h, w1l, act=1, out=hid, planes_out=True, precision=precision)
+        ops.linear_planes(hp[0], hp[1], w2h, w2l, out=out, precision=precision)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+    return sum(ts) / len(ts), 2.0 * 2.0 * P * 256 * 1024
+
+
+class Flusher:
+    """Evicts the 126 MB L2 between timed forward iterations (the B = 1 working sets fit in it): a 256 MiB memset."""
+
+    def __init__(self, dev):
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def __call__(self):
+        self.buf.zero_()
+
+
+def time_forward(fn, iters, warmup, flush):
+    for _ in range(warmup):
+        fn()
+    evs = []
+    for _ in range(iters):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) * 1e-3 / iters
+
+
+def time_e2e_forward(model, x_host, iters, warmup):
+    """Public call with HOST buffers: pinned mixture -> device, ``model(mixture)``, estimates -> pinned host, per iteration."""
+    dev = next(model.parameters()).device
+    x_d = torch.empty(x_host.shape, device=dev)
+    est_h = None
+
+    def once():
+        nonlocal est_h
+        x_d.copy_(x_host, non_blocking=True)
+        with torch.no_grad():
+            est = model(x_d)
+        if est_h is None:
+            est_h = torch.empty(est.shape, dtype=est.dtype).pin_memory()
+        est_h.copy_(est, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        once()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        once()
+    dt = (time.perf_counter() - t0) / iters
+    return dt, int(x_host.numel() * 4), int(est_h.numel() * 4)
+
+
+def forward_config(name, workload, build, cfgkw, B, T, sr, precision, golden, iters, flush, pk, roofline_fn=None, eager_cls=None):
+    """One forward-only config: parity of this run against the reference golden (fp32 mode rel-L2; bf16 mode dPIT-SI-SNR), device-timed
+    value, e2e with host copies, roofline of the dominant kernel, optional eager-PyTorch-on-B200 bar with the unmodified reference module."""
+    import headline as HL
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(0)
+    model = build(**cfgkw).to(dev).eval()
+    out = {"workload": workload, "batch": B, "samples": T, "sample_rate": sr, "precision_timed": precision}
+    # ---- parity (golden utterance at row B // 2 of the batch)
+    if golden is not None:
+        x1, src, y_ref = golden
+        xb, row = HL.embed_batch(x1, B) if B > 1 else (x1, 0)
+        par = {}
+        for mode in ("fp32", "bf16"):
+            model.precision = mode
+            with torch.no_grad():
+                y = model(xb.to(dev))[row : row + 1].float().cpu()
+            if mode == "fp32":
+                par["rel_l2_fp32"] = HL.rel_l2(y, y_ref)
+            else:
+                par.update({"bf16_" + k: v for k, v in HL.bf16_gate(y, y_ref, src).items()} if src is not None
+                           else {"bf16_rel_l2": HL.rel_l2(y, y_ref)})
+        if precision == "bf16":   # BASELINE.json names bf16 for this config: both gates apply
+            par["gates"] = "fp32 mode rel-L2 <= 1e-4; bf16 mode (the timed one) |dPIT-SI-SNR| <= 0.05 dB vs the fp32 reference output"
+            par["pass"] = bool(par["rel_l2_fp32"] <= 1e-4 and par.get("bf16_delta_pit_sisnr_db", 0.0) <= 0.05)
+        else:                     # fp32 config: the bf16 numbers are informational (random-weight PIT-SI-SNR sits near -33 dB, SURVEY 7 hard part 8)
+            par["gates"] = "fp32 mode (the timed one) rel-L2 <= 1e-4; bf16 figures informational"
+            par["pass"] = bool(par["rel_l2_fp32"] <= 1e-4)
+        out["parity"] = par
+    else:
+        xb = synthetic(B, 4242, T)[0]
+    model.precision = precision
+    x_d = xb.to(dev)
+
+    def fwd():
+        with torch.no_grad():
+            model(x_d)
+
+    sec = time_forward(fwd, iters, 3, flush)
+    audio_s = B * T / sr
+    out.update({"metric": "separated audio-sec/sec (forward)", "value": audio_s / sec, "unit": "audio-s/s", "ms_per_forward": 1e3 * sec,
+                "gpu_launches_per_forward": int(model.last_launches)})
+    dt, h2d, d2h = time_e2e_forward(model, xb.pin_memory(), iters, 3)
+    out["e2e"] = {"value": audio_s / dt, "unit": "audio-s/s", "ms_per_forward": 1e3 * dt, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    if roofline_fn is not None:
+        out["roofline"] = roofline_fn(model)
+    if eager_cls is not None:
+        out["eager_b200"] = eager_forward(eager_cls, cfgkw, xb, sr, audio_s, flush)
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def eager_forward(cls, cfgkw, xb, sr, audio_s, flush):
+    """The UNMODIFIED reference module on the same B200, eager PyTorch (cuDNN LSTM with flattened weights, cuBLAS), TF32 off."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        m = cls(sample_rate=sr, **cfgkw).to(dev).eval()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.LSTM):
+                mod.flatten_parameters()
+        x_d = xb.to(dev)
+
+        def fwd():
+            with torch.no_grad():
+                m(x_d)
+
+        sec = time_forward(fwd, 5, 2, flush)
+        return {"value": audio_s / sec, "unit": "audio-s/s", "ms_per_forward": 1e3 * sec,
+                "what": "unmodified look2hear module from baseline/_ref, eager PyTorch on this B200, TF32 disabled"}
+    except Exception as exc:  # the bar is informational: never let it take the bench down
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
+
+def eager_train_step(M, L, cfgkw, B, flush):
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        m = M.TasNet(sample_rate=SR, **cfgkw).to(dev).train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.LSTM):
+                mod.flatten_parameters()
+        loss_fn = L.PITLossWrapper(L.pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+        mix, tgt = synthetic(B, 1234)
+        mix, tgt = mix.to(dev), tgt.to(dev)
+
+        def step():
+            opt.zero_grad()
+            loss_fn(m(mix), tgt).backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+            opt.step()
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / 5
+        return {"value": B / sec, "unit": "samples/s", "ms_per_step": 1e3 * sec,
+                "what": "unmodified look2hear TasNet + PITLossWrapper from baseline/_ref, eager PyTorch training step on this B200 "
+                        "(cuDNN LSTM, flatten_parameters, TF32 disabled)"}
+    except Exception as exc:
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
+
+def other_configs(args, pk, pk_kind, rec):
+    """The configs block (N = 1): C1, C3, C4, C5 with parity measured in this run against the reference goldens."""
+    import numpy as np
+
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+    from audio_only_speech_separation_b200.models import Sepformer, TasNet
+    from audio_only_speech_separation_b200.trainer import DualPathTrainer
+    import headline as HL
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    flush = Flusher(dev)
+    ref = reference_modules()
+    RM = ref[0] if ref is not None else None
+    f_sec, b_sec, i_sec, k_flops, k_hbm, k_hbm_inf = rec
+    out = {}
+
+    def lstm_roofline(B):
+        def fn(model):
+            fs, bs, isec, fl, hb, hbi = time_recurrence(model, B, "fp32") if B != args.batch else rec
+            return {"kernel": "BiLSTM recurrence forward, inference mode (intra-chunk pass: reads G, writes H)", "bound": "hbm",
+                    "achieved": hbi / isec / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbi / isec / 1e9 / pk["hbm_gbs"], "traffic": None,
+                    "ms_per_launch": 1e3 * isec, "algorithmic_bytes_per_launch": hbi,
+                    "note": "at B = 1 the pass is a chain of dependent time steps on a fraction of the SMs (latency-bound, SURVEY 7 hard part 3); "
+                            "the fraction is reported against HBM as the contract asks"}
+        return fn
+
+    # C1: DPRNN-wsj0 forward, B = 1 (the first half of BASELINE.json's metric)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "model_dprnn_wsj0_b1_t32000.npz"))
+    gold = (torch.from_numpy(g["x"]), None, torch.from_numpy(g["y"]))
+    out["C1"] = forward_config("C1", "configs/dprnn_wsj0.yml DPRNN forward, B=1, 4 s @ 8 kHz (configs[0])", lambda **kw: TasNet(sample_rate=SR, **kw),
+                               CFG_DPRNN, 1, T4S, SR, "fp32", gold, 20, flush, pk, lstm_roofline(1), RM.TasNet if RM else None)
+    out["C1_B16"] = forward_config("C1_B16", "configs/dprnn_wsj0.yml DPRNN forward, B=16", lambda **kw: TasNet(sample_rate=SR, **kw), CFG_DPRNN, 16,
+                                   T4S, SR, "fp32", gold, 10, flush, pk, lstm_roofline(16), RM.TasNet if RM else None)
+    # C3: unfolded DPRNN, B = 32, 2 s @ 16 kHz (same tensor shapes)
+    x, s, y, _ = HL.load_case("headline_dprnn_unfold_t32000")
+    out["C3"] = forward_config("C3", "configs/dprnn_lrs2_unfolded.yml DPRNN unfolded forward, B=32, 2 s @ 16 kHz (configs[2])",
+                               lambda **kw: TasNet(sample_rate=16000, **kw), CFG_UNFOLD, 32, 32000, 16000, "fp32", (x, s, y), 10, flush, pk,
+                               lstm_roofline(32), RM.TasNet if RM else None)
+    # C4: DPTNet bf16, B = 1 and 16
+    x, s, y, _ = HL.load_case("headline_dptnet_t32000")
+    for B in (1, 16):
+        out["C4" if B == 1 else "C4_B16"] = forward_config(
+            "C4", f"configs/dptnet_wsj0.yml DPTNet forward, B={B}, 4 s @ 8 kHz, bf16 (configs[3])", lambda **kw: TasNet(sample_rate=SR, **kw),
+            CFG_DPTNET, B, T4S, SR, "bf16", (x, s, y), 20 if B == 1 else 10, flush, pk, None, RM.TasNet if RM and B == 1 else None)
+    # C5: SepFormer 16 s, bf16 inference (8 kHz: T = 128000; the YAML's 16 kHz: T = 256000) + training step
+    def ffn_roofline(P):
+        def fn(_model):
+            sec, fl = time_ffn_gemm(P, "bf16")
+            return {"kernel": "gemm_tma_nt_kernel: FFN1 (+ReLU, planes out) + FFN2 of one layer, bf16, timed as a pair", "bound": "tensor",
+                    "achieved": fl / sec / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / sec / 1e12 / pk["bf16_tflops"],
+                    "traffic": None, "ms_per_launch_pair": 1e3 * sec, "peak_source": f"{pk_kind} cuBLAS bf16 burst"}
+        return fn
+
+    for T, key in ((128000, "C5"), (256000, "C5_16k")):
+        x, s, y, _ = HL.load_case(f"headline_sepformer_t{T}")
+        S2 = {128000: 130, 256000: 258}[T]
+        out[key] = forward_config(key, f"configs/sepformer_base.yml SepFormer forward, B=1, 16 s @ {T // 16000} kHz (T={T}), bf16 (configs[4])",
+                                  lambda **kw: Sepformer(sample_rate=SR, **kw), {}, 1, T, T // 16, "bf16", (x, s, y), 10, flush, pk,
+                                  ffn_roofline(250 * S2), RM.Sepformer if RM and T == 128000 else None)
+    # C5 training step (YAML: batch_size 1, PIT neg-SNR with threshold_byloss, dropout 0.1 active), fused trainer
+    for T, key in ((128000, "C5_train"),):
+        torch.manual_seed(0)
+        m = Sepformer(sample_rate=SR).to(dev).train()
+        m.precision = "bf16"
+        tr = DualPathTrainer(m, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=True), lr=1e-3, max_norm=5.0)
+        mix_h, tgt_h = synthetic(1, 99, T)
+        mix_h, tgt_h = mix_h.pin_memory(), tgt_h.pin_memory()
+        mix_d, tgt_d = mix_h.to(dev), tgt_h.to(dev)
+        for _ in range(3):
+            tr.step(mix_d, tgt_d)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 10
+        e0.record()
+        for _ in range(n):
+            tr.step(mix_d, tgt_d)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / n
+        mix_s, tgt_s = torch.empty_like(mix_d), torch.empty_like(tgt_d)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            mix_s.copy_(mix_h, non_blocking=True)
+            tgt_s.copy_(tgt_h, non_blocking=True)
+            loss = tr.step(mix_s, tgt_s).item()
+        dt = (time.perf_counter() - t0) / n
+        out[key] = {"workload": f"configs/sepformer_base.yml SepFormer training step, B=1, 16 s @ 8 kHz (T={T}), bf16, dropout 0.1, fused "
+                                "forward + PIT neg-SNR + backward + clip 5.0 + Adam (DualPathTrainer)", "metric": "train audio-sec/sec",
+                    "value": T / SR / sec, "unit": "audio-s/s", "ms_per_step": 1e3 * sec, "samples_per_s": 1.0 / sec,
+                    "gpu_launches_per_step": int(tr.launches_per_step),
+                    "e2e": {"value": T / SR / dt, "unit": "audio-s/s", "ms_per_step": 1e3 * dt, "h2d_bytes_per_step": int(mix_h.numel() * 4 + tgt_h.numel() * 4),
+                            "d2h_bytes_per_step": 4, "loss": loss},
+                    "parity": "gradients / dropout replay: tests/test_gpu_sepformer.py; forward at this shape: C5.parity"}
+        del m, tr
+        torch.cuda.empty_cache()
+    # the eager-PyTorch-on-B200 bar for the headline training step (SURVEY 2.2: the cuDNN LSTM is the kernel to beat)
+    if ref is not None:
+        out["C2_eager_b200"] = eager_train_step(ref[0], ref[1], CFG_DPRNN, args.batch, flush)
+    return out
 
 
 def run_ours(args):
@@ -213,7 +567,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     torch.manual_seed(0)
-    model = TasNet(sample_rate=SR, **CFG).to(dev)
+    model = TasNet(sample_rate=SR, **CFG_DPRNN).to(dev)
     model.precision = args.precision
     model.train()
     trainer = DualPathTrainer(model, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False), lr=1e-3, max_norm=5.0,
@@ -253,7 +607,8 @@ def run_ours(args):
         tgt_s.copy_(tgt_h, non_blocking=True)
         last["loss"] = trainer.step(mix_s, tgt_s).item()  # D2H read of the step's result
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_device()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -263,6 +618,17 @@ def run_ours(args):
     sec_e2e = timed(step_e2e, args.steps)
     value = args.batch * world * args.steps / sec
     e2e = args.batch * world * args.steps / sec_e2e
+    launches = trainer.launches_per_step
+    # strong scaling: the global batch stays 16, every rank takes 16 / N utterances
+    strong = None
+    if world > 1 and args.batch % world == 0:
+        bs = args.batch // world
+        ms_, ts_ = mix_d[:bs].contiguous(), tgt_d[:bs].contiguous()
+        for _ in range(3):
+            trainer.step(ms_, ts_)
+        sec_s = timed(lambda: trainer.step(ms_, ts_), args.steps)
+        strong = {"global_batch": args.batch, "batch_per_gpu": bs, "value": args.batch * args.steps / sec_s, "unit": "samples/s",
+                  "ms_per_step": 1e3 * sec_s / args.steps, "scaling": "strong"}
     # informational: the same step in the other precision mode (never the headline value)
     other = "bf16" if args.precision == "fp32" else "fp32"
     model.precision = other
@@ -274,49 +640,67 @@ def run_ours(args):
 
     if rank == 0:
         pk, pk_kind = peaks()
-        f_sec, k_sec, k_flops, k_hbm = time_recurrence(model, args.batch, args.precision)
+        rec = time_recurrence(model, args.batch, args.precision)
+        f_sec, k_sec, i_sec, k_flops, k_hbm, k_hbm_inf = rec
         tf = k_flops / k_sec / 1e12
         cpu = None
+        configs = None
+        if world == 1 and not args.no_configs:
+            del trainer
+            torch.cuda.empty_cache()
+            try:
+                configs = other_configs(args, pk, pk_kind, rec)
+            except Exception as exc:  # the headline line must survive a failure in the extra block, loudly
+                import traceback
+
+                configs = {"error": f"{type(exc).__name__}: {exc}"[:300], "trace": traceback.format_exc()[-600:]}
         if world == 1 and not args.no_cpu_baseline:
-            stepf = cpu_reference_step_fn(1)
+            cb = 4
+            stepf, kind = cpu_reference_step_fn(cb)
             stepf()
             t0 = time.perf_counter()
-            n = 3
+            n = 2
             for _ in range(n):
                 stepf()
             dt = time.perf_counter() - t0
-            cpu = {"value": n / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"{n} training steps of 1 utterance (4 s @ 8 kHz) after 1 warm-up; oracle port of the reference, torch CPU"}
+            cpu = {"value": cb * n / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": kind,
+                   "sample": f"{n} training steps of {cb} utterances (4 s @ 8 kHz) after 1 warm-up; "
+                             + ("unmodified look2hear TasNet + PITLossWrapper (baseline/_ref)" if kind == "reference" else "oracle port of the reference")
+                             + f", torch CPU, {os.cpu_count()} threads; the reference arm (--impl reference) runs the full batch of {args.batch}"}
         line = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (bf16x3 split tensor-core products, fp32 accumulate/state)" if args.precision == "fp32" else "bf16",
             "data": "synthetic",
             "config": {"workload": "configs/dprnn_wsj0.yml DPRNN training step, 4 s @ 8 kHz (configs[1])", "batch_per_gpu": args.batch,
-                       "global_batch": args.batch * world, "samples": int(SR * SECONDS), "parallelism": f"dp{world}",
-                       "l2": "per-step working set (~9.6 GB of saved activations at batch 16) is far larger than the 126 MB L2"},
+                       "global_batch": args.batch * world, "samples": T4S, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (~9.6 GB of saved activations at batch 16) is far larger than the 126 MB L2; the forward-only "
+                             "configs flush the L2 (256 MiB memset) between timed iterations"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(mix_h.numel() * 4 + tgt_h.numel() * 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * sec_e2e / args.steps, "loss": last.get("loss")},
-            "gpu_launches": trainer.launches_per_step * args.steps,
+            "gpu_launches": launches * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "lstm_bwd_ks_kernel (persistent BiLSTM BPTT recurrence, intra-chunk pass; largest single share of the step: "
-                                   "the recurrence kernels fwd + bwd are ~57% of it)", "bound": "hbm",
+            "roofline": {"kernel": "BiLSTM BPTT recurrence (persistent, intra-chunk pass; largest single share of the step: the recurrence "
+                                   "kernels fwd + bwd are ~57% of it)", "bound": "hbm",
                          "achieved": k_hbm / k_sec / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": k_hbm / k_sec / 1e9 / pk["hbm_gbs"],
                          "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.batch),
                          "peak_source": f"{pk_kind} HBM copy bandwidth (kernel timed alone)", "ms_per_launch": 1e3 * k_sec,
                          "algorithmic_bytes_per_launch": k_hbm, "tensor_tflops": tf, "tensor_frac": tf / pk["bf16_tflops"],
-                         "forward_kernel": {"kernel": "lstm_fwd_pipe_kernel (same pass, forward, training mode)", "ms_per_launch": 1e3 * f_sec,
+                         "forward_kernel": {"kernel": "BiLSTM recurrence forward (same pass, training mode)", "ms_per_launch": 1e3 * f_sec,
                                             "achieved": k_hbm / f_sec / 1e9, "frac": k_hbm / f_sec / 1e9 / pk["hbm_gbs"],
                                             "traffic": TRAFFIC_FWD_BYTES_PER_LAUNCH.get(args.batch)},
                          "note": "84 MB per utterance (SURVEY 8d: bwd reads activated gates, c_t and dH and writes d(pre-activations); fwd "
-                                 "reads G and writes gates + c_t + H); the kernels are bound by the per-step dependent chain (tensor-core "
-                                 "issue, shared-memory operand traffic, MUFU), not by HBM: both fractions reported"},
+                                 "reads G and writes gates + c_t + H)"},
             "cpu_baseline": cpu,
             "other_precision_mode": {"dtype": other, "value": other_value, "unit": "samples/s",
                                      "note": "informational only: the same training step with single bf16 tensor-core products and "
                                              "tanh.approx gates (forward within 0.05 dB PIT-SI-SNR of the fp32 reference); the headline "
                                              "value above is the fp32-parity mode" if other == "bf16" else "informational only"},
         }
+        if strong is not None:
+            line["strong"] = strong
+        if configs is not None:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -332,6 +716,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("DUALPATH_PRECISION", "fp32"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1/C3/C4/C5 block (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
