@@ -48,7 +48,8 @@ constexpr size_t PK_WIHT_HI = PK_WB_LO + 2 * 8192 * 16;
 constexpr size_t PK_WIHT_LO = PK_WIHT_HI + 65536 * 2;
 constexpr size_t PK_PROJT_HI = PK_WIHT_LO + 65536 * 2;
 constexpr size_t PK_PROJT_LO = PK_PROJT_HI + 16384 * 2;
-constexpr size_t PK_BYTES = PK_PROJT_LO + 16384 * 2;
+constexpr size_t PK_REC5 = PK_PROJT_LO + 16384 * 2;          // tcgen05 recurrence images (lstm_rec5.cu): 1 MB
+constexpr size_t PK_BYTES = PK_REC5 + 8 * 131072;
 
 struct LstmPackView {
     const __nv_bfloat16* wih_hi;
@@ -74,6 +75,7 @@ LstmPackView view_pack(const void* pack) {
     v.wiht_lo = reinterpret_cast<const __nv_bfloat16*>(b + PK_WIHT_LO);
     v.projt_hi = reinterpret_cast<const __nv_bfloat16*>(b + PK_PROJT_HI);
     v.projt_lo = reinterpret_cast<const __nv_bfloat16*>(b + PK_PROJT_LO);
+    v.rec.rec5 = b + PK_REC5;
     return v;
 }
 LstmPackOut out_pack(void* pack) {
@@ -90,6 +92,7 @@ LstmPackOut out_pack(void* pack) {
     o.wiht_lo = reinterpret_cast<__nv_bfloat16*>(b + PK_WIHT_LO);
     o.projt_hi = reinterpret_cast<__nv_bfloat16*>(b + PK_PROJT_HI);
     o.projt_lo = reinterpret_cast<__nv_bfloat16*>(b + PK_PROJT_LO);
+    o.rec5 = b + PK_REC5;
     return o;
 }
 
@@ -155,6 +158,10 @@ int dp_set_attention_forward(int mode) {
 }
 int dp_set_lstm_pipeline(int mode) {
     if (lstm_set_pipeline(mode) != 0) return fail("dp_set_lstm_pipeline: 0 (plain 8-warp kernels), 1 (automatic), 2 (pipelined sequence groups) or 3 (16-warp kernel)");
+    return 0;
+}
+int dp_set_lstm_tcgen05(int mode) {
+    if (lstm_set_rec5(mode) != 0) return fail("dp_set_lstm_tcgen05: 0 (mma.sync recurrence kernels), 1 (automatic) or 2 (tcgen05 recurrence kernels always)");
     return 0;
 }
 const char* dp_last_error(void) { return g_err; }

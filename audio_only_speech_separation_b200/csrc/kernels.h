@@ -152,6 +152,7 @@ struct LstmPack {  // per ProjRNN, both directions
     const uint4* whh_f_lo;
     const uint4* whh_b_hi;  // [2][8][32][32]   fragment-ordered W_hh^T (backward recurrence A operand)
     const uint4* whh_b_lo;
+    const void* rec5;       // weight images of the tcgen05 recurrence (lstm_rec5.cu), null: mma.sync kernels only
 };
 // G: [P,1024] gate pre-activations (packed column order dir*512 + unit*4 + gate); overwritten with the
 // activated gates when save != 0.  H: [P,256] = [h_fwd | h_bwd].  Cst: [P,256] cell states (save only).
@@ -185,6 +186,18 @@ cudaError_t launch_lstm_fused_fwd(const void* pack, const float* bias, const __n
 cudaError_t launch_lstm_bwd(const LstmPack& w, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,
                             cudaStream_t st, __nv_bfloat16* dG_hi = nullptr, __nv_bfloat16* dG_lo = nullptr);
 
+// ---- tcgen05 recurrence (lstm_rec5.cu): same interface, W_hh hi in tensor memory, lo in shared memory ----
+size_t lstm_rec5_pack_bytes();
+cudaError_t launch_pack_lstm_rec5(const float* const w_hh[2], void* pack, cudaStream_t st);
+// 0: never, 1: automatic (passes with enough sequences), 2: always
+int lstm_set_rec5(int mode);
+int lstm_get_rec5();
+bool lstm_rec5_wanted(const SeqMap& m);
+cudaError_t launch_lstm_rec5_fwd(const void* pack, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, cudaStream_t st,
+                                 const LstmPlanes& pl);
+cudaError_t launch_lstm_rec5_bwd(const void* pack, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,
+                                 cudaStream_t st, __nv_bfloat16* dG_hi, __nv_bfloat16* dG_lo);
+
 // Build all packed forms of one ProjRNN's LSTM weights from the natural fp32 parameters.
 struct LstmPackOut {
     __nv_bfloat16* wih_hi;  // [1024,64] packed row order
@@ -198,6 +211,7 @@ struct LstmPackOut {
     __nv_bfloat16* wiht_lo;
     __nv_bfloat16* projt_hi;  // [256,64] = proj.weight transposed (optional, needs proj_w)
     __nv_bfloat16* projt_lo;
+    void* rec5;               // lstm_rec5_pack_bytes() bytes (optional)
 };
 cudaError_t launch_pack_lstm(const float* const w_ih[2], const float* const w_hh[2], const float* const b_ih[2],
                              const float* const b_hh[2], const float* proj_w, const LstmPackOut& o, cudaStream_t st);

@@ -898,6 +898,7 @@ cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, c
     LstmPlanes pl;
     memset(&pl, 0, sizeof(pl));
     if (planes) pl = *planes;
+    if (w.rec5 != nullptr && lstm_rec5_wanted(m)) return launch_lstm_rec5_fwd(w.rec5, G, H, Cst, m, split, save, st, pl);
     const int nt = lstm_pick_nt(m.nseq);
     int pipe = g_lstm_pipeline;
     // automatic (measured on B200 with tests/tools/time_recurrence.py, training mode, intra / inter pass):
@@ -928,7 +929,10 @@ cudaError_t launch_pack_lstm(const float* const w_ih[2], const float* const w_hh
     a.o = o;
     int total = 65536 * 3 + 1024 + 65536 + 16384;
     pack_lstm_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a);
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (o.rec5 != nullptr) return launch_pack_lstm_rec5(w_hh, o.rec5, st);
+    return cudaSuccess;
 }
 
 cudaError_t launch_unpack_lstm_grads(const float* d_wih_pack, const float* d_whh_pack, const float* d_bias_pack,

@@ -38,6 +38,10 @@ int dp_set_fused_lstm(int mode);
  * 3 = 16-warp kernel (8 hidden units per warp, 128 registers, four warps per scheduler); 1 (default) = automatic by pass size and
  * precision.  All variants perform the same arithmetic in the same order per cell. */
 int dp_set_lstm_pipeline(int mode);
+/* LSTM recurrence (forward and BPTT, gc3_basics.py:16,22) on tcgen05 / tensor memory (csrc/lstm_rec5.cu: W_hh hi half resident in
+ * tensor memory, lo half in shared memory, 32 sequences per CTA): 1 (default) = automatic (passes with >= 256 sequences per direction),
+ * 2 = always, 0 = never (the register-stationary mma.sync kernels selected by dp_set_lstm_pipeline). */
+int dp_set_lstm_tcgen05(int mode);
 /* Attention forward kernel of the DPTNet / SepFormer engines where both apply (sequences <= 256): 1 = tcgen05 kernel (TMA-fed, scores in
  * tensor memory), 2 = warp-level tensor-core kernel (online softmax, fp32 QKV in), 0 (default) = the faster one per shape and precision
  * as measured (tests/tools/time_attention.py). */
