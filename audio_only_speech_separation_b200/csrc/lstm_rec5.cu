@@ -69,8 +69,30 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 __device__ __forceinline__ void sts16(uint32_t saddr, __nv_bfloat16 v) {
     asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(saddr), "h"(*reinterpret_cast<const uint16_t*>(&v)) : "memory");
 }
+__device__ __forceinline__ unsigned lds32(uint32_t saddr) {
+    unsigned v;
+    asm("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(saddr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts64(uint32_t saddr, const uint2& v) {
     asm volatile("st.shared.v2.b32 [%0], {%1,%2};\n" ::"r"(saddr), "r"(v.x), "r"(v.y) : "memory");
+}
+// bf16 hi / lo split of two values with PACKED conversions only (cvt.rn.bf16x2.f32 runs on the FMA-side pipe; the scalar
+// cvt.rn.bf16.f32 is an XU instruction and competes with ex2 / rcp): hi = bf16(a) | bf16(b) << 16, lo = bf16(a - hi_a) | bf16(b - hi_b) << 16
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo_elem, float hi_elem) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+    return d;
+}
+__device__ __forceinline__ void split_pair_packed(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = cvt_bf16x2(a, b);
+    lo = cvt_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+__device__ __forceinline__ void sts16r(uint32_t saddr, uint32_t v) {   // low 16 bits of v
+    asm volatile("{\n .reg .b16 lo, hi;\n mov.b32 {lo, hi}, %1;\n st.shared.b16 [%0], lo;\n}\n" ::"r"(saddr), "r"(v) : "memory");
 }
 __device__ __forceinline__ float ld_f_ordered(const float* p) {
     float v;
@@ -94,9 +116,9 @@ __device__ __forceinline__ void r5_wait(uint64_t* bar, uint32_t parity) {
     long long t0 = 0;
     while (true) {
         asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)   // suspend-time hint (ns): the warp sleeps in hardware instead of spinning
             : "memory");
         if (done) break;
         const long long now = clock64();
@@ -355,9 +377,10 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
         const bool has_h = p.H != nullptr;
         // h tile offsets of cells (k, e): row n = 8k + 2c + e -> 1024 k + (2c + e) * 128, swizzle term (chunk ^ (2c + e)) << 4 (independent of k)
         const int chunk = (unit & 63) >> 3;
-        const uint32_t hs_s = smem_u32(hs) + (uint32_t)((unit >> 6) * KB + (unit & 7) * 2);
-        const uint32_t hoff0 = hs_s + (uint32_t)((2 * c) * 128 + ((chunk ^ (2 * c)) << 4));
-        const uint32_t hoff1 = hs_s + (uint32_t)((2 * c + 1) * 128 + ((chunk ^ (2 * c + 1)) << 4));
+        // even unit of a pair stores sequence 2c of both units, odd unit sequence 2c + 1: 4 bytes at the even unit's column
+        const int odd = u8 & 1, rowe = 2 * c + odd;
+        const uint32_t hrow = smem_u32(hs) + (uint32_t)((unit >> 6) * KB + (u8 & 6) * 2 + rowe * 128 + ((chunk ^ rowe) << 4));
+        const uint32_t sel_send = odd ? 0x5410u : 0x7632u, sel_hi = odd ? 0x3254u : 0x5410u, sel_lo = odd ? 0x3276u : 0x7610u;
         // the step's gate pre-activations (one 128-bit word per cell) are staged one step ahead into this thread's own shared-memory slots
         const uint32_t gst_s = smem_u32(smem + OFF_G) + (uint32_t)(((warp - 4) * 256 + lane) * 16);
         const int kmax = (nv + 7) >> 3;   // sequence octets in use (warp-uniform)
@@ -394,6 +417,7 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (k < kmax) {
+                    float hh[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int i = 2 * k + e;
@@ -405,18 +429,22 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
                         const float og = sigmoid_cell<SPLIT>(__uint_as_float(rb[4 * k + 2 + e]) + gp.w);
                         const float cc = fmaf(fg, cst[i], ig * gg);
                         cst[i] = cc;
-                        const float hh = og * tanh_cell<SPLIT>(cc);
+                        hh[e] = og * tanh_cell<SPLIT>(cc);
                         const size_t pos = (size_t)(sb[i] + toff);
-                        if (has_h) stg_pred(Hc + pos * 256, hh, vld);
+                        if (has_h) stg_pred(Hc + pos * 256, hh[e], vld);
                         if (SAVE) {
                             stg_pred(Cc + pos * 256, cc, vld);
                             stg_pred(reinterpret_cast<float4*>(Gc + pos * 1024), ig, fg, gg, og, vld);
                         }
-                        const __nv_bfloat16 hb = __float2bfloat16_rn(hh);
-                        const uint32_t off = (e ? hoff1 : hoff0) + (uint32_t)(k * 1024);
-                        sts16(off, hb);
-                        if (SPLIT) sts16(off + PLANE, __float2bfloat16_rn(hh - __bfloat162float(hb)));
                     }
+                    // h -> bf16 hi / lo with packed conversions; the two lanes of a unit pair (lane ^ 4) swap one sequence each, so that every
+                    // lane stores ONE 32-bit word (two neighbouring units of one sequence) per plane: no 16-bit stores, no bank conflicts
+                    uint32_t Hw, Lw = 0u;
+                    if (SPLIT) split_pair_packed(hh[0], hh[1], Hw, Lw);
+                    else Hw = cvt_bf16x2(hh[0], hh[1]);
+                    const uint32_t recv = __shfl_xor_sync(0xffffffffu, __byte_perm(Hw, Lw, sel_send), 4);
+                    sts32(hrow + (uint32_t)(k * 1024), __byte_perm(Hw, recv, sel_hi));
+                    if (SPLIT) sts32(hrow + (uint32_t)(k * 1024 + PLANE), __byte_perm(Lw, recv, sel_lo));
                 }
             }
             proxy_fence_async();  // h slice (generic-proxy stores) -> visible to the tensor core's async proxy
@@ -528,19 +556,16 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_bwd_kernel(const R5Ar
         const int chunk = (unit & 15) >> 1;
         const uint32_t ds_s = smem_u32(ds) + (uint32_t)((unit >> 4) * KB + (unit & 1) * 8 + part * 1024);
         const int cnt = nv > part ? (nv - part + 3) >> 2 : 0;   // sequences of this octet (warp-uniform)
-        unsigned sb[8];
+        const uint32_t sb_s = smem_u32(sbase) + (uint32_t)(part * 32);   // position bases stay in shared memory (register budget)
         float dcs[8], ct[8], bsum[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            sb[i] = (unsigned)sbase[8 * part + i];
-            dcs[i] = 0.f;
-        }
+        for (int i = 0; i < 8; ++i) dcs[i] = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) bsum[i] = 0.f;
         const int dstep = dir ? (int)s_t : -(int)s_t;               // reverse of the forward visiting order
         unsigned toff = dir ? 0u : (unsigned)((len - 1) * (int)s_t);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ct[i] = i < cnt ? ld_f_ordered(Cc + (size_t)(sb[i] + toff) * 256) : 0.f;
+        for (int i = 0; i < 8; ++i) ct[i] = i < cnt ? ld_f_ordered(Cc + (size_t)(lds32(sb_s + i * 4) + toff) * 256) : 0.f;
         for (int s = 0; s < len; ++s) {
             const bool first = (s == len - 1);       // the forward pass's first step: c_prev = 0
             float4 a[8];
@@ -548,17 +573,17 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_bwd_kernel(const R5Ar
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (i < cnt) {
-                    const size_t pos = (size_t)(sb[i] + toff);
+                    const size_t pos = (size_t)(lds32(sb_s + i * 4) + toff);
                     a[i] = ld_f4_ordered(Gc + pos * 1024);
                     dh[i] = ld_f_ordered(Dc + pos * 256);
-                    cp[i] = first ? 0.f : ld_f_ordered(Cc + (size_t)(sb[i] + toff + (unsigned)dstep) * 256);
+                    cp[i] = first ? 0.f : ld_f_ordered(Cc + (size_t)(lds32(sb_s + i * 4) + toff + (unsigned)dstep) * 256);
                 }
             }
             if (!first) {   // next step's lines -> L2
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if (i < cnt) {
-                        const size_t pos = (size_t)(sb[i] + toff + (unsigned)dstep);
+                        const size_t pos = (size_t)(lds32(sb_s + i * 4) + toff + (unsigned)dstep);
                         prefetch_l2(Gc + pos * 1024);
                         prefetch_l2(Dc + pos * 256);
                     }
@@ -589,9 +614,9 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_bwd_kernel(const R5Ar
                     dg.w = dhh * tc * a[i].w * (1.f - a[i].w);
                     ct[i] = cp[i];
                     uint2 hi, lo;
-                    split_pair(dg.x, dg.y, hi.x, lo.x);
-                    split_pair(dg.z, dg.w, hi.y, lo.y);
-                    const size_t pos = (size_t)(sb[i] + toff);
+                    split_pair_packed(dg.x, dg.y, hi.x, lo.x);
+                    split_pair_packed(dg.z, dg.w, hi.y, lo.y);
+                    const size_t pos = (size_t)(lds32(sb_s + i * 4) + toff);
                     if (planes) {
                         *reinterpret_cast<uint2*>(Ph + pos * 1024) = hi;
                         if (SPLIT && planes_lo) *reinterpret_cast<uint2*>(Pl + pos * 1024) = lo;
