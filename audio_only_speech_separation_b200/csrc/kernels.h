@@ -192,7 +192,7 @@ cudaError_t launch_pack_lstm_rec5(const float* const w_hh[2], void* pack, cudaSt
 // 0: never, 1: automatic (passes with enough sequences), 2: always
 int lstm_set_rec5(int mode);
 int lstm_get_rec5();
-bool lstm_rec5_wanted(const SeqMap& m);
+bool lstm_rec5_wanted(const SeqMap& m, bool split, bool backward);
 cudaError_t launch_lstm_rec5_fwd(const void* pack, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, cudaStream_t st,
                                  const LstmPlanes& pl);
 cudaError_t launch_lstm_rec5_bwd(const void* pack, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,

@@ -898,7 +898,7 @@ cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, c
     LstmPlanes pl;
     memset(&pl, 0, sizeof(pl));
     if (planes) pl = *planes;
-    if (w.rec5 != nullptr && lstm_rec5_wanted(m)) return launch_lstm_rec5_fwd(w.rec5, G, H, Cst, m, split, save, st, pl);
+    if (w.rec5 != nullptr && lstm_rec5_wanted(m, split, false)) return launch_lstm_rec5_fwd(w.rec5, G, H, Cst, m, split, save, st, pl);
     const int nt = lstm_pick_nt(m.nseq);
     int pipe = g_lstm_pipeline;
     // automatic (measured on B200 with tests/tools/time_recurrence.py, training mode, intra / inter pass):

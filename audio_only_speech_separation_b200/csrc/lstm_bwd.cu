@@ -457,7 +457,7 @@ int lstm_seqs_per_cta(int nseq, int slots);
 cudaError_t launch_lstm_bwd(const LstmPack& w, float* G, const float* Cst, const float* dH, float* dbias, const SeqMap& m, bool split,
                             cudaStream_t st, __nv_bfloat16* dG_hi, __nv_bfloat16* dG_lo) {
     if (m.nseq <= 0 || m.len <= 0) return cudaSuccess;
-    if (w.rec5 != nullptr && lstm_rec5_wanted(m)) return launch_lstm_rec5_bwd(w.rec5, G, Cst, dH, dbias, m, split, st, dG_hi, dG_lo);
+    if (w.rec5 != nullptr && lstm_rec5_wanted(m, split, true)) return launch_lstm_rec5_bwd(w.rec5, G, Cst, dH, dbias, m, split, st, dG_hi, dG_lo);
     switch (lstm_pick_nt(m.nseq)) {
         case 1: return bwd_launch<1>(w, G, Cst, dH, dbias, m, split, dG_hi, dG_lo, st);
         case 2: return bwd_launch<2>(w, G, Cst, dH, dbias, m, split, dG_hi, dG_lo, st);

@@ -711,11 +711,17 @@ int lstm_set_rec5(int mode) {
 int lstm_get_rec5() { return g_rec5; }
 
 // The tcgen05 recurrence handles one wave of 32-sequence tiles per direction; larger passes run several waves.
-bool lstm_rec5_wanted(const SeqMap& m) {
+// Automatic choice, measured on B200 (tests/tools/time_rec5.py, intra / inter pass, training mode, us):
+//   B = 16 fp32: forward 395 / 357 against 503 / 420 (mma.sync), BPTT 348 / 310 against 645 / 545
+//   B = 16 bf16: forward 378 / 379 against 320 / 297 -> mma.sync, BPTT 290 / 275 against 448 / 393
+//   B = 32 fp32: forward 1115 / 912 against 1031 / 847 (two waves of 32-sequence tiles) -> mma.sync, BPTT 883 / 736 against 1309 / 1082
+bool lstm_rec5_wanted(const SeqMap& m, bool split, bool backward) {
     if (g_rec5 == 0) return false;
     if (g_rec5 == 2) return true;
     if (lstm_get_pipeline() != 1) return false;   // an explicitly selected mma.sync variant (dp_set_lstm_pipeline) is honoured
-    return m.nseq >= 256;   // small passes: the evenly spread mma.sync kernels keep more SMs busy
+    if (m.nseq < 256) return false;               // small passes: the evenly spread mma.sync kernels keep more SMs busy
+    if (backward) return true;
+    return split && ceil_div(m.nseq, R5_NS) <= 74;   // forward: fp32-parity mode, one wave of tiles
 }
 
 cudaError_t launch_lstm_rec5_fwd(const void* pack, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, cudaStream_t st,

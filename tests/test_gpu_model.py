@@ -311,8 +311,17 @@ def test_multi_wave_batch_properties(manifest):
         loss.backward()
         return loss.item(), torch.cat([p.grad.flatten() for p in m.parameters()]).clone()
 
-    l_all, g_all = grads(slice(0, 40))
-    l_a, g_a = grads(slice(0, 20))
-    l_b, g_b = grads(slice(20, 40))
-    assert abs(l_all - 0.5 * (l_a + l_b)) < 1e-5 * max(1.0, abs(l_all))
-    assert rel_l2(g_all, 0.5 * (g_a + g_b)) < 2e-5
+    from audio_only_speech_separation_b200 import _lib
+
+    # automatic kernel choice: B = 40 runs the mma.sync forward recurrence (two waves of tiles), B = 20 the tcgen05 one (other summation
+    # order, ~1e-5 on the activations, amplified by 12 layers of backward); with one kernel family forced the sums agree to 2e-5
+    for mode, tol in ((1, 1e-4), (2, 2e-5), (0, 2e-5)):
+        _lib.check(_lib.lib().dp_set_lstm_tcgen05(mode))
+        try:
+            l_all, g_all = grads(slice(0, 40))
+            l_a, g_a = grads(slice(0, 20))
+            l_b, g_b = grads(slice(20, 40))
+        finally:
+            _lib.check(_lib.lib().dp_set_lstm_tcgen05(1))
+        assert abs(l_all - 0.5 * (l_a + l_b)) < 1e-5 * max(1.0, abs(l_all)), mode
+        assert rel_l2(g_all, 0.5 * (g_a + g_b)) < tol, mode
