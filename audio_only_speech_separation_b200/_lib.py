@@ -80,6 +80,10 @@ PROTOTYPES = {
     "dp_pit_loss_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "dp_pit_loss_backward": (_i, [_p, _p, _i, _i, _p, _f, _p, _p]),
     "dp_pit_reorder": (_i, [_p, _p, _p, _i, _i, _p]),
+    "dp_pitn_loss_workspace_bytes": (_i64, [_i, _i]),
+    "dp_pitn_loss_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "dp_pitn_loss_backward": (_i, [_p, _p, _i, _i, _i, _p, _f, _p, _p]),
+    "dp_pitn_reorder": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "dp_adam_clip_step": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p]),
     "dp_tasnet_create": (_i, [C.POINTER(TasnetConfig), C.POINTER(_i64), _i, _i64, C.POINTER(_p)]),
     "dp_tasnet_destroy": (None, [_p]),

@@ -390,6 +390,40 @@ int dp_pit_reorder(const float* est, const int32_t* perm, float* out, int B, int
     return 0;
 }
 
+// general n_src: workspace = sums [B][2N] | second [B][2N*N+N] | noise [B][N*N] (fp64) | coef [B][N][3] (fp32)
+namespace {
+struct PitNView { double* sums; double* second; double* noise; float* coef; };
+PitNView pitn_view(void* ws, int B, int N) {
+    char* b = static_cast<char*>(ws);
+    PitNView v;
+    v.sums = reinterpret_cast<double*>(b);
+    v.second = v.sums + (size_t)B * 2 * N;
+    v.noise = v.second + (size_t)B * (2 * N * N + N);
+    v.coef = reinterpret_cast<float*>(v.noise + (size_t)B * N * N);
+    return v;
+}
+}  // namespace
+int64_t dp_pitn_loss_workspace_bytes(int B, int N) { return (int64_t)B * ((3 * N * N + 3 * N) * 8 + 3 * N * 4) + 64; }
+int dp_pitn_loss_forward(const float* est, const float* tgt, int B, int N, int T, int sdr_type, int threshold_byloss, void* ws, float* pw,
+                         float* loss, int32_t* perm, void* stream) {
+    if (sdr_type < 0 || sdr_type > 2) return fail("dp_pitn_loss_forward: sdr_type must be 0 (snr), 1 (sisdr) or 2 (sdsdr)");
+    if (N < 1 || N > 4) return fail("dp_pitn_loss_forward: n_src must be 1 .. 4 (got %d)", N);
+    PitNView v = pitn_view(ws, B, N);
+    PitLossWs w{v.sums, v.second, v.noise};
+    CK(launch_pitn_loss_fwd(est, tgt, B, N, T, sdr_type, threshold_byloss, w, pw, loss, perm, v.coef, S(stream)));
+    return 0;
+}
+int dp_pitn_loss_backward(const float* est, const float* tgt, int B, int N, int T, const void* ws, float grad_scale, float* d_est, void* stream) {
+    if (N < 1 || N > 4) return fail("dp_pitn_loss_backward: n_src must be 1 .. 4 (got %d)", N);
+    PitNView v = pitn_view(const_cast<void*>(ws), B, N);
+    CK(launch_pitn_loss_bwd(est, tgt, B, N, T, v.sums, v.coef, grad_scale, d_est, S(stream)));
+    return 0;
+}
+int dp_pitn_reorder(const float* est, const int32_t* perm, float* out, int B, int N, int T, void* stream) {
+    CK(launch_reorder_sources_n(est, perm, out, B, N, T, S(stream)));
+    return 0;
+}
+
 int dp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, double* norm2, float grad_scale, float max_norm, float lr,
                       float beta1, float beta2, float eps, int step, float weight_decay, void* stream) {
     if (step < 1) return fail("dp_adam_clip_step: step counts from 1");

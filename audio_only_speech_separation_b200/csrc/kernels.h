@@ -320,7 +320,7 @@ cudaError_t launch_gate_bwd(const float* dg, const float* t1, const float* t2, f
 cudaError_t launch_prelu_bwd(const float* du, const float* x, float* dx, long long n, const float* slope, float* dslope, cudaStream_t st);
 cudaError_t launch_relu_bwd_add(const float* a, const float* b, const float* m, float* out, long long n, cudaStream_t st);
 
-// ---------------- loss (loss.cu) ----------------
+// ---------------- loss (loss.cu: n_src = 2; loss_n.cu: n_src = 1 .. 4) ----------------
 struct PitLossWs {  // device scratch, all double unless noted
     double* sums;    // [B][4]   sum e0,e1,t0,t1
     double* second;  // [B][10]  dot[2][2], dist2[2][2], tt[2]
@@ -330,6 +330,13 @@ struct PitLossWs {  // device scratch, all double unless noted
 // coef [B][2][3] backward coefficients (per estimate: a on (e - mean e), b on (t_j - mean t_j), j index as float)
 cudaError_t launch_pit_loss_fwd(const float* est, const float* tgt, int B, int T, int sdr_type, int threshold_byloss,
                                 const PitLossWs& ws, float* pw, float* loss, int* perm, float* coef, cudaStream_t st);
+// General n_src = N (1..4): sums [B][2N], second [B][2N*N + N], noise [B][N*N]; pw [B,N,N]; perm [B,N] = estimate index per target
+// (find_best_perm_factorial's batch_indices); coef [B][N][3]
+cudaError_t launch_pitn_loss_fwd(const float* est, const float* tgt, int B, int N, int T, int sdr_type, int threshold_byloss, const PitLossWs& ws,
+                                 float* pw, float* loss, int* perm, float* coef, cudaStream_t st);
+cudaError_t launch_pitn_loss_bwd(const float* est, const float* tgt, int B, int N, int T, const double* sums, const float* coef, float grad_scale,
+                                 float* d_est, cudaStream_t st);
+cudaError_t launch_reorder_sources_n(const float* est, const int* perm, float* out, int B, int N, int T, cudaStream_t st);
 cudaError_t launch_pit_loss_bwd(const float* est, const float* tgt, int B, int T, const double* sums, const float* coef,
                                 float grad_scale, float* d_est, cudaStream_t st);
 cudaError_t launch_reorder_sources(const float* est, const int* perm, float* out, int B, int T, cudaStream_t st);

@@ -42,9 +42,32 @@ CFG_DPRNN = dict(enc_dim=64, bn_dim=64, hidden_dim=128, win=16, layer=6, num_spk
 CFG_UNFOLD = dict(CFG_DPRNN, unfold=True)
 CFG_DPTNET = dict(CFG_DPRNN, module="DPTNet")
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full captures under profiles/), by batch
-TRAFFIC_BYTES_PER_LAUNCH = {16: 1294316032}      # lstm_bwd_ks_kernel, profiles/r1_lstm_bwd_v11_full.summary.txt
-TRAFFIC_FWD_BYTES_PER_LAUNCH = {16: 1287374592}  # lstm_fwd_pipe_kernel, profiles/r1_lstm_fwd_v11_full.summary.txt
+TRAFFIC_BYTES_PER_LAUNCH = {16: 1290858752}      # lstm_rec5_bwd_kernel, profiles/r2_rec5_fwd_bwd_v1_full.summary.txt
+TRAFFIC_FWD_BYTES_PER_LAUNCH = {16: 1289721088}  # lstm_rec5_fwd_kernel, same capture
 METRIC = "train samples/sec (DPRNN wsj0, batch 16/GPU, 4 s @ 8 kHz, fwd + PIT-SNR loss + bwd + clip + Adam)"
+
+
+def rec_roofline(b_sec, f_sec, hbm_bytes, flops, pk, pk_kind, batch):
+    """Roofline entry of the dominant kernel family: the persistent BiLSTM recurrence (tcgen05 / tensor-memory kernels of
+    csrc/lstm_rec5.cu), intra-chunk pass at the bench shape, forward (training mode) and BPTT each timed alone; the slower of the
+    two is the headline entry, the other one sits beside it."""
+    note = ("84 MB per utterance (SURVEY 8d: bwd reads activated gates, c_t and dH and writes d(pre-activations); fwd reads G and writes "
+            "gates + c_t + H); 12 forward + 12 BPTT launches per step, together ~47% of it")
+
+    def entry(name, sec, traffic):
+        return {"kernel": name, "bound": "hbm", "achieved": hbm_bytes / sec / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": hbm_bytes / sec / 1e9 / pk["hbm_gbs"], "traffic": traffic, "ms_per_launch": 1e3 * sec,
+                "algorithmic_bytes_per_launch": hbm_bytes}
+
+    fwd = entry("BiLSTM recurrence forward, training mode (lstm_rec5_fwd_kernel: tcgen05.mma, W_hh in tensor memory + shared memory)", f_sec,
+                TRAFFIC_FWD_BYTES_PER_LAUNCH.get(batch))
+    bwd = entry("BiLSTM BPTT recurrence (lstm_rec5_bwd_kernel: tcgen05.mma, W_hh^T in tensor memory + shared memory)", b_sec,
+                TRAFFIC_BYTES_PER_LAUNCH.get(batch))
+    top, other, key = (fwd, bwd, "bptt_kernel") if f_sec >= b_sec else (bwd, fwd, "forward_kernel")
+    tf = flops / max(f_sec, b_sec) / 1e12
+    top.update({"peak_source": f"{pk_kind} HBM copy bandwidth (kernel timed alone)", "tensor_tflops": tf, "tensor_frac": tf / pk["bf16_tflops"],
+                key: other, "note": note})
+    return top
 
 
 def peaks():
@@ -680,17 +703,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * sec_e2e / args.steps, "loss": last.get("loss")},
             "gpu_launches": launches * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "BiLSTM BPTT recurrence (persistent, intra-chunk pass; largest single share of the step: the recurrence "
-                                   "kernels fwd + bwd are ~57% of it)", "bound": "hbm",
-                         "achieved": k_hbm / k_sec / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": k_hbm / k_sec / 1e9 / pk["hbm_gbs"],
-                         "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.batch),
-                         "peak_source": f"{pk_kind} HBM copy bandwidth (kernel timed alone)", "ms_per_launch": 1e3 * k_sec,
-                         "algorithmic_bytes_per_launch": k_hbm, "tensor_tflops": tf, "tensor_frac": tf / pk["bf16_tflops"],
-                         "forward_kernel": {"kernel": "BiLSTM recurrence forward (same pass, training mode)", "ms_per_launch": 1e3 * f_sec,
-                                            "achieved": k_hbm / f_sec / 1e9, "frac": k_hbm / f_sec / 1e9 / pk["hbm_gbs"],
-                                            "traffic": TRAFFIC_FWD_BYTES_PER_LAUNCH.get(args.batch)},
-                         "note": "84 MB per utterance (SURVEY 8d: bwd reads activated gates, c_t and dH and writes d(pre-activations); fwd "
-                                 "reads G and writes gates + c_t + H)"},
+            "roofline": rec_roofline(k_sec, f_sec, k_hbm, k_flops, pk, pk_kind, args.batch),
             "cpu_baseline": cpu,
             "other_precision_mode": {"dtype": other, "value": other_value, "unit": "samples/s",
                                      "note": "informational only: the same training step with single bf16 tensor-core products and "

@@ -160,6 +160,16 @@ int dp_pit_loss_backward(const float* est, const float* tgt, int B, int T, const
 /* pit_wrapper.py:90-94 reordered_sources */
 int dp_pit_reorder(const float* est, const int32_t* perm, float* out, int B, int T, void* stream);
 
+/* The same for n_src = N in 1 .. 4 and every pit_from of pit_wrapper.py:30-88 (pw_mtx / pw_pt build this pair matrix, perm_avg averages
+ * its entries per permutation: matrix.py:22-57,75-106,119-152); permutations in itertools order, first minimum wins
+ * (find_best_perm_factorial, pit_wrapper.py:106-131).  perm[B,N] = estimate index per target (batch_indices). */
+int64_t dp_pitn_loss_workspace_bytes(int B, int N);
+int dp_pitn_loss_forward(const float* est, const float* tgt, int B, int N, int T, int sdr_type, int threshold_byloss, void* ws,
+                         float* pw, float* loss, int32_t* perm, void* stream);
+int dp_pitn_loss_backward(const float* est, const float* tgt, int B, int N, int T, const void* ws, float grad_scale, float* d_est,
+                          void* stream);
+int dp_pitn_reorder(const float* est, const int32_t* perm, float* out, int B, int N, int T, void* stream);
+
 /* ---- optimizer step: clip_grad_norm_(max_norm) + Adam, audio_train.py:48,128 ------------------------------ */
 /* norm2: device fp64 scalar (scratch).  grad_scale is applied to g first (1/world_size after all-reduce SUM). */
 int dp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, double* norm2, float grad_scale,
