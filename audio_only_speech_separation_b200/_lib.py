@@ -80,6 +80,8 @@ PROTOTYPES = {
     "dp_pit_loss_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "dp_pit_loss_backward": (_i, [_p, _p, _i, _i, _p, _f, _p, _p]),
     "dp_pit_reorder": (_i, [_p, _p, _p, _i, _i, _p]),
+    "dp_bss_sdr_workspace_bytes": (_i64, [_i, _i, _i]),
+    "dp_bss_sdr_pit": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "dp_pitn_loss_workspace_bytes": (_i64, [_i, _i]),
     "dp_pitn_loss_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "dp_pitn_loss_backward": (_i, [_p, _p, _i, _i, _i, _p, _f, _p, _p]),

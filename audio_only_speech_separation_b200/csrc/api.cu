@@ -424,6 +424,15 @@ int dp_pitn_reorder(const float* est, const int32_t* perm, float* out, int B, in
     return 0;
 }
 
+int64_t dp_bss_sdr_workspace_bytes(int B, int n_src, int filter_len) { return (int64_t)bss_sdr_workspace_bytes(B, n_src, filter_len); }
+int dp_bss_sdr_pit(const float* est, const float* ref, int B, int n_src, int T, int filter_len, void* ws, float* mean_sdr, float* sdr_mat,
+                   void* stream) {
+    if (n_src < 1 || n_src > 4) return fail("dp_bss_sdr_pit: n_src must be 1 .. 4 (got %d)", n_src);
+    if (filter_len < 1 || filter_len > 512) return fail("dp_bss_sdr_pit: filter_len must be 1 .. 512 (got %d)", filter_len);
+    CK(launch_bss_sdr_pit(est, ref, B, n_src, T, filter_len, ws, mean_sdr, sdr_mat, S(stream)));
+    return 0;
+}
+
 int dp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, double* norm2, float grad_scale, float max_norm, float lr,
                       float beta1, float beta2, float eps, int step, float weight_decay, void* stream) {
     if (step < 1) return fail("dp_adam_clip_step: step counts from 1");

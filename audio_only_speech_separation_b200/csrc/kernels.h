@@ -320,6 +320,11 @@ cudaError_t launch_gate_bwd(const float* dg, const float* t1, const float* t2, f
 cudaError_t launch_prelu_bwd(const float* du, const float* x, float* dx, long long n, const float* slope, float* dslope, cudaStream_t st);
 cudaError_t launch_relu_bwd_add(const float* a, const float* b, const float* m, float* out, long long n, cudaStream_t st);
 
+// ---------------- BSS-eval SDR metric (bss_sdr.cu) ----------------
+size_t bss_sdr_workspace_bytes(int B, int n, int L);
+// mean SDR (dB) per utterance under the best permutation, 512-tap distortion filter; sdr_mat [B,n,n] (ref, est) optional
+cudaError_t launch_bss_sdr_pit(const float* est, const float* ref, int B, int n, int T, int L, void* ws, float* out, float* sdr_mat, cudaStream_t st);
+
 // ---------------- loss (loss.cu: n_src = 2; loss_n.cu: n_src = 1 .. 4) ----------------
 struct PitLossWs {  // device scratch, all double unless noted
     double* sums;    // [B][4]   sum e0,e1,t0,t1

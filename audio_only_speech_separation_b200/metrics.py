@@ -6,8 +6,11 @@
 per utterance (the reference calls ``.item()`` six times per utterance); rows are materialised in ``update()`` / ``final()``.
 
 The ``sdr`` / ``sdr_i`` columns of the reference come from ``fast_bss_eval.sdr_pit_loss`` (BSS-eval SDR with a 512-tap distortion
-filter), a third-party package that is neither vendored in the reference nor installed in this image; they are written as ``nan``
-rather than restated without anything to pin them against.
+filter, wrapper.py:38-41), a third-party package that is neither vendored in the reference nor installed in this image.  Its published
+algorithm is restated as CUDA kernels (csrc/bss_sdr.cu: unit-norm rows, 512-lag correlations, Levinson solve of the Toeplitz systems in
+fp64, coherence -> dB, best permutation) with the reference's argument order kept: ``sdr_pit_loss(clean, estimate)`` passes the clean
+sources as the *estimates* and the network output as the *references* of the projection (and ``(mix, clean)`` for the baseline).
+Pinned against a numpy / scipy fp64 restatement and known-answer properties (tests/test_metrics_sdr.py), not against the package.
 
 ``evaluate`` is ``audio_test.py:72-81`` with utterances of equal length batched together (every utterance is independent through the
 network -- DESIGN.md section 6 -- so a batch of equal-length mixtures gives the per-utterance results of the reference's one-by-one loop).
@@ -20,6 +23,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+from ._lib import check, lib, ptr, require_cuda, stream_ptr
 from .losses.matrix import pit_sdr_forward
 
 CSV_COLUMNS = ["snt_id", "sdr", "sdr_i", "si-snr", "si-snr_i"]
@@ -34,6 +38,22 @@ def pit_si_snr(estimates: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
     return -torch.minimum(ident, swap)
 
 
+def bss_sdr_pit(est: torch.Tensor, ref: torch.Tensor, filter_length: int = 512, return_matrix: bool = False):
+    """``-fast_bss_eval.sdr_pit_loss(est, ref).mean()`` per batch row: ``est, ref [B, n_src, T]`` (fp32, CUDA) -> ``[B]`` mean SDR in dB under
+    the best permutation (device tensor, no host synchronisation); ``return_matrix`` adds the ``[B, n_ref, n_est]`` SDR matrix."""
+    if est.shape != ref.shape or est.ndim != 3:
+        raise TypeError(f"expected est/ref [B,n_src,T]; got {tuple(est.shape)}, {tuple(ref.shape)}")
+    require_cuda(est, "est")
+    require_cuda(ref, "ref")
+    est, ref = est.float().contiguous(), ref.float().contiguous()
+    B, n, T = est.shape
+    ws = torch.empty(lib().dp_bss_sdr_workspace_bytes(B, n, filter_length), device=est.device, dtype=torch.uint8)
+    out = torch.empty(B, device=est.device, dtype=torch.float32)
+    mat = torch.empty(B, n, n, device=est.device, dtype=torch.float32) if return_matrix else None
+    check(lib().dp_bss_sdr_pit(ptr(est), ptr(ref), B, n, T, filter_length, ptr(ws), ptr(out), ptr(mat), stream_ptr()), "dp_bss_sdr_pit")
+    return (out, mat) if return_matrix else out
+
+
 class MetricsTracker:
     def __init__(self, save_file: str = ""):
         self.all_sdrs: List[float] = []
@@ -44,7 +64,7 @@ class MetricsTracker:
         self.writer = csv.DictWriter(self.results_csv, fieldnames=CSV_COLUMNS) if self.results_csv else None
         if self.writer:
             self.writer.writeheader()
-        self._pending: List[Tuple[Sequence[str], torch.Tensor, torch.Tensor]] = []   # (keys, si_snr[B], si_snr_i[B]) on the device
+        self._pending: List[Tuple] = []   # (keys, si_snr[B], si_snr_i[B], sdr[B], sdr_i[B]) on the device
 
     # -- reference interface: one utterance -------------------------------------------------------------------------------
     def __call__(self, mix: torch.Tensor, clean: torch.Tensor, estimate: torch.Tensor, key: str):
@@ -57,18 +77,22 @@ class MetricsTracker:
         if clean.shape != estimate.shape or clean.ndim != 3 or mix.shape != (clean.shape[0], clean.shape[2]):
             raise TypeError(f"expected mix [B,T], clean/estimate [B,n_src,T]; got {tuple(mix.shape)}, {tuple(clean.shape)}, {tuple(estimate.shape)}")
         si = pit_si_snr(estimate, clean)
-        base = pit_si_snr(mix.unsqueeze(1).expand(-1, clean.shape[1], -1).contiguous(), clean)   # the mixture as every estimate (wrapper.py:34)
-        self._pending.append((list(keys), si, si - base))
+        mixes = mix.unsqueeze(1).expand(-1, clean.shape[1], -1).contiguous()   # the mixture as every estimate (wrapper.py:34)
+        base = pit_si_snr(mixes, clean)
+        # wrapper.py:38-40, argument order as written there: sdr_pit_loss(est = clean, ref = estimate), baseline sdr_pit_loss(est = mix, ref = clean)
+        sdr = bss_sdr_pit(clean, estimate)
+        sdr_base = bss_sdr_pit(mixes, clean)
+        self._pending.append((list(keys), si, si - base, sdr, sdr - sdr_base))
 
     def _flush(self):
-        for keys, si, si_i in self._pending:
-            si_h, si_i_h = si.detach().cpu().tolist(), si_i.detach().cpu().tolist()
-            for k, a, b in zip(keys, si_h, si_i_h):
-                row = {"snt_id": k, "sdr": float("nan"), "sdr_i": float("nan"), "si-snr": a, "si-snr_i": b}
+        for keys, si, si_i, sdr, sdr_i in self._pending:
+            cols = [t.detach().cpu().tolist() for t in (si, si_i, sdr, sdr_i)]
+            for k, a, b, c, d in zip(keys, *cols):
+                row = {"snt_id": k, "sdr": c, "sdr_i": d, "si-snr": a, "si-snr_i": b}
                 if self.writer:
                     self.writer.writerow(row)
-                self.all_sdrs.append(float("nan"))
-                self.all_sdrs_i.append(float("nan"))
+                self.all_sdrs.append(c)
+                self.all_sdrs_i.append(d)
                 self.all_sisnrs.append(a)
                 self.all_sisnrs_i.append(b)
         self._pending = []

@@ -170,6 +170,13 @@ int dp_pitn_loss_backward(const float* est, const float* tgt, int B, int N, int 
                           void* stream);
 int dp_pitn_reorder(const float* est, const int32_t* perm, float* out, int B, int N, int T, void* stream);
 
+/* ---- SDR metric of the evaluation loop: -fast_bss_eval.sdr_pit_loss(est, ref).mean() per utterance (metrics/wrapper.py:38-41; the
+ * package is a third-party dependency, its published algorithm is restated: unit-norm rows, 512-lag correlations, Toeplitz solve,
+ * coherence -> dB, best permutation).  mean_sdr[B]; sdr_mat[B,n,n] (reference, estimate) optional. */
+int64_t dp_bss_sdr_workspace_bytes(int B, int n_src, int filter_len);
+int dp_bss_sdr_pit(const float* est, const float* ref, int B, int n_src, int T, int filter_len, void* ws, float* mean_sdr, float* sdr_mat,
+                   void* stream);
+
 /* ---- optimizer step: clip_grad_norm_(max_norm) + Adam, audio_train.py:48,128 ------------------------------ */
 /* norm2: device fp64 scalar (scratch).  grad_scale is applied to g first (1/world_size after all-reduce SUM). */
 int dp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, double* norm2, float grad_scale,

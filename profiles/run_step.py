@@ -22,7 +22,7 @@ ap.add_argument("--mode", default="train")
 ap.add_argument("--warm", type=int, default=2)
 a = ap.parse_args()
 torch.manual_seed(0)
-model = TasNet(sample_rate=8000, **bench.CFG).cuda()
+model = TasNet(sample_rate=8000, **bench.CFG_DPRNN).cuda()
 model.precision = a.precision
 mix, tgt = bench.synthetic(a.batch, 1234)
 mix, tgt = mix.cuda(), tgt.cuda()

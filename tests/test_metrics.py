@@ -17,13 +17,14 @@ def test_tracker_interface_and_csv(tmp_path):
     with pytest.raises(TypeError):
         t.add_batch(torch.zeros(2, 10), torch.zeros(2, 2, 11), torch.zeros(2, 2, 11), ["a", "b"])
     # rows are buffered on the device; inject two by hand to exercise update() / final() without a GPU
-    t._pending.append((["u1", "u2"], torch.tensor([10.0, 12.0]), torch.tensor([9.0, 11.0])))
-    assert t.update() == {"sdr_i": pytest.approx(float("nan"), nan_ok=True), "si-snr_i": 10.0}
+    t._pending.append((["u1", "u2"], torch.tensor([10.0, 12.0]), torch.tensor([9.0, 11.0]), torch.tensor([11.0, 13.0]), torch.tensor([8.0, 10.0])))
+    assert t.update() == {"sdr_i": 9.0, "si-snr_i": 10.0}
     out = t.final()
     assert out["si-snr"] == 11.0 and out["si-snr_i"] == 10.0
     rows = list(csv.DictReader(open(tmp_path / "metrics.csv")))
     assert [r["snt_id"] for r in rows] == ["u1", "u2", "avg", "std"]
-    assert float(rows[2]["si-snr"]) == 11.0 and float(rows[3]["si-snr"]) == 1.0 and math.isnan(float(rows[0]["sdr"]))
+    assert float(rows[2]["si-snr"]) == 11.0 and float(rows[3]["si-snr"]) == 1.0 and float(rows[0]["sdr"]) == 11.0
+    assert float(rows[2]["sdr"]) == 12.0 and float(rows[2]["sdr_i"]) == 9.0
 
 
 def test_evaluate_buckets_by_exact_length():
