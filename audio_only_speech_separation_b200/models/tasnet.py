@@ -250,13 +250,58 @@ class TasNet(BaseModel):
         _lib.require_cuda(x.contiguous(), "TasNet input")
         xin = x.contiguous().float()
         self._sync_flat(xin.device)
-        if self.group_size > 1:
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._uniq)
+        if self.cuda_graph and not needs_grad and not torch.cuda.is_current_stream_capturing():
+            est = self._graph_forward(xin)
+        elif self.group_size > 1:
             est = self._gc_forward(xin)
         else:
             est = _TasNetFunction.apply(self, xin, *self._uniq)
         if est.dtype != input.dtype and input.dtype.is_floating_point:
             est = est.to(input.dtype)
         return est.squeeze(0) if was_one_d else est
+
+    # ---- inference forwards as CUDA graphs -------------------------------------------------------------------------------------------
+    # One forward is 70-odd dependent launches (DESIGN.md sections 5 / 5b); at small batch the GroupComm engine is launch-bound.  The second
+    # forward with the same (batch, samples, precision, weights) is captured (torch.cuda.CUDAGraph: the engine makes no allocation and no
+    # synchronisation, its workspace comes from the graph's private pool) and later calls replay it.  Set ``model.cuda_graph = False`` to opt out.
+    cuda_graph = True
+    _GRAPH_SLOTS = 8
+
+    def _eager_inference(self, xin):
+        if self.group_size > 1:
+            return self._gc_forward(xin)
+        return self._engine_forward(xin, False)[0]
+
+    def _graph_forward(self, xin):
+        if self.group_size == 1:
+            self._ensure_pack()
+        key = (tuple(xin.shape), str(self.precision), self._flat.data_ptr(), tuple(p._version for p in self._uniq), xin.device.index)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        seen = self.__dict__.setdefault("_graph_seen", {})
+        ent = graphs.get(key)
+        if ent is None:
+            if key not in seen:            # first sight of this shape: run it eagerly (variable-length evaluation never pays for a capture)
+                if len(seen) >= 64:
+                    seen.clear()
+                seen[key] = True
+                return self._eager_inference(xin)
+            if len(graphs) >= self._GRAPH_SLOTS:
+                graphs.clear()
+            static_in = xin.clone()
+            side = torch.cuda.Stream(device=xin.device)
+            side.wait_stream(torch.cuda.current_stream(xin.device))
+            with torch.cuda.stream(side):      # warm-up outside the capture (function attributes, lazily loaded kernels)
+                self._eager_inference(static_in)
+            torch.cuda.current_stream(xin.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._eager_inference(static_in)
+            ent = graphs[key] = (g, static_in, static_out)
+        g, static_in, static_out = ent
+        static_in.copy_(xin)
+        g.replay()
+        return static_out.clone()
 
     def get_model_args(self):
         return {"n_src": 2}  # gc3_network.py:186-188

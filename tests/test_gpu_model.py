@@ -325,3 +325,38 @@ def test_multi_wave_batch_properties(manifest):
             _lib.check(_lib.lib().dp_set_lstm_tcgen05(1))
         assert abs(l_all - 0.5 * (l_a + l_b)) < 1e-5 * max(1.0, abs(l_all)), mode
         assert rel_l2(g_all, 0.5 * (g_a + g_b)) < tol, mode
+
+
+def test_cuda_graph_inference_replays_equal_eager(manifest):
+    """Inference forwards are captured as CUDA graphs on their second call per (shape, precision, weights): same bits as the eager engine
+    call, new graph after a weight update, variable lengths stay eager; also for the GroupComm engine."""
+    from audio_only_speech_separation_b200.models import TasNet
+
+    m, _, _ = _model(manifest, "dprnn_wsj0_b2_t8001")
+    m.eval()
+    g = torch.Generator().manual_seed(3)
+    xs = [(torch.randn(2, 8001, generator=g) * 0.1).cuda() for _ in range(3)]
+    with torch.no_grad():
+        m.cuda_graph = False
+        ref = [m(x).clone() for x in xs]
+        m.cuda_graph = True
+        out = [m(x).clone() for x in xs]          # 1st eager, 2nd captures + replays, 3rd replays
+        assert len(m._graphs) == 1
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b)
+        y_short = m(xs[0][:, :5000])              # another length: eager again, no new graph
+        assert y_short.shape == (2, 2, 5000) and len(m._graphs) == 1
+        p = next(iter(m.parameters()))
+        p.mul_(1.01)                              # in-place update bumps the version: the old graph is not reused
+        y_new = m(xs[0])
+        y_new2 = m(xs[0])
+        m.cuda_graph = False
+        assert torch.equal(y_new2, m(xs[0])) and torch.equal(y_new, y_new2) and not torch.equal(y_new, ref[0])
+    torch.manual_seed(0)
+    gc = TasNet(sample_rate=8000, enc_dim=64, bn_dim=64, hidden_dim=128, layer=2, group_size=16, module="DPRNN", context_size=24).cuda().eval()
+    with torch.no_grad():
+        gc.cuda_graph = False
+        r = gc(xs[1])
+        gc.cuda_graph = True
+        outs = [gc(xs[1]) for _ in range(3)]
+    assert all(torch.equal(o, r) for o in outs) and len(gc._graphs) == 1
