@@ -8,7 +8,8 @@
 * epoch  : mean validation loss (per rank, then the mean over ranks), ``ReduceLROnPlateau`` on it          audio_litmodule.py:99-140, optimizers / scheduler config
 * stop   : early stopping (``training.early_stop``: patience, mode min)                                  audio_train.py:95-100
 * output : ``exp_dir/best_model.pth`` = ``model.serialize()`` of the best epoch, ``exp_dir/conf.yml``,    audio_train.py:52-55,141-152
-           ``exp_dir/history.json`` (train / val loss and lr per epoch; the reference logs these to TensorBoard / wandb)
+           ``exp_dir/history.json`` and TensorBoard scalars under ``exp_dir/tensorboard_logs`` (``train_loss``, ``val_loss``, ``lr``,
+           ``learning_rate``, ``val_pit_sisnr`` per epoch: audio_train.py:115-117, audio_litmodule.py:79-141; tb_writer.py)
 
 ``train_batches`` / ``val_batches`` are callables returning an iterable of ``(mixtures [B,T], targets [B,n_src,T], keys)`` per epoch,
 the batch format of the reference's data modules (datas/lrs2datamodule.py:129-184); host tensors are copied to the device here.
@@ -24,6 +25,7 @@ import torch
 
 from . import losses as _losses
 from . import models as _models
+from .tb_writer import ScalarWriter
 from .trainer import DualPathTrainer
 
 
@@ -101,6 +103,7 @@ def fit(config: dict, train_batches: Callable[[int], Iterable], val_batches: Cal
 
         rank = dist.get_rank()
     history, best = [], math.inf
+    tb = ScalarWriter(os.path.join(exp_dir, "tensorboard_logs")) if rank == 0 else None
     for epoch in range(epochs):
         model.train()
         tl, n = torch.zeros((), device=device), 0
@@ -132,8 +135,13 @@ def fit(config: dict, train_batches: Callable[[int], Iterable], val_batches: Cal
             log(f"epoch {epoch}: train_loss {train_l:.4f} val_loss {val_l:.4f} lr {lr_used:.2e}")
             with open(os.path.join(exp_dir, "history.json"), "w") as f:
                 json.dump(history, f, indent=1)
+            for tag, v in (("train_loss", train_l), ("val_loss", val_l), ("lr", lr_used), ("learning_rate", lr_used), ("val_pit_sisnr", -val_l)):
+                tb.add_scalar(tag, v, epoch)
+            tb.flush()
         if stopper.step(val_l):
             if rank == 0:
                 log(f"early stop at epoch {epoch} (no improvement for {stopper.patience} epochs)")
             break
+    if tb is not None:
+        tb.close()
     return history

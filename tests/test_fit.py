@@ -59,6 +59,9 @@ def test_fit_runs_saves_best_checkpoint_and_lowers_the_loss(tmp_path):
     assert all(h["lr"] == 1e-3 for h in hist)
     for f in ("best_model.pth", "conf.yml", "history.json"):
         assert os.path.exists(tmp_path / f), f
+    import glob
+
+    assert len(glob.glob(str(tmp_path / "tensorboard_logs" / "events.out.tfevents.*"))) == 1   # audio_train.py:115-117
     m = BaseModel.from_pretrain(str(tmp_path / "best_model.pth"), sample_rate=8000, **CONFIG["audionet"]["audionet_config"]).cuda().eval()
     with torch.no_grad():
         assert m(data[0][0].cuda()).shape == (2, 2, 4000)
@@ -88,3 +91,29 @@ def test_end_to_end_wav_corpus_to_metrics(tmp_path):
     res = tracker.final()
     assert len(tracker.all_sisnrs) == 6 and all(map(lambda v: v == v, tracker.all_sisnrs_i)) and "si-snr_i" in res
     assert os.path.exists(os.path.join(exp, "metrics.csv"))
+
+
+@pytest.mark.gpu
+def test_fit_runs_sepformer_config(tmp_path):
+    """configs/sepformer_base.yml through fit(): the fused DualPathTrainer step (flat gradient buffer, clip + Adam) on the SepFormer engine,
+    shrunk to one block / one layer per path; dropout is active in train() mode like in the reference."""
+    from audio_only_speech_separation_b200.fit import fit
+    from audio_only_speech_separation_b200.models import BaseModel
+
+    net = dict(encoder_kernel_size=16, encoder_in_nchannels=1, encoder_out_nchannels=256, masknet_chunksize=250, masknet_numlayers=1,
+               masknet_norm="gLN", masknet_numspks=2, intra_numlayers=1, inter_numlayers=1, intra_nhead=8, inter_nhead=8, intra_dffn=1024,
+               inter_dffn=1024, intra_use_positional=True, inter_use_positional=True, intra_norm_before=True, inter_norm_before=True,
+               intra_causal=False, inter_causal=False)
+    cfg = {**CONFIG, "audionet": {"audionet_name": "Sepformer", "audionet_config": net},
+           "loss": {"train": {"loss_func": "PITLossWrapper", "sdr_type": "pairwise_neg_snr", "config": {"pit_from": "pw_mtx", "threshold_byloss": True}},
+                    "val": {"loss_func": "PITLossWrapper", "sdr_type": "pairwise_neg_sisdr", "config": {"pit_from": "pw_mtx", "threshold_byloss": False}}},
+           "optimizer": {"optim_name": "adam", "lr": 0.00015, "weight_decay": 0}}
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(6, 2, 8000, generator=g) * 0.1
+    data = [(src[i:i + 1].sum(1), src[i:i + 1], [f"u{i}"]) for i in range(6)]     # one utterance per batch, as the reference trains it
+    hist = fit(cfg, lambda e: data[:4], lambda e: data[4:], str(tmp_path), max_epochs=4, log=lambda s: None)
+    assert len(hist) == 4 and all(h["train_loss"] == h["train_loss"] and h["val_loss"] == h["val_loss"] for h in hist)
+    assert hist[-1]["train_loss"] < hist[0]["train_loss"]
+    m = BaseModel.from_pretrain(str(tmp_path / "best_model.pth"), sample_rate=8000, **net).cuda().eval()
+    with torch.no_grad():
+        assert m(data[0][0].cuda()).shape == (1, 2, 8000)
