@@ -101,6 +101,9 @@ PROTOTYPES = {
     "dp_gctasnet_workspace_bytes": (_i64, [_p, _i, _i]),
     "dp_gctasnet_forward": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
     "dp_gctasnet_last_launches": (_i, [_p]),
+    "dp_gctasnet_train_workspace_bytes": (_i64, [_p, _i, _i]),
+    "dp_gctasnet_forward_train": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
+    "dp_gctasnet_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "dp_gctasnet_set_lstm_staging": (_i, [_i]),
     "dp_sepformer_create": (_i, [C.POINTER(SepformerConfig), C.POINTER(_i64), _i, _i64, C.POINTER(_p)]),
     "dp_sepformer_destroy": (None, [_p]),

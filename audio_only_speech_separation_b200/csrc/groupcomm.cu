@@ -948,3 +948,909 @@ int dp_gctasnet_set_lstm_staging(int on) {
 }
 
 }  // extern "C"
+
+// =====================================================================================================================================
+// Training: forward that keeps every stage's input, pre-norm tensor, LSTM output and activated gates, and the backward of every stage
+// (grouped DPRNN stack; the grouped DPTNet stack has no backward yet).  Reference: autograd through gc3_network.py:133-184,
+// groupcomm.py:26-45, gc3_basics.py:7-60, dprnn.py:53-88.  The model has ~31 k parameters shared by all groups, so the kernels below are
+// written for clarity (one thread per (position, group) or per (sequence, direction, unit), recomputation instead of extra saves);
+// parameter gradients are accumulated by one generic reduction kernel (gct_wgrad_kernel) or in registers (the recurrent weights).
+// =====================================================================================================================================
+namespace {
+
+struct TacG { float *w1, *b1, *a1, *w2, *b2, *a2, *w3, *b3, *a3, *gamma, *beta; };
+struct RnnG { float *wih[2], *whh[2], *bih[2], *bhh[2], *pw, *pb, *gamma, *beta; };
+TacG tac_g(const dp_gctasnet* h, float* p, int base) {
+    float* q[TAC_N];
+    for (int i = 0; i < TAC_N; ++i) q[i] = p + h->off[base + i];
+    return TacG{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], q[10]};
+}
+RnnG rnn_g(const dp_gctasnet* h, float* p, int base) {
+    RnnG w;
+    for (int d = 0; d < 2; ++d) {
+        w.wih[d] = p + h->off[base + 4 * d];
+        w.whh[d] = p + h->off[base + 4 * d + 1];
+        w.bih[d] = p + h->off[base + 4 * d + 2];
+        w.bhh[d] = p + h->off[base + 4 * d + 3];
+    }
+    w.pw = p + h->off[base + 8]; w.pb = p + h->off[base + 9]; w.gamma = p + h->off[base + 10]; w.beta = p + h->off[base + 11];
+    return w;
+}
+
+__device__ __forceinline__ float block_sum_f(float v, float* sh) {   // sh: 32 floats
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+    return s;
+}
+
+// ---- BiLSTM forward that also saves (i, f, g, o, c) per step: S5 [item = pos * G + g][dir][HG][5] ------------------------------------
+template <int NG, int HG>
+__global__ void __launch_bounds__(128) gct_lstm_kernel(const float* __restrict__ X, float* __restrict__ Hh, float* __restrict__ S5, RnnW w,
+                                                       long long nouter, int G, int len, int qdiv, long long s_hi, long long s_lo, long long s_t) {
+    const int dir = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (int)(i % HG);
+    const long long q = i / HG;
+    const bool active = q < nouter * G;
+    const long long qc = active ? q : nouter * G - 1;
+    const int g = (int)(qc % G);
+    const long long o = qc / G;
+    const long long bp = (o / qdiv) * s_hi + (o % qdiv) * s_lo;
+    float wi[4][NG], wh[4][HG], b[4];
+#pragma unroll
+    for (int gt = 0; gt < 4; ++gt) {
+        const int row = gt * HG + j;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) wi[gt][k] = __ldg(w.wih[dir] + row * NG + k);
+#pragma unroll
+        for (int k = 0; k < HG; ++k) wh[gt][k] = __ldg(w.whh[dir] + row * HG + k);
+        b[gt] = __ldg(w.bih[dir] + row) + __ldg(w.bhh[dir] + row);
+    }
+    const int C = G * NG;
+    float h = 0.f, c = 0.f;
+    int t = dir ? len - 1 : 0;
+    const int dt = dir ? -1 : 1;
+    for (int step = 0; step < len; ++step, t += dt) {
+        const long long pos = bp + (long long)t * s_t;
+        float a[4] = {b[0], b[1], b[2], b[3]};
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            const float xk = X[pos * C + g * NG + k];
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt) a[gt] = fmaf(wi[gt][k], xk, a[gt]);
+        }
+#pragma unroll
+        for (int k = 0; k < HG; ++k) {
+            const float hk = __shfl_sync(0xffffffffu, h, k, HG);
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt) a[gt] = fmaf(wh[gt][k], hk, a[gt]);
+        }
+        const float ig = sigmoid_cell<true>(a[0]), fg = sigmoid_cell<true>(a[1]), gg = tanh_cell<true>(a[2]), og = sigmoid_cell<true>(a[3]);
+        c = fmaf(fg, c, ig * gg);
+        h = og * tanh_cell<true>(c);
+        if (active) {
+            Hh[(pos * G + g) * 2 * HG + dir * HG + j] = h;
+            float* s5 = S5 + (((pos * G + g) * 2 + dir) * HG + j) * 5;
+            s5[0] = ig; s5[1] = fg; s5[2] = gg; s5[3] = og; s5[4] = c;
+        }
+    }
+}
+
+// ---- BPTT of that BiLSTM: thread = (sequence, direction, unit).  dXd [dir][item][NG]: gradient with respect to the LSTM input, one
+// buffer per direction (summed later); the recurrent / input weights and bias gradients are accumulated in registers and reduced per CTA.
+template <int NG, int HG>
+__global__ void __launch_bounds__(128) gct_lstm_bwd_kernel(const float* __restrict__ X, const float* __restrict__ Hh, const float* __restrict__ S5,
+                                                           const float* __restrict__ dHh, float* __restrict__ dXd, RnnW w, RnnG gw,
+                                                           long long nouter, int G, int len, int qdiv, long long s_hi, long long s_lo,
+                                                           long long s_t, long long nitems) {
+    constexpr int NACC = 4 * HG + 4 * NG + 4;
+    __shared__ float acc_sm[HG * NACC];
+    for (int i = threadIdx.x; i < HG * NACC; i += blockDim.x) acc_sm[i] = 0.f;
+    __syncthreads();
+    const int dir = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (int)(i % HG);
+    const long long q = i / HG;
+    const bool active = q < nouter * G;
+    const long long qc = active ? q : nouter * G - 1;
+    const int g = (int)(qc % G);
+    const long long o = qc / G;
+    const long long bp = (o / qdiv) * s_hi + (o % qdiv) * s_lo;
+    float wi[4][NG], whc[4][HG];   // whc[gt][k] = W_hh[gt * HG + k][j]: what unit k's gate gradients send back to h_j
+#pragma unroll
+    for (int gt = 0; gt < 4; ++gt) {
+#pragma unroll
+        for (int k = 0; k < NG; ++k) wi[gt][k] = __ldg(w.wih[dir] + (gt * HG + j) * NG + k);
+#pragma unroll
+        for (int k = 0; k < HG; ++k) whc[gt][k] = __ldg(w.whh[dir] + (gt * HG + k) * HG + j);
+    }
+    float aWhh[4][HG], aWih[4][NG], ab[4];
+#pragma unroll
+    for (int gt = 0; gt < 4; ++gt) {
+        ab[gt] = 0.f;
+#pragma unroll
+        for (int k = 0; k < HG; ++k) aWhh[gt][k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) aWih[gt][k] = 0.f;
+    }
+    const int C = G * NG;
+    float dh_rec = 0.f, dc_carry = 0.f;
+    for (int s = 0; s < len; ++s) {
+        const int t = dir ? s : len - 1 - s;             // reverse of the forward visiting order
+        const int tp = dir ? t + 1 : t - 1;              // the step the forward visited just before t
+        const bool first = (s == len - 1);
+        const long long pos = bp + (long long)t * s_t, item = pos * G + g;
+        const long long ppos = bp + (long long)tp * s_t, pitem = ppos * G + g;
+        const float* s5 = S5 + ((item * 2 + dir) * HG + j) * 5;
+        const float ig = s5[0], fg = s5[1], gg = s5[2], og = s5[3], c = s5[4];
+        const float cp = first ? 0.f : S5[((pitem * 2 + dir) * HG + j) * 5 + 4];
+        const float hp = first ? 0.f : Hh[pitem * 2 * HG + dir * HG + j];
+        const float dh = dHh[item * 2 * HG + dir * HG + j] + dh_rec;
+        const float tc = tanh_cell<true>(c);
+        const float dc = fmaf(dh * og, 1.f - tc * tc, dc_carry);
+        dc_carry = dc * fg;
+        float dg[4];
+        dg[0] = dc * gg * ig * (1.f - ig);
+        dg[1] = dc * cp * fg * (1.f - fg);
+        dg[2] = dc * ig * (1.f - gg * gg);
+        dg[3] = dh * tc * og * (1.f - og);
+        if (!active) { dg[0] = dg[1] = dg[2] = dg[3] = 0.f; }
+        float xk[NG], px[NG];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            xk[k] = X[pos * C + g * NG + k];
+            px[k] = 0.f;
+        }
+        dh_rec = 0.f;
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) {
+            ab[gt] += dg[gt];
+#pragma unroll
+            for (int k = 0; k < NG; ++k) {
+                aWih[gt][k] = fmaf(dg[gt], xk[k], aWih[gt][k]);
+                px[k] = fmaf(wi[gt][k], dg[gt], px[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < HG; ++k) {
+                aWhh[gt][k] = fmaf(dg[gt], __shfl_sync(0xffffffffu, hp, k, HG), aWhh[gt][k]);
+                dh_rec = fmaf(whc[gt][k], __shfl_sync(0xffffffffu, dg[gt], k, HG), dh_rec);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+#pragma unroll
+            for (int m = HG >> 1; m; m >>= 1) px[k] += __shfl_xor_sync(0xffffffffu, px[k], m);
+        }
+        if (active && j == 0) {
+#pragma unroll
+            for (int k = 0; k < NG; ++k) dXd[(long long)dir * nitems * NG + item * NG + k] = px[k];
+        }
+    }
+    // reduce the weight-gradient accumulators over the CTA's sequences (shared-memory atomics), then one global atomic per element
+    float* mine = acc_sm + j * NACC;
+#pragma unroll
+    for (int gt = 0; gt < 4; ++gt) {
+#pragma unroll
+        for (int k = 0; k < HG; ++k) atomicAdd(mine + gt * HG + k, aWhh[gt][k]);
+#pragma unroll
+        for (int k = 0; k < NG; ++k) atomicAdd(mine + 4 * HG + gt * NG + k, aWih[gt][k]);
+        atomicAdd(mine + 4 * HG + 4 * NG + gt, ab[gt]);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < HG * NACC; e += blockDim.x) {
+        const int jj = e / NACC, r = e % NACC;
+        const float v = acc_sm[e];
+        if (r < 4 * HG) atomicAdd(gw.whh[dir] + ((r / HG) * HG + jj) * HG + r % HG, v);
+        else if (r < 4 * HG + 4 * NG) { const int r2 = r - 4 * HG; atomicAdd(gw.wih[dir] + ((r2 / NG) * HG + jj) * NG + r2 % NG, v); }
+        else { const int gt = r - 4 * HG - 4 * NG; atomicAdd(gw.bih[dir] + gt * HG + jj, v); atomicAdd(gw.bhh[dir] + gt * HG + jj, v); }
+    }
+}
+
+// ---- GroupNorm(1, n) per (sample, group) backward, pass 1: domain sums of gamma dO and gamma dO yhat, and dgamma / dbeta ----------------
+template <int NG>
+__global__ void __launch_bounds__(256) gct_gn_sums_kernel(const float* __restrict__ dO, const float* __restrict__ Y, const double* __restrict__ stats,
+                                                          const float* __restrict__ gamma, double* __restrict__ bst, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, int total, int G, int pps, double eps) {
+    __shared__ float sh[32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < total;
+    const int gshift = 31 - __clz(G);
+    const int ic = active ? i : total - 1;
+    const int pos = ic >> gshift, g = ic & (G - 1);
+    const double* d = stats + 2 * ((size_t)(pos / pps) * G + g);
+    const double inv = 1.0 / ((double)pps * NG), mean = d[0] * inv;
+    double var = d[1] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + eps));
+    float s1 = 0.f, s2 = 0.f, dga[NG], dbe[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+        const float go = active ? dO[(size_t)i * NG + k] : 0.f;
+        const float yh = (Y[(size_t)ic * NG + k] - mu) * rstd;
+        const float ga = __ldg(gamma + k);
+        s1 = fmaf(ga, go, s1);
+        s2 = fmaf(ga * go, yh, s2);
+        dga[k] = go * yh;
+        dbe[k] = go;
+    }
+    if (active) {
+        double* b = bst + 2 * ((size_t)(pos / pps) * G + g);
+        atomicAdd(b, (double)s1);
+        atomicAdd(b + 1, (double)s2);
+    }
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+        const float a = block_sum_f(dga[k], sh), b = block_sum_f(dbe[k], sh);
+        if (threadIdx.x == 0) { atomicAdd(dgamma + k, a); atomicAdd(dbeta + k, b); }
+    }
+}
+
+// pass 2: dY = rstd (gamma dO - mean(gamma dO) - yhat mean(gamma dO yhat))
+template <int NG>
+__global__ void __launch_bounds__(256) gct_gn_apply_kernel(const float* __restrict__ dO, const float* __restrict__ Y, const double* __restrict__ stats,
+                                                           const double* __restrict__ bst, const float* __restrict__ gamma, float* __restrict__ dY,
+                                                           int total, int G, int pps, double eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int gshift = 31 - __clz(G);
+    const int pos = i >> gshift, g = i & (G - 1);
+    const size_t dom = (size_t)(pos / pps) * G + g;
+    const double inv = 1.0 / ((double)pps * NG), mean = stats[2 * dom] * inv;
+    double var = stats[2 * dom + 1] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + eps));
+    const float m1 = (float)(bst[2 * dom] * inv), m2 = (float)(bst[2 * dom + 1] * inv);
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+        const float yh = (Y[(size_t)i * NG + k] - mu) * rstd;
+        dY[(size_t)i * NG + k] = rstd * (__ldg(gamma + k) * dO[(size_t)i * NG + k] - m1 - yh * m2);
+    }
+}
+
+// unfold: Out = prelu(cat_w (R + GN(Y)) + cat_b): turns dOut into the gradient of u = R + GN(Y) in place; concat_block gradients
+template <int NG>
+__global__ void __launch_bounds__(256) gct_cat_bwd_kernel(float* __restrict__ dO, const float* __restrict__ R, const float* __restrict__ Y,
+                                                          const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ cw, const float* __restrict__ cb,
+                                                          const float* __restrict__ ca, float* __restrict__ gcw, float* __restrict__ gcb,
+                                                          float* __restrict__ gca, int total, int G, int pps, double eps) {
+    __shared__ float sh[32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < total;
+    const int gshift = 31 - __clz(G);
+    const int ic = active ? i : total - 1;
+    const int pos = ic >> gshift, g = ic & (G - 1);
+    const double* d = stats + 2 * ((size_t)(pos / pps) * G + g);
+    const double inv = 1.0 / ((double)pps * NG), mean = d[0] * inv;
+    double var = d[1] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + eps));
+    const float a = __ldg(ca);
+    float da = 0.f, dw[NG], db[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+        const float u = R[(size_t)ic * NG + k] + ((Y[(size_t)ic * NG + k] - mu) * rstd * __ldg(gamma + k) + __ldg(beta + k));
+        const float z = fmaf(u, __ldg(cw + k), __ldg(cb + k));
+        const float go = active ? dO[(size_t)i * NG + k] : 0.f;
+        const float dz = z >= 0.f ? go : a * go;
+        da += z >= 0.f ? 0.f : go * z;
+        dw[k] = dz * u;
+        db[k] = dz;
+        if (active) dO[(size_t)i * NG + k] = dz * __ldg(cw + k);
+    }
+    const float sa = block_sum_f(da, sh);
+    if (threadIdx.x == 0) atomicAdd(gca, sa);
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+        const float x = block_sum_f(dw[k], sh), y = block_sum_f(db[k], sh);
+        if (threadIdx.x == 0) { atomicAdd(gcw + k, x); atomicAdd(gcb + k, y); }
+    }
+}
+
+// ---- generic small weight gradient: dW[r][c] += sum_i A[i*lda + r] * Bm[i*ldb + c]  (r < R, c < Cc), db[r] += sum_i A[i*lda + r] --------
+__global__ void __launch_bounds__(256) gct_wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb, long long n,
+                                                        int R, int Cc, float* __restrict__ dW, float* __restrict__ db, int relu_b, int chunk) {
+    const long long i0 = (long long)blockIdx.x * chunk, i1 = i0 + chunk < n ? i0 + chunk : n;
+    for (int e = threadIdx.x; e < R * Cc + (db ? R : 0); e += blockDim.x) {
+        float acc = 0.f;
+        if (e < R * Cc) {
+            const int r = e / Cc, c = e % Cc;
+            for (long long i = i0; i < i1; ++i) {
+                float b = Bm[i * ldb + c];
+                if (relu_b) b = fmaxf(b, 0.f);
+                acc = fmaf(A[i * lda + r], b, acc);
+            }
+            atomicAdd(dW + e, acc);
+        } else {
+            const int r = e - R * Cc;
+            for (long long i = i0; i < i1; ++i) acc += A[i * lda + r];
+            atomicAdd(db + r, acc);
+        }
+    }
+}
+
+// ---- generic small linear backward (data): dX[i][k] (+)= sum_o dY[i][o] W[o][k]; optional mask (dY counted where Yact > 0: ReLU) -----------
+__global__ void __launch_bounds__(256) gct_lin_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ W, const float* __restrict__ Yact,
+                                                          float* __restrict__ dX, long long n, int nin, int nout, int accumulate) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * nin) return;
+    const long long i = e / nin;
+    const int k = (int)(e % nin);
+    float acc = 0.f;
+    for (int o = 0; o < nout; ++o) {
+        float g = dY[i * nout + o];
+        if (Yact && Yact[i * nout + o] <= 0.f) g = 0.f;
+        acc = fmaf(g, __ldg(W + o * nin + k), acc);
+    }
+    dX[e] = accumulate ? dX[e] + acc : acc;
+}
+
+__global__ void __launch_bounds__(256) gct_add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                                       float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i] + (c ? c[i] : 0.f);
+}
+__global__ void __launch_bounds__(256) gct_relu_mask_kernel(float* __restrict__ d, const float* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && y[i] <= 0.f) d[i] = 0.f;
+}
+
+// ---- TAC backward (gc3_basics.py:38-55 + the GroupNorm / residual that follow).  dYraw = gradient of the TAC output before the norm.
+// Writes dX = dOut + (TAC path) and the operands of the weight-gradient reductions:
+//   S3 [item][NG] = d(pre-activation 3), A3 [item][2 TH] = [y1 ; y2];  S2 [pos][TH], Mv [pos][TH] = group mean of y1;  S1 [item][TH]
+template <int NG, int HG>
+__global__ void __launch_bounds__(128) gct_tac_bwd_kernel(const float* __restrict__ X, const float* __restrict__ dYraw, const float* __restrict__ dOut,
+                                                          float* __restrict__ dX, TacW w, float* __restrict__ S3, float* __restrict__ A3,
+                                                          float* __restrict__ S2, float* __restrict__ Mv, float* __restrict__ S1,
+                                                          float* __restrict__ ga1, float* __restrict__ ga2, float* __restrict__ ga3, int npos, int G) {
+    constexpr int TH = 3 * HG;
+    __shared__ float sh[32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pos = i / G, g = i % G;
+    const bool active = pos < npos;
+    const int ic = active ? i : npos * G - 1;
+    const float a1 = __ldg(w.a1), a2 = __ldg(w.a2), a3 = __ldg(w.a3);
+    float x[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) x[k] = X[(size_t)ic * NG + k];
+    float y1[TH], p1[TH], mv[TH];
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+        float acc = __ldg(w.b1 + r);
+#pragma unroll
+        for (int k = 0; k < NG; ++k) acc = fmaf(__ldg(w.w1 + r * NG + k), x[k], acc);
+        p1[r] = acc;
+        y1[r] = prelu1(acc, a1);
+        float v = active ? y1[r] : 0.f;   // inactive lanes only exist in the last, partial warp and belong to positions >= npos
+        for (int o = G >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 32);
+        mv[r] = v / (float)G;
+    }
+    float y2[TH], p2[TH];
+    for (int r = 0; r < TH; ++r) {
+        float acc = __ldg(w.b2 + r);
+#pragma unroll
+        for (int c = 0; c < TH; ++c) acc = fmaf(__ldg(w.w2 + r * TH + c), mv[c], acc);
+        p2[r] = acc;
+        y2[r] = prelu1(acc, a2);
+    }
+    float d3[NG], da3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+        float acc = __ldg(w.b3 + k);
+#pragma unroll
+        for (int r = 0; r < TH; ++r) acc = fmaf(__ldg(w.w3 + k * 2 * TH + r), y1[r], acc);
+#pragma unroll
+        for (int r = 0; r < TH; ++r) acc = fmaf(__ldg(w.w3 + k * 2 * TH + TH + r), y2[r], acc);
+        const float go = active ? dYraw[(size_t)i * NG + k] : 0.f;
+        d3[k] = acc >= 0.f ? go : a3 * go;
+        da3 += acc >= 0.f ? 0.f : go * acc;
+    }
+    float dy1[TH], dy2[TH];
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+        float s = 0.f, t = 0.f;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            s = fmaf(__ldg(w.w3 + k * 2 * TH + r), d3[k], s);
+            t = fmaf(__ldg(w.w3 + k * 2 * TH + TH + r), d3[k], t);
+        }
+        dy1[r] = s;
+        for (int o = G >> 1; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o, 32);   // y2 is shared by the groups of a position
+        dy2[r] = t;
+    }
+    float d2[TH], da2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+        d2[r] = p2[r] >= 0.f ? dy2[r] : a2 * dy2[r];
+        da2 += p2[r] >= 0.f ? 0.f : dy2[r] * p2[r];
+    }
+    float da1 = 0.f, dx[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) dx[k] = 0.f;
+    for (int c = 0; c < TH; ++c) {
+        float dm = 0.f;
+#pragma unroll
+        for (int r = 0; r < TH; ++r) dm = fmaf(__ldg(w.w2 + r * TH + c), d2[r], dm);
+        const float dyc = dy1[c] + dm / (float)G;
+        const float d1 = p1[c] >= 0.f ? dyc : a1 * dyc;
+        da1 += p1[c] >= 0.f ? 0.f : dyc * p1[c];
+        if (active) S1[(size_t)i * TH + c] = d1;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) dx[k] = fmaf(__ldg(w.w1 + c * NG + k), d1, dx[k]);
+    }
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            dX[(size_t)i * NG + k] = dOut[(size_t)i * NG + k] + dx[k];
+            S3[(size_t)i * NG + k] = d3[k];
+        }
+#pragma unroll
+        for (int r = 0; r < TH; ++r) {
+            A3[(size_t)i * 2 * TH + r] = y1[r];
+            A3[(size_t)i * 2 * TH + TH + r] = y2[r];
+        }
+        if (g == 0) {
+#pragma unroll
+            for (int r = 0; r < TH; ++r) { S2[(size_t)pos * TH + r] = d2[r]; Mv[(size_t)pos * TH + r] = mv[r]; }
+        }
+    }
+    // PReLU slopes: a2's gradient is counted once per position (lane g == 0)
+    const float s1 = block_sum_f(active ? da1 : 0.f, sh), s2 = block_sum_f(active && g == 0 ? da2 : 0.f, sh), s3 = block_sum_f(da3, sh);
+    if (threadIdx.x == 0) { atomicAdd(ga1, s1); atomicAdd(ga2, s2); atomicAdd(ga3, s3); }
+}
+
+// ---- ends of the network -----------------------------------------------------------------------------------------------------------------
+// decoder backward: dMk[b,f,g,s,j] = enc[b,f,e] * sum_k Wd[e][k] d_est[b,s,t(f,k)],  denc[b,f,e] = sum_s Mk * (same sum);  e = g * eg + j
+__global__ void __launch_bounds__(256) gct_decoder_bwd_kernel(const float* __restrict__ d_est, const float* __restrict__ Mk, const float* __restrict__ enc,
+                                                              const float* __restrict__ Wd, float* __restrict__ dMk, float* __restrict__ denc,
+                                                              float* __restrict__ Q, int B, int spk, int T, int F, int E, int G, int win) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * F * E) return;
+    const int e = (int)(i % E), f = (int)((i / E) % F), b = (int)(i / ((long long)E * F));
+    const int stride = win / 2, eg = E / G, g = e / eg, j = e % eg;
+    float de = 0.f;
+    for (int s = 0; s < spk; ++s) {
+        float q = 0.f;
+        for (int k = 0; k < win; ++k) {
+            const int t = f * stride + k - stride;
+            if (t >= 0 && t < T) q = fmaf(__ldg(Wd + e * win + k), d_est[((size_t)b * spk + s) * T + t], q);
+        }
+        const size_t mi = ((size_t)b * F + f) * (size_t)(spk * E) + g * (spk * eg) + s * eg + j;
+        dMk[mi] = q * enc[i];
+        de = fmaf(q, Mk[mi], de);
+        Q[((size_t)b * F + f) * (size_t)(spk * E) + (size_t)s * E + e] = Mk[mi] * enc[i];   // masked encoder output, [b,f,s,e]
+    }
+    denc[i] = de;
+}
+// dWd[e][k] += sum_{b,s,f} masked[b,f,s,e] * d_est[b,s,t(f,k)]
+__global__ void __launch_bounds__(256) gct_decoder_wgrad_kernel(const float* __restrict__ d_est, const float* __restrict__ Q, float* __restrict__ dWd,
+                                                                int B, int spk, int T, int F, int E, int win, int fchunk) {
+    const int e = threadIdx.x % E, kk = threadIdx.x / E, kpb = blockDim.x / E;
+    const int b = blockIdx.y, f0 = blockIdx.x * fchunk, f1 = min(F, f0 + fchunk), stride = win / 2;
+    for (int k = kk; k < win; k += kpb) {
+        float acc = 0.f;
+        for (int s = 0; s < spk; ++s)
+            for (int f = f0; f < f1; ++f) {
+                const int t = f * stride + k - stride;
+                if (t >= 0 && t < T) acc = fmaf(Q[((size_t)b * F + f) * (size_t)(spk * E) + (size_t)s * E + e], d_est[((size_t)b * spk + s) * T + t], acc);
+            }
+        atomicAdd(dWd + e * win + k, acc);
+    }
+}
+// encoder: dW[e][k] += sum_{b,f} denc[b,f,e] * x[b,t(f,k)]
+__global__ void __launch_bounds__(256) gct_encoder_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ denc, float* __restrict__ dW,
+                                                                int T, int F, int E, int win, int fchunk) {
+    const int e = threadIdx.x % E, kk = threadIdx.x / E, kpb = blockDim.x / E;
+    const int b = blockIdx.y, f0 = blockIdx.x * fchunk, f1 = min(F, f0 + fchunk), stride = win / 2;
+    for (int k = kk; k < win; k += kpb) {
+        float acc = 0.f;
+        for (int f = f0; f < f1; ++f) {
+            const int t = f * stride + k - stride;
+            if (t >= 0 && t < T) acc = fmaf(denc[((size_t)b * F + f) * E + e], x[(size_t)b * T + t], acc);
+        }
+        atomicAdd(dW + e * win + k, acc);
+    }
+}
+// bottleneck GroupNorm(1, E) over (F, E) per sample with per-channel affine: pass 1 sums, pass 2 applies and adds into denc
+__global__ void __launch_bounds__(256) gct_bn_sums_kernel(const float* __restrict__ dU, const float* __restrict__ enc, const double* __restrict__ stats,
+                                                          const float* __restrict__ gamma, double* __restrict__ bst, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, int F, int E, double eps) {
+    // grid (frame chunks, B), block = E threads x (256 / E) frame lanes; one thread = one channel of every (256 / E)-th frame of the chunk
+    __shared__ float sh[32];
+    const int e = threadIdx.x % E, fl = threadIdx.x / E, fpb = blockDim.x / E, b = blockIdx.y;
+    const double inv = 1.0 / ((double)F * E), mean = stats[2 * b] * inv;
+    double var = stats[2 * b + 1] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + eps)), ga = __ldg(gamma + e);
+    float s1 = 0.f, s2 = 0.f, dg = 0.f, dbv = 0.f;
+    for (int f = blockIdx.x * FRAMES_PER_CTA + fl; f < min(F, (int)(blockIdx.x + 1) * FRAMES_PER_CTA); f += fpb) {
+        const size_t i = ((size_t)b * F + f) * E + e;
+        const float go = dU[i], yh = (enc[i] - mu) * rstd;
+        s1 = fmaf(ga, go, s1);
+        s2 = fmaf(ga * go, yh, s2);
+        dg = fmaf(go, yh, dg);
+        dbv += go;
+    }
+    atomicAdd(dgamma + e, dg);
+    atomicAdd(dbeta + e, dbv);
+    const float t1 = block_sum_f(s1, sh), t2 = block_sum_f(s2, sh);
+    if (threadIdx.x == 0) { atomicAdd(bst + 2 * b, (double)t1); atomicAdd(bst + 2 * b + 1, (double)t2); }
+}
+__global__ void __launch_bounds__(256) gct_bn_apply_kernel(const float* __restrict__ dU, const float* __restrict__ enc, const double* __restrict__ stats,
+                                                           const double* __restrict__ bst, const float* __restrict__ gamma, float* __restrict__ denc,
+                                                           long long total, int F, int E, double eps) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int e = (int)(i % E), b = (int)(i / ((long long)E * F));
+    const double inv = 1.0 / ((double)F * E), mean = stats[2 * b] * inv;
+    double var = stats[2 * b + 1] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + eps));
+    const float m1 = (float)(bst[2 * b] * inv), m2 = (float)(bst[2 * b + 1] * inv);
+    const float yh = (enc[i] - mu) * rstd;
+    denc[i] += rstd * (__ldg(gamma + e) * dU[i] - m1 - yh * m2);
+}
+// normalised encoder output (the operand of the bottleneck conv's weight gradient)
+__global__ void __launch_bounds__(256) gct_bn_norm_kernel(const float* __restrict__ enc, const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ out, long long total, int F, int E,
+                                                          double eps) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int e = (int)(i % E), b = (int)(i / ((long long)E * F));
+    const double inv = 1.0 / ((double)F * E), mean = stats[2 * b] * inv;
+    double var = stats[2 * b + 1] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    out[i] = (enc[i] - (float)mean) * (float)(1.0 / sqrt(var + eps)) * __ldg(gamma + e) + __ldg(beta + e);
+}
+__global__ void __launch_bounds__(256) gct_ctx_mean_bwd_kernel(const float* __restrict__ dsq, float* __restrict__ dA, long long total, int ctx, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long bl = i / ((long long)ctx * C);
+    dA[i] = dsq[bl * C + i % C] / (float)ctx;
+}
+__global__ void __launch_bounds__(256) gct_ctx_sum_kernel(const float* __restrict__ dX, float* __restrict__ dfmap, long long total, int ctx, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long bl = i / C;
+    const int c = (int)(i % C);
+    float s = 0.f;
+    for (int t = 0; t < ctx; ++t) s += dX[(bl * ctx + t) * C + c];
+    dfmap[i] = s;
+}
+
+}  // namespace
+
+namespace {
+
+struct TLayout {
+    size_t enc, feat, feat2, Mk, Q, xn, sqm, fmap, yout;
+    size_t ce[5], cd[5], yce[4], ycd[4], hce[2], hcd[2], sce[2], scd[2];
+    std::vector<size_t> dp, ydp, hdp, sdp;
+    size_t stats, bst, stats_bytes;
+    size_t gA, gB, T1, T2, T3, S3, A3, S2, Mv, S1, dMk, denc, dframe, dsq;
+    size_t s_ce[4], s_cd[4];      // statistics slots (in doubles) of the context stages: TAC 0, RNN 0, TAC 1, RNN 1
+    std::vector<size_t> s_dp;     // of the DPRNN stack: per layer TAC, row RNN, column RNN
+    size_t total;
+};
+void t_layout(const dp_gctasnet* h, const GGeo& g, TLayout& l) {
+    Carver c;
+    const size_t f = sizeof(float), L = (size_t)h->cfg.layer;
+    const size_t bfe = (size_t)g.B * g.F * g.E * f, bfc = (size_t)g.B * g.F * g.C * f, pc = (size_t)g.PC * g.C * f, pd = (size_t)g.PD * g.C * f;
+    const size_t blc = (size_t)g.B * g.Lc * g.C * f, pm = (size_t)g.PM * g.C * f;
+    const size_t th = 3 * (size_t)g.h;
+    l.enc = c.take(bfe); l.feat = c.take(bfc); l.feat2 = c.take(bfc); l.xn = c.take(bfe);
+    l.Mk = c.take((size_t)g.B * g.F * g.spk * g.E * f); l.Q = c.take((size_t)g.B * g.F * g.spk * g.E * f);
+    l.sqm = c.take(blc); l.fmap = c.take(blc); l.yout = c.take(pd);
+    for (int i = 0; i < 5; ++i) { l.ce[i] = c.take(pc); l.cd[i] = c.take(pc); }
+    for (int i = 0; i < 4; ++i) { l.yce[i] = c.take(pc); l.ycd[i] = c.take(pc); }
+    for (int i = 0; i < 2; ++i) {
+        l.hce[i] = c.take((size_t)g.PC * g.G * 2 * g.h * f); l.hcd[i] = c.take((size_t)g.PC * g.G * 2 * g.h * f);
+        l.sce[i] = c.take((size_t)g.PC * g.G * 2 * g.h * 5 * f); l.scd[i] = c.take((size_t)g.PC * g.G * 2 * g.h * 5 * f);
+    }
+    l.dp.resize(3 * L + 1); l.ydp.resize(3 * L); l.hdp.resize(2 * L); l.sdp.resize(2 * L); l.s_dp.resize(3 * L);
+    for (size_t i = 0; i <= 3 * L; ++i) l.dp[i] = c.take(pd);
+    for (size_t i = 0; i < 3 * L; ++i) l.ydp[i] = c.take(pd);
+    for (size_t i = 0; i < 2 * L; ++i) { l.hdp[i] = c.take((size_t)g.PD * g.G * 2 * g.h * f); l.sdp[i] = c.take((size_t)g.PD * g.G * 2 * g.h * 5 * f); }
+    const size_t slot = (size_t)g.B * g.Lc * g.G * 2, dslot = (size_t)g.B * g.G * 2;
+    l.stats_bytes = ((size_t)g.B + 8 * (size_t)g.B * g.Lc * g.G + 3 * L * g.B * g.G) * 2 * sizeof(double);
+    l.stats = c.take(l.stats_bytes);
+    l.bst = c.take(l.stats_bytes);
+    size_t o = 2 * (size_t)g.B;
+    for (int i = 0; i < 4; ++i) { l.s_ce[i] = o; o += slot; }
+    for (size_t i = 0; i < 3 * L; ++i) { l.s_dp[i] = o; o += dslot; }
+    for (int i = 0; i < 4; ++i) { l.s_cd[i] = o; o += slot; }
+    l.gA = c.take(pm); l.gB = c.take(pm); l.T1 = c.take(pm); l.T2 = c.take((size_t)g.PM * g.G * 2 * g.h * f); l.T3 = c.take(2 * pm);
+    l.S3 = c.take(pm); l.A3 = c.take((size_t)g.PM * g.G * 2 * th * f); l.S2 = c.take((size_t)g.PM * th * f); l.Mv = c.take((size_t)g.PM * th * f);
+    l.S1 = c.take((size_t)g.PM * g.G * th * f);
+    l.dMk = c.take((size_t)g.B * g.F * g.spk * g.E * f); l.denc = c.take(bfe); l.dframe = c.take(bfc); l.dsq = c.take(blc);
+    l.total = c.off;
+}
+
+inline int wgrad_chunk(long long n) {
+    long long c = ceil_div_ll(n, 592);
+    return (int)(c < 64 ? 64 : c);
+}
+inline cudaError_t wgrad(const float* A, int lda, const float* Bm, int ldb, long long n, int R, int Cc, float* dW, float* db, int relu_b, cudaStream_t s) {
+    const int chunk = wgrad_chunk(n);
+    gct_wgrad_kernel<<<blocks_for(n, chunk), 256, 0, s>>>(A, lda, Bm, ldb, n, R, Cc, dW, db, relu_b, chunk);
+    return cudaGetLastError();
+}
+
+template <int NG, int HG>
+struct TrainOps {
+    using F = Ops<NG, HG>;
+    static constexpr int TH = 3 * HG;
+
+    static int rnn_fwd(dp_gctasnet* h, const float* Ain, float* Y, float* Hh, float* S5, float* Out, double* st, const RnnW& w, long long npos, int G,
+                       int pps, const SeqWalk& q, double eps, cudaStream_t s, const float* cw, const float* cb, const float* ca) {
+        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
+        gct_lstm_kernel<NG, HG><<<grid, 128, 0, s>>>(Ain, Hh, S5, w, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t);
+        gc_proj_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Y, st, w, (int)npos, G, pps);
+        gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, Ain, Out, st, w.gamma, w.beta, (int)(npos * G), G, pps, eps, cw, cb, ca);
+        h->launches += 3;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    // GC_RNN with everything kept: X[0] -> X[1] (TAC 0) -> X[2] (RNN 0) -> X[3] (TAC 1) -> X[4] (RNN 1)
+    static int gc_rnn_fwd(dp_gctasnet* h, const float* p, int base, void* ws, const size_t* X, const size_t* Y, const size_t* Hh, const size_t* S5,
+                          const size_t* slots, double* st0, const GGeo& g, cudaStream_t s) {
+        const SeqWalk q{(long long)g.B * g.Lc, g.ctx, 1, (long long)g.ctx, 0, 1};
+        for (int i = 0; i < 2; ++i) {
+            CK(F::tac(h, at<float>(ws, X[2 * i]), at<float>(ws, Y[2 * i]), at<float>(ws, X[2 * i + 1]), st0 + slots[2 * i],
+                      tac_w(h, p, base + i * GC_LAYER), g.PC, g.G, g.ctx, s));
+            if (rnn_fwd(h, at<float>(ws, X[2 * i + 1]), at<float>(ws, Y[2 * i + 1]), at<float>(ws, Hh[i]), at<float>(ws, S5[i]),
+                        at<float>(ws, X[2 * i + 2]), st0 + slots[2 * i + 1], rnn_w(h, p, base + i * GC_LAYER + TAC_N), g.PC, g.G, g.ctx, q, 1e-5, s,
+                        nullptr, nullptr, nullptr))
+                return 1;
+        }
+        return 0;
+    }
+
+    static int forward(dp_gctasnet* h, const float* p, const float* mix, float* est, void* ws, const GGeo& g, cudaStream_t s) {
+        const auto& c = h->cfg;
+        TLayout l;
+        t_layout(h, g, l);
+        float *enc = at<float>(ws, l.enc), *feat = at<float>(ws, l.feat);
+        double* st = at<double>(ws, l.stats);
+        h->launches = 0;
+        CK(cudaMemsetAsync(st, 0, l.stats_bytes, s));
+        const int fpb = 256 / g.E;
+        dim3 fgrid(ceil_div(g.F, FRAMES_PER_CTA), g.B);
+        gc_encoder_kernel<<<fgrid, 256, (size_t)g.E * c.win * sizeof(float), s>>>(mix, p + h->off[P_ENC_W], enc, st, g.T, g.F, g.E, c.win);
+        const size_t smem = ((size_t)g.E * (g.C + 1) + (size_t)fpb * g.E) * sizeof(float);
+        gc_bottleneck_kernel<<<fgrid, 256, smem, s>>>(enc, p + h->off[P_BN_G], p + h->off[P_BN_B], p + h->off[P_BN_W], st, feat, g.F, g.E, g.C,
+                                                      (double)1.1920928955078125e-07f);
+        CK(cudaGetLastError());
+        CK(launch_segment_cl(feat, at<float>(ws, l.ce[0]), g.B, g.F, g.ctx, g.Lc, g.C, s));
+        if (gc_rnn_fwd(h, p, HEAD, ws, l.ce, l.yce, l.hce, l.sce, l.s_ce, st, g, s)) return 1;
+        gc_ctx_mean_kernel<<<blocks_for((long long)g.B * g.Lc * g.C), 256, 0, s>>>(at<float>(ws, l.ce[4]), at<float>(ws, l.sqm),
+                                                                                  (long long)g.B * g.Lc * g.C, g.ctx, g.C);
+        CK(cudaGetLastError());
+        CK(launch_segment_cl(at<float>(ws, l.sqm), at<float>(ws, l.dp[0]), g.B, g.Lc, g.K, g.S2, g.C, s));
+        const int pps = g.S2 * g.K;
+        const SeqWalk row{(long long)g.B * g.S2, g.K, 1, (long long)g.K, 0, 1};
+        const SeqWalk col{(long long)g.B * g.K, g.S2, g.K, (long long)g.S2 * g.K, 1, (long long)g.K};
+        const float *cw = c.unfold ? p + h->off[P_CAT_W] : nullptr, *cb = c.unfold ? p + h->off[P_CAT_B] : nullptr;
+        const float* ca = c.unfold ? p + h->off[P_CAT_A] : nullptr;
+        for (int i = 0; i < c.layer; ++i) {
+            const int base = HEAD + 2 * GC_BLOCK + i * DP_LAYER;
+            CK(F::tac(h, at<float>(ws, l.dp[3 * i]), at<float>(ws, l.ydp[3 * i]), at<float>(ws, l.dp[3 * i + 1]), st + l.s_dp[3 * i], tac_w(h, p, base),
+                      g.PD, g.G, pps, s));
+            if (rnn_fwd(h, at<float>(ws, l.dp[3 * i + 1]), at<float>(ws, l.ydp[3 * i + 1]), at<float>(ws, l.hdp[2 * i]), at<float>(ws, l.sdp[2 * i]),
+                        at<float>(ws, l.dp[3 * i + 2]), st + l.s_dp[3 * i + 1], rnn_w(h, p, base + TAC_N), g.PD, g.G, pps, row, 1e-8, s, nullptr, nullptr,
+                        nullptr))
+                return 1;
+            if (rnn_fwd(h, at<float>(ws, l.dp[3 * i + 2]), at<float>(ws, l.ydp[3 * i + 2]), at<float>(ws, l.hdp[2 * i + 1]),
+                        at<float>(ws, l.sdp[2 * i + 1]), at<float>(ws, l.dp[3 * i + 3]), st + l.s_dp[3 * i + 2], rnn_w(h, p, base + TAC_N + RNN_N), g.PD,
+                        g.G, pps, col, 1e-8, s, cw, cb, ca))
+                return 1;
+        }
+        CK(F::group_linear(h, at<float>(ws, l.dp[3 * c.layer]), at<float>(ws, l.yout), p + h->off[P_OUT_W], p + h->off[P_OUT_B], g.PD * g.G, g.n, 0, s));
+        CK(launch_overlap_add_cl(at<float>(ws, l.yout), at<float>(ws, l.fmap), g.B, g.Lc, g.K, g.S2, g.C, s));
+        gc_bcast_add_kernel<<<blocks_for(g.PC * g.C), 256, 0, s>>>(at<float>(ws, l.fmap), at<float>(ws, l.ce[0]), at<float>(ws, l.cd[0]), g.PC * g.C,
+                                                                   g.ctx, g.C);
+        CK(cudaGetLastError());
+        if (gc_rnn_fwd(h, p, HEAD + GC_BLOCK, ws, l.cd, l.ycd, l.hcd, l.scd, l.s_cd, st, g, s)) return 1;
+        CK(launch_overlap_add_cl(at<float>(ws, l.cd[4]), at<float>(ws, l.feat2), g.B, g.F, g.ctx, g.Lc, g.C, s));
+        CK(F::group_linear(h, at<float>(ws, l.feat2), at<float>(ws, l.Mk), p + h->off[P_MASK_W], p + h->off[P_MASK_B], (long long)g.B * g.F * g.G,
+                           g.spk * g.E / g.G, 1, s));
+        gc_decoder_kernel<<<blocks_for((long long)g.B * g.spk * g.T), 256, 0, s>>>(at<float>(ws, l.Mk), enc, p + h->off[P_DEC_W], est, g.B, g.spk, g.T,
+                                                                                   g.F, g.E, g.G, c.win);
+        CK(cudaGetLastError());
+        h->launches += 9;
+        return 0;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------------- backward of one stage
+    struct Scratch { float *T1, *T2, *T3, *S3, *A3, *S2, *Mv, *S1; };
+
+    // Out = X + GN(TAC(X)):  dOut -> dX
+    static int tac_bwd(dp_gctasnet* h, const float* p, float* gp, int base, const float* X, const float* Y, const double* st, double* bst,
+                       const float* dOut, float* dX, long long npos, int G, int pps, const Scratch& k, cudaStream_t s) {
+        const TacW w = tac_w(h, p, base);
+        const TacG gw = tac_g(h, gp, base);
+        const int total = (int)(npos * G);
+        gct_gn_sums_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Y, st, w.gamma, bst, gw.gamma, gw.beta, total, G, pps, 1e-5);
+        gct_gn_apply_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Y, st, bst, w.gamma, k.T1, total, G, pps, 1e-5);
+        gct_tac_bwd_kernel<NG, HG><<<blocks_for(total, 128), 128, 0, s>>>(X, k.T1, dOut, dX, w, k.S3, k.A3, k.S2, k.Mv, k.S1, gw.a1, gw.a2, gw.a3,
+                                                                          (int)npos, G);
+        CK(cudaGetLastError());
+        CK(wgrad(k.S3, NG, k.A3, 2 * TH, total, NG, 2 * TH, gw.w3, gw.b3, 0, s));
+        CK(wgrad(k.S2, TH, k.Mv, TH, npos, TH, TH, gw.w2, gw.b2, 0, s));
+        CK(wgrad(k.S1, TH, X, NG, total, TH, NG, gw.w1, gw.b1, 0, s));
+        h->launches += 6;
+        return 0;
+    }
+    // Out = [concat_block] (Ain + GN(Linear(BiLSTM(Ain)))):  dOut (clobbered) -> dAin
+    static int rnn_bwd(dp_gctasnet* h, const float* p, float* gp, int base, const float* Ain, const float* Y, const float* Hh, const float* S5,
+                       const double* st, double* bst, float* dOut, float* dAin, long long npos, int G, int pps, const SeqWalk& q, double eps,
+                       bool cat, const Scratch& k, cudaStream_t s) {
+        const RnnW w = rnn_w(h, p, base);
+        const RnnG gw = rnn_g(h, gp, base);
+        const int total = (int)(npos * G);
+        if (cat)
+            gct_cat_bwd_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Ain, Y, st, w.gamma, w.beta, p + h->off[P_CAT_W], p + h->off[P_CAT_B],
+                                                                     p + h->off[P_CAT_A], gp + h->off[P_CAT_W], gp + h->off[P_CAT_B],
+                                                                     gp + h->off[P_CAT_A], total, G, pps, eps);
+        gct_gn_sums_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Y, st, w.gamma, bst, gw.gamma, gw.beta, total, G, pps, eps);
+        gct_gn_apply_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Y, st, bst, w.gamma, k.T1, total, G, pps, eps);
+        gct_lin_bwd_kernel<<<blocks_for((long long)total * 2 * HG), 256, 0, s>>>(k.T1, w.pw, nullptr, k.T2, total, 2 * HG, NG, 0);
+        CK(cudaGetLastError());
+        CK(wgrad(k.T1, NG, Hh, 2 * HG, total, NG, 2 * HG, gw.pw, gw.pb, 0, s));
+        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
+        gct_lstm_bwd_kernel<NG, HG><<<grid, 128, 0, s>>>(Ain, Hh, S5, k.T2, k.T3, w, gw, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t,
+                                                         (long long)total);
+        gct_add3_kernel<<<blocks_for((long long)total * NG), 256, 0, s>>>(dOut, k.T3, k.T3 + (size_t)total * NG, dAin, (long long)total * NG);
+        CK(cudaGetLastError());
+        h->launches += 6 + (cat ? 1 : 0);
+        return 0;
+    }
+    // GC_RNN backward: gradient of X[4] in `gin` -> gradient of X[0] (returned pointer is gin or gout)
+    static float* gc_rnn_bwd(dp_gctasnet* h, const float* p, float* gp, int base, void* ws, const size_t* X, const size_t* Y, const size_t* Hh,
+                             const size_t* S5, const size_t* slots, const double* st0, double* bst0, float* gin, float* gout, const GGeo& g,
+                             const Scratch& k, cudaStream_t s, int* err) {
+        const SeqWalk q{(long long)g.B * g.Lc, g.ctx, 1, (long long)g.ctx, 0, 1};
+        for (int i = 1; i >= 0; --i) {
+            if (rnn_bwd(h, p, gp, base + i * GC_LAYER + TAC_N, at<float>(ws, X[2 * i + 1]), at<float>(ws, Y[2 * i + 1]), at<float>(ws, Hh[i]),
+                        at<float>(ws, S5[i]), st0 + slots[2 * i + 1], bst0 + slots[2 * i + 1], gin, gout, g.PC, g.G, g.ctx, q, 1e-5, false, k, s)) {
+                *err = 1;
+                return nullptr;
+            }
+            if (tac_bwd(h, p, gp, base + i * GC_LAYER, at<float>(ws, X[2 * i]), at<float>(ws, Y[2 * i]), st0 + slots[2 * i], bst0 + slots[2 * i], gout,
+                        gin, g.PC, g.G, g.ctx, k, s)) {
+                *err = 1;
+                return nullptr;
+            }
+        }
+        return gin;   // two ping-pongs per layer: the result is back in gin
+    }
+
+    static int backward(dp_gctasnet* h, const float* p, float* gp, const float* mix, const float* d_est, void* ws, const GGeo& g, cudaStream_t s) {
+        const auto& c = h->cfg;
+        TLayout l;
+        t_layout(h, g, l);
+        const double* st = at<double>(ws, l.stats);
+        double* bst = at<double>(ws, l.bst);
+        float *gA = at<float>(ws, l.gA), *gB = at<float>(ws, l.gB), *dMk = at<float>(ws, l.dMk), *denc = at<float>(ws, l.denc);
+        float *dframe = at<float>(ws, l.dframe), *dsq = at<float>(ws, l.dsq), *enc = at<float>(ws, l.enc), *Mk = at<float>(ws, l.Mk), *Q = at<float>(ws, l.Q);
+        const Scratch k{at<float>(ws, l.T1), at<float>(ws, l.T2), at<float>(ws, l.T3), at<float>(ws, l.S3), at<float>(ws, l.A3), at<float>(ws, l.S2),
+                        at<float>(ws, l.Mv), at<float>(ws, l.S1)};
+        h->launches = 0;
+        CK(cudaMemsetAsync(bst, 0, l.stats_bytes, s));
+        const long long bfe = (long long)g.B * g.F * g.E, bfg = (long long)g.B * g.F * g.G;
+        const int mo = g.spk * g.E / g.G;   // mask conv outputs per group
+        // decoder, masking, mask conv + ReLU
+        gct_decoder_bwd_kernel<<<blocks_for(bfe), 256, 0, s>>>(d_est, Mk, enc, p + h->off[P_DEC_W], dMk, denc, Q, g.B, g.spk, g.T, g.F, g.E, g.G, c.win);
+        {
+            const int fchunk = 128;
+            dim3 grid(ceil_div(g.F, fchunk), g.B);
+            gct_decoder_wgrad_kernel<<<grid, 256, 0, s>>>(d_est, Q, gp + h->off[P_DEC_W], g.B, g.spk, g.T, g.F, g.E, c.win, fchunk);
+        }
+        gct_relu_mask_kernel<<<blocks_for(bfg * mo), 256, 0, s>>>(dMk, Mk, bfg * mo);
+        gct_lin_bwd_kernel<<<blocks_for(bfg * NG), 256, 0, s>>>(dMk, p + h->off[P_MASK_W], nullptr, dframe, bfg, NG, mo, 0);
+        CK(cudaGetLastError());
+        CK(wgrad(dMk, mo, at<float>(ws, l.feat2), NG, bfg, mo, NG, gp + h->off[P_MASK_W], gp + h->off[P_MASK_B], 0, s));
+        // overlap-add of the decoded context blocks -> its adjoint is the segmentation
+        CK(launch_segment_cl(dframe, gA, g.B, g.F, g.ctx, g.Lc, g.C, s));
+        int err = 0;
+        float* gcd0 = gc_rnn_bwd(h, p, gp, HEAD + GC_BLOCK, ws, l.cd, l.ycd, l.hcd, l.scd, l.s_cd, st, bst, gA, gB, g, k, s, &err);
+        if (err) return 1;
+        // cd[0] = ce[0] + broadcast(fmap): gradient of ce[0] (kept in T3's second half until the encoder stage is done) and of fmap
+        float* gce0_extra = at<float>(ws, l.yout);   // [PC * C] does not fit yout in general: use dedicated space below
+        (void)gce0_extra;
+        float* keep = at<float>(ws, l.cd[0]);        // cd[0] itself is dead now (its only reader, the first decoder TAC, is done): reuse it
+        CK(cudaMemcpyAsync(keep, gcd0, (size_t)g.PC * g.C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        gct_ctx_sum_kernel<<<blocks_for((long long)g.B * g.Lc * g.C), 256, 0, s>>>(gcd0, dsq, (long long)g.B * g.Lc * g.C, g.ctx, g.C);
+        CK(cudaGetLastError());
+        // fmap = overlap_add(yout) -> adjoint segmentation; DPRNN output conv
+        float* gy = gA == gcd0 ? gB : gA;
+        CK(launch_segment_cl(dsq, gy, g.B, g.Lc, g.K, g.S2, g.C, s));
+        float* gx = gy == gA ? gB : gA;
+        gct_lin_bwd_kernel<<<blocks_for(g.PD * g.G * NG), 256, 0, s>>>(gy, p + h->off[P_OUT_W], nullptr, gx, g.PD * g.G, NG, NG, 0);
+        CK(cudaGetLastError());
+        CK(wgrad(gy, NG, at<float>(ws, l.dp[3 * c.layer]), NG, g.PD * g.G, NG, NG, gp + h->off[P_OUT_W], gp + h->off[P_OUT_B], 0, s));
+        const int pps = g.S2 * g.K;
+        const SeqWalk row{(long long)g.B * g.S2, g.K, 1, (long long)g.K, 0, 1};
+        const SeqWalk col{(long long)g.B * g.K, g.S2, g.K, (long long)g.S2 * g.K, 1, (long long)g.K};
+        float *cur = gx, *oth = gy;
+        for (int i = c.layer - 1; i >= 0; --i) {
+            const int base = HEAD + 2 * GC_BLOCK + i * DP_LAYER;
+            if (rnn_bwd(h, p, gp, base + TAC_N + RNN_N, at<float>(ws, l.dp[3 * i + 2]), at<float>(ws, l.ydp[3 * i + 2]), at<float>(ws, l.hdp[2 * i + 1]),
+                        at<float>(ws, l.sdp[2 * i + 1]), st + l.s_dp[3 * i + 2], bst + l.s_dp[3 * i + 2], cur, oth, g.PD, g.G, pps, col, 1e-8,
+                        c.unfold != 0, k, s))
+                return 1;
+            if (rnn_bwd(h, p, gp, base + TAC_N, at<float>(ws, l.dp[3 * i + 1]), at<float>(ws, l.ydp[3 * i + 1]), at<float>(ws, l.hdp[2 * i]),
+                        at<float>(ws, l.sdp[2 * i]), st + l.s_dp[3 * i + 1], bst + l.s_dp[3 * i + 1], oth, cur, g.PD, g.G, pps, row, 1e-8, false, k, s))
+                return 1;
+            if (tac_bwd(h, p, gp, base, at<float>(ws, l.dp[3 * i]), at<float>(ws, l.ydp[3 * i]), st + l.s_dp[3 * i], bst + l.s_dp[3 * i], cur, oth, g.PD,
+                        g.G, pps, k, s))
+                return 1;
+            float* t = cur; cur = oth; oth = t;
+        }
+        // dp[0] = segmentation(sqm) -> adjoint overlap-add; sqm = mean over the context window of ce[4]
+        CK(launch_overlap_add_cl(cur, dsq, g.B, g.Lc, g.K, g.S2, g.C, s));
+        gct_ctx_mean_bwd_kernel<<<blocks_for(g.PC * g.C), 256, 0, s>>>(dsq, gA, g.PC * g.C, g.ctx, g.C);
+        CK(cudaGetLastError());
+        float* gce0 = gc_rnn_bwd(h, p, gp, HEAD, ws, l.ce, l.yce, l.hce, l.sce, l.s_ce, st, bst, gA, gB, g, k, s, &err);
+        if (err) return 1;
+        gct_add3_kernel<<<blocks_for(g.PC * g.C), 256, 0, s>>>(gce0, keep, nullptr, gce0, g.PC * g.C);
+        // ce[0] = segmentation(feat) -> adjoint overlap-add; bottleneck; encoder
+        CK(launch_overlap_add_cl(gce0, dframe, g.B, g.F, g.ctx, g.Lc, g.C, s));
+        float* dU = at<float>(ws, l.Q);   // gradient of the normalised encoder output [B F E] (Q is dead: the decoder weight gradient is done)
+        gct_lin_bwd_kernel<<<blocks_for(bfe), 256, 0, s>>>(dframe, p + h->off[P_BN_W], nullptr, dU, (long long)g.B * g.F, g.E, g.C, 0);
+        gct_bn_norm_kernel<<<blocks_for(bfe), 256, 0, s>>>(enc, st, p + h->off[P_BN_G], p + h->off[P_BN_B], at<float>(ws, l.xn), bfe, g.F, g.E,
+                                                           (double)1.1920928955078125e-07f);
+        CK(cudaGetLastError());
+        CK(wgrad(dframe, g.C, at<float>(ws, l.xn), g.E, (long long)g.B * g.F, g.C, g.E, gp + h->off[P_BN_W], nullptr, 0, s));
+        {
+            dim3 grid(ceil_div(g.F, FRAMES_PER_CTA), g.B);
+            gct_bn_sums_kernel<<<grid, 256, 0, s>>>(dU, enc, st, p + h->off[P_BN_G], bst, gp + h->off[P_BN_G], gp + h->off[P_BN_B], g.F, g.E,
+                                                    (double)1.1920928955078125e-07f);
+            gct_bn_apply_kernel<<<blocks_for(bfe), 256, 0, s>>>(dU, enc, st, bst, p + h->off[P_BN_G], denc, bfe, g.F, g.E, (double)1.1920928955078125e-07f);
+            const int fchunk = 128;
+            dim3 g2(ceil_div(g.F, fchunk), g.B);
+            gct_encoder_wgrad_kernel<<<g2, 256, 0, s>>>(mix, denc, gp + h->off[P_ENC_W], g.T, g.F, g.E, c.win, fchunk);
+        }
+        CK(cudaGetLastError());
+        h->launches += 20;
+        return 0;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int64_t dp_gctasnet_train_workspace_bytes(const dp_gctasnet* h, int B, int T) {
+    GGeo g;
+    if (!h || !gc_geometry(h, B, T, g)) { fail("dp_gctasnet_train_workspace_bytes: bad arguments"); return -1; }
+    if (h->cfg.module != DP_MODULE_DPRNN) { fail("dp_gctasnet_train_workspace_bytes: the training path is built for module DPRNN"); return -1; }
+    TLayout l;
+    t_layout(h, g, l);
+    return (int64_t)l.total;
+}
+
+int dp_gctasnet_forward_train(dp_gctasnet* h, const float* params, const float* mixture, float* est, void* workspace, int B, int T, void* stream) {
+    if (!h || !params || !mixture || !est || !workspace) return fail("dp_gctasnet_forward_train: null argument");
+    if (h->cfg.module != DP_MODULE_DPRNN) return fail("dp_gctasnet_forward_train: the training path is built for module DPRNN (grouped DPTNet: inference only)");
+    GGeo g;
+    if (!gc_geometry(h, B, T, g)) return fail("dp_gctasnet_forward_train: bad batch / length (B=%d, T=%d)", B, T);
+    if (g.n == 4) return TrainOps<4, 8>::forward(h, params, mixture, est, workspace, g, S(stream));
+    return TrainOps<8, 16>::forward(h, params, mixture, est, workspace, g, S(stream));
+}
+
+int dp_gctasnet_backward(dp_gctasnet* h, const float* params, float* grads, const float* mixture, const float* d_est, void* workspace, int B, int T,
+                         void* stream) {
+    if (!h || !params || !grads || !mixture || !d_est || !workspace) return fail("dp_gctasnet_backward: null argument");
+    if (h->cfg.module != DP_MODULE_DPRNN) return fail("dp_gctasnet_backward: the training path is built for module DPRNN (grouped DPTNet: inference only)");
+    GGeo g;
+    if (!gc_geometry(h, B, T, g)) return fail("dp_gctasnet_backward: bad batch / length (B=%d, T=%d)", B, T);
+    if (g.n == 4) return TrainOps<4, 8>::backward(h, params, grads, mixture, d_est, workspace, g, S(stream));
+    return TrainOps<8, 16>::backward(h, params, grads, mixture, d_est, workspace, g, S(stream));
+}
+
+}  // extern "C"

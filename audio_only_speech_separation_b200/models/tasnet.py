@@ -169,6 +169,27 @@ class _TasNetFunction(torch.autograd.Function):
         return (None, None, *grads)
 
 
+class _GcTasNetFunction(torch.autograd.Function):
+    """Autograd node of the GroupComm engine (group_size > 1, module DPRNN): training forward + backward of csrc/groupcomm.cu."""
+
+    @staticmethod
+    def forward(ctx, model, mixture, *params):
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("TasNet: the engine has no gradient with respect to the input waveform; detach the mixture")
+        est, saved = model._gc_train_forward(mixture)
+        ctx.model, ctx.saved, ctx.dims = model, saved, mixture.shape
+        return est
+
+    @staticmethod
+    def backward(ctx, d_est):
+        model = ctx.model
+        gflat = torch.zeros_like(model._flat)
+        model._gc_train_backward(d_est.contiguous().float(), gflat, ctx.saved, *ctx.dims)
+        ctx.saved = None
+        grads = [gflat[o : o + p.numel()].view(p.shape) for p, o in zip(model._uniq, model._uniq_off)]
+        return (None, None, *grads)
+
+
 class TasNet(BaseModel):
     def __init__(
         self,
@@ -254,7 +275,7 @@ class TasNet(BaseModel):
         if self.cuda_graph and not needs_grad and not torch.cuda.is_current_stream_capturing():
             est = self._graph_forward(xin)
         elif self.group_size > 1:
-            est = self._gc_forward(xin)
+            est = _GcTasNetFunction.apply(self, xin, *self._uniq) if needs_grad else self._gc_forward(xin)
         else:
             est = _TasNetFunction.apply(self, xin, *self._uniq)
         if est.dtype != input.dtype and input.dtype.is_floating_point:
@@ -344,9 +365,7 @@ class TasNet(BaseModel):
         return table
 
     def _gc_forward(self, xin):
-        """GroupComm engine: inference only (the training backward of this path is not built; it fails loudly instead of falling back)."""
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self._uniq):
-            raise NotImplementedError("TasNet(group_size > 1): the GroupComm engine is inference-only (call model.eval(); DESIGN.md scope table)")
+        """GroupComm engine, inference forward (nothing saved)."""
         B, T = xin.shape
         nbytes = lib().dp_gctasnet_workspace_bytes(self._handle, B, T)
         if nbytes < 0:
@@ -505,14 +524,40 @@ class TasNet(BaseModel):
     # fused training interface (DualPathTrainer): forward that saves, backward into a flat gradient buffer
     @property
     def pack_launches(self) -> int:
-        return 1 + 2 * self.layer
+        return 0 if self.group_size > 1 else 1 + 2 * self.layer
 
     def _train_forward(self, mixture, ws=None):
+        if self.group_size > 1:
+            return self._gc_train_forward(mixture, ws)
         est, ws = self._engine_forward(mixture, True, ws=ws)
         return est, (ws,)
 
     def _train_backward(self, d_est, gflat, ctx, B, T):
+        if self.group_size > 1:
+            return self._gc_train_backward(d_est, gflat, ctx, B, T)
         self._engine_backward(d_est, gflat, ctx[0], B, T)
+
+    # GroupComm engine (group_size > 1): training forward that keeps every stage's tensors, backward into the flat gradient buffer
+    def _gc_train_forward(self, mixture, ws=None):
+        if self.model_name != "DPRNN":
+            raise NotImplementedError("TasNet(group_size > 1, module='DPTNet'): the training backward is built for the grouped DPRNN stack only")
+        B, T = mixture.shape
+        nbytes = lib().dp_gctasnet_train_workspace_bytes(self._handle, B, T)
+        if nbytes < 0:
+            check(1, "dp_gctasnet_train_workspace_bytes")
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, device=mixture.device, dtype=torch.uint8)
+        est = torch.empty(B, self.num_spk, T, device=mixture.device, dtype=torch.float32)
+        check(lib().dp_gctasnet_forward_train(self._handle, ptr(self._flat), ptr(mixture), ptr(est), ptr(ws), B, T, stream_ptr()),
+              "dp_gctasnet_forward_train")
+        self.last_launches = lib().dp_gctasnet_last_launches(self._handle)
+        return est, (ws, mixture)
+
+    def _gc_train_backward(self, d_est, gflat, ctx, B, T):
+        ws, mixture = ctx
+        check(lib().dp_gctasnet_backward(self._handle, ptr(self._flat), ptr(gflat), ptr(mixture), ptr(d_est), ptr(ws), B, T, stream_ptr()),
+              "dp_gctasnet_backward")
+        self.last_launches = lib().dp_gctasnet_last_launches(self._handle)
 
     def _engine_backward(self, d_est, gflat, ws, B, T):
         self._require_training_engine()

@@ -295,6 +295,13 @@ int64_t dp_gctasnet_workspace_bytes(const dp_gctasnet* h, int B, int T);
 /* mixture[B,T] -> est[B,num_spk,T] */
 int dp_gctasnet_forward(dp_gctasnet* h, const float* params, const float* mixture, float* est, void* workspace, int B, int T, void* stream);
 int dp_gctasnet_last_launches(const dp_gctasnet* h);
+/* Training (module DPRNN): the forward that keeps every stage's input, pre-norm tensor, LSTM output and activated gates in the workspace,
+ * and the backward of the whole network (autograd through gc3_network.py:133-184, groupcomm.py:26-45, gc3_basics.py:7-60,
+ * dprnn.py:53-88): grads (same offsets as params) is ACCUMULATED into; d_est = gradient of est [B, num_spk, T]. */
+int64_t dp_gctasnet_train_workspace_bytes(const dp_gctasnet* h, int B, int T);
+int dp_gctasnet_forward_train(dp_gctasnet* h, const float* params, const float* mixture, float* est, void* workspace, int B, int T, void* stream);
+int dp_gctasnet_backward(dp_gctasnet* h, const float* params, float* grads, const float* mixture, const float* d_est, void* workspace, int B,
+                         int T, void* stream);
 /* the narrow recurrence stages a CTA's input sequences in shared memory (default, sequences up to ~800 steps) or prefetches them from
  * global memory one step ahead (longer sequences; 0 forces this path, for cross-checks).  Returns the previous setting. */
 int dp_gctasnet_set_lstm_staging(int on);

@@ -141,3 +141,84 @@ def test_staged_and_prefetching_recurrence_agree():
                 lib().dp_gctasnet_set_lstm_staging(prev)
         assert prev == 1
         assert rel_l2(y1, y0) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ training backward (grouped DPRNN)
+def _gc_grads(kwargs, seed, x, tgt):
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+    from audio_only_speech_separation_b200.models import TasNet
+
+    torch.manual_seed(seed)
+    m = TasNet(**kwargs)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda().train()
+    loss = PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False)(m(x.cuda()), tgt.cuda())
+    loss.backward()
+    return m, sd, loss
+
+
+def test_groupcomm_gradients_match_reference_golden():
+    """Every parameter gradient of the reference's own loss.backward() (tests/golden/groupcomm_grads_g16.npz, G = 16, 2 layers)."""
+    c = GC_MANIFEST["cases"]["grads_g16"]
+    z = load_npz("groupcomm_grads_g16.npz")
+    m, sd, loss = _gc_grads(c["kwargs"], c["seed"], torch.from_numpy(z["x"]), torch.from_numpy(z["tgt"]))
+    assert abs(loss.item() - float(z["loss"])) < 1e-4
+    num = den = 0.0
+    worst = (0.0, None)
+    for k, p in m.named_parameters():
+        ref = torch.from_numpy(z["grad::" + k])
+        assert p.grad is not None, k
+        e = rel_l2(p.grad, ref)
+        num += float((p.grad.cpu().double() - ref.double()).pow(2).sum())
+        den += float(ref.double().pow(2).sum())
+        worst = max(worst, (e, k))
+    record("groupcomm_grads", total_rel_l2=(num / den) ** 0.5, worst=worst[0], worst_key=worst[1])
+    assert (num / den) ** 0.5 < 1e-4, worst
+    assert worst[0] < 5e-3, worst
+
+
+@pytest.mark.parametrize("kw", [dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16, layer=2, unfold=True),
+                                dict(module="DPRNN", enc_dim=64, bn_dim=64, hidden_dim=128, group_size=8, layer=1, context_size=16, block_size=20),
+                                dict(module="DPRNN", enc_dim=128, bn_dim=128, hidden_dim=256, group_size=32, layer=1)],
+                         ids=["g16_unfold", "g8_ctx16", "g32"])
+def test_groupcomm_gradients_match_oracle_autograd(kw):
+    """Other configurations (unfold with the shared concat_block, per-group widths (8, 16), another context / block size, G = 32) against
+    autograd through the oracle (itself pinned to the reference's gradients, tests/test_groupcomm_oracle.py)."""
+    from oracle import dualpath_oracle as O
+
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 2600, generator=g) * 0.1
+    tgt = torch.randn(2, 2, 2600, generator=g) * 0.1
+    m, sd, loss = _gc_grads(kw, 1, x, tgt)
+    by_storage, leaf = {}, {}
+    for k, v in m.state_dict().items():   # unfold: aliased entries share one leaf so that autograd sums their gradients
+        if v.data_ptr() not in by_storage:
+            by_storage[v.data_ptr()] = sd[k].clone().requires_grad_(True)
+        leaf[k] = by_storage[v.data_ptr()]
+    est = GO.tasnet_gc_forward(leaf, x, enc_dim=kw["enc_dim"], bn_dim=kw["bn_dim"], group_size=kw["group_size"], layer=kw["layer"], module="DPRNN",
+                               unfold=kw.get("unfold", False), context_size=kw.get("context_size", 24), block_size=kw.get("block_size", 100))
+    ref_loss = O.pit_loss(est, tgt, "snr", False)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-4 * max(1.0, abs(ref_loss.item()))
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        gr = leaf[k].grad
+        num += float((p.grad.cpu().double() - gr.double()).pow(2).sum())
+        den += float(gr.double().pow(2).sum())
+    assert (num / den) ** 0.5 < 1e-4
+
+
+def test_groupcomm_fused_training_steps_lower_the_loss():
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+    from audio_only_speech_separation_b200.models import TasNet
+    from audio_only_speech_separation_b200.trainer import DualPathTrainer
+
+    torch.manual_seed(0)
+    m = TasNet(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16, layer=2).cuda().train()
+    tr = DualPathTrainer(m, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False))
+    g = torch.Generator().manual_seed(2)
+    src = (torch.randn(4, 2, 4000, generator=g) * 0.1).cuda()
+    losses = [tr.step(src.sum(1).contiguous(), src).item() for _ in range(8)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
+    with pytest.raises(NotImplementedError):
+        TasNet(module="DPTNet", enc_dim=64, bn_dim=64, group_size=16, layer=1).cuda().train()(src.sum(1))
