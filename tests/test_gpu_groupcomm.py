@@ -95,8 +95,11 @@ def test_training_and_unsupported_configurations_fail_loudly():
     m, _, _ = _model("g16_b1_t300")
     x = torch.randn(1, 800).cuda()
     m.train()
-    with pytest.raises(NotImplementedError):
-        m(x)
+    assert m(x).requires_grad                # grouped DPRNN: the training engine serves it (gradient tests below)
+    md, _, _ = _model("dpt_g16_b2_t4001")
+    md.train()
+    with pytest.raises(NotImplementedError):   # grouped DPTNet: inference only
+        md(x)
     with torch.no_grad():
         assert m(x).shape == (1, 2, 800)   # no graph requested: the inference engine serves it
     with pytest.raises(_lib.DualPathError):
@@ -179,7 +182,7 @@ def test_groupcomm_gradients_match_reference_golden():
 
 @pytest.mark.parametrize("kw", [dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16, layer=2, unfold=True),
                                 dict(module="DPRNN", enc_dim=64, bn_dim=64, hidden_dim=128, group_size=8, layer=1, context_size=16, block_size=20),
-                                dict(module="DPRNN", enc_dim=128, bn_dim=128, hidden_dim=256, group_size=32, layer=1)],
+                                dict(module="DPRNN", enc_dim=64, bn_dim=128, hidden_dim=256, group_size=32, layer=1)],
                          ids=["g16_unfold", "g8_ctx16", "g32"])
 def test_groupcomm_gradients_match_oracle_autograd(kw):
     """Other configurations (unfold with the shared concat_block, per-group widths (8, 16), another context / block size, G = 32) against
