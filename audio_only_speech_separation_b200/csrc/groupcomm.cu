@@ -500,8 +500,8 @@ __global__ void __launch_bounds__(128) gc_dpt_attn_kernel(const float* __restric
 // ---- second half (dptnet.py:79-82) after the BiLSTM: ReLU, Linear(4n -> n), residual, LayerNorm(n), then the residual of the dual-path
 // block (dptnet.py:150,157) and, with unfold after the column path, the shared concat_block
 template <int NG, int HG>
-__global__ void __launch_bounds__(256) gc_dpt_out_kernel(const float* __restrict__ Hh, const float* __restrict__ Z, float* A, XfW w, long long total,
-                                                         const float* __restrict__ cat_w, const float* __restrict__ cat_b,
+__global__ void __launch_bounds__(256) gc_dpt_out_kernel(const float* __restrict__ Hh, const float* __restrict__ Z, const float* Ain, float* A, XfW w,
+                                                         long long total, const float* __restrict__ cat_w, const float* __restrict__ cat_b,
                                                          const float* __restrict__ cat_a) {
     __shared__ float s_w[NG * 2 * HG], s_b[NG];
     for (int i = threadIdx.x; i < NG * 2 * HG; i += blockDim.x) s_w[i] = w.rnn.pw[i];
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(256) gc_dpt_out_kernel(const float* __restrict
     const float rstd = 1.f / sqrtf(var * (1.f / NG) + 1e-5f);
 #pragma unroll
     for (int j = 0; j < NG; ++j) {
-        float o = A[i * NG + j] + ((y[j] - mean) * rstd * __ldg(w.rnn.gamma + j) + __ldg(w.rnn.beta + j));
+        float o = Ain[i * NG + j] + ((y[j] - mean) * rstd * __ldg(w.rnn.gamma + j) + __ldg(w.rnn.beta + j));
         if (cat_w) o = prelu1(fmaf(o, __ldg(cat_w + j), __ldg(cat_b + j)), __ldg(cat_a));
         A[i * NG + j] = o;
     }
@@ -783,7 +783,7 @@ struct Ops {
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gc_dpt_attn_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gc_dpt_attn_kernel<NG><<<blocks_for(q.nouter * G, spb), 128, smem, s>>>(A, Z, w, q.nouter, G, q.len, spb, q.qdiv, q.s_hi, q.s_lo, q.s_t);
         CK(lstm(Z, Hh, w.rnn, G, q, s));
-        gc_dpt_out_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Z, A, w, npos * G, cat_w, cat_b, cat_a);
+        gc_dpt_out_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Z, A, A, w, npos * G, cat_w, cat_b, cat_a);
         h->launches += 3;
         CK(cudaGetLastError());
         return 0;
@@ -1524,12 +1524,302 @@ __global__ void __launch_bounds__(256) gct_ctx_sum_kernel(const float* __restric
 
 }  // namespace
 
+
+namespace {
+
+// ---- grouped DPTNet, backward of the second half of a transformer layer (gc_dpt_out_kernel): Out = [concat_block](Ain + LN(Z + Linear(relu(Hh)))).
+// Writes dRes (gradient reaching Ain through the residual), dYn (gradient of the LayerNorm input = of Z through its residual, and the operand of
+// the Linear's weight gradient) and dHh (through the ReLU); LayerNorm / concat_block parameter gradients by block reductions.
+template <int NG, int HG>
+__global__ void __launch_bounds__(256) gct_dpt_out_bwd_kernel(const float* __restrict__ Hh, const float* __restrict__ Z, const float* __restrict__ Ain,
+                                                              const float* __restrict__ dOut, float* __restrict__ dRes, float* __restrict__ dYn,
+                                                              float* __restrict__ dHh, XfW w, float* __restrict__ ggam, float* __restrict__ gbet,
+                                                              long long total, const float* __restrict__ cw, const float* __restrict__ cb,
+                                                              const float* __restrict__ ca, float* __restrict__ gcw, float* __restrict__ gcb,
+                                                              float* __restrict__ gca) {
+    __shared__ float s_w[NG * 2 * HG], s_b[NG], sh[32];
+    for (int i = threadIdx.x; i < NG * 2 * HG; i += blockDim.x) s_w[i] = w.rnn.pw[i];
+    if (threadIdx.x < NG) s_b[threadIdx.x] = w.rnn.pb[threadIdx.x];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < total;
+    const long long ic = active ? i : total - 1;
+    float y[NG], hr[2 * HG];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) y[j] = s_b[j];
+#pragma unroll
+    for (int k = 0; k < 2 * HG; ++k) {
+        hr[k] = fmaxf(Hh[ic * 2 * HG + k], 0.f);
+#pragma unroll
+        for (int j = 0; j < NG; ++j) y[j] = fmaf(s_w[j * 2 * HG + k], hr[k], y[j]);
+    }
+    float mean = 0.f;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) { y[j] += Z[ic * NG + j]; mean += y[j]; }
+    mean *= 1.f / NG;
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) var = fmaf(y[j] - mean, y[j] - mean, var);
+    const float rstd = 1.f / sqrtf(var * (1.f / NG) + 1e-5f);
+    float du[NG], yh[NG], dga[NG], dbe[NG], dcw[NG], dcb[NG], dca = 0.f, m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+        yh[j] = (y[j] - mean) * rstd;
+        float go = active ? dOut[i * NG + j] : 0.f;
+        dcw[j] = dcb[j] = 0.f;
+        if (cw) {
+            const float u = Ain[ic * NG + j] + (yh[j] * __ldg(w.rnn.gamma + j) + __ldg(w.rnn.beta + j));
+            const float z = fmaf(u, __ldg(cw + j), __ldg(cb + j)), a = __ldg(ca);
+            const float dz = z >= 0.f ? go : a * go;
+            dca += z >= 0.f ? 0.f : go * z;
+            dcw[j] = dz * u;
+            dcb[j] = dz;
+            go = dz * __ldg(cw + j);
+        }
+        du[j] = go;
+        dga[j] = go * yh[j];
+        dbe[j] = go;
+        const float dyh = go * __ldg(w.rnn.gamma + j);
+        m1 += dyh;
+        m2 = fmaf(dyh, yh[j], m2);
+    }
+    m1 *= 1.f / NG;
+    m2 *= 1.f / NG;
+    float dy[NG];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) dy[j] = rstd * (du[j] * __ldg(w.rnn.gamma + j) - m1 - yh[j] * m2);
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < NG; ++j) { dRes[i * NG + j] = du[j]; dYn[i * NG + j] = dy[j]; }
+#pragma unroll
+        for (int k = 0; k < 2 * HG; ++k) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < NG; ++j) acc = fmaf(s_w[j * 2 * HG + k], dy[j], acc);
+            dHh[i * 2 * HG + k] = hr[k] > 0.f ? acc : 0.f;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+        const float a = block_sum_f(dga[j], sh), b = block_sum_f(dbe[j], sh);
+        if (threadIdx.x == 0) { atomicAdd(ggam + j, a); atomicAdd(gbet + j, b); }
+        if (cw) {
+            const float c = block_sum_f(dcw[j], sh), d = block_sum_f(dcb[j], sh);
+            if (threadIdx.x == 0) { atomicAdd(gcw + j, c); atomicAdd(gcb + j, d); }
+        }
+    }
+    if (cw) {
+        const float e = block_sum_f(dca, sh);
+        if (threadIdx.x == 0) atomicAdd(gca, e);
+    }
+}
+
+// ---- backward of the first half (gc_dpt_attn_kernel): Z = LN(x + Wo attention(x) + bo).  One CTA per `spb` sequences, everything of a sequence in
+// shared memory; the softmax is recomputed.  dZ = gradient of Z; dA = dRes + gradient through x (written).  Operands of the weight-gradient
+// reductions go to global scratch: DQ [item][3 NG] (gradient of the in-projection output), DZ [item][NG] (of the LayerNorm input), OS [item][NG]
+// (attention output); LayerNorm parameter gradients by block reductions.
+template <int NG>
+__global__ void __launch_bounds__(128) gct_dpt_attn_bwd_kernel(const float* __restrict__ A, const float* __restrict__ dZ, const float* __restrict__ dRes,
+                                                               float* __restrict__ dA, float* __restrict__ DQ, float* __restrict__ DZ,
+                                                               float* __restrict__ OS, XfW w, float* __restrict__ gg1, float* __restrict__ gb1,
+                                                               long long nouter, int G, int len, int spb, int qdiv, long long s_hi, long long s_lo,
+                                                               long long s_t) {
+    constexpr int HD = NG / 4;
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float sh[32];
+    const int items = spb * len, C = G * NG;
+    float *xs = sm, *qs = xs + items * NG, *ks = qs + items * NG, *vs = ks + items * NG, *os = vs + items * NG, *dos = os + items * NG;
+    float *dqs = dos + items * NG, *dks = dqs + items * NG, *dvs = dks + items * NG, *ms = dvs + items * NG, *dens = ms + items * 4, *Ds = dens + items * 4;
+    const long long nseq = nouter * G, q0 = (long long)blockIdx.x * spb;
+    const float scale = HD == 1 ? 1.f : 0.70710678118654752f;
+    // forward recomputation: x, q (scaled), k, v
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const long long q = q0 + it / len;
+        if (q >= nseq) continue;
+        const int i = it % len, g = (int)(q % G);
+        const long long o = q / G, pos = (o / qdiv) * s_hi + (o % qdiv) * s_lo + (long long)i * s_t;
+        float x[NG];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) x[k] = A[pos * C + g * NG + k];
+#pragma unroll
+        for (int r = 0; r < 3 * NG; ++r) {
+            float acc = __ldg(w.bin + r);
+#pragma unroll
+            for (int k = 0; k < NG; ++k) acc = fmaf(__ldg(w.win + r * NG + k), x[k], acc);
+            if (r < NG) qs[it * NG + r] = acc * scale;
+            else if (r < 2 * NG) ks[it * NG + r - NG] = acc;
+            else vs[it * NG + r - 2 * NG] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < NG; ++k) xs[it * NG + k] = x[k];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < items * 4; idx += blockDim.x) {   // attention output, row maximum and denominator per (query, head)
+        const int it = idx >> 2, hh = idx & 3, sl = it / len;
+        if (q0 + sl >= nseq) continue;
+        const float* kb = ks + sl * len * NG + hh * HD;
+        const float* vb = vs + sl * len * NG + hh * HD;
+        float qv[HD], acc[HD], m = -INFINITY, den = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) { qv[d] = qs[it * NG + hh * HD + d] * 1.4426950408889634f; acc[d] = 0.f; }
+        for (int j = 0; j < len; ++j) {
+            float sc = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) sc = fmaf(qv[d], kb[j * NG + d], sc);
+            m = fmaxf(m, sc);
+        }
+        for (int j = 0; j < len; ++j) {
+            float sc = -m;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) sc = fmaf(qv[d], kb[j * NG + d], sc);
+            const float e = ex2_approx(sc);
+            den += e;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) acc[d] = fmaf(e, vb[j * NG + d], acc[d]);
+        }
+        ms[idx] = m;
+        dens[idx] = den;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) os[it * NG + hh * HD + d] = acc[d] / den;
+    }
+    __syncthreads();
+    // LayerNorm backward, out-projection backward: dos = Wo^T dz
+    float ag1[NG], ab1[NG];
+#pragma unroll
+    for (int r = 0; r < NG; ++r) ag1[r] = ab1[r] = 0.f;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const long long q = q0 + it / len;
+        if (q >= nseq) continue;
+        const int i = it % len, g = (int)(q % G);
+        const long long o = q / G, pos = (o / qdiv) * s_hi + (o % qdiv) * s_lo + (long long)i * s_t, item = pos * G + g;
+        float z[NG], mean = 0.f;
+#pragma unroll
+        for (int r = 0; r < NG; ++r) {
+            float acc = __ldg(w.bo + r);
+#pragma unroll
+            for (int k = 0; k < NG; ++k) acc = fmaf(__ldg(w.wo + r * NG + k), os[it * NG + k], acc);
+            z[r] = xs[it * NG + r] + acc;
+            mean += z[r];
+        }
+        mean *= 1.f / NG;
+        float var = 0.f;
+#pragma unroll
+        for (int r = 0; r < NG; ++r) var = fmaf(z[r] - mean, z[r] - mean, var);
+        const float rstd = 1.f / sqrtf(var * (1.f / NG) + 1e-5f);
+        float dzv[NG], m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < NG; ++r) {
+            const float zh = (z[r] - mean) * rstd, go = dZ[item * NG + r];
+            ag1[r] = fmaf(go, zh, ag1[r]);
+            ab1[r] += go;
+            const float dzh = go * __ldg(w.g1 + r);
+            m1 += dzh;
+            m2 = fmaf(dzh, zh, m2);
+            dzv[r] = zh;   // keep zhat; finished below
+        }
+        m1 *= 1.f / NG;
+        m2 *= 1.f / NG;
+#pragma unroll
+        for (int r = 0; r < NG; ++r) {
+            dzv[r] = rstd * (dZ[item * NG + r] * __ldg(w.g1 + r) - m1 - dzv[r] * m2);
+            DZ[item * NG + r] = dzv[r];
+            OS[item * NG + r] = os[it * NG + r];
+        }
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < NG; ++r) acc = fmaf(__ldg(w.wo + r * NG + k), dzv[r], acc);
+            dos[it * NG + k] = acc;
+        }
+#pragma unroll
+        for (int r = 0; r < NG; ++r) xs[it * NG + r] = dzv[r];   // x is not needed any more: keep dz (the residual path's gradient) in its place
+    }
+    __syncthreads();
+    // attention backward, queries: D_i = sum_j p_ij dP_ij, dq_i = sum_j p_ij (dP_ij - D_i) k_j
+    for (int idx = threadIdx.x; idx < items * 4; idx += blockDim.x) {
+        const int it = idx >> 2, hh = idx & 3, sl = it / len;
+        if (q0 + sl >= nseq) continue;
+        const float* kb = ks + sl * len * NG + hh * HD;
+        const float* vb = vs + sl * len * NG + hh * HD;
+        float qv[HD], dov[HD], dq[HD], D = 0.f;
+        const float m = ms[idx], inv = 1.f / dens[idx];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) { qv[d] = qs[it * NG + hh * HD + d] * 1.4426950408889634f; dov[d] = dos[it * NG + hh * HD + d]; dq[d] = 0.f; }
+        for (int j = 0; j < len; ++j) {
+            float sc = -m, dp = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) { sc = fmaf(qv[d], kb[j * NG + d], sc); dp = fmaf(dov[d], vb[j * NG + d], dp); }
+            D = fmaf(ex2_approx(sc) * inv, dp, D);
+        }
+        for (int j = 0; j < len; ++j) {
+            float sc = -m, dp = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) { sc = fmaf(qv[d], kb[j * NG + d], sc); dp = fmaf(dov[d], vb[j * NG + d], dp); }
+            const float ds = ex2_approx(sc) * inv * (dp - D);
+#pragma unroll
+            for (int d = 0; d < HD; ++d) dq[d] = fmaf(ds, kb[j * NG + d], dq[d]);
+        }
+        Ds[idx] = D;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) dqs[it * NG + hh * HD + d] = dq[d] * scale;   // gradient of the UNSCALED in-projection output
+    }
+    __syncthreads();
+    // keys / values: dk_j = sum_i dS_ij q_i, dv_j = sum_i p_ij dO_i
+    for (int idx = threadIdx.x; idx < items * 4; idx += blockDim.x) {
+        const int jt = idx >> 2, hh = idx & 3, sl = jt / len;
+        if (q0 + sl >= nseq) continue;
+        float kv[HD], vv[HD], dk[HD], dv[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) { kv[d] = ks[jt * NG + hh * HD + d]; vv[d] = vs[jt * NG + hh * HD + d]; dk[d] = dv[d] = 0.f; }
+        for (int i = 0; i < len; ++i) {
+            const int it = sl * len + i, qi = it * 4 + hh;
+            float sc = -ms[qi], dp = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) { sc = fmaf(qs[it * NG + hh * HD + d] * 1.4426950408889634f, kv[d], sc); dp = fmaf(dos[it * NG + hh * HD + d], vv[d], dp); }
+            const float pij = ex2_approx(sc) / dens[qi], ds = pij * (dp - Ds[qi]);
+#pragma unroll
+            for (int d = 0; d < HD; ++d) { dk[d] = fmaf(ds, qs[it * NG + hh * HD + d], dk[d]); dv[d] = fmaf(pij, dos[it * NG + hh * HD + d], dv[d]); }
+        }
+#pragma unroll
+        for (int d = 0; d < HD; ++d) { dks[jt * NG + hh * HD + d] = dk[d]; dvs[jt * NG + hh * HD + d] = dv[d]; }
+    }
+    __syncthreads();
+    // in-projection backward: dx = dz + Win^T [dq ; dk ; dv]
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const long long q = q0 + it / len;
+        if (q >= nseq) continue;
+        const int i = it % len, g = (int)(q % G);
+        const long long o = q / G, pos = (o / qdiv) * s_hi + (o % qdiv) * s_lo + (long long)i * s_t, item = pos * G + g;
+        float d3[3 * NG];
+#pragma unroll
+        for (int r = 0; r < NG; ++r) { d3[r] = dqs[it * NG + r]; d3[NG + r] = dks[it * NG + r]; d3[2 * NG + r] = dvs[it * NG + r]; }
+#pragma unroll
+        for (int r = 0; r < 3 * NG; ++r) DQ[item * 3 * NG + r] = d3[r];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            float acc = xs[it * NG + k];
+#pragma unroll
+            for (int r = 0; r < 3 * NG; ++r) acc = fmaf(__ldg(w.win + r * NG + k), d3[r], acc);
+            dA[item * NG + k] = dRes[item * NG + k] + acc;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NG; ++r) {
+        const float a = block_sum_f(ag1[r], sh), b = block_sum_f(ab1[r], sh);
+        if (threadIdx.x == 0) { atomicAdd(gg1 + r, a); atomicAdd(gb1 + r, b); }
+    }
+}
+
+}  // namespace
+
 namespace {
 
 struct TLayout {
     size_t enc, feat, feat2, Mk, Q, xn, sqm, fmap, yout;
     size_t ce[5], cd[5], yce[4], ycd[4], hce[2], hcd[2], sce[2], scd[2];
-    std::vector<size_t> dp, ydp, hdp, sdp;
+    std::vector<size_t> dp, ydp, hdp, sdp, zdp;   // zdp: first-half outputs Z of the grouped DPTNet's transformer layers
+    size_t DQ, OS;
     size_t stats, bst, stats_bytes;
     size_t gA, gB, T1, T2, T3, S3, A3, S2, Mv, S1, dMk, denc, dframe, dsq;
     size_t s_ce[4], s_cd[4];      // statistics slots (in doubles) of the context stages: TAC 0, RNN 0, TAC 1, RNN 1
@@ -1551,10 +1841,14 @@ void t_layout(const dp_gctasnet* h, const GGeo& g, TLayout& l) {
         l.hce[i] = c.take((size_t)g.PC * g.G * 2 * g.h * f); l.hcd[i] = c.take((size_t)g.PC * g.G * 2 * g.h * f);
         l.sce[i] = c.take((size_t)g.PC * g.G * 2 * g.h * 5 * f); l.scd[i] = c.take((size_t)g.PC * g.G * 2 * g.h * 5 * f);
     }
-    l.dp.resize(3 * L + 1); l.ydp.resize(3 * L); l.hdp.resize(2 * L); l.sdp.resize(2 * L); l.s_dp.resize(3 * L);
+    l.dp.resize(3 * L + 1); l.ydp.resize(3 * L); l.hdp.resize(2 * L); l.sdp.resize(2 * L); l.s_dp.resize(3 * L); l.zdp.resize(2 * L);
     for (size_t i = 0; i <= 3 * L; ++i) l.dp[i] = c.take(pd);
     for (size_t i = 0; i < 3 * L; ++i) l.ydp[i] = c.take(pd);
     for (size_t i = 0; i < 2 * L; ++i) { l.hdp[i] = c.take((size_t)g.PD * g.G * 2 * g.h * f); l.sdp[i] = c.take((size_t)g.PD * g.G * 2 * g.h * 5 * f); }
+    const bool dpt = h->cfg.module == DP_MODULE_DPTNET;
+    for (size_t i = 0; i < 2 * L; ++i) l.zdp[i] = dpt ? c.take(pd) : 0;
+    l.DQ = dpt ? c.take(3 * pd) : 0;
+    l.OS = dpt ? c.take(pd) : 0;
     const size_t slot = (size_t)g.B * g.Lc * g.G * 2, dslot = (size_t)g.B * g.G * 2;
     l.stats_bytes = ((size_t)g.B + 8 * (size_t)g.B * g.Lc * g.G + 3 * L * g.B * g.G) * 2 * sizeof(double);
     l.stats = c.take(l.stats_bytes);
@@ -1591,6 +1885,22 @@ struct TrainOps {
         gct_lstm_kernel<NG, HG><<<grid, 128, 0, s>>>(Ain, Hh, S5, w, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t);
         gc_proj_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Y, st, w, (int)npos, G, pps);
         gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, Ain, Out, st, w.gamma, w.beta, (int)(npos * G), G, pps, eps, cw, cb, ca);
+        h->launches += 3;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    // one transformer layer of the grouped DPTNet with everything kept: Z = first half's output, Hh / S5 of its BiLSTM feed-forward
+    static int xf_fwd(dp_gctasnet* h, const float* Ain, float* Z, float* Hh, float* S5, float* Out, const XfW& w, long long npos, int G,
+                      const SeqWalk& q, cudaStream_t s, const float* cw, const float* cb, const float* ca) {
+        int spb = 32 / q.len;
+        if (spb < 1) spb = 1;
+        const size_t smem = (size_t)spb * q.len * NG * 5 * sizeof(float);
+        if (smem > 200 * 1024) return fail("dp_gctasnet_forward_train: sequence of %d frames does not fit the attention kernel's shared memory", q.len);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gc_dpt_attn_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gc_dpt_attn_kernel<NG><<<blocks_for(q.nouter * G, spb), 128, smem, s>>>(Ain, Z, w, q.nouter, G, q.len, spb, q.qdiv, q.s_hi, q.s_lo, q.s_t);
+        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
+        gct_lstm_kernel<NG, HG><<<grid, 128, 0, s>>>(Z, Hh, S5, w.rnn, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t);
+        gc_dpt_out_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Z, Ain, Out, w, npos * G, cw, cb, ca);
         h->launches += 3;
         CK(cudaGetLastError());
         return 0;
@@ -1636,7 +1946,7 @@ struct TrainOps {
         const SeqWalk col{(long long)g.B * g.K, g.S2, g.K, (long long)g.S2 * g.K, 1, (long long)g.K};
         const float *cw = c.unfold ? p + h->off[P_CAT_W] : nullptr, *cb = c.unfold ? p + h->off[P_CAT_B] : nullptr;
         const float* ca = c.unfold ? p + h->off[P_CAT_A] : nullptr;
-        for (int i = 0; i < c.layer; ++i) {
+        for (int i = 0; i < c.layer && c.module != DP_MODULE_DPTNET; ++i) {
             const int base = HEAD + 2 * GC_BLOCK + i * DP_LAYER;
             CK(F::tac(h, at<float>(ws, l.dp[3 * i]), at<float>(ws, l.ydp[3 * i]), at<float>(ws, l.dp[3 * i + 1]), st + l.s_dp[3 * i], tac_w(h, p, base),
                       g.PD, g.G, pps, s));
@@ -1647,6 +1957,17 @@ struct TrainOps {
             if (rnn_fwd(h, at<float>(ws, l.dp[3 * i + 2]), at<float>(ws, l.ydp[3 * i + 2]), at<float>(ws, l.hdp[2 * i + 1]),
                         at<float>(ws, l.sdp[2 * i + 1]), at<float>(ws, l.dp[3 * i + 3]), st + l.s_dp[3 * i + 2], rnn_w(h, p, base + TAC_N + RNN_N), g.PD,
                         g.G, pps, col, 1e-8, s, cw, cb, ca))
+                return 1;
+        }
+        for (int i = 0; i < c.layer && c.module == DP_MODULE_DPTNET; ++i) {   // dptnet.py:138-157
+            const int base = HEAD + 2 * GC_BLOCK + i * DPT_LAYER;
+            CK(F::tac(h, at<float>(ws, l.dp[3 * i]), at<float>(ws, l.ydp[3 * i]), at<float>(ws, l.dp[3 * i + 1]), st + l.s_dp[3 * i], tac_w(h, p, base),
+                      g.PD, g.G, pps, s));
+            if (xf_fwd(h, at<float>(ws, l.dp[3 * i + 1]), at<float>(ws, l.zdp[2 * i]), at<float>(ws, l.hdp[2 * i]), at<float>(ws, l.sdp[2 * i]),
+                       at<float>(ws, l.dp[3 * i + 2]), xf_w(h, p, base + TAC_N), g.PD, g.G, row, s, nullptr, nullptr, nullptr))
+                return 1;
+            if (xf_fwd(h, at<float>(ws, l.dp[3 * i + 2]), at<float>(ws, l.zdp[2 * i + 1]), at<float>(ws, l.hdp[2 * i + 1]),
+                       at<float>(ws, l.sdp[2 * i + 1]), at<float>(ws, l.dp[3 * i + 3]), xf_w(h, p, base + TAC_N + XF_N), g.PD, g.G, col, s, cw, cb, ca))
                 return 1;
         }
         CK(F::group_linear(h, at<float>(ws, l.dp[3 * c.layer]), at<float>(ws, l.yout), p + h->off[P_OUT_W], p + h->off[P_OUT_B], g.PD * g.G, g.n, 0, s));
@@ -1666,7 +1987,7 @@ struct TrainOps {
     }
 
     // ---------------------------------------------------------------------------------------------------------------- backward of one stage
-    struct Scratch { float *T1, *T2, *T3, *S3, *A3, *S2, *Mv, *S1; };
+    struct Scratch { float *T1, *T2, *T3, *S3, *A3, *S2, *Mv, *S1, *DQ, *OS; };
 
     // Out = X + GN(TAC(X)):  dOut -> dX
     static int tac_bwd(dp_gctasnet* h, const float* p, float* gp, int base, const float* X, const float* Y, const double* st, double* bst,
@@ -1709,6 +2030,37 @@ struct TrainOps {
         h->launches += 6 + (cat ? 1 : 0);
         return 0;
     }
+    // Out = [concat_block](Ain + LN2(Z + Linear(relu(BiLSTM(Z))))), Z = LN1(Ain + out_proj(attention(in_proj(Ain)))):  dOut -> dAin
+    static int xf_bwd(dp_gctasnet* h, const float* p, float* gp, int base, const float* Ain, const float* Z, const float* Hh, const float* S5,
+                      const float* dOut, float* dAin, long long npos, int G, const SeqWalk& q, bool cat, const Scratch& k, cudaStream_t s) {
+        const XfW w = xf_w(h, p, base);
+        const RnnG gw = rnn_g(h, gp, base);
+        const long long total = npos * G;
+        // second half: k.S3 = gradient through the block residual, k.T1 = gradient of the LayerNorm input, k.T2 = gradient of the BiLSTM output
+        gct_dpt_out_bwd_kernel<NG, HG><<<blocks_for(total), 256, 0, s>>>(Hh, Z, Ain, dOut, k.S3, k.T1, k.T2, w, gw.gamma, gw.beta, total,
+                                                                        cat ? p + h->off[P_CAT_W] : nullptr, cat ? p + h->off[P_CAT_B] : nullptr,
+                                                                        cat ? p + h->off[P_CAT_A] : nullptr, gp + (cat ? h->off[P_CAT_W] : 0),
+                                                                        gp + (cat ? h->off[P_CAT_B] : 0), gp + (cat ? h->off[P_CAT_A] : 0));
+        CK(cudaGetLastError());
+        CK(wgrad(k.T1, NG, Hh, 2 * HG, total, NG, 2 * HG, gw.pw, gw.pb, 1, s));   // linear2: operand relu(Hh)
+        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
+        gct_lstm_bwd_kernel<NG, HG><<<grid, 128, 0, s>>>(Z, Hh, S5, k.T2, k.T3, w.rnn, gw, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t, total);
+        // gradient of Z: LayerNorm-2 residual + both LSTM directions (into k.S1)
+        gct_add3_kernel<<<blocks_for(total * NG), 256, 0, s>>>(k.T1, k.T3, k.T3 + (size_t)total * NG, k.S1, total * NG);
+        int spb = 32 / q.len;
+        if (spb < 1) spb = 1;
+        const size_t smem = (size_t)spb * q.len * (9 * NG + 12) * sizeof(float);
+        if (smem > 200 * 1024) return fail("dp_gctasnet_backward: sequence of %d frames does not fit the attention kernel's shared memory", q.len);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gct_dpt_attn_bwd_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gct_dpt_attn_bwd_kernel<NG><<<blocks_for(q.nouter * G, spb), 128, smem, s>>>(Ain, k.S1, k.S3, dAin, k.DQ, k.T1, k.OS, w, gp + h->off[base + 16],
+                                                                                     gp + h->off[base + 17], q.nouter, G, q.len, spb, q.qdiv, q.s_hi,
+                                                                                     q.s_lo, q.s_t);
+        CK(cudaGetLastError());
+        CK(wgrad(k.DQ, 3 * NG, Ain, NG, total, 3 * NG, NG, gp + h->off[base + 12], gp + h->off[base + 13], 0, s));   // in_proj
+        CK(wgrad(k.T1, NG, k.OS, NG, total, NG, NG, gp + h->off[base + 14], gp + h->off[base + 15], 0, s));           // out_proj (T1 = dz now)
+        h->launches += 7;
+        return 0;
+    }
     // GC_RNN backward: gradient of X[4] in `gin` -> gradient of X[0] (returned pointer is gin or gout)
     static float* gc_rnn_bwd(dp_gctasnet* h, const float* p, float* gp, int base, void* ws, const size_t* X, const size_t* Y, const size_t* Hh,
                              const size_t* S5, const size_t* slots, const double* st0, double* bst0, float* gin, float* gout, const GGeo& g,
@@ -1738,7 +2090,7 @@ struct TrainOps {
         float *gA = at<float>(ws, l.gA), *gB = at<float>(ws, l.gB), *dMk = at<float>(ws, l.dMk), *denc = at<float>(ws, l.denc);
         float *dframe = at<float>(ws, l.dframe), *dsq = at<float>(ws, l.dsq), *enc = at<float>(ws, l.enc), *Mk = at<float>(ws, l.Mk), *Q = at<float>(ws, l.Q);
         const Scratch k{at<float>(ws, l.T1), at<float>(ws, l.T2), at<float>(ws, l.T3), at<float>(ws, l.S3), at<float>(ws, l.A3), at<float>(ws, l.S2),
-                        at<float>(ws, l.Mv), at<float>(ws, l.S1)};
+                        at<float>(ws, l.Mv), at<float>(ws, l.S1), l.DQ ? at<float>(ws, l.DQ) : nullptr, l.OS ? at<float>(ws, l.OS) : nullptr};
         h->launches = 0;
         CK(cudaMemsetAsync(bst, 0, l.stats_bytes, s));
         const long long bfe = (long long)g.B * g.F * g.E, bfg = (long long)g.B * g.F * g.G;
@@ -1777,7 +2129,20 @@ struct TrainOps {
         const SeqWalk row{(long long)g.B * g.S2, g.K, 1, (long long)g.K, 0, 1};
         const SeqWalk col{(long long)g.B * g.K, g.S2, g.K, (long long)g.S2 * g.K, 1, (long long)g.K};
         float *cur = gx, *oth = gy;
-        for (int i = c.layer - 1; i >= 0; --i) {
+        for (int i = c.layer - 1; i >= 0 && c.module == DP_MODULE_DPTNET; --i) {
+            const int base = HEAD + 2 * GC_BLOCK + i * DPT_LAYER;
+            if (xf_bwd(h, p, gp, base + TAC_N + XF_N, at<float>(ws, l.dp[3 * i + 2]), at<float>(ws, l.zdp[2 * i + 1]), at<float>(ws, l.hdp[2 * i + 1]),
+                       at<float>(ws, l.sdp[2 * i + 1]), cur, oth, g.PD, g.G, col, c.unfold != 0, k, s))
+                return 1;
+            if (xf_bwd(h, p, gp, base + TAC_N, at<float>(ws, l.dp[3 * i + 1]), at<float>(ws, l.zdp[2 * i]), at<float>(ws, l.hdp[2 * i]),
+                       at<float>(ws, l.sdp[2 * i]), oth, cur, g.PD, g.G, row, false, k, s))
+                return 1;
+            if (tac_bwd(h, p, gp, base, at<float>(ws, l.dp[3 * i]), at<float>(ws, l.ydp[3 * i]), st + l.s_dp[3 * i], bst + l.s_dp[3 * i], cur, oth, g.PD,
+                        g.G, pps, k, s))
+                return 1;
+            float* t = cur; cur = oth; oth = t;
+        }
+        for (int i = c.layer - 1; i >= 0 && c.module != DP_MODULE_DPTNET; --i) {
             const int base = HEAD + 2 * GC_BLOCK + i * DP_LAYER;
             if (rnn_bwd(h, p, gp, base + TAC_N + RNN_N, at<float>(ws, l.dp[3 * i + 2]), at<float>(ws, l.ydp[3 * i + 2]), at<float>(ws, l.hdp[2 * i + 1]),
                         at<float>(ws, l.sdp[2 * i + 1]), st + l.s_dp[3 * i + 2], bst + l.s_dp[3 * i + 2], cur, oth, g.PD, g.G, pps, col, 1e-8,
@@ -1828,7 +2193,6 @@ extern "C" {
 int64_t dp_gctasnet_train_workspace_bytes(const dp_gctasnet* h, int B, int T) {
     GGeo g;
     if (!h || !gc_geometry(h, B, T, g)) { fail("dp_gctasnet_train_workspace_bytes: bad arguments"); return -1; }
-    if (h->cfg.module != DP_MODULE_DPRNN) { fail("dp_gctasnet_train_workspace_bytes: the training path is built for module DPRNN"); return -1; }
     TLayout l;
     t_layout(h, g, l);
     return (int64_t)l.total;
@@ -1836,7 +2200,6 @@ int64_t dp_gctasnet_train_workspace_bytes(const dp_gctasnet* h, int B, int T) {
 
 int dp_gctasnet_forward_train(dp_gctasnet* h, const float* params, const float* mixture, float* est, void* workspace, int B, int T, void* stream) {
     if (!h || !params || !mixture || !est || !workspace) return fail("dp_gctasnet_forward_train: null argument");
-    if (h->cfg.module != DP_MODULE_DPRNN) return fail("dp_gctasnet_forward_train: the training path is built for module DPRNN (grouped DPTNet: inference only)");
     GGeo g;
     if (!gc_geometry(h, B, T, g)) return fail("dp_gctasnet_forward_train: bad batch / length (B=%d, T=%d)", B, T);
     if (g.n == 4) return TrainOps<4, 8>::forward(h, params, mixture, est, workspace, g, S(stream));
@@ -1846,7 +2209,6 @@ int dp_gctasnet_forward_train(dp_gctasnet* h, const float* params, const float* 
 int dp_gctasnet_backward(dp_gctasnet* h, const float* params, float* grads, const float* mixture, const float* d_est, void* workspace, int B, int T,
                          void* stream) {
     if (!h || !params || !grads || !mixture || !d_est || !workspace) return fail("dp_gctasnet_backward: null argument");
-    if (h->cfg.module != DP_MODULE_DPRNN) return fail("dp_gctasnet_backward: the training path is built for module DPRNN (grouped DPTNet: inference only)");
     GGeo g;
     if (!gc_geometry(h, B, T, g)) return fail("dp_gctasnet_backward: bad batch / length (B=%d, T=%d)", B, T);
     if (g.n == 4) return TrainOps<4, 8>::backward(h, params, grads, mixture, d_est, workspace, g, S(stream));

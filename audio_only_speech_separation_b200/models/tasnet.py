@@ -170,7 +170,7 @@ class _TasNetFunction(torch.autograd.Function):
 
 
 class _GcTasNetFunction(torch.autograd.Function):
-    """Autograd node of the GroupComm engine (group_size > 1, module DPRNN): training forward + backward of csrc/groupcomm.cu."""
+    """Autograd node of the GroupComm engine (group_size > 1, DPRNN or DPTNet stack): training forward + backward of csrc/groupcomm.cu."""
 
     @staticmethod
     def forward(ctx, model, mixture, *params):
@@ -539,8 +539,6 @@ class TasNet(BaseModel):
 
     # GroupComm engine (group_size > 1): training forward that keeps every stage's tensors, backward into the flat gradient buffer
     def _gc_train_forward(self, mixture, ws=None):
-        if self.model_name != "DPRNN":
-            raise NotImplementedError("TasNet(group_size > 1, module='DPTNet'): the training backward is built for the grouped DPRNN stack only")
         B, T = mixture.shape
         nbytes = lib().dp_gctasnet_train_workspace_bytes(self._handle, B, T)
         if nbytes < 0:

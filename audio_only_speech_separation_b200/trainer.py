@@ -24,8 +24,6 @@ class DualPathTrainer:
                  process_group=None, distributed=False):
         if not isinstance(loss, PITLossWrapper) or not isinstance(loss.loss_func, PairwiseNegSDR) or loss.pit_from != "pw_mtx":
             raise NotImplementedError("DualPathTrainer needs PITLossWrapper(PairwiseNegSDR(...), pit_from='pw_mtx')")
-        if getattr(model, "group_size", 1) > 1 and getattr(model, "model_name", "DPRNN") != "DPRNN":
-            raise NotImplementedError("DualPathTrainer: TasNet(group_size > 1) trains with module='DPRNN' (the grouped DPTNet stack is inference-only)")
         if not (hasattr(model, "_train_forward") and hasattr(model, "_train_backward")):
             raise NotImplementedError(f"DualPathTrainer: {type(model).__name__} does not expose the fused training interface "
                                       "(_train_forward / _train_backward into a flat gradient buffer)")

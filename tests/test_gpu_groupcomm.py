@@ -95,11 +95,7 @@ def test_training_and_unsupported_configurations_fail_loudly():
     m, _, _ = _model("g16_b1_t300")
     x = torch.randn(1, 800).cuda()
     m.train()
-    assert m(x).requires_grad                # grouped DPRNN: the training engine serves it (gradient tests below)
-    md, _, _ = _model("dpt_g16_b2_t4001")
-    md.train()
-    with pytest.raises(NotImplementedError):   # grouped DPTNet: inference only
-        md(x)
+    assert m(x).requires_grad                # the training engine serves it (gradient tests below)
     with torch.no_grad():
         assert m(x).shape == (1, 2, 800)   # no graph requested: the inference engine serves it
     with pytest.raises(_lib.DualPathError):
@@ -160,10 +156,12 @@ def _gc_grads(kwargs, seed, x, tgt):
     return m, sd, loss
 
 
-def test_groupcomm_gradients_match_reference_golden():
-    """Every parameter gradient of the reference's own loss.backward() (tests/golden/groupcomm_grads_g16.npz, G = 16, 2 layers)."""
-    c = GC_MANIFEST["cases"]["grads_g16"]
-    z = load_npz("groupcomm_grads_g16.npz")
+@pytest.mark.parametrize("name", ["g16", "dpt_g16"])
+def test_groupcomm_gradients_match_reference_golden(name):
+    """Every parameter gradient of the reference's own loss.backward() (tests/golden/groupcomm_grads_{g16,dpt_g16}.npz: grouped DPRNN and
+    grouped DPTNet, G = 16, 2 layers)."""
+    c = GC_MANIFEST["cases"][f"grads_{name}"]
+    z = load_npz(f"groupcomm_grads_{name}.npz")
     m, sd, loss = _gc_grads(c["kwargs"], c["seed"], torch.from_numpy(z["x"]), torch.from_numpy(z["tgt"]))
     assert abs(loss.item() - float(z["loss"])) < 1e-4
     num = den = 0.0
@@ -175,15 +173,17 @@ def test_groupcomm_gradients_match_reference_golden():
         num += float((p.grad.cpu().double() - ref.double()).pow(2).sum())
         den += float(ref.double().pow(2).sum())
         worst = max(worst, (e, k))
-    record("groupcomm_grads", total_rel_l2=(num / den) ** 0.5, worst=worst[0], worst_key=worst[1])
+    record("groupcomm_grads", case=name, total_rel_l2=(num / den) ** 0.5, worst=worst[0], worst_key=worst[1])
     assert (num / den) ** 0.5 < 1e-4, worst
     assert worst[0] < 5e-3, worst
 
 
 @pytest.mark.parametrize("kw", [dict(module="DPRNN", enc_dim=64, bn_dim=64, group_size=16, layer=2, unfold=True),
                                 dict(module="DPRNN", enc_dim=64, bn_dim=64, hidden_dim=128, group_size=8, layer=1, context_size=16, block_size=20),
-                                dict(module="DPRNN", enc_dim=64, bn_dim=128, hidden_dim=256, group_size=32, layer=1)],
-                         ids=["g16_unfold", "g8_ctx16", "g32"])
+                                dict(module="DPRNN", enc_dim=64, bn_dim=128, hidden_dim=256, group_size=32, layer=1),
+                                dict(module="DPTNet", enc_dim=64, bn_dim=64, group_size=16, layer=2, unfold=True),
+                                dict(module="DPTNet", enc_dim=64, bn_dim=64, hidden_dim=128, group_size=8, layer=1, block_size=30)],
+                         ids=["g16_unfold", "g8_ctx16", "g32", "dpt_g16_unfold", "dpt_g8"])
 def test_groupcomm_gradients_match_oracle_autograd(kw):
     """Other configurations (unfold with the shared concat_block, per-group widths (8, 16), another context / block size, G = 32) against
     autograd through the oracle (itself pinned to the reference's gradients, tests/test_groupcomm_oracle.py)."""
@@ -198,7 +198,7 @@ def test_groupcomm_gradients_match_oracle_autograd(kw):
         if v.data_ptr() not in by_storage:
             by_storage[v.data_ptr()] = sd[k].clone().requires_grad_(True)
         leaf[k] = by_storage[v.data_ptr()]
-    est = GO.tasnet_gc_forward(leaf, x, enc_dim=kw["enc_dim"], bn_dim=kw["bn_dim"], group_size=kw["group_size"], layer=kw["layer"], module="DPRNN",
+    est = GO.tasnet_gc_forward(leaf, x, enc_dim=kw["enc_dim"], bn_dim=kw["bn_dim"], group_size=kw["group_size"], layer=kw["layer"], module=kw["module"],
                                unfold=kw.get("unfold", False), context_size=kw.get("context_size", 24), block_size=kw.get("block_size", 100))
     ref_loss = O.pit_loss(est, tgt, "snr", False)
     ref_loss.backward()
@@ -223,5 +223,8 @@ def test_groupcomm_fused_training_steps_lower_the_loss():
     src = (torch.randn(4, 2, 4000, generator=g) * 0.1).cuda()
     losses = [tr.step(src.sum(1).contiguous(), src).item() for _ in range(8)]
     assert all(l == l for l in losses) and losses[-1] < losses[0]
-    with pytest.raises(NotImplementedError):
-        TasNet(module="DPTNet", enc_dim=64, bn_dim=64, group_size=16, layer=1).cuda().train()(src.sum(1))
+    torch.manual_seed(0)
+    md = TasNet(module="DPTNet", enc_dim=64, bn_dim=64, group_size=16, layer=1).cuda().train()
+    trd = DualPathTrainer(md, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False))
+    losses = [trd.step(src.sum(1).contiguous(), src).item() for _ in range(8)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0]

@@ -81,9 +81,8 @@ def test_unsupported_variants_raise():
     from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
     from audio_only_speech_separation_b200.trainer import DualPathTrainer
 
-    DualPathTrainer(gc, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False))   # grouped DPRNN trains (csrc/groupcomm.cu)
-    with pytest.raises(NotImplementedError):   # the grouped DPTNet stack has no backward
-        DualPathTrainer(TasNet(module="DPTNet", group_size=16), PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False))
+    DualPathTrainer(gc, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False))   # GroupComm models train (csrc/groupcomm.cu)
+    DualPathTrainer(TasNet(module="DPTNet", group_size=16), PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False))
 
     with pytest.raises(RuntimeError):   # CUDA-only: CPU tensors are refused, there is no CPU path
         TasNet(module="DPRNN", group_size=16).eval()(torch.zeros(1, 800))

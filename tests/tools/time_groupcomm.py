@@ -35,6 +35,34 @@ with torch.no_grad():
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 out = {"module": MODULE, "unfold": UNFOLD, "B": B, "T": T, "group_size": G, "forward_ms": ms, "launches": m.last_launches, "audio_s_per_s_8k": B * T / 8000 / (ms * 1e-3)}
+with torch.no_grad():   # the same forward without the CUDA graph (eager engine call)
+    m.cuda_graph = False
+    for _ in range(3):
+        m(xd)
+    e0.record()
+    for _ in range(n):
+        m(xd)
+    e1.record()
+    torch.cuda.synchronize()
+    out["forward_ms_no_graph"] = e0.elapsed_time(e1) / n
+    m.cuda_graph = True
+if MODULE == "DPRNN" and os.environ.get("TRAIN", "1") == "1":   # fused training step (forward + PIT-SNR + backward + clip + Adam)
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+    from audio_only_speech_separation_b200.trainer import DualPathTrainer
+
+    m.train()
+    tr = DualPathTrainer(m, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False))
+    tgt = (torch.randn(B, 2, T, generator=torch.Generator().manual_seed(2)) * 0.1).cuda()
+    for _ in range(2):
+        tr.step(xd, tgt)
+    e0.record()
+    for _ in range(5):
+        tr.step(xd, tgt)
+    e1.record()
+    torch.cuda.synchronize()
+    out["train_step_ms"] = e0.elapsed_time(e1) / 5
+    out["train_launches"] = tr.launches_per_step
+    m.eval()
 if sys.argv[-1] == "cpu":
     from oracle import groupcomm_oracle as GO
 
