@@ -572,6 +572,51 @@ def other_configs(args, pk, pk_kind, rec):
                     "parity": "gradients / dropout replay: tests/test_gpu_sepformer.py; forward at this shape: C5.parity"}
         del m, tr
         torch.cuda.empty_cache()
+    # GC: GroupComm TasNet (group_size = 16, the reference's unit_tests.py:69-86 configuration): forward and fused training step at
+    # B = 16 x 4 s, parity of this run against the committed reference golden (tests/golden/groupcomm_g16_b2_t8001.npz)
+    try:
+        gman = json.load(open(os.path.join(ROOT, "tests", "golden", "groupcomm_manifest.json")))["cases"]["g16_b2_t8001"]
+        gz = np.load(os.path.join(ROOT, "tests", "golden", "groupcomm_g16_b2_t8001.npz"))
+        torch.manual_seed(gman["seed"])
+        gm = TasNet(**gman["kwargs"]).to(dev).eval()
+        with torch.no_grad():
+            gpar = HL.rel_l2(gm(torch.from_numpy(gz["x"]).to(dev)).float().cpu(), torch.from_numpy(gz["y"]))
+        gx_h, gt_h = synthetic(16, 4242, T4S)
+        gx_h, gt_h = gx_h.pin_memory(), gt_h.pin_memory()
+        gx, gt = gx_h.to(dev), gt_h.to(dev)
+
+        def gfwd():
+            with torch.no_grad():
+                gm(gx)
+
+        gsec = time_forward(gfwd, 10, 3, flush)
+        gdt, gh2d, gd2h = time_e2e_forward(gm, gx_h, 10, 3)
+        out["GC"] = {"workload": "TasNet(module=DPRNN, group_size=16) GroupComm forward, B=16, 4 s @ 8 kHz, fp32 (SURVEY 8 f1)", "batch": 16,
+                     "metric": "separated audio-sec/sec (forward)", "value": 16 * SECONDS / gsec, "unit": "audio-s/s", "ms_per_forward": 1e3 * gsec,
+                     "gpu_launches_per_forward": int(gm.last_launches), "cuda_graph_replay": bool(gm.cuda_graph),
+                     "parity": {"rel_l2_fp32": gpar, "golden": "groupcomm_g16_b2_t8001 (reference output)", "pass": bool(gpar <= 1e-4)},
+                     "e2e": {"value": 16 * SECONDS / gdt, "unit": "audio-s/s", "ms_per_forward": 1e3 * gdt, "h2d_bytes_per_step": gh2d,
+                             "d2h_bytes_per_step": gd2h}}
+        gm.train()
+        gtr = DualPathTrainer(gm, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False), lr=1e-3, max_norm=5.0)
+        for _ in range(3):
+            gtr.step(gx, gt)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            gloss = gtr.step(gx, gt)
+        e1.record()
+        torch.cuda.synchronize()
+        gts = e0.elapsed_time(e1) * 1e-3 / 5
+        out["GC_train"] = {"workload": "TasNet(module=DPRNN, group_size=16) GroupComm training step, B=16, 4 s @ 8 kHz, fp32: fused forward + PIT "
+                                       "neg-SNR + backward + clip 5.0 + Adam (DualPathTrainer)", "metric": "train samples/sec", "value": 16 / gts,
+                           "unit": "samples/s", "ms_per_step": 1e3 * gts, "gpu_launches_per_step": int(gtr.launches_per_step), "loss": float(gloss),
+                           "parity": "every parameter gradient against the reference's loss.backward(): tests/test_gpu_groupcomm.py (1e-6 total rel-L2)"}
+        del gm, gtr
+        torch.cuda.empty_cache()
+    except Exception as exc:  # informational line: never take the bench down
+        out["GC"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
     # the eager-PyTorch-on-B200 bar for the headline training step (the cuDNN LSTM is the kernel to beat)
     if ref is not None:
         out["C2_eager_b200"] = eager_train_step(ref[0], ref[1], CFG_DPRNN, args.batch, flush)
