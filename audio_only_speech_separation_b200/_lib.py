@@ -48,6 +48,7 @@ PROTOTYPES = {
     "dp_set_fused_lstm": (_i, [_i]),
     "dp_set_lstm_pipeline": (_i, [_i]),
     "dp_set_lstm_tcgen05": (_i, [_i]),
+    "dp_set_wgrad_multicast": (_i, [_i]),
     "dp_set_attention_forward": (_i, [_i]),
     "dp_seg_geometry": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "dp_wave_geometry": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),

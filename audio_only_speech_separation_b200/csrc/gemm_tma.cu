@@ -436,7 +436,30 @@ namespace {
 constexpr int KP = 32;                      // positions per pipeline stage (2 MMAs of K = 16)
 constexpr int BOX = KP * 128;               // one TMA box: KP rows of 64 bf16 = 4 KB (4 swizzle atoms of 8 rows)
 
-template <bool SPLIT>
+// Cluster variant (MC): the four CTAs of a cluster take the four 128-row slices of the output for the SAME position range, so they need the same
+// B tiles: every CTA loads a quarter of the stage's B boxes and multicasts them to all four (cp.async.bulk.tensor ... .multicast::cluster); a
+// stage is free again when all four CTAs have consumed it (tcgen05.commit with a cluster multicast onto every CTA's `empty` barrier).  Without
+// it every B tile crosses L2 -> SM four times and the kernel runs into the L2 bandwidth (measured 7.5 TB/s L2 -> SM at 88 us per launch).
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_w(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "{\n .reg .pred q;\n elect.sync _|q, 0xffffffff;\n"
+        " @q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}\n" ::"r"(smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+template <bool SPLIT, bool MC>
 __global__ void __launch_bounds__(192, 1)
 gemm_tma_tn_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmB0h, const __grid_constant__ CUtensorMap tmB0l,
@@ -454,15 +477,18 @@ gemm_tma_tn_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, MC ? 4 : 1); }
         mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();   // every CTA's barriers exist before a peer multicasts into them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    uint32_t crank = 0;
+    if (MC) asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
 
     const int m0 = blockIdx.y * 128;
     const int pbeg = blockIdx.x * rows_per_cta, pend = min(p.P, pbeg + rows_per_cta);
@@ -486,8 +512,15 @@ gemm_tma_tn_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                     const CUtensorMap* mb0 = pl ? &tmB0l : &tmB0h;
                     const CUtensorMap* mb1 = pl ? &tmB1l : &tmB1h;
                     int bx = 0;
-                    for (int c = 0; c < p.nb0; c += 64, ++bx) tma_load_2d(sb + bx * BOX, mb0, full + stage, c, p0);
-                    for (int c = 0; c < p.nb1; c += 64, ++bx) tma_load_2d(sb + bx * BOX, mb1, full + stage, c, p0);
+                    if (MC) {   // box b of the stage is loaded by CTA (b + plane) % 4 of the cluster and lands in all four
+                        for (int c = 0; c < p.nb0; c += 64, ++bx)
+                            if (((bx + pl) & 3) == (int)crank) tma_load_2d_mc(sb + bx * BOX, mb0, full + stage, c, p0, (uint16_t)0xF);
+                        for (int c = 0; c < p.nb1; c += 64, ++bx)
+                            if (((bx + pl) & 3) == (int)crank) tma_load_2d_mc(sb + bx * BOX, mb1, full + stage, c, p0, (uint16_t)0xF);
+                    } else {
+                        for (int c = 0; c < p.nb0; c += 64, ++bx) tma_load_2d(sb + bx * BOX, mb0, full + stage, c, p0);
+                        for (int c = 0; c < p.nb1; c += 64, ++bx) tma_load_2d(sb + bx * BOX, mb1, full + stage, c, p0);
+                    }
                 }
                 if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
             }
@@ -514,7 +547,8 @@ gemm_tma_tn_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                         umma_w(tmem, al, bh, idesc, 1);
                     }
                 }
-                umma_commit_w(empty + stage);
+                if (MC) umma_commit_mc_w(empty + stage, (uint16_t)0xF);
+                else umma_commit_w(empty + stage);
                 if (it == nst - 1) umma_commit_w(done);
             }
             __syncwarp();
@@ -544,6 +578,7 @@ gemm_tma_tn_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();   // no CTA leaves while a peer may still multicast into its shared memory or arrive on its barriers
     if (warp == 1) tmem_dealloc(tmem, tmem_cols);
 }
 
@@ -561,6 +596,11 @@ bool make_map_mn(CUtensorMap* map, const void* base, long long P, long long cols
 }
 
 }  // namespace
+
+// Measured on B200 (tests/tools/time_wgrad.py, dW_ih | dW_hh of one direction at B = 16): 142 us plain, 144 us with the multicast -- for clusters
+// of <= 4 CTAs the L2 already serves the four unicast requests of a B tile about as cheaply, so the variant is kept (tested) but off by default.
+int g_wgrad_multicast = 0;   // gemm_tma_set_wgrad_multicast
+int gemm_tma_set_wgrad_multicast(int on) { const int prev = g_wgrad_multicast; g_wgrad_multicast = on ? 1 : 0; return prev; }
 
 bool gemm_tma_tn_supported(const TmaWgradArgs& a) {
     if (a.P <= 0 || a.Mo <= 0 || a.Mo % 128) return false;
@@ -589,21 +629,44 @@ cudaError_t launch_gemm_tma_tn(const TmaWgradArgs& a, bool split, cudaStream_t s
     if (stages > 8) stages = 8;
     const int smem = stages * stage_bytes + 1024 + 256;
     const int mtiles = a.Mo / 128;
-    int ksplit = 148 / mtiles;
+    // cluster / multicast variant: the output has a multiple of four 128-row slices.  33 clusters of four CTAs are co-resident on a B200
+    // (cudaOccupancyMaxActiveClusters, tests/tools/ubench_cluster.cu): split the positions over 132 / mtiles ranges so that one wave covers the launch
+    const bool mc = g_wgrad_multicast && (mtiles % 4 == 0);
+    int ksplit = (mc ? 132 : 148) / mtiles;
     if (ksplit < 1) ksplit = 1;
     int rows = ceil_div(ceil_div(a.P, ksplit), KP) * KP;
     if (rows < 4 * KP) rows = 4 * KP;
     dim3 grid(ceil_div(a.P, rows), mtiles);
     const uint32_t tcols = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
     cudaError_t e;
+    if (mc) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 4; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (split) {
+            e = cudaFuncSetAttribute(gemm_tma_tn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            return cudaLaunchKernelEx(&cfg, gemm_tma_tn_kernel<true, true>, mAh, mAl, mB0h, mB0l, mB1h, mB1l, a, rows, stages, tcols);
+        }
+        e = cudaFuncSetAttribute(gemm_tma_tn_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        return cudaLaunchKernelEx(&cfg, gemm_tma_tn_kernel<false, true>, mAh, mAl, mB0h, mB0l, mB1h, mB1l, a, rows, stages, tcols);
+    }
     if (split) {
-        e = cudaFuncSetAttribute(gemm_tma_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(gemm_tma_tn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        gemm_tma_tn_kernel<true><<<grid, 192, smem, st>>>(mAh, mAl, mB0h, mB0l, mB1h, mB1l, a, rows, stages, tcols);
+        gemm_tma_tn_kernel<true, false><<<grid, 192, smem, st>>>(mAh, mAl, mB0h, mB0l, mB1h, mB1l, a, rows, stages, tcols);
     } else {
-        e = cudaFuncSetAttribute(gemm_tma_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(gemm_tma_tn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        gemm_tma_tn_kernel<false><<<grid, 192, smem, st>>>(mAh, mAl, mB0h, mB0l, mB1h, mB1l, a, rows, stages, tcols);
+        gemm_tma_tn_kernel<false, false><<<grid, 192, smem, st>>>(mAh, mAl, mB0h, mB0l, mB1h, mB1l, a, rows, stages, tcols);
     }
     return cudaGetLastError();
 }

@@ -99,6 +99,8 @@ struct TmaWgradArgs {
     float scale;
 };
 bool gemm_tma_tn_supported(const TmaWgradArgs& a);
+// 1: outputs with a multiple of four 128-row slices run as 4-CTA clusters that multicast the shared B tiles; 0 (default): never.  Returns the previous setting.
+int gemm_tma_set_wgrad_multicast(int on);
 cudaError_t launch_gemm_tma_tn(const TmaWgradArgs& a, bool split, cudaStream_t st);
 // fp32 rows [rows, C] (row stride ld) -> bf16 hi / lo planes [rows, C] (lo optional); relu applies max(x, 0) first
 cudaError_t launch_split_rows(const float* src, long long ld, __nv_bfloat16* hi, __nv_bfloat16* lo, long long rows, int C, int relu,

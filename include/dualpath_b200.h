@@ -42,6 +42,9 @@ int dp_set_lstm_pipeline(int mode);
  * tensor memory, lo half in shared memory, 32 sequences per CTA): 1 (default) = automatic (passes with >= 256 sequences per direction),
  * 2 = always, 0 = never (the register-stationary mma.sync kernels selected by dp_set_lstm_pipeline). */
 int dp_set_lstm_tcgen05(int mode);
+/* Weight-gradient GEMM (autograd's dW = dY^T X) as 4-CTA clusters that multicast the shared operand tiles (outputs with a multiple of four
+ * 128-row slices): 1 on, 0 (default) off -- measured equal on B200 (the L2 already shares the four unicast requests).  Returns the previous setting. */
+int dp_set_wgrad_multicast(int on);
 /* Attention forward kernel of the DPTNet / SepFormer engines where both apply (sequences <= 256): 1 = tcgen05 kernel (TMA-fed, scores in
  * tensor memory), 2 = warp-level tensor-core kernel (online softmax, fp32 QKV in), 0 (default) = the faster one per shape and precision
  * as measured (tests/tools/time_attention.py). */

@@ -47,9 +47,19 @@ def test_linear_planes_agrees_with_mma_sync_backend():
     assert rel_l2(c, ref) < 1e-5
 
 
+@pytest.fixture(params=[0, 1], ids=["unicast", "multicast"])
+def wgrad_multicast(request):
+    """Both variants of the weight-gradient GEMM: plain, and 4-CTA clusters multicasting the shared operand tiles (Mo % 512 == 0 only)."""
+    from audio_only_speech_separation_b200 import _lib
+
+    _lib.lib().dp_set_wgrad_multicast(request.param)
+    yield request.param
+    _lib.lib().dp_set_wgrad_multicast(0)
+
+
 @pytest.mark.parametrize("P,Mo,nb0,nb1", [(1000, 128, 64, 0), (5000, 512, 64, 128), (131, 256, 64, 0), (20000, 1024, 64, 0), (9000, 512, 128, 64)])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_wgrad_planes_matches_torch(P, Mo, nb0, nb1, precision):
+def test_wgrad_planes_matches_torch(wgrad_multicast, P, Mo, nb0, nb1, precision):
     from audio_only_speech_separation_b200 import ops
 
     g = torch.Generator().manual_seed(P + Mo)
