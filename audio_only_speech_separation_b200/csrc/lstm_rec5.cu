@@ -179,26 +179,35 @@ __device__ __forceinline__ void r5_issue(uint32_t d, uint32_t a_tm, uint64_t d_w
 
 // forward step s, K blocks 2 PQ and 2 PQ + 1 (hidden units 32 PQ .. 32 PQ + 31 = the h slice tile PQ's warps write) for all four gate tiles.
 // d_w / d_xh / d_xl: descriptors of the W_lo image, the h hi plane and the h lo plane at offset 0.
-template <bool SPLIT, int PQ, int J>
+template <bool SPLIT, int PQ, int J, int NS>
 __device__ __forceinline__ void r5_fwd_tile(uint32_t dcol, uint32_t tmem, uint64_t d_w, uint64_t d_xh, uint64_t d_xl) {
-    constexpr uint32_t IDESC = idesc_bf16(128, R5_NS, 0, 0);
-    constexpr int KB = R5_NS * 128;
-    r5_issue<SPLIT, PQ == 0, J * 32, J * 64 + PQ * 16, ((J * 2 + (PQ >> 1)) * 16384) / 16 + (PQ & 1) * 4, ((PQ >> 1) * KB) / 16 + (PQ & 1) * 4>(
+    constexpr uint32_t IDESC = idesc_bf16(128, NS, 0, 0);
+    constexpr int KB = NS * 128;
+    r5_issue<SPLIT, PQ == 0, J * NS, J * 64 + PQ * 16, ((J * 2 + (PQ >> 1)) * 16384) / 16 + (PQ & 1) * 4, ((PQ >> 1) * KB) / 16 + (PQ & 1) * 4>(
         dcol, tmem, d_w, d_xh, d_xl, IDESC);
 }
-template <bool SPLIT, int PQ>
+// NS = 32: accumulators double buffered, block PQ starts as soon as h slice PQ of the previous step is written.  NS = 64: the four accumulators
+// fill tensor memory (256 columns) and are single buffered, so the first block waits for ALL cell-update warps (they have read the previous step's
+// accumulators by then) and the step's products run after its cell updates.
+template <bool SPLIT, int PQ, int NS>
 __device__ __forceinline__ void r5_fwd_block(uint64_t* h_ready, uint64_t* d_full, int s, uint32_t dcol, uint32_t tmem, uint64_t d_w, uint64_t d_xh,
                                              uint64_t d_xl) {
-    r5_wait(h_ready + PQ, (s - 1) & 1);
+    if (NS == 32) {
+        r5_wait(h_ready + PQ, (s - 1) & 1);
+    } else if (PQ == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r5_wait(h_ready + j, (s - 1) & 1);
+    }
     tc_fence_after();
-    r5_fwd_tile<SPLIT, PQ, 0>(dcol, tmem, d_w, d_xh, d_xl);
-    if (PQ == 3) umma_commit_w(d_full + (s & 1) * 4 + 0);
-    r5_fwd_tile<SPLIT, PQ, 1>(dcol, tmem, d_w, d_xh, d_xl);
-    if (PQ == 3) umma_commit_w(d_full + (s & 1) * 4 + 1);
-    r5_fwd_tile<SPLIT, PQ, 2>(dcol, tmem, d_w, d_xh, d_xl);
-    if (PQ == 3) umma_commit_w(d_full + (s & 1) * 4 + 2);
-    r5_fwd_tile<SPLIT, PQ, 3>(dcol, tmem, d_w, d_xh, d_xl);
-    if (PQ == 3) umma_commit_w(d_full + (s & 1) * 4 + 3);
+    uint64_t* df = NS == 32 ? d_full + (s & 1) * 4 : d_full;
+    r5_fwd_tile<SPLIT, PQ, 0, NS>(dcol, tmem, d_w, d_xh, d_xl);
+    if (PQ == 3) umma_commit_w(df + 0);
+    r5_fwd_tile<SPLIT, PQ, 1, NS>(dcol, tmem, d_w, d_xh, d_xl);
+    if (PQ == 3) umma_commit_w(df + 1);
+    r5_fwd_tile<SPLIT, PQ, 2, NS>(dcol, tmem, d_w, d_xh, d_xl);
+    if (PQ == 3) umma_commit_w(df + 2);
+    r5_fwd_tile<SPLIT, PQ, 3, NS>(dcol, tmem, d_w, d_xh, d_xl);
+    if (PQ == 3) umma_commit_w(df + 3);
 }
 
 // BPTT step, unit quadrant Q: packed gate columns 128 Q .. 128 Q + 127 = K blocks 8 Q .. 8 Q + 7 = 64-wide blocks 2 Q, 2 Q + 1
@@ -231,9 +240,9 @@ static_assert(128 * 40 + 512 * 104 <= 640 * 96, "setmaxnreg budget exceeds the l
 
 // position bases of the tile's sequences (invalid slots alias the tile's first sequence: loads harmless, stores suppressed).
 // SPREAD: the v-th sequence sits in slot (v & 3) * 8 + (v >> 2) (BPTT: equal work for the four sequence octets), else in slot v.
-template <bool SPREAD>
+template <bool SPREAD, int NS = R5_NS>
 __device__ __forceinline__ void r5_fill_bases(int* sbase, int q0, int nv, const SeqMap& m) {
-    if (threadIdx.x < R5_NS) {
+    if (threadIdx.x < NS) {
         const int n = (int)threadIdx.x;
         const int v = SPREAD ? (n & 7) * 4 + (n >> 3) : n;
         const int q = v < nv ? q0 + v : q0;
@@ -242,10 +251,11 @@ __device__ __forceinline__ void r5_fill_bases(int* sbase, int q0, int nv, const 
 }
 
 // ================================================================================================ forward
-template <bool SPLIT, bool SAVE>
+template <bool SPLIT, bool SAVE, int NS>
 __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Args p) {
     constexpr int PL = SPLIT ? 2 : 1;
-    constexpr int KB = R5_NS * 128;                 // one 64-wide K block of the h tile: [32 rows][128 B]
+    constexpr int HALVES = NS / 32;                 // 32-sequence column blocks of the accumulators (NS = 32 or 64 sequence slots)
+    constexpr int KB = NS * 128;                    // one 64-wide K block of the h tile: [NS rows][128 B]
     constexpr int PLANE = 2 * KB;                   // one plane (hi or lo) of the h tile
     constexpr int OFF_H = SPLIT ? R5_IMG : 0;
     constexpr int OFF_G = OFF_H + PL * PLANE;       // staged gate pre-activations: [16 warps][8 cells][32 lanes] x 16 B = 64 KB
@@ -256,7 +266,7 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
     uint64_t* h_ready = d_full + 8;                                   // [4 tiles]
     uint64_t* h_copied = h_ready + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_copied + 1);
-    int* sbase = reinterpret_cast<int*>(tmem_slot + 2);               // [32]
+    int* sbase = reinterpret_cast<int*>(tmem_slot + 2);               // [NS]
     uint8_t* hs = smem + OFF_H;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
         mbar_init(h_copied, 3);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    r5_fill_bases<false>(sbase, q0, nv, p.m);
+    r5_fill_bases<false, NS>(sbase, q0, nv, p.m);
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (SPLIT) {
         const uint4* src = p.w_sm + (size_t)dir * (R5_IMG / 16);
@@ -313,11 +323,11 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
         const uint64_t d_w = desc_sw128(smem_u32(smem), 16, 1024), d_xh = desc_sw128(smem_u32(hs), 16, 1024);
         const uint64_t d_xl = d_xh + (uint64_t)(PLANE >> 4);
         for (int s = 1; s < len; ++s) {
-            const uint32_t dcol = tmem + 256 + (uint32_t)((s & 1) * 128);
-            r5_fwd_block<SPLIT, 0>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
-            r5_fwd_block<SPLIT, 1>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
-            r5_fwd_block<SPLIT, 2>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
-            r5_fwd_block<SPLIT, 3>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+            const uint32_t dcol = tmem + 256 + (NS == 32 ? (uint32_t)((s & 1) * 128) : 0u);
+            r5_fwd_block<SPLIT, 0, NS>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+            r5_fwd_block<SPLIT, 1, NS>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+            r5_fwd_block<SPLIT, 2, NS>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+            r5_fwd_block<SPLIT, 3, NS>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
             __syncwarp();
         }
     } else if (warp < 4) {
@@ -325,7 +335,7 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
         const int cl = (warp - 1) * 32 + lane;
         if (SAVE && p.pl.hp_hi != nullptr) {  // h_prev of the first visited step is zero
             const long long t0 = (long long)(dir ? len - 1 : 0) * s_t;
-            for (int ch = cl; ch < R5_NS * 16; ch += 96) {
+            for (int ch = cl; ch < NS * 16; ch += 96) {
                 const int n = ch >> 4, u = ch & 15;
                 if (n >= nv) continue;
                 const size_t o = (size_t)(sbase[n] + t0) * 256 + dir * kH + u * 8;
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
 #pragma unroll
             for (int pq = 0; pq < 4; ++pq) r5_wait(h_ready + pq, s & 1);
             if (any) {
-                for (int ch = cl; ch < R5_NS * 16; ch += 96) {
+                for (int ch = cl; ch < NS * 16; ch += 96) {
                     const int n = ch >> 4, u = ch & 15;
                     if (n >= nv) continue;
                     const uint32_t off = (u >> 3) * KB + n * 128 + (((u & 7) ^ (n & 7)) << 4);
@@ -370,25 +380,26 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
         // tile 0 goes to the highest warp ids: the scheduler favours them, so the slice the next step's first K blocks wait for is done first
         const int j = 3 - ((warp - 4) >> 2), q = warp & 3, u8 = lane >> 2, c = lane & 3;
         const int unit = 32 * j + 8 * q + u8;
-        const uint32_t acc_addr = tmem + ((uint32_t)(q * 32) << 16) + 256 + (uint32_t)(j * 32);
+        const uint32_t acc_addr = tmem + ((uint32_t)(q * 32) << 16) + 256 + (uint32_t)(j * NS);
         float* const Gc = p.G + (size_t)dir * kG + unit * 4;
         float* const Cc = p.Cst + (size_t)dir * kH + unit;
         float* const Hc = p.H + (size_t)dir * kH + unit;
         const bool has_h = p.H != nullptr;
-        // h tile offsets of cells (k, e): row n = 8k + 2c + e -> 1024 k + (2c + e) * 128, swizzle term (chunk ^ (2c + e)) << 4 (independent of k)
-        const int chunk = (unit & 63) >> 3;
         // even unit of a pair stores sequence 2c of both units, odd unit sequence 2c + 1: 4 bytes at the even unit's column
+        // (row n = 8k + 2c + odd -> 1024 k + rowe * 128, swizzle term (chunk ^ rowe) << 4, independent of k)
+        const int chunk = (unit & 63) >> 3;
         const int odd = u8 & 1, rowe = 2 * c + odd;
         const uint32_t hrow = smem_u32(hs) + (uint32_t)((unit >> 6) * KB + (u8 & 6) * 2 + rowe * 128 + ((chunk ^ rowe) << 4));
         const uint32_t sel_send = odd ? 0x5410u : 0x7632u, sel_hi = odd ? 0x3254u : 0x5410u, sel_lo = odd ? 0x3276u : 0x7610u;
-        // the step's gate pre-activations (one 128-bit word per cell) are staged one step ahead into this thread's own shared-memory slots
+        // the step's gate pre-activations (one 128-bit word per cell) are staged ahead into this thread's own shared-memory slots: eight slots =
+        // one 32-sequence half; NS = 64 stages its second half while the first one is being consumed
         const uint32_t gst_s = smem_u32(smem + OFF_G) + (uint32_t)(((warp - 4) * 256 + lane) * 16);
         const int kmax = (nv + 7) >> 3;   // sequence octets in use (warp-uniform)
-        unsigned sb[8];
+        unsigned sb[8 * HALVES];
         unsigned valid = 0;
-        float cst[8];
+        float cst[8 * HALVES];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8 * HALVES; ++i) {
             const int n = 8 * (i >> 1) + 2 * c + (i & 1);
             sb[i] = (unsigned)sbase[n];
             valid |= (n < nv ? 1u : 0u) << i;
@@ -396,67 +407,73 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
         }
         const int dstep = dir ? -(int)s_t : (int)s_t;
         unsigned toff = dir ? (unsigned)((len - 1) * (int)s_t) : 0u;
+        auto stage = [&](int hf, unsigned to) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if ((i >> 1) < kmax) cp_async16_s(gst_s + i * 512, Gc + (size_t)(sb[i] + toff) * 1024);
-        asm volatile("cp.async.commit_group;\n" ::);
+            for (int i = 0; i < 8; ++i)
+                if (4 * hf + (i >> 1) < kmax) cp_async16_s(gst_s + i * 512, Gc + (size_t)(sb[8 * hf + i] + to) * 1024);
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
+        stage(0, toff);
         for (int s = 0; s < len; ++s) {
-            uint32_t ra[16], rb[16];
             if (s > 0) {
-                r5_wait(d_full + (s & 1) * 4 + j, (uint32_t)(((s - 2 + (s & 1)) >> 1) & 1));
+                if (NS == 32) r5_wait(d_full + (s & 1) * 4 + j, (uint32_t)(((s - 2 + (s & 1)) >> 1) & 1));
+                else r5_wait(d_full + j, (uint32_t)((s - 1) & 1));
                 tc_fence_after();
-                tmem_ld_16x256b_x4(acc_addr + (uint32_t)((s & 1) * 128), ra);                  // lanes 0..15: i rows, f rows
-                tmem_ld_16x256b_x4(acc_addr + (uint32_t)((s & 1) * 128) + (16u << 16), rb);    // lanes 16..31: g rows, o rows
-                tmem_ld_wait();
-                r5_wait(h_copied, (s - 1) & 1);   // the copy-out warps are done with the previous h tile
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { ra[i] = 0u; rb[i] = 0u; }
             }
-            asm volatile("cp.async.wait_all;\n" ::: "memory");   // this thread's own staged words
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (k < kmax) {
-                    float hh[2];
+            for (int hf = 0; hf < HALVES; ++hf) {
+                if (hf > 0) stage(hf, toff);   // the slots of the previous half were read below
+                uint32_t ra[16], rb[16];
+                if (s > 0) {
+                    const uint32_t col = (NS == 32 ? (uint32_t)((s & 1) * 128) : 0u) + (uint32_t)(hf * 32);
+                    tmem_ld_16x256b_x4(acc_addr + col, ra);                  // lanes 0..15: i rows, f rows
+                    tmem_ld_16x256b_x4(acc_addr + col + (16u << 16), rb);    // lanes 16..31: g rows, o rows
+                    tmem_ld_wait();
+                    if (hf == 0) r5_wait(h_copied, (s - 1) & 1);   // the copy-out warps are done with the previous h tile
+                } else {
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int i = 2 * k + e;
-                        const float4 gp = lds128(gst_s + i * 512);
-                        const bool vld = (valid >> i) & 1u;
-                        const float ig = sigmoid_cell<SPLIT>(__uint_as_float(ra[4 * k + e]) + gp.x);
-                        const float fg = sigmoid_cell<SPLIT>(__uint_as_float(ra[4 * k + 2 + e]) + gp.y);
-                        const float gg = tanh_cell<SPLIT>(__uint_as_float(rb[4 * k + e]) + gp.z);
-                        const float og = sigmoid_cell<SPLIT>(__uint_as_float(rb[4 * k + 2 + e]) + gp.w);
-                        const float cc = fmaf(fg, cst[i], ig * gg);
-                        cst[i] = cc;
-                        hh[e] = og * tanh_cell<SPLIT>(cc);
-                        const size_t pos = (size_t)(sb[i] + toff);
-                        if (has_h) stg_pred(Hc + pos * 256, hh[e], vld);
-                        if (SAVE) {
-                            stg_pred(Cc + pos * 256, cc, vld);
-                            stg_pred(reinterpret_cast<float4*>(Gc + pos * 1024), ig, fg, gg, og, vld);
+                    for (int i = 0; i < 16; ++i) { ra[i] = 0u; rb[i] = 0u; }
+                }
+                asm volatile("cp.async.wait_all;\n" ::: "memory");   // this thread's own staged words
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (4 * hf + k < kmax) {
+                        float hh[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int i = 8 * hf + 2 * k + e;
+                            const float4 gp = lds128(gst_s + (2 * k + e) * 512);
+                            const bool vld = (valid >> i) & 1u;
+                            const float ig = sigmoid_cell<SPLIT>(__uint_as_float(ra[4 * k + e]) + gp.x);
+                            const float fg = sigmoid_cell<SPLIT>(__uint_as_float(ra[4 * k + 2 + e]) + gp.y);
+                            const float gg = tanh_cell<SPLIT>(__uint_as_float(rb[4 * k + e]) + gp.z);
+                            const float og = sigmoid_cell<SPLIT>(__uint_as_float(rb[4 * k + 2 + e]) + gp.w);
+                            const float cc = fmaf(fg, cst[i], ig * gg);
+                            cst[i] = cc;
+                            hh[e] = og * tanh_cell<SPLIT>(cc);
+                            const size_t pos = (size_t)(sb[i] + toff);
+                            if (has_h) stg_pred(Hc + pos * 256, hh[e], vld);
+                            if (SAVE) {
+                                stg_pred(Cc + pos * 256, cc, vld);
+                                stg_pred(reinterpret_cast<float4*>(Gc + pos * 1024), ig, fg, gg, og, vld);
+                            }
                         }
+                        // h -> bf16 hi / lo with packed conversions; the two lanes of a unit pair (lane ^ 4) swap one sequence each, so that every
+                        // lane stores ONE 32-bit word (two neighbouring units of one sequence) per plane: no 16-bit stores, no bank conflicts
+                        uint32_t Hw, Lw = 0u;
+                        if (SPLIT) split_pair_packed(hh[0], hh[1], Hw, Lw);
+                        else Hw = cvt_bf16x2(hh[0], hh[1]);
+                        const uint32_t recv = __shfl_xor_sync(0xffffffffu, __byte_perm(Hw, Lw, sel_send), 4);
+                        sts32(hrow + (uint32_t)((4 * hf + k) * 1024), __byte_perm(Hw, recv, sel_hi));
+                        if (SPLIT) sts32(hrow + (uint32_t)((4 * hf + k) * 1024 + PLANE), __byte_perm(Lw, recv, sel_lo));
                     }
-                    // h -> bf16 hi / lo with packed conversions; the two lanes of a unit pair (lane ^ 4) swap one sequence each, so that every
-                    // lane stores ONE 32-bit word (two neighbouring units of one sequence) per plane: no 16-bit stores, no bank conflicts
-                    uint32_t Hw, Lw = 0u;
-                    if (SPLIT) split_pair_packed(hh[0], hh[1], Hw, Lw);
-                    else Hw = cvt_bf16x2(hh[0], hh[1]);
-                    const uint32_t recv = __shfl_xor_sync(0xffffffffu, __byte_perm(Hw, Lw, sel_send), 4);
-                    sts32(hrow + (uint32_t)(k * 1024), __byte_perm(Hw, recv, sel_hi));
-                    if (SPLIT) sts32(hrow + (uint32_t)(k * 1024 + PLANE), __byte_perm(Lw, recv, sel_lo));
                 }
             }
             proxy_fence_async();  // h slice (generic-proxy stores) -> visible to the tensor core's async proxy
             tc_fence_before();
             mbar_arrive(h_ready + j);
             toff += (unsigned)dstep;
-            if (s + 1 < len) {     // next step's words: the slots were read above
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if ((i >> 1) < kmax) cp_async16_s(gst_s + i * 512, Gc + (size_t)(sb[i] + toff) * 1024);
-                asm volatile("cp.async.commit_group;\n" ::);
-            }
+            if (s + 1 < len) stage(0, toff);   // next step's first half: the slots were read above
         }
     }
     tc_fence_before();
@@ -714,14 +731,18 @@ int lstm_get_rec5() { return g_rec5; }
 // Automatic choice, measured on B200 (tests/tools/time_rec5.py, intra / inter pass, training mode, us):
 //   B = 16 fp32: forward 395 / 357 against 503 / 420 (mma.sync), BPTT 348 / 310 against 645 / 545
 //   B = 16 bf16: forward 378 / 379 against 320 / 297 -> mma.sync, BPTT 290 / 275 against 448 / 393
-//   B = 32 fp32: forward 1115 / 912 against 1031 / 847 (two waves of 32-sequence tiles) -> mma.sync, BPTT 883 / 736 against 1309 / 1082
+//   B = 32 fp32: forward with 64-sequence tiles 846 / 880 against 1032 / 849, BPTT 880 / 732 against 1322 / 1090
 bool lstm_rec5_wanted(const SeqMap& m, bool split, bool backward) {
     if (g_rec5 == 0) return false;
     if (g_rec5 == 2) return true;
     if (lstm_get_pipeline() != 1) return false;   // an explicitly selected mma.sync variant (dp_set_lstm_pipeline) is honoured
     if (m.nseq < 256) return false;               // small passes: the evenly spread mma.sync kernels keep more SMs busy
     if (backward) return true;
-    return split && ceil_div(m.nseq, R5_NS) <= 74;   // forward: fp32-parity mode, one wave of tiles
+    if (!split) return false;                      // forward: fp32-parity mode only
+    if (ceil_div(m.nseq, R5_NS) <= 74) return true;   // one wave of 32-sequence tiles
+    // 64-sequence tiles (accumulators single buffered, two column halves per step): B = 32 intra 846 us against 1 032 (mma.sync), inter (44
+    // sequences per CTA = six octets) 880 against 849 -> only while a CTA holds at most five sequence octets
+    return ceil_div(m.nseq, 64) <= 74 && ceil_div(lstm_seqs_per_cta(m.nseq, 64), 8) <= 5;
 }
 
 cudaError_t launch_lstm_rec5_fwd(const void* pack, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, cudaStream_t st,
@@ -733,18 +754,25 @@ cudaError_t launch_lstm_rec5_fwd(const void* pack, float* G, float* H, float* Cs
     a.w_tm = reinterpret_cast<const uint32_t*>(b);
     a.w_sm = reinterpret_cast<const uint4*>(b + (size_t)2 * R5_IMG);
     a.G = G; a.H = H; a.Cst = Cst; a.pl = pl; a.m = m;
-    a.spc = lstm_seqs_per_cta(m.nseq, R5_NS);
+    // 32-sequence tiles while one wave of them covers the pass (B <= 28 at the bench geometry), 64-sequence tiles beyond
+    const int ns = ceil_div(m.nseq, R5_NS) <= 74 ? R5_NS : 64;
+    a.spc = lstm_seqs_per_cta(m.nseq, ns);
     dim3 grid(ceil_div(m.nseq, a.spc), 2);
-    const int smem = (split ? R5_IMG : 0) + (split ? 2 : 1) * 2 * R5_NS * 128 + 16 * 8 * 32 * 16 + 512 + 1024;
+    const int smem = (split ? R5_IMG : 0) + (split ? 2 : 1) * 2 * ns * 128 + 16 * 8 * 32 * 16 + 512 + 1024;
     cudaError_t e;
-#define DP_R5F(SP, SV)                                                                                              \
-    do {                                                                                                            \
-        e = cudaFuncSetAttribute(lstm_rec5_fwd_kernel<SP, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
-        if (e != cudaSuccess) return e;                                                                             \
-        lstm_rec5_fwd_kernel<SP, SV><<<grid, R5_THREADS, smem, st>>>(a);                                            \
+#define DP_R5F(SP, SV, NSV)                                                                                              \
+    do {                                                                                                                 \
+        e = cudaFuncSetAttribute(lstm_rec5_fwd_kernel<SP, SV, NSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
+        if (e != cudaSuccess) return e;                                                                                  \
+        lstm_rec5_fwd_kernel<SP, SV, NSV><<<grid, R5_THREADS, smem, st>>>(a);                                            \
     } while (0)
-    if (split) { if (save) DP_R5F(true, true); else DP_R5F(true, false); }
-    else       { if (save) DP_R5F(false, true); else DP_R5F(false, false); }
+    if (ns == R5_NS) {
+        if (split) { if (save) DP_R5F(true, true, 32); else DP_R5F(true, false, 32); }
+        else       { if (save) DP_R5F(false, true, 32); else DP_R5F(false, false, 32); }
+    } else {
+        if (split) { if (save) DP_R5F(true, true, 64); else DP_R5F(true, false, 64); }
+        else       { if (save) DP_R5F(false, true, 64); else DP_R5F(false, false, 64); }
+    }
 #undef DP_R5F
     return cudaGetLastError();
 }
