@@ -987,19 +987,22 @@ __device__ __forceinline__ float block_sum_f(float v, float* sh) {   // sh: 32 f
     return s;
 }
 
-// ---- BiLSTM forward that also saves (i, f, g, o, c) per step: S5 [item = pos * G + g][dir][HG][5] ------------------------------------
+// 4-byte asynchronous global -> shared copies: the LSTM kernels below keep several time steps of their operands in flight this way (one
+// thread advances one time step per ~0.5 us, while a load takes ~1 us under the write traffic of these kernels)
+__device__ __forceinline__ void gct_cp4(void* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gct_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void gct_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- BiLSTM forward that also saves (i, f, g, o, c) per step: S5 [item = pos * G + g][dir][5][HG] ------------------------------------
 template <int NG, int HG>
 __global__ void __launch_bounds__(128) gct_lstm_kernel(const float* __restrict__ X, float* __restrict__ Hh, float* __restrict__ S5, RnnW w,
                                                        long long nouter, int G, int len, int qdiv, long long s_hi, long long s_lo, long long s_t) {
+    static_assert(128 % HG == 0, "a CTA holds whole unit groups");
     const int dir = blockIdx.y;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = (int)(i % HG);
-    const long long q = i / HG;
-    const bool active = q < nouter * G;
-    const long long qc = active ? q : nouter * G - 1;
-    const int g = (int)(qc % G);
-    const long long o = qc / G;
-    const long long bp = (o / qdiv) * s_hi + (o % qdiv) * s_lo;
+    const int j = threadIdx.x % HG;
     float wi[4][NG], wh[4][HG], b[4];
 #pragma unroll
     for (int gt = 0; gt < 4; ++gt) {
@@ -1011,15 +1014,40 @@ __global__ void __launch_bounds__(128) gct_lstm_kernel(const float* __restrict__
         b[gt] = __ldg(w.bih[dir] + row) + __ldg(w.bhh[dir] + row);
     }
     const int C = G * NG;
+    const int dt = dir ? -1 : 1;
+    // the input of a (sequence, group) is the same for its HG unit lanes: lane j == 0 requests it FD steps ahead into shared memory
+    constexpr int FD = 8;
+    __shared__ float xring[FD][128 / HG][NG];
+    const int grp = threadIdx.x / HG;
+    // a CTA walks several blocks of 128 / HG sequences: the weights stay in registers
+    for (long long blk = blockIdx.x; blk * (128 / HG) < nouter * G; blk += gridDim.x) {
+    const long long q = blk * (128 / HG) + grp;
+    const bool active = q < nouter * G;
+    const long long qc = active ? q : nouter * G - 1;
+    const int g = (int)(qc % G);
+    const long long o = qc / G;
+    const long long bp = (o / qdiv) * s_hi + (o % qdiv) * s_lo;
     float h = 0.f, c = 0.f;
     int t = dir ? len - 1 : 0;
-    const int dt = dir ? -1 : 1;
+    auto request = [&](int step) {
+        if (step < len && j == 0) {
+            const int tt = dir ? len - 1 - step : step;
+            const float* src = X + (bp + (long long)tt * s_t) * C + g * NG;
+#pragma unroll
+            for (int k = 0; k < NG; ++k) gct_cp4(&xring[step % FD][grp][k], src + k);
+        }
+        gct_cp_commit();
+    };
+    for (int step = 0; step < FD - 1; ++step) request(step);
     for (int step = 0; step < len; ++step, t += dt) {
         const long long pos = bp + (long long)t * s_t;
         float a[4] = {b[0], b[1], b[2], b[3]};
+        request(step + FD - 1);
+        gct_cp_wait<FD - 1>();
+        __syncwarp();
 #pragma unroll
         for (int k = 0; k < NG; ++k) {
-            const float xk = X[pos * C + g * NG + k];
+            const float xk = xring[step % FD][grp][k];
 #pragma unroll
             for (int gt = 0; gt < 4; ++gt) a[gt] = fmaf(wi[gt][k], xk, a[gt]);
         }
@@ -1034,9 +1062,11 @@ __global__ void __launch_bounds__(128) gct_lstm_kernel(const float* __restrict__
         h = og * tanh_cell<true>(c);
         if (active) {
             Hh[(pos * G + g) * 2 * HG + dir * HG + j] = h;
-            float* s5 = S5 + (((pos * G + g) * 2 + dir) * HG + j) * 5;
-            s5[0] = ig; s5[1] = fg; s5[2] = gg; s5[3] = og; s5[4] = c;
+            float* s5 = S5 + ((pos * G + g) * 2 + dir) * 5 * HG + j;
+            s5[0] = ig; s5[HG] = fg; s5[2 * HG] = gg; s5[3 * HG] = og; s5[4 * HG] = c;
         }
+        __syncwarp();   // lane 0 requests into this step's ring slot again in the next iteration
+    }
     }
 }
 
@@ -1051,15 +1081,9 @@ __global__ void __launch_bounds__(128) gct_lstm_bwd_kernel(const float* __restri
     __shared__ float acc_sm[HG * NACC];
     for (int i = threadIdx.x; i < HG * NACC; i += blockDim.x) acc_sm[i] = 0.f;
     __syncthreads();
+    static_assert(128 % HG == 0, "a CTA holds whole unit groups");
     const int dir = blockIdx.y;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = (int)(i % HG);
-    const long long q = i / HG;
-    const bool active = q < nouter * G;
-    const long long qc = active ? q : nouter * G - 1;
-    const int g = (int)(qc % G);
-    const long long o = qc / G;
-    const long long bp = (o / qdiv) * s_hi + (o % qdiv) * s_lo;
+    const int j = threadIdx.x % HG;
     float wi[4][NG], whc[4][HG];   // whc[gt][k] = W_hh[gt * HG + k][j]: what unit k's gate gradients send back to h_j
 #pragma unroll
     for (int gt = 0; gt < 4; ++gt) {
@@ -1078,18 +1102,53 @@ __global__ void __launch_bounds__(128) gct_lstm_bwd_kernel(const float* __restri
         for (int k = 0; k < NG; ++k) aWih[gt][k] = 0.f;
     }
     const int C = G * NG;
+    // What one step reads from global memory is requested BD steps ahead into a shared-memory ring (cp.async): per thread the saved gates
+    // and cell state, the previous h and the incoming gradient; per (sequence, group) the LSTM input, requested by lane j == 0.
+    constexpr int BD = 4;
+    __shared__ float ring[BD][8][128];
+    __shared__ float xring[BD][128 / HG][NG];
+    const int grp = threadIdx.x / HG;
+    // a CTA walks several blocks of 128 / HG sequences: weights and gradient accumulators stay in registers, one reduction at the end
+    for (long long blk = blockIdx.x; blk * (128 / HG) < nouter * G; blk += gridDim.x) {
+    const long long q = blk * (128 / HG) + grp;
+    const bool active = q < nouter * G;
+    const long long qc = active ? q : nouter * G - 1;
+    const int g = (int)(qc % G);
+    const long long o = qc / G;
+    const long long bp = (o / qdiv) * s_hi + (o % qdiv) * s_lo;
     float dh_rec = 0.f, dc_carry = 0.f;
+    auto item_of = [&](int s) { return (bp + (long long)(dir ? s : len - 1 - s) * s_t) * G + g; };   // reverse of the forward visiting order
+    auto request = [&](int s) {
+        if (s < len) {
+            const int t = dir ? s : len - 1 - s;
+            const int tp = dir ? t + 1 : t - 1;              // the step the forward visited just before t
+            const long long pos = bp + (long long)t * s_t, item = pos * G + g;
+            const float* s5 = S5 + (item * 2 + dir) * 5 * HG + j;
+            const int st = s % BD;
+#pragma unroll
+            for (int q5 = 0; q5 < 5; ++q5) gct_cp4(&ring[st][q5][threadIdx.x], s5 + q5 * HG);
+            if (s != len - 1) gct_cp4(&ring[st][5][threadIdx.x], Hh + ((bp + (long long)tp * s_t) * G + g) * 2 * HG + dir * HG + j);
+            gct_cp4(&ring[st][6][threadIdx.x], dHh + item * 2 * HG + dir * HG + j);
+            if (j == 0) {
+#pragma unroll
+                for (int k = 0; k < NG; ++k) gct_cp4(&xring[st][grp][k], X + pos * C + g * NG + k);
+            }
+        }
+        gct_cp_commit();
+    };
+    for (int s = 0; s < BD - 1; ++s) request(s);
     for (int s = 0; s < len; ++s) {
-        const int t = dir ? s : len - 1 - s;             // reverse of the forward visiting order
-        const int tp = dir ? t + 1 : t - 1;              // the step the forward visited just before t
         const bool first = (s == len - 1);
-        const long long pos = bp + (long long)t * s_t, item = pos * G + g;
-        const long long ppos = bp + (long long)tp * s_t, pitem = ppos * G + g;
-        const float* s5 = S5 + ((item * 2 + dir) * HG + j) * 5;
-        const float ig = s5[0], fg = s5[1], gg = s5[2], og = s5[3], c = s5[4];
-        const float cp = first ? 0.f : S5[((pitem * 2 + dir) * HG + j) * 5 + 4];
-        const float hp = first ? 0.f : Hh[pitem * 2 * HG + dir * HG + j];
-        const float dh = dHh[item * 2 * HG + dir * HG + j] + dh_rec;
+        request(s + BD - 1);
+        if (first) gct_cp_wait<0>(); else gct_cp_wait<BD - 2>();   // step s and, for its starting cell state, step s + 1
+        __syncwarp();
+        const int st = s % BD;
+        const long long item = item_of(s);
+        const float ig = ring[st][0][threadIdx.x], fg = ring[st][1][threadIdx.x], gg = ring[st][2][threadIdx.x], og = ring[st][3][threadIdx.x];
+        const float c = ring[st][4][threadIdx.x];
+        const float cp = first ? 0.f : ring[(s + 1) % BD][4][threadIdx.x];   // the cell state the forward step started from
+        const float hp = first ? 0.f : ring[st][5][threadIdx.x];
+        const float dh = ring[st][6][threadIdx.x] + dh_rec;
         const float tc = tanh_cell<true>(c);
         const float dc = fmaf(dh * og, 1.f - tc * tc, dc_carry);
         dc_carry = dc * fg;
@@ -1102,10 +1161,13 @@ __global__ void __launch_bounds__(128) gct_lstm_bwd_kernel(const float* __restri
         float xk[NG], px[NG];
 #pragma unroll
         for (int k = 0; k < NG; ++k) {
-            xk[k] = X[pos * C + g * NG + k];
+            xk[k] = xring[st][grp][k];
             px[k] = 0.f;
         }
         dh_rec = 0.f;
+        float hpk[HG];
+#pragma unroll
+        for (int k = 0; k < HG; ++k) hpk[k] = __shfl_sync(0xffffffffu, hp, k, HG);
 #pragma unroll
         for (int gt = 0; gt < 4; ++gt) {
             ab[gt] += dg[gt];
@@ -1116,7 +1178,7 @@ __global__ void __launch_bounds__(128) gct_lstm_bwd_kernel(const float* __restri
             }
 #pragma unroll
             for (int k = 0; k < HG; ++k) {
-                aWhh[gt][k] = fmaf(dg[gt], __shfl_sync(0xffffffffu, hp, k, HG), aWhh[gt][k]);
+                aWhh[gt][k] = fmaf(dg[gt], hpk[k], aWhh[gt][k]);
                 dh_rec = fmaf(whc[gt][k], __shfl_sync(0xffffffffu, dg[gt], k, HG), dh_rec);
             }
         }
@@ -1129,6 +1191,8 @@ __global__ void __launch_bounds__(128) gct_lstm_bwd_kernel(const float* __restri
 #pragma unroll
             for (int k = 0; k < NG; ++k) dXd[(long long)dir * nitems * NG + item * NG + k] = px[k];
         }
+        __syncwarp();   // the ring slot of this step is requested again by lane 0 in the next iteration
+    }
     }
     // reduce the weight-gradient accumulators over the CTA's sequences (shared-memory atomics), then one global atomic per element
     float* mine = acc_sm + j * NACC;
@@ -1154,46 +1218,78 @@ __global__ void __launch_bounds__(128) gct_lstm_bwd_kernel(const float* __restri
 template <int NG>
 __global__ void __launch_bounds__(256) gct_gn_sums_kernel(const float* __restrict__ dO, const float* __restrict__ Y, const double* __restrict__ stats,
                                                           const float* __restrict__ gamma, double* __restrict__ bst, float* __restrict__ dgamma,
-                                                          float* __restrict__ dbeta, int total, int G, int pps, double eps) {
+                                                          float* __restrict__ dbeta, int total, int G, int pps, double eps, int tiles_per_cta) {
+    // A CTA walks a contiguous run of 256-item tiles.  The (sample, group) sums are gathered in shared memory and leave as one fp64 atomic
+    // per group whenever the run crosses into another sample (items of a tile that belong to the next sample go to global memory directly);
+    // dgamma / dbeta stay in registers until the end of the run.
     __shared__ float sh[32];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < total;
+    __shared__ float acc[64];   // [G][2], G <= 32
     const int gshift = 31 - __clz(G);
-    const int ic = active ? i : total - 1;
-    const int pos = ic >> gshift, g = ic & (G - 1);
-    const double* d = stats + 2 * ((size_t)(pos / pps) * G + g);
-    const double inv = 1.0 / ((double)pps * NG), mean = d[0] * inv;
-    double var = d[1] * inv - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + eps));
-    float s1 = 0.f, s2 = 0.f, dga[NG], dbe[NG];
+    if (threadIdx.x < 64) acc[threadIdx.x] = 0.f;
+    __syncthreads();
+    float dga[NG], dbe[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) dga[k] = dbe[k] = 0.f;
+    const int ntiles = (total + 255) >> 8;
+    const int tile0 = blockIdx.x * tiles_per_cta, tile1 = min(tile0 + tiles_per_cta, ntiles);
+    int held = -1;   // the sample whose sums are in acc
+    auto flush = [&]() {
+        __syncthreads();
+        if (held >= 0 && threadIdx.x < 2 * G) {
+            atomicAdd(bst + 2 * (size_t)held * G + threadIdx.x, (double)acc[threadIdx.x]);
+            acc[threadIdx.x] = 0.f;
+        }
+        __syncthreads();
+    };
+    for (int tile = tile0; tile < tile1; ++tile) {
+        const int first_sample = ((tile << 8) >> gshift) / pps;
+        if (first_sample != held) {
+            flush();
+            held = first_sample;
+        }
+        const int i = (tile << 8) + threadIdx.x;
+        if (i < total) {
+            const int pos = i >> gshift, g = i & (G - 1), smp = pos / pps;
+            const double* d = stats + 2 * ((size_t)smp * G + g);
+            const double inv = 1.0 / ((double)pps * NG), mean = d[0] * inv;
+            double var = d[1] * inv - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + eps));
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < NG; ++k) {
+                const float go = dO[(size_t)i * NG + k];
+                const float yh = (Y[(size_t)i * NG + k] - mu) * rstd;
+                const float ga = __ldg(gamma + k);
+                s1 = fmaf(ga, go, s1);
+                s2 = fmaf(ga * go, yh, s2);
+                dga[k] = fmaf(go, yh, dga[k]);
+                dbe[k] += go;
+            }
+            if (smp == held) {
+                atomicAdd(&acc[2 * g], s1);
+                atomicAdd(&acc[2 * g + 1], s2);
+            } else {
+                double* bb = bst + 2 * ((size_t)smp * G + g);
+                atomicAdd(bb, (double)s1);
+                atomicAdd(bb + 1, (double)s2);
+            }
+        }
+    }
+    flush();
 #pragma unroll
     for (int k = 0; k < NG; ++k) {
-        const float go = active ? dO[(size_t)i * NG + k] : 0.f;
-        const float yh = (Y[(size_t)ic * NG + k] - mu) * rstd;
-        const float ga = __ldg(gamma + k);
-        s1 = fmaf(ga, go, s1);
-        s2 = fmaf(ga * go, yh, s2);
-        dga[k] = go * yh;
-        dbe[k] = go;
-    }
-    if (active) {
-        double* b = bst + 2 * ((size_t)(pos / pps) * G + g);
-        atomicAdd(b, (double)s1);
-        atomicAdd(b + 1, (double)s2);
-    }
-#pragma unroll
-    for (int k = 0; k < NG; ++k) {
-        const float a = block_sum_f(dga[k], sh), b = block_sum_f(dbe[k], sh);
-        if (threadIdx.x == 0) { atomicAdd(dgamma + k, a); atomicAdd(dbeta + k, b); }
+        const float a = block_sum_f(dga[k], sh), bsum = block_sum_f(dbe[k], sh);
+        if (threadIdx.x == 0) { atomicAdd(dgamma + k, a); atomicAdd(dbeta + k, bsum); }
     }
 }
 
-// pass 2: dY = rstd (gamma dO - mean(gamma dO) - yhat mean(gamma dO yhat))
 template <int NG>
 __global__ void __launch_bounds__(256) gct_gn_apply_kernel(const float* __restrict__ dO, const float* __restrict__ Y, const double* __restrict__ stats,
                                                            const double* __restrict__ bst, const float* __restrict__ gamma, float* __restrict__ dY,
-                                                           int total, int G, int pps, double eps) {
+                                                           int total, int G, int pps, double eps, const float* __restrict__ Wp,
+                                                           float* __restrict__ dH, int nh) {
+    // Wp != nullptr: also dH[i][c] = sum_k dY[i][k] Wp[k][c] (c < nh): the data gradient of the projection that produced the norm's input
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int gshift = 31 - __clz(G);
@@ -1204,10 +1300,32 @@ __global__ void __launch_bounds__(256) gct_gn_apply_kernel(const float* __restri
     if (var < 0.0) var = 0.0;
     const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + eps));
     const float m1 = (float)(bst[2 * dom] * inv), m2 = (float)(bst[2 * dom + 1] * inv);
+    float dy[NG];
 #pragma unroll
     for (int k = 0; k < NG; ++k) {
         const float yh = (Y[(size_t)i * NG + k] - mu) * rstd;
-        dY[(size_t)i * NG + k] = rstd * (__ldg(gamma + k) * dO[(size_t)i * NG + k] - m1 - yh * m2);
+        dy[k] = rstd * (__ldg(gamma + k) * dO[(size_t)i * NG + k] - m1 - yh * m2);
+        dY[(size_t)i * NG + k] = dy[k];
+    }
+    if (Wp) {
+        if ((nh & 3) == 0) {
+            for (int c = 0; c < nh; c += 4) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < NG; ++k) {
+                    const float4 wv = __ldg(reinterpret_cast<const float4*>(Wp + k * nh + c));
+                    o.x = fmaf(dy[k], wv.x, o.x); o.y = fmaf(dy[k], wv.y, o.y); o.z = fmaf(dy[k], wv.z, o.z); o.w = fmaf(dy[k], wv.w, o.w);
+                }
+                *reinterpret_cast<float4*>(dH + (size_t)i * nh + c) = o;
+            }
+        } else {
+            for (int c = 0; c < nh; ++c) {
+                float o = 0.f;
+#pragma unroll
+                for (int k = 0; k < NG; ++k) o = fmaf(dy[k], __ldg(Wp + k * nh + c), o);
+                dH[(size_t)i * nh + c] = o;
+            }
+        }
     }
 }
 
@@ -1273,6 +1391,68 @@ __global__ void __launch_bounds__(256) gct_wgrad_kernel(const float* __restrict_
     }
 }
 
+// Tiled form for R * Cc <= 1024 with Cc % 4 == 0 and contiguous, 16-byte aligned operands (every TAC / projection / attention weight here):
+// 128 rows of A and Bm are staged in shared memory with coalesced 16-byte loads; a thread owns one row r and four columns of dW and every
+// (256 / (R Cc / 4))-th staged row; the row slices are summed in shared memory, then one global atomic per element and CTA.
+constexpr int WG_ROWS = 128;
+__global__ void __launch_bounds__(256) gct_wgrad_tile_kernel(const float* __restrict__ A, const float* __restrict__ Bm, long long n, int R, int Cc,
+                                                             float* __restrict__ dW, float* __restrict__ db, int relu_b, int chunk) {
+    extern __shared__ __align__(16) float wg_sm[];
+    float* As = wg_sm;
+    float* Bs = wg_sm + WG_ROWS * R;
+    const int c4n = Cc >> 2, nog = R * c4n, nsl = 256 / nog;
+    const int og = threadIdx.x % nog, sl = threadIdx.x / nog;
+    const int r = og / c4n, c4 = og % c4n;
+    const bool worker = sl < nsl;
+    const long long i0 = (long long)blockIdx.x * chunk, i1 = i0 + chunk < n ? i0 + chunk : n;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb = 0.f;
+    for (long long t0 = i0; t0 < i1; t0 += WG_ROWS) {
+        const int rows = (int)(i1 - t0 < WG_ROWS ? i1 - t0 : WG_ROWS);
+        __syncthreads();
+        const float4* a4 = reinterpret_cast<const float4*>(A + t0 * R);
+        for (int idx = threadIdx.x; idx < WG_ROWS * R / 4; idx += 256)
+            reinterpret_cast<float4*>(As)[idx] = idx * 4 < rows * R ? a4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* b4 = reinterpret_cast<const float4*>(Bm + t0 * Cc);
+        for (int idx = threadIdx.x; idx < WG_ROWS * Cc / 4; idx += 256) {
+            float4 v = idx * 4 < rows * Cc ? b4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (relu_b) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            reinterpret_cast<float4*>(Bs)[idx] = v;
+        }
+        __syncthreads();
+        if (worker) {
+#pragma unroll 4
+            for (int i = sl; i < WG_ROWS; i += nsl) {
+                const float a = As[i * R + r];
+                const float4 b = *reinterpret_cast<const float4*>(Bs + i * Cc + c4 * 4);
+                acc[0] = fmaf(a, b.x, acc[0]);
+                acc[1] = fmaf(a, b.y, acc[1]);
+                acc[2] = fmaf(a, b.z, acc[2]);
+                acc[3] = fmaf(a, b.w, acc[3]);
+                accb += a;
+            }
+        }
+    }
+    __syncthreads();
+    float* red = wg_sm;                       // [nsl][R * Cc] | [nsl][R]
+    float* redb = wg_sm + nsl * R * Cc;
+    if (worker) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) red[sl * R * Cc + r * Cc + c4 * 4 + u] = acc[u];
+        if (c4 == 0) redb[sl * R + r] = accb;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < R * Cc + (db ? R : 0); e += 256) {
+        float v = 0.f;
+        if (e < R * Cc) {
+            for (int s = 0; s < nsl; ++s) v += red[s * R * Cc + e];
+            atomicAdd(dW + e, v);
+        } else {
+            for (int s = 0; s < nsl; ++s) v += redb[s * R + (e - R * Cc)];
+            atomicAdd(db + (e - R * Cc), v);
+        }
+    }
+}
+
 // ---- generic small linear backward (data): dX[i][k] (+)= sum_o dY[i][o] W[o][k]; optional mask (dY counted where Yact > 0: ReLU) -----------
 __global__ void __launch_bounds__(256) gct_lin_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ W, const float* __restrict__ Yact,
                                                           float* __restrict__ dX, long long n, int nin, int nout, int accumulate) {
@@ -1302,13 +1482,25 @@ __global__ void __launch_bounds__(256) gct_relu_mask_kernel(float* __restrict__ 
 // ---- TAC backward (gc3_basics.py:38-55 + the GroupNorm / residual that follow).  dYraw = gradient of the TAC output before the norm.
 // Writes dX = dOut + (TAC path) and the operands of the weight-gradient reductions:
 //   S3 [item][NG] = d(pre-activation 3), A3 [item][2 TH] = [y1 ; y2];  S2 [pos][TH], Mv [pos][TH] = group mean of y1;  S1 [item][TH]
-template <int NG, int HG>
+template <int NG, int HG, int G>
 __global__ void __launch_bounds__(128) gct_tac_bwd_kernel(const float* __restrict__ X, const float* __restrict__ dYraw, const float* __restrict__ dOut,
                                                           float* __restrict__ dX, TacW w, float* __restrict__ S3, float* __restrict__ A3,
                                                           float* __restrict__ S2, float* __restrict__ Mv, float* __restrict__ S1,
-                                                          float* __restrict__ ga1, float* __restrict__ ga2, float* __restrict__ ga3, int npos, int G) {
-    constexpr int TH = 3 * HG;
+                                                          float* __restrict__ ga1, float* __restrict__ ga2, float* __restrict__ ga3, int npos) {
+    constexpr int TH = 3 * HG, W2S = TH + 4, MINE = (TH + G - 1) / G;   // W2S: padded row of W2 (lanes of a group read different rows)
     __shared__ float sh[32];
+    // the ~1.5 k weights are read by every thread for every product: shared memory (16-byte broadcast reads), W2 also transposed
+    __shared__ __align__(16) float sW1[TH * NG], sW2[TH * W2S], sW2t[TH * W2S], sW3[NG * 2 * TH], sB1[TH], sB2[TH], sB3[NG];
+    for (int e = threadIdx.x; e < TH * TH; e += blockDim.x) {
+        const float v = __ldg(w.w2 + e);
+        sW2[(e / TH) * W2S + e % TH] = v;
+        sW2t[(e % TH) * W2S + e / TH] = v;
+    }
+    for (int e = threadIdx.x; e < TH * NG; e += blockDim.x) sW1[e] = __ldg(w.w1 + e);
+    for (int e = threadIdx.x; e < NG * 2 * TH; e += blockDim.x) sW3[e] = __ldg(w.w3 + e);
+    for (int e = threadIdx.x; e < TH; e += blockDim.x) { sB1[e] = __ldg(w.b1 + e); sB2[e] = __ldg(w.b2 + e); }
+    if (threadIdx.x < NG) sB3[threadIdx.x] = __ldg(w.b3 + threadIdx.x);
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int pos = i / G, g = i % G;
     const bool active = pos < npos;
@@ -1317,85 +1509,128 @@ __global__ void __launch_bounds__(128) gct_tac_bwd_kernel(const float* __restric
     float x[NG];
 #pragma unroll
     for (int k = 0; k < NG; ++k) x[k] = X[(size_t)ic * NG + k];
-    float y1[TH], p1[TH], mv[TH];
+    float p1[TH], mv[TH];   // y1 = PReLU(p1) and y2 = PReLU(p2) are re-derived where they are used (registers)
 #pragma unroll
     for (int r = 0; r < TH; ++r) {
-        float acc = __ldg(w.b1 + r);
+        float acc = sB1[r];
 #pragma unroll
-        for (int k = 0; k < NG; ++k) acc = fmaf(__ldg(w.w1 + r * NG + k), x[k], acc);
+        for (int k = 0; k < NG; ++k) acc = fmaf(sW1[r * NG + k], x[k], acc);
         p1[r] = acc;
-        y1[r] = prelu1(acc, a1);
-        float v = active ? y1[r] : 0.f;   // inactive lanes only exist in the last, partial warp and belong to positions >= npos
+        float v = active ? prelu1(acc, a1) : 0.f;   // inactive lanes only exist in the last, partial warp and belong to positions >= npos
         for (int o = G >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 32);
         mv[r] = v / (float)G;
     }
-    float y2[TH], p2[TH];
-    for (int r = 0; r < TH; ++r) {
-        float acc = __ldg(w.b2 + r);
+    // y2 = PReLU(W2 mean + b2) is the same for the G lanes of a position: lane g computes rows g, g + G, ... and the group exchanges them
+    float p2[TH], part[MINE];
 #pragma unroll
-        for (int c = 0; c < TH; ++c) acc = fmaf(__ldg(w.w2 + r * TH + c), mv[c], acc);
-        p2[r] = acc;
-        y2[r] = prelu1(acc, a2);
+    for (int m = 0; m < MINE; ++m) {
+        const int r = m * G + g;
+        float acc = 0.f;
+        if (r < TH) {
+            acc = sB2[r];
+#pragma unroll
+            for (int c = 0; c < TH; ++c) acc = fmaf(sW2[r * W2S + c], mv[c], acc);
+        }
+        part[m] = acc;
+    }
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+        p2[r] = __shfl_sync(0xffffffffu, part[r / G], r % G, G);
     }
     float d3[NG], da3 = 0.f;
 #pragma unroll
     for (int k = 0; k < NG; ++k) {
-        float acc = __ldg(w.b3 + k);
+        float acc = sB3[k];
 #pragma unroll
-        for (int r = 0; r < TH; ++r) acc = fmaf(__ldg(w.w3 + k * 2 * TH + r), y1[r], acc);
+        for (int r = 0; r < TH; ++r) acc = fmaf(sW3[k * 2 * TH + r], prelu1(p1[r], a1), acc);
 #pragma unroll
-        for (int r = 0; r < TH; ++r) acc = fmaf(__ldg(w.w3 + k * 2 * TH + TH + r), y2[r], acc);
+        for (int r = 0; r < TH; ++r) acc = fmaf(sW3[k * 2 * TH + TH + r], prelu1(p2[r], a2), acc);
         const float go = active ? dYraw[(size_t)i * NG + k] : 0.f;
         d3[k] = acc >= 0.f ? go : a3 * go;
         da3 += acc >= 0.f ? 0.f : go * acc;
     }
-    float dy1[TH], dy2[TH];
+    float dy1[TH], d2[TH], da2 = 0.f;
 #pragma unroll
     for (int r = 0; r < TH; ++r) {
         float s = 0.f, t = 0.f;
 #pragma unroll
         for (int k = 0; k < NG; ++k) {
-            s = fmaf(__ldg(w.w3 + k * 2 * TH + r), d3[k], s);
-            t = fmaf(__ldg(w.w3 + k * 2 * TH + TH + r), d3[k], t);
+            s = fmaf(sW3[k * 2 * TH + r], d3[k], s);
+            t = fmaf(sW3[k * 2 * TH + TH + r], d3[k], t);
         }
         dy1[r] = s;
         for (int o = G >> 1; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o, 32);   // y2 is shared by the groups of a position
-        dy2[r] = t;
-    }
-    float d2[TH], da2 = 0.f;
-#pragma unroll
-    for (int r = 0; r < TH; ++r) {
-        d2[r] = p2[r] >= 0.f ? dy2[r] : a2 * dy2[r];
-        da2 += p2[r] >= 0.f ? 0.f : dy2[r] * p2[r];
+        d2[r] = p2[r] >= 0.f ? t : a2 * t;
+        da2 += p2[r] >= 0.f ? 0.f : t * p2[r];
     }
     float da1 = 0.f, dx[NG];
 #pragma unroll
     for (int k = 0; k < NG; ++k) dx[k] = 0.f;
-    for (int c = 0; c < TH; ++c) {
+#pragma unroll
+    for (int m = 0; m < MINE; ++m) {   // W2^T d2, again one share of the rows per lane
+        const int c = m * G + g;
         float dm = 0.f;
+        if (c < TH) {
 #pragma unroll
-        for (int r = 0; r < TH; ++r) dm = fmaf(__ldg(w.w2 + r * TH + c), d2[r], dm);
-        const float dyc = dy1[c] + dm / (float)G;
-        const float d1 = p1[c] >= 0.f ? dyc : a1 * dyc;
-        da1 += p1[c] >= 0.f ? 0.f : dyc * p1[c];
-        if (active) S1[(size_t)i * TH + c] = d1;
-#pragma unroll
-        for (int k = 0; k < NG; ++k) dx[k] = fmaf(__ldg(w.w1 + c * NG + k), d1, dx[k]);
+            for (int r = 0; r < TH; ++r) dm = fmaf(sW2t[c * W2S + r], d2[r], dm);
+        }
+        part[m] = dm;
     }
-    if (active) {
+    constexpr int CV = TH % 4 == 0 ? 4 : 1;   // S1 leaves in 16-byte pieces when the row length allows
 #pragma unroll
-        for (int k = 0; k < NG; ++k) {
-            dX[(size_t)i * NG + k] = dOut[(size_t)i * NG + k] + dx[k];
-            S3[(size_t)i * NG + k] = d3[k];
+    for (int c0 = 0; c0 < TH; c0 += CV) {
+        float d1v[CV];
+#pragma unroll
+        for (int u = 0; u < CV; ++u) {
+            const int c = c0 + u;
+            const float dm = __shfl_sync(0xffffffffu, part[c / G], c % G, G);
+            const float dyc = dy1[c] + dm / (float)G;
+            const float d1 = p1[c] >= 0.f ? dyc : a1 * dyc;
+            da1 += p1[c] >= 0.f ? 0.f : dyc * p1[c];
+            d1v[u] = d1;
+#pragma unroll
+            for (int k = 0; k < NG; ++k) dx[k] = fmaf(sW1[c * NG + k], d1, dx[k]);
         }
-#pragma unroll
-        for (int r = 0; r < TH; ++r) {
-            A3[(size_t)i * 2 * TH + r] = y1[r];
-            A3[(size_t)i * 2 * TH + TH + r] = y2[r];
+        if (active) {
+            if constexpr (CV == 4) *reinterpret_cast<float4*>(S1 + (size_t)i * TH + c0) = make_float4(d1v[0], d1v[1], d1v[2], d1v[3]);
+            else S1[(size_t)i * TH + c0] = d1v[0];
         }
-        if (g == 0) {
+    }
+    if (active) {   // 16-byte stores: a thread's rows are contiguous
+        if constexpr (NG % 4 == 0 && TH % 4 == 0) {
 #pragma unroll
-            for (int r = 0; r < TH; ++r) { S2[(size_t)pos * TH + r] = d2[r]; Mv[(size_t)pos * TH + r] = mv[r]; }
+            for (int k = 0; k < NG; k += 4) {
+                const float4 o = *reinterpret_cast<const float4*>(dOut + (size_t)i * NG + k);
+                *reinterpret_cast<float4*>(dX + (size_t)i * NG + k) = make_float4(o.x + dx[k], o.y + dx[k + 1], o.z + dx[k + 2], o.w + dx[k + 3]);
+                *reinterpret_cast<float4*>(S3 + (size_t)i * NG + k) = make_float4(d3[k], d3[k + 1], d3[k + 2], d3[k + 3]);
+            }
+#pragma unroll
+            for (int r = 0; r < TH; r += 4) {
+                *reinterpret_cast<float4*>(A3 + (size_t)i * 2 * TH + r) = make_float4(prelu1(p1[r], a1), prelu1(p1[r + 1], a1), prelu1(p1[r + 2], a1), prelu1(p1[r + 3], a1));
+                *reinterpret_cast<float4*>(A3 + (size_t)i * 2 * TH + TH + r) = make_float4(prelu1(p2[r], a2), prelu1(p2[r + 1], a2), prelu1(p2[r + 2], a2), prelu1(p2[r + 3], a2));
+            }
+            if (g == 0) {
+#pragma unroll
+                for (int r = 0; r < TH; r += 4) {
+                    *reinterpret_cast<float4*>(S2 + (size_t)pos * TH + r) = make_float4(d2[r], d2[r + 1], d2[r + 2], d2[r + 3]);
+                    *reinterpret_cast<float4*>(Mv + (size_t)pos * TH + r) = make_float4(mv[r], mv[r + 1], mv[r + 2], mv[r + 3]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NG; ++k) {
+                dX[(size_t)i * NG + k] = dOut[(size_t)i * NG + k] + dx[k];
+                S3[(size_t)i * NG + k] = d3[k];
+            }
+#pragma unroll
+            for (int r = 0; r < TH; ++r) {
+                A3[(size_t)i * 2 * TH + r] = prelu1(p1[r], a1);
+                A3[(size_t)i * 2 * TH + TH + r] = prelu1(p2[r], a2);
+            }
+            if (g == 0) {
+#pragma unroll
+                for (int r = 0; r < TH; ++r) { S2[(size_t)pos * TH + r] = d2[r]; Mv[(size_t)pos * TH + r] = mv[r]; }
+            }
         }
     }
     // PReLU slopes: a2's gradient is counted once per position (lane g == 0)
@@ -1864,14 +2099,35 @@ void t_layout(const dp_gctasnet* h, const GGeo& g, TLayout& l) {
     l.total = c.off;
 }
 
-inline int wgrad_chunk(long long n) {
-    long long c = ceil_div_ll(n, 592);
+inline int wgrad_chunk(long long n, int blocks) {
+    long long c = ceil_div_ll(n, blocks);
     return (int)(c < 64 ? 64 : c);
 }
 inline cudaError_t wgrad(const float* A, int lda, const float* Bm, int ldb, long long n, int R, int Cc, float* dW, float* db, int relu_b, cudaStream_t s) {
-    const int chunk = wgrad_chunk(n);
+    const bool tiled = lda == R && ldb == Cc && (Cc & 3) == 0 && (R & 3) == 0 && R * Cc <= 1024 && R + Cc <= 128 &&
+                       ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bm)) & 15) == 0;
+    if (tiled) {
+        int chunk = wgrad_chunk(n, 148 * 8);
+        chunk = ceil_div(chunk, WG_ROWS) * WG_ROWS;   // whole tiles: every CTA's first row stays 16-byte aligned
+        size_t fl = (size_t)WG_ROWS * (R + Cc);
+        if (fl < 1280) fl = 1280;
+        static const cudaError_t attr = cudaFuncSetAttribute(gct_wgrad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (attr != cudaSuccess) return attr;
+        gct_wgrad_tile_kernel<<<blocks_for(n, chunk), 256, fl * sizeof(float), s>>>(A, Bm, n, R, Cc, dW, db, relu_b, chunk);
+        return cudaGetLastError();
+    }
+    const int chunk = wgrad_chunk(n, 592);
     gct_wgrad_kernel<<<blocks_for(n, chunk), 256, 0, s>>>(A, lda, Bm, ldb, n, R, Cc, dW, db, relu_b, chunk);
     return cudaGetLastError();
+}
+
+// 256-item tiles one CTA of gct_gn_sums_kernel walks: about eight CTAs per SM
+inline int gn_tiles_per_cta(long long total) { return (int)ceil_div_ll(ceil_div_ll(total, 256), 148 * 8); }
+
+// grid of the persistent LSTM kernels: x = blocks of sequences (balanced over the rounds a resident set of CTAs needs), y = direction
+inline dim3 lstm_grid(long long nblk, int resident_per_dir) {
+    const long long rounds = ceil_div_ll(nblk, resident_per_dir);
+    return dim3((unsigned)ceil_div_ll(nblk, rounds), 2);
 }
 
 template <int NG, int HG>
@@ -1881,7 +2137,7 @@ struct TrainOps {
 
     static int rnn_fwd(dp_gctasnet* h, const float* Ain, float* Y, float* Hh, float* S5, float* Out, double* st, const RnnW& w, long long npos, int G,
                        int pps, const SeqWalk& q, double eps, cudaStream_t s, const float* cw, const float* cb, const float* ca) {
-        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
+        const dim3 grid = lstm_grid(blocks_for(q.nouter * G * HG, 128), 1 << 30);   // one block of sequences per CTA measured faster here
         gct_lstm_kernel<NG, HG><<<grid, 128, 0, s>>>(Ain, Hh, S5, w, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t);
         gc_proj_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Y, st, w, (int)npos, G, pps);
         gc_gn_res_kernel<NG><<<blocks_for(npos * G), 256, 0, s>>>(Y, Ain, Out, st, w.gamma, w.beta, (int)(npos * G), G, pps, eps, cw, cb, ca);
@@ -1898,7 +2154,7 @@ struct TrainOps {
         if (smem > 200 * 1024) return fail("dp_gctasnet_forward_train: sequence of %d frames does not fit the attention kernel's shared memory", q.len);
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(gc_dpt_attn_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gc_dpt_attn_kernel<NG><<<blocks_for(q.nouter * G, spb), 128, smem, s>>>(Ain, Z, w, q.nouter, G, q.len, spb, q.qdiv, q.s_hi, q.s_lo, q.s_t);
-        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
+        const dim3 grid = lstm_grid(blocks_for(q.nouter * G * HG, 128), 1 << 30);   // one block of sequences per CTA measured faster here
         gct_lstm_kernel<NG, HG><<<grid, 128, 0, s>>>(Z, Hh, S5, w.rnn, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t);
         gc_dpt_out_kernel<NG, HG><<<blocks_for(npos * G), 256, 0, s>>>(Hh, Z, Ain, Out, w, npos * G, cw, cb, ca);
         h->launches += 3;
@@ -1995,10 +2251,18 @@ struct TrainOps {
         const TacW w = tac_w(h, p, base);
         const TacG gw = tac_g(h, gp, base);
         const int total = (int)(npos * G);
-        gct_gn_sums_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Y, st, w.gamma, bst, gw.gamma, gw.beta, total, G, pps, 1e-5);
-        gct_gn_apply_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Y, st, bst, w.gamma, k.T1, total, G, pps, 1e-5);
-        gct_tac_bwd_kernel<NG, HG><<<blocks_for(total, 128), 128, 0, s>>>(X, k.T1, dOut, dX, w, k.S3, k.A3, k.S2, k.Mv, k.S1, gw.a1, gw.a2, gw.a3,
-                                                                          (int)npos, G);
+        const int tpc = gn_tiles_per_cta(total);
+        gct_gn_sums_kernel<NG><<<blocks_for(blocks_for(total), tpc), 256, 0, s>>>(dOut, Y, st, w.gamma, bst, gw.gamma, gw.beta, total, G, pps, 1e-5, tpc);
+        gct_gn_apply_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Y, st, bst, w.gamma, k.T1, total, G, pps, 1e-5, nullptr, nullptr, 0);
+        if (G == 8)
+            gct_tac_bwd_kernel<NG, HG, 8><<<blocks_for(total, 128), 128, 0, s>>>(X, k.T1, dOut, dX, w, k.S3, k.A3, k.S2, k.Mv, k.S1, gw.a1, gw.a2,
+                                                                                 gw.a3, (int)npos);
+        else if (G == 16)
+            gct_tac_bwd_kernel<NG, HG, 16><<<blocks_for(total, 128), 128, 0, s>>>(X, k.T1, dOut, dX, w, k.S3, k.A3, k.S2, k.Mv, k.S1, gw.a1, gw.a2,
+                                                                                  gw.a3, (int)npos);
+        else
+            gct_tac_bwd_kernel<NG, HG, 32><<<blocks_for(total, 128), 128, 0, s>>>(X, k.T1, dOut, dX, w, k.S3, k.A3, k.S2, k.Mv, k.S1, gw.a1, gw.a2,
+                                                                                  gw.a3, (int)npos);
         CK(cudaGetLastError());
         CK(wgrad(k.S3, NG, k.A3, 2 * TH, total, NG, 2 * TH, gw.w3, gw.b3, 0, s));
         CK(wgrad(k.S2, TH, k.Mv, TH, npos, TH, TH, gw.w2, gw.b2, 0, s));
@@ -2017,17 +2281,18 @@ struct TrainOps {
             gct_cat_bwd_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Ain, Y, st, w.gamma, w.beta, p + h->off[P_CAT_W], p + h->off[P_CAT_B],
                                                                      p + h->off[P_CAT_A], gp + h->off[P_CAT_W], gp + h->off[P_CAT_B],
                                                                      gp + h->off[P_CAT_A], total, G, pps, eps);
-        gct_gn_sums_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Y, st, w.gamma, bst, gw.gamma, gw.beta, total, G, pps, eps);
-        gct_gn_apply_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Y, st, bst, w.gamma, k.T1, total, G, pps, eps);
-        gct_lin_bwd_kernel<<<blocks_for((long long)total * 2 * HG), 256, 0, s>>>(k.T1, w.pw, nullptr, k.T2, total, 2 * HG, NG, 0);
+        const int tpc = gn_tiles_per_cta(total);
+        gct_gn_sums_kernel<NG><<<blocks_for(blocks_for(total), tpc), 256, 0, s>>>(dOut, Y, st, w.gamma, bst, gw.gamma, gw.beta, total, G, pps, eps, tpc);
+        // k.T1 = gradient of the projection output, k.T2 = gradient of the BiLSTM output (projection weight [NG][2 HG])
+        gct_gn_apply_kernel<NG><<<blocks_for(total), 256, 0, s>>>(dOut, Y, st, bst, w.gamma, k.T1, total, G, pps, eps, w.pw, k.T2, 2 * HG);
         CK(cudaGetLastError());
         CK(wgrad(k.T1, NG, Hh, 2 * HG, total, NG, 2 * HG, gw.pw, gw.pb, 0, s));
-        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
+        const dim3 grid = lstm_grid(blocks_for(q.nouter * G * HG, 128), 222);
         gct_lstm_bwd_kernel<NG, HG><<<grid, 128, 0, s>>>(Ain, Hh, S5, k.T2, k.T3, w, gw, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t,
                                                          (long long)total);
         gct_add3_kernel<<<blocks_for((long long)total * NG), 256, 0, s>>>(dOut, k.T3, k.T3 + (size_t)total * NG, dAin, (long long)total * NG);
         CK(cudaGetLastError());
-        h->launches += 6 + (cat ? 1 : 0);
+        h->launches += 5 + (cat ? 1 : 0);
         return 0;
     }
     // Out = [concat_block](Ain + LN2(Z + Linear(relu(BiLSTM(Z))))), Z = LN1(Ain + out_proj(attention(in_proj(Ain)))):  dOut -> dAin
@@ -2043,7 +2308,7 @@ struct TrainOps {
                                                                         gp + (cat ? h->off[P_CAT_B] : 0), gp + (cat ? h->off[P_CAT_A] : 0));
         CK(cudaGetLastError());
         CK(wgrad(k.T1, NG, Hh, 2 * HG, total, NG, 2 * HG, gw.pw, gw.pb, 1, s));   // linear2: operand relu(Hh)
-        dim3 grid(blocks_for(q.nouter * G * HG, 128), 2);
+        const dim3 grid = lstm_grid(blocks_for(q.nouter * G * HG, 128), 222);
         gct_lstm_bwd_kernel<NG, HG><<<grid, 128, 0, s>>>(Z, Hh, S5, k.T2, k.T3, w.rnn, gw, q.nouter, G, q.len, q.qdiv, q.s_hi, q.s_lo, q.s_t, total);
         // gradient of Z: LayerNorm-2 residual + both LSTM directions (into k.S1)
         gct_add3_kernel<<<blocks_for(total * NG), 256, 0, s>>>(k.T1, k.T3, k.T3 + (size_t)total * NG, k.S1, total * NG);
