@@ -32,15 +32,27 @@ namespace dp {
 namespace {
 
 constexpr int BM = 128, BK = 64;
+
+__device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 constexpr int A_TILE = BM * BK * 2;  // 16 KB
 
 template <int BN, bool SPLIT>
 struct NtCfg {
     static constexpr int W_TILE = BN * BK * 2;
     static constexpr int STAGE = (A_TILE + W_TILE) * (SPLIT ? 2 : 1);
-    static constexpr int STAGES = (196 * 1024) / STAGE > 6 ? 6 : (196 * 1024) / STAGE;
-    static constexpr int OUT_STAGE = 2 * 128 * 128;  // two [128 rows x 32 fp32] swizzled staging tiles for the TMA stores (one per warp set)
+    // [128 rows x 32 fp32] swizzled staging tiles for the TMA stores: one per warp set, two where two operand stages still fit beside
+    // them (the store of chunk i then drains while chunk i + 1 is converted; with one tile the epilogue waited ~40 % of its time there)
+    static constexpr int OUT_TILE = 128 * 128;
+    static constexpr int OUT_BUFS = 2 * STAGE + 4 * OUT_TILE + 1280 <= 227 * 1024 ? 2 : 1;
+    static constexpr int OUT_STAGE = 2 * OUT_BUFS * OUT_TILE;
+    static constexpr int STAGES = (227 * 1024 - 1280 - OUT_STAGE) / STAGE > 6 ? 6 : (227 * 1024 - 1280 - OUT_STAGE) / STAGE;
     static constexpr int SMEM = STAGES * STAGE + OUT_STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static_assert(STAGES >= 2 && SMEM <= 227 * 1024, "operand ring and staging tiles must fit");
     static constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
 };
 
@@ -135,6 +147,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;
         uint32_t as = 0, aphase = 0;
+        int ob = 0;   // staging tile of this warp set in use
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
             mbar_wait(tfull + as, aphase);
@@ -143,7 +156,7 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             const bool ok = row < p.M;
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-            for (int c0 = half * 32; c0 < BN; c0 += 64) {
+            for (int c0 = half * 32; c0 < BN; c0 += 64, ob ^= (Cfg::OUT_BUFS - 1)) {
                 float v[32];
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + as * BN + c0, v);
                 if (ok) {
@@ -247,19 +260,21 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 if (tma_store) {
                     // fp32 output through shared memory and a TMA store: full 128-byte rows leave the SM as bulk writes instead
                     // of 16-byte pieces of 32 different lines per store instruction.  One staging tile per warp set (4 warps).
-                    uint8_t* stg = out_stage + half * (128 * 128);
+                    const uint32_t stg = smem_u32(out_stage) + (half * Cfg::OUT_BUFS + ob) * Cfg::OUT_TILE;
                     const int bar_id = 1 + half;
-                    if ((warp & 3) == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous store drained
+                    if ((warp & 3) == 2 && lane == 0) {   // the store that last read this staging tile has drained
+                        if (Cfg::OUT_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+                    }
                     asm volatile("bar.sync %0, 128;\n" ::"r"(bar_id) : "memory");
                     const int rl = q * 32 + lane;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(stg + rl * 128 + ((j ^ (rl & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j) sts128f(stg + rl * 128 + ((j ^ (rl & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     proxy_fence_async();
                     asm volatile("bar.sync %0, 128;\n" ::"r"(bar_id) : "memory");
                     if ((warp & 3) == 2 && lane == 0) {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(&tmC),
-                                     "r"(smem_u32(stg)), "r"(n0 + c0), "r"(m0)
+                                     "r"(stg), "r"(n0 + c0), "r"(m0)
                                      : "memory");
                         asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
                     }
@@ -267,29 +282,31 @@ gemm_tma_nt_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 if (tma_planes) {
                     // plane outputs through shared memory and TMA stores as well: [128 rows x 32 bf16] tiles (64-byte rows, 64-byte
                     // swizzle), hi at +0 and lo at +8 KB of this warp set's staging area (never used together with the fp32 staging)
-                    uint8_t* stg = out_stage + half * (128 * 128);
+                    const uint32_t stg = smem_u32(out_stage) + (half * Cfg::OUT_BUFS + ob) * Cfg::OUT_TILE;
                     const int bar_id = 1 + half;
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-                    if ((warp & 3) == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous stores drained
+                    if ((warp & 3) == 2 && lane == 0) {   // the stores that last read this staging tile have drained
+                        if (Cfg::OUT_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+                    }
                     asm volatile("bar.sync %0, 128;\n" ::"r"(bar_id) : "memory");
                     const int rl = q * 32 + lane, sw = (rl >> 1) & 3;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        *reinterpret_cast<uint4*>(stg + rl * 64 + ((j ^ sw) << 4)) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        if (p.C_lo)
-                            *reinterpret_cast<uint4*>(stg + 8192 + rl * 64 + ((j ^ sw) << 4)) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        sts128u(stg + rl * 64 + ((j ^ sw) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        if (p.C_lo) sts128u(stg + 8192 + rl * 64 + ((j ^ sw) << 4), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
                     proxy_fence_async();
                     asm volatile("bar.sync %0, 128;\n" ::"r"(bar_id) : "memory");
                     if ((warp & 3) == 2 && lane == 0) {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(&tmCh),
-                                     "r"(smem_u32(stg)), "r"(n0 + c0), "r"(m0)
+                                     "r"(stg), "r"(n0 + c0), "r"(m0)
                                      : "memory");
                         if (p.C_lo)
                             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(&tmCl),
-                                         "r"(smem_u32(stg + 8192)), "r"(n0 + c0), "r"(m0)
+                                         "r"(stg + 8192), "r"(n0 + c0), "r"(m0)
                                          : "memory");
                         asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
                     }
