@@ -47,6 +47,7 @@ PROTOTYPES = {
     "dp_set_gemm_backend": (_i, [_i]),
     "dp_set_fused_lstm": (_i, [_i]),
     "dp_set_lstm_pipeline": (_i, [_i]),
+    "dp_set_lstm_cluster": (_i, [_i]),
     "dp_set_lstm_tcgen05": (_i, [_i]),
     "dp_set_wgrad_multicast": (_i, [_i]),
     "dp_set_attention_forward": (_i, [_i]),

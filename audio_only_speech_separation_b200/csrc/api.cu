@@ -160,6 +160,10 @@ int dp_set_lstm_pipeline(int mode) {
     if (lstm_set_pipeline(mode) != 0) return fail("dp_set_lstm_pipeline: 0 (plain 8-warp kernels), 1 (automatic), 2 (pipelined sequence groups) or 3 (16-warp kernel)");
     return 0;
 }
+int dp_set_lstm_cluster(int mode) {
+    if (lstm_set_cluster(mode) != 0) return fail("dp_set_lstm_cluster: 0 (off), 1 (automatic: inference passes of <= 128 sequences) or 2 (every inference pass)");
+    return 0;
+}
 int dp_set_wgrad_multicast(int on) { return gemm_tma_set_wgrad_multicast(on); }
 int dp_set_lstm_tcgen05(int mode) {
     if (lstm_set_rec5(mode) != 0) return fail("dp_set_lstm_tcgen05: 0 (mma.sync recurrence kernels), 1 (automatic) or 2 (tcgen05 recurrence kernels always)");

@@ -171,6 +171,8 @@ struct LstmPlanes {
 // forward recurrence kernel choice: 0 plain 8-warp kernels, 1 automatic, 2 software-pipelined sequence groups, 3 16-warp kernel
 int lstm_set_pipeline(int mode);
 int lstm_get_pipeline();
+int lstm_set_cluster(int mode);   // 0 off, 1 automatic, 2 always: four-CTA-cluster forward recurrence for small inference passes
+int lstm_get_cluster();
 // H may be null when only the planes are wanted.
 cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save,
                             cudaStream_t st, const LstmPlanes* planes = nullptr);

@@ -656,6 +656,226 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd16_kernel(const LstmPack w, fl
     }
 }
 
+// ---- cluster forward recurrence (small passes, inference) --------------------------------------------------------
+// At B = 1 a pass has ~80-100 sequences per direction: 11-13 tiles of 8, i.e. two dozen busy SMs, and each of them is bound by the
+// legacy tensor pipe -- the products of W_hh (512 x 128, three bf16 pairs) cost 768 mma.m16n8k16 per step whatever the number of
+// sequences (measured 1.7-2.0 us per step).  Here the gate rows of a tile are split over a cluster of four CTAs: CTA r owns the hidden
+// units [32 r, 32 r + 32) (four warps x 8 units, W_hh hi in registers as in the 16-warp kernel, lo in 32 KB of shared memory), does a
+// quarter of the products, updates its cells and writes its slice of h_t (bf16 hi / lo) into the h tile of ALL four CTAs through
+// distributed shared memory; one cluster barrier per step.  The h tile is double buffered: step t writes buffer t & 1 while slower
+// peers may still read h_{t-1} from the other one.  Same per-warp product order as lstm_fwd16_kernel: identical results.
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_peer(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_peer_b16(uint32_t addr, __nv_bfloat16 v) {
+    asm volatile("st.shared::cluster.b16 [%0], %1;\n" ::"r"(addr), "h"(__bfloat16_as_ushort(v)) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+constexpr int GSL = 128 + 4;   // staged gate rows of one CTA: 32 units x 4 gates (+ pad)
+
+template <int NT, bool SPLIT>
+__global__ void __launch_bounds__(128, 1) lstm_fwdc_kernel(const LstmPack w, const float* __restrict__ G, float* __restrict__ H, const SeqMap m,
+                                                           const LstmPlanes pl, const int spc) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NS = 8 * NT;
+    constexpr int ALO = SPLIT ? 4 * 2 * 8 * 32 * 16 : 0;
+    constexpr int HPL = NS * HST;                                  // one plane of one h buffer (bf16 elements)
+    uint4* alo = reinterpret_cast<uint4*>(smem);
+    __nv_bfloat16* hb0 = reinterpret_cast<__nv_bfloat16*>(smem + ALO);   // [buffer][plane hi | lo][NS][HST]
+    float* gs = reinterpret_cast<float*>(hb0 + 4 * HPL);               // [buffer][NS][GSL]
+    int* sbase = reinterpret_cast<int*>(gs + 2 * NS * GSL);
+    __nv_bfloat16* hst = reinterpret_cast<__nv_bfloat16*>(sbase + NS);   // this CTA's slice of h_t: [plane][NS][32 units], sent as 16-byte pieces
+    uint64_t* full = reinterpret_cast<uint64_t*>(hst + 2 * NS * 32);      // [2]: every CTA's slice of h_t has landed in buffer b
+    uint64_t* empty = full + 2;                                           // [2]: all four CTAs are done reading their buffer b
+    constexpr uint32_t SLICES = (SPLIT ? 2u : 1u) * NS * 256u;            // bytes one step delivers into one buffer
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int dir = blockIdx.y;
+    const int rank = (int)cluster_rank();
+    const int q0 = (blockIdx.x >> 2) * spc;
+    const int nv = min(spc, m.nseq - q0);
+    const int gw = 4 * rank + warp;                                   // this warp's place among the 16 unit octets
+
+    uint4 ahi[2][8];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(w.whh_f_hi) + ((size_t)dir * 8 + (gw >> 1)) * (4 * 8 * 32 * 4);
+        const int comp = gw & 1;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const int b0 = (((2 * mt) * 8 + ks) * 32 + lane) * 4, b1 = (((2 * mt + 1) * 8 + ks) * 32 + lane) * 4;
+                ahi[mt][ks] = make_uint4(src[b0 + comp], src[b1 + comp], src[b0 + comp + 2], src[b1 + comp + 2]);
+            }
+    }
+    if (SPLIT) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(w.whh_f_lo) + (size_t)dir * 8192 * 4;
+        for (int i = tid; i < 2048; i += 128) {  // alo[((warp * 2 + mt) * 8 + ks) * 32 + lane]
+            const int ln = i & 31, ks = (i >> 5) & 7, mt = (i >> 8) & 1, w16 = 4 * rank + (i >> 9), comp = w16 & 1;
+            const int wb = (w16 >> 1) * (4 * 8 * 32 * 4);
+            const int b0 = wb + (((2 * mt) * 8 + ks) * 32 + ln) * 4, b1 = wb + (((2 * mt + 1) * 8 + ks) * 32 + ln) * 4;
+            alo[i] = make_uint4(src[b0 + comp], src[b1 + comp], src[b0 + comp + 2], src[b1 + comp + 2]);
+        }
+    }
+    for (int i = tid; i < 4 * HPL / 2; i += 128) reinterpret_cast<uint32_t*>(hb0)[i] = 0u;   // h_{-1} = 0
+    for (int i = tid; i < 2 * NS * GSL; i += 128) gs[i] = 0.f;                                  // unused slots are never staged
+    fill_seq_bases(sbase, NS, q0, nv, m);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(full + i)), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(empty + i)), "r"(4));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    auto stage_gates = [&](int buf, int t) {
+        const unsigned toff = (unsigned)t * (unsigned)m.s_t;
+#pragma unroll
+        for (int i = 0; i < NS / 4; ++i) {
+            const int ch = tid + 128 * i, sq = ch >> 5, col = ch & 31;
+            const float* src = G + ((size_t)(sbase[sq] + toff) * 1024 + dir * kG + rank * 128 + col * 4);
+            if (sq < nv) cp_async16(gs + (buf * NS + sq) * GSL + col * 4, src);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    stage_gates(0, dir ? m.len - 1 : 0);
+
+    unsigned hoff[NT][2];
+    bool valid[NT][2];
+    float cst[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int sl = n * 8 + 2 * c + e;
+            valid[n][e] = sl < nv;
+            hoff[n][e] = (unsigned)sbase[sl] * 256u + (unsigned)(dir * kH + 8 * gw + g);
+            cst[n][e] = 0.f;
+        }
+    const int ucol = (8 * warp + g) * 4;   // this thread's unit inside the CTA's staged gate rows
+    uint32_t peer[4];   // the peers' h area; their barriers sit at the same distance from it as here
+#pragma unroll
+    for (int r = 0; r < 4; ++r) peer[r] = map_peer(smem_u32(hb0), (uint32_t)r);
+    const uint32_t full_off = smem_u32(full) - smem_u32(hb0), empty_off = smem_u32(empty) - smem_u32(hb0);
+
+    cp_async_wait_all();
+    cluster_barrier();   // every CTA of the cluster has zeroed its h tile and initialised its barriers; the first gate rows have landed
+
+    for (int step = 0; step < m.len; ++step) {
+        const int t = dir ? (m.len - 1 - step) : step;
+        const unsigned toff = (unsigned)t * (unsigned)m.s_t;
+        const int cur = step & 1;
+        const __nv_bfloat16* hp_hi = hb0 + (cur ^ 1) * 2 * HPL;   // h_{t-1}
+        const __nv_bfloat16* hp_lo = hp_hi + HPL;
+        if (step + 1 < m.len) stage_gates(cur ^ 1, dir ? t - 1 : t + 1);
+        if (tid == 0)   // this step's slices will land in buffer `cur`
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(full + cur)), "r"(SLICES) : "memory");
+        float acc[2][NT][4];  // [0]: rows g = i, g + 8 = f;  [1]: g-gate, o
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float4 v = *reinterpret_cast<const float4*>(gs + (cur * NS + n * 8 + 2 * c + e) * GSL + ucol);
+                acc[0][n][e] = v.x; acc[0][n][2 + e] = v.y; acc[1][n][e] = v.z; acc[1][n][2 + e] = v.w;
+            }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            uint32_t bh[NT][2];
+            load_b_frags<NT>(hp_hi, HST, ks * 16, lane, bh);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) mma_bf16(acc[mt][n], ahi[mt][ks], bh[n]);
+            if (SPLIT) {
+                {
+                    uint4 al[2];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) al[mt] = alo[((warp * 2 + mt) * 8 + ks) * 32 + lane];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int n = 0; n < NT; ++n) mma_bf16(acc[mt][n], al[mt], bh[n]);
+                }
+                uint32_t bl[NT][2];
+                load_b_frags<NT>(hp_lo, HST, ks * 16, lane, bl);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) mma_bf16(acc[mt][n], ahi[mt][ks], bl[n]);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float ig = sigmoid_cell<SPLIT>(acc[0][n][e]);
+                const float fg = sigmoid_cell<SPLIT>(acc[0][n][2 + e]);
+                const float gg = tanh_cell<SPLIT>(acc[1][n][e]);
+                const float og = sigmoid_cell<SPLIT>(acc[1][n][2 + e]);
+                const float cc = fmaf(fg, cst[n][e], ig * gg);
+                cst[n][e] = cc;
+                const float hh = og * tanh_cell<SPLIT>(cc);
+                stg_pred(H + (hoff[n][e] + toff * 256u), hh, valid[n][e] && H != nullptr);
+                const int so = (n * 8 + 2 * c + e) * 32 + 8 * warp + g;
+                const __nv_bfloat16 hb = __float2bfloat16_rn(hh);
+                hst[so] = hb;
+                if (SPLIT) hst[NS * 32 + so] = __float2bfloat16_rn(hh - __bfloat162float(hb));
+            }
+        cp_async_wait_all();
+        __syncthreads();   // slice staged; every warp is done reading h_{t-1} (buffer cur ^ 1); the next gate rows are visible
+        if (tid < 4)       // tell every CTA that this one no longer needs its buffer cur ^ 1
+            asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(peer[tid] + empty_off + (uint32_t)((cur ^ 1) * 8)) : "memory");
+        if (step > 0) {    // all four CTAs are done reading buffer `cur` (they were at step - 1): it may be overwritten
+            const uint32_t par = (uint32_t)(((step - 1) >> 1) & 1), bar = smem_u32(empty + cur);
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(done) : "r"(bar), "r"(par) : "memory");
+        }
+        // the slice (64 bytes per sequence and plane) into buffer `cur` of all four CTAs: 16-byte asynchronous stores that count on the
+        // destination's `full` barrier (no fence: a release at cluster scope would also wait for the global stores of H)
+        for (int i = tid; i < (SPLIT ? 2 : 1) * NS * 4 * 4; i += 128) {
+            const int r = i & 3, q = (i >> 2) & 3, row = (i >> 4) % NS, plane = (i >> 4) / NS;
+            const uint4 v = *reinterpret_cast<const uint4*>(hst + (plane * NS + row) * 32 + q * 8);
+            const uint32_t dst = peer[r] + (uint32_t)(((cur * 2 + plane) * HPL + row * HST + 32 * rank + q * 8) * 2);
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(dst), "r"(v.x),
+                         "r"(v.y), "r"(v.z), "r"(v.w), "r"(peer[r] + full_off + (uint32_t)(cur * 8))
+                         : "memory");
+        }
+        {   // h_t complete in this CTA's buffer `cur`
+            const uint32_t par = (uint32_t)((step >> 1) & 1), bar = smem_u32(full + cur);
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(done) : "r"(bar), "r"(par) : "memory");
+        }
+        if (pl.h_hi != nullptr) {   // this CTA's 32 units of h_t -> planes
+            const __nv_bfloat16* hc_hi = hb0 + cur * 2 * HPL;
+            for (int ch = tid; ch < NS * 4; ch += 128) {
+                const int sq = ch >> 2, c16 = 4 * rank + (ch & 3);
+                if (sq >= nv) continue;
+                const size_t o = (size_t)((unsigned)sbase[sq] + toff) * 256 + (size_t)dir * kH + c16 * 8;
+                *reinterpret_cast<uint4*>(pl.h_hi + o) = *reinterpret_cast<const uint4*>(hc_hi + sq * HST + c16 * 8);
+                if (SPLIT && pl.h_lo != nullptr)
+                    *reinterpret_cast<uint4*>(pl.h_lo + o) = *reinterpret_cast<const uint4*>(hc_hi + HPL + sq * HST + c16 * 8);
+            }
+        }
+    }
+    cluster_barrier();   // no CTA leaves while a peer could still address its shared memory
+}
+
 // ------------------------------------------------------------------------------------------------
 struct PackArgs {
     const float* w_ih[2];
@@ -874,6 +1094,31 @@ cudaError_t fwd16_launch(const LstmPack& w, float* G, float* H, float* Cst, cons
     return cudaGetLastError();
 }
 
+template <int NT>
+cudaError_t fwdc_launch(const LstmPack& w, const float* G, float* H, const SeqMap& m, bool split, const LstmPlanes& pl, int spc, cudaStream_t st) {
+    const int smem = (split ? 4 * 2 * 8 * 32 * 16 : 0) + 4 * 8 * NT * HST * 2 + 2 * 8 * NT * GSL * 4 + 8 * NT * 4 + 2 * 8 * NT * 32 * 2 + 64;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * ceil_div(m.nseq, spc), 2);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    if (split) {
+        e = set_smem(lstm_fwdc_kernel<NT, true>, smem);
+        if (e != cudaSuccess) return e;
+        return cudaLaunchKernelEx(&cfg, lstm_fwdc_kernel<NT, true>, w, G, H, m, pl, spc);
+    }
+    e = set_smem(lstm_fwdc_kernel<NT, false>, smem);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchKernelEx(&cfg, lstm_fwdc_kernel<NT, false>, w, G, H, m, pl, spc);
+}
+
+int g_lstm_cluster = 1;   // 0 off, 1 automatic (inference passes of <= 128 sequences), 2 always (inference)
 int g_lstm_pipeline = 1;  // 0 plain kernels, 1 automatic, 2 pipelined (groups of 16 + 8 sequences), 3 16-warp kernel
 
 }  // namespace
@@ -884,6 +1129,12 @@ int lstm_set_pipeline(int mode) {
     return 0;
 }
 int lstm_get_pipeline() { return g_lstm_pipeline; }
+int lstm_set_cluster(int mode) {
+    if (mode < 0 || mode > 2) return -1;
+    g_lstm_cluster = mode;
+    return 0;
+}
+int lstm_get_cluster() { return g_lstm_cluster; }
 
 int lstm_pick_nt(int nseq) {
     // smallest tile that still fits the whole pass in one wave of 148 SMs (2 directions per tile)
@@ -899,6 +1150,16 @@ cudaError_t launch_lstm_fwd(const LstmPack& w, float* G, float* H, float* Cst, c
     memset(&pl, 0, sizeof(pl));
     if (planes) pl = *planes;
     if (w.rec5 != nullptr && lstm_rec5_wanted(m, split, false)) return launch_lstm_rec5_fwd(w.rec5, G, H, Cst, m, split, save, st, pl);
+    // inference passes too small to fill the GPU: gate rows split over four-CTA clusters (33 clusters are co-resident on a B200)
+    // (16 sequence tiles per direction = 32 clusters = one wave).  Measured per pass (tests/tools/time_cluster_rec.py, fp32 / bf16 mode, us):
+    // 82 sequences 123 / 82 against 182 / 91 (16-warp kernel), 100: 104 / 71 against 156 / 78; 164: 186 / 122 against 190 / 117 -> automatic
+    // up to 128 sequences (8-sequence tiles)
+    if (!save && pl.hp_hi == nullptr && g_lstm_cluster != 0 && (g_lstm_cluster == 2 || m.nseq <= 128)) {
+        int spc = ceil_div(m.nseq, 16);
+        if (spc > 16) spc = 16;
+        if (spc <= 8) return fwdc_launch<1>(w, G, H, m, split, pl, spc, st);
+        return fwdc_launch<2>(w, G, H, m, split, pl, spc, st);
+    }
     const int nt = lstm_pick_nt(m.nseq);
     int pipe = g_lstm_pipeline;
     // automatic (measured on B200 with tests/tools/time_recurrence.py, training mode, intra / inter pass):

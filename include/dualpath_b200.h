@@ -42,6 +42,10 @@ int dp_set_lstm_pipeline(int mode);
  * tensor memory, lo half in shared memory, 32 sequences per CTA): 1 (default) = automatic (passes with >= 256 sequences per direction),
  * 2 = always, 0 = never (the register-stationary mma.sync kernels selected by dp_set_lstm_pipeline). */
 int dp_set_lstm_tcgen05(int mode);
+/* Forward LSTM recurrence of small inference passes (B = 1: ~80-100 sequences per direction) with the gate rows of a sequence tile split
+ * over a cluster of four CTAs that exchange h_t through distributed shared memory (csrc/lstm.cu, lstm_fwdc_kernel; same arithmetic and
+ * order per cell as the 16-warp kernel): 1 (default) = automatic (inference passes of <= 128 sequences), 2 = every inference pass, 0 = off. */
+int dp_set_lstm_cluster(int mode);
 /* Weight-gradient GEMM (autograd's dW = dY^T X) as 4-CTA clusters that multicast the shared operand tiles (outputs with a multiple of four
  * 128-row slices): 1 on, 0 (default) off -- measured equal on B200 (the L2 already shares the four unicast requests).  Returns the previous setting. */
 int dp_set_wgrad_multicast(int on);

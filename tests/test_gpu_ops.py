@@ -199,6 +199,7 @@ def test_bilstm_forward_kernel_variants(ops, layout, mode, B, S, K):
     ref = _oracle_bilstm(xr, leaf, layout, impl="aten")
     ref.backward(dH)
     _lib.check(_lib.lib().dp_set_lstm_pipeline(mode))
+    _lib.check(_lib.lib().dp_set_lstm_cluster(0))   # the inference call below must run the selected variant, not the cluster kernel
     try:
         for prec, tol in (("fp32", 2e-5), ("bf16", 3e-2)):
             H, _, _ = ops.bilstm_forward(pack, x.cuda(), layout, precision=prec)
@@ -212,6 +213,54 @@ def test_bilstm_forward_kernel_variants(ops, layout, mode, B, S, K):
                 assert rel_l2(dx, xr.grad) < 5e-5
     finally:
         _lib.check(_lib.lib().dp_set_lstm_pipeline(1))
+        _lib.check(_lib.lib().dp_set_lstm_cluster(1))
+
+
+@pytest.mark.parametrize("layout", ["intra", "inter"])
+@pytest.mark.parametrize("B,S,K", [(1, 5, 7), (1, 82, 100), (2, 82, 100), (3, 21, 9), (5, 82, 12)])
+def test_bilstm_forward_cluster_kernel(ops, layout, B, S, K):
+    """dp_set_lstm_cluster: the four-CTA-cluster forward recurrence (gate rows split over the cluster, h exchanged through distributed
+    shared memory) against the oracle and bit for bit against the 16-warp kernel: ragged tiles (5 / 7 sequences), the B = 1 and B = 2
+    pass sizes of the bench geometry (8- and 16-sequence tiles), several waves of clusters (410 sequences, forced), fp32 and bf16 mode,
+    fp32 H and the hi / lo operand planes."""
+    from audio_only_speech_separation_b200 import _lib
+
+    lstm, sd, pack = _lstm_and_pack(ops, seed=5)
+    g = torch.Generator().manual_seed(B * 100 + S + K)
+    x = torch.randn(B, S, K, 64, generator=g)
+    with torch.no_grad():
+        ref = _oracle_bilstm(x, sd, layout)
+    L = _lib.lib()
+    try:
+        for prec, tol in (("fp32", 2e-5), ("bf16", 3e-2)):
+            _lib.check(L.dp_set_lstm_cluster(0))
+            _lib.check(L.dp_set_lstm_pipeline(3))
+            _lib.check(L.dp_set_lstm_tcgen05(0))
+            H0, _, _ = ops.bilstm_forward(pack, x.cuda(), layout, precision=prec)
+            _lib.check(L.dp_set_lstm_cluster(2))
+            H1, _, _ = ops.bilstm_forward(pack, x.cuda(), layout, precision=prec)
+            err = rel_l2(H1, ref)
+            record("bilstm_fwd_cluster", prec=prec, layout=layout, B=B, S=S, K=K, rel_l2=err, bit_equal=bool(torch.equal(H0, H1)))
+            assert err < tol
+            assert torch.equal(H0, H1)
+        # operand planes (what the engines consume in inference)
+        P = B * S * K
+        nseq, ln, qdiv, s_hi, s_lo, s_t = (B * S, K, 1 << 30, 0, K, 1) if layout == "intra" else (B * K, S, K, S * K, 1, K)
+        G0 = (torch.randn(P, 1024, generator=g) * 0.5).cuda()
+        outs = []
+        for mode in (0, 2):
+            _lib.check(L.dp_set_lstm_cluster(mode))
+            hh, hl = (torch.full((P, 256), float("nan"), device="cuda", dtype=torch.bfloat16) for _ in range(2))
+            Gw = G0.clone()
+            _lib.check(L.dp_lstm_recurrence_planes_f32(_lib.ptr(pack.buf), _lib.ptr(Gw), None, None, _lib.ptr(hh), _lib.ptr(hl), None, None, nseq, ln,
+                                                      qdiv, s_hi, s_lo, s_t, 0, 0, _lib.stream_ptr()))
+            assert torch.equal(Gw, G0)   # inference leaves the pre-activations alone
+            outs.append((hh, hl))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    finally:
+        _lib.check(L.dp_set_lstm_cluster(1))
+        _lib.check(L.dp_set_lstm_pipeline(1))
+        _lib.check(L.dp_set_lstm_tcgen05(1))
 
 
 @pytest.mark.parametrize("layout", ["intra", "inter"])

@@ -20,6 +20,9 @@ else:
     m = TasNet(sample_rate=sr, module="DPTNet" if name == "dptnet" else "DPRNN", unfold=name == "dprnn_unfold")
 m = m.cuda().eval()
 m.precision = prec
+if "LSTM_CLUSTER" in os.environ:   # 0 off / 1 automatic / 2 always: the four-CTA-cluster recurrence of small inference passes
+    from audio_only_speech_separation_b200 import _lib
+    _lib.check(_lib.lib().dp_set_lstm_cluster(int(os.environ["LSTM_CLUSTER"])))
 x = torch.randn(B, T, device="cuda") * 0.1
 with torch.no_grad():
     for _ in range(3):
