@@ -585,10 +585,20 @@ gemm_tma_tn_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 float* C = seg1 ? p.C1 : p.C0;
                 const int ldc = seg1 ? p.ldc1 : p.ldc0, cb = seg1 ? c0 - p.nb0 : c0;
                 const int tr = seg1 ? p.transpose1 : p.transpose0;
+                if (!tr && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+                    // 32 consecutive floats of one output row: eight 16-byte vector reductions instead of 32 scalar ones
+                    float* dst = C + (size_t)row * ldc + cb;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float* dst = tr ? C + (size_t)(cb + j) * ldc + row : C + (size_t)row * ldc + cb + j;
-                    atomicAdd(dst, v[j] * p.scale);
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst + j), "f"(v[j] * p.scale), "f"(v[j + 1] * p.scale),
+                                     "f"(v[j + 2] * p.scale), "f"(v[j + 3] * p.scale)
+                                     : "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float* dst = tr ? C + (size_t)(cb + j) * ldc + row : C + (size_t)row * ldc + cb + j;
+                        atomicAdd(dst, v[j] * p.scale);
+                    }
                 }
             }
         }
