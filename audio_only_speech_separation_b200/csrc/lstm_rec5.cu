@@ -177,36 +177,40 @@ __device__ __forceinline__ void r5_issue(uint32_t d, uint32_t a_tm, uint64_t d_w
     }
 }
 
-// forward step s, K blocks 2 PQ and 2 PQ + 1 (hidden units 32 PQ .. 32 PQ + 31 = the h slice tile PQ's warps write) for all four gate tiles.
-// d_w / d_xh / d_xl: descriptors of the W_lo image, the h hi plane and the h lo plane at offset 0.
-template <bool SPLIT, int PQ, int J, int NS>
+// forward step s, K blocks 2 PQ and 2 PQ + 1 (hidden units 32 PQ .. 32 PQ + 31 = the h slice tile PQ's warps write) for all four gate tiles of one
+// 32-sequence group.  d_w / d_xh / d_xl: descriptors of the W_lo image, the h hi plane and the h lo plane at offset 0.  Every product is
+// M = 128, N = 32: a small-N tcgen05.mma costs ~40 cycles whatever N <= 64 is (it streams its 4 KB A tile), so a CTA with 64 sequences runs
+// TWO independent groups half a step apart -- one group's products overlap the other group's cell update -- instead of one N = 64 product
+// whose cell update (twice as long) cannot overlap anything.  NS = 64: group GRP owns accumulator columns 128 GRP .. 128 GRP + 127 and rows
+// 32 GRP .. 32 GRP + 31 of the h tile (+4 096 bytes inside every K block).
+template <bool SPLIT, int PQ, int J, int NS, int GRP>
 __device__ __forceinline__ void r5_fwd_tile(uint32_t dcol, uint32_t tmem, uint64_t d_w, uint64_t d_xh, uint64_t d_xl) {
-    constexpr uint32_t IDESC = idesc_bf16(128, NS, 0, 0);
+    constexpr uint32_t IDESC = idesc_bf16(128, 32, 0, 0);
     constexpr int KB = NS * 128;
-    r5_issue<SPLIT, PQ == 0, J * NS, J * 64 + PQ * 16, ((J * 2 + (PQ >> 1)) * 16384) / 16 + (PQ & 1) * 4, ((PQ >> 1) * KB) / 16 + (PQ & 1) * 4>(
-        dcol, tmem, d_w, d_xh, d_xl, IDESC);
+    r5_issue<SPLIT, PQ == 0, GRP * 128 + J * 32, J * 64 + PQ * 16, ((J * 2 + (PQ >> 1)) * 16384) / 16 + (PQ & 1) * 4,
+             ((PQ >> 1) * KB) / 16 + (PQ & 1) * 4 + GRP * 256>(dcol, tmem, d_w, d_xh, d_xl, IDESC);
 }
-// NS = 32: accumulators double buffered, block PQ starts as soon as h slice PQ of the previous step is written.  NS = 64: the four accumulators
-// fill tensor memory (256 columns) and are single buffered, so the first block waits for ALL cell-update warps (they have read the previous step's
-// accumulators by then) and the step's products run after its cell updates.
-template <bool SPLIT, int PQ, int NS>
+// NS = 32: one group, accumulators double buffered by step parity (dcol), block PQ starts as soon as h slice PQ of the previous step is
+// written.  NS = 64: two groups with one accumulator set each; a group's first block waits for all of the group's cell-update warps (they
+// have read the accumulators before they publish h) -- the other group's products fill that time.
+template <bool SPLIT, int PQ, int NS, int GRP>
 __device__ __forceinline__ void r5_fwd_block(uint64_t* h_ready, uint64_t* d_full, int s, uint32_t dcol, uint32_t tmem, uint64_t d_w, uint64_t d_xh,
                                              uint64_t d_xl) {
     if (NS == 32) {
         r5_wait(h_ready + PQ, (s - 1) & 1);
-    } else if (PQ == 0) {
+    } else if (PQ == 0) {   // the block overwrites all four accumulators of the group: every tile's warps must have read the previous step's
 #pragma unroll
-        for (int j = 0; j < 4; ++j) r5_wait(h_ready + j, (s - 1) & 1);
+        for (int j = 0; j < 4; ++j) r5_wait(h_ready + GRP * 4 + j, (s - 1) & 1);
     }
     tc_fence_after();
-    uint64_t* df = NS == 32 ? d_full + (s & 1) * 4 : d_full;
-    r5_fwd_tile<SPLIT, PQ, 0, NS>(dcol, tmem, d_w, d_xh, d_xl);
+    uint64_t* df = NS == 32 ? d_full + (s & 1) * 4 : d_full + GRP * 4;
+    r5_fwd_tile<SPLIT, PQ, 0, NS, GRP>(dcol, tmem, d_w, d_xh, d_xl);
     if (PQ == 3) umma_commit_w(df + 0);
-    r5_fwd_tile<SPLIT, PQ, 1, NS>(dcol, tmem, d_w, d_xh, d_xl);
+    r5_fwd_tile<SPLIT, PQ, 1, NS, GRP>(dcol, tmem, d_w, d_xh, d_xl);
     if (PQ == 3) umma_commit_w(df + 1);
-    r5_fwd_tile<SPLIT, PQ, 2, NS>(dcol, tmem, d_w, d_xh, d_xl);
+    r5_fwd_tile<SPLIT, PQ, 2, NS, GRP>(dcol, tmem, d_w, d_xh, d_xl);
     if (PQ == 3) umma_commit_w(df + 2);
-    r5_fwd_tile<SPLIT, PQ, 3, NS>(dcol, tmem, d_w, d_xh, d_xl);
+    r5_fwd_tile<SPLIT, PQ, 3, NS, GRP>(dcol, tmem, d_w, d_xh, d_xl);
     if (PQ == 3) umma_commit_w(df + 3);
 }
 
@@ -262,10 +266,10 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
     constexpr int OFF_BAR = OFF_G + 16 * 8 * 32 * 16;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* d_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);  // [2 buffers][4 tiles]
-    uint64_t* h_ready = d_full + 8;                                   // [4 tiles]
-    uint64_t* h_copied = h_ready + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_copied + 1);
+    uint64_t* d_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);  // [2 buffers (NS = 32) or 2 sequence groups (NS = 64)][4 tiles]
+    uint64_t* h_ready = d_full + 8;                                   // [group][4 tiles]
+    uint64_t* h_copied = h_ready + 8;                                 // [group]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_copied + 2);
     int* sbase = reinterpret_cast<int*>(tmem_slot + 2);               // [NS]
     uint8_t* hs = smem + OFF_H;
 
@@ -278,8 +282,8 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
 
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) mbar_init(d_full + i, 1);
-        for (int i = 0; i < 4; ++i) mbar_init(h_ready + i, 128);
-        mbar_init(h_copied, 3);
+        for (int i = 0; i < 8; ++i) mbar_init(h_ready + i, 128);
+        for (int i = 0; i < 2; ++i) mbar_init(h_copied + i, 3);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     r5_fill_bases<false, NS>(sbase, q0, nv, p.m);
@@ -324,10 +328,16 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
         const uint64_t d_xl = d_xh + (uint64_t)(PLANE >> 4);
         for (int s = 1; s < len; ++s) {
             const uint32_t dcol = tmem + 256 + (NS == 32 ? (uint32_t)((s & 1) * 128) : 0u);
-            r5_fwd_block<SPLIT, 0, NS>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
-            r5_fwd_block<SPLIT, 1, NS>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
-            r5_fwd_block<SPLIT, 2, NS>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
-            r5_fwd_block<SPLIT, 3, NS>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+            r5_fwd_block<SPLIT, 0, NS, 0>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+            r5_fwd_block<SPLIT, 1, NS, 0>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+            r5_fwd_block<SPLIT, 2, NS, 0>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+            r5_fwd_block<SPLIT, 3, NS, 0>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+            if (NS == 64) {   // the second group's products run while the first group's cells are updated, and vice versa
+                r5_fwd_block<SPLIT, 0, NS, 1>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+                r5_fwd_block<SPLIT, 1, NS, 1>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+                r5_fwd_block<SPLIT, 2, NS, 1>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+                r5_fwd_block<SPLIT, 3, NS, 1>(h_ready, d_full, s, dcol, tmem, d_w, d_xh, d_xl);
+            }
             __syncwarp();
         }
     } else if (warp < 4) {
@@ -350,37 +360,40 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
             const long long tnext = (long long)(dir ? t - 1 : t + 1) * s_t;
             const bool has_next = s + 1 < len;
 #pragma unroll
-            for (int pq = 0; pq < 4; ++pq) r5_wait(h_ready + pq, s & 1);
-            if (any) {
-                for (int ch = cl; ch < NS * 16; ch += 96) {
-                    const int n = ch >> 4, u = ch & 15;
-                    if (n >= nv) continue;
-                    const uint32_t off = (u >> 3) * KB + n * 128 + (((u & 7) ^ (n & 7)) << 4);
-                    const uint4 vh = *reinterpret_cast<const uint4*>(hs + off);
-                    uint4 vl = make_uint4(0, 0, 0, 0);
-                    if (SPLIT) vl = *reinterpret_cast<const uint4*>(hs + PLANE + off);
-                    const size_t col = (size_t)dir * kH + u * 8;
-                    if (p.pl.h_hi != nullptr) {
-                        const size_t o = (size_t)(sbase[n] + toff) * 256 + col;
-                        *reinterpret_cast<uint4*>(p.pl.h_hi + o) = vh;
-                        if (SPLIT && p.pl.h_lo != nullptr) *reinterpret_cast<uint4*>(p.pl.h_lo + o) = vl;
-                    }
-                    if (SAVE && has_next && p.pl.hp_hi != nullptr) {
-                        const size_t o = (size_t)(sbase[n] + tnext) * 256 + col;
-                        *reinterpret_cast<uint4*>(p.pl.hp_hi + o) = vh;
-                        if (SPLIT && p.pl.hp_lo != nullptr) *reinterpret_cast<uint4*>(p.pl.hp_lo + o) = vl;
+            for (int grp = 0; grp < HALVES; ++grp) {
+#pragma unroll
+                for (int pq = 0; pq < 4; ++pq) r5_wait(h_ready + grp * 4 + pq, s & 1);
+                if (any) {
+                    for (int ch = grp * 512 + cl; ch < (grp + 1) * 512; ch += 96) {
+                        const int n = ch >> 4, u = ch & 15;
+                        if (n >= nv) continue;
+                        const uint32_t off = (u >> 3) * KB + n * 128 + (((u & 7) ^ (n & 7)) << 4);
+                        const uint4 vh = *reinterpret_cast<const uint4*>(hs + off);
+                        uint4 vl = make_uint4(0, 0, 0, 0);
+                        if (SPLIT) vl = *reinterpret_cast<const uint4*>(hs + PLANE + off);
+                        const size_t col = (size_t)dir * kH + u * 8;
+                        if (p.pl.h_hi != nullptr) {
+                            const size_t o = (size_t)(sbase[n] + toff) * 256 + col;
+                            *reinterpret_cast<uint4*>(p.pl.h_hi + o) = vh;
+                            if (SPLIT && p.pl.h_lo != nullptr) *reinterpret_cast<uint4*>(p.pl.h_lo + o) = vl;
+                        }
+                        if (SAVE && has_next && p.pl.hp_hi != nullptr) {
+                            const size_t o = (size_t)(sbase[n] + tnext) * 256 + col;
+                            *reinterpret_cast<uint4*>(p.pl.hp_hi + o) = vh;
+                            if (SPLIT && p.pl.hp_lo != nullptr) *reinterpret_cast<uint4*>(p.pl.hp_lo + o) = vl;
+                        }
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(h_copied + grp);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(h_copied);
         }
     } else {
         // ===================== cell update: warp = (tile j, quadrant q), thread = unit 32j + 8q + (lane >> 2), 8 sequence slots =====================
         // tile 0 goes to the highest warp ids: the scheduler favours them, so the slice the next step's first K blocks wait for is done first
         const int j = 3 - ((warp - 4) >> 2), q = warp & 3, u8 = lane >> 2, c = lane & 3;
         const int unit = 32 * j + 8 * q + u8;
-        const uint32_t acc_addr = tmem + ((uint32_t)(q * 32) << 16) + 256 + (uint32_t)(j * NS);
+        const uint32_t acc_addr = tmem + ((uint32_t)(q * 32) << 16) + 256 + (uint32_t)(j * 32);   // + 128 per buffer (NS = 32) or sequence group (NS = 64)
         float* const Gc = p.G + (size_t)dir * kG + unit * 4;
         float* const Cc = p.Cst + (size_t)dir * kH + unit;
         float* const Hc = p.H + (size_t)dir * kH + unit;
@@ -392,7 +405,8 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
         const uint32_t hrow = smem_u32(hs) + (uint32_t)((unit >> 6) * KB + (u8 & 6) * 2 + rowe * 128 + ((chunk ^ rowe) << 4));
         const uint32_t sel_send = odd ? 0x5410u : 0x7632u, sel_hi = odd ? 0x3254u : 0x5410u, sel_lo = odd ? 0x3276u : 0x7610u;
         // the step's gate pre-activations (one 128-bit word per cell) are staged ahead into this thread's own shared-memory slots: eight slots =
-        // one 32-sequence half; NS = 64 stages its second half while the first one is being consumed
+        // one 32-sequence group.  NS = 64: as soon as a pair of slots has been consumed it is requested again for the cells the thread updates
+        // next (the other group's of this step, then the first group's of the next step)
         const uint32_t gst_s = smem_u32(smem + OFF_G) + (uint32_t)(((warp - 4) * 256 + lane) * 16);
         const int kmax = (nv + 7) >> 3;   // sequence octets in use (warp-uniform)
         unsigned sb[8 * HALVES];
@@ -415,21 +429,23 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
         };
         stage(0, toff);
         for (int s = 0; s < len; ++s) {
-            if (s > 0) {
-                if (NS == 32) r5_wait(d_full + (s & 1) * 4 + j, (uint32_t)(((s - 2 + (s & 1)) >> 1) & 1));
-                else r5_wait(d_full + j, (uint32_t)((s - 1) & 1));
+            if (NS == 32 && s > 0) {
+                r5_wait(d_full + (s & 1) * 4 + j, (uint32_t)(((s - 2 + (s & 1)) >> 1) & 1));
                 tc_fence_after();
             }
 #pragma unroll
             for (int hf = 0; hf < HALVES; ++hf) {
-                if (hf > 0) stage(hf, toff);   // the slots of the previous half were read below
+                if (NS == 64 && s > 0) {   // this group's accumulators (the other group's products are in flight meanwhile)
+                    r5_wait(d_full + hf * 4 + j, (uint32_t)((s - 1) & 1));
+                    tc_fence_after();
+                }
                 uint32_t ra[16], rb[16];
                 if (s > 0) {
-                    const uint32_t col = (NS == 32 ? (uint32_t)((s & 1) * 128) : 0u) + (uint32_t)(hf * 32);
+                    const uint32_t col = NS == 32 ? (uint32_t)((s & 1) * 128) : (uint32_t)(hf * 128);
                     tmem_ld_16x256b_x4(acc_addr + col, ra);                  // lanes 0..15: i rows, f rows
                     tmem_ld_16x256b_x4(acc_addr + col + (16u << 16), rb);    // lanes 16..31: g rows, o rows
                     tmem_ld_wait();
-                    if (hf == 0) r5_wait(h_copied, (s - 1) & 1);   // the copy-out warps are done with the previous h tile
+                    r5_wait(h_copied + hf, (s - 1) & 1);   // the copy-out warps are done with the group's previous h rows
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { ra[i] = 0u; rb[i] = 0u; }
@@ -467,13 +483,29 @@ __global__ void __launch_bounds__(R5_THREADS, 1) lstm_rec5_fwd_kernel(const R5Ar
                         sts32(hrow + (uint32_t)((4 * hf + k) * 1024), __byte_perm(Hw, recv, sel_hi));
                         if (SPLIT) sts32(hrow + (uint32_t)((4 * hf + k) * 1024 + PLANE), __byte_perm(Lw, recv, sel_lo));
                     }
+                    if (NS == 64) {   // slots 2k, 2k + 1 are free: the words of the cells this thread updates next
+                        const int nh = hf ^ 1;
+                        const unsigned to = hf == 0 ? toff : toff + (unsigned)dstep;
+                        if ((hf == 0 || s + 1 < len) && 4 * nh + k < kmax) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) cp_async16_s(gst_s + (2 * k + e) * 512, Gc + (size_t)(sb[8 * nh + 2 * k + e] + to) * 1024);
+                        }
+                    }
+                }
+                if (NS == 64) {
+                    asm volatile("cp.async.commit_group;\n" ::);
+                    proxy_fence_async();  // the group's h rows (generic-proxy stores) -> visible to the tensor core's async proxy
+                    tc_fence_before();
+                    mbar_arrive(h_ready + hf * 4 + j);
                 }
             }
-            proxy_fence_async();  // h slice (generic-proxy stores) -> visible to the tensor core's async proxy
-            tc_fence_before();
-            mbar_arrive(h_ready + j);
+            if (NS == 32) {
+                proxy_fence_async();  // h slice (generic-proxy stores) -> visible to the tensor core's async proxy
+                tc_fence_before();
+                mbar_arrive(h_ready + j);
+            }
             toff += (unsigned)dstep;
-            if (s + 1 < len) stage(0, toff);   // next step's first half: the slots were read above
+            if (NS == 32 && s + 1 < len) stage(0, toff);   // next step: the slots were read above
         }
     }
     tc_fence_before();
@@ -731,7 +763,8 @@ int lstm_get_rec5() { return g_rec5; }
 // Automatic choice, measured on B200 (tests/tools/time_rec5.py, intra / inter pass, training mode, us):
 //   B = 16 fp32: forward 395 / 357 against 503 / 420 (mma.sync), BPTT 348 / 310 against 645 / 545
 //   B = 16 bf16: forward 378 / 379 against 320 / 297 -> mma.sync, BPTT 290 / 275 against 448 / 393
-//   B = 32 fp32: forward with 64-sequence tiles 846 / 880 against 1032 / 849, BPTT 880 / 732 against 1322 / 1090
+//   B = 32 fp32: forward with 64-sequence tiles (two groups of 32 half a step apart) 737 / 750 against 1032 / 849 (one N = 64 group:
+//                846 / 880), BPTT 880 / 732 against 1322 / 1090;  B = 40: forward 977 / 959 against 1030 / 1263
 bool lstm_rec5_wanted(const SeqMap& m, bool split, bool backward) {
     if (g_rec5 == 0) return false;
     if (g_rec5 == 2) return true;
@@ -740,9 +773,7 @@ bool lstm_rec5_wanted(const SeqMap& m, bool split, bool backward) {
     if (backward) return true;
     if (!split) return false;                      // forward: fp32-parity mode only
     if (ceil_div(m.nseq, R5_NS) <= 74) return true;   // one wave of 32-sequence tiles
-    // 64-sequence tiles (accumulators single buffered, two column halves per step): B = 32 intra 846 us against 1 032 (mma.sync), inter (44
-    // sequences per CTA = six octets) 880 against 849 -> only while a CTA holds at most five sequence octets
-    return ceil_div(m.nseq, 64) <= 74 && ceil_div(lstm_seqs_per_cta(m.nseq, 64), 8) <= 5;
+    return ceil_div(m.nseq, 64) <= 74;                // one wave of 64-sequence tiles (two groups of 32 per CTA)
 }
 
 cudaError_t launch_lstm_rec5_fwd(const void* pack, float* G, float* H, float* Cst, const SeqMap& m, bool split, bool save, cudaStream_t st,
