@@ -89,6 +89,8 @@ PROTOTYPES = {
     "dp_pitn_loss_backward": (_i, [_p, _p, _i, _i, _i, _p, _f, _p, _p]),
     "dp_pitn_reorder": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "dp_adam_clip_step": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p]),
+    "dp_adam_set_hyper": (_i, [_p, _f, _f, _f, _i, _p]),
+    "dp_adam_clip_step_dev": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _p, _f, _f, _f, _f, _p]),
     "dp_tasnet_create": (_i, [C.POINTER(TasnetConfig), C.POINTER(_i64), _i, _i64, C.POINTER(_p)]),
     "dp_tasnet_destroy": (None, [_p]),
     "dp_tasnet_pack_bytes": (_i64, [_p]),

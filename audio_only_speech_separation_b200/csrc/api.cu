@@ -448,6 +448,21 @@ int dp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, d
     return 0;
 }
 
+int dp_adam_set_hyper(float* hyper, float lr, float beta1, float beta2, int step, void* stream) {
+    if (!hyper || step < 1) return fail("dp_adam_set_hyper: hyper = device pointer to three floats, step counts from 1");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    CK(launch_set_hyper(hyper, lr, (float)bc1, (float)bc2, S(stream)));
+    return 0;
+}
+int dp_adam_clip_step_dev(float* p, const float* g, float* m, float* v, int64_t n, double* norm2, float grad_scale, float max_norm,
+                          const float* hyper, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+    if (!hyper) return fail("dp_adam_clip_step_dev: hyper = device pointer to (lr, 1 - beta1^t, 1 - beta2^t)");
+    CK(cudaMemsetAsync(norm2, 0, sizeof(double), S(stream)));
+    if (max_norm > 0.f) CK(launch_sumsq(g, n, norm2, S(stream)));
+    CK(launch_adam_clip(p, g, m, v, n, norm2, grad_scale, max_norm, 0.f, beta1, beta2, eps, 1.f, 1.f, weight_decay, S(stream), hyper));
+    return 0;
+}
+
 }  // extern "C"
 
 // ================================================================================================

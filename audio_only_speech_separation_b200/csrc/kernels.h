@@ -351,11 +351,12 @@ cudaError_t launch_pit_loss_bwd(const float* est, const float* tgt, int B, int T
 cudaError_t launch_reorder_sources(const float* est, const int* perm, float* out, int B, int T, cudaStream_t st);
 
 // ---------------- optimizer (optim.cu) ----------------
+cudaError_t launch_set_hyper(float* hyper, float lr, float bc1, float bc2, cudaStream_t st);
 cudaError_t launch_sumsq(const float* g, long long n, double* out /*+=*/, cudaStream_t st);
 // torch clip_grad_norm_ + Adam, fused.  norm2 holds sum of squares of the *unscaled* grads; gscale is applied first
 // (1/world_size after an all-reduce SUM).
 cudaError_t launch_adam_clip(float* p, const float* g, float* m, float* v, long long n, const double* norm2, float gscale,
                              float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2, float wd,
-                             cudaStream_t st);
+                             cudaStream_t st, const float* hyper = nullptr);
 
 }  // namespace dp

@@ -29,7 +29,10 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, long long n, const double* __restrict__ norm2, float gscale,
                                                         float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2,
-                                                        float wd) {
+                                                        float wd, const float* __restrict__ hyper) {
+    if (hyper) {   // (lr, 1 - b1^t, 1 - b2^t) from device memory: a captured step (CUDA graph) must not bake them into the launch
+        lr = hyper[0]; bc1 = hyper[1]; bc2 = hyper[2];
+    }
     float coef = gscale;
     if (max_norm > 0.f) {
         float total = (float)sqrt(*norm2) * gscale;
@@ -48,7 +51,16 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
     }
 }
 
+__global__ void set_hyper_kernel(float* hyper, float a, float b, float c) {
+    hyper[0] = a; hyper[1] = b; hyper[2] = c;
+}
+
 }  // namespace
+
+cudaError_t launch_set_hyper(float* hyper, float lr, float bc1, float bc2, cudaStream_t st) {
+    set_hyper_kernel<<<1, 1, 0, st>>>(hyper, lr, bc1, bc2);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_sumsq(const float* g, long long n, double* out, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
@@ -59,11 +71,11 @@ cudaError_t launch_sumsq(const float* g, long long n, double* out, cudaStream_t 
 }
 
 cudaError_t launch_adam_clip(float* p, const float* g, float* m, float* v, long long n, const double* norm2, float gscale, float max_norm,
-                             float lr, float b1, float b2, float eps, float bc1, float bc2, float wd, cudaStream_t st) {
+                             float lr, float b1, float b2, float eps, float bc1, float bc2, float wd, cudaStream_t st, const float* hyper) {
     if (n <= 0) return cudaSuccess;
     long long blocks = ceil_div_ll(n, 256 * 4);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    adam_clip_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, norm2, gscale, max_norm, lr, b1, b2, eps, bc1, bc2, wd);
+    adam_clip_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, norm2, gscale, max_norm, lr, b1, b2, eps, bc1, bc2, wd, hyper);
     return cudaGetLastError();
 }
 

@@ -77,8 +77,9 @@ def build_from_config(config: dict, sample_rate: Optional[int] = None):
 
 
 def fit(config: dict, train_batches: Callable[[int], Iterable], val_batches: Callable[[int], Iterable], exp_dir: str, *, device="cuda",
-        distributed=False, max_epochs: Optional[int] = None, log: Callable[[str], None] = print):
-    """Run the reference's training procedure; returns the per-epoch history."""
+        distributed=False, max_epochs: Optional[int] = None, log: Callable[[str], None] = print, cuda_graph: bool = True):
+    """Run the reference's training procedure; returns the per-epoch history.  cuda_graph: batches of a shape seen twice before are
+    stepped by CUDA-graph replay (TasNet models; the reference trains on fixed-length segments)."""
     import yaml
 
     os.makedirs(exp_dir, exist_ok=True)
@@ -90,7 +91,7 @@ def fit(config: dict, train_batches: Callable[[int], Iterable], val_batches: Cal
     if str(opt.get("optim_name", "adam")).lower() != "adam":
         raise NotImplementedError("the fused step implements Adam (optimizer.optim_name: adam), what every dual-path config of the reference uses")
     trainer = DualPathTrainer(model, train_loss, lr=float(opt.get("lr", 1e-3)), weight_decay=float(opt.get("weight_decay", 0.0)), max_norm=5.0,
-                              distributed=distributed)
+                              distributed=distributed, cuda_graph=cuda_graph)
     sch = config.get("scheduler", {})
     scheduler = None
     if sch.get("sche_name") == "ReduceLROnPlateau":

@@ -526,6 +526,9 @@ class TasNet(BaseModel):
     def pack_launches(self) -> int:
         return 0 if self.group_size > 1 else 1 + 2 * self.layer
 
+    # the fused step draws nothing on the host (no dropout): DualPathTrainer(cuda_graph=True) may replay it as a CUDA graph
+    graph_safe_training = True
+
     def _train_forward(self, mixture, ws=None):
         if self.group_size > 1:
             return self._gc_train_forward(mixture, ws)

@@ -21,7 +21,7 @@ from .losses.pit_wrapper import PITLossWrapper
 
 class DualPathTrainer:
     def __init__(self, model, loss: PITLossWrapper, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=5.0,
-                 process_group=None, distributed=False):
+                 process_group=None, distributed=False, cuda_graph=False):
         if not isinstance(loss, PITLossWrapper) or not isinstance(loss.loss_func, PairwiseNegSDR) or loss.pit_from != "pw_mtx":
             raise NotImplementedError("DualPathTrainer needs PITLossWrapper(PairwiseNegSDR(...), pit_from='pw_mtx')")
         if not (hasattr(model, "_train_forward") and hasattr(model, "_train_backward")):
@@ -36,6 +36,12 @@ class DualPathTrainer:
         self._state_for = None
         self._ws = None
         self.launches_per_step = 0
+        # cuda_graph: from the third step with the same batch shape the step is replayed as two CUDA graphs (pack + forward + loss + backward:
+        # ~265 launches; clip + Adam) with the NCCL all-reduce between them; learning rate and bias corrections reach the Adam kernel through
+        # device memory
+        self.cuda_graph = bool(cuda_graph) and bool(getattr(model, "graph_safe_training", False))
+        self._graphs, self._graph_seen = {}, {}
+        self._hyper_dev = None
 
     def _ensure_state(self, device):
         m = self.model
@@ -62,8 +68,61 @@ class DualPathTrainer:
 
         return dist.get_world_size(self.group)
 
+    _GRAPH_SLOTS = 4
+
     def step(self, mixtures: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         """One optimisation step on a device-resident batch; returns the (device, 0-d) loss of this rank."""
+        if not self.cuda_graph:
+            return self._step(mixtures, targets)
+        self._ensure_state(mixtures.device)
+        key = (tuple(mixtures.shape), str(getattr(self.model, "precision", "")), self.model._flat.data_ptr(), mixtures.device.index)
+        ent = self._graphs.get(key)
+        if ent is None:
+            seen = self._graph_seen.get(key, 0)
+            if seen < 2:   # workspaces, lazily loaded kernels and the NCCL communicator come into being in eager steps
+                if len(self._graph_seen) >= 64:
+                    self._graph_seen.clear()
+                self._graph_seen[key] = seen + 1
+                return self._step(mixtures, targets)
+            if len(self._graphs) >= self._GRAPH_SLOTS:
+                self._graphs.clear()
+            if self._hyper_dev is None:
+                self._hyper_dev = torch.zeros(3, dtype=torch.float32, device=mixtures.device)
+            static_mix, static_tgt = mixtures.clone(), targets.clone()
+            torch.cuda.synchronize(mixtures.device)
+            # two graphs around the gradient all-reduce, which stays an ordinary NCCL call between the replays; nothing executes while capturing
+            g_grad, g_update = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_grad):
+                static_loss = self._forward_backward(static_mix, static_tgt)
+            with torch.cuda.graph(g_update):
+                self._update(1.0 / self.world_size(), True)
+            ent = self._graphs[key] = (g_grad, g_update, static_mix, static_tgt, static_loss)
+        g_grad, g_update, static_mix, static_tgt, static_loss = ent
+        static_mix.copy_(mixtures)
+        static_tgt.copy_(targets)
+        g_grad.replay()
+        self._all_reduce()
+        self.step_count += 1
+        self._set_hyper(self.step_count)
+        g_update.replay()
+        self.model.mark_params_dirty()
+        return static_loss.clone()
+
+    def _set_hyper(self, step: int):
+        """(lr, 1 - beta1^t, 1 - beta2^t) of the coming step into device memory, on the stream, ahead of the replay."""
+        check(lib().dp_adam_set_hyper(ptr(self._hyper_dev), float(self.lr), float(self.betas[0]), float(self.betas[1]), step, stream_ptr()),
+              "dp_adam_set_hyper")
+
+    def _step(self, mixtures: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        loss = self._forward_backward(mixtures, targets)
+        gscale = self._all_reduce()
+        self.step_count += 1
+        self._update(gscale, False)
+        self.model.mark_params_dirty()
+        return loss
+
+    def _forward_backward(self, mixtures: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        """Pack (if the weights changed), forward, PIT loss, backward into the flat gradient buffer of this rank."""
         m = self.model
         self._ensure_state(mixtures.device)
         B, T = mixtures.shape
@@ -77,23 +136,36 @@ class DualPathTrainer:
         self.gflat.zero_()
         m._train_backward(d_est, self.gflat, ctx, B, T)
         launches += m.last_launches
-        gscale = 1.0
-        if self.distributed:
-            import torch.distributed as dist
-
-            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.group)
-            gscale = 1.0 / dist.get_world_size(self.group)
-        self.step_count += 1
-        check(
-            lib().dp_adam_clip_step(ptr(m._flat), ptr(self.gflat), ptr(self.exp_avg), ptr(self.exp_avg_sq), m._flat.numel(),
-                                    ptr(self.norm2), gscale, float(self.max_norm), float(self.lr), float(self.betas[0]),
-                                    float(self.betas[1]), float(self.eps), self.step_count, float(self.weight_decay), stream_ptr()),
-            "dp_adam_clip_step",
-        )
-        m.mark_params_dirty()
-        launches += 2 + m.pack_launches  # sumsq + adam, and the re-pack of the weights the next forward triggers
-        self.launches_per_step = launches
+        self.launches_per_step = launches + 2 + m.pack_launches  # + sumsq + adam, and the re-pack of the weights the next forward triggers
         return loss.reshape(())
+
+    def _all_reduce(self) -> float:
+        """Sum of the gradients over the ranks (one NCCL call on the flat buffer); returns the scale that turns it into the mean."""
+        if not self.distributed:
+            return 1.0
+        import torch.distributed as dist
+
+        dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.group)
+        return 1.0 / dist.get_world_size(self.group)
+
+    def _update(self, gscale: float, captured: bool):
+        """Fused clip + Adam over the flat buffers.  captured: learning rate and bias corrections come from device memory (written before
+        every replay by _set_hyper), not from the launch arguments."""
+        m = self.model
+        if captured:
+            check(
+                lib().dp_adam_clip_step_dev(ptr(m._flat), ptr(self.gflat), ptr(self.exp_avg), ptr(self.exp_avg_sq), m._flat.numel(),
+                                            ptr(self.norm2), gscale, float(self.max_norm), ptr(self._hyper_dev), float(self.betas[0]),
+                                            float(self.betas[1]), float(self.eps), float(self.weight_decay), stream_ptr()),
+                "dp_adam_clip_step_dev",
+            )
+        else:
+            check(
+                lib().dp_adam_clip_step(ptr(m._flat), ptr(self.gflat), ptr(self.exp_avg), ptr(self.exp_avg_sq), m._flat.numel(),
+                                        ptr(self.norm2), gscale, float(self.max_norm), float(self.lr), float(self.betas[0]),
+                                        float(self.betas[1]), float(self.eps), self.step_count, float(self.weight_decay), stream_ptr()),
+                "dp_adam_clip_step",
+            )
 
     def grad_norm(self) -> torch.Tensor:
         """Total gradient norm of the last step (after the all-reduce average), as clip_grad_norm_ would report it."""

@@ -189,6 +189,11 @@ int dp_bss_sdr_pit(const float* est, const float* ref, int B, int n_src, int T, 
 int dp_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, double* norm2, float grad_scale,
                       float max_norm, float lr, float beta1, float beta2, float eps, int step, float weight_decay,
                       void* stream);
+/* The same step with (lr, 1 - beta1^t, 1 - beta2^t) read from three floats of device memory by the kernel: a training step captured in a CUDA
+ * graph replays with the current learning rate and step number: dp_adam_set_hyper writes the three floats on the stream before each replay. */
+int dp_adam_set_hyper(float* hyper, float lr, float beta1, float beta2, int step, void* stream);
+int dp_adam_clip_step_dev(float* p, const float* g, float* m, float* v, int64_t n, double* norm2, float grad_scale, float max_norm,
+                          const float* hyper, float beta1, float beta2, float eps, float weight_decay, void* stream);
 
 /* ---- whole-model engine: TasNet(module="DPRNN").forward, gc3_network.py:133-184 --------------------------- */
 typedef struct dp_tasnet dp_tasnet;

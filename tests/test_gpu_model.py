@@ -360,3 +360,42 @@ def test_cuda_graph_inference_replays_equal_eager(manifest):
         gc.cuda_graph = True
         outs = [gc(xs[1]) for _ in range(3)]
     assert all(torch.equal(o, r) for o in outs) and len(gc._graphs) == 1
+
+
+@pytest.mark.parametrize("group_size", [1, 16])
+def test_trainer_cuda_graph_matches_eager_steps(group_size):
+    """DualPathTrainer(cuda_graph=True): from its third step with a batch shape the whole step is one graph replay.  Two identically
+    initialised models take the same eight steps (the learning rate changes after the fifth, another batch shape interleaves), eager and
+    replayed: same losses and parameters up to the summation order of the split-K / atomic reductions; bias corrections and learning rate
+    reach the replayed Adam kernel through device memory."""
+    from audio_only_speech_separation_b200.losses import PITLossWrapper, pairwise_neg_snr
+    from audio_only_speech_separation_b200.models import TasNet
+    from audio_only_speech_separation_b200.trainer import DualPathTrainer
+
+    def build():
+        torch.manual_seed(7)
+        kw = dict(enc_dim=64, bn_dim=64, hidden_dim=128, layer=2, group_size=16, context_size=24) if group_size > 1 else dict(layer=2)
+        return TasNet(sample_rate=8000, module="DPRNN", **kw).cuda().train()
+
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(2, 2, 8000, generator=g) * 0.1).cuda() for _ in range(8)]
+    other = (torch.randn(1, 2, 6000, generator=g) * 0.1).cuda()
+    runs = []
+    for graph in (False, True):
+        m = build()
+        tr = DualPathTrainer(m, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False), cuda_graph=graph)
+        losses = []
+        for i, src in enumerate(batches):
+            if i == 5:
+                tr.lr = 3e-4
+            if i == 4:   # a batch of another shape in between: eager step, the step counter stays in line
+                losses.append(float(tr.step(other.sum(1).contiguous(), other)))
+            losses.append(float(tr.step(src.sum(1).contiguous(), src)))
+        torch.cuda.synchronize()
+        runs.append((losses, m._flat.detach().clone(), float(tr.grad_norm()), len(tr._graphs), tr.step_count))
+    (l0, p0, n0, g0, c0), (l1, p1, n1, g1, c1) = runs
+    assert g0 == 0 and g1 == 1 and c0 == c1 == 9
+    for a, b in zip(l0, l1):
+        assert abs(a - b) < 2e-4 * max(1.0, abs(a)), (l0, l1)
+    assert rel_l2(p1, p0) < 2e-4
+    assert abs(n0 - n1) < 5e-3 * max(1.0, n0)   # two nine-step trajectories with differently ordered atomic sums
