@@ -598,7 +598,8 @@ def other_configs(args, pk, pk_kind, rec):
                      "e2e": {"value": 16 * SECONDS / gdt, "unit": "audio-s/s", "ms_per_forward": 1e3 * gdt, "h2d_bytes_per_step": gh2d,
                              "d2h_bytes_per_step": gd2h}}
         gm.train()
-        gtr = DualPathTrainer(gm, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False), lr=1e-3, max_norm=5.0)
+        gtr = DualPathTrainer(gm, PITLossWrapper(pairwise_neg_snr, pit_from="pw_mtx", threshold_byloss=False), lr=1e-3, max_norm=5.0,
+                              cuda_graph=not args.no_train_graph)
         for _ in range(3):
             gtr.step(gx, gt)
         torch.cuda.synchronize()
