@@ -499,8 +499,8 @@ class TasNet(BaseModel):
 
     def _require_training_engine(self):
         if self.group_size > 1:  # the handle is a dp_gctasnet: never hand it to the dp_tasnet_* entry points
-            raise NotImplementedError("TasNet(group_size > 1): the GroupComm engine is inference-only; the fused training step "
-                                      "(DualPathTrainer / fit) needs group_size=1 (DESIGN.md scope table)")
+            raise NotImplementedError("TasNet(group_size > 1) runs on the GroupComm engine (dp_gctasnet_*): its handle must not reach the "
+                                      "dp_tasnet_* entry points; training goes through _train_forward / _train_backward (autograd, DualPathTrainer, fit)")
 
     def _engine_forward(self, mixture, train: bool, est=None, ws=None):
         self._require_training_engine()
