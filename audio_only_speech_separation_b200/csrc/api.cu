@@ -1048,7 +1048,7 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
                 __nv_bfloat16* Hrh = at<__nv_bfloat16>(ws, l.tHrhl);
                 const __nv_bfloat16* S1hl = at<__nv_bfloat16>(ws, l.S1hl[pp]);
                 const __nv_bfloat16* Hphl = at<__nv_bfloat16>(ws, l.Hphl[pp]);
-                CK(launch_split_rows(dY, 64, dYhl, sp ? dYhl + plX : nullptr, g.PT, 64, 0, st)); ++nl;
+                CK(launch_split_rows_colsum(dY, 64, dYhl, sp ? dYhl + plX : nullptr, g.PT, 64, grads + po[9], st)); ++nl;   // planes + bias gradient
                 CK(launch_split_rows(H, 256, Hrh, sp ? Hrh + plH : nullptr, g.PT, 256, 1, st)); ++nl;   // relu(H), recomputed
                 {   // linear2 + ReLU: dH = (dY Wp) where H > 0 ; dWp = dY^T relu(H) (as relu(H)^T dY, stored transposed) ; dbp
                     TmaGemmArgs a = tma_args(dYhl, plX, 64, v.projt_hi, v.projt_lo, 64, dH, 256, PTi, 256, 64);
@@ -1060,7 +1060,6 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
                     t.B0_hi = dYhl; t.B0_lo = dYhl + plX; t.ldb0 = 64; t.nb0 = 64;
                     t.C0 = grads + po[8]; t.ldc0 = 256; t.transpose0 = 1; t.P = PTi; t.scale = 1.f;
                     CK(launch_gemm_tma_tn(t, sp, st)); ++nl;
-                    CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[9], nullptr, st)); ++nl;
                 }
                 CK(launch_lstm_bwd(v.rec, G, at<float>(ws, l.Cst[pp]), dH, dpk + 65536 + 131072, m, sp, st, dGhl, sp ? dGhl + plG : nullptr)); ++nl;
                 {   // d src (after norm1) = d z2 + dG W_ih (K = 1024)
@@ -1143,8 +1142,9 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
             const __nv_bfloat16* Xhl = at<__nv_bfloat16>(ws, l.Xhl[pp]);
             const __nv_bfloat16* Hhl = at<__nv_bfloat16>(ws, l.Hhl[pp]);
             const __nv_bfloat16* Hphl = at<__nv_bfloat16>(ws, l.Hphl[pp]);
-            CK(launch_split_rows(dY, 64, dYhl, sp ? dYhl + plX : nullptr, g.PT, 64, 0, st)); ++nl;
-            {   // out-projection Linear(256 -> 64): dH = dY Wp ; dWp = dY^T H (computed as H^T dY, stored transposed) ; dbp
+            // operand planes of dY and, in the same pass, its column sums = the bias gradient of the out-projection
+            CK(launch_split_rows_colsum(dY, 64, dYhl, sp ? dYhl + plX : nullptr, g.PT, 64, grads + po[9], st)); ++nl;
+            {   // out-projection Linear(256 -> 64): dH = dY Wp ; dWp = dY^T H (computed as H^T dY, stored transposed)
                 TmaGemmArgs a = tma_args(dYhl, plX, 64, v.projt_hi, v.projt_lo, 64, dH, 256, PTi, 256, 64);
                 CK(launch_gemm_tma_nt(a, sp, st)); ++nl;
                 TmaWgradArgs t;
@@ -1153,7 +1153,6 @@ int dp_tasnet_backward(dp_tasnet* h, const float* params, const void* pack, cons
                 t.B0_hi = dYhl; t.B0_lo = dYhl + plX; t.ldb0 = 64; t.nb0 = 64;
                 t.C0 = grads + po[8]; t.ldc0 = 256; t.transpose0 = 1; t.P = PTi; t.scale = 1.f;
                 CK(launch_gemm_tma_tn(t, sp, st)); ++nl;
-                CK(launch_colsum(dY, 64, PTi, 64, 1.f, grads + po[9], nullptr, st)); ++nl;
             }
             // BPTT: activated gates (G) + dH -> d(pre-activations) written as operand planes
             CK(launch_lstm_bwd(v.rec, G, at<float>(ws, l.Cst[pp]), dH, dpk + 65536 + 131072, m, sp, st, dGhl, sp ? dGhl + plG : nullptr)); ++nl;
