@@ -38,7 +38,8 @@ class DualPathTrainer:
         self.launches_per_step = 0
         # cuda_graph: from the third step with the same batch shape the step is replayed as two CUDA graphs (pack + forward + loss + backward:
         # ~265 launches; clip + Adam) with the NCCL all-reduce between them; learning rate and bias corrections reach the Adam kernel through
-        # device memory
+        # device memory (`lr` may change between steps; `betas`, `eps`, `weight_decay`, `max_norm` are fixed at capture: change them -> clear
+        # `self._graphs`)
         self.cuda_graph = bool(cuda_graph) and bool(getattr(model, "graph_safe_training", False))
         self._graphs, self._graph_seen = {}, {}
         self._hyper_dev = None
